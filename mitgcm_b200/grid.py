@@ -1,0 +1,246 @@
+"""Tile layout, grid metrics and masks in the reference's own memory layout.
+
+This is host-side set-up (numpy), the counterpart of what the Fortran model has
+already done before the hot path is entered: INI_CARTESIAN_GRID
+(model/src/ini_cartesian_grid.F:56-140), INI_LOCAL_GRID (ini_local_grid.F:100-165),
+INI_MASKS_ETC (ini_masks_etc.F:100-300, 400-480), INI_CORI (ini_cori.F:60-90),
+INI_LINEAR_PHISURF (ini_linear_phisurf.F:84-85).  Arrays are C-contiguous numpy
+arrays of shape (nSy, nSx, [Nr,] sNy+2*OLy, sNx+2*OLx), which is byte-for-byte
+the Fortran layout (1-OLx:sNx+OLx, 1-OLy:sNy+OLy, [Nr,] nSx, nSy) of
+model/inc/SIZE.h / GRID.h, so the same buffers can be handed to the C-ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+GRID2D = ("dxC dyC dxG dyG dxF dyF dxV dyU rA rAw rAs rAz "
+          "recip_dxC recip_dyC recip_dxG recip_dyG recip_dxF recip_dyF recip_dxV recip_dyU "
+          "recip_rA recip_rAw recip_rAs recip_rAz fCori fCoriG tanPhiAtU tanPhiAtV recip_Bo Bo_surf").split()
+GRID3D = "hFacC hFacW hFacS recip_hFacC recip_hFacW recip_hFacS maskC maskW maskS".split()
+GRID1D = "drF drC recip_drF recip_drC".split()
+GRIDJ = "cosFacU cosFacV".split()
+
+
+@dataclass(frozen=True)
+class Dims:
+    """Compile-time sizes of model/inc/SIZE.h for one process (one GPU)."""
+    sNx: int
+    sNy: int
+    OLx: int
+    OLy: int
+    nSx: int = 1
+    nSy: int = 1
+    Nr: int = 1
+    nPx: int = 1
+    nPy: int = 1
+    myPx: int = 0   # this process's position in the nPx x nPy process grid
+    myPy: int = 0
+
+    @property
+    def PX(self):
+        return self.sNx + 2 * self.OLx
+
+    @property
+    def PY(self):
+        return self.sNy + 2 * self.OLy
+
+    @property
+    def shape2(self):
+        return (self.nSy, self.nSx, self.PY, self.PX)
+
+    @property
+    def shape3(self):
+        return (self.nSy, self.nSx, self.Nr, self.PY, self.PX)
+
+    def shape3n(self, n):
+        return (self.nSy, self.nSx, n, self.PY, self.PX)
+
+    @property
+    def Nx(self):
+        return self.sNx * self.nSx * self.nPx
+
+    @property
+    def Ny(self):
+        return self.sNy * self.nSy * self.nPy
+
+    def interior(self):
+        return (slice(self.OLy, self.OLy + self.sNy), slice(self.OLx, self.OLx + self.sNx))
+
+
+def exch_xyz(d: Dims, a: np.ndarray) -> np.ndarray:
+    """EXCH_XY(Z)_RL on one periodic process (eesupp/src/exch1_rx.template:170-201):
+    X phase first, then Y phase over the full X range so corners propagate.
+    `a` has shape (nSy, nSx, ..., PY, PX); updated in place."""
+    assert d.nPx == 1 and d.nPy == 1, "host exchange helper is single-process"
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    for bj in range(d.nSy):
+        for bi in range(d.nSx):
+            bw, be = (bi - 1) % d.nSx, (bi + 1) % d.nSx
+            a[bj, bi, ..., oy:oy + sy, 0:ox] = a[bj, bw, ..., oy:oy + sy, sx:sx + ox]
+            a[bj, bi, ..., oy:oy + sy, ox + sx:] = a[bj, be, ..., oy:oy + sy, ox:2 * ox]
+    tmp = a.copy()
+    for bj in range(d.nSy):
+        bs, bn = (bj - 1) % d.nSy, (bj + 1) % d.nSy
+        a[bj, :, ..., 0:oy, :] = tmp[bs, :, ..., sy:sy + oy, :]
+        a[bj, :, ..., oy + sy:, :] = tmp[bn, :, ..., oy:2 * oy, :]
+    return a
+
+
+@dataclass
+class Grid:
+    d: Dims
+    a: dict = field(default_factory=dict)
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["a"][name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    def set_recips(self):
+        for n in "dxC dyC dxG dyG dxF dyF dxV dyU rA rAw rAs rAz".split():
+            v = self.a[n]
+            r = np.zeros_like(v)
+            np.divide(1.0, v, out=r, where=v != 0.0)   # ini_grid.F zero-guarded reciprocals
+            self.a["recip_" + n] = r
+
+
+def cartesian_grid(d: Dims, delX, delY, delR, xgOrigin=0.0, ygOrigin=0.0,
+                   f0=1e-4, beta=1e-11, gBaro=9.81) -> Grid:
+    """usingCartesianGrid: INI_CARTESIAN_GRID + INI_CORI(selectCoriMap=1) +
+    INI_LINEAR_PHISURF.  delX/delY are the global spacings (length Nx/Ny)."""
+    delX = np.asarray(delX, dtype=np.float64)
+    delY = np.asarray(delY, dtype=np.float64)
+    delR = np.asarray(delR, dtype=np.float64)
+    assert len(delX) == d.Nx and len(delY) == d.Ny and len(delR) == d.Nr
+    g = Grid(d)
+    z2 = lambda: np.zeros(d.shape2)
+    for n in GRID2D:
+        g.a[n] = z2()
+    xC, yC, xG, yG = z2(), z2(), z2(), z2()
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    for bj in range(d.nSy):
+        for bi in range(d.nSx):
+            iG0 = (d.myPx * d.nSx + bi) * sx
+            jG0 = (d.myPy * d.nSy + bj) * sy
+            # sequential sums, same order as ini_local_grid.F:127-145
+            xG0 = np.float64(xgOrigin)
+            for i in range(iG0):
+                xG0 = xG0 + delX[i]
+            for i in range(1, ox + 1):
+                xG0 = xG0 - delX[(iG0 - i + ox * d.Nx) % d.Nx]
+            yG0 = np.float64(ygOrigin)
+            for j in range(jG0):
+                yG0 = yG0 + delY[j]
+            for j in range(1, oy + 1):
+                yG0 = yG0 - delY[(jG0 - j + oy * d.Ny) % d.Ny]
+            dXl = delX[[(iG0 + i - 1 + ox * d.Nx) % d.Nx for i in range(1 - ox, sx + ox + 1)]]
+            dYl = delY[[(jG0 + j - 1 + oy * d.Ny) % d.Ny for j in range(1 - oy, sy + oy + 1)]]
+            xGl = np.empty(d.PX + 1)
+            xGl[0] = xG0
+            for i in range(d.PX):
+                xGl[i + 1] = xGl[i] + dXl[i]
+            yGl = np.empty(d.PY + 1)
+            yGl[0] = yG0
+            for j in range(d.PY):
+                yGl[j + 1] = yGl[j] + dYl[j]
+            XG = np.broadcast_to(xGl[None, :], (d.PY + 1, d.PX + 1))
+            YG = np.broadcast_to(yGl[:, None], (d.PY + 1, d.PX + 1))
+            xG[bj, bi] = XG[:-1, :-1]
+            yG[bj, bi] = YG[:-1, :-1]
+            xC[bj, bi] = 0.25 * (((XG[:-1, :-1] + XG[:-1, 1:]) + XG[1:, :-1]) + XG[1:, 1:])
+            yC[bj, bi] = 0.25 * (((YG[:-1, :-1] + YG[:-1, 1:]) + YG[1:, :-1]) + YG[1:, 1:])
+            dxF = np.broadcast_to(dXl[None, :], (d.PY, d.PX)).copy()
+            dyF = np.broadcast_to(dYl[:, None], (d.PY, d.PX)).copy()
+            g.a["dxF"][bj, bi] = dxF
+            g.a["dyF"][bj, bi] = dyF
+            g.a["dxG"][bj, bi] = dxF
+            g.a["dyG"][bj, bi] = dyF
+            g.a["dxC"][bj, bi][:, 1:] = 0.5 * (dxF[:, 1:] + dxF[:, :-1])
+            g.a["dyC"][bj, bi][1:, :] = 0.5 * (dyF[1:, :] + dyF[:-1, :])
+            g.a["dxV"][bj, bi][1:, 1:] = 0.5 * (dxF[1:, 1:] + dxF[1:, :-1])
+            g.a["dyU"][bj, bi][1:, 1:] = 0.5 * (dyF[1:, 1:] + dyF[:-1, 1:])
+            g.a["rA"][bj, bi] = dxF * dyF
+            g.a["rAw"][bj, bi] = g.a["dxC"][bj, bi] * dyF
+            g.a["rAs"][bj, bi] = dxF * g.a["dyC"][bj, bi]
+            g.a["rAz"][bj, bi] = g.a["dxV"][bj, bi] * g.a["dyU"][bj, bi]
+    g.a["xC"], g.a["yC"], g.a["xG"], g.a["yG"] = xC, yC, xG, yG
+    g.a["fCori"] = f0 + beta * yC * 1.0
+    g.a["fCoriG"] = f0 + beta * yG * 1.0
+    g.a["Bo_surf"] = np.full(d.shape2, gBaro)
+    g.a["recip_Bo"] = np.full(d.shape2, 1.0 / gBaro)
+    g.a["cosFacU"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.a["cosFacV"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.set_recips()
+    set_vertical(g, delR)
+    return g
+
+
+def set_vertical(g: Grid, delR) -> None:
+    """INI_VERTICAL_GRID for z coordinates: drF = delR, drC(1) = delR(1)/2,
+    drC(k) = (delR(k-1)+delR(k))/2, drC(Nr+1) = delR(Nr)/2."""
+    delR = np.asarray(delR, dtype=np.float64)
+    Nr = len(delR)
+    drF = delR.copy()
+    drC = np.empty(Nr + 1)
+    drC[0] = 0.5 * delR[0]
+    for k in range(1, Nr):
+        drC[k] = 0.5 * (delR[k - 1] + delR[k])
+    drC[Nr] = 0.5 * delR[Nr - 1]
+    g.a["drF"], g.a["drC"] = drF, drC
+    g.a["recip_drF"], g.a["recip_drC"] = 1.0 / drF, 1.0 / drC
+    rF = np.empty(Nr + 1)
+    rF[0] = 0.0
+    for k in range(Nr):
+        rF[k + 1] = rF[k] - delR[k]
+    g.a["rF"] = rF
+
+
+def masks_from_depth(g: Grid, depth_global: np.ndarray, hFacMin=1.0, hFacMinDr=0.0) -> None:
+    """INI_DEPTHS + INI_MASKS_ETC for z coordinates with Ro_surf = 0 and a linear
+    free surface: hFacC from R_low with the hFacMin / hFacMinDr rule
+    (ini_masks_etc.F:100-125), hFacW/S = min of the two neighbours (:238-262),
+    EXCH_UV_XYZ_RS (:402), reciprocals and masks (:461-478).
+    depth_global is (Ny, Nx), negative below the surface, 0 on land."""
+    d = g.d
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    assert depth_global.shape == (d.Ny, d.Nx)
+    R_low = np.zeros(d.shape2)
+    for bj in range(d.nSy):
+        for bi in range(d.nSx):
+            iG0 = (d.myPx * d.nSx + bi) * sx
+            jG0 = (d.myPy * d.nSy + bj) * sy
+            jj = [(jG0 + j - oy) % d.Ny for j in range(d.PY)]
+            ii = [(iG0 + i - ox) % d.Nx for i in range(d.PX)]
+            R_low[bj, bi] = depth_global[np.ix_(jj, ii)]     # periodic read + exchange
+    drF, rdrF, rF = g.a["drF"], g.a["recip_drF"], g.a["rF"]
+    hFacC = np.zeros(d.shape3)
+    for k in range(d.Nr):
+        mn = max(hFacMin, min(hFacMinDr * rdrF[k], 1.0))
+        h = (rF[k] - R_low) * rdrF[k]
+        h = np.minimum(np.maximum(h, 0.0), 1.0)
+        hFacC[:, :, k] = np.where((h < mn * 0.5) | (R_low >= 0.0), 0.0, np.maximum(h, mn))
+    hFacW = np.zeros(d.shape3)
+    hFacS = np.zeros(d.shape3)
+    hFacW[..., :, 1:] = np.minimum(hFacC[..., :, 1:], hFacC[..., :, :-1])
+    hFacS[..., 1:, :] = np.minimum(hFacC[..., 1:, :], hFacC[..., :-1, :])
+    if d.nPx == 1 and d.nPy == 1:
+        exch_xyz(d, hFacW)
+        exch_xyz(d, hFacS)
+    set_hfac(g, hFacC, hFacW, hFacS)
+
+
+def set_hfac(g: Grid, hFacC, hFacW, hFacS) -> None:
+    for n, h in (("C", hFacC), ("W", hFacW), ("S", hFacS)):
+        r = np.zeros_like(h)
+        np.divide(1.0, h, out=r, where=h != 0.0)
+        g.a["hFac" + n] = np.ascontiguousarray(h)
+        g.a["recip_hFac" + n] = r
+        g.a["mask" + n] = (h != 0.0).astype(np.float64)
+
+
+def global_area(g: Grid) -> float:
+    d = g.d
+    jj, ii = d.interior()
+    return float((g.a["rA"][:, :, jj, ii] * g.a["maskC"][:, :, 0, jj, ii]).sum())

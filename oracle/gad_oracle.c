@@ -1,0 +1,373 @@
+/* gad_oracle.c -- CPU restatement of GAD_CALC_RHS, its leaf stencils and
+ * CALC_ADV_FLOW.  TEST INFRASTRUCTURE ONLY (see mitgcm_oracle.h).
+ * Follows pkg/generic_advdiff/gad_calc_rhs.F:193-781 and the leaves
+ * gad_{c2,dst2u1,u3,c4,dst3,dst3fl,fluxlimit}_adv_{x,y,r}.F, gad_diff_{x,y,r}.F,
+ * gad_grad_{x,y}.F, gad_del2.F, gad_biharm_{x,y,r}.F (loop ranges as in the
+ * reference).  Not restated: GM/Redi, KPP, OBCS, Smolarkiewicz hack, OS7MP,
+ * SMAG_3D diffusivity, cubed-sphere corner fill; maskInC == 1; deepFac/rhoFac == 1.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "mitgcm_oracle.h"
+
+#define S(i, j) ((size_t)((i) + OLx - 1) + (size_t)px * (size_t)((j) + OLy - 1))
+#define G2(a, i, j) (a)[S(i, j) + off2]
+#define G3(a, i, j, k) (a)[S(i, j) + (size_t)px * py * (size_t)((k)-1) + off3]
+#define K3(a, i, j, k) (a)[S(i, j) + (size_t)px * py * (size_t)((k)-1)]
+#define FORALL for (int j = 1 - OLy; j <= sNy + OLy; j++) for (int i = 1 - OLx; i <= sNx + OLx; i++)
+#define SETUP                                                                          \
+  const og_dims *d = &g->d;                                                            \
+  const int sNx = d->sNx, sNy = d->sNy, OLx = d->OLx, OLy = d->OLy, Nr = d->Nr;        \
+  const size_t px = (size_t)(sNx + 2 * OLx), py = (size_t)(sNy + 2 * OLy);             \
+  const size_t tile = (size_t)(bi - 1) + (size_t)d->nSx * (size_t)(bj - 1);            \
+  const size_t off2 = px * py * tile, off3 = px * py * (size_t)Nr * tile;              \
+  const size_t offc = py * tile;                                                       \
+  (void)Nr; (void)off2; (void)off3; (void)offc;
+
+enum { UPWIND_1RST = 1, CENTERED_2ND = 2, UPWIND_3RD = 3, CENTERED_4TH = 4, DST2 = 20,
+       FLUX_LIMIT = 77, DST3 = 30, DST3_FLUX_LIMIT = 33 };
+
+static const double oneSixth = 1.0 / 6.0;
+
+/* GAD_FLUX_LIMITER.h: Superbee */
+static double Limiter(double Cr) { return fmax(0., fmax(fmin(1., 2. * Cr), fmin(2., Cr))); }
+
+void og_calc_adv_flow(const og_grid *g, int bi, int bj, int k,
+                      const double *uVel, const double *vVel, const double *wVel,
+                      double *xA, double *yA, double *maskUp,
+                      double *uFld, double *vFld, double *wFld,
+                      double *uTrans, double *vTrans, double *rTrans, double *rTransKp1) {
+  SETUP
+  /* uVel.. are the global tile3d arrays; uFld.. receive the level-k slabs the
+   * callers pass on (temp_integrate.F:357-370). rTrans is in/out: on entry the
+   * value left by level k+1 (calc_adv_flow.F, non-AUTODIFF branch). */
+  FORALL {
+    xA[S(i, j)] = G2(g->dyG, i, j) * g->drF[k - 1] * G3(g->hFacW, i, j, k);
+    yA[S(i, j)] = G2(g->dxG, i, j) * g->drF[k - 1] * G3(g->hFacS, i, j, k);
+  }
+  if (k == Nr) { FORALL rTransKp1[S(i, j)] = 0.; }
+  else { FORALL rTransKp1[S(i, j)] = rTrans[S(i, j)]; }
+  FORALL {
+    uFld[S(i, j)] = G3(uVel, i, j, k);
+    vFld[S(i, j)] = G3(vVel, i, j, k);
+    wFld[S(i, j)] = G3(wVel, i, j, k);
+    uTrans[S(i, j)] = G3(uVel, i, j, k) * xA[S(i, j)];
+    vTrans[S(i, j)] = G3(vVel, i, j, k) * yA[S(i, j)];
+  }
+  if (k == 1) {
+    FORALL { maskUp[S(i, j)] = 0.; rTrans[S(i, j)] = 0.; }
+  } else {
+    FORALL {
+      maskUp[S(i, j)] = G3(g->maskC, i, j, k - 1) * G3(g->maskC, i, j, k);
+      rTrans[S(i, j)] = G3(wVel, i, j, k) * G2(g->rA, i, j) * maskUp[S(i, j)];
+    }
+  }
+}
+
+/* horizontal advective flux, direction dir = 0 (x) / 1 (y).
+ * gad_*_adv_x.F / gad_*_adv_y.F */
+static void adv_h(const og_grid *g, int bi, int bj, int k, int dir, int scheme, double deltaTloc,
+                  const double *trans, const double *vel, const double *maskLoc,
+                  const double *tr, double *af) {
+  SETUP
+  const int di = dir == 0, dj = dir == 1;
+  const double *recip_dC = dir == 0 ? g->recip_dxC : g->recip_dyC;
+  /* leading rows/columns the reference zeroes explicitly */
+  if (scheme == CENTERED_2ND || scheme == UPWIND_1RST || scheme == DST2) {
+    if (dir == 0) for (int j = 1 - OLy; j <= sNy + OLy; j++) af[S(1 - OLx, j)] = 0.;
+    else for (int i = 1 - OLx; i <= sNx + OLx; i++) af[S(i, 1 - OLy)] = 0.;
+  } else {
+    if (dir == 0) for (int j = 1 - OLy; j <= sNy + OLy; j++) {
+      af[S(1 - OLx, j)] = 0.; af[S(2 - OLx, j)] = 0.; af[S(sNx + OLx, j)] = 0.;
+    } else for (int i = 1 - OLx; i <= sNx + OLx; i++) {
+      af[S(i, 1 - OLy)] = 0.; af[S(i, 2 - OLy)] = 0.; af[S(i, sNy + OLy)] = 0.;
+    }
+  }
+  const int wide = !(scheme == CENTERED_2ND || scheme == UPWIND_1RST || scheme == DST2);
+  const int iLo = 1 - OLx + (di ? (wide ? 2 : 1) : 0), iHi = sNx + OLx - (di && wide ? 1 : 0);
+  const int jLo = 1 - OLy + (dj ? (wide ? 2 : 1) : 0), jHi = sNy + OLy - (dj && wide ? 1 : 0);
+  for (int j = jLo; j <= jHi; j++)
+    for (int i = iLo; i <= iHi; i++) {
+      const double T0 = tr[S(i, j)], Tm1 = tr[S(i - di, j - dj)];
+      const double uT = trans[S(i, j)];
+      if (scheme == CENTERED_2ND) {
+        af[S(i, j)] = uT * (T0 + Tm1) * 0.5;
+        continue;
+      }
+      if (scheme == UPWIND_1RST || scheme == DST2) {
+        const double xLimit = scheme == DST2 ? 1. : 0.;
+        double uCFL = fabs(vel[S(i, j)] * deltaTloc * G2(recip_dC, i, j));
+        double uAbs = fabs(uT) * (1. - xLimit * (1. - uCFL));
+        af[S(i, j)] = (uT + uAbs) * 0.5 * Tm1 + (uT - uAbs) * 0.5 * T0;
+        continue;
+      }
+      const double Tp1 = tr[S(i + di, j + dj)], Tm2 = tr[S(i - 2 * di, j - 2 * dj)];
+      const double Rjp = (Tp1 - T0) * maskLoc[S(i + di, j + dj)];
+      const double Rj = (T0 - Tm1) * maskLoc[S(i, j)];
+      const double Rjm = (Tm1 - Tm2) * maskLoc[S(i - di, j - dj)];
+      if (scheme == UPWIND_3RD || scheme == CENTERED_4TH) {
+        const double Rjjp = Rjp - Rj, Rjjm = Rj - Rjm;
+        double v = uT * (T0 + Tm1 - oneSixth * (Rjjp + Rjjm)) * 0.5;
+        if (scheme == UPWIND_3RD)
+          v = v + fabs(uT) * 0.5 * oneSixth * (Rjjp - Rjjm);
+        else {
+          const double *mk = dir == 0 ? g->maskW : g->maskS;
+          v = v + fabs(uT) * 0.5 * oneSixth * (Rjjp - Rjjm)
+                  * (1. - G3(mk, i - di, j - dj, k) * G3(mk, i + di, j + dj, k));
+        }
+        af[S(i, j)] = v;
+        continue;
+      }
+      const double uCFL = fabs(vel[S(i, j)] * deltaTloc * G2(recip_dC, i, j));
+      if (scheme == FLUX_LIMIT) {
+        const double CrMax = 1.e6;
+        double Cr = (uT > 0.) ? Rjm : Rjp;
+        if (fabs(Rj) * CrMax <= fabs(Cr)) Cr = copysign(CrMax, Cr) * copysign(1., Rj);
+        else Cr = Cr / Rj;
+        Cr = Limiter(Cr);
+        af[S(i, j)] = uT * (T0 + Tm1) * 0.5 - fabs(uT) * ((1. - Cr) + uCFL * Cr) * Rj * 0.5;
+        continue;
+      }
+      const double d0 = (2. - uCFL) * (1. - uCFL) * oneSixth;
+      const double d1 = (1. - uCFL * uCFL) * oneSixth;
+      if (scheme == DST3) {
+        af[S(i, j)] = 0.5 * (uT + fabs(uT)) * (Tm1 + (d0 * Rj + d1 * Rjm))
+                    + 0.5 * (uT - fabs(uT)) * (T0 - (d0 * Rj + d1 * Rjp));
+      } else { /* DST3_FLUX_LIMIT */
+        const double thetaMax = 1.e20;
+        double thetaP, thetaM;
+        if (fabs(Rj) * thetaMax <= fabs(Rjm)) thetaP = copysign(thetaMax, Rjm * Rj);
+        else thetaP = Rjm / Rj;
+        if (fabs(Rj) * thetaMax <= fabs(Rjp)) thetaM = copysign(thetaMax, Rjp * Rj);
+        else thetaM = Rjp / Rj;
+        double psiP = d0 + d1 * thetaP;
+        psiP = fmax(0., fmin(fmin(1., psiP), thetaP * (1. - uCFL) / (uCFL + 1.e-20)));
+        double psiM = d0 + d1 * thetaM;
+        psiM = fmax(0., fmin(fmin(1., psiM), thetaM * (1. - uCFL) / (uCFL + 1.e-20)));
+        af[S(i, j)] = 0.5 * (uT + fabs(uT)) * (Tm1 + psiP * Rj)
+                    + 0.5 * (uT - fabs(uT)) * (T0 - psiM * Rj);
+      }
+    }
+}
+
+/* vertical advective flux at interface k, gad_*_adv_r.F */
+static void adv_r(const og_grid *g, const og_params *p, int bi, int bj, int k, int scheme,
+                  double dTarg, const double *rTrans, const double *wFld, const double *tr,
+                  double *wT) {
+  SETUP
+  const int km2 = k - 2 > 1 ? k - 2 : 1, km1 = k - 1 > 1 ? k - 1 : 1, kp1 = k + 1 < Nr ? k + 1 : Nr;
+  const int zeroTop = (k == 1 || k > Nr);
+  if ((scheme == CENTERED_2ND || scheme == UPWIND_1RST || scheme == DST2 || scheme == UPWIND_3RD ||
+       scheme == CENTERED_4TH) && zeroTop) {
+    FORALL wT[S(i, j)] = 0.;
+    return;
+  }
+  if (scheme == FLUX_LIMIT && k > Nr) { FORALL wT[S(i, j)] = 0.; return; }
+  FORALL {
+    const double Tk = K3(tr, i, j, k), Tkm1 = K3(tr, i, j, km1), Tkm2 = K3(tr, i, j, km2), Tkp1 = K3(tr, i, j, kp1);
+    const double rT = rTrans[S(i, j)];
+    const double mkm1 = G3(g->maskC, i, j, km1);
+    if (scheme == CENTERED_2ND) {
+      wT[S(i, j)] = mkm1 * rT * (Tk + Tkm1) * 0.5;
+    } else if (scheme == UPWIND_1RST || scheme == DST2) {
+      const double rLimit = scheme == DST2 ? 1. : 0.;
+      double wCFL = fabs(wFld[S(i, j)] * dTarg * g->recip_drC[k - 1]);
+      double wAbs = fabs(rT) * p->rkSign * (1. - rLimit * (1. - wCFL));
+      wT[S(i, j)] = mkm1 * ((rT + wAbs) * 0.5 * Tkm1 + (rT - wAbs) * 0.5 * Tk);
+    } else if (scheme == UPWIND_3RD || scheme == CENTERED_4TH) {
+      const double Rjp = (Tkp1 - Tk) * G3(g->maskC, i, j, kp1);
+      const double Rj = (Tk - Tkm1);
+      const double Rjm = (Tkm1 - Tkm2) * (scheme == UPWIND_3RD ? G3(g->maskC, i, j, km2) : mkm1);
+      const double Rjjp = Rjp - Rj, Rjjm = Rj - Rjm;
+      if (scheme == UPWIND_3RD)
+        wT[S(i, j)] = mkm1 * (rT * ((Tk + Tkm1) * 0.5 - oneSixth * (Rjjm + Rjjp) * 0.5)
+                              + fabs(rT) * oneSixth * (Rjjm - Rjjp) * 0.5);
+      else {
+        double maskPM = 1.;
+        if (k <= 2 || k >= Nr) maskPM = 0.;
+        double maskBound = maskPM * G3(g->maskC, i, j, km2) * G3(g->maskC, i, j, kp1);
+        wT[S(i, j)] = mkm1 * (rT * ((Tk + Tkm1) * 0.5 - oneSixth * (Rjjm + Rjjp) * 0.5)
+                              + fabs(rT) * oneSixth * (Rjjm - Rjjp) * 0.5 * (1. - maskBound));
+      }
+    } else if (scheme == FLUX_LIMIT) {
+      const double CrMax = 1.e6;
+      double wCFL = fabs(wFld[S(i, j)] * dTarg * g->recip_drC[k - 1]);
+      const double Rjp = (Tkp1 - Tk) * G3(g->maskC, i, j, kp1);
+      const double Rj = (Tk - Tkm1);
+      const double Rjm = (Tkm1 - Tkm2) * G3(g->maskC, i, j, km2);
+      double Cr = (rT < 0.) ? Rjm : Rjp;
+      if (fabs(Rj) * CrMax <= fabs(Cr)) Cr = copysign(CrMax, Cr) * copysign(1., Rj);
+      else Cr = Cr / Rj;
+      Cr = Limiter(Cr);
+      wT[S(i, j)] = mkm1 * (rT * (Tk + Tkm1) * 0.5 + fabs(rT) * ((1. - Cr) + wCFL * Cr) * Rj * 0.5);
+    } else { /* DST3 / DST3_FLUX_LIMIT */
+      const double Rjp = (Tk - Tkp1) * G3(g->maskC, i, j, kp1);
+      const double Rj = (Tkm1 - Tk) * G3(g->maskC, i, j, k) * mkm1;
+      const double Rjm = (Tkm2 - Tkm1) * mkm1;
+      double cfl = fabs(wFld[S(i, j)] * dTarg * g->recip_drC[k - 1]);
+      const double d0 = (2. - cfl) * (1. - cfl) * oneSixth;
+      const double d1 = (1. - cfl * cfl) * oneSixth;
+      if (scheme == DST3) {
+        wT[S(i, j)] = 0.5 * (rT + fabs(rT)) * (Tk + (d0 * Rj + d1 * Rjp))
+                    + 0.5 * (rT - fabs(rT)) * (Tkm1 - (d0 * Rj + d1 * Rjm));
+      } else {
+        const double thetaMax = 1.e20;
+        double thetaP, thetaM;
+        if (fabs(Rj) * thetaMax <= fabs(Rjm)) thetaP = copysign(thetaMax, Rjm * Rj);
+        else thetaP = Rjm / Rj;
+        if (fabs(Rj) * thetaMax <= fabs(Rjp)) thetaM = copysign(thetaMax, Rjp * Rj);
+        else thetaM = Rjp / Rj;
+        double psiP = d0 + d1 * thetaP;
+        psiP = fmax(0., fmin(fmin(1., psiP), thetaP * (1. - cfl) / (cfl + 1.e-20)));
+        double psiM = d0 + d1 * thetaM;
+        psiM = fmax(0., fmin(fmin(1., psiM), thetaM * (1. - cfl) / (cfl + 1.e-20)));
+        wT[S(i, j)] = 0.5 * (rT + fabs(rT)) * (Tk + psiM * Rj)
+                    + 0.5 * (rT - fabs(rT)) * (Tkm1 - psiP * Rj);
+      }
+    }
+  }
+}
+
+void og_gad_calc_rhs(const og_grid *g, const og_params *p, int bi, int bj,
+                     int iMin, int iMax, int jMin, int jMax, int k, int kM1, int kUp, int kDown,
+                     const double *xA, const double *yA, const double *maskUp,
+                     const double *uFld, const double *vFld, const double *wFld,
+                     const double *uTrans, const double *vTrans, const double *rTrans,
+                     const double *rTransKp1, double diffKh, double diffK4,
+                     const double *KappaR, const double *diffKr4,
+                     const double *TracerN, const double *TracAB, const double *deltaTLev,
+                     int advectionScheme, int vertAdvecScheme,
+                     int calcAdvection, int implicitAdvection, int applyAB_onTracer,
+                     int trUseDiffKr4,
+                     double *fZon, double *fMer, double *fVerT, double *gTracer) {
+  SETUP
+  (void)iMin; (void)iMax; (void)jMin; (void)jMax; (void)kM1;
+  const size_t ns = px * py;
+  double *buf = (double *)calloc(ns * 7, sizeof(double));
+  double *df4 = buf, *af = buf + ns, *df = buf + 2 * ns, *localT = buf + 3 * ns, *locABT = buf + 4 * ns,
+         *maskLocW = buf + 5 * ns, *maskLocS = buf + 6 * ns;
+  double *fVerUp = fVerT + ns * (size_t)(kUp - 1);
+  const double *fVerDn = fVerT + ns * (size_t)(kDown - 1);
+
+  double advFac = 0.;
+  if (calcAdvection) advFac = 1.;
+  double rAdvFac = p->rkSign * advFac;
+  if (implicitAdvection) rAdvFac = p->rkSign;
+
+  FORALL { fZon[S(i, j)] = 0.; fMer[S(i, j)] = 0.; fVerUp[S(i, j)] = 0.; }
+  FORALL {
+    localT[S(i, j)] = K3(TracerN, i, j, k);
+    locABT[S(i, j)] = applyAB_onTracer ? K3(TracAB, i, j, k) : K3(TracerN, i, j, k);
+  }
+  /* del^2 T for the bi-harmonic term: GAD_GRAD_X/Y + GAD_DEL2, :226-242 */
+  if (diffK4 != 0.) {
+    for (int j = 1 - OLy; j <= sNy + OLy; j++) {
+      fZon[S(1 - OLx, j)] = 0.;
+      for (int i = 2 - OLx; i <= sNx + OLx; i++)
+        fZon[S(i, j)] = xA[S(i, j)] * G2(g->recip_dxC, i, j) * (localT[S(i, j)] - localT[S(i - 1, j)]);
+    }
+    for (int i = 1 - OLx; i <= sNx + OLx; i++) fMer[S(i, 1 - OLy)] = 0.;
+    for (int j = 2 - OLy; j <= sNy + OLy; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx; i++)
+        fMer[S(i, j)] = yA[S(i, j)] * G2(g->recip_dyC, i, j) * (localT[S(i, j)] - localT[S(i, j - 1)]);
+    for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx - 1; i++)
+        df4[S(i, j)] = G2(g->recip_rA, i, j) * g->recip_drF[k - 1] * G3(g->recip_hFacC, i, j, k)
+                       * ((fZon[S(i + 1, j)] - fZon[S(i, j)]) + (fMer[S(i, j + 1)] - fMer[S(i, j)]));
+  }
+  /* ---- X ---- :245-355 */
+  FORALL fZon[S(i, j)] = 0.;
+  if (calcAdvection) {
+    FORALL maskLocW[S(i, j)] = G3(g->maskW, i, j, k);
+    adv_h(g, bi, bj, k, 0, advectionScheme, deltaTLev[k - 1], uTrans, uFld, maskLocW, locABT, af);
+    FORALL fZon[S(i, j)] = fZon[S(i, j)] + af[S(i, j)];
+  }
+  if (diffKh != 0.) {
+    for (int j = 1 - OLy; j <= sNy + OLy; j++) {
+      df[S(1 - OLx, j)] = 0.;
+      for (int i = 2 - OLx; i <= sNx + OLx; i++)
+        df[S(i, j)] = -diffKh * xA[S(i, j)] * G2(g->recip_dxC, i, j)
+                      * (localT[S(i, j)] - localT[S(i - 1, j)]) * g->cosFacU[(j + OLy - 1) + offc];
+    }
+  } else {
+    FORALL df[S(i, j)] = 0.;
+  }
+  if (diffK4 != 0.)
+    for (int j = 1 - OLy; j <= sNy + OLy; j++)
+      for (int i = 2 - OLx; i <= sNx + OLx; i++)
+        df[S(i, j)] = df[S(i, j)] + diffK4 * xA[S(i, j)] * G2(g->recip_dxC, i, j)
+                      * (df4[S(i, j)] - df4[S(i - 1, j)]) * g->cosFacU[(j + OLy - 1) + offc];
+  FORALL fZon[S(i, j)] = fZon[S(i, j)] + df[S(i, j)];
+  /* ---- Y ---- :374-484 */
+  FORALL fMer[S(i, j)] = 0.;
+  if (calcAdvection) {
+    FORALL maskLocS[S(i, j)] = G3(g->maskS, i, j, k);
+    adv_h(g, bi, bj, k, 1, advectionScheme, deltaTLev[k - 1], vTrans, vFld, maskLocS, locABT, af);
+    FORALL fMer[S(i, j)] = fMer[S(i, j)] + af[S(i, j)];
+  }
+  if (diffKh != 0.) {
+    for (int i = 1 - OLx; i <= sNx + OLx; i++) df[S(i, 1 - OLy)] = 0.;
+    for (int j = 2 - OLy; j <= sNy + OLy; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx; i++)
+        df[S(i, j)] = -diffKh * yA[S(i, j)] * G2(g->recip_dyC, i, j) * (localT[S(i, j)] - localT[S(i, j - 1)]);
+  } else {
+    FORALL df[S(i, j)] = 0.;
+  }
+  if (diffK4 != 0.)
+    for (int j = 2 - OLy; j <= sNy + OLy; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx; i++)
+        df[S(i, j)] = df[S(i, j)] + diffK4 * yA[S(i, j)] * G2(g->recip_dyC, i, j) * (df4[S(i, j)] - df4[S(i, j - 1)]);
+  FORALL fMer[S(i, j)] = fMer[S(i, j)] + df[S(i, j)];
+  /* ---- R ---- :502-632 */
+  if (calcAdvection && !implicitAdvection && k >= 2) {
+    adv_r(g, p, bi, bj, k, vertAdvecScheme, deltaTLev[k - 1], rTrans, wFld,
+          applyAB_onTracer ? TracAB : TracerN, af);
+    FORALL fVerUp[S(i, j)] = fVerUp[S(i, j)] + af[S(i, j)];
+  }
+  if (p->implicitDiffusion) {
+    FORALL df[S(i, j)] = 0.;
+  } else {
+    /* GAD_DIFF_R */
+    const int km1 = k - 1 > 1 ? k - 1 : 1;
+    if (k == 1 || k > Nr) { FORALL df[S(i, j)] = 0.; }
+    else FORALL df[S(i, j)] = -KappaR[S(i, j)] * maskUp[S(i, j)] * G2(g->rA, i, j) * g->recip_drC[k - 1]
+                              * (K3(TracerN, i, j, k) - K3(TracerN, i, j, km1)) * p->rkSign;
+  }
+  if (trUseDiffKr4 && k >= 2) {
+    /* GAD_BIHARM_R (tmpFac of the del2T loop is computed but unused in the reference) */
+    double *gradR = (double *)calloc(ns * 3, sizeof(double));
+    double *del2T = (double *)calloc(ns * 2, sizeof(double));
+    for (int n = 1; n <= 3; n++) {
+      int km = k + n - 3, kl = k + n - 2;
+      if (km < 1 || kl > Nr) { FORALL gradR[S(i, j) + ns * (n - 1)] = 0.; }
+      else {
+        double tmpFac = g->recip_drC[kl - 1];
+        FORALL gradR[S(i, j) + ns * (n - 1)] = (K3(TracerN, i, j, kl) - K3(TracerN, i, j, km))
+            * tmpFac * G3(g->maskC, i, j, kl) * G3(g->maskC, i, j, km);
+      }
+    }
+    for (int n = 1; n <= 2; n++) {
+      int kl = k + n - 2;
+      FORALL del2T[S(i, j) + ns * (n - 1)] = (gradR[S(i, j) + ns * n] - gradR[S(i, j) + ns * (n - 1)])
+          * G3(g->recip_hFacC, i, j, kl);
+    }
+    double tmpFac = p->rkSign * g->recip_drC[k - 1];
+    FORALL df[S(i, j)] = df[S(i, j)] + diffKr4[k - 1] * (del2T[S(i, j) + ns] - del2T[S(i, j)])
+                         * tmpFac * G2(g->rA, i, j) * maskUp[S(i, j)];
+    free(gradR); free(del2T);
+  }
+  FORALL fVerUp[S(i, j)] = fVerUp[S(i, j)] + df[S(i, j)];
+  /* ---- divergence ---- :767-781 */
+  for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 1 - OLx; i <= sNx + OLx - 1; i++)
+      K3(gTracer, i, j, k) = K3(gTracer, i, j, k)
+          - G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j)
+            * ((fZon[S(i + 1, j)] - fZon[S(i, j)])
+             + (fMer[S(i, j + 1)] - fMer[S(i, j)])
+             + (fVerDn[S(i, j)] - fVerUp[S(i, j)]) * p->rkSign
+             - localT[S(i, j)] * ((uTrans[S(i + 1, j)] - uTrans[S(i, j)]) * advFac
+                                + (vTrans[S(i, j + 1)] - vTrans[S(i, j)]) * advFac
+                                + (rTransKp1[S(i, j)] - rTrans[S(i, j)]) * rAdvFac));
+  free(buf);
+}

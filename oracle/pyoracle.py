@@ -1,0 +1,182 @@
+"""ctypes binding of the CPU oracle (oracle/_ref/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs, never by mitgcm_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "liboracle.so")
+P = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in "sNx sNy OLx OLy nSx nSy Nr".split()]
+
+
+GRID_FIELDS = ("dxC dyC dxG dyG dxF dyF dxV dyU rA rAw rAs rAz "
+               "recip_dxC recip_dyC recip_dxG recip_dyG recip_dxF recip_dyF recip_dxV recip_dyU "
+               "recip_rA recip_rAw recip_rAs recip_rAz fCori fCoriG tanPhiAtU tanPhiAtV "
+               "cosFacU cosFacV drF drC recip_drF recip_drC "
+               "hFacC hFacW hFacS recip_hFacC recip_hFacW recip_hFacS maskC maskW maskS recip_Bo").split()
+
+
+class GridS(C.Structure):
+    _fields_ = [("d", Dims)] + [(n, P) for n in GRID_FIELDS]
+
+
+PARAM_D = ("deltaTMom deltaTFreeSurf freeSurfFac implicSurfPress implicDiv2DFlow rkSign "
+           "cg2dpcOffDFac cg2dTargetResidual cg2dTargetResWunit globalArea "
+           "viscAhD viscAhZ viscA4D viscA4Z sideDragFactor bottomDragLinear bottomDragQuadratic "
+           "recip_rSphere afFacMom vfFacMom cfFacMom mtFacMom").split()
+PARAM_I = ("momAdvection momViscosity useBiharmonicVisc implicitViscosity no_slip_sides no_slip_bottom "
+           "bottomVisc_pCell selectBotDragQuadr selectImplicitDrag useCDscheme selectCoriScheme "
+           "selectMetricTerms usingSphericalPolarGrid rigidLid select_rStar selectKEscheme "
+           "implicitDiffusion").split()
+
+
+class ParamS(C.Structure):
+    _fields_ = [(n, C.c_double) for n in PARAM_D] + [(n, C.c_int) for n in PARAM_I]
+
+
+class Cg2dOp(C.Structure):
+    _fields_ = [(n, P) for n in "aW2d aS2d aC2d pW pS pC".split()] + \
+               [("cg2dNorm", C.c_double), ("cg2dTolerance_sq", C.c_double), ("cg2dNormaliseRHS", C.c_int)]
+
+
+DEFAULT_PARAMS = dict(
+    deltaTMom=1200.0, deltaTFreeSurf=1200.0, freeSurfFac=1.0, implicSurfPress=1.0, implicDiv2DFlow=1.0,
+    rkSign=-1.0, cg2dpcOffDFac=0.51, cg2dTargetResidual=1e-7, cg2dTargetResWunit=-1.0, globalArea=0.0,
+    viscAhD=0.0, viscAhZ=0.0, viscA4D=0.0, viscA4Z=0.0, sideDragFactor=2.0, bottomDragLinear=0.0,
+    bottomDragQuadratic=0.0, recip_rSphere=1.0 / 6370e3, afFacMom=1.0, vfFacMom=1.0, cfFacMom=1.0,
+    mtFacMom=1.0, momAdvection=1, momViscosity=1, useBiharmonicVisc=0, implicitViscosity=0,
+    no_slip_sides=1, no_slip_bottom=1, bottomVisc_pCell=0, selectBotDragQuadr=-1, selectImplicitDrag=0,
+    useCDscheme=0, selectCoriScheme=0, selectMetricTerms=0, usingSphericalPolarGrid=0, rigidLid=0,
+    select_rStar=0, selectKEscheme=0, implicitDiffusion=0)
+
+
+def ptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "oracle needs contiguous float64"
+    return a.ctypes.data_as(P)
+
+
+class Oracle:
+    """Holds the loaded library plus a grid/params pair in C form."""
+
+    def __init__(self, grid, params=None):
+        self.lib = C.CDLL(build())
+        self.grid = grid
+        d = grid.d
+        self.d = Dims(d.sNx, d.sNy, d.OLx, d.OLy, d.nSx, d.nSy, d.Nr)
+        self.g = GridS()
+        self.g.d = self.d
+        self._keep = []
+        for n in GRID_FIELDS:
+            a = grid.a.get(n)
+            if a is None:
+                a = np.zeros(d.shape3 if n.startswith(("hFac", "recip_hFac", "mask")) else d.shape2)
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            grid.a[n] = a
+            setattr(self.g, n, ptr(a))
+        self.set_params(**(params or {}))
+        L = self.lib
+        L.og_global_sum_tile.restype = C.c_double
+
+    def set_params(self, **kw):
+        self.params = dict(DEFAULT_PARAMS)
+        self.params.update(kw)
+        self.p = ParamS(**self.params)
+
+    # ---- eesupp ----
+    def exch_xyz(self, a, nz=1):
+        self.lib.og_exch_xyz(C.byref(self.d), ptr(a), C.c_int(nz))
+        return a
+
+    # ---- cg2d ----
+    def ini_cg2d(self):
+        d = self.grid.d
+        arrs = {n: np.zeros(d.shape2) for n in "aW2d aS2d aC2d pW pS pC".split()}
+        op = Cg2dOp(**{n: ptr(a) for n, a in arrs.items()})
+        self.lib.og_ini_cg2d(C.byref(self.g), C.byref(self.p), C.byref(op))
+        arrs.update(cg2dNorm=op.cg2dNorm, cg2dTolerance_sq=op.cg2dTolerance_sq,
+                    cg2dNormaliseRHS=bool(op.cg2dNormaliseRHS))
+        return arrs
+
+    def _op(self, op):
+        return Cg2dOp(**{n: ptr(op[n]) for n in "aW2d aS2d aC2d pW pS pC".split()},
+                      cg2dNorm=op["cg2dNorm"], cg2dTolerance_sq=op["cg2dTolerance_sq"],
+                      cg2dNormaliseRHS=int(op["cg2dNormaliseRHS"]))
+
+    def cg2d(self, op, b, x, numIters, nIterMin=-1, sr=False, history=False):
+        """Returns dict(firstResidual, minResidualSq, lastResidual, numIters, nIterMin, sumRHS, rhsMax[, hist]);
+        b and x are updated in place exactly as CG2D does."""
+        cop = self._op(op)
+        f, m, l, s, r = (C.c_double() for _ in range(5))
+        ni, nm = C.c_int(numIters), C.c_int(nIterMin)
+        hist = np.zeros(max(numIters, 1)) if history else None
+        fn = self.lib.og_cg2d_sr if sr else self.lib.og_cg2d
+        fn(C.byref(self.d), C.byref(cop), ptr(b), ptr(x), C.byref(f), C.byref(m), C.byref(l),
+           C.byref(ni), C.byref(nm), C.byref(s), C.byref(r), ptr(hist) if history else None)
+        out = dict(firstResidual=f.value, minResidualSq=m.value, lastResidual=l.value,
+                   numIters=ni.value, nIterMin=nm.value, sumRHS=s.value, rhsMax=r.value)
+        if history:
+            out["hist"] = hist[:ni.value]
+        return out
+
+    # ---- momentum ----
+    def mom_fluxform(self, bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm,
+                     fVerUkp, fVerVkp, guDiss, gvDiss, uVel, vVel, wVel, gU, gV):
+        self.lib.og_mom_fluxform(C.byref(self.g), C.byref(self.p), bi, bj, k, iMin, iMax, jMin, jMax,
+                                 ptr(kappaRU), ptr(kappaRV), ptr(fVerUkm), ptr(fVerVkm), ptr(fVerUkp),
+                                 ptr(fVerVkp), ptr(guDiss), ptr(gvDiss), ptr(uVel), ptr(vVel), ptr(wVel),
+                                 ptr(gU), ptr(gV))
+
+    # ---- tracers ----
+    def calc_adv_flow(self, bi, bj, k, uVel, vVel, wVel, xA, yA, maskUp, uFld, vFld, wFld,
+                      uTrans, vTrans, rTrans, rTransKp1):
+        self.lib.og_calc_adv_flow(C.byref(self.g), bi, bj, k, ptr(uVel), ptr(vVel), ptr(wVel), ptr(xA), ptr(yA),
+                                  ptr(maskUp), ptr(uFld), ptr(vFld), ptr(wFld), ptr(uTrans), ptr(vTrans),
+                                  ptr(rTrans), ptr(rTransKp1))
+
+    def gad_calc_rhs(self, bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld,
+                     wFld, uTrans, vTrans, rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN,
+                     TracAB, deltaTLev, advScheme, vertAdvScheme, calcAdvection, implicitAdvection,
+                     applyAB_onTracer, trUseDiffKr4, fZon, fMer, fVerT, gTracer):
+        self.lib.og_gad_calc_rhs(
+            C.byref(self.g), C.byref(self.p), bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown,
+            ptr(xA), ptr(yA), ptr(maskUp), ptr(uFld), ptr(vFld), ptr(wFld), ptr(uTrans), ptr(vTrans),
+            ptr(rTrans), ptr(rTransKp1), C.c_double(diffKh), C.c_double(diffK4), ptr(KappaR), ptr(diffKr4),
+            ptr(TracerN), ptr(TracAB), ptr(deltaTLev), int(advScheme), int(vertAdvScheme),
+            int(calcAdvection), int(implicitAdvection), int(applyAB_onTracer), int(trUseDiffKr4),
+            ptr(fZon), ptr(fMer), ptr(fVerT), ptr(gTracer))
+
+    # ---- glue ----
+    def timestep(self, bi, bj, k, iMin, iMax, jMin, jMax, dPhiHydX, dPhiHydY, guDiss, gvDiss, sfU, sfV,
+                 momForcing, momDissip_In_AB, abFac, uVel, vVel, gU, gV, guNm1, gvNm1):
+        self.lib.og_timestep(C.byref(self.g), C.byref(self.p), bi, bj, k, iMin, iMax, jMin, jMax,
+                             ptr(dPhiHydX), ptr(dPhiHydY), ptr(guDiss), ptr(gvDiss), ptr(sfU), ptr(sfV),
+                             int(momForcing), int(momDissip_In_AB), C.c_double(abFac), ptr(uVel), ptr(vVel),
+                             ptr(gU), ptr(gV), ptr(guNm1), ptr(gvNm1))
+
+    def solve_rhs(self, bi, bj, etaN, gU, gV, b, x):
+        self.lib.og_solve_rhs(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]), ptr(etaN),
+                              ptr(gU), ptr(gV), ptr(b), ptr(x))
+
+    def correction_step(self, bi, bj, etaN, gU, gV, uVel, vVel):
+        self.lib.og_correction_step(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]),
+                                    ptr(etaN), ptr(gU), ptr(gV), ptr(uVel), ptr(vVel))
+
+    def integrate_for_w(self, bi, bj, uVel, vVel, wVel):
+        self.lib.og_integrate_for_w(C.byref(self.g), C.byref(self.p), bi, bj, ptr(uVel), ptr(vVel), ptr(wVel))

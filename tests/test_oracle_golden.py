@@ -1,0 +1,80 @@
+"""Pins the CPU oracle against the reference's own golden output
+(verification/tutorial_barotropic_gyre/results/output.txt, extracted to
+tests/golden/tutorial_barotropic_gyre.json by tests/golden/extract_golden.py).
+
+Pass rule = the reference's own (verification/testreport:956-987): number of
+matching significant digits, here required on every printed digit (the goldens
+print 15 digits for cg2d_*, 14 for %MON)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import barotropic_gyre as bg
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_barotropic_gyre.json")))
+
+
+@pytest.fixture(scope="module")
+def run10():
+    return bg.run(10)
+
+
+def fmt(v, nd):
+    return f"{v:.{nd}E}"
+
+
+def test_inputs_match_reference_files():
+    ref = "/root/reference/verification/tutorial_barotropic_gyre/input"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    h, t = bg.gen_inputs()
+    assert h.tobytes() == open(os.path.join(ref, "bathy.bin"), "rb").read()
+    assert t.tobytes() == open(os.path.join(ref, "windx_cosy.bin"), "rb").read()
+
+
+def test_cg2d_norm(run10):
+    norm, _ = run10
+    assert fmt(norm, 16) == GOLD["cg2dNorm"]          # ini_cg2d.F:161 '(1PE23.16)'
+
+
+def test_cg2d_lines_all_steps(run10):
+    _, out = run10
+    assert [r["numIters"] for r in out] == GOLD["cg2d_iters"]
+    for r, ir, lr, (sr, rm) in zip(out, GOLD["cg2d_init_res"], GOLD["cg2d_last_res"], GOLD["sumRHS_rhsMax"]):
+        assert fmt(r["firstResidual"], 14) == ir       # solve_for_pressure.F:337 '(1PE23.14)'
+        assert fmt(r["lastResidual"], 14) == lr
+        assert fmt(r["rhsMax"], 14) == rm              # cg2d.F:199 '(1P2E22.14)'
+        assert abs(r["sumRHS"] - float(sr)) <= 1e-14 * max(1.0, abs(float(sr))) or fmt(r["sumRHS"], 14) == sr
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel"])
+@pytest.mark.parametrize("st", ["max", "min", "sd"])
+def test_monitor_dynstats(run10, fld, st):
+    _, out = run10
+    gold = GOLD[f"dynstat_{fld}_{st}"][1:]             # entry 0 is the initial state
+    for r, gv in zip(out, gold):
+        a, b = r[fld][st], float(gv)
+        # testreport's tr_cmpnum: digits = -log10(|a-b| / (0.5(|a|+|b|))); the monitor prints 14
+        assert a == pytest.approx(b, rel=5e-13, abs=1e-30), (fld, st)
+
+
+def test_multi_tile_decomposition_reproduces_golden():
+    """SIZE.h_mpi-style 2x2 tiling of the same domain (31x31 tiles): with the ordered
+    tile sum the iteration counts stay identical and init_res agrees to >= 12 digits
+    (summation order inside GLOBAL_SUM_TILE changes with the tiling)."""
+    _, out = bg.run(4, nSx=2, nSy=2)
+    assert [r["numIters"] for r in out] == GOLD["cg2d_iters"][:4]
+    for r, ir in zip(out, GOLD["cg2d_init_res"]):
+        assert r["firstResidual"] == pytest.approx(float(ir), rel=1e-11)
+
+
+def test_cg2d_sr_converges_to_same_solution():
+    """CG2D_SR (cg2d_sr.F) is a different recurrence: same tolerance, close counts."""
+    _, a = bg.run(3)
+    _, b = bg.run(3, sr=True)
+    for ra, rb in zip(a, b):
+        assert abs(ra["numIters"] - rb["numIters"]) <= 3
+        assert rb["lastResidual"] < 1e-7
+        assert rb["eta"]["max"] == pytest.approx(ra["eta"]["max"], rel=1e-6)
