@@ -1,0 +1,136 @@
+/* mitgcm_b200.h -- C ABI of the B200-native CG2D / GAD_CALC_RHS / MOM_FLUXFORM path.
+ *
+ * Calling convention = what a Fortran-77 MITgcm build binds without any glue
+ * (the convention the tree already uses for cloc_/sigreg_, eesupp/src/tim.c,
+ * tools/genmake2:792-886): lower-case name with a trailing underscore, every
+ * argument by reference, LOGICAL passed as 4-byte int, arrays in the eesupp tile
+ * layout (1-OLx:sNx+OLx, 1-OLy:sNy+OLy, [Nr,] nSx, nSy) of model/inc/SIZE.h.
+ * No torch types, no C++ types.  Array arguments may be HOST pointers (the
+ * reference call sites; the library stages them through the GPU) or DEVICE
+ * pointers (resident state; no copies) -- detected per pointer.
+ *
+ * Error convention: the library never exits.  Every entry point
+ * that can fail sets *ierr (0 = ok); hot-path entry points that keep the exact
+ * reference argument list record the code for mitgcm_b200_last_error_().
+ * Solver non-convergence is NOT an error (cg2d.F:358-369).
+ * Threading: master thread only (nTx = nTy = 1); one process <-> one GPU.
+ */
+#ifndef MITGCM_B200_H
+#define MITGCM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- field ids for the device mirrors of COMMON-block arrays --------------- */
+/* 2-D tile arrays, model/inc/GRID.h:311-506, CG2D.h:32-42, SURFACE.h, FFIELDS.h */
+enum {
+  MG_DXC = 0, MG_DYC, MG_DXG, MG_DYG, MG_DXF, MG_DYF, MG_DXV, MG_DYU,
+  MG_RA, MG_RAW, MG_RAS, MG_RAZ,
+  MG_RECIP_DXC, MG_RECIP_DYC, MG_RECIP_DXG, MG_RECIP_DYG, MG_RECIP_DXF, MG_RECIP_DYF,
+  MG_RECIP_DXV, MG_RECIP_DYU, MG_RECIP_RA, MG_RECIP_RAW, MG_RECIP_RAS, MG_RECIP_RAZ,
+  MG_FCORI, MG_FCORIG, MG_TANPHIATU, MG_TANPHIATV, MG_RECIP_BO, MG_BO_SURF,
+  MG_AW2D, MG_AS2D, MG_AC2D, MG_PW, MG_PS, MG_PC,
+  MG_ETAN, MG_SURFFORCU, MG_SURFFORCV, MG_SURFFORCT,
+  MG_N2D,
+  /* 3-D tile arrays (Nr levels), GRID.h, DYNVARS.h */
+  MG_HFACC = 100, MG_HFACW, MG_HFACS, MG_RECIP_HFACC, MG_RECIP_HFACW, MG_RECIP_HFACS,
+  MG_MASKC, MG_MASKW, MG_MASKS,
+  MG_UVEL, MG_VVEL, MG_WVEL, MG_THETA, MG_SALT, MG_GU, MG_GV, MG_GUNM1, MG_GVNM1,
+  MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART,
+  MG_N3D_END,
+  /* (Nr+1)-level tile arrays */
+  MG_KAPPARU = 200, MG_KAPPARV, MG_N3DP_END,
+  /* per-row arrays (1-OLy:sNy+OLy,nSx,nSy) */
+  MG_COSFACU = 300, MG_COSFACV, MG_NJ_END,
+  /* vertical arrays: drF,recip_drF (Nr); drC,recip_drC (Nr+1) */
+  MG_DRF = 400, MG_DRC, MG_RECIP_DRF, MG_RECIP_DRC, MG_TREF, MG_NK_END
+};
+
+/* ---- run-time parameter ids (model/inc/PARAMS.h) ---------------------------- */
+enum {
+  MP_DELTATMOM = 0, MP_DELTATFREESURF, MP_FREESURFFAC, MP_IMPLICSURFPRESS, MP_IMPLICDIV2DFLOW,
+  MP_RKSIGN, MP_CG2DNORM, MP_CG2DTOLERANCE_SQ,
+  MP_VISCAHD, MP_VISCAHZ, MP_VISCA4D, MP_VISCA4Z, MP_SIDEDRAGFACTOR, MP_BOTTOMDRAGLINEAR,
+  MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
+  MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
+  MP_ND,
+  MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
+  MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
+  MI_NO_SLIP_SIDES, MI_NO_SLIP_BOTTOM, MI_BOTTOMVISC_PCELL, MI_SELECTBOTDRAGQUADR,
+  MI_SELECTIMPLICITDRAG, MI_USECDSCHEME, MI_SELECTCORISCHEME, MI_SELECTMETRICTERMS,
+  MI_USINGSPHERICALPOLARGRID, MI_RIGIDLID, MI_SELECT_RSTAR, MI_IMPLICITDIFFUSION,
+  MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
+  MI_NI_END
+};
+
+/* ---- life cycle -------------------------------------------------------------- */
+/* dims = {sNx,sNy,OLx,OLy,nSx,nSy,Nr,nPx,nPy,myPx,myPy} (model/inc/SIZE.h + the process
+ * position INI_PROCS derives, eesupp/src/ini_procs.F:145-260); device = CUDA ordinal or -1
+ * for LOCAL_RANK / 0. */
+void mitgcm_b200_init_(const int *dims, const int *device, int *ierr);
+void mitgcm_b200_finalize_(void);
+int  mitgcm_b200_last_error_(void);
+const char *mitgcm_b200_last_error_string(void);
+
+void mitgcm_b200_set_param_d_(const int *id, const double *val, int *ierr);
+void mitgcm_b200_set_param_i_(const int *id, const int *val, int *ierr);
+
+/* device mirrors: host -> device (creates the mirror on first use), device -> host,
+ * and the raw device address (for callers that keep state resident). */
+void mitgcm_b200_set_field_(const int *id, const double *host, int *ierr);
+void mitgcm_b200_get_field_(const int *id, double *host, int *ierr);
+double *mitgcm_b200_field_ptr(int id);
+void mitgcm_b200_sync_(void);
+
+/* ---- CG2D / CG2D_SR ------------------------------------------------------------
+ * Same argument list as SUBROUTINE CG2D (model/src/cg2d.F:13-17) and CG2D_SR
+ * (model/src/cg2d_sr.F:13-17); operators come from the mirrors MG_AW2D..MG_PC of
+ * COMMON /CG2D_I_RS/ (model/inc/CG2D.h:32-42), cg2dNorm / cg2dTolerance_sq /
+ * cg2dNormaliseRHS from the parameters.  Caller: solve_for_pressure.F:292,309. */
+void cg2d_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
+                double *lastResidual, int *numIters, int *nIterMin, const int *myThid);
+void cg2d_sr_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
+                   double *lastResidual, int *numIters, int *nIterMin, const int *myThid);
+/* The values cg2d.F:199-200 prints inside the solver (`cg2d: Sum(rhs),rhsMax`), and the
+ * per-iteration residuals of cg2d.F:329-336 (n <= iterations run). */
+void mitgcm_b200_cg2d_stats_(double *sumRHS, double *rhsMax);
+void mitgcm_b200_cg2d_residuals_(double *resid, const int *n);
+
+/* ---- GAD_CALC_RHS ---------------------------------------------------------------
+ * Same argument list as pkg/generic_advdiff/gad_calc_rhs.F:10-21 (callers
+ * temp_integrate.F:357, salt_integrate.F:349, ptracers_integrate.F:315).  Grid arrays
+ * come from the mirrors. */
+void gad_calc_rhs_b200_(const int *bi, const int *bj, const int *iMin, const int *iMax,
+                        const int *jMin, const int *jMax, const int *k, const int *kM1,
+                        const int *kUp, const int *kDown,
+                        const double *xA, const double *yA, const double *maskUp,
+                        const double *uFld, const double *vFld, const double *wFld,
+                        const double *uTrans, const double *vTrans, const double *rTrans,
+                        const double *rTransKp1, const double *diffKh, const double *diffK4,
+                        const double *KappaR, const double *diffKr4,
+                        const double *TracerN, const double *TracAB, const double *deltaTLev,
+                        const int *trIdentity, const int *advectionSchArg, const int *vertAdvecSchArg,
+                        const int *calcAdvection, const int *implicitAdvection,
+                        const int *applyAB_onTracer, const int *trUseDiffKr4, const int *trUseGMRedi,
+                        const int *trUseKPP, const int *trUseSmolHack,
+                        double *fZon, double *fMer, double *fVerT, double *gTracer,
+                        const double *myTime, const int *myIter, const int *myThid);
+
+/* ---- MOM_FLUXFORM -----------------------------------------------------------------
+ * Same argument list as pkg/mom_fluxform/mom_fluxform.F:42-48 (caller dynamics.F:517),
+ * followed by the COMMON /DYNVARS_R/ arrays the routine reads and writes
+ * (model/inc/DYNVARS.h): the shim passes them explicitly. */
+void mom_fluxform_b200_(const int *bi, const int *bj, const int *k, const int *iMin, const int *iMax,
+                        const int *jMin, const int *jMax,
+                        const double *kappaRU, const double *kappaRV,
+                        double *fVerUkm, double *fVerVkm, double *fVerUkp, double *fVerVkp,
+                        double *guDiss, double *gvDiss,
+                        const double *myTime, const int *myIter, const int *myThid,
+                        const double *uVel, const double *vVel, const double *wVel,
+                        double *gU, double *gV);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,71 @@
+// context.h -- process-wide state of libmitgcm_b200: tile geometry, device mirrors
+// of the COMMON-block arrays, run-time parameters, scratch buffers and the stream.
+// One process <-> one GPU, like one MPI rank of the reference (eesupp/src/ini_procs.F).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/mitgcm_b200.h"
+
+namespace mg {
+
+struct Geom {
+  int sNx, sNy, OLx, OLy, nSx, nSy, Nr;
+  int nPx, nPy, myPx, myPy;
+  int PX, PY, nTiles;
+  size_t slab;   // PX*PY
+  size_t n2;     // slab*nTiles
+  size_t n3;     // slab*Nr*nTiles
+};
+
+enum FieldKind { K2D, K3D, K3DP, KJ, KK };
+
+struct Params {
+  double d[MP_ND];
+  int i[MI_NI_END - 100];
+  double D(int id) const { return d[id]; }
+  int I(int id) const { return i[id - 100]; }
+};
+
+struct Ctx {
+  bool ready = false;
+  Geom g{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Params p{};
+  std::map<int, double *> fields;
+  int lastError = 0;
+  std::string lastErrorString;
+  // staging buffers for host-pointer arguments, keyed by a small slot number
+  std::map<int, std::pair<double *, size_t>> stage;
+  // halo push tables for width-1 exchanges (cg2d): index of the halo cell that mirrors
+  // each edge point, per tile: [W(sNy) | E(sNy) | S(sNx) | N(sNx)]
+  int *pushTab = nullptr;
+  // cg2d workspace
+  struct Cg2dWs *cg2d = nullptr;
+  int numSMs = 0;
+};
+
+Ctx &ctx();
+bool fail(int code, const std::string &msg);          // records error, returns false
+#define MG_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      mg::fail(1000 + (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+      return false;                                                                \
+    }                                                                              \
+  } while (0)
+
+size_t field_elems(const Geom &g, int id);             // 0 if id is unknown
+double *field(int id, bool create = true);             // device mirror (zero-filled on creation)
+bool is_device_ptr(const void *p);
+// returns a device pointer for `p`: p itself if it is a device pointer, else a staging
+// buffer (slot) of n doubles, filled from p when `upload`.
+double *to_device(const double *p, size_t n, int slot, bool upload);
+bool from_device(double *hostOrDev, const double *dev, size_t n);  // no-op when same pointer
+
+}  // namespace mg

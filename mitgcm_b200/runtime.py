@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference interfaces on top of the C ABI.
+
+Function names and argument meaning follow the Fortran routines they replace
+(CG2D, CG2D_SR, GAD_CALC_RHS, MOM_FLUXFORM); arrays are numpy arrays (host,
+reference layout) or torch CUDA tensors (resident on the GPU, no copies)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .grid import Dims, Grid
+
+E = _lib.ENUMS
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _addr(a):
+    """void* of a numpy array (host) or a torch tensor (host or device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+        return C.c_void_p(a.ctypes.data)
+    # torch tensor
+    import torch
+    assert isinstance(a, torch.Tensor) and a.dtype == torch.float64 and a.is_contiguous()
+    return C.c_void_p(a.data_ptr())
+
+
+def _check(ierr=None):
+    L = _lib.lib()
+    code = L.mitgcm_b200_last_error_() if ierr is None else (ierr.value or L.mitgcm_b200_last_error_() if ierr.value else 0)
+    if code:
+        raise B200Error(f"libmitgcm_b200 error {code}: {L.mitgcm_b200_last_error_string().decode()}")
+
+
+def init(d: Dims, device: int = -1):
+    L = _lib.lib()
+    dims = (C.c_int * 11)(d.sNx, d.sNy, d.OLx, d.OLy, d.nSx, d.nSy, d.Nr, d.nPx, d.nPy, d.myPx, d.myPy)
+    ierr = C.c_int(0)
+    L.mitgcm_b200_init_(dims, C.byref(C.c_int(device)), C.byref(ierr))
+    _check(ierr)
+
+
+def finalize():
+    _lib.lib().mitgcm_b200_finalize_()
+
+
+def sync():
+    _lib.lib().mitgcm_b200_sync_()
+
+
+def set_params(**kw):
+    """set_params(deltaTMom=1200., momAdvection=True, ...): names as in PARAMS.h."""
+    L = _lib.lib()
+    ierr = C.c_int(0)
+    for k, v in kw.items():
+        kd, ki = "MP_" + k.upper(), "MI_" + k.upper()
+        if kd in E:
+            L.mitgcm_b200_set_param_d_(C.byref(C.c_int(E[kd])), C.byref(C.c_double(float(v))), C.byref(ierr))
+        elif ki in E:
+            L.mitgcm_b200_set_param_i_(C.byref(C.c_int(E[ki])), C.byref(C.c_int(int(v))), C.byref(ierr))
+        else:
+            raise KeyError(f"unknown parameter {k}")
+        _check(ierr)
+
+
+def field_id(name: str) -> int:
+    return E["MG_" + name.upper()]
+
+
+def set_field(name: str, a):
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_set_field_(C.byref(C.c_int(field_id(name))), _addr(a), C.byref(ierr))
+    _check(ierr)
+
+
+def get_field(name: str, out):
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_get_field_(C.byref(C.c_int(field_id(name))), _addr(out), C.byref(ierr))
+    _check(ierr)
+    return out
+
+
+GRID_FIELD_NAMES = ("dxC dyC dxG dyG dxF dyF dxV dyU rA rAw rAs rAz recip_dxC recip_dyC recip_dxG recip_dyG "
+                    "recip_dxF recip_dyF recip_dxV recip_dyU recip_rA recip_rAw recip_rAs recip_rAz fCori fCoriG "
+                    "tanPhiAtU tanPhiAtV recip_Bo Bo_surf hFacC hFacW hFacS recip_hFacC recip_hFacW recip_hFacS "
+                    "maskC maskW maskS cosFacU cosFacV").split()
+
+
+def set_grid(g: Grid):
+    """Uploads the GRID.h arrays (what INI_GRID / INI_MASKS_ETC left in COMMON)."""
+    for n in GRID_FIELD_NAMES:
+        if n in g.a:
+            set_field(n, np.ascontiguousarray(g.a[n], dtype=np.float64))
+    Nr = g.d.Nr
+    for n in ("drF", "drC", "recip_drF", "recip_drC"):
+        v = np.zeros(Nr + 1)
+        v[:len(g.a[n])] = g.a[n]
+        set_field(n, v)
+
+
+def set_cg2d_operator(op: dict):
+    """Uploads COMMON /CG2D_I_RS/ + cg2dNorm, cg2dTolerance_sq, cg2dNormaliseRHS
+    (model/inc/CG2D.h) as produced by INI_CG2D / UPDATE_CG2D."""
+    for n in "aW2d aS2d aC2d pW pS pC".split():
+        set_field(n, op[n])
+    set_params(cg2dNorm=op["cg2dNorm"], cg2dTolerance_sq=op["cg2dTolerance_sq"],
+               cg2dNormaliseRHS=bool(op["cg2dNormaliseRHS"]))
+
+
+def cg2d(cg2d_b, cg2d_x, numIters: int, nIterMin: int = -1, sr: bool = False, residuals: bool = False):
+    """CALL CG2D( cg2d_b, cg2d_x, firstResidual, minResidualSq, lastResidual, numIters,
+    nIterMin, myThid ) -- model/src/cg2d.F:13-17 (CG2D_SR when sr).  b and x are updated in
+    place like the Fortran dummies; the scalar outputs come back as a dict, together with the
+    `cg2d: Sum(rhs),rhsMax` values the reference prints inside the solver."""
+    L = _lib.lib()
+    f, m, l, s, r = (C.c_double() for _ in range(5))
+    ni, nm = C.c_int(numIters), C.c_int(nIterMin)
+    fn = L.cg2d_sr_b200_ if sr else L.cg2d_b200_
+    fn(_addr(cg2d_b), _addr(cg2d_x), C.byref(f), C.byref(m), C.byref(l), C.byref(ni), C.byref(nm),
+       C.byref(C.c_int(1)))
+    _check()
+    L.mitgcm_b200_cg2d_stats_(C.byref(s), C.byref(r))
+    out = dict(firstResidual=f.value, minResidualSq=m.value, lastResidual=l.value, numIters=ni.value,
+               nIterMin=nm.value, sumRHS=s.value, rhsMax=r.value)
+    if residuals:
+        h = np.zeros(max(ni.value, 1))
+        L.mitgcm_b200_cg2d_residuals_(_addr(h), C.byref(C.c_int(ni.value)))
+        out["hist"] = h[:ni.value]
+    return out

@@ -172,6 +172,9 @@ void og_ini_cg2d(const og_grid *g, const og_params *p, og_cg2d_op *op) {
 }
 
 #define TILES for (int bj = 1; bj <= d->nSy; bj++) for (int bi = 1; bi <= d->nSx; bi++)
+/* Tiles are independent inside a sweep (per-tile partial sums), exactly the reference's
+ * thread / MPI-rank parallelism over tiles; results do not depend on the thread count. */
+#define TILES_PAR _Pragma("omp parallel for collapse(2) schedule(static)") TILES
 #define INTERIOR for (int j = 1; j <= sNy; j++) for (int i = 1; i <= sNx; i++)
 
 /* shared prologue: cg2d.F:100-200 == cg2d_sr.F:111-216 */
@@ -247,7 +250,7 @@ void og_cg2d(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *cg2
   if (!(err_sq < op->cg2dTolerance_sq)) {
     for (int it2d = 1; it2d <= *numIters; it2d++) {
       /* q = M r ; eta = <q,r>   cg2d.F:217-243 */
-      TILES {
+      TILES_PAR {
         tileA[IT(bi, bj)] = 0.;
         INTERIOR {
           q[IQ(i, j, bi, bj)] =
@@ -262,10 +265,10 @@ void og_cg2d(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *cg2
       double eta_qrN = og_global_sum_tile(d, tileA);
       double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      TILES INTERIOR s[IR(i, j, bi, bj)] = q[IQ(i, j, bi, bj)] + cgBeta * s[IR(i, j, bi, bj)];
+      TILES_PAR INTERIOR s[IR(i, j, bi, bj)] = q[IQ(i, j, bi, bj)] + cgBeta * s[IR(i, j, bi, bj)];
       og_exch_s3d(d, s);
       /* q = A s ; alpha = <s,q>   cg2d.F:274-301 */
-      TILES {
+      TILES_PAR {
         tileA[IT(bi, bj)] = 0.;
         INTERIOR {
           q[IQ(i, j, bi, bj)] =
@@ -280,7 +283,7 @@ void og_cg2d(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *cg2
       double alpha = og_global_sum_tile(d, tileA);
       alpha = eta_qrN / alpha;
       /* x += alpha s ; r -= alpha q ; err = <r,r>   cg2d.F:305-327 */
-      TILES {
+      TILES_PAR {
         tileA[IT(bi, bj)] = 0.;
         INTERIOR {
           cg2d_x[I2(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)] + alpha * s[IR(i, j, bi, bj)];
@@ -295,7 +298,7 @@ void og_cg2d(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *cg2
       if (err_sq < *minResidualSq) {
         *minResidualSq = err_sq;
         *nIterMin = it2d;
-        TILES INTERIOR xmin[IQ(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)];
+        TILES_PAR INTERIOR xmin[IQ(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)];
       }
       og_exch_s3d(d, r);
     }
@@ -330,7 +333,7 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
   if (*nIterMin >= 0) { *nIterMin = 0; *minResidualSq = err_sq; }
   if (!(err_sq < op->cg2dTolerance_sq)) {
     /* start-up iteration, cg2d_sr.F:220-291 */
-    TILES {
+    TILES_PAR {
       t1[IT(bi, bj)] = 0.;
       INTERIOR {
         y[IR(i, j, bi, bj)] =
@@ -346,7 +349,7 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
     og_exch_s3d(d, s);
     double eta_qrN = og_global_sum_tile(d, t1);
     eta_qrNM1 = eta_qrN;
-    TILES {
+    TILES_PAR {
       t1[IT(bi, bj)] = 0.;
       INTERIOR {
         q[IQ(i, j, bi, bj)] =
@@ -368,7 +371,7 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
     int converged = 0;
     /* main loop, cg2d_sr.F:294-410; Fortran DO leaves it2d = numIters on exhaustion */
     for (it2d = 1; it2d <= *numIters - 1; it2d++) {
-      TILES INTERIOR {
+      TILES_PAR INTERIOR {
         y[IR(i, j, bi, bj)] =
             op->pC[I2(i, j, bi, bj)] * r[IR(i, j, bi, bj)]
           + op->pW[I2(i, j, bi, bj)] * r[IR(i - 1, j, bi, bj)]
@@ -377,7 +380,7 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
           + op->pS[I2(i, j + 1, bi, bj)] * r[IR(i, j + 1, bi, bj)];
       }
       og_exch_s3d(d, y);
-      TILES {
+      TILES_PAR {
         t1[IT(bi, bj)] = 0.; t2[IT(bi, bj)] = 0.; t3[IT(bi, bj)] = 0.;
         INTERIOR {
           v[IQ(i, j, bi, bj)] =
@@ -400,13 +403,13 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
       if (err_sq < *minResidualSq) {
         *minResidualSq = err_sq;
         *nIterMin = it2d;
-        TILES INTERIOR xmin[IQ(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)];
+        TILES_PAR INTERIOR xmin[IQ(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)];
       }
       double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
       alpha = delta - (cgBeta * cgBeta) * alpha;
       sigma = eta_qrN / alpha;
-      TILES INTERIOR {
+      TILES_PAR INTERIOR {
         s[IR(i, j, bi, bj)] = y[IR(i, j, bi, bj)] + cgBeta * s[IR(i, j, bi, bj)];
         cg2d_x[I2(i, j, bi, bj)] = cg2d_x[I2(i, j, bi, bj)] + sigma * s[IR(i, j, bi, bj)];
         q[IQ(i, j, bi, bj)] = v[IQ(i, j, bi, bj)] + cgBeta * q[IQ(i, j, bi, bj)];
@@ -416,7 +419,7 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
     }
     if (!converged) {
       /* cg2d_sr.F:411-423 (loop fell through; it2d == MAX(numIters,1)) */
-      TILES {
+      TILES_PAR {
         t1[IT(bi, bj)] = 0.;
         INTERIOR t1[IT(bi, bj)] = t1[IT(bi, bj)] + r[IR(i, j, bi, bj)] * r[IR(i, j, bi, bj)];
       }
