@@ -19,6 +19,7 @@
 // the summation order of the dot products differs.
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "context.h"
 
@@ -26,7 +27,7 @@ namespace cgrp = cooperative_groups;
 
 namespace mg {
 
-constexpr int CG_THREADS = 512;
+constexpr int CG_THREADS = 256;
 constexpr int CG_WARPS = CG_THREADS / 32;
 constexpr int MAX_PART = 2048;   // max CTAs in the cooperative grid
 
@@ -38,7 +39,8 @@ struct Cg2dOut {
 struct Cg2dArgs {
   int sNx, sNy, OLx, OLy, PX, nTiles;
   size_t slab;
-  int nIB, nJB, RY, nItems;
+  int nIB, nJB, RY, nItems;          // scalar decomposition: warp items of 32 columns x RY rows
+  int nIB2, nJB2, RY2, nItems2, vec2;  // vector decomposition: 64 columns x RY2 rows (double2 per lane)
   const double *aW, *aS, *aC, *pW, *pS, *pC;
   double *b, *x;
   double *r[2], *s[2], *q, *z, *xmin, *v;   // v: extra vector of the SR variant
@@ -316,7 +318,198 @@ __device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending
   }
 }
 
-__global__ void __launch_bounds__(CG_THREADS) cg2d_kernel(Cg2dArgs a) {
+// ---- vectorised phases: two columns per lane (double2), two rows per step -----------------
+// Used when OLx, PX and sNx are even, so every interior row pair (i, i+1), i odd, is 16-byte
+// aligned.  East/west neighbours come from the adjacent lanes by shuffle; only the first and
+// last lanes of a strip touch memory for them.
+
+struct Item2 {
+  int tile, i, j0, j1;
+  size_t base;
+  bool active, edgeW, edgeE;
+};
+
+__device__ __forceinline__ Item2 decode_item2(const Cg2dArgs &a, int item, int lane) {
+  Item2 it;
+  int perTile = a.nIB2 * a.nJB2;
+  it.tile = item / perTile;
+  int rem = item - it.tile * perTile;
+  int jb = rem / a.nIB2, ib = rem - jb * a.nIB2;
+  it.i = 1 + ib * 64 + 2 * lane;
+  it.j0 = 1 + jb * a.RY2;
+  it.j1 = min(it.j0 + a.RY2 - 1, a.sNy);
+  it.active = it.i <= a.sNx;
+  it.edgeW = lane == 0;
+  it.edgeE = lane == 31 || it.i + 2 > a.sNx;
+  it.base = (size_t)(it.i + a.OLx - 1) + (size_t)a.PX * (size_t)(it.j0 + a.OLy - 1) + a.slab * (size_t)it.tile;
+  return it;
+}
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+__device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j, double *f0, double2 v0, double *f1,
+                                       double2 v1) {
+  const int per = 2 * a.sNy + 2 * a.sNx;
+  const int *t = a.pushTab + (size_t)per * it.tile;
+  if (it.i == 1) { int d = t[j - 1]; f0[d] = v0.x; f1[d] = v1.x; }
+  if (it.i + 1 == a.sNx) { int d = t[a.sNy + j - 1]; f0[d] = v0.y; f1[d] = v1.y; }
+  if (j == 1) {
+    int d = t[2 * a.sNy + it.i - 1], e = t[2 * a.sNy + it.i];
+    f0[d] = v0.x; f1[d] = v1.x; f0[e] = v0.y; f1[e] = v1.y;
+  }
+  if (j == a.sNy) {
+    int d = t[2 * a.sNy + a.sNx + it.i - 1], e = t[2 * a.sNy + a.sNx + it.i];
+    f0[d] = v0.x; f1[d] = v1.x; f0[e] = v0.y; f1[e] = v1.y;
+  }
+}
+
+// R rows of phase B starting at row j (flat index idx of column it.i).
+template <int R>
+__device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew,
+                                        double beta, bool saveMin, const Item2 &it, size_t idx, int j, double2 &tS,
+                                        double2 &tC, double2 &aSj, double &acc) {
+  const int PX = a.PX;
+  double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R];
+  double zW[R], sW[R], zE[R], sE[R], aWEl[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    size_t id = idx + (size_t)r * PX;
+    zN[r] = sN[r] = aSN[r] = aWv[r] = aCv[r] = xv[r] = make_double2(0.0, 0.0);
+    zW[r] = sW[r] = zE[r] = sE[r] = aWEl[r] = 0.0;
+    if (it.active) {
+      zN[r] = ld2(a.z + id + PX);
+      sN[r] = ld2(sOld + id + PX);
+      aSN[r] = ldg2(a.aS + id + PX);
+      aWv[r] = ldg2(a.aW + id);
+      aCv[r] = ldg2(a.aC + id);
+      if (saveMin) xv[r] = ld2(a.x + id);
+      if (it.edgeW) { zW[r] = a.z[id - 1]; sW[r] = sOld[id - 1]; }
+      if (it.edgeE) { zE[r] = a.z[id + 2]; sE[r] = sOld[id + 2]; aWEl[r] = __ldg(a.aW + id + 2); }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    size_t id = idx + (size_t)r * PX;
+    double2 tN = make_double2(zN[r].x + beta * sN[r].x, zN[r].y + beta * sN[r].y);
+    double tW = __shfl_up_sync(0xffffffffu, tC.y, 1);
+    double tE = __shfl_down_sync(0xffffffffu, tC.x, 1);
+    double aWE = __shfl_down_sync(0xffffffffu, aWv[r].x, 1);
+    if (it.edgeW) tW = zW[r] + beta * sW[r];
+    if (it.edgeE) { tE = zE[r] + beta * sE[r]; aWE = aWEl[r]; }
+    double q0 = aWv[r].x * tW + aWv[r].y * tC.y + aSj.x * tS.x + aSN[r].x * tN.x + aCv[r].x * tC.x;
+    double q1 = aWv[r].y * tC.x + aWE * tE + aSj.y * tS.y + aSN[r].y * tN.y + aCv[r].y * tC.y;
+    if (it.active) {
+      double2 qv = make_double2(q0, q1);
+      st2(sNew + id, tC);
+      st2(a.q + id, qv);
+      push2v(a, it, j + r, sNew, tC, a.q, qv);
+      if (saveMin) st2(a.xmin + id, xv[r]);
+      acc += tC.x * q0;
+      acc += tC.y * q1;
+    }
+    tS = tC; tC = tN; aSj = aSN[r];
+  }
+}
+
+__device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew, double beta,
+                         bool saveMin, double *sm) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  const int PX = a.PX;
+  double acc[1] = {0.0};
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    size_t idx = it.base;
+    double2 tS = make_double2(0.0, 0.0), tC = tS, aSj = tS;
+    if (it.active) {
+      double2 z0 = ld2(a.z + idx - PX), s0 = ld2(sOld + idx - PX), z1 = ld2(a.z + idx), s1 = ld2(sOld + idx);
+      tS = make_double2(z0.x + beta * s0.x, z0.y + beta * s0.y);
+      tC = make_double2(z1.x + beta * s1.x, z1.y + beta * s1.y);
+      aSj = ldg2(a.aS + idx);
+    }
+    int j = it.j0;
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, it, idx, j, tS, tC, aSj, acc[0]);
+    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, it, idx, j, tS, tC, aSj, acc[0]);
+  }
+  block_partials<1, false>(a, acc, sm);
+}
+
+template <int R>
+__device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
+                                         const double *__restrict__ sCur, double alpha, const Item2 &it, size_t idx,
+                                         int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH) {
+  const int PX = a.PX;
+  double2 rN[R], qN[R], xv[R], sv[R], pCv[R], pWv[R], pSN[R];
+  double rW[R], qW[R], rE[R], qE[R], pWEl[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    size_t id = idx + (size_t)r * PX;
+    rN[r] = qN[r] = xv[r] = sv[r] = pCv[r] = pWv[r] = pSN[r] = make_double2(0.0, 0.0);
+    rW[r] = qW[r] = rE[r] = qE[r] = pWEl[r] = 0.0;
+    if (it.active) {
+      rN[r] = ld2(rOld + id + PX);
+      qN[r] = ld2(a.q + id + PX);
+      xv[r] = ld2(a.x + id);
+      sv[r] = ld2(sCur + id);
+      pCv[r] = ldg2(a.pC + id);
+      pWv[r] = ldg2(a.pW + id);
+      pSN[r] = ldg2(a.pS + id + PX);
+      if (it.edgeW) { rW[r] = rOld[id - 1]; qW[r] = a.q[id - 1]; }
+      if (it.edgeE) { rE[r] = rOld[id + 2]; qE[r] = a.q[id + 2]; pWEl[r] = __ldg(a.pW + id + 2); }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    size_t id = idx + (size_t)r * PX;
+    double2 rNn = make_double2(rN[r].x - alpha * qN[r].x, rN[r].y - alpha * qN[r].y);
+    double rWn = __shfl_up_sync(0xffffffffu, rC.y, 1);
+    double rEn = __shfl_down_sync(0xffffffffu, rC.x, 1);
+    double pWE = __shfl_down_sync(0xffffffffu, pWv[r].x, 1);
+    if (it.edgeW) rWn = rW[r] - alpha * qW[r];
+    if (it.edgeE) { rEn = rE[r] - alpha * qE[r]; pWE = pWEl[r]; }
+    double z0 = pCv[r].x * rC.x + pWv[r].x * rWn + pWv[r].y * rC.y + pSj.x * rS.x + pSN[r].x * rNn.x;
+    double z1 = pCv[r].y * rC.y + pWv[r].y * rC.x + pWE * rEn + pSj.y * rS.y + pSN[r].y * rNn.y;
+    if (it.active) {
+      double2 zv = make_double2(z0, z1);
+      st2(a.x + id, make_double2(xv[r].x + alpha * sv[r].x, xv[r].y + alpha * sv[r].y));
+      st2(rNew + id, rC);
+      st2(a.z + id, zv);
+      push2v(a, it, j + r, rNew, rC, a.z, zv);
+      accE += rC.x * rC.x;
+      accE += rC.y * rC.y;
+      accH += z0 * rC.x;
+      accH += z1 * rC.y;
+    }
+    rS = rC; rC = rNn; pSj = pSN[r];
+  }
+}
+
+__device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
+                          const double *__restrict__ sCur, double alpha, double *sm) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  const int PX = a.PX;
+  double acc[2] = {0.0, 0.0};
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    size_t idx = it.base;
+    double2 rS = make_double2(0.0, 0.0), rC = rS, pSj = rS;
+    if (it.active) {
+      double2 r0 = ld2(rOld + idx - PX), q0 = ld2(a.q + idx - PX), r1 = ld2(rOld + idx), q1 = ld2(a.q + idx);
+      rS = make_double2(r0.x - alpha * q0.x, r0.y - alpha * q0.y);
+      rC = make_double2(r1.x - alpha * q1.x, r1.y - alpha * q1.y);
+      pSj = ldg2(a.pS + idx);
+    }
+    int j = it.j0;
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) ca2_rows<2>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1]);
+    if (j <= it.j1) ca2_rows<1>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1]);
+  }
+  block_partials<2, false>(a, acc, sm);
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   double t1[1], t2[2];
@@ -354,13 +547,15 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_kernel(Cg2dArgs a) {
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, sm);
+      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, sm);
+      else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, sm);
       saveMin = false;
       scur ^= 1;
       grid.sync();
       grid_totals<1, false>(a, t1, sm);
       const double alpha = eta_qrN / t1[0];
-      phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
+      if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm);
+      else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
       grid.sync();
       grid_totals<2, false>(a, t2, sm);
@@ -640,16 +835,25 @@ static bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResid
   a.cg2dNorm = c.p.D(MP_CG2DNORM); a.tolSq = c.p.D(MP_CG2DTOLERANCE_SQ);
   a.normaliseRHS = c.p.I(MI_CG2DNORMALISERHS);
   a.maxIters = *numIters; a.nIterMinIn = *nIterMin;
-  // work decomposition: warp items of 32 columns x RY rows
-  a.nIB = (g.sNx + 31) / 32;
+  // Work decomposition.  Warp items are column strips (32 columns scalar / 64 columns vector)
+  // of RY rows; RY is chosen so that every co-resident warp gets one item of equal size
+  // (balanced: no tail), but never fewer than 2 rows.
   const int maxBlocks = std::min(sr ? w->maxBlocksSR : w->maxBlocks, MAX_PART);
   const long totalWarps = (long)maxBlocks * CG_WARPS;
-  long rows = (long)g.sNy * a.nIB * g.nTiles;     // warp-rows of work
-  int RY = (int)std::min<long>(16, std::max<long>(1, rows / (2 * totalWarps)));
-  a.RY = RY;
-  a.nJB = (g.sNy + RY - 1) / RY;
-  a.nItems = g.nTiles * a.nIB * a.nJB;
-  int blocks = std::min(maxBlocks, (a.nItems + CG_WARPS - 1) / CG_WARPS);
+  auto decomp = [&](int cols, int &nIB, int &nJB, int &RY, int &nItems) {
+    nIB = (g.sNx + cols - 1) / cols;
+    long strips = (long)nIB * g.nTiles;
+    long wps = std::max<long>(1, totalWarps / strips);          // warps per strip
+    RY = (int)std::max<long>(2, (g.sNy + wps - 1) / wps);
+    RY = std::min(RY, g.sNy);
+    nJB = (g.sNy + RY - 1) / RY;
+    nItems = g.nTiles * nIB * nJB;
+  };
+  decomp(32, a.nIB, a.nJB, a.RY, a.nItems);
+  a.vec2 = (!sr && g.OLx % 2 == 0 && g.PX % 2 == 0 && g.sNx % 2 == 0 && g.slab % 2 == 0) ? 1 : 0;
+  if (getenv("MITGCM_B200_CG2D_SCALAR")) a.vec2 = 0;
+  decomp(64, a.nIB2, a.nJB2, a.RY2, a.nItems2);
+  int blocks = std::min(maxBlocks, (std::max(a.nItems, a.vec2 ? a.nItems2 : 0) + CG_WARPS - 1) / CG_WARPS);
   if (blocks < 1) blocks = 1;
   // zero-initialised work arrays incl. ring 0 / sN+1 (cg2d.F:142-147)
   size_t bytes = g.n2 * sizeof(double);

@@ -3,6 +3,8 @@ usage: python scripts/cg2d_perf.py [N=2048] [iters=200] [reps=3] [sr=0]"""
 import sys
 import time
 
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 

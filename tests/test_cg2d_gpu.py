@@ -46,7 +46,8 @@ def test_fixed_iterations_match_oracle(rt, case, sr):
     """Same number of iterations on both sides (tolerance unreachable): fields must agree."""
     g = make_grid(**case, seed=3)
     o, op, b, x = cg2d_problem(g, tol=1e-30)
-    for nit in (1, 2, 7, 25):
+    # a 9-unknown system is solved exactly after <= 9 iterations; beyond that both sides divide 0/0
+    for nit in ((1, 2, 4) if case["sNx"] == 1 else (1, 2, 7, 25)):
         bo, xo, bg, xg = b.copy(), x.copy(), b.copy(), x.copy()
         ro = o.cg2d(op, bo, xo, nit, -1, sr=sr, history=True)
         setup(rt, g, op)
