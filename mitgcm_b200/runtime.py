@@ -134,3 +134,43 @@ def cg2d(cg2d_b, cg2d_x, numIters: int, nIterMin: int = -1, sr: bool = False, re
         L.mitgcm_b200_cg2d_residuals_(_addr(h), C.byref(C.c_int(ni.value)))
         out["hist"] = h[:ni.value]
     return out
+
+
+def _i(v):
+    return C.byref(C.c_int(int(v)))
+
+
+def _d(v):
+    return C.byref(C.c_double(float(v)))
+
+
+def gad_calc_rhs(bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld,
+                 uTrans, vTrans, rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB,
+                 deltaTLev, trIdentity, advectionSchArg, vertAdvecSchArg, calcAdvection, implicitAdvection,
+                 applyAB_onTracer, trUseDiffKr4, trUseGMRedi, trUseKPP, trUseSmolHack, fZon, fMer, fVerT,
+                 gTracer, myTime=0.0, myIter=0, myThid=1):
+    """CALL GAD_CALC_RHS(...) -- pkg/generic_advdiff/gad_calc_rhs.F:10-21, same argument order.
+    diffKr4 and deltaTLev are host numpy vectors of length Nr."""
+    L = _lib.lib()
+    L.gad_calc_rhs_b200_(
+        _i(bi), _i(bj), _i(iMin), _i(iMax), _i(jMin), _i(jMax), _i(k), _i(kM1), _i(kUp), _i(kDown),
+        _addr(xA), _addr(yA), _addr(maskUp), _addr(uFld), _addr(vFld), _addr(wFld), _addr(uTrans),
+        _addr(vTrans), _addr(rTrans), _addr(rTransKp1), _d(diffKh), _d(diffK4), _addr(KappaR),
+        _addr(np.ascontiguousarray(diffKr4, dtype=np.float64)), _addr(TracerN), _addr(TracAB),
+        _addr(np.ascontiguousarray(deltaTLev, dtype=np.float64)), _i(trIdentity), _i(advectionSchArg),
+        _i(vertAdvecSchArg), _i(calcAdvection), _i(implicitAdvection), _i(applyAB_onTracer), _i(trUseDiffKr4),
+        _i(trUseGMRedi), _i(trUseKPP), _i(trUseSmolHack), _addr(fZon), _addr(fMer), _addr(fVerT),
+        _addr(gTracer), _d(myTime), _i(myIter), _i(myThid))
+    _check()
+
+
+def mom_fluxform(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm, fVerUkp, fVerVkp,
+                 guDiss, gvDiss, uVel, vVel, wVel, gU, gV, myTime=0.0, myIter=0, myThid=1):
+    """CALL MOM_FLUXFORM(...) -- pkg/mom_fluxform/mom_fluxform.F:42-48, followed by the COMMON
+    /DYNVARS_R/ arrays uVel, vVel, wVel (in) and gU, gV (out) the routine works on."""
+    L = _lib.lib()
+    L.mom_fluxform_b200_(_i(bi), _i(bj), _i(k), _i(iMin), _i(iMax), _i(jMin), _i(jMax), _addr(kappaRU),
+                         _addr(kappaRV), _addr(fVerUkm), _addr(fVerVkm), _addr(fVerUkp), _addr(fVerVkp),
+                         _addr(guDiss), _addr(gvDiss), _d(myTime), _i(myIter), _i(myThid), _addr(uVel),
+                         _addr(vVel), _addr(wVel), _addr(gU), _addr(gV))
+    _check()
