@@ -31,13 +31,13 @@ enum {
   MG_RECIP_DXV, MG_RECIP_DYU, MG_RECIP_RA, MG_RECIP_RAW, MG_RECIP_RAS, MG_RECIP_RAZ,
   MG_FCORI, MG_FCORIG, MG_TANPHIATU, MG_TANPHIATV, MG_RECIP_BO, MG_BO_SURF,
   MG_AW2D, MG_AS2D, MG_AC2D, MG_PW, MG_PS, MG_PC,
-  MG_ETAN, MG_SURFFORCU, MG_SURFFORCV, MG_SURFFORCT,
+  MG_ETAN, MG_SURFFORCU, MG_SURFFORCV, MG_SURFFORCT, MG_CG2D_B, MG_CG2D_X,
   MG_N2D,
   /* 3-D tile arrays (Nr levels), GRID.h, DYNVARS.h */
   MG_HFACC = 100, MG_HFACW, MG_HFACS, MG_RECIP_HFACC, MG_RECIP_HFACW, MG_RECIP_HFACS,
   MG_MASKC, MG_MASKW, MG_MASKS,
   MG_UVEL, MG_VVEL, MG_WVEL, MG_THETA, MG_SALT, MG_GU, MG_GV, MG_GUNM1, MG_GVNM1,
-  MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART,
+  MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART, MG_THETA2,
   MG_N3D_END,
   /* (Nr+1)-level tile arrays */
   MG_KAPPARU = 200, MG_KAPPARV, MG_N3DP_END,
@@ -54,6 +54,7 @@ enum {
   MP_VISCAHD, MP_VISCAHZ, MP_VISCA4D, MP_VISCA4Z, MP_SIDEDRAGFACTOR, MP_BOTTOMDRAGLINEAR,
   MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
   MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
+  MP_DIFFKRT, MP_VISCAR,
   MP_ND,
   MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
   MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
@@ -61,6 +62,7 @@ enum {
   MI_SELECTIMPLICITDRAG, MI_USECDSCHEME, MI_SELECTCORISCHEME, MI_SELECTMETRICTERMS,
   MI_USINGSPHERICALPOLARGRID, MI_RIGIDLID, MI_SELECT_RSTAR, MI_IMPLICITDIFFUSION,
   MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
+  MI_TEMPSTEPPING, MI_NITER0,
   MI_NI_END
 };
 
@@ -81,6 +83,7 @@ void mitgcm_b200_set_param_i_(const int *id, const int *val, int *ierr);
 void mitgcm_b200_set_field_(const int *id, const double *host, int *ierr);
 void mitgcm_b200_get_field_(const int *id, double *host, int *ierr);
 double *mitgcm_b200_field_ptr(int id);
+void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr);   /* mirror := value */
 void mitgcm_b200_sync_(void);
 
 /* ---- CG2D / CG2D_SR ------------------------------------------------------------
@@ -129,6 +132,19 @@ void mom_fluxform_b200_(const int *bi, const int *bj, const int *k, const int *i
                         const double *myTime, const int *myIter, const int *myThid,
                         const double *uVel, const double *vVel, const double *wVel,
                         double *gU, double *gV);
+
+/* ---- resident time step ----------------------------------
+ * One model step on the device mirrors in the order of model/src/forward_step.F (non-staggered):
+ * THERMODYNAMICS (TEMP_INTEGRATE: CALC_ADV_FLOW + GAD_CALC_RHS + ADAMS_BASHFORTH2 + TIMESTEP_TRACER
+ * + CYCLE_TRACER), DYNAMICS (MOM_FLUXFORM + TIMESTEP), SOLVE_FOR_PRESSURE (CALC_DIV_GHAT + CG2D),
+ * MOMENTUM_CORRECTION_STEP, INTEGR_CONTINUITY, DO_FIELDS_BLOCKING_EXCHANGES.  State and forcing
+ * are the mirrors MG_UVEL.. MG_ETAN, MG_SURFFORCU/V; nothing crosses PCIe.  The solver scalars of
+ * the step are returned like SOLVE_FOR_PRESSURE prints them (solve_for_pressure.F:337-348). */
+void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg2d_iters,
+                               double *cg2d_last_res, int *ierr);
+/* EXCH_XYZ_RL / EXCH_XY_RL on a mirror (eesupp/src/exch_xyz_rx.template, exch_xy_rx.template):
+ * full-width halo with corners. */
+void mitgcm_b200_exch_(const int *id, int *ierr);
 
 #ifdef __cplusplus
 }

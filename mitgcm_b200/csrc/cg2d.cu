@@ -814,7 +814,7 @@ static bool ensure_ws(int maxIters) {
   return true;
 }
 
-static bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
+bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
                      double *lastResidual, int *numIters, int *nIterMin) {
   Ctx &c = ctx();
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");

@@ -211,6 +211,21 @@ void mitgcm_b200_get_field_(const int *id, double *host, int *ierr) {
   *ierr = 0;
 }
 
+__global__ void fill_kernel(double *p, size_t n, double v) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
+void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr) {
+  Ctx &c = ctx();
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  double *d = field(*id);
+  if (!d) return;
+  fill_kernel<<<c.numSMs * 8, 256, 0, c.stream>>>(d, field_elems(c.g, *id), *value);
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "fill_field"); return; }
+  *ierr = 0;
+}
+
 double *mitgcm_b200_field_ptr(int id) { return ctx().ready ? field(id) : nullptr; }
 
 void mitgcm_b200_sync_(void) {

@@ -67,7 +67,7 @@ __device__ __forceinline__ double mom_rTransV(const TileGrid &g, const MomState 
   return 0.5 * (MW(i, j - 1, kk) * g.rA[g.s(i, j - 1)] + MW(i, j, kk) * g.rA[g.s(i, j)]);
 }
 // MOM_U_ADV_WU / MOM_V_ADV_WV at interface kk
-__device__ double mom_adv_wu(const TileGrid &g, const MomState &st, const MomPar &p, int kk, int i, int j) {
+__device__ inline double mom_adv_wu(const TileGrid &g, const MomState &st, const MomPar &p, int kk, int i, int j) {
   if (kk > g.Nr || (kk == 1 && p.rigidLid)) return 0.;
   const double rT = mom_rTransU(g, st, kk, i, j);
   if (kk == 1) return rT * MU(i, j, kk);
@@ -78,7 +78,7 @@ __device__ double mom_adv_wu(const TileGrid &g, const MomState &st, const MomPar
                 MU(i, j, kk);
   return f;
 }
-__device__ double mom_adv_wv(const TileGrid &g, const MomState &st, const MomPar &p, int kk, int i, int j) {
+__device__ inline double mom_adv_wv(const TileGrid &g, const MomState &st, const MomPar &p, int kk, int i, int j) {
   if (kk > g.Nr || (kk == 1 && p.rigidLid)) return 0.;
   const double rT = mom_rTransV(g, st, kk, i, j);
   if (kk == 1) return rT * MV(i, j, kk);
@@ -114,7 +114,7 @@ __device__ __forceinline__ double mom_v_rvisc(const TileGrid &g, const MomState 
          g.maskS[g.s3(i, j, kk)] * g.maskS[g.s3(i, j, kk - 1)];
 }
 // MOM_U_DEL2U / MOM_V_DEL2V (zero outside 2-OL..sN+OL-1, like the zero-initialised v4F)
-__device__ double mom_del2u(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
+__device__ inline double mom_del2u(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
   if (!p.useBiharmonicVisc) return 0.;
   if (i < 2 - g.OLx || i > g.sNx + g.OLx - 1 || j < 2 - g.OLy || j > g.sNy + g.OLy - 1) return 0.;
   auto fZ = [&](int ii) {
@@ -134,7 +134,7 @@ __device__ double mom_del2u(const TileGrid &g, const MomState &st, const MomPar 
   }
   return d;
 }
-__device__ double mom_del2v(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
+__device__ inline double mom_del2v(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
   if (!p.useBiharmonicVisc) return 0.;
   if (i < 2 - g.OLx || i > g.sNx + g.OLx - 1 || j < 2 - g.OLy || j > g.sNy + g.OLy - 1) return 0.;
   auto fZ = [&](int ii) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ double mom_v_yvisc(const TileGrid &g, const MomState 
          g.recip_dyF[g.s(i, j)];
 }
 // MOM_U_SIDEDRAG / MOM_V_SIDEDRAG, sideDragFactor > 0 branch, constant viscosity
-__device__ double mom_u_sidedrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
+__device__ inline double mom_u_sidedrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
   double hS = g.hFacW[g.s3(i, j, k)] - mom_hfacz(g, k, i, j);
   double hN = g.hFacW[g.s3(i, j, k)] - mom_hfacz(g, k, i, j + 1);
   double t = p.viscAhZ * MU(i, j, k) - p.viscA4Z * mom_del2u(g, st, p, k, i, j);
@@ -188,7 +188,7 @@ __device__ double mom_u_sidedrag(const TileGrid &g, const MomState &st, const Mo
          (hS * g.dxV[g.s(i, j)] * g.recip_dyU[g.s(i, j)] * t + hN * g.dxV[g.s(i, j + 1)] * g.recip_dyU[g.s(i, j + 1)] * t) *
          g.drF[k - 1] * p.sideDragFactor;
 }
-__device__ double mom_v_sidedrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
+__device__ inline double mom_v_sidedrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j) {
   const double cf = g.cosFacV[j + g.OLy - 1];
   double hW = g.hFacS[g.s3(i, j, k)] - mom_hfacz(g, k, i, j);
   double hE = g.hFacS[g.s3(i, j, k)] - mom_hfacz(g, k, i + 1, j);
@@ -198,7 +198,7 @@ __device__ double mom_v_sidedrag(const TileGrid &g, const MomState &st, const Mo
          g.drF[k - 1] * p.sideDragFactor;
 }
 // MOM_U_BOTDRAG_COEFF / MOM_V_BOTDRAG_COEFF (z coordinates, inp_KE = .TRUE.)
-__device__ double mom_botdrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int isV, int i, int j) {
+__device__ inline double mom_botdrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int isV, int i, int j) {
   const int Nr = g.Nr;
   const double viscFac = p.no_slip_bottom ? 2. : 0.;
   const int kDown = min(k + 1, Nr), kLowF = k + 1;
@@ -245,7 +245,7 @@ struct MomOut { double gU, gV, guDiss, gvDiss; };
 
 // Tendencies of one cell (mom_fluxform.F:502-517, :602-662, :716-721, :757-772, :860-921,
 // :975-980, :995-1022, :1044-1051) given the vertical advective fluxes above (km) and below (kp).
-__device__ MomOut mom_cell(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j, double fVerUkm,
+__device__ inline MomOut mom_cell(const TileGrid &g, const MomState &st, const MomPar &p, int k, int i, int j, double fVerUkm,
                            double fVerUkp, double fVerVkm, double fVerVkp) {
   MomOut o;
   const double rhW = g.recip_hFacW[g.s3(i, j, k)], rhS = g.recip_hFacS[g.s3(i, j, k)], rdrF = g.recip_drF[k - 1];

@@ -1,0 +1,359 @@
+// step.cu -- resident model step: the glue either side of the hot path fused into the kernels
+// (SURVEY.md section 8(f) rank 1), in the order of model/src/forward_step.F (non-staggered).
+//   thermo_kernel : TEMP_INTEGRATE for k = Nr..1 per column: CALC_ADV_FLOW (calc_adv_flow.F) +
+//                   GAD_CALC_RHS (gad.cuh) + ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86) +
+//                   TIMESTEP_TRACER (timestep_tracer.F) + CYCLE_TRACER, vertical flux kept in a register
+//   dyn_kernel    : DYNAMICS for k = 1..Nr per column on 0..sN+1: MOM_FLUXFORM (mom.cuh) + TIMESTEP
+//                   (timestep.F:95-385: dissipation and surface stress inside AB, AB2, u* = u + dt G)
+//   rhs_kernel    : SOLVE_FOR_PRESSURE right-hand side (solve_for_pressure.F:120-238, calc_div_ghat.F:64-167)
+//   corr_kernel   : MOMENTUM_CORRECTION_STEP (calc_grad_phi_surf.F, correction_step.F:152-231) +
+//                   INTEGRATE_FOR_W (integrate_for_w.F), k = Nr..1 per column
+//   exch_kernel   : EXCH_XYZ_RL with corners on one periodic process (exch1_rx.template:170-201)
+// Assumptions of this driver (checked): linear free surface, implicSurfPress = implicDiv2DFlow = 1,
+// no CD scheme, z coordinates, buoyancy decoupled (dPhiHyd = 0), surface stress forcing only.
+#include "mom.cuh"
+
+namespace mg {
+
+bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
+              double *lastResidual, int *numIters, int *nIterMin);
+bool make_mom_par(MomPar &p);
+
+// ---- halo exchange ---------------------------------------------------------------------------
+// One pass: every halo cell (corners included) reads the interior cell it mirrors under the
+// periodic nSx x nSy tiling.  Equivalent to the X-then-Y sequence of EXCH1_RX because all sources
+// are interior cells.
+__global__ void exch_kernel(double *f, int nz, int sNx, int sNy, int OLx, int OLy, int nSx, int nSy) {
+  const int PX = sNx + 2 * OLx, PY = sNy + 2 * OLy;
+  const size_t slab = (size_t)PX * PY;
+  const int nHalo = PX * PY - sNx * sNy;
+  const size_t total = (size_t)nHalo * nz * nSx * nSy;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int h = (int)(t % nHalo);
+    size_t r = t / nHalo;
+    int k = (int)(r % nz);
+    int tile = (int)(r / nz);
+    // enumerate halo cells: south rows, north rows, then west/east columns of the middle rows
+    int ii, jj;
+    if (h < OLy * PX) { jj = h / PX; ii = h % PX; }
+    else if (h < 2 * OLy * PX) { int q = h - OLy * PX; jj = OLy + sNy + q / PX; ii = q % PX; }
+    else {
+      int q = h - 2 * OLy * PX;
+      jj = OLy + q / (2 * OLx);
+      int c = q % (2 * OLx);
+      ii = c < OLx ? c : sNx + c;
+    }
+    int bi = tile % nSx, bj = tile / nSx;
+    // global interior coordinates of the mirrored cell
+    int gi = bi * sNx + (ii - OLx), gj = bj * sNy + (jj - OLy);
+    const int Nx = sNx * nSx, Ny = sNy * nSy;
+    gi = ((gi % Nx) + Nx) % Nx;
+    gj = ((gj % Ny) + Ny) % Ny;
+    int sbi = gi / sNx, sbj = gj / sNy;
+    int si = gi - sbi * sNx + OLx, sj = gj - sbj * sNy + OLy;
+    size_t dst = (size_t)ii + (size_t)PX * jj + slab * ((size_t)k + (size_t)nz * tile);
+    size_t src = (size_t)si + (size_t)PX * sj + slab * ((size_t)k + (size_t)nz * (sbi + nSx * sbj));
+    f[dst] = f[src];
+  }
+}
+
+bool exch_field(double *f, int nz) {
+  Ctx &c = ctx();
+  const Geom &g = c.g;
+  if (g.nPx != 1 || g.nPy != 1) return fail(60, "exch: multi-process exchange goes through the distributed driver");
+  const size_t total = (size_t)(g.PX * g.PY - g.sNx * g.sNy) * nz * g.nTiles;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  exch_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(f, nz, g.sNx, g.sNy, g.OLx, g.OLy, g.nSx, g.nSy);
+  MG_CUDA(cudaGetLastError());
+  return true;
+}
+
+// ---- thermodynamics ---------------------------------------------------------------------------
+// CALC_ADV_FLOW fused: level-k transports derived from the resident 3-D state.
+struct FusedAcc {
+  TileGrid g;
+  const double *u, *v, *w, *T_, *kapT;
+  int k;
+  __device__ __forceinline__ double T(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
+  __device__ __forceinline__ double TA(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
+  __device__ __forceinline__ double xA(int i, int j) const { return g.dyG[g.s(i, j)] * g.drF[k - 1] * g.hFacW[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double yA(int i, int j) const { return g.dxG[g.s(i, j)] * g.drF[k - 1] * g.hFacS[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double uFld(int i, int j) const { return u[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double vFld(int i, int j) const { return v[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double wFld(int i, int j) const { return w[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double uTrans(int i, int j) const { return u[g.s3(i, j, k)] * xA(i, j); }
+  __device__ __forceinline__ double vTrans(int i, int j) const { return v[g.s3(i, j, k)] * yA(i, j); }
+  __device__ __forceinline__ double maskUpAt(int i, int j, int kk) const {
+    return kk == 1 ? 0. : g.maskC[g.s3(i, j, kk - 1)] * g.maskC[g.s3(i, j, kk)];
+  }
+  __device__ __forceinline__ double rTransAt(int i, int j, int kk) const {
+    return kk == 1 ? 0. : w[g.s3(i, j, kk)] * g.rA[g.s(i, j)] * maskUpAt(i, j, kk);
+  }
+  __device__ __forceinline__ double maskUp(int i, int j) const { return maskUpAt(i, j, k); }
+  __device__ __forceinline__ double rTrans(int i, int j) const { return rTransAt(i, j, k); }
+  __device__ __forceinline__ double rTransKp1(int i, int j) const { return k == g.Nr ? 0. : rTransAt(i, j, k + 1); }
+  __device__ __forceinline__ double KappaR(int i, int j) const { return kapT[g.s3(i, j, k)]; }
+};
+
+__global__ void __launch_bounds__(128) thermo_kernel(TileGrid g, const double *u, const double *v, const double *w,
+                                                     const double *theta, const double *kapT, double *thetaNew,
+                                                     double *gtNm1, GadPar p0, double abFac) {
+  const int i = 1 + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx || j > g.sNy) return;
+  FusedAcc a{g, u, v, w, theta, kapT, 0};
+  GadPar p = p0;
+  double fVdn = 0.;   // fVer(kDown): flux left by level k+1 (zero below the bottom level, temp_integrate.F:211-215)
+  for (int k = g.Nr; k >= 1; k--) {
+    a.k = k;
+    p.k = k;
+    const double fz0 = gad_fzon(g, a, p, i, j), fz1 = gad_fzon(g, a, p, i + 1, j);
+    const double fm0 = gad_fmer(g, a, p, i, j), fm1 = gad_fmer(g, a, p, i, j + 1);
+    const double fvu = gad_fver(g, a, p, i, j);
+    double gT = gad_tendency(g, a, p, i, j, 0., fz0, fz1, fm0, fm1, fvu, fVdn);
+    const size_t s3 = g.s3(i, j, k);
+    const double ab = abFac * (gT - gtNm1[s3]);            // ADAMS_BASHFORTH2
+    gtNm1[s3] = gT;
+    gT = gT + ab;
+    thetaNew[s3] = theta[s3] + p.deltaT * gT;              // TIMESTEP_TRACER + CYCLE_TRACER
+    fVdn = fvu;
+  }
+}
+
+// ---- dynamics ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
+                                                  double *gU, double *gV, double *guNm1, double *gvNm1,
+                                                  double deltaTMom, double abFac, int momForcing, int dissInAB) {
+  const int i = blockIdx.x * 32 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
+  const int j = blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx + 1 || j > g.sNy + 1) return;
+  double ukm = 0., vkm = 0.;
+  if (p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
+  const size_t s = g.s(i, j);
+  for (int k = 1; k <= g.Nr; k++) {
+    double ukp = 0., vkp = 0.;
+    if (p.momAdvection) { ukp = mom_adv_wu(g, st, p, k + 1, i, j); vkp = mom_adv_wv(g, st, p, k + 1, i, j); }
+    MomOut o = mom_cell(g, st, p, k, i, j, ukm, ukp, vkm, vkp);
+    const size_t s3 = g.s3(i, j, k);
+    double gu = o.gU, gv = o.gV;
+    // timestep.F:120-121 with dPhiHydX = dPhiHydY = 0 (buoyancy decoupled): gU - phFac*0
+    gu = gu - 0.; gv = gv - 0.;
+    if (p.momViscosity && dissInAB) { gu = gu + o.guDiss; gv = gv + o.gvDiss; }
+    if (momForcing) {       // apply_forcing.F:142-148: surface stress in the top level
+      double ge = 0., he = 0.;
+      if (k == 1) {
+        if (i >= 1 && i <= g.sNx + 1) ge = 0. + sfU[s] * g.recip_drF[0] * g.recip_hFacW[s3];
+        if (j >= 1 && j <= g.sNy + 1) he = 0. + sfV[s] * g.recip_drF[0] * g.recip_hFacS[s3];
+      }
+      gu = gu + ge; gv = gv + he;
+    }
+    double ab = abFac * (gu - guNm1[s3]);                  // ADAMS_BASHFORTH2
+    guNm1[s3] = gu;
+    gu = gu + ab;
+    ab = abFac * (gv - gvNm1[s3]);
+    gvNm1[s3] = gv;
+    gv = gv + ab;
+    if (p.momViscosity && !dissInAB) { gu = gu + o.guDiss; gv = gv + o.gvDiss; }
+    gU[s3] = st.u[s3] + deltaTMom * (gu + 0.) * g.maskW[s3];   // timestep.F:375-384
+    gV[s3] = st.v[s3] + deltaTMom * (gv + 0.) * g.maskS[s3];
+    ukm = ukp; vkm = vkp;
+  }
+}
+
+// ---- surface pressure right-hand side -----------------------------------------------------------
+__global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *gU, const double *gV, const double *etaN,
+                                                  const double *Bo_surf, double *cg2d_b, double *cg2d_x,
+                                                  double deltaTMom, double deltaTFreeSurf, double freeSurfFac) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j);
+  cg2d_x[s] = Bo_surf[s] * etaN[s];                       // solve_for_pressure.F:129 (full halo range)
+  double b = 0.;
+  if (i >= 1 && i <= g.sNx && j >= 1 && j <= g.sNy) {
+    for (int k = g.Nr; k >= 1; k--) {
+      auto pfx = [&](int ii) { return g.dyG[g.s(ii, j)] * g.drF[k - 1] * g.hFacW[g.s3(ii, j, k)] * gU[g.s3(ii, j, k)] / deltaTMom; };
+      auto pfy = [&](int jj) { return g.dxG[g.s(i, jj)] * g.drF[k - 1] * g.hFacS[g.s3(i, jj, k)] * gV[g.s3(i, jj, k)] / deltaTMom; };
+      b = b + pfx(i + 1) - pfx(i);
+      b = b + pfy(j + 1) - pfy(j);
+    }
+    b = b - freeSurfFac * g.rA[s] / deltaTMom / deltaTFreeSurf * etaN[s];
+  }
+  cg2d_b[s] = b;
+}
+
+__global__ void eta_kernel(size_t n, const double *recip_Bo, const double *x, double *etaN) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < n) etaN[t] = recip_Bo[t] * x[t];               // solve_for_pressure.F:377-385
+}
+
+// ---- correction step + continuity ---------------------------------------------------------------
+__global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *gU, const double *gV, const double *etaN,
+                                                   const double *Bo_surf, double *uVel, double *vVel, double *wVel,
+                                                   double deltaTMom, double implicSurfPress, int rigidLid) {
+  const int i = 1 + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx || j > g.sNy) return;
+  const double psFac = 1. * implicSurfPress;
+  auto phiX = [&](int ii) { return g.recip_dxC[g.s(ii, j)] * (Bo_surf[g.s(ii, j)] * etaN[g.s(ii, j)] - Bo_surf[g.s(ii - 1, j)] * etaN[g.s(ii - 1, j)]); };
+  auto phiY = [&](int jj) { return g.recip_dyC[g.s(i, jj)] * (Bo_surf[g.s(i, jj)] * etaN[g.s(i, jj)] - Bo_surf[g.s(i, jj - 1)] * etaN[g.s(i, jj - 1)]); };
+  const double px0 = phiX(i), px1 = phiX(i + 1), py0 = phiY(j), py1 = phiY(j + 1);
+  double wKp1 = 0.;
+  for (int k = g.Nr; k >= 1; k--) {
+    auto uNew = [&](int ii, double px) {
+      size_t q = g.s3(ii, j, k);
+      double dpx = -psFac * px * g.maskW[q];
+      return (gU[q] + deltaTMom * dpx) * g.maskW[q];
+    };
+    auto vNew = [&](int jj, double py) {
+      size_t q = g.s3(i, jj, k);
+      double dpy = -psFac * py * g.maskS[q];
+      return (gV[q] + deltaTMom * dpy) * g.maskS[q];
+    };
+    const double u0 = uNew(i, px0), u1 = uNew(i + 1, px1), v0 = vNew(j, py0), v1 = vNew(j + 1, py1);
+    const size_t s3 = g.s3(i, j, k);
+    uVel[s3] = u0;
+    vVel[s3] = v0;
+    // INTEGRATE_FOR_W
+    const double uT0 = u0 * g.dyG[g.s(i, j)] * g.drF[k - 1] * g.hFacW[s3];
+    const double uT1 = u1 * g.dyG[g.s(i + 1, j)] * g.drF[k - 1] * g.hFacW[g.s3(i + 1, j, k)];
+    const double vT0 = v0 * g.dxG[g.s(i, j)] * g.drF[k - 1] * g.hFacS[s3];
+    const double vT1 = v1 * g.dxG[g.s(i, j + 1)] * g.drF[k - 1] * g.hFacS[g.s3(i, j + 1, k)];
+    const double conv2d = -(uT1 - uT0 + vT1 - vT0);
+    double wv;
+    if (rigidLid) {
+      if (k == 1) wv = 0.;
+      else if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * g.maskC[s3] * g.maskC[g.s3(i, j, k - 1)];
+      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * g.maskC[s3] * g.maskC[g.s3(i, j, k - 1)];
+    } else {
+      if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * g.maskC[s3];
+      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * g.maskC[s3];
+    }
+    wVel[s3] = wv;
+    wKp1 = wv;
+  }
+}
+
+static bool forward_step(int myIter, double *initRes, int *iters, double *lastRes) {
+  Ctx &c = ctx();
+  if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
+  const Geom &g = c.g;
+  const Params &q = c.p;
+  if (q.D(MP_IMPLICSURFPRESS) != 1.0 || q.D(MP_IMPLICDIV2DFLOW) != 1.0 || q.I(MI_USECDSCHEME))
+    return fail(61, "forward_step: needs implicSurfPress = implicDiv2DFlow = 1 and no CD scheme");
+  MomPar mp;
+  if (!make_mom_par(mp)) return false;
+  const double abFac = (myIter == q.I(MI_NITER0)) ? 0.0 : 0.5 + q.D(MP_ABEPS);
+  double *u = field(MG_UVEL), *v = field(MG_VVEL), *w = field(MG_WVEL);
+  double *gU = field(MG_GU), *gV = field(MG_GV), *guN = field(MG_GUNM1), *gvN = field(MG_GVNM1);
+  double *eta = field(MG_ETAN), *b = field(MG_CG2D_B), *x = field(MG_CG2D_X);
+  double *sfU = field(MG_SURFFORCU), *sfV = field(MG_SURFFORCV), *Bo = field(MG_BO_SURF), *rBo = field(MG_RECIP_BO);
+  double *kapU = field(MG_KAPPARU), *kapV = field(MG_KAPPARV);
+  if (!u || !v || !w || !gU || !gV || !guN || !gvN || !eta || !b || !x || !sfU || !sfV || !Bo || !rBo || !kapU || !kapV) return false;
+  const size_t ns = g.slab;
+  dim3 blk(32, 4);
+  // THERMODYNAMICS
+  if (q.I(MI_TEMPSTEPPING)) {
+    double *th = field(MG_THETA), *th2 = field(MG_THETA2), *gtN = field(MG_GTNM1), *kapT = field(MG_KAPPART);
+    if (!th || !th2 || !gtN || !kapT) return false;
+    GadPar p;
+    p.k = 0; p.advScheme = q.I(MI_TEMPADVSCHEME); p.vertAdvScheme = q.I(MI_TEMPVERTADVSCHEME);
+    p.calcAdvection = 1; p.implicitAdvection = 0; p.applyAB = 0; p.useDiffKr4 = 0;
+    p.implicitDiffusion = q.I(MI_IMPLICITDIFFUSION);
+    p.diffKh = q.D(MP_DIFFKHT); p.diffK4 = q.D(MP_DIFFK4T); p.rkSign = q.D(MP_RKSIGN);
+    p.deltaT = q.D(MP_DELTATTRACER); p.diffKr4k = 0.;
+    dim3 grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
+        thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
+      }
+    MG_CUDA(cudaGetLastError());
+    // CYCLE_TRACER: theta <- theta** (interior); halos follow in the blocking exchange below
+    std::swap(c.fields[MG_THETA], c.fields[MG_THETA2]);
+  }
+  // DYNAMICS
+  {
+    dim3 grd((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
+        size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
+        MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
+        dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+                                              q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+      }
+    MG_CUDA(cudaGetLastError());
+  }
+  // SOLVE_FOR_PRESSURE
+  {
+    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
+        size_t o3 = ns * g.Nr * t, o2 = ns * t;
+        rhs_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
+                                              q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC));
+      }
+    MG_CUDA(cudaGetLastError());
+    int numIters = q.I(MI_CG2DMAXITERS), nIterMin = q.I(MI_CG2DUSEMINRESSOL) - 1;
+    double first, minsq, last;
+    if (!cg2d_run(q.I(MI_USESRCGSOLVER) != 0, b, x, &first, &minsq, &last, &numIters, &nIterMin)) return false;
+    *initRes = first; *iters = numIters; *lastRes = last;
+    if (!exch_field(x, 1)) return false;
+    eta_kernel<<<(unsigned)((g.n2 + 255) / 256), 256, 0, c.stream>>>(g.n2, rBo, x, eta);
+    MG_CUDA(cudaGetLastError());
+  }
+  // MOMENTUM_CORRECTION_STEP + INTEGR_CONTINUITY
+  {
+    dim3 grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
+        size_t o3 = ns * g.Nr * t, o2 = ns * t;
+        corr_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
+                                               q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS), q.I(MI_RIGIDLID));
+      }
+    MG_CUDA(cudaGetLastError());
+  }
+  // DO_FIELDS_BLOCKING_EXCHANGES
+  if (!exch_field(u, g.Nr) || !exch_field(v, g.Nr) || !exch_field(w, g.Nr)) return false;
+  if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
+  return true;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg2d_iters, double *cg2d_last_res,
+                               int *ierr) {
+  ctx().lastError = 0;
+  *ierr = forward_step(*myIter, cg2d_init_res, cg2d_iters, cg2d_last_res) ? 0 : 1;
+}
+
+void mitgcm_b200_exch_(const int *id, int *ierr) {
+  Ctx &c = ctx();
+  c.lastError = 0;
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  double *f = field(*id);
+  if (!f) return;
+  int nz = (*id >= 0 && *id < MG_N2D) ? 1 : (*id >= 100 && *id < MG_N3D_END) ? c.g.Nr : (*id >= 200 && *id < MG_N3DP_END) ? c.g.Nr + 1 : 0;
+  if (nz == 0) { fail(2, "exch: not a tile array"); return; }
+  if (!exch_field(f, nz)) return;
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "exch: stream error"); return; }
+  *ierr = 0;
+}
+
+}  // extern "C"

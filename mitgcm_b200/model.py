@@ -1,0 +1,113 @@
+"""Resident model driver: the synthetic doubly-periodic channel of BASELINE.json (config 5) and
+its small-grid variants, stepping entirely on the device through the C ABI
+(mitgcm_b200_forward_step_).  Set-up mirrors what the Fortran model has done before the first
+FORWARD_STEP: grid, masks, INI_CG2D operator, initial fields and forcing in the mirrors."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import runtime as rt
+from .grid import Dims, Grid, cartesian_grid, masks_from_depth, exch_xyz, global_area
+
+DEFAULTS = dict(deltaTMom=1200.0, deltaTFreeSurf=1200.0, deltaTtracer=1200.0, abEps=0.01,
+                viscAhD=400.0, viscAhZ=400.0, viscAr=1e-2, diffKhT=1e3, diffK4T=0.0, diffKrT=1e-5,
+                no_slip_sides=1, no_slip_bottom=1, sideDragFactor=2.0, selectBotDragQuadr=-1,
+                tempAdvScheme=2, tempStepping=1, cg2dTargetResidual=1e-7, cg2dMaxIters=1000,
+                momForcing=1, momDissip_In_AB=1, useSRCGSolver=0)
+
+LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z sideDragFactor bottomDragLinear "
+              "bottomDragQuadratic no_slip_sides no_slip_bottom bottomVisc_pCell selectBotDragQuadr "
+              "useBiharmonicVisc implicitViscosity selectCoriScheme rigidLid momAdvection momViscosity "
+              "diffKhT diffK4T diffKrT viscAr tempStepping cg2dMaxIters momForcing momDissip_In_AB "
+              "implicitDiffusion useSRCGSolver").split()
+
+
+def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
+    """Initial state and forcing of the synthetic channel: smooth multi-mode
+    flow of 0.1 m/s + noise, theta = tRef(k) + 0.1 N(0,1), eta = 0.1 sin cos, zonal wind stress
+    -tau0 cos(2 pi y / Ly).  Generated per global index, so any tiling sees the same field."""
+    d = g.d
+    rng = np.random.default_rng(seed)
+    Nx, Ny, Nr = d.Nx, d.Ny, d.Nr
+    X = (np.arange(Nx) + 0.5) / Nx
+    Y = (np.arange(Ny) + 0.5) / Ny
+    YY, XX = np.meshgrid(Y, X, indexing="ij")
+    psi_u = 0.1 * np.sin(2 * np.pi * XX) * np.cos(4 * np.pi * YY) + 0.03 * np.cos(6 * np.pi * XX) * np.sin(2 * np.pi * YY)
+    psi_v = 0.1 * np.cos(2 * np.pi * XX) * np.sin(4 * np.pi * YY) - 0.03 * np.sin(6 * np.pi * XX) * np.cos(2 * np.pi * YY)
+    glob = {
+        "uVel": psi_u[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * rng.standard_normal((Nr, Ny, Nx)),
+        "vVel": psi_v[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * rng.standard_normal((Nr, Ny, Nx)),
+        "theta": np.linspace(20.0, 2.0, Nr)[:, None, None] + 0.1 * rng.standard_normal((Nr, Ny, Nx)),
+    }
+    eta = 0.1 * np.sin(2 * np.pi * XX) * np.cos(2 * np.pi * YY)
+    tau = -tau0 * np.cos(2 * np.pi * YY)
+
+    def tile(a3):
+        out = np.zeros((d.nSy, d.nSx) + a3.shape[:-2] + (d.PY, d.PX))
+        for bj in range(d.nSy):
+            for bi in range(d.nSx):
+                out[bj, bi, ..., d.OLy:d.OLy + d.sNy, d.OLx:d.OLx + d.sNx] = \
+                    a3[..., bj * d.sNy:(bj + 1) * d.sNy, bi * d.sNx:(bi + 1) * d.sNx]
+        return exch_xyz(d, out)
+    s = {k: tile(v) for k, v in glob.items()}
+    s["uVel"] *= g.maskW
+    s["vVel"] *= g.maskS
+    s["theta"] *= g.maskC
+    s["wVel"] = np.zeros(d.shape3)
+    s["etaN"] = tile(eta) * g.maskC[:, :, 0]
+    s["surfForcU"] = tile(tau) * (1.0 / rhoConst)
+    s["surfForcV"] = np.zeros(d.shape2)
+    return s
+
+
+def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=0.0, seed=20261018, **params):
+    d = Dims(sNx=sNx, sNy=sNy, OLx=OL, OLy=OL, nSx=nSx, nSy=nSy, Nr=Nr)
+    g = cartesian_grid(d, [dx] * d.Nx, [dx] * d.Ny, [dz] * Nr, f0=1e-4, beta=1e-11, gBaro=9.81)
+    rng = np.random.default_rng(seed + 1)
+    depth = -dz * Nr * np.ones((d.Ny, d.Nx))
+    if land_frac > 0:
+        for _ in range(max(1, int(land_frac * 40))):      # rectangular islands
+            j0, i0 = rng.integers(0, d.Ny), rng.integers(0, d.Nx)
+            h, w = rng.integers(1, max(2, d.Ny // 6)), rng.integers(1, max(2, d.Nx // 6))
+            depth[j0:j0 + h, i0:i0 + w] = 0.0
+        depth *= 0.4 + 0.6 * rng.random(depth.shape)       # partial cells
+    masks_from_depth(g, depth, hFacMin=0.2 if land_frac > 0 else 1.0)
+    P = dict(DEFAULTS)
+    P.update(params)
+    P["globalArea"] = global_area(g)
+    return g, P, channel_state(g, seed)
+
+
+class Model:
+    """Device-resident model: Model(grid, params, state).step() == one FORWARD_STEP."""
+
+    def __init__(self, g: Grid, P: dict, state: dict, op: dict, device=-1):
+        self.g, self.d, self.P = g, g.d, P
+        rt.init(g.d, device)
+        rt.set_grid(g)
+        rt.set_params(**{k: P[k] for k in LIB_PARAMS if k in P})
+        rt.set_params(deltaTtracer=P.get("deltaTtracer", P["deltaTMom"]), tempAdvScheme=P.get("tempAdvScheme", 2),
+                      tempVertAdvScheme=P.get("tempAdvScheme", 2), nIter0=0)
+        rt.set_cg2d_operator(op)
+        for n, fid in (("uVel", "uVel"), ("vVel", "vVel"), ("wVel", "wVel"), ("theta", "theta"), ("etaN", "etaN"),
+                       ("surfForcU", "surfForcU"), ("surfForcV", "surfForcV")):
+            rt.set_field(fid, np.ascontiguousarray(state[n]))
+        rt.fill_field("kappaRU", P.get("viscAr", 0.0))
+        rt.fill_field("kappaRV", P.get("viscAr", 0.0))
+        rt.fill_field("kappaRT", P.get("diffKrT", 0.0))
+        for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1", "theta2", "cg2d_b", "cg2d_x"):
+            rt.fill_field(n, 0.0)
+        self.it = 0
+
+    def step(self):
+        r = rt.forward_step(self.it)
+        self.it += 1
+        return r
+
+    def get(self, name):
+        d = self.d
+        shape = d.shape2 if rt.field_id(name) < 100 else d.shape3
+        return rt.get_field(name, np.zeros(shape))
+
+    def close(self):
+        rt.finalize()

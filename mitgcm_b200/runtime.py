@@ -174,3 +174,25 @@ def mom_fluxform(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, f
                          _addr(guDiss), _addr(gvDiss), _d(myTime), _i(myIter), _i(myThid), _addr(uVel),
                          _addr(vVel), _addr(wVel), _addr(gU), _addr(gV))
     _check()
+
+
+def fill_field(name: str, value: float):
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_fill_field_(C.byref(C.c_int(field_id(name))), _d(value), C.byref(ierr))
+    _check(ierr)
+
+
+def exch(name: str):
+    """_EXCH_XY_RL / _EXCH_XYZ_RL on a device mirror."""
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_exch_(C.byref(C.c_int(field_id(name))), C.byref(ierr))
+    _check(ierr)
+
+
+def forward_step(myIter: int):
+    """One FORWARD_STEP on the resident state; returns the three numbers SOLVE_FOR_PRESSURE
+    prints (cg2d_init_res, cg2d_iters, cg2d_last_res)."""
+    f, l, n, ierr = C.c_double(), C.c_double(), C.c_int(), C.c_int(0)
+    _lib.lib().mitgcm_b200_forward_step_(_i(myIter), C.byref(f), C.byref(n), C.byref(l), C.byref(ierr))
+    _check(ierr)
+    return dict(firstResidual=f.value, numIters=n.value, lastResidual=l.value)

@@ -1,0 +1,113 @@
+"""Oracle model step for Nr-level Cartesian configurations with one passive/active tracer.
+
+TEST INFRASTRUCTURE ONLY.  Same sequence as barotropic_gyre.py (which is pinned to the
+reference's golden output) extended by TEMP_INTEGRATE (temp_integrate.F:296-540: CALC_ADV_FLOW,
+GAD_CALC_RHS, ADAMS_BASHFORTH2, TIMESTEP_TRACER, CYCLE_TRACER) in the forward_step.F order:
+THERMODYNAMICS, DYNAMICS, SOLVE_FOR_PRESSURE, MOMENTUM_CORRECTION_STEP, INTEGR_CONTINUITY,
+DO_FIELDS_BLOCKING_EXCHANGES.  Used as the checker of the resident CUDA step and as the CPU
+baseline of bench.py.  Tiles are processed by a thread pool (the reference's parallelism)."""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from .pyoracle import Oracle
+
+
+class ChannelOracle:
+    def __init__(self, grid, params, state, threads=1):
+        """params: dict with the Oracle params plus abEps, deltaTtracer, diffKhT, diffK4T, diffKrT,
+        viscAr, tempAdvScheme, tempStepping, cg2dMaxIters, momForcing, momDissip_In_AB.
+        state: dict of numpy arrays uVel vVel wVel theta etaN surfForcU surfForcV (copied)."""
+        self.g, self.d = grid, grid.d
+        self.P = dict(abEps=0.01, deltaTtracer=params.get("deltaTMom", 1200.0), diffKhT=0.0, diffK4T=0.0,
+                      diffKrT=0.0, viscAr=0.0, tempAdvScheme=2, tempStepping=1, cg2dMaxIters=150,
+                      momForcing=1, momDissip_In_AB=1, useSRCGSolver=0)
+        extra = {k: params[k] for k in list(params) if k in self.P}
+        self.P.update(extra)
+        self.o = Oracle(grid, {k: v for k, v in params.items() if k not in self.P})
+        self.op = self.o.ini_cg2d()
+        d = self.d
+        self.s = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in state.items()}
+        for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1"):
+            self.s[n] = np.zeros(d.shape3)
+        self.kapU = np.full((d.Nr + 1, d.PY, d.PX), float(self.P["viscAr"]))
+        self.kapT = np.full((d.PY, d.PX), float(self.P["diffKrT"]))
+        self.threads = threads
+        self.it = 0
+
+    def _tiles(self):
+        return [(bi, bj) for bj in range(1, self.d.nSy + 1) for bi in range(1, self.d.nSx + 1)]
+
+    def _map(self, fn):
+        if self.threads > 1 and len(self._tiles()) > 1:
+            with ThreadPoolExecutor(self.threads) as ex:
+                list(ex.map(fn, self._tiles()))
+        else:
+            for t in self._tiles():
+                fn(t)
+
+    def step(self):
+        d, o, s, P = self.d, self.o, self.s, self.P
+        ns = (d.PY, d.PX)
+        abFac = 0.0 if self.it == 0 else 0.5 + P["abEps"]
+        dT = np.full(d.Nr, float(P["deltaTtracer"]))
+        zr = np.zeros(d.Nr)
+
+        def thermo(t):
+            bi, bj = t
+            ti = (bj - 1, bi - 1)
+            gT = np.zeros((d.Nr,) + ns)
+            fV = np.zeros((2,) + ns)
+            rTrans = np.zeros(ns)
+            sl = {n: np.zeros(ns) for n in "xA yA maskUp uFld vFld wFld uTrans vTrans rTransKp1 fZon fMer".split()}
+            theta = np.ascontiguousarray(s["theta"][ti])
+            for k in range(d.Nr, 0, -1):
+                kUp, kDown = 1 + (k + 1) % 2, 1 + k % 2
+                o.calc_adv_flow(bi, bj, k, s["uVel"], s["vVel"], s["wVel"], sl["xA"], sl["yA"], sl["maskUp"],
+                                sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans, sl["rTransKp1"])
+                o.gad_calc_rhs(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, max(1, k - 1), kUp, kDown, sl["xA"], sl["yA"],
+                               sl["maskUp"], sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans,
+                               sl["rTransKp1"], P["diffKhT"], P["diffK4T"], self.kapT, zr, theta, theta, dT,
+                               P["tempAdvScheme"], P["tempAdvScheme"], 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
+                # ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86)
+                gNm1 = s["gtNm1"][ti][k - 1]
+                ab = abFac * (gT[k - 1] - gNm1)
+                gNm1[...] = gT[k - 1]
+                gT[k - 1] = gT[k - 1] + ab
+            # TIMESTEP_TRACER + CYCLE_TRACER
+            s["theta"][ti] = theta + dT[:, None, None] * gT
+
+        def dyn(t):
+            bi, bj = t
+            fU, fVv = np.zeros((2,) + ns), np.zeros((2,) + ns)
+            z = np.zeros(ns)
+            for k in range(1, d.Nr + 1):
+                kUp, kDown = 1 + (k + 1) % 2, 1 + k % 2
+                gd, hd = np.zeros(ns), np.zeros(ns)
+                o.mom_fluxform(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, self.kapU, self.kapU, fU[kUp - 1], fVv[kUp - 1],
+                               fU[kDown - 1], fVv[kDown - 1], gd, hd, s["uVel"], s["vVel"], s["wVel"], s["gU"], s["gV"])
+                o.timestep(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, z, z, gd, hd, s["surfForcU"], s["surfForcV"],
+                           P["momForcing"], P["momDissip_In_AB"], abFac, s["uVel"], s["vVel"], s["gU"], s["gV"],
+                           s["guNm1"], s["gvNm1"])
+
+        if P["tempStepping"]:
+            self._map(thermo)
+        self._map(dyn)
+        b, x = np.zeros(d.shape2), np.zeros(d.shape2)
+        self._map(lambda t: o.solve_rhs(t[0], t[1], s["etaN"], s["gU"], s["gV"], b, x))
+        res = o.cg2d(self.op, b, x, int(P["cg2dMaxIters"]), -1, sr=bool(P["useSRCGSolver"]))
+        o.exch_xyz(x)
+        s["etaN"] = self.g.recip_Bo * x
+
+        def corr(t):
+            o.correction_step(t[0], t[1], s["etaN"], s["gU"], s["gV"], s["uVel"], s["vVel"])
+            o.integrate_for_w(t[0], t[1], s["uVel"], s["vVel"], s["wVel"])
+        self._map(corr)
+        for n in ("uVel", "vVel", "wVel"):
+            o.exch_xyz(s[n], d.Nr)
+        if P["tempStepping"]:
+            o.exch_xyz(s["theta"], d.Nr)
+        self.it += 1
+        return res
