@@ -62,7 +62,7 @@ enum {
   MI_SELECTIMPLICITDRAG, MI_USECDSCHEME, MI_SELECTCORISCHEME, MI_SELECTMETRICTERMS,
   MI_USINGSPHERICALPOLARGRID, MI_RIGIDLID, MI_SELECT_RSTAR, MI_IMPLICITDIFFUSION,
   MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
-  MI_TEMPSTEPPING, MI_NITER0,
+  MI_TEMPSTEPPING, MI_NITER0, MI_PROFILE,
   MI_NI_END
 };
 
@@ -85,6 +85,15 @@ void mitgcm_b200_get_field_(const int *id, double *host, int *ierr);
 double *mitgcm_b200_field_ptr(int id);
 void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr);   /* mirror := value */
 void mitgcm_b200_sync_(void);
+/* Timing on the library's own stream (CUDA events), for bench.py: record event `slot`
+ * (0..15) / elapsed milliseconds between two recorded slots (synchronises on the later one). */
+void mitgcm_b200_event_record_(const int *slot);
+void mitgcm_b200_event_elapsed_ms_(const int *slotA, const int *slotB, double *ms);
+/* Number of kernels the library has launched since init (bench.py's gpu_launches). */
+long long mitgcm_b200_launch_count_(void);
+/* Per-phase device time of the last forward step when MI_PROFILE != 0, milliseconds:
+ * {thermo, dyn, rhs, cg2d, eta+exch(x), corr, exchanges}. */
+void mitgcm_b200_step_timings_(double *ms7);
 
 /* ---- CG2D / CG2D_SR ------------------------------------------------------------
  * Same argument list as SUBROUTINE CG2D (model/src/cg2d.F:13-17) and CG2D_SR

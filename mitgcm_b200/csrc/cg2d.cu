@@ -859,6 +859,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   size_t bytes = g.n2 * sizeof(double);
   for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->v}) MG_CUDA(cudaMemsetAsync(p, 0, bytes, c.stream));
   void *args[] = {&a};
+  c.launches++;
   MG_CUDA(cudaLaunchCooperativeKernel(sr ? (void *)cg2d_sr_kernel : (void *)cg2d_kernel, dim3(blocks), dim3(CG_THREADS),
                                       args, 0, c.stream));
   Cg2dOut out;

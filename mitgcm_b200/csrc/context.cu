@@ -166,6 +166,9 @@ void mitgcm_b200_finalize_(void) {
   if (c.pushTab) cudaFree(c.pushTab);
   c.pushTab = nullptr;
   cg2d_free_workspace();
+  for (auto &e : c.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto &e : c.pev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  c.launches = 0;
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   c.ready = false;
@@ -221,12 +224,30 @@ void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr) {
   if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
   double *d = field(*id);
   if (!d) return;
+  c.launches++;
   fill_kernel<<<c.numSMs * 8, 256, 0, c.stream>>>(d, field_elems(c.g, *id), *value);
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "fill_field"); return; }
   *ierr = 0;
 }
 
 double *mitgcm_b200_field_ptr(int id) { return ctx().ready ? field(id) : nullptr; }
+
+void mitgcm_b200_event_record_(const int *slot) {
+  Ctx &c = ctx();
+  if (!c.ready || *slot < 0 || *slot >= 16) return;
+  if (!c.ev[*slot]) cudaEventCreate(&c.ev[*slot]);
+  cudaEventRecord(c.ev[*slot], c.stream);
+}
+void mitgcm_b200_event_elapsed_ms_(const int *a, const int *b, double *ms) {
+  Ctx &c = ctx();
+  *ms = -1.0;
+  if (!c.ready || !c.ev[*a] || !c.ev[*b]) return;
+  cudaEventSynchronize(c.ev[*b]);
+  float f = 0.f;
+  if (cudaEventElapsedTime(&f, c.ev[*a], c.ev[*b]) == cudaSuccess) *ms = f;
+}
+long long mitgcm_b200_launch_count_(void) { return ctx().launches; }
+void mitgcm_b200_step_timings_(double *ms7) { for (int i = 0; i < 7; i++) ms7[i] = ctx().stepMs[i]; }
 
 void mitgcm_b200_sync_(void) {
   if (ctx().ready) cudaStreamSynchronize(ctx().stream);

@@ -47,6 +47,10 @@ struct Ctx {
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;
+  long long launches = 0;
+  cudaEvent_t ev[16] = {};
+  cudaEvent_t pev[8] = {};
+  double stepMs[7] = {};
 };
 
 Ctx &ctx();

@@ -160,6 +160,7 @@ extern "C" void gad_calc_rhs_b200_(
   p.deltaT = deltaTLev[K - 1];
   p.diffKr4k = *trUseDiffKr4 ? diffKr4[K - 1] : 0.0;
   dim3 blk(32, 8), grd((g.PX + 31) / 32, (g.PY + 7) / 8);
+  c.launches++;
   gad_level_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, fZ, fM, fV + ns * (*kUp - 1), fV + ns * (*kDown - 1), gT);
   if (cudaGetLastError() != cudaSuccess) { fail(5, "gad_level_kernel launch failed"); return; }
   if (!from_device(fZon, fZ, ns) || !from_device(fMer, fM, ns)) return;

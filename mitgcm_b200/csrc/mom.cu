@@ -123,6 +123,7 @@ extern "C" void mom_fluxform_b200_(const int *bi, const int *bj, const int *k, c
     cudaMemcpyAsync(dgV + off3 + ns * (K - 1), gV + off3 + ns * (K - 1), ns * sizeof(double), cudaMemcpyHostToDevice, c.stream);
   }
   dim3 blk(32, 8), grd((g.PX + 31) / 32, (g.PY + 7) / 8);
+  c.launches++;
   mom_level_kernel<<<grd, blk, 0, c.stream>>>(tg, st, p, K, *iMin, *iMax, *jMin, *jMax, slabD[0], slabD[1], slabD[2],
                                               slabD[3], slabD[4], slabD[5], dgU + off3, dgV + off3);
   if (cudaGetLastError() != cudaSuccess) { fail(5, "mom_level_kernel launch failed"); return; }

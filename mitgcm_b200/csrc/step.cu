@@ -63,6 +63,7 @@ bool exch_field(double *f, int nz) {
   if (g.nPx != 1 || g.nPy != 1) return fail(60, "exch: multi-process exchange goes through the distributed driver");
   const size_t total = (size_t)(g.PX * g.PY - g.sNx * g.sNy) * nz * g.nTiles;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  c.launches++;
   exch_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(f, nz, g.sNx, g.sNy, g.OLx, g.OLy, g.nSx, g.nSy);
   MG_CUDA(cudaGetLastError());
   return true;
@@ -252,6 +253,13 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   if (!u || !v || !w || !gU || !gV || !guN || !gvN || !eta || !b || !x || !sfU || !sfV || !Bo || !rBo || !kapU || !kapV) return false;
   const size_t ns = g.slab;
   dim3 blk(32, 4);
+  const bool prof = q.I(MI_PROFILE) != 0;
+  auto mark = [&](int n) {
+    if (!prof) return;
+    if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
+    cudaEventRecord(c.pev[n], c.stream);
+  };
+  mark(0);
   // THERMODYNAMICS
   if (q.I(MI_TEMPSTEPPING)) {
     double *th = field(MG_THETA), *th2 = field(MG_THETA2), *gtN = field(MG_GTNM1), *kapT = field(MG_KAPPART);
@@ -268,12 +276,14 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
         TileGrid tg;
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
+        c.launches++;
         thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
       }
     MG_CUDA(cudaGetLastError());
     // CYCLE_TRACER: theta <- theta** (interior); halos follow in the blocking exchange below
     std::swap(c.fields[MG_THETA], c.fields[MG_THETA2]);
   }
+  mark(1);
   // DYNAMICS
   {
     dim3 grd((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 3) / 4);
@@ -284,11 +294,13 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
+        c.launches++;
         dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
                                               q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
       }
     MG_CUDA(cudaGetLastError());
   }
+  mark(2);
   // SOLVE_FOR_PRESSURE
   {
     dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
@@ -298,18 +310,23 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
+        c.launches++;
         rhs_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
                                               q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC));
       }
     MG_CUDA(cudaGetLastError());
+    mark(3);
     int numIters = q.I(MI_CG2DMAXITERS), nIterMin = q.I(MI_CG2DUSEMINRESSOL) - 1;
     double first, minsq, last;
     if (!cg2d_run(q.I(MI_USESRCGSOLVER) != 0, b, x, &first, &minsq, &last, &numIters, &nIterMin)) return false;
     *initRes = first; *iters = numIters; *lastRes = last;
+    mark(4);
     if (!exch_field(x, 1)) return false;
+    c.launches++;
     eta_kernel<<<(unsigned)((g.n2 + 255) / 256), 256, 0, c.stream>>>(g.n2, rBo, x, eta);
     MG_CUDA(cudaGetLastError());
   }
+  mark(5);
   // MOMENTUM_CORRECTION_STEP + INTEGR_CONTINUITY
   {
     dim3 grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
@@ -319,14 +336,25 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
+        c.launches++;
         corr_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
                                                q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS), q.I(MI_RIGIDLID));
       }
     MG_CUDA(cudaGetLastError());
   }
+  mark(6);
   // DO_FIELDS_BLOCKING_EXCHANGES
   if (!exch_field(u, g.Nr) || !exch_field(v, g.Nr) || !exch_field(w, g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
+  if (prof) {
+    mark(7);
+    cudaEventSynchronize(c.pev[7]);
+    for (int n = 0; n < 7; n++) {
+      float f = 0.f;
+      cudaEventElapsedTime(&f, c.pev[n], c.pev[n + 1]);
+      c.stepMs[n] = f;
+    }
+  }
   return true;
 }
 

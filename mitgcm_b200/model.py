@@ -111,3 +111,50 @@ class Model:
 
     def close(self):
         rt.finalize()
+
+
+def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None) -> dict:
+    """INI_CG2D (model/src/ini_cg2d.F:76-234) vectorised over the horizontal, level loop kept in
+    order so the sums are bit-identical to the Fortran.  hfac_flat: use hFacW = hFacS = const
+    instead of the 3-D arrays (flat-bottom set-ups whose masks live only on the device).
+    This is model set-up (it runs once, or once per step under NLFS), not the hot path."""
+    d = g.d
+    jj, ii = d.interior()
+    I = (slice(None), slice(None), jj, ii)
+    aW, aS = np.zeros(d.shape2), np.zeros(d.shape2)
+    fac = P.get("implicSurfPress", 1.0) * P.get("implicDiv2DFlow", 1.0)
+    for k in range(d.Nr):
+        hW = hfac_flat if hfac_flat is not None else g.hFacW[:, :, k][I]
+        hS = hfac_flat if hfac_flat is not None else g.hFacS[:, :, k][I]
+        aW[I] = aW[I] + fac * (g.dyG[I] * g.drF[k] * hW) * g.recip_dxC[I]
+        aS[I] = aS[I] + fac * (g.dxG[I] * g.drF[k] * hS) * g.recip_dyC[I]
+    myNorm = max(np.abs(aW[I]).max(), np.abs(aS[I]).max())
+    myNorm = 1.0 / myNorm if myNorm != 0 else 1.0
+    aW[I] = aW[I] * myNorm
+    aS[I] = aS[I] * myNorm
+    exch_xyz(d, aW)
+    exch_xyz(d, aS)
+    normalise = P.get("cg2dTargetResWunit", -1.0) <= 0.0
+    tol = P.get("cg2dTargetResidual", 1e-7) if normalise else \
+        myNorm * P["cg2dTargetResWunit"] * P["globalArea"] / P["deltaTMom"]
+    oy, ox = d.OLy, d.OLx
+    C0 = (slice(None), slice(None), slice(oy - 1, oy + d.sNy), slice(ox - 1, ox + d.sNx))       # 0..sN
+    CE = (slice(None), slice(None), slice(oy - 1, oy + d.sNy), slice(ox, ox + d.sNx + 1))       # i+1
+    CN = (slice(None), slice(None), slice(oy, oy + d.sNy + 1), slice(ox - 1, ox + d.sNx))       # j+1
+    aC = np.zeros(d.shape2)
+    aC[C0] = -((((aW[C0] + aW[CE]) + aS[C0]) + aS[CN]) +
+               P.get("freeSurfFac", 1.0) * myNorm * g.recip_Bo[C0] * g.rA[C0] / P["deltaTMom"] / P["deltaTFreeSurf"])
+    W = (slice(None), slice(None), jj, slice(ox - 1, ox + d.sNx - 1))
+    S = (slice(None), slice(None), slice(oy - 1, oy + d.sNy - 1), ii)
+    pC, pW, pS = np.zeros(d.shape2), np.zeros(d.shape2), np.zeros(d.shape2)
+    off = P.get("cg2dpcOffDFac", 0.51)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pC[I] = np.where(aC[I] == 0.0, 1.0, 1.0 / aC[I])
+        tw = off * (aC[W] + aC[I])
+        pW[I] = np.where(aC[I] + aC[W] == 0.0, 0.0, -aW[I] / (tw * tw))
+        ts = off * (aC[S] + aC[I])
+        pS[I] = np.where(aC[I] + aC[S] == 0.0, 0.0, -aS[I] / (ts * ts))
+    for a in (pC, pW, pS):
+        exch_xyz(d, a)
+    return dict(aW2d=aW, aS2d=aS, aC2d=aC, pW=pW, pS=pS, pC=pC, cg2dNorm=myNorm, cg2dTolerance_sq=tol * tol,
+                cg2dNormaliseRHS=normalise)
