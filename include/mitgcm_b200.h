@@ -155,6 +155,23 @@ void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg
  * full-width halo with corners. */
 void mitgcm_b200_exch_(const int *id, int *ierr);
 
+/* ---- multi-GPU (one process per GPU on one NVSwitch domain) --------------------------------
+ * CG2D: every rank exports its solver workspace as a CUDA IPC handle (64 bytes) and, after the
+ * handles of all ranks have been gathered, maps its peers.  Edge values are then stored directly
+ * into the neighbour's halo cells and dot products are combined through peer-mapped mailboxes
+ * inside the persistent kernel (replaces EXCH_S3D_RL + GLOBAL_SUM_TILE_RL; no MPI, no host round
+ * trips).  rank = myPx + nPx*myPy (MPI_CART_CREATE order, eesupp/src/ini_procs.F:145). */
+void mitgcm_b200_comm_handle_(unsigned char *handle64, int *ierr);
+void mitgcm_b200_comm_connect_(const int *nRanks, const int *myRank, const unsigned char *handles, int *ierr);
+/* Per-step halo exchange pieces for EXCH_XY_RL / EXCH_XYZ_RL over NCCL send/recv: pack the strip
+ * to send towards dir (0 W, 1 E, 2 S, 3 N) into buf, or (unpack != 0) scatter a received strip
+ * into the halo on side dir; exch_dir does one periodic direction locally (nPx or nPy == 1). */
+void mitgcm_b200_pack_(const int *id, const int *dir, double *buf, const int *unpack, int *ierr);
+void mitgcm_b200_exch_dir_(const int *id, const int *ydir, int *ierr);
+/* The resident step in two parts with the halo exchanges left to the caller (see step.cu). */
+void mitgcm_b200_step_part_(const int *part, const int *myIter, double *cg2d_init_res, int *cg2d_iters,
+                            double *cg2d_last_res, int *ierr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "lib", "libmitgcm_b200.so")
+LIB = os.environ.get("MITGCM_B200_LIB") or os.path.join(HERE, "lib", "libmitgcm_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "mitgcm_b200.h")
 
 PD = C.POINTER(C.c_double)

@@ -33,7 +33,16 @@ constexpr int MAX_PART = 2048;   // max CTAs in the cooperative grid
 
 struct Cg2dOut {
   double firstResidual, minResidualSq, lastResidual, sumRHS, rhsMax;
-  int numIters, nIterMin, pad;
+  int numIters, nIterMin, error;
+  unsigned long long seq;
+};
+
+// Cross-GPU reduction mailbox: rank r writes val then seq into slot [r][parity] of EVERY rank's
+// array through peer-mapped memory (NVLink); the reader sums the slots in rank order, so every
+// rank forms bit-identical totals (GLOBAL_SUM_TILE_RL semantics, global_sum_tile.F:161-191).
+struct Mail {
+  double val[3];
+  unsigned long long seq;
 };
 
 struct Cg2dArgs {
@@ -44,7 +53,13 @@ struct Cg2dArgs {
   const double *aW, *aS, *aC, *pW, *pS, *pC;
   double *b, *x;
   double *r[2], *s[2], *q, *z, *xmin, *v;   // v: extra vector of the SR variant
-  const int *pushTab;
+  const int *pushTab;    // bits 0..27 index, bits 28..30 peer slot (0 self, 1 W, 2 E, 3 S, 4 N)
+  long long peerDelta[5];   // byte offset from this rank's workspace block to the peer's mapping of its block
+  int nRanks, myRank;
+  struct Mail *mail[8];     // every rank's mailbox array (peer-mapped), indexed by rank
+  double *gtot;             // [2][4] cross-rank totals published by CTA 0
+  unsigned long long *gflag;
+  unsigned long long seq0;  // reduction sequence number at kernel start
   double *partials;      // [4][MAX_PART]
   double *resid;         // per-iteration residual (sqrt(err_sq)), maxIters entries
   Cg2dOut *out;
@@ -53,8 +68,17 @@ struct Cg2dArgs {
 };
 
 struct Cg2dWs {
+  double *block = nullptr;       // one allocation (IPC-shareable): r0 r1 s0 s1 q z v xmin xw | mailboxes | gtot | gflag
+  size_t blockBytes = 0;
   double *r[2] = {nullptr, nullptr}, *s[2] = {nullptr, nullptr}, *q = nullptr, *z = nullptr, *xmin = nullptr,
-         *v = nullptr;
+         *v = nullptr, *xw = nullptr;
+  Mail *mail = nullptr;
+  double *gtot = nullptr;
+  unsigned long long *gflag = nullptr;
+  int nRanks = 1, myRank = 0;
+  void *peerBase[8] = {};        // peer mappings of every rank's block (own block for myRank)
+  int nbrRank[5] = {0, 0, 0, 0, 0};
+  unsigned long long seq = 0;
   double *partials = nullptr, *resid = nullptr;
   Cg2dOut *out = nullptr;
   int residCap = 0;
@@ -68,7 +92,9 @@ void cg2d_free_workspace() {
   Ctx &c = ctx();
   if (!c.cg2d) return;
   Cg2dWs *w = c.cg2d;
-  for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->xmin, w->v, w->partials, w->resid})
+  for (int r = 0; r < w->nRanks; r++)
+    if (r != w->myRank && w->peerBase[r]) cudaIpcCloseMemHandle(w->peerBase[r]);
+  for (double *p : {w->block, w->partials, w->resid})
     if (p) cudaFree(p);
   if (w->out) cudaFree(w->out);
   delete w;
@@ -97,23 +123,29 @@ __device__ __forceinline__ Item decode_item(const Cg2dArgs &a, int item, int lan
   return it;
 }
 
+// Destination of a pushed edge value: local halo cell, or the same cell of the neighbouring
+// rank's workspace block through its peer mapping (NVLink store).
+__device__ __forceinline__ double *pdst(const Cg2dArgs &a, double *f, int enc) {
+  return reinterpret_cast<double *>(reinterpret_cast<char *>(f) + a.peerDelta[(enc >> 28) & 7]) + (enc & 0x0FFFFFFF);
+}
+
 // Mirror an edge value into the halo cell(s) of the neighbouring tile(s).
 __device__ __forceinline__ void push2(const Cg2dArgs &a, const Item &it, int j, double *f0, double v0,
                                       double *f1, double v1) {
   const int per = 2 * a.sNy + 2 * a.sNx;
   const int *t = a.pushTab + (size_t)per * it.tile;
-  if (it.i == 1) { int d = t[j - 1]; f0[d] = v0; f1[d] = v1; }
-  if (it.i == a.sNx) { int d = t[a.sNy + j - 1]; f0[d] = v0; f1[d] = v1; }
-  if (j == 1) { int d = t[2 * a.sNy + it.i - 1]; f0[d] = v0; f1[d] = v1; }
-  if (j == a.sNy) { int d = t[2 * a.sNy + a.sNx + it.i - 1]; f0[d] = v0; f1[d] = v1; }
+  if (it.i == 1) { int d = t[j - 1]; *pdst(a, f0, d) = v0; *pdst(a, f1, d) = v1; }
+  if (it.i == a.sNx) { int d = t[a.sNy + j - 1]; *pdst(a, f0, d) = v0; *pdst(a, f1, d) = v1; }
+  if (j == 1) { int d = t[2 * a.sNy + it.i - 1]; *pdst(a, f0, d) = v0; *pdst(a, f1, d) = v1; }
+  if (j == a.sNy) { int d = t[2 * a.sNy + a.sNx + it.i - 1]; *pdst(a, f0, d) = v0; *pdst(a, f1, d) = v1; }
 }
 __device__ __forceinline__ void push1(const Cg2dArgs &a, const Item &it, int j, double *f0, double v0) {
   const int per = 2 * a.sNy + 2 * a.sNx;
   const int *t = a.pushTab + (size_t)per * it.tile;
-  if (it.i == 1) f0[t[j - 1]] = v0;
-  if (it.i == a.sNx) f0[t[a.sNy + j - 1]] = v0;
-  if (j == 1) f0[t[2 * a.sNy + it.i - 1]] = v0;
-  if (j == a.sNy) f0[t[2 * a.sNy + a.sNx + it.i - 1]] = v0;
+  if (it.i == 1) *pdst(a, f0, t[j - 1]) = v0;
+  if (it.i == a.sNx) *pdst(a, f0, t[a.sNy + j - 1]) = v0;
+  if (j == 1) *pdst(a, f0, t[2 * a.sNy + it.i - 1]) = v0;
+  if (j == a.sNy) *pdst(a, f0, t[2 * a.sNy + a.sNx + it.i - 1]) = v0;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -145,20 +177,68 @@ __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N]
   __syncthreads();
 }
 
-// After a grid barrier: every CTA forms the same ordered sum over the per-CTA partials.
+// After a grid barrier: every CTA forms the same ordered sum over the per-CTA partials.  With
+// several ranks, CTA 0 then exchanges the rank totals through the peer-mapped mailboxes
+// (replaces the MPI_Allreduce of global_sum_tile.F:182) and publishes the rank-ordered sum.
+// rseq counts reductions; it is uniform across all threads of all ranks.
+__device__ int g_cg2d_spin_error = 0;
+
 template <int N, bool MAXOP>
-__device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N], double *sm) {
+__device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N], double *sm, unsigned long long &rseq) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (w < N) {
-    double t = MAXOP ? 0.0 : 0.0;
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      double p = __ldcg(&a.partials[w * MAX_PART + i]);
-      t = MAXOP ? fmax(t, p) : t + p;
+  rseq++;
+  if (a.nRanks == 1 || blockIdx.x == 0) {
+    if (w < N) {
+      double t = 0.0;
+      for (int i = lane; i < (int)gridDim.x; i += 32) {
+        double p = __ldcg(&a.partials[w * MAX_PART + i]);
+        t = MAXOP ? fmax(t, p) : t + p;
+      }
+      t = MAXOP ? warp_max(t) : warp_sum(t);
+      if (lane == 0) sm[w] = t;
     }
-    t = MAXOP ? warp_max(t) : warp_sum(t);
-    if (lane == 0) sm[w] = t;
+    __syncthreads();
   }
-  __syncthreads();
+  if (a.nRanks > 1) {
+    const int par = (int)(rseq & 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();   // this rank's halo pushes (ordered before us by the grid barrier) become visible first
+      for (int r = 0; r < a.nRanks; r++) {
+        Mail *m = a.mail[r] + (size_t)a.myRank * 2 + par;
+        for (int k = 0; k < N; k++) m->val[k] = sm[k];
+      }
+      __threadfence_system();
+      for (int r = 0; r < a.nRanks; r++)
+        *reinterpret_cast<volatile unsigned long long *>(&(a.mail[r] + (size_t)a.myRank * 2 + par)->seq) = rseq;
+      double t[N];
+      for (int k = 0; k < N; k++) t[k] = 0.0;
+      for (int r = 0; r < a.nRanks; r++) {
+        Mail *m = a.mail[a.myRank] + (size_t)r * 2 + par;
+        long long spins = 0;
+        while (*reinterpret_cast<volatile unsigned long long *>(&m->seq) != rseq) {
+          if (++spins > (1LL << 31)) { g_cg2d_spin_error = 1; break; }
+        }
+        __threadfence_system();
+        for (int k = 0; k < N; k++) {
+          double v = *reinterpret_cast<volatile double *>(&m->val[k]);
+          t[k] = MAXOP ? fmax(t[k], v) : t[k] + v;
+        }
+      }
+      for (int k = 0; k < N; k++) a.gtot[par * 4 + k] = t[k];
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long *>(a.gflag) = rseq;
+    }
+    if (threadIdx.x == 0) {
+      long long spins = 0;
+      while (*reinterpret_cast<volatile unsigned long long *>(a.gflag) < rseq) {
+        if (++spins > (1LL << 31)) break;
+      }
+    }
+    __syncthreads();
+    __threadfence();            // drop stale L1 lines: halo cells were written by the peers
+    if (threadIdx.x < N) sm[threadIdx.x] = __ldcg(&a.gtot[par * 4 + threadIdx.x]);
+    __syncthreads();
+  }
 #pragma unroll
   for (int k = 0; k < N; k++) tot[k] = sm[k];
   __syncthreads();
@@ -353,15 +433,15 @@ __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j
                                        double2 v1) {
   const int per = 2 * a.sNy + 2 * a.sNx;
   const int *t = a.pushTab + (size_t)per * it.tile;
-  if (it.i == 1) { int d = t[j - 1]; f0[d] = v0.x; f1[d] = v1.x; }
-  if (it.i + 1 == a.sNx) { int d = t[a.sNy + j - 1]; f0[d] = v0.y; f1[d] = v1.y; }
+  if (it.i == 1) { int d = t[j - 1]; *pdst(a, f0, d) = v0.x; *pdst(a, f1, d) = v1.x; }
+  if (it.i + 1 == a.sNx) { int d = t[a.sNy + j - 1]; *pdst(a, f0, d) = v0.y; *pdst(a, f1, d) = v1.y; }
   if (j == 1) {
     int d = t[2 * a.sNy + it.i - 1], e = t[2 * a.sNy + it.i];
-    f0[d] = v0.x; f1[d] = v1.x; f0[e] = v0.y; f1[e] = v1.y;
+    *pdst(a, f0, d) = v0.x; *pdst(a, f1, d) = v1.x; *pdst(a, f0, e) = v0.y; *pdst(a, f1, e) = v1.y;
   }
   if (j == a.sNy) {
     int d = t[2 * a.sNy + a.sNx + it.i - 1], e = t[2 * a.sNy + a.sNx + it.i];
-    f0[d] = v0.x; f1[d] = v1.x; f0[e] = v0.y; f1[e] = v1.y;
+    *pdst(a, f0, d) = v0.x; *pdst(a, f1, d) = v1.x; *pdst(a, f0, e) = v0.y; *pdst(a, f1, e) = v1.y;
   }
 }
 
@@ -513,10 +593,11 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   double t1[1], t2[2];
+  unsigned long long rseq = a.seq0;
 
   phase_scale_b(a, sm);
   grid.sync();
-  grid_totals<1, true>(a, t1, sm);
+  grid_totals<1, true>(a, t1, sm, rseq);
   const double rhsMax = t1[0];
   double rhsNorm = 1.0;
   if (a.normaliseRHS && rhsMax != 0.0) rhsNorm = 1.0 / rhsMax;
@@ -524,7 +605,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   grid.sync();
   phase_residual(a, sm);
   grid.sync();
-  grid_totals<2, false>(a, t2, sm);
+  grid_totals<2, false>(a, t2, sm, rseq);
   double err_sq = t2[0];
   const double sumRHS = t2[1];
   const double firstResidual = sqrt(err_sq);
@@ -542,7 +623,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     cur = 1;   // r[1] now holds r (with halos); s[0] is the (zero) current s
     int scur = 0;
     grid.sync();
-    grid_totals<2, false>(a, t2, sm);
+    grid_totals<2, false>(a, t2, sm, rseq);
     double eta_qrN = t2[1];
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
@@ -552,13 +633,13 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
       saveMin = false;
       scur ^= 1;
       grid.sync();
-      grid_totals<1, false>(a, t1, sm);
+      grid_totals<1, false>(a, t1, sm, rseq);
       const double alpha = eta_qrN / t1[0];
       if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
       grid.sync();
-      grid_totals<2, false>(a, t2, sm);
+      grid_totals<2, false>(a, t2, sm, rseq);
       err_sq = t2[0];
       eta_qrN = t2[1];
       actualIts = it2d;
@@ -583,6 +664,8 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     a.out->rhsMax = rhsMax;
     a.out->numIters = actualIts;
     a.out->nIterMin = nIterMin;
+    a.out->seq = rseq;
+    a.out->error = g_cg2d_spin_error;
   }
 }
 
@@ -708,11 +791,12 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   double t1[1], t2[2], t3[3];
+  unsigned long long rseq = a.seq0;
   double *r = a.r[0], *y = a.z, *s = a.s[0];
 
   phase_scale_b(a, sm);
   grid.sync();
-  grid_totals<1, true>(a, t1, sm);
+  grid_totals<1, true>(a, t1, sm, rseq);
   const double rhsMax = t1[0];
   double rhsNorm = 1.0;
   if (a.normaliseRHS && rhsMax != 0.0) rhsNorm = 1.0 / rhsMax;
@@ -720,7 +804,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
   grid.sync();
   phase_residual(a, sm);
   grid.sync();
-  grid_totals<2, false>(a, t2, sm);
+  grid_totals<2, false>(a, t2, sm, rseq);
   double err_sq = t2[0];
   const double sumRHS = t2[1];
   const double firstResidual = sqrt(err_sq);
@@ -734,12 +818,12 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
     // start-up iteration, cg2d_sr.F:220-291
     sr_phase_y(a, r, y, s, sm, true);
     grid.sync();
-    grid_totals<1, false>(a, t1, sm);
+    grid_totals<1, false>(a, t1, sm, rseq);
     double eta_qrN = t1[0];
     double eta_qrNM1 = eta_qrN;
     sr_phase_as(a, s, sm);
     grid.sync();
-    grid_totals<1, false>(a, t1, sm);
+    grid_totals<1, false>(a, t1, sm, rseq);
     double alpha = t1[0];
     double sigma = eta_qrN / alpha;
     sr_phase_update(a, r, 0.0, sigma, true, false);
@@ -750,7 +834,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
       grid.sync();
       sr_phase_v(a, y, r, sm);
       grid.sync();
-      grid_totals<3, false>(a, t3, sm);
+      grid_totals<3, false>(a, t3, sm, rseq);
       eta_qrN = t3[0];
       const double delta = t3[1];
       err_sq = t3[2];
@@ -768,7 +852,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
     if (!converged) {
       sr_phase_err(a, r, sm);
       grid.sync();
-      grid_totals<1, false>(a, t1, sm);
+      grid_totals<1, false>(a, t1, sm, rseq);
       err_sq = t1[0];
     }
   }
@@ -782,6 +866,8 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
     a.out->rhsMax = rhsMax;
     a.out->numIters = it2d;
     a.out->nIterMin = nIterMin;
+    a.out->seq = rseq;
+    a.out->error = g_cg2d_spin_error;
   }
 }
 
@@ -792,11 +878,17 @@ static bool ensure_ws(int maxIters) {
   if (!c.cg2d) {
     Cg2dWs *w = new Cg2dWs();
     c.cg2d = w;
-    size_t bytes = c.g.n2 * sizeof(double);
-    for (double **p : {&w->r[0], &w->r[1], &w->s[0], &w->s[1], &w->q, &w->z, &w->xmin, &w->v}) {
-      MG_CUDA(cudaMalloc(p, bytes));
-      MG_CUDA(cudaMemsetAsync(*p, 0, bytes, c.stream));
-    }
+    const size_t n2 = c.g.n2;
+    const size_t mailBytes = sizeof(Mail) * 8 * 2, totBytes = sizeof(double) * 8, flagBytes = 64;
+    w->blockBytes = 9 * n2 * sizeof(double) + mailBytes + totBytes + flagBytes;
+    MG_CUDA(cudaMalloc(&w->block, w->blockBytes));
+    MG_CUDA(cudaMemset(w->block, 0, w->blockBytes));
+    double *p = w->block;
+    for (double **q : {&w->r[0], &w->r[1], &w->s[0], &w->s[1], &w->q, &w->z, &w->v, &w->xmin, &w->xw}) { *q = p; p += n2; }
+    w->mail = reinterpret_cast<Mail *>(p);
+    w->gtot = reinterpret_cast<double *>(reinterpret_cast<char *>(p) + mailBytes);
+    w->gflag = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p) + mailBytes + totBytes);
+    w->peerBase[0] = w->block;
     MG_CUDA(cudaMalloc(&w->partials, 4 * MAX_PART * sizeof(double)));
     MG_CUDA(cudaMalloc(&w->out, sizeof(Cg2dOut)));
     int nb = 0;
@@ -814,6 +906,54 @@ static bool ensure_ws(int maxIters) {
   return true;
 }
 
+// ---- multi-GPU wiring (one process per GPU, all on one NVSwitch domain) ------------------------
+// Every rank exports its workspace block as a CUDA IPC handle; after the handles have been
+// all-gathered (torch.distributed, see mitgcm_b200/distributed.py) each rank maps its peers'
+// blocks.  Edge pushes then store straight into the neighbour's halo cells and the dot products
+// are combined through the mailboxes -- EXCH_S3D_RL and GLOBAL_SUM_TILE_RL without MPI.
+bool cg2d_comm_handle(unsigned char *handle64) {
+  if (!ctx().ready) return fail(30, "mitgcm_b200_init_ not called");
+  if (!ensure_ws(1)) return false;
+  cudaIpcMemHandle_t h;
+  MG_CUDA(cudaIpcGetMemHandle(&h, ctx().cg2d->block));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return true;
+}
+
+bool cg2d_comm_connect(int nRanks, int myRank, const unsigned char *handles) {
+  Ctx &c = ctx();
+  if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
+  if (!ensure_ws(1)) return false;
+  const Geom &g = c.g;
+  if (nRanks != g.nPx * g.nPy || nRanks > 8) return fail(70, "comm_connect: nRanks must equal nPx*nPy (<= 8)");
+  if (g.nTiles != 1) return fail(70, "comm_connect: multi-rank runs use one tile per rank (nSx = nSy = 1)");
+  if (myRank != g.myPx + g.nPx * g.myPy) return fail(70, "comm_connect: rank must be myPx + nPx*myPy");
+  if (g.n2 >= (1u << 28)) return fail(70, "comm_connect: tile2d array too large for the push encoding");
+  Cg2dWs *w = c.cg2d;
+  w->nRanks = nRanks; w->myRank = myRank;
+  for (int r = 0; r < nRanks; r++) {
+    if (r == myRank) { w->peerBase[r] = w->block; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    MG_CUDA(cudaIpcOpenMemHandle(&w->peerBase[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  auto rk = [&](int px, int py) { return ((px % g.nPx) + g.nPx) % g.nPx + g.nPx * (((py % g.nPy) + g.nPy) % g.nPy); };
+  w->nbrRank[0] = myRank;
+  w->nbrRank[1] = rk(g.myPx - 1, g.myPy); w->nbrRank[2] = rk(g.myPx + 1, g.myPy);
+  w->nbrRank[3] = rk(g.myPx, g.myPy - 1); w->nbrRank[4] = rk(g.myPx, g.myPy + 1);
+  // re-encode the push table: edges whose neighbour lives on another rank get the peer slot
+  const int per = 2 * g.sNy + 2 * g.sNx;
+  std::vector<int> t(per);
+  MG_CUDA(cudaMemcpy(t.data(), c.pushTab, per * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int n = 0; n < per; n++) {
+    int slot = n < g.sNy ? 1 : n < 2 * g.sNy ? 2 : n < 2 * g.sNy + g.sNx ? 3 : 4;
+    if (w->nbrRank[slot] != myRank) t[n] = (t[n] & 0x0FFFFFFF) | (slot << 28);
+  }
+  MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
+  return true;
+}
+
 bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
                      double *lastResidual, int *numIters, int *nIterMin) {
   Ctx &c = ctx();
@@ -827,8 +967,21 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   a.aW = field(MG_AW2D); a.aS = field(MG_AS2D); a.aC = field(MG_AC2D);
   a.pW = field(MG_PW); a.pS = field(MG_PS); a.pC = field(MG_PC);
   a.b = to_device(cg2d_b, g.n2, 0, true);
-  a.x = to_device(cg2d_x, g.n2, 1, true);
-  if (!a.b || !a.x || !a.aW || !a.pC) return false;
+  double *xUser = to_device(cg2d_x, g.n2, 1, true);
+  if (!a.b || !xUser || !a.aW || !a.pC) return false;
+  a.x = xUser;
+  if (w->nRanks > 1) {   // x needs halo pushes from the peers: iterate on the copy inside the shared block
+    MG_CUDA(cudaMemcpyAsync(w->xw, xUser, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    a.x = w->xw;
+  }
+  a.nRanks = w->nRanks; a.myRank = w->myRank; a.seq0 = w->seq;
+  a.gtot = w->gtot; a.gflag = w->gflag;
+  for (int r = 0; r < 8; r++)
+    a.mail[r] = r < w->nRanks ? reinterpret_cast<Mail *>(reinterpret_cast<char *>(w->peerBase[r]) +
+                                                         (reinterpret_cast<char *>(w->mail) - reinterpret_cast<char *>(w->block)))
+                              : nullptr;
+  for (int sl = 0; sl < 5; sl++)
+    a.peerDelta[sl] = reinterpret_cast<char *>(w->peerBase[w->nbrRank[sl]]) - reinterpret_cast<char *>(w->block);
   a.r[0] = w->r[0]; a.r[1] = w->r[1]; a.s[0] = w->s[0]; a.s[1] = w->s[1];
   a.q = w->q; a.z = w->z; a.xmin = w->xmin; a.v = w->v;
   a.pushTab = c.pushTab; a.partials = w->partials; a.resid = w->resid; a.out = w->out;
@@ -865,7 +1018,8 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   Cg2dOut out;
   MG_CUDA(cudaMemcpyAsync(&out, w->out, sizeof(out), cudaMemcpyDeviceToHost, c.stream));
   if (!from_device(cg2d_b, a.b, g.n2)) return false;
-  if (!from_device(cg2d_x, a.x, g.n2)) return false;
+  if (w->nRanks > 1) MG_CUDA(cudaMemcpyAsync(xUser, w->xw, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  if (!from_device(cg2d_x, xUser, g.n2)) return false;
   MG_CUDA(cudaStreamSynchronize(c.stream));
   *firstResidual = out.firstResidual;
   *minResidualSq = out.minResidualSq;
@@ -875,6 +1029,8 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   w->sumRHS = out.sumRHS;
   w->rhsMax = out.rhsMax;
   w->lastIters = out.numIters;
+  w->seq = out.seq;
+  if (out.error) return fail(71, "cg2d: timed out waiting for a peer rank");
   return true;
 }
 
@@ -894,6 +1050,16 @@ void cg2d_sr_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double
   (void)myThid;
   mg::ctx().lastError = 0;
   mg::cg2d_run(true, cg2d_b, cg2d_x, firstResidual, minResidualSq, lastResidual, numIters, nIterMin);
+}
+
+void mitgcm_b200_comm_handle_(unsigned char *handle64, int *ierr) {
+  mg::ctx().lastError = 0;
+  *ierr = mg::cg2d_comm_handle(handle64) ? 0 : 1;
+}
+
+void mitgcm_b200_comm_connect_(const int *nRanks, const int *myRank, const unsigned char *handles, int *ierr) {
+  mg::ctx().lastError = 0;
+  *ierr = mg::cg2d_comm_connect(*nRanks, *myRank, handles) ? 0 : 1;
 }
 
 void mitgcm_b200_cg2d_stats_(double *sumRHS, double *rhsMax) {

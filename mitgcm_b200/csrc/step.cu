@@ -96,7 +96,10 @@ struct FusedAcc {
   __device__ __forceinline__ double KappaR(int i, int j) const { return kapT[g.s3(i, j, k)]; }
 };
 
-__global__ void __launch_bounds__(128) thermo_kernel(TileGrid g, const double *u, const double *v, const double *w,
+#ifndef THERMO_MINB
+#define THERMO_MINB 4
+#endif
+__global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, const double *u, const double *v, const double *w,
                                                      const double *theta, const double *kapT, double *thetaNew,
                                                      double *gtNm1, GadPar p0, double abFac) {
   const int i = 1 + blockIdx.x * 32 + threadIdx.x;
@@ -122,7 +125,10 @@ __global__ void __launch_bounds__(128) thermo_kernel(TileGrid g, const double *u
 }
 
 // ---- dynamics ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
+#ifndef DYN_MINB
+#define DYN_MINB 4
+#endif
+__global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
                                                   double *gU, double *gV, double *guNm1, double *gvNm1,
                                                   double deltaTMom, double abFac, int momForcing, int dissInAB) {
   const int i = blockIdx.x * 32 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
@@ -235,7 +241,11 @@ __global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *gU,
   }
 }
 
-static bool forward_step(int myIter, double *initRes, int *iters, double *lastRes) {
+// part 0: THERMODYNAMICS, DYNAMICS, SOLVE_FOR_PRESSURE up to and including CG2D
+// part 1: etaN = recip_Bo * cg2d_x (after the halo update of cg2d_x), MOMENTUM_CORRECTION_STEP, INTEGR_CONTINUITY
+// The halo exchanges between and after the parts are done by the caller: locally (one rank) or
+// over NCCL (mitgcm_b200/distributed.py).
+static bool step_part(int part, int myIter, double *initRes, int *iters, double *lastRes) {
   Ctx &c = ctx();
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   const Geom &g = c.g;
@@ -259,6 +269,7 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
     if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
     cudaEventRecord(c.pev[n], c.stream);
   };
+  if (part == 0) {
   mark(0);
   // THERMODYNAMICS
   if (q.I(MI_TEMPSTEPPING)) {
@@ -321,7 +332,10 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
     if (!cg2d_run(q.I(MI_USESRCGSOLVER) != 0, b, x, &first, &minsq, &last, &numIters, &nIterMin)) return false;
     *initRes = first; *iters = numIters; *lastRes = last;
     mark(4);
-    if (!exch_field(x, 1)) return false;
+  }
+  return true;
+  }   // part 0
+  {
     c.launches++;
     eta_kernel<<<(unsigned)((g.n2 + 255) / 256), 256, 0, c.stream>>>(g.n2, rBo, x, eta);
     MG_CUDA(cudaGetLastError());
@@ -343,8 +357,26 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
     MG_CUDA(cudaGetLastError());
   }
   mark(6);
+  return true;
+}
+
+static bool forward_step(int myIter, double *initRes, int *iters, double *lastRes) {
+  Ctx &c = ctx();
+  if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
+  const Geom &g = c.g;
+  const Params &q = c.p;
+  if (g.nPx * g.nPy > 1) return fail(62, "forward_step: multi-rank runs step through mitgcm_b200_step_part_ + NCCL exchanges");
+  if (!step_part(0, myIter, initRes, iters, lastRes)) return false;
+  if (!exch_field(field(MG_CG2D_X), 1)) return false;
+  if (!step_part(1, myIter, initRes, iters, lastRes)) return false;
+  const bool prof = q.I(MI_PROFILE) != 0;
+  auto mark = [&](int n) {
+    if (!prof) return;
+    if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
+    cudaEventRecord(c.pev[n], c.stream);
+  };
   // DO_FIELDS_BLOCKING_EXCHANGES
-  if (!exch_field(u, g.Nr) || !exch_field(v, g.Nr) || !exch_field(w, g.Nr)) return false;
+  if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr) || !exch_field(field(MG_WVEL), g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
   if (prof) {
     mark(7);
@@ -358,11 +390,100 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   return true;
 }
 
+// ---- multi-rank halo exchange pieces (one tile per rank) ------------------------------------------
+// X phase strips: OLx columns x sNy interior rows; Y phase strips: OLy rows x the full PX width
+// (so corners propagate, exch1_rx.template:172-200).  dir: 0 = west, 1 = east, 2 = south, 3 = north.
+__global__ void pack_kernel(const double *f, double *buf, int nz, int sNx, int sNy, int OLx, int OLy, int dir, int unpack,
+                            double *fw) {
+  const int PX = sNx + 2 * OLx, PY = sNy + 2 * OLy;
+  const size_t slab = (size_t)PX * PY;
+  const int w = dir < 2 ? OLx : PX, h = dir < 2 ? sNy : OLy;
+  const size_t total = (size_t)w * h * nz;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int a = (int)(t % w), b = (int)((t / w) % h), k = (int)(t / ((size_t)w * h));
+    int ii, jj;
+    if (dir < 2) {
+      jj = OLy + b;
+      if (!unpack) ii = dir == 0 ? OLx + a : sNx + a;            // send: first / last OLx interior columns
+      else ii = dir == 0 ? a : OLx + sNx + a;                    // receive: west / east halo
+    } else {
+      ii = a;
+      if (!unpack) jj = dir == 2 ? OLy + b : sNy + b;
+      else jj = dir == 2 ? b : OLy + sNy + b;
+    }
+    size_t idx = (size_t)ii + (size_t)PX * jj + slab * k;
+    if (unpack) fw[idx] = buf[t];
+    else buf[t] = f[idx];
+  }
+}
+
+__global__ void exch_dir_kernel(double *f, int nz, int sNx, int sNy, int OLx, int OLy, int ydir) {
+  const int PX = sNx + 2 * OLx, PY = sNy + 2 * OLy;
+  const size_t slab = (size_t)PX * PY;
+  const int w = ydir ? PX : OLx, h = ydir ? OLy : sNy;
+  const size_t total = (size_t)w * h * nz;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int a = (int)(t % w), b = (int)((t / w) % h), k = (int)(t / ((size_t)w * h));
+    double *p = f + slab * k;
+    if (!ydir) {
+      size_t row = (size_t)PX * (OLy + b);
+      p[row + a] = p[row + sNx + a];
+      p[row + OLx + sNx + a] = p[row + OLx + a];
+    } else {
+      p[(size_t)PX * b + a] = p[(size_t)PX * (sNy + b) + a];
+      p[(size_t)PX * (OLy + sNy + b) + a] = p[(size_t)PX * (OLy + b) + a];
+    }
+  }
+}
+
+static int field_nz(int id) {
+  const Geom &g = ctx().g;
+  return (id >= 0 && id < MG_N2D) ? 1 : (id >= 100 && id < MG_N3D_END) ? g.Nr : (id >= 200 && id < MG_N3DP_END) ? g.Nr + 1 : 0;
+}
+
 }  // namespace mg
 
 using namespace mg;
 
 extern "C" {
+
+void mitgcm_b200_step_part_(const int *part, const int *myIter, double *cg2d_init_res, int *cg2d_iters,
+                            double *cg2d_last_res, int *ierr) {
+  ctx().lastError = 0;
+  *ierr = step_part(*part, *myIter, cg2d_init_res, cg2d_iters, cg2d_last_res) ? 0 : 1;
+}
+
+void mitgcm_b200_pack_(const int *id, const int *dir, double *buf, const int *unpack, int *ierr) {
+  Ctx &c = ctx();
+  c.lastError = 0;
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  if (g.nTiles != 1) { fail(70, "pack: one tile per rank"); return; }
+  double *f = field(*id);
+  int nz = field_nz(*id);
+  if (!f || nz == 0 || *dir < 0 || *dir > 3) { fail(2, "pack: bad field or direction"); return; }
+  c.launches++;
+  pack_kernel<<<c.numSMs * 4, 256, 0, c.stream>>>(f, buf, nz, g.sNx, g.sNy, g.OLx, g.OLy, *dir, *unpack, f);
+  if (cudaGetLastError() != cudaSuccess) { fail(5, "pack launch"); return; }
+  *ierr = 0;
+}
+
+void mitgcm_b200_exch_dir_(const int *id, const int *ydir, int *ierr) {
+  Ctx &c = ctx();
+  c.lastError = 0;
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  if (g.nTiles != 1) { fail(70, "exch_dir: one tile per rank"); return; }
+  double *f = field(*id);
+  int nz = field_nz(*id);
+  if (!f || nz == 0) { fail(2, "exch_dir: bad field"); return; }
+  c.launches++;
+  exch_dir_kernel<<<c.numSMs * 4, 256, 0, c.stream>>>(f, nz, g.sNx, g.sNy, g.OLx, g.OLy, *ydir);
+  if (cudaGetLastError() != cudaSuccess) { fail(5, "exch_dir launch"); return; }
+  *ierr = 0;
+}
 
 void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg2d_iters, double *cg2d_last_res,
                                int *ierr) {
@@ -377,7 +498,7 @@ void mitgcm_b200_exch_(const int *id, int *ierr) {
   if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
   double *f = field(*id);
   if (!f) return;
-  int nz = (*id >= 0 && *id < MG_N2D) ? 1 : (*id >= 100 && *id < MG_N3D_END) ? c.g.Nr : (*id >= 200 && *id < MG_N3DP_END) ? c.g.Nr + 1 : 0;
+  int nz = field_nz(*id);
   if (nz == 0) { fail(2, "exch: not a tile array"); return; }
   if (!exch_field(f, nz)) return;
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "exch: stream error"); return; }
