@@ -602,6 +602,12 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   double rhsNorm = 1.0;
   if (a.normaliseRHS && rhsMax != 0.0) rhsNorm = 1.0 / rhsMax;
   phase_normalise(a, rhsNorm, a.normaliseRHS != 0);
+  if (a.nRanks > 1) {   // the peers' x-edge pushes must have landed before the residual reads the halo:
+    double dummy[1] = {0.0};   // a cross-rank reduction doubles as the barrier
+    block_partials<1, true>(a, dummy, sm);
+    grid.sync();
+    grid_totals<1, true>(a, t1, sm, rseq);
+  }
   grid.sync();
   phase_residual(a, sm);
   grid.sync();
@@ -801,6 +807,12 @@ __global__ void __launch_bounds__(CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
   double rhsNorm = 1.0;
   if (a.normaliseRHS && rhsMax != 0.0) rhsNorm = 1.0 / rhsMax;
   phase_normalise(a, rhsNorm, a.normaliseRHS != 0);
+  if (a.nRanks > 1) {   // the peers' x-edge pushes must have landed before the residual reads the halo:
+    double dummy[1] = {0.0};   // a cross-rank reduction doubles as the barrier
+    block_partials<1, true>(a, dummy, sm);
+    grid.sync();
+    grid_totals<1, true>(a, t1, sm, rseq);
+  }
   grid.sync();
   phase_residual(a, sm);
   grid.sync();

@@ -73,3 +73,17 @@ def test_exchange_matches_oracle(shape):
         assert np.array_equal(rt.get_field("etaN", np.zeros_like(a2)), b2)
     finally:
         rt.finalize()
+
+
+def test_two_rank_step_matches_single_rank():
+    """N > 1 path on real GPUs: 2 ranks (CUDA IPC peer pushes + mailbox all-reduce in CG2D, NCCL
+    halo exchange) must reproduce the single-rank run of the same global domain.  Needs 2 GPUs."""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run scripts/dist_check.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "scripts", "dist_check.py"), "64", "48", "4", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
