@@ -247,7 +247,19 @@ void mitgcm_b200_event_elapsed_ms_(const int *a, const int *b, double *ms) {
   if (cudaEventElapsedTime(&f, c.ev[*a], c.ev[*b]) == cudaSuccess) *ms = f;
 }
 long long mitgcm_b200_launch_count_(void) { return ctx().launches; }
-void mitgcm_b200_step_timings_(double *ms7) { for (int i = 0; i < 7; i++) ms7[i] = ctx().stepMs[i]; }
+void mitgcm_b200_step_timings_(double *ms7) {
+  // elapsed time between the phase marks recorded by the last step (MI_PROFILE != 0); in a
+  // multi-rank step the caller's NCCL exchange of cg2d_x falls into slot 4 and slot 6 is 0
+  Ctx &c = ctx();
+  for (int i = 0; i < 7; i++) {
+    ms7[i] = 0.0;
+    if (!c.pev[i] || !c.pev[i + 1]) continue;
+    if (cudaEventSynchronize(c.pev[i + 1]) != cudaSuccess) continue;
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, c.pev[i], c.pev[i + 1]) == cudaSuccess && f >= 0.f) ms7[i] = f;
+  }
+  cudaGetLastError();
+}
 
 void mitgcm_b200_sync_(void) {
   if (ctx().ready) cudaStreamSynchronize(ctx().stream);

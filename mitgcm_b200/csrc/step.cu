@@ -378,15 +378,7 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   // DO_FIELDS_BLOCKING_EXCHANGES
   if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr) || !exch_field(field(MG_WVEL), g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
-  if (prof) {
-    mark(7);
-    cudaEventSynchronize(c.pev[7]);
-    for (int n = 0; n < 7; n++) {
-      float f = 0.f;
-      cudaEventElapsedTime(&f, c.pev[n], c.pev[n + 1]);
-      c.stepMs[n] = f;
-    }
-  }
+  mark(7);
   return true;
 }
 

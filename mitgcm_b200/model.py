@@ -113,12 +113,15 @@ class Model:
         rt.finalize()
 
 
-def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None) -> dict:
+def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None, exch=None) -> dict:
     """INI_CG2D (model/src/ini_cg2d.F:76-234) vectorised over the horizontal, level loop kept in
     order so the sums are bit-identical to the Fortran.  hfac_flat: use hFacW = hFacS = const
     instead of the 3-D arrays (flat-bottom set-ups whose masks live only on the device).
-    This is model set-up (it runs once, or once per step under NLFS), not the hot path."""
+    This is model set-up (it runs once, or once per step under NLFS), not the hot path.
+    exch(d, a): halo update used for aW/aS and pC/pW/pS (EXCH_UV_XY_RS / EXCH_XY_RS); defaults to
+    the single-process periodic exchange."""
     d = g.d
+    exch_xyz = exch or globals()["exch_xyz"]
     jj, ii = d.interior()
     I = (slice(None), slice(None), jj, ii)
     aW, aS = np.zeros(d.shape2), np.zeros(d.shape2)
