@@ -11,7 +11,8 @@
 //   exch_kernel   : EXCH_XYZ_RL with corners on one periodic process (exch1_rx.template:170-201)
 // Assumptions of this driver (checked): linear free surface, implicSurfPress = implicDiv2DFlow = 1,
 // no CD scheme, z coordinates, buoyancy decoupled (dPhiHyd = 0), surface stress forcing only.
-#include "mom.cuh"
+#include <cstdlib>
+#include "step_fast.cuh"
 
 namespace mg {
 
@@ -288,7 +289,11 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
         c.launches++;
-        thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
+        if (thermo_fast_ok(g, p))
+          thermo_fast_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
+              tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
+        else
+          thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
       }
     MG_CUDA(cudaGetLastError());
     // CYCLE_TRACER: theta <- theta** (interior); halos follow in the blocking exchange below
@@ -306,8 +311,13 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
-                                              q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+        if (dyn_fast_ok(g, mp))
+          dyn_fast_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
+              tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
+              q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+        else
+          dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+                                                q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
       }
     MG_CUDA(cudaGetLastError());
   }
