@@ -4,15 +4,16 @@
 // The reference runs four sweeps per iteration with three global sums and two halo
 // exchanges.  Here an iteration is two fused sweeps separated by grid-wide barriers:
 //   phase B : s = z + beta*s (recomputed on the 5-point stencil from z and the old s, so no
-//             separate s sweep and no s exchange), q = A s, partial <s,q>
-//   phase CA: x += alpha s ; r = r - alpha q (recomputed on the stencil from the old r and q),
+//             separate s sweep and no s exchange), q = A s, partial <s,q>; also the x += alpha s
+//             of the PREVIOUS iteration, which needs the old s this phase reads anyway
+//   phase CA: r = r - alpha q (recomputed on the stencil from the old r and q),
 //             z = M r, partial <r,r> and <z,r>
 // r and s are double-buffered so neighbours always read the previous iterate.  Edge points
 // are "pushed" into the halo cell that mirrors them (ctx.pushTab), which replaces
 // EXCH_S3D_RL (eesupp/src/exch_s3d_rx.template) without a separate pass.  Dot products are a
 // fixed-shape reduction (lane accumulate -> warp shuffle -> CTA -> ordered sum over CTAs),
 // replacing GLOBAL_SUM_TILE_RL (eesupp/src/global_sum_tile.F); run-to-run deterministic.
-// Algorithmic traffic: 7 + 10 = 17 words = 136 B per point per iteration.
+// Algorithmic traffic: 9 + 7 = 16 words = 128 B per point per iteration.
 //
 // Compiled with -fmad=false: every expression is evaluated in the reference's order without
 // contraction, so single operator applies are bit-identical to the Fortran -ieee build; only
@@ -336,7 +337,6 @@ __device__ void phase_ca(const Cg2dArgs &a, const double *rOld, double *rNew, co
         rN = rOld[idx + PX] - alpha * a.q[idx + PX];
         rW = rOld[idx - 1] - alpha * a.q[idx - 1];
         rE = rOld[idx + 1] - alpha * a.q[idx + 1];
-        a.x[idx] = a.x[idx] + alpha * sCur[idx];
       }
       double zv = a.pC[idx] * rC + a.pW[idx] * rW + a.pW[idx + 1] * rE + a.pS[idx] * rS + a.pS[idx + PX] * rN;
       rNew[idx] = rC;
@@ -353,7 +353,8 @@ __device__ void phase_ca(const Cg2dArgs &a, const double *rOld, double *rNew, co
 
 // Phase B (cg2d.F:252-289): s = z + beta s on the stencil, q = A s, partial <s,q>.
 // saveMin: store the lowest-residual solution first (cg2d.F:338-351).
-__device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, double beta, bool saveMin, double *sm) {
+__device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, double beta, bool saveMin, double alphaPrev,
+                        bool updX, double *sm) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -372,7 +373,11 @@ __device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, dou
       sNew[idx] = tC;
       a.q[idx] = qv;
       push2(a, it, j, sNew, tC, a.q, qv);
-      if (saveMin) a.xmin[idx] = a.x[idx];
+      if (updX) {   // x += alpha s of the previous iteration (cg2d.F:311), deferred to share the read of s
+        double xv = a.x[idx] + alphaPrev * sOld[idx];
+        a.x[idx] = xv;
+        if (saveMin) a.xmin[idx] = xv;
+      } else if (saveMin) a.xmin[idx] = a.x[idx];
       acc[0] += tC * qv;
       tS = tC;
       tC = tN;
@@ -382,7 +387,8 @@ __device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, dou
 }
 
 // cg2d.F:358-384: restore the min-residual solution, un-normalise.
-__device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending, double rhsNorm) {
+__device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending, double rhsNorm,
+                             const double *sLast = nullptr, double alphaLast = 0.0) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   (void)saveMinPending;
@@ -392,6 +398,7 @@ __device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending
     size_t idx = it.base;
     for (int j = it.j0; j <= it.j1; j++, idx += a.PX) {
       double xv = useMin ? a.xmin[idx] : a.x[idx];
+      if (!useMin && sLast) xv = xv + alphaLast * sLast[idx];   // the x update of the last iteration (cg2d.F:311)
       if (a.normaliseRHS) xv = xv / rhsNorm;
       a.x[idx] = xv;
     }
@@ -426,7 +433,11 @@ __device__ __forceinline__ Item2 decode_item2(const Cg2dArgs &a, int item, int l
 }
 
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+#ifdef CG2D_STREAM_OPS
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+#else
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+#endif
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
 __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j, double *f0, double2 v0, double *f1,
@@ -448,8 +459,8 @@ __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j
 // R rows of phase B starting at row j (flat index idx of column it.i).
 template <int R>
 __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew,
-                                        double beta, bool saveMin, const Item2 &it, size_t idx, int j, double2 &tS,
-                                        double2 &tC, double2 &aSj, double &acc) {
+                                        double beta, bool saveMin, double alphaPrev, bool updX, const Item2 &it, size_t idx,
+                                        int j, double2 &tS, double2 &tC, double2 &aSj, double2 &sC, double &acc) {
   const int PX = a.PX;
   double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R];
   double zW[R], sW[R], zE[R], sE[R], aWEl[R];
@@ -464,7 +475,7 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
       aSN[r] = ldg2(a.aS + id + PX);
       aWv[r] = ldg2(a.aW + id);
       aCv[r] = ldg2(a.aC + id);
-      if (saveMin) xv[r] = ld2(a.x + id);
+      if (saveMin || updX) xv[r] = ld2(a.x + id);
       if (it.edgeW) { zW[r] = a.z[id - 1]; sW[r] = sOld[id - 1]; }
       if (it.edgeE) { zE[r] = a.z[id + 2]; sE[r] = sOld[id + 2]; aWEl[r] = __ldg(a.aW + id + 2); }
     }
@@ -485,16 +496,20 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
       st2(sNew + id, tC);
       st2(a.q + id, qv);
       push2v(a, it, j + r, sNew, tC, a.q, qv);
+      if (updX) {   // deferred x += alpha s of the previous iteration (sC = old s of this row)
+        xv[r] = make_double2(xv[r].x + alphaPrev * sC.x, xv[r].y + alphaPrev * sC.y);
+        st2(a.x + id, xv[r]);
+      }
       if (saveMin) st2(a.xmin + id, xv[r]);
       acc += tC.x * q0;
       acc += tC.y * q1;
     }
-    tS = tC; tC = tN; aSj = aSN[r];
+    tS = tC; tC = tN; aSj = aSN[r]; sC = sN[r];
   }
 }
 
 __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew, double beta,
-                         bool saveMin, double *sm) {
+                         bool saveMin, double alphaPrev, bool updX, double *sm) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -502,16 +517,17 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
   for (int item = gw; item < a.nItems2; item += nw) {
     Item2 it = decode_item2(a, item, lane);
     size_t idx = it.base;
-    double2 tS = make_double2(0.0, 0.0), tC = tS, aSj = tS;
+    double2 tS = make_double2(0.0, 0.0), tC = tS, aSj = tS, sC = tS;
     if (it.active) {
       double2 z0 = ld2(a.z + idx - PX), s0 = ld2(sOld + idx - PX), z1 = ld2(a.z + idx), s1 = ld2(sOld + idx);
       tS = make_double2(z0.x + beta * s0.x, z0.y + beta * s0.y);
       tC = make_double2(z1.x + beta * s1.x, z1.y + beta * s1.y);
       aSj = ldg2(a.aS + idx);
+      sC = s1;
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, it, idx, j, tS, tC, aSj, acc[0]);
-    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, it, idx, j, tS, tC, aSj, acc[0]);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0]);
+    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0]);
   }
   block_partials<1, false>(a, acc, sm);
 }
@@ -521,18 +537,16 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
                                          const double *__restrict__ sCur, double alpha, const Item2 &it, size_t idx,
                                          int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH) {
   const int PX = a.PX;
-  double2 rN[R], qN[R], xv[R], sv[R], pCv[R], pWv[R], pSN[R];
+  double2 rN[R], qN[R], pCv[R], pWv[R], pSN[R];
   double rW[R], qW[R], rE[R], qE[R], pWEl[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     size_t id = idx + (size_t)r * PX;
-    rN[r] = qN[r] = xv[r] = sv[r] = pCv[r] = pWv[r] = pSN[r] = make_double2(0.0, 0.0);
+    rN[r] = qN[r] = pCv[r] = pWv[r] = pSN[r] = make_double2(0.0, 0.0);
     rW[r] = qW[r] = rE[r] = qE[r] = pWEl[r] = 0.0;
     if (it.active) {
       rN[r] = ld2(rOld + id + PX);
       qN[r] = ld2(a.q + id + PX);
-      xv[r] = ld2(a.x + id);
-      sv[r] = ld2(sCur + id);
       pCv[r] = ldg2(a.pC + id);
       pWv[r] = ldg2(a.pW + id);
       pSN[r] = ldg2(a.pS + id + PX);
@@ -553,7 +567,6 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
     double z1 = pCv[r].y * rC.y + pWv[r].y * rC.x + pWE * rEn + pSj.y * rS.y + pSN[r].y * rNn.y;
     if (it.active) {
       double2 zv = make_double2(z0, z1);
-      st2(a.x + id, make_double2(xv[r].x + alpha * sv[r].x, xv[r].y + alpha * sv[r].y));
       st2(rNew + id, rC);
       st2(a.z + id, zv);
       push2v(a, it, j + r, rNew, rC, a.z, zv);
@@ -572,7 +585,12 @@ __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, do
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
   double acc[2] = {0.0, 0.0};
-  for (int item = gw; item < a.nItems2; item += nw) {
+  for (int item0 = gw; item0 < a.nItems2; item0 += nw) {
+#ifdef CG2D_REVERSE_CA
+    const int item = a.nItems2 - 1 - item0;
+#else
+    const int item = item0;
+#endif
     Item2 it = decode_item2(a, item, lane);
     size_t idx = it.base;
     double2 rS = make_double2(0.0, 0.0), rC = rS, pSj = rS;
@@ -622,6 +640,8 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   double eta_qrNM1 = 1.0;
   int cur = 0;              // r[cur] / s[cur] hold the current iterate
   bool saveMin = false;     // x_min = x is pending (done inside the next phase B)
+  const double *sLast = nullptr;   // s and alpha of the last iteration: its x update is still pending
+  double alphaLast = 0.0;
 
   if (!(err_sq < a.tolSq)) {
     // z = M r for the first iteration
@@ -634,13 +654,15 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, sm);
-      else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, sm);
+      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
+      else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
       saveMin = false;
       scur ^= 1;
       grid.sync();
       grid_totals<1, false>(a, t1, sm, rseq);
       const double alpha = eta_qrN / t1[0];
+      sLast = a.s[scur];
+      alphaLast = alpha;
       if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
@@ -661,7 +683,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   // a pending x_min = x copy only matters if x_min is used, i.e. err_sq > minResidualSq, which
   // cannot hold for the iterate that set minResidualSq = err_sq; so it can be dropped.
   const bool useMin = (nIterMin >= 0 && err_sq > minResidualSq);
-  phase_finish(a, useMin, saveMin, rhsNorm);
+  phase_finish(a, useMin, saveMin, rhsNorm, sLast, alphaLast);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.out->firstResidual = firstResidual;
     a.out->minResidualSq = minResidualSq;

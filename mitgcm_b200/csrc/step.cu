@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
 }
 
 // ---- surface pressure right-hand side -----------------------------------------------------------
-__global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *gU, const double *gV, const double *etaN,
-                                                  const double *Bo_surf, double *cg2d_b, double *cg2d_x,
+__global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+                                                  const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
+                                                  double *__restrict__ cg2d_b, double *__restrict__ cg2d_x,
                                                   double deltaTMom, double deltaTFreeSurf, double freeSurfFac) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
@@ -179,11 +180,19 @@ __global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *gU, 
   cg2d_x[s] = Bo_surf[s] * etaN[s];                       // solve_for_pressure.F:129 (full halo range)
   double b = 0.;
   if (i >= 1 && i <= g.sNx && j >= 1 && j <= g.sNy) {
+    const size_t slab = g.slab;
+    const int PX = g.PX;
+    const double dyG0 = g.dyG[s], dyG1 = g.dyG[s + 1], dxG0 = g.dxG[s], dxG1 = g.dxG[s + PX];
+    const double *__restrict__ hW = g.hFacW, *__restrict__ hS = g.hFacS;
+#pragma unroll 5
     for (int k = g.Nr; k >= 1; k--) {
-      auto pfx = [&](int ii) { return g.dyG[g.s(ii, j)] * g.drF[k - 1] * g.hFacW[g.s3(ii, j, k)] * gU[g.s3(ii, j, k)] / deltaTMom; };
-      auto pfy = [&](int jj) { return g.dxG[g.s(i, jj)] * g.drF[k - 1] * g.hFacS[g.s3(i, jj, k)] * gV[g.s3(i, jj, k)] / deltaTMom; };
-      b = b + pfx(i + 1) - pfx(i);
-      b = b + pfy(j + 1) - pfy(j);
+      const size_t q = s + slab * (size_t)(k - 1);
+      const double drFk = g.drF[k - 1];
+      // calc_div_ghat.F:64-167: pf = xA*gU/deltaTMom with xA = dyG*drF*hFacW
+      const double px1 = dyG1 * drFk * hW[q + 1] * gU[q + 1] / deltaTMom, px0 = dyG0 * drFk * hW[q] * gU[q] / deltaTMom;
+      const double py1 = dxG1 * drFk * hS[q + PX] * gV[q + PX] / deltaTMom, py0 = dxG0 * drFk * hS[q] * gV[q] / deltaTMom;
+      b = b + px1 - px0;
+      b = b + py1 - py0;
     }
     b = b - freeSurfFac * g.rA[s] / deltaTMom / deltaTFreeSurf * etaN[s];
   }
@@ -196,8 +205,9 @@ __global__ void eta_kernel(size_t n, const double *recip_Bo, const double *x, do
 }
 
 // ---- correction step + continuity ---------------------------------------------------------------
-__global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *gU, const double *gV, const double *etaN,
-                                                   const double *Bo_surf, double *uVel, double *vVel, double *wVel,
+__global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+                                                   const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
+                                                   double *__restrict__ uVel, double *__restrict__ vVel, double *__restrict__ wVel,
                                                    double deltaTMom, double implicSurfPress, int rigidLid) {
   const int i = 1 + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 + blockIdx.y * 4 + threadIdx.y;
@@ -207,6 +217,7 @@ __global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *gU,
   auto phiY = [&](int jj) { return g.recip_dyC[g.s(i, jj)] * (Bo_surf[g.s(i, jj)] * etaN[g.s(i, jj)] - Bo_surf[g.s(i, jj - 1)] * etaN[g.s(i, jj - 1)]); };
   const double px0 = phiX(i), px1 = phiX(i + 1), py0 = phiY(j), py1 = phiY(j + 1);
   double wKp1 = 0.;
+#pragma unroll 5
   for (int k = g.Nr; k >= 1; k--) {
     auto uNew = [&](int ii, double px) {
       size_t q = g.s3(ii, j, k);

@@ -20,13 +20,19 @@
 
 namespace mg {
 
-constexpr int FT_X = 32, FT_Y = 8, FT_W = FT_X + 2, FT_H = FT_Y + 2, FT_N = FT_W * FT_H;
+#ifndef FT_YV
+#define FT_YV 8
+#endif
+#ifndef DYNF_MINB
+#define DYNF_MINB 2
+#endif
+constexpr int FT_X = 32, FT_Y = FT_YV, FT_W = FT_X + 2, FT_H = FT_Y + 2, FT_N = FT_W * FT_H;
 
 struct DynSmem {
   double u[FT_N], v[FT_N], uT[FT_N], vT[FT_N], hW[FT_N], hS[FT_N], hC[FT_N], hZ[FT_N], wA[FT_N], mC[2][FT_N];
 };
 
-__global__ void __launch_bounds__(FT_X *FT_Y, 2)
+__global__ void __launch_bounds__(FT_X *FT_Y, DYNF_MINB)
     dyn_fast_kernel(TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU, const double *__restrict__ sfV,
                     double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
                     double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB) {
