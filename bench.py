@@ -234,6 +234,13 @@ def run_cuda(args, rank, world):
     }
     dom = max(cand, key=lambda k: cand[k][1])
     ach = cand[dom][0] / (cand[dom][1] * 1e-3) / 1e9
+    traffic = None
+    try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("workload") == f"{NX}x{NY}x{NR}" and dom in tj:
+            traffic = tj[dom]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     out = {
         "metric": "timesteps/s at 2048x2048x50 (per-GPU block of the weak-scaled channel; aggregate = ranks x steps/s)",
         "value": value * world, "unit": "block-timesteps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -249,7 +256,8 @@ def run_cuda(args, rank, world):
         "phase_share": shares, "phase_ms_per_step": {n: float(phase[i] / K) for i, n in enumerate(names)},
         "kernel_hbm_gbs": {k: float(v[0] / (v[1] * 1e-3) / 1e9) for k, v in cand.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "peak_source": peak_kind, "traffic": None},
+                     "peak_source": peak_kind, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": cand[dom][0]},
         "e2e": {"value": world * K / e2e_s, "unit": "block-timesteps/s", "h2d_bytes_per_step": int(2 * sfU_host.numel() * 8),
                 "d2h_bytes_per_step": int(eta_host.numel() * 8 + 24)},
         "gpu_launches": launches, "clocks": clocks, "setup_s": t_setup, "finite": finite,
