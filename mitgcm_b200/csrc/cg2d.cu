@@ -202,32 +202,39 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
   }
   if (a.nRanks > 1) {
     const int par = (int)(rseq & 1);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      __threadfence_system();   // this rank's halo pushes (ordered before us by the grid barrier) become visible first
-      for (int r = 0; r < a.nRanks; r++) {
+    if (blockIdx.x == 0) {
+      // one thread per peer rank: post this rank's totals into the peer's mailbox and fetch the
+      // peer's totals from ours, all peers in parallel.  The system-scope fence between values and
+      // flag also publishes this rank's halo pushes (ordered before us by the grid barrier).
+      // (Letting every CTA poll the mailbox itself was measured slower: 128 vs 116 us/iteration
+      // on 4 GPUs -- 296 CTAs of system-scope fences.)
+      if (threadIdx.x < a.nRanks) {
+        const int r = threadIdx.x;
         Mail *m = a.mail[r] + (size_t)a.myRank * 2 + par;
         for (int k = 0; k < N; k++) m->val[k] = sm[k];
-      }
-      __threadfence_system();
-      for (int r = 0; r < a.nRanks; r++)
-        *reinterpret_cast<volatile unsigned long long *>(&(a.mail[r] + (size_t)a.myRank * 2 + par)->seq) = rseq;
-      double t[N];
-      for (int k = 0; k < N; k++) t[k] = 0.0;
-      for (int r = 0; r < a.nRanks; r++) {
-        Mail *m = a.mail[a.myRank] + (size_t)r * 2 + par;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&m->seq) = rseq;
+        Mail *mm = a.mail[a.myRank] + (size_t)r * 2 + par;
         long long spins = 0;
-        while (*reinterpret_cast<volatile unsigned long long *>(&m->seq) != rseq) {
+        while (*reinterpret_cast<volatile unsigned long long *>(&mm->seq) != rseq) {
           if (++spins > (1LL << 31)) { g_cg2d_spin_error = 1; break; }
         }
         __threadfence_system();
-        for (int k = 0; k < N; k++) {
-          double v = *reinterpret_cast<volatile double *>(&m->val[k]);
-          t[k] = MAXOP ? fmax(t[k], v) : t[k] + v;
-        }
+        for (int k = 0; k < N; k++) sm[CG_WARPS + r * 3 + k] = *reinterpret_cast<volatile double *>(&mm->val[k]);
       }
-      for (int k = 0; k < N; k++) a.gtot[par * 4 + k] = t[k];
-      __threadfence();
-      *reinterpret_cast<volatile unsigned long long *>(a.gflag) = rseq;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int k = 0; k < N; k++) {
+          double t = 0.0;
+          for (int r = 0; r < a.nRanks; r++) {          // rank order: identical totals on every rank
+            double v = sm[CG_WARPS + r * 3 + k];
+            t = MAXOP ? fmax(t, v) : t + v;
+          }
+          a.gtot[par * 4 + k] = t;
+        }
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long *>(a.gflag) = rseq;
+      }
     }
     if (threadIdx.x == 0) {
       long long spins = 0;
