@@ -52,37 +52,47 @@ def _buf(key, n):
     return b
 
 
-def _pack(fid, direction, buf, unpack):
+def _pack(fid, direction, ptr, unpack):
     ierr = C.c_int(0)
-    _lib.lib().mitgcm_b200_pack_(C.byref(C.c_int(fid)), C.byref(C.c_int(direction)), C.c_void_p(buf.data_ptr()),
+    _lib.lib().mitgcm_b200_pack_(C.byref(C.c_int(fid)), C.byref(C.c_int(direction)), C.c_void_p(ptr),
                                  C.byref(C.c_int(unpack)), C.byref(ierr))
     rt._check(ierr)
 
 
-def exchange(name: str):
+def exchange(*names: str):
+    """EXCH_XY(Z)_RL of one or several mirrors: the strips of all fields travel in ONE message per
+    neighbour and phase."""
     d, nbr = _S["d"], _S["nbr"]
     L = _lib.lib()
-    fid = rt.field_id(name)
-    nz = 1 if fid < 100 else (d.Nr if fid < 200 else d.Nr + 1)
+    fids = [rt.field_id(n) for n in names]
+    nzs = [1 if f < 100 else (d.Nr if f < 200 else d.Nr + 1) for f in fids]
     ierr = C.c_int(0)
     for ydir, (lo, hi, nP, w, h) in enumerate(((("W", "E", d.nPx, d.OLx, d.sNy)), ("S", "N", d.nPy, d.PX, d.OLy))):
         if nP == 1:
-            L.mitgcm_b200_exch_dir_(C.byref(C.c_int(fid)), C.byref(C.c_int(ydir)), C.byref(ierr))
-            rt._check(ierr)
+            for fid in fids:
+                L.mitgcm_b200_exch_dir_(C.byref(C.c_int(fid)), C.byref(C.c_int(ydir)), C.byref(ierr))
+                rt._check(ierr)
             continue
-        n = w * h * nz
+        sizes = [w * h * nz for nz in nzs]
+        n = sum(sizes)
         s_lo, s_hi = _buf(("s", ydir, 0), n), _buf(("s", ydir, 1), n)
         r_lo, r_hi = _buf(("r", ydir, 0), n), _buf(("r", ydir, 1), n)
-        _pack(fid, 2 * ydir, s_lo, 0)          # strip next to my low edge -> low neighbour's high halo
-        _pack(fid, 2 * ydir + 1, s_hi, 0)
+        off = 0
+        for fid, sz in zip(fids, sizes):
+            _pack(fid, 2 * ydir, s_lo.data_ptr() + 8 * off, 0)       # strip at my low edge -> low neighbour's high halo
+            _pack(fid, 2 * ydir + 1, s_hi.data_ptr() + 8 * off, 0)
+            off += sz
         rt.sync()
         ops = [dist.P2POp(dist.isend, s_lo[:n], nbr[lo]), dist.P2POp(dist.isend, s_hi[:n], nbr[hi]),
                dist.P2POp(dist.irecv, r_hi[:n], nbr[hi]), dist.P2POp(dist.irecv, r_lo[:n], nbr[lo])]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         torch.cuda.synchronize()
-        _pack(fid, 2 * ydir, r_lo, 1)
-        _pack(fid, 2 * ydir + 1, r_hi, 1)
+        off = 0
+        for fid, sz in zip(fids, sizes):
+            _pack(fid, 2 * ydir, r_lo.data_ptr() + 8 * off, 1)
+            _pack(fid, 2 * ydir + 1, r_hi.data_ptr() + 8 * off, 1)
+            off += sz
     rt.sync()
 
 
@@ -96,6 +106,5 @@ def forward_step(myIter: int):
     exchange("cg2d_x")
     L.mitgcm_b200_step_part_(C.byref(C.c_int(1)), C.byref(C.c_int(myIter)), C.byref(f), C.byref(n), C.byref(l), C.byref(ierr))
     rt._check(ierr)
-    for name in ("uVel", "vVel", "wVel", "theta"):
-        exchange(name)
+    exchange("uVel", "vVel", "wVel", "theta")
     return dict(firstResidual=f.value, numIters=n.value, lastResidual=l.value)
