@@ -322,7 +322,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        if (dyn_fast_ok(g, mp))
+        if (dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
+          static bool attr = false;
+          if (!attr) {
+            cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
+            attr = true;
+          }
+          dyn_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(DynPipeSmem),
+                            c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
+                                        abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+        } else if (dyn_fast_ok(g, mp))
           dyn_fast_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
