@@ -31,7 +31,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CG2D_BYTES_PER_POINT_ITER = 128.0     # 16 words (9 in phase B, 7 in phase CA)
+CG2D_BYTES_PER_POINT_ITER = 136.0     # 17 words, the minimum of the three-sync CG2D structure
+                                      # (this implementation moves 14-16 words: DESIGN.md section 5)
 DYN_BYTES_PER_CELL = 152.0            # 19 words (MOM_FLUXFORM + TIMESTEP fused)
 THERMO_BYTES_PER_CELL = 96.0          # 12 words (GAD_CALC_RHS + AB2 + TIMESTEP_TRACER fused)
 

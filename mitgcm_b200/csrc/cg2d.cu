@@ -51,6 +51,7 @@ struct Cg2dArgs {
   size_t slab;
   int nIB, nJB, RY, nItems;          // scalar decomposition: warp items of 32 columns x RY rows
   int nIB2, nJB2, RY2, nItems2, vec2;  // vector decomposition: 64 columns x RY2 rows (double2 per lane)
+  int resident, resRows;               // the first resRows rows of every strip of q / z stay in shared memory between the phases
   const double *aW, *aS, *aC, *pW, *pS, *pC;
   double *b, *x;
   double *r[2], *s[2], *q, *z, *xmin, *v;   // v: extra vector of the SR variant
@@ -467,7 +468,8 @@ __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j
 template <int R>
 __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew,
                                         double beta, bool saveMin, double alphaPrev, bool updX, const Item2 &it, size_t idx,
-                                        int j, double2 &tS, double2 &tC, double2 &aSj, double2 &sC, double &acc) {
+                                        int j, double2 &tS, double2 &tC, double2 &aSj, double2 &sC, double &acc,
+                                        double *wb, bool zRes) {
   const int PX = a.PX;
   double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R];
   double zW[R], sW[R], zE[R], sE[R], aWEl[R];
@@ -477,7 +479,7 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
     zN[r] = sN[r] = aSN[r] = aWv[r] = aCv[r] = xv[r] = make_double2(0.0, 0.0);
     zW[r] = sW[r] = zE[r] = sE[r] = aWEl[r] = 0.0;
     if (it.active) {
-      zN[r] = ld2(a.z + id + PX);
+      zN[r] = (zRes && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2(a.z + id + PX);
       sN[r] = ld2(sOld + id + PX);
       aSN[r] = ldg2(a.aS + id + PX);
       aWv[r] = ldg2(a.aW + id);
@@ -501,7 +503,9 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
     if (it.active) {
       double2 qv = make_double2(q0, q1);
       st2(sNew + id, tC);
-      st2(a.q + id, qv);
+      const bool inRes = wb && j + r - it.j0 < a.resRows;
+      if (inRes) st2(wb + (size_t)(j + r - it.j0) * 64, qv);   // q replaces the dead z of this row in the resident strip
+      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2(a.q + id, qv);   // neighbours read the rim
       push2v(a, it, j + r, sNew, tC, a.q, qv);
       if (updX) {   // deferred x += alpha s of the previous iteration (sC = old s of this row)
         xv[r] = make_double2(xv[r].x + alphaPrev * sC.x, xv[r].y + alphaPrev * sC.y);
@@ -516,7 +520,7 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
 }
 
 __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew, double beta,
-                         bool saveMin, double alphaPrev, bool updX, double *sm) {
+                         bool saveMin, double alphaPrev, bool updX, double *sm, double *wb, bool zRes) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -526,15 +530,15 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
     size_t idx = it.base;
     double2 tS = make_double2(0.0, 0.0), tC = tS, aSj = tS, sC = tS;
     if (it.active) {
-      double2 z0 = ld2(a.z + idx - PX), s0 = ld2(sOld + idx - PX), z1 = ld2(a.z + idx), s1 = ld2(sOld + idx);
+      double2 z0 = ld2(a.z + idx - PX), s0 = ld2(sOld + idx - PX), z1 = zRes ? ld2(wb) : ld2(a.z + idx), s1 = ld2(sOld + idx);
       tS = make_double2(z0.x + beta * s0.x, z0.y + beta * s0.y);
       tC = make_double2(z1.x + beta * s1.x, z1.y + beta * s1.y);
       aSj = ldg2(a.aS + idx);
       sC = s1;
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0]);
-    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0]);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes);
+    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes);
   }
   block_partials<1, false>(a, acc, sm);
 }
@@ -542,7 +546,7 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
 template <int R>
 __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
                                          const double *__restrict__ sCur, double alpha, const Item2 &it, size_t idx,
-                                         int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH) {
+                                         int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH, double *wb) {
   const int PX = a.PX;
   double2 rN[R], qN[R], pCv[R], pWv[R], pSN[R];
   double rW[R], qW[R], rE[R], qE[R], pWEl[R];
@@ -553,7 +557,7 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
     rW[r] = qW[r] = rE[r] = qE[r] = pWEl[r] = 0.0;
     if (it.active) {
       rN[r] = ld2(rOld + id + PX);
-      qN[r] = ld2(a.q + id + PX);
+      qN[r] = (wb && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2(a.q + id + PX);
       pCv[r] = ldg2(a.pC + id);
       pWv[r] = ldg2(a.pW + id);
       pSN[r] = ldg2(a.pS + id + PX);
@@ -575,7 +579,9 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
     if (it.active) {
       double2 zv = make_double2(z0, z1);
       st2(rNew + id, rC);
-      st2(a.z + id, zv);
+      const bool inRes = wb && j + r - it.j0 < a.resRows;
+      if (inRes) st2(wb + (size_t)(j + r - it.j0) * 64, zv);   // z replaces the dead q of this row
+      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2(a.z + id, zv);
       push2v(a, it, j + r, rNew, rC, a.z, zv);
       accE += rC.x * rC.x;
       accE += rC.y * rC.y;
@@ -587,7 +593,7 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
 }
 
 __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
-                          const double *__restrict__ sCur, double alpha, double *sm) {
+                          const double *__restrict__ sCur, double alpha, double *sm, double *wb) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -602,14 +608,14 @@ __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, do
     size_t idx = it.base;
     double2 rS = make_double2(0.0, 0.0), rC = rS, pSj = rS;
     if (it.active) {
-      double2 r0 = ld2(rOld + idx - PX), q0 = ld2(a.q + idx - PX), r1 = ld2(rOld + idx), q1 = ld2(a.q + idx);
+      double2 r0 = ld2(rOld + idx - PX), q0 = ld2(a.q + idx - PX), r1 = ld2(rOld + idx), q1 = wb ? ld2(wb) : ld2(a.q + idx);
       rS = make_double2(r0.x - alpha * q0.x, r0.y - alpha * q0.y);
       rC = make_double2(r1.x - alpha * q1.x, r1.y - alpha * q1.y);
       pSj = ldg2(a.pS + idx);
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) ca2_rows<2>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1]);
-    if (j <= it.j1) ca2_rows<1>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1]);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) ca2_rows<2>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb);
+    if (j <= it.j1) ca2_rows<1>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb);
   }
   block_partials<2, false>(a, acc, sm);
 }
@@ -617,6 +623,13 @@ __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, do
 __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
+  // Resident strips: with one equal strip per warp (balanced partition) the warp that produces q
+  // in phase B is the one that consumes it in phase CA, and likewise for z from CA to the next B,
+  // and q / z are never alive together.  They therefore share one 64 x RY2 strip of shared
+  // memory per warp (thread-private columns, no barrier); only the rim of a strip is written to
+  // global memory, for the neighbouring strips.  Saves 4 of the 16 words per point and iteration.
+  extern __shared__ __align__(16) double cg_wbuf[];
+  double *wb = a.resident ? cg_wbuf + (size_t)(threadIdx.x >> 5) * a.resRows * 64 + 2 * (threadIdx.x & 31) : nullptr;
   double t1[1], t2[2];
   unsigned long long rseq = a.seq0;
 
@@ -661,7 +674,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
+      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm, wb, wb != nullptr && it2d > 1);
       else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
       saveMin = false;
       scur ^= 1;
@@ -670,7 +683,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
       const double alpha = eta_qrN / t1[0];
       sLast = a.s[scur];
       alphaLast = alpha;
-      if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm);
+      if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm, wb);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
       grid.sync();
@@ -1049,13 +1062,34 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   decomp(64, a.nIB2, a.nJB2, a.RY2, a.nItems2);
   int blocks = std::min(maxBlocks, (std::max(a.nItems, a.vec2 ? a.nItems2 : 0) + CG_WARPS - 1) / CG_WARPS);
   if (blocks < 1) blocks = 1;
+  a.resident = 0;
+  a.resRows = 0;
+  size_t dynSmem = 0;
+  if (a.vec2 && a.nItems2 <= blocks * CG_WARPS && !getenv("MITGCM_B200_CG2D_NORESIDENT")) {
+    // as many rows of each strip as fit next to a second CTA on the SM (a whole vector of a
+    // 2048^2 tile is 227 KB per SM and does not fit: half of every strip stays resident there)
+    // (larger carve-outs starve the L1: 100 KB per CTA was measured 25 % slower than none)
+    const int rowsFit = (int)((size_t)(56 * 1024) / ((size_t)CG_WARPS * 64 * sizeof(double)));
+    const int rows = std::min(a.RY2, rowsFit);
+    const size_t need = (size_t)CG_WARPS * rows * 64 * sizeof(double);
+    int nb = 0;
+    // worth it only when a good part of the strip fits (12 % of a 4096^2 strip was measured a net loss)
+    if (rows >= 1 && rows * 3 >= a.RY2 && cudaFuncSetAttribute(cg2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg2d_kernel, CG_THREADS, need) == cudaSuccess &&
+        nb * c.numSMs >= blocks) {
+      a.resident = 1;
+      a.resRows = rows;
+      dynSmem = need;
+    }
+    cudaGetLastError();
+  }
   // zero-initialised work arrays incl. ring 0 / sN+1 (cg2d.F:142-147)
   size_t bytes = g.n2 * sizeof(double);
   for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->v}) MG_CUDA(cudaMemsetAsync(p, 0, bytes, c.stream));
   void *args[] = {&a};
   c.launches++;
   MG_CUDA(cudaLaunchCooperativeKernel(sr ? (void *)cg2d_sr_kernel : (void *)cg2d_kernel, dim3(blocks), dim3(CG_THREADS),
-                                      args, 0, c.stream));
+                                      args, sr ? 0 : dynSmem, c.stream));
   Cg2dOut out;
   MG_CUDA(cudaMemcpyAsync(&out, w->out, sizeof(out), cudaMemcpyDeviceToHost, c.stream));
   if (!from_device(cg2d_b, a.b, g.n2)) return false;

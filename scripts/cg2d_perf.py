@@ -48,8 +48,8 @@ for rep in range(reps):
     r = rt.cg2d(bd, xd, iters, -1, sr=sr)
     dt = time.perf_counter() - t0
     n = r["numIters"]
-    gbs = 128.0 * N * N * n / dt / 1e9
+    gbs = 136.0 * N * N * n / dt / 1e9
     print(f"N={N} sr={sr} iters={n} time={dt*1e3:.2f} ms  {n/dt:.1f} it/s  {dt/n*1e6:.1f} us/it  "
-          f"{gbs:.1f} GB/s (128 B/pt/it) = {gbs/6556.2*100:.1f}% of measured HBM peak; "
+          f"{gbs:.1f} GB/s (136 B/pt/it, SURVEY 8d) = {gbs/6556.2*100:.1f}% of measured HBM peak; "
           f"res {r['firstResidual']:.3e}->{r['lastResidual']:.3e}")
 rt.finalize()
