@@ -29,6 +29,14 @@ namespace mg {
 #endif
 constexpr int FT_X = 32, FT_Y = FT_YV, FT_W = FT_X + 2, FT_H = FT_Y + 2, FT_N = FT_W * FT_H;
 
+// Vertical grid arrays staged once per CTA (they were an exposed L2 round trip per level).
+constexpr int FT_NRMAX = 160;
+struct VertSmem { double drF[FT_NRMAX], rdrF[FT_NRMAX], rdrC[FT_NRMAX + 1]; };
+__device__ __forceinline__ void stage_vert(VertSmem &vs, const TileGrid &g, int t, int nthreads) {
+  for (int k = t; k < g.Nr; k += nthreads) { vs.drF[k] = g.drF[k]; vs.rdrF[k] = g.recip_drF[k]; }
+  for (int k = t; k <= g.Nr; k += nthreads) vs.rdrC[k] = g.recip_drC[k];
+}
+
 struct DynSmem {
   double u[FT_N], v[FT_N], uT[FT_N], vT[FT_N], hW[FT_N], hS[FT_N], hC[FT_N], hZ[FT_N], wA[FT_N], mC[2][FT_N];
 };
@@ -48,6 +56,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNF_MINB)
   int se[2];
   size_t sg[2];
   bool sv_[2];
+#pragma unroll
   for (int r = 0; r < 2; r++) {
     int e = t + r * FT_X * FT_Y;
     sv_[r] = e < FT_N;
@@ -75,6 +84,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNF_MINB)
   double uK = st.u[s], vK = st.v[s], mWk = g.maskW[s], mSk = g.maskS[s];
   double kapUk = st.kapU[s], kapVk = st.kapV[s];
   // interface k = 1: stage w*rA and maskC of level 1 to form the surface flux (mom_fluxform.F:384-417)
+#pragma unroll
   for (int r = 0; r < 2; r++)
     if (sv_[r]) { sm.wA[se[r]] = st.w[sg[r]] * g.rA[sg[r]]; sm.mC[0][se[r]] = g.maskC[sg[r]]; }
   __syncthreads();
@@ -98,6 +108,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNF_MINB)
     const double rhW = g.recip_hFacW[s3], rhS = g.recip_hFacS[s3];
     const double guOld = guNm1[s3], gvOld = gvNm1[s3];
     // ---- stage level k (and interface k+1) ----
+#pragma unroll
     for (int r = 0; r < 2; r++)
       if (sv_[r]) {
         const size_t q = sg[r] + ko;
@@ -108,6 +119,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNF_MINB)
         if (below) { sm.wA[se[r]] = st.w[q + slab] * g.rA[sg[r]]; sm.mC[cur ^ 1][se[r]] = g.maskC[q + slab]; }
       }
     __syncthreads();
+#pragma unroll
     for (int r = 0; r < 2; r++)
       if (sv_[r]) {     // MOM_CALC_HFACZ at the south-west corner of every staged cell that has its neighbours
         int e = se[r], li = e % FT_W, lj = e / FT_W;
@@ -260,7 +272,9 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
                     double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB) {
   extern __shared__ __align__(16) unsigned char dyn_pipe_smem[];
   DynPipeSmem &sm = *reinterpret_cast<DynPipeSmem *>(dyn_pipe_smem);
+  __shared__ VertSmem vs;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FT_X + tx;
+  stage_vert(vs, g, t, FT_X * FT_Y);
   const int i0 = blockIdx.x * FT_X, j0 = blockIdx.y * FT_Y;     // output range 0..sN+1 (dynamics.F:191-192)
   const int i = i0 + tx, j = j0 + ty;
   const bool active = i <= g.sNx + 1 && j <= g.sNy + 1;
@@ -279,6 +293,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
   int se[2];
   size_t sg[2];
   bool sv_[2];
+#pragma unroll
   for (int r = 0; r < 2; r++) {
     int e = t + r * FT_X * FT_Y;
     sv_[r] = e < FT_N;
@@ -308,6 +323,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
   // k-invariant metrics of the staged cells, the surface interface (w*rA, maskC of level 1:
   // mom_fluxform.F:384-417), and the asynchronous prefetch of level 1 into ring slot 1
   int rb = 1;
+#pragma unroll
   for (int r = 0; r < 2; r++)
     if (sv_[r]) {
       sm.dyG[se[r]] = g.dyG[sg[r]]; sm.dxG[se[r]] = g.dxG[sg[r]]; sm.rA[se[r]] = g.rA[sg[r]];
@@ -325,7 +341,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
   __syncthreads();
   for (int k = 1; k <= g.Nr; k++) {
     const size_t ko = slab * (size_t)(k - 1);
-    const double drFk = g.drF[k - 1], rdrF = g.recip_drF[k - 1];
+    const double drFk = vs.drF[k - 1], rdrF = vs.rdrF[k - 1];
     const bool below = k + 1 <= g.Nr;
     // own column: issue every global load of this level up front, so one memory latency is exposed
     // per level (the compiler cannot hoist loads over the barriers below)
@@ -338,6 +354,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
     // ---- level k has been prefetched into ring slot rb (cp.async); derive what the fluxes share ----
     __pipeline_wait_prior(0);
     __syncthreads();
+#pragma unroll
     for (int r = 0; r < 2; r++)
       if (sv_[r]) {
         const int e = se[r], li = e % FT_W, lj = e / FT_W;
@@ -355,6 +372,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
       }
     __syncthreads();
     if (below) {      // prefetch level k+1 into the other slot while this level is computed
+#pragma unroll
       for (int r = 0; r < 2; r++)
         if (sv_[r]) dyn_pipe_prefetch(sm, rb ^ 1, se[r], sg[r], g, st, slab, k + 1, k + 2 <= g.Nr);
     }
@@ -395,8 +413,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
         const double yv0 = dxV00 * drFk * hZ00 * (-p.viscAhZ * (u00 - SM(u, 0, -1)) + p.viscA4Z * (0. - 0.)) * rdyU00;
         double fVrUp = 0., fVrDw = 0.;
         if (!p.implicitViscosity) {
-          if (k > 1) fVrUp = -kapUk * rAw * (uK - uKm1) * p.rkSign * g.recip_drC[k - 1] * mWk * mWkm1;
-          if (below) fVrDw = -kapUkp1 * rAw * (uKp1 - uK) * p.rkSign * g.recip_drC[k] * mWkp1 * mWk;
+          if (k > 1) fVrUp = -kapUk * rAw * (uK - uKm1) * p.rkSign * vs.rdrC[k - 1] * mWk * mWkm1;
+          if (below) fVrDw = -kapUkp1 * rAw * (uKp1 - uK) * p.rkSign * vs.rdrC[k] * mWkp1 * mWk;
         }
         guD = -rhW * rdrF * r_rAw * ((xv1 - xv0) * AhFac + (yv1 - yv0) * AhFac + (fVrDw - fVrUp) * p.rkSign * ArFac);
         // V: MOM_V_XVISCFLUX, MOM_V_YVISCFLUX, MOM_V_RVISCFLUX
@@ -406,8 +424,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
         const double yw0 = dxF0m * drFk * SM(hC, 0, -1) * (-p.viscAhD * (v00 - SM(v, 0, -1)) + p.viscA4D * (0. - 0.)) * rdyF0m;
         double gVrUp = 0., gVrDw = 0.;
         if (!p.implicitViscosity) {
-          if (k > 1) gVrUp = -kapVk * rAs * (vK - vKm1) * p.rkSign * g.recip_drC[k - 1] * mSk * mSkm1;
-          if (below) gVrDw = -kapVkp1 * rAs * (vKp1 - vK) * p.rkSign * g.recip_drC[k] * mSkp1 * mSk;
+          if (k > 1) gVrUp = -kapVk * rAs * (vK - vKm1) * p.rkSign * vs.rdrC[k - 1] * mSk * mSkm1;
+          if (below) gVrDw = -kapVkp1 * rAs * (vKp1 - vK) * p.rkSign * vs.rdrC[k] * mSkp1 * mSk;
         }
         gvD = -rhS * rdrF * r_rAs * ((xw1 - xw0) * AhFac + (yw1 - yw0) * AhFac + (gVrDw - gVrUp) * p.rkSign * ArFac);
         if (p.no_slip_sides) {   // MOM_U_SIDEDRAG / MOM_V_SIDEDRAG
@@ -419,7 +437,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
         }
         if (p.bottomDragTerms) {  // MOM_{U,V}_BOTDRAG_COEFF with selectBotDragQuadr = -1
           const double viscFac = p.no_slip_bottom ? 2. : 0.;
-          const double recDrC = (k == g.Nr) ? rdrF : g.recip_drC[k];
+          const double recDrC = (k == g.Nr) ? rdrF : vs.rdrC[k];
           double cu = p.bottomDragLinear * 1., cv = p.bottomDragLinear * 1.;
           if (p.no_slip_bottom && p.bottomVisc_pCell) { cu = cu + kapUkp1 * recDrC * viscFac * rhW; cv = cv + kapVkp1 * recDrC * viscFac * rhS; }
           else if (p.no_slip_bottom) { cu = cu + kapUkp1 * recDrC * viscFac; cv = cv + kapVkp1 * recDrC * viscFac; }
@@ -448,8 +466,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 2)
       if (momForcing) {
         double ge = 0., he = 0.;
         if (k == 1) {
-          if (i >= 1 && i <= g.sNx + 1) ge = 0. + sfu * g.recip_drF[0] * rhW;
-          if (j >= 1 && j <= g.sNy + 1) he = 0. + sfv * g.recip_drF[0] * rhS;
+          if (i >= 1 && i <= g.sNx + 1) ge = 0. + sfu * vs.rdrF[0] * rhW;
+          if (j >= 1 && j <= g.sNy + 1) he = 0. + sfv * vs.rdrF[0] * rhS;
         }
         gu = gu + ge; gv = gv + he;
       }
@@ -490,7 +508,10 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
                        const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
                        double *__restrict__ gtNm1, GadPar p, double abFac) {
   __shared__ ThermoSmem sm;
+  __shared__ VertSmem vs;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FT_X + tx;
+  stage_vert(vs, g, t, FT_X * FT_Y);
+  __syncthreads();
   const int i0 = 1 + blockIdx.x * FT_X, j0 = 1 + blockIdx.y * FT_Y;
   const int i = i0 + tx, j = j0 + ty;
   const bool active = i <= g.sNx && j <= g.sNy;
@@ -499,6 +520,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
   int se[2];
   size_t sg[2];
   bool sv_[2];
+#pragma unroll
   for (int r = 0; r < 2; r++) {
     int e = t + r * FT_X * FT_Y;
     sv_[r] = e < FT_N;
@@ -518,11 +540,12 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
   double fVdn = 0., rTransKp1 = 0.;
   for (int k = g.Nr; k >= 1; k--) {
     const size_t ko = slab * (size_t)(k - 1);
-    const double drFk = g.drF[k - 1];
+    const double drFk = vs.drF[k - 1];
     // own-column loads first: one exposed memory latency per level
     const size_t s3 = s + ko;
     const double Tkm1 = k >= 2 ? theta[s3 - slab] : 0., mC = g.maskC[s3], mCm1 = k >= 2 ? g.maskC[s3 - slab] : 0.;
     const double wK = w[s3], kapK = kapT[s3], rhC = g.recip_hFacC[s3], gtOld = gtNm1[s3];
+#pragma unroll
     for (int r = 0; r < 2; r++)
       if (sv_[r]) {
         const size_t q = sg[r] + ko;
@@ -556,10 +579,10 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
         rTrans = wK * rA * maskUp;
         if (p.calcAdvection && !p.implicitAdvection) fvu = fvu + mCm1 * rTrans * (T00 + Tkm1) * 0.5;
         double df = 0.;
-        if (!p.implicitDiffusion) df = -kapK * maskUp * rA * g.recip_drC[k - 1] * (T00 - Tkm1) * p.rkSign;
+        if (!p.implicitDiffusion) df = -kapK * maskUp * rA * vs.rdrC[k - 1] * (T00 - Tkm1) * p.rkSign;
         fvu = fvu + df;
       }
-      double gT = 0. - rhC * g.recip_drF[k - 1] * r_rA *
+      double gT = 0. - rhC * vs.rdrF[k - 1] * r_rA *
                            ((fz1 - fz0) + (fm1 - fm0) + (fVdn - fvu) * p.rkSign -
                             T00 * ((SM(uT, 1, 0) - SM(uT, 0, 0)) * advFac + (SM(vT, 0, 1) - SM(vT, 0, 0)) * advFac +
                                    (rTransKp1 - rTrans) * rAdvFac));
@@ -577,12 +600,13 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
 
 inline bool thermo_fast_ok(const Geom &g, const GadPar &p) {
   return p.advScheme == ADV_CENTERED_2ND && p.vertAdvScheme == ADV_CENTERED_2ND && p.diffK4 == 0. && !p.useDiffKr4 &&
-         g.OLx >= 2 && g.OLy >= 2 && !getenv("MITGCM_B200_GENERIC_STEP");
+         g.OLx >= 2 && g.OLy >= 2 && g.Nr < FT_NRMAX && !getenv("MITGCM_B200_GENERIC_STEP");
 }
 
 inline bool dyn_fast_ok(const Geom &g, const MomPar &p) {
   return !p.useBiharmonicVisc && p.selectBotDragQuadr == -1 && (p.selectCoriScheme == 0 || p.selectCoriScheme == 2) &&
-         !(p.usingSphericalPolarGrid && p.metricTerms) && g.OLx >= 2 && g.OLy >= 2 && !getenv("MITGCM_B200_GENERIC_STEP");
+         !(p.usingSphericalPolarGrid && p.metricTerms) && g.OLx >= 2 && g.OLy >= 2 && g.Nr < FT_NRMAX &&
+         !getenv("MITGCM_B200_GENERIC_STEP");
 }
 
 }  // namespace mg
