@@ -177,6 +177,96 @@ def cartesian_grid(d: Dims, delX, delY, delR, xgOrigin=0.0, ygOrigin=0.0,
     return g
 
 
+def spherical_polar_grid(d: Dims, delX, delY, delR, xgOrigin=0.0, ygOrigin=0.0,
+                         rSphere=6370e3, rotationPeriod=86164.0, gBaro=9.81, cosPower=0.0) -> Grid:
+    """usingSphericalPolarGrid: INI_SPHERICAL_POLAR_GRID (model/src/ini_spherical_polar_grid.F:60-230)
+    + INI_LOCAL_GRID (ini_local_grid.F:100-165) + INI_CORI with selectCoriMap = 2 (ini_cori.F) +
+    INI_LINEAR_PHISURF.  delX/delY in degrees.  Transcendentals go through libm (math.sin/cos/tan),
+    which is what the gfortran-built reference calls."""
+    import math
+    assert cosPower == 0.0, "cosPower != 0 (cosFacU/V) not restated"
+    delX = np.asarray(delX, dtype=np.float64)
+    delY = np.asarray(delY, dtype=np.float64)
+    assert len(delX) == d.Nx and len(delY) == d.Ny and len(delR) == d.Nr
+    PI = 3.14159265358979323844
+    deg2rad = 2.0 * PI / 360.0
+    omega = 2.0 * PI / rotationPeriod
+    g = Grid(d)
+    z2 = lambda: np.zeros(d.shape2)
+    for n in GRID2D:
+        g.a[n] = z2()
+    xC, yC, xG, yG = z2(), z2(), z2(), z2()
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    PX, PY = d.PX, d.PY
+    for bj in range(d.nSy):
+        for bi in range(d.nSx):
+            iG0 = (d.myPx * d.nSx + bi) * sx
+            jG0 = (d.myPy * d.nSy + bj) * sy
+            xG0 = float(xgOrigin)
+            for i in range(iG0):
+                xG0 = xG0 + delX[i]
+            for i in range(1, ox + 1):
+                xG0 = xG0 - delX[(iG0 - i + ox * d.Nx) % d.Nx]
+            yG0 = float(ygOrigin)
+            for j in range(jG0):
+                yG0 = yG0 + delY[j]
+            for j in range(1, oy + 1):
+                yG0 = yG0 - delY[(jG0 - j + oy * d.Ny) % d.Ny]
+            # delXloc(0-OLx:sNx+OLx): array index a <-> Fortran index a - ox
+            dXl = [float(delX[(iG0 + (a - ox) - 1 + ox * d.Nx) % d.Nx]) for a in range(PX + 1)]
+            dYl = [float(delY[(jG0 + (a - oy) - 1 + oy * d.Ny) % d.Ny]) for a in range(PY + 1)]
+            xGl = [xG0]
+            for a in range(1, PX + 1):
+                xGl.append(xGl[-1] + dXl[a])
+            yGl = [yG0]
+            for a in range(1, PY + 1):
+                yGl.append(yGl[-1] + dYl[a])
+            A = g.a
+            for jj in range(PY):
+                for ii in range(PX):
+                    xG[bj, bi, jj, ii] = xGl[ii]
+                    yG[bj, bi, jj, ii] = yGl[jj]
+                    xC[bj, bi, jj, ii] = 0.25 * (((xGl[ii] + xGl[ii + 1]) + xGl[ii]) + xGl[ii + 1])
+                    yc = 0.25 * (((yGl[jj] + yGl[jj]) + yGl[jj + 1]) + yGl[jj + 1])
+                    yC[bj, bi, jj, ii] = yc
+                    dlon, dlat = dXl[ii + 1], dYl[jj + 1]
+                    A["dxF"][bj, bi, jj, ii] = rSphere * math.cos(yc * deg2rad) * dlon * deg2rad
+                    A["dyF"][bj, bi, jj, ii] = rSphere * dlat * deg2rad
+                    lat = 0.5 * (yGl[jj] + yGl[jj])
+                    dxg = rSphere * math.cos(deg2rad * lat) * dlon * deg2rad
+                    A["dxG"][bj, bi, jj, ii] = 0.0 if dxg < 1.0 else dxg
+                    A["dyG"][bj, bi, jj, ii] = rSphere * dlat * deg2rad
+                    A["rA"][bj, bi, jj, ii] = rSphere * rSphere * dlon * deg2rad * abs(
+                        math.sin((lat + dlat) * deg2rad) - math.sin(lat * deg2rad))
+                    dlatS = 0.5 * (dYl[jj + 1] + dYl[jj])
+                    ras = rSphere * rSphere * dlon * deg2rad * abs(
+                        math.sin(yc * deg2rad) - math.sin((yc - dlatS) * deg2rad))
+                    A["rAs"][bj, bi, jj, ii] = 0.0 if (abs(yc) > 90.0 or abs(yc - dlatS) > 90.0) else ras
+                    latZ = 0.5 * (yGl[jj] + yGl[jj + 1])
+                    dlonZ = 0.5 * (dXl[ii + 1] + dXl[ii])
+                    raz = rSphere * rSphere * dlonZ * deg2rad * abs(
+                        math.sin(latZ * deg2rad) - math.sin((latZ - dlatS) * deg2rad))
+                    A["rAz"][bj, bi, jj, ii] = 0.0 if (abs(latZ) > 90.0 or abs(latZ - dlatS) > 90.0) else raz
+                    A["tanPhiAtU"][bj, bi, jj, ii] = math.tan(latZ * deg2rad)
+                    A["tanPhiAtV"][bj, bi, jj, ii] = math.tan(lat * deg2rad)
+                    A["fCori"][bj, bi, jj, ii] = 2.0 * omega * math.sin(yc * deg2rad)
+                    A["fCoriG"][bj, bi, jj, ii] = 2.0 * omega * math.sin(yGl[jj] * deg2rad)
+            dxF, dyF, dxG, dyG, rA = (A[n][bj, bi] for n in "dxF dyF dxG dyG rA".split())
+            A["dxC"][bj, bi][:, 1:] = 0.5 * (dxF[:, 1:] + dxF[:, :-1])
+            A["dyC"][bj, bi][1:, :] = 0.5 * (dyF[1:, :] + dyF[:-1, :])
+            A["dxV"][bj, bi][1:, 1:] = 0.5 * (dxG[1:, 1:] + dxG[1:, :-1])
+            A["dyU"][bj, bi][1:, 1:] = 0.5 * (dyG[1:, 1:] + dyG[:-1, 1:])
+            A["rAw"][bj, bi][:, 1:] = 0.5 * (rA[:, 1:] + rA[:, :-1])
+    g.a["xC"], g.a["yC"], g.a["xG"], g.a["yG"] = xC, yC, xG, yG
+    g.a["Bo_surf"] = np.full(d.shape2, gBaro)
+    g.a["recip_Bo"] = np.full(d.shape2, 1.0 / gBaro)
+    g.a["cosFacU"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.a["cosFacV"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.set_recips()
+    set_vertical(g, delR)
+    return g
+
+
 def set_vertical(g: Grid, delR) -> None:
     """INI_VERTICAL_GRID for z coordinates: drF = delR, drC(1) = delR(1)/2,
     drC(k) = (delR(k-1)+delR(k))/2, drC(Nr+1) = delR(Nr)/2."""
@@ -195,6 +285,11 @@ def set_vertical(g: Grid, delR) -> None:
     for k in range(Nr):
         rF[k + 1] = rF[k] - delR[k]
     g.a["rF"] = rF
+    rC = np.empty(Nr)
+    rC[0] = rF[0] - drC[0]
+    for k in range(1, Nr):
+        rC[k] = rC[k - 1] - drC[k]
+    g.a["rC"] = rC
 
 
 def masks_from_depth(g: Grid, depth_global: np.ndarray, hFacMin=1.0, hFacMinDr=0.0) -> None:

@@ -95,9 +95,9 @@ void og_timestep(const og_grid *g, const og_params *p, int bi, int bj, int k,
 /* Right-hand side of the surface-pressure equation for one tile:
  * solve_for_pressure.F:120-238 (cg2d_x = Bo_surf*etaN, cg2d_b = 0, CALC_DIV_GHAT
  * for k = Nr..1 with implicDiv2DFlow = 1 (calc_div_ghat.F:64-167), free-surface
- * term with exactConserv = F). */
+ * term on etaFS = etaH (exactConserv, :213-222) or etaN (:224-233)). */
 void og_solve_rhs(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf,
-                  const double *etaN, const double *gU, const double *gV,
+                  const double *etaN, const double *etaFS, const double *gU, const double *gV,
                   double *cg2d_b, double *cg2d_x) {
   SETUP
   const size_t ns = px * py;
@@ -125,7 +125,7 @@ void og_solve_rhs(const og_grid *g, const og_params *p, int bi, int bj, const do
   for (int j = 1; j <= sNy; j++)
     for (int i = 1; i <= sNx; i++)
       G2(cg2d_b, i, j) = G2(cg2d_b, i, j)
-          - p->freeSurfFac * G2(g->rA, i, j) / p->deltaTMom / p->deltaTFreeSurf * G2(etaN, i, j);
+          - p->freeSurfFac * G2(g->rA, i, j) * 1. / p->deltaTMom / p->deltaTFreeSurf * G2(etaFS, i, j);
   free(xA);
 }
 

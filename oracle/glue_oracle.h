@@ -13,14 +13,37 @@ void og_timestep(const og_grid *g, const og_params *p, int bi, int bj, int k,
                  int momForcing, int momDissip_In_AB, double abFac,
                  const double *uVel, const double *vVel,
                  double *gU, double *gV, double *guNm1, double *gvNm1);
+/* etaFS = the field of the free-surface term: etaH when exactConserv (solve_for_pressure.F:213-222),
+ * else etaN (:224-233). */
 void og_solve_rhs(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf,
-                  const double *etaN, const double *gU, const double *gV,
+                  const double *etaN, const double *etaFS, const double *gU, const double *gV,
                   double *cg2d_b, double *cg2d_x);
 void og_correction_step(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf,
                         const double *etaN, const double *gU, const double *gV,
                         double *uVel, double *vVel);
 void og_integrate_for_w(const og_grid *g, const og_params *p, int bi, int bj,
                         const double *uVel, const double *vVel, double *wVel);
+
+/* ---- physics glue of config 2 (phys_oracle.c) ---- */
+typedef struct { double rhoNil, rhoConst, tAlpha, sBeta; } og_eos;
+void og_density_ivdc(const og_grid *g, const og_params *p, const og_eos *e, int bi, int bj,
+                     const double *theta, const double *salt, const double *tRef, const double *sRef,
+                     double *rhoInSitu, double *IVDConvCount);
+void og_forcing_surf_relax_T(const og_grid *g, int bi, int bj, const double *theta, const double *SST,
+                             const double *lambdaThetaClimRelax, double recip_Cp, double mass2rUnit,
+                             double *surfaceForcingT);
+void og_apply_forcing_T(const og_grid *g, int bi, int bj, int k, const double *surfaceForcingT, double *gtForc);
+void og_calc_3d_diffusivity(const og_grid *g, int bi, int bj, const double *IVDConvCount, double ivdc_kappa,
+                            const double *KbryanLewis79, const double *diffKrNrT, double *kappaRk);
+int og_gad_implicit_r(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax,
+                      const double *deltaTLev, const double *kappaRX, const double *recip_hFac, double *gTracer);
+void og_calc_phi_hyd(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax, int k,
+                     const double *rhoInSitu, const double *rF, const double *rC, double gravity,
+                     double recip_rhoConst, const double *phi0surf,
+                     double *phiHydF, double *phiHydC, double *dPhiHydX, double *dPhiHydY);
+void og_integr_continuity_ec(const og_grid *g, const og_params *p, int bi, int bj, const double *uVel,
+                             const double *vVel, const double *etaH, double *dEtaHdt, double *etaN,
+                             int updateEtaN);
 #ifdef __cplusplus
 }
 #endif

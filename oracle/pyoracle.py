@@ -170,9 +170,10 @@ class Oracle:
                              int(momForcing), int(momDissip_In_AB), C.c_double(abFac), ptr(uVel), ptr(vVel),
                              ptr(gU), ptr(gV), ptr(guNm1), ptr(gvNm1))
 
-    def solve_rhs(self, bi, bj, etaN, gU, gV, b, x):
+    def solve_rhs(self, bi, bj, etaN, gU, gV, b, x, etaH=None):
+        """etaH given = exactConserv (solve_for_pressure.F:213-222)."""
         self.lib.og_solve_rhs(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]), ptr(etaN),
-                              ptr(gU), ptr(gV), ptr(b), ptr(x))
+                              ptr(etaN if etaH is None else etaH), ptr(gU), ptr(gV), ptr(b), ptr(x))
 
     def correction_step(self, bi, bj, etaN, gU, gV, uVel, vVel):
         self.lib.og_correction_step(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]),
@@ -180,3 +181,37 @@ class Oracle:
 
     def integrate_for_w(self, bi, bj, uVel, vVel, wVel):
         self.lib.og_integrate_for_w(C.byref(self.g), C.byref(self.p), bi, bj, ptr(uVel), ptr(vVel), ptr(wVel))
+
+    # ---- physics glue of config 2 (phys_oracle.c) ----
+    def density_ivdc(self, eos, bi, bj, theta, salt, tRef, sRef, rhoInSitu, IVDConvCount):
+        self.lib.og_density_ivdc(C.byref(self.g), C.byref(self.p), C.byref(eos), bi, bj, ptr(theta), ptr(salt),
+                                 ptr(tRef), ptr(sRef), ptr(rhoInSitu), ptr(IVDConvCount))
+
+    def forcing_surf_relax_T(self, bi, bj, theta, SST, lam, recip_Cp, mass2rUnit, sfT):
+        self.lib.og_forcing_surf_relax_T(C.byref(self.g), bi, bj, ptr(theta), ptr(SST), ptr(lam),
+                                         C.c_double(recip_Cp), C.c_double(mass2rUnit), ptr(sfT))
+
+    def apply_forcing_T(self, bi, bj, k, sfT, gtForc):
+        self.lib.og_apply_forcing_T(C.byref(self.g), bi, bj, k, ptr(sfT), ptr(gtForc))
+
+    def calc_3d_diffusivity(self, bi, bj, IVDConvCount, ivdc_kappa, KbryanLewis79, diffKrNrT, kappaRk):
+        self.lib.og_calc_3d_diffusivity(C.byref(self.g), bi, bj, ptr(IVDConvCount), C.c_double(ivdc_kappa),
+                                        ptr(KbryanLewis79), ptr(diffKrNrT), ptr(kappaRk))
+
+    def gad_implicit_r(self, bi, bj, iMin, iMax, jMin, jMax, deltaTLev, kappaRX, recip_hFac, gTracer):
+        return self.lib.og_gad_implicit_r(C.byref(self.g), bi, bj, iMin, iMax, jMin, jMax, ptr(deltaTLev),
+                                          ptr(kappaRX), ptr(recip_hFac), ptr(gTracer))
+
+    def calc_phi_hyd(self, bi, bj, iMin, iMax, jMin, jMax, k, rhoInSitu, rF, rC, gravity, recip_rhoConst,
+                     phi0surf, phiHydF, phiHydC, dPhiHydX, dPhiHydY):
+        self.lib.og_calc_phi_hyd(C.byref(self.g), bi, bj, iMin, iMax, jMin, jMax, k, ptr(rhoInSitu), ptr(rF),
+                                 ptr(rC), C.c_double(gravity), C.c_double(recip_rhoConst), ptr(phi0surf),
+                                 ptr(phiHydF), ptr(phiHydC), ptr(dPhiHydX), ptr(dPhiHydY))
+
+    def integr_continuity_ec(self, bi, bj, uVel, vVel, etaH, dEtaHdt, etaN, updateEtaN=True):
+        self.lib.og_integr_continuity_ec(C.byref(self.g), C.byref(self.p), bi, bj, ptr(uVel), ptr(vVel),
+                                         ptr(etaH), ptr(dEtaHdt), ptr(etaN), int(updateEtaN))
+
+
+class Eos(C.Structure):
+    _fields_ = [(n, C.c_double) for n in "rhoNil rhoConst tAlpha sBeta".split()]

@@ -78,3 +78,56 @@ def test_cg2d_sr_converges_to_same_solution():
         assert abs(ra["numIters"] - rb["numIters"]) <= 3
         assert rb["lastResidual"] < 1e-7
         assert rb["eta"]["max"] == pytest.approx(ra["eta"]["max"], rel=1e-6)
+
+
+# ---------------------------------------------------------------------------------------
+# Config 2: verification/tutorial_baroclinic_gyre (62x62x15 spherical polar, 2x2 tiles).
+# Pins GAD_CALC_RHS (c2 advection, Laplacian diffusion, implicit vertical diffusion with
+# IVDC) and the Nr > 1 / spherical branches of MOM_FLUXFORM (vertical advection and
+# viscosity, metric terms, no-slip sides) against results/output.txt.
+# ---------------------------------------------------------------------------------------
+from oracle import baroclinic_gyre as bc
+
+GOLD2 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_baroclinic_gyre.json")))
+
+
+@pytest.fixture(scope="module")
+def bc10():
+    return bc.run(10)
+
+
+def test_config2_inputs_match_reference_files():
+    ref = "/root/reference/verification/tutorial_baroclinic_gyre/input"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    h, t, s = bc.gen_inputs()
+    assert h.tobytes() == open(os.path.join(ref, "bathy.bin"), "rb").read()
+    assert t.tobytes() == open(os.path.join(ref, "windx_cosy.bin"), "rb").read()
+    assert s.tobytes() == open(os.path.join(ref, "SST_relax.bin"), "rb").read()
+
+
+def test_config2_cg2d_norm_spherical_grid(bc10):
+    norm, _ = bc10
+    assert fmt(norm, 16) == GOLD2["cg2dNorm"]         # 1.4846576448792053E-04
+
+
+def test_config2_cg2d_lines_all_steps(bc10):
+    _, out = bc10
+    assert [r["numIters"] for r in out] == GOLD2["cg2d_iters"]
+    for r, ir, lr, (sr, rm) in zip(out, GOLD2["cg2d_init_res"], GOLD2["cg2d_last_res"], GOLD2["sumRHS_rhsMax"]):
+        assert fmt(r["firstResidual"], 14) == ir
+        assert fmt(r["lastResidual"], 14) == lr
+        assert fmt(r["rhsMax"], 14) == rm
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel", "theta"])
+@pytest.mark.parametrize("st", ["max", "min", "mean", "sd"])
+def test_config2_monitor_dynstats(bc10, fld, st):
+    """Every printed digit of %MON dynstat_* for the 10 steps (the means of eta, vvel, wvel are
+    round-off residues of order 1e-20 and are compared like the others: they only match when the
+    summation order is the reference's)."""
+    _, out = bc10
+    gold = GOLD2[f"dynstat_{fld}_{st}"][1:]
+    for r, gv in zip(out, gold):
+        assert fmt(r[fld][st], 13) == gv.replace("-0.0000000000000E+00", "0.0000000000000E+00") or \
+            r[fld][st] == pytest.approx(float(gv), rel=5e-13, abs=1e-30), (fld, st)
