@@ -36,3 +36,42 @@ def cg2d_problem(g, seed=1, tol=1e-9, **params):
     b *= wet * g.rA / 1200.0
     x = 0.1 * rng.standard_normal(d.shape2) * wet
     return o, op, b, x
+
+
+class CudaEngine:
+    """Adapter with the Oracle's method signatures (mom_fluxform, gad_calc_rhs, cg2d) that routes to the
+    CUDA library through mitgcm_b200.runtime, i.e. through the C ABI with host buffers and the reference
+    argument lists.  Lets the end-to-end drivers under oracle/ run with the CUDA kernels in the loop."""
+
+    def __init__(self, rt, use_gad=True, use_mom=True, use_cg2d=True, fallback=None):
+        self.rt, self.fb = rt, fallback
+        self.use_gad, self.use_mom, self.use_cg2d = use_gad, use_mom, use_cg2d
+
+    def setup(self, g, params, op):
+        from mitgcm_b200 import _lib
+        rt = self.rt
+        rt.init(g.d)
+        rt.set_grid(g)
+        known = {k: v for k, v in params.items() if "MP_" + k.upper() in _lib.ENUMS or "MI_" + k.upper() in _lib.ENUMS}
+        rt.set_params(**known)
+        rt.set_cg2d_operator(op)
+
+    def gad_calc_rhs(self, bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld,
+                     uTrans, vTrans, rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB, deltaTLev,
+                     advScheme, vertAdvScheme, calcAdvection, implicitAdvection, applyAB_onTracer, trUseDiffKr4,
+                     fZon, fMer, fVerT, gTracer):
+        a = (bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld, uTrans, vTrans,
+             rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB, deltaTLev)
+        if not self.use_gad:
+            return self.fb.gad_calc_rhs(*a, advScheme, vertAdvScheme, calcAdvection, implicitAdvection,
+                                        applyAB_onTracer, trUseDiffKr4, fZon, fMer, fVerT, gTracer)
+        self.rt.gad_calc_rhs(*a, 1, advScheme, vertAdvScheme, calcAdvection, implicitAdvection, applyAB_onTracer,
+                             trUseDiffKr4, 0, 0, 0, fZon, fMer, fVerT, gTracer)
+
+    def mom_fluxform(self, *a):
+        return (self.rt if self.use_mom else self.fb).mom_fluxform(*a)
+
+    def cg2d(self, op, b, x, numIters, nIterMin=-1, sr=False):
+        if not self.use_cg2d:
+            return self.fb.cg2d(op, b, x, numIters, nIterMin, sr=sr)
+        return self.rt.cg2d(b, x, numIters, nIterMin, sr=sr)
