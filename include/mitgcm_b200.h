@@ -155,6 +155,19 @@ void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg
  * full-width halo with corners. */
 void mitgcm_b200_exch_(const int *id, int *ierr);
 
+/* ---- pkg/exch2 tile graph (cubed sphere and other multi-facet grids) ---------------------------
+ * Hands over the topology the model holds in COMMON /W2_EXCH2_TOPO_I/ and /W2_EXCH2_HALO_SPEC/
+ * (pkg/exch2/W2_EXCH2_TOPOLOGY.h:63-122, filled by W2_E2SETUP) plus W2_myTileList (:162), arrays in
+ * Fortran order: (W2_maxNeighbours, nTiles), pij (4, W2_maxNeighbours, nTiles).  From then on the
+ * width-1 exchange inside CG2D / CG2D_SR follows EXCH2_S3D_RX (exch2_s3d_rx.template) and
+ * mitgcm_b200_exch_ follows EXCH2_3D_RX (exch2_3d_rx.template: IGNORE_CORNERS pass, then
+ * UPDATE_CORNERS pass) instead of the periodic nSx x nSy tiling.  All tiles live on this GPU. */
+void mitgcm_b200_set_exch2_topology_(
+    const int *nTiles, const int *maxNeighbours, const int *nNeighbours, const int *neighbourId,
+    const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
+    const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex, const int *tBasey,
+    const int *myTileList, int *ierr);
+
 /* ---- multi-GPU (one process per GPU on one NVSwitch domain) --------------------------------
  * CG2D: every rank exports its solver workspace as a CUDA IPC handle (64 bytes) and, after the
  * handles of all ranks have been gathered, maps its peers.  Edge values are then stored directly

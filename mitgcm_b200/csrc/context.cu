@@ -165,6 +165,9 @@ void mitgcm_b200_finalize_(void) {
   c.stage.clear();
   if (c.pushTab) cudaFree(c.pushTab);
   c.pushTab = nullptr;
+  if (c.e2List) cudaFree(c.e2List);
+  c.e2List = nullptr;
+  c.e2Count = 0;
   cg2d_free_workspace();
   for (auto &e : c.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto &e : c.pev) if (e) { cudaEventDestroy(e); e = nullptr; }

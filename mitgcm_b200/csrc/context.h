@@ -44,6 +44,9 @@ struct Ctx {
   // halo push tables for width-1 exchanges (cg2d): index of the halo cell that mirrors
   // each edge point, per tile: [W(sNy) | E(sNy) | S(sNx) | N(sNx)]
   int *pushTab = nullptr;
+  // pkg/exch2 tile graph (exch2.cu): gather list (dst, src) pairs of the full-width scalar exchange
+  int *e2List = nullptr;
+  int e2Count = 0;
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;
@@ -71,5 +74,7 @@ bool is_device_ptr(const void *p);
 // buffer (slot) of n doubles, filled from p when `upload`.
 double *to_device(const double *p, size_t n, int slot, bool upload);
 bool from_device(double *hostOrDev, const double *dev, size_t n);  // no-op when same pointer
+bool exch2_active();                                   // a pkg/exch2 topology has been set
+bool exch2_field(double *f, int nz);                   // EXCH2_3D_RX as one gather
 
 }  // namespace mg

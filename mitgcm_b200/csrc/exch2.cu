@@ -1,0 +1,184 @@
+// exch2.cu -- pkg/exch2 (tile-graph halo exchange, e.g. the cubed sphere) for scalar fields on
+// one GPU.  The reference walks, per tile and per neighbour entry, an index range of the halo
+// and copies it through an affine index map into buffers, twice (EXCH2_RX1_CUBE with
+// EXCH_IGNORE_CORNERS, then with EXCH_UPDATE_CORNERS: pkg/exch2/exch2_3d_rx.template:60-80,
+// exch2_rx1_cube.template:95-262, exch2_get_scal_bounds.F:44-126, exch2_put_rx1.template:160-175).
+// Here the topology tables of COMMON /W2_EXCH2_TOPO_I/ and /W2_EXCH2_HALO_SPEC/
+// (W2_EXCH2_TOPOLOGY.h:63-122) are compiled ONCE into a gather list: for every halo cell the cell
+// whose pre-exchange value it holds after both passes (the two passes are composed cell by cell,
+// later neighbour entries overriding earlier ones exactly as the sequential GETs do).  An exchange
+// of any field is then one launch of a coalesced gather over (list entry, level), and the width-1
+// exchange inside CG2D (EXCH2_S3D_RX, exch2_s3d_rx.template:45-62) becomes the solver's push table.
+#include <algorithm>
+#include <vector>
+#include "context.h"
+
+namespace mg {
+
+struct E2Tables {
+  int nT = 0, maxN = 0;
+  std::vector<int> nN, nid, opp, ndir, pij, oi, oj, iLo, iHi, jLo, jHi, bx, by, local;
+  int N(int t) const { return nN[t]; }
+  int at(const std::vector<int> &a, int n, int t) const { return a[n + maxN * t]; }
+  int P(int k, int n, int t) const { return pij[k + 4 * (n + maxN * t)]; }
+};
+
+static void target_range(const E2Tables &T, int n, int t, int eW, bool corners, int r[4]) {
+  int i0 = T.at(T.iLo, n, t), i1 = T.at(T.iHi, n, t), j0 = T.at(T.jLo, n, t), j1 = T.at(T.jHi, n, t);
+  const int grow = corners ? eW - 1 : -1;
+  // the four tests are sequential on the updated values, as in exch2_get_scal_bounds.F:50-124
+  if (i0 == i1 && i0 == 0) { i0 = 1 - eW; j0 -= grow; j1 += grow; }       // west edge overlap
+  if (i0 == i1 && i0 > 1) { i1 = i1 + eW - 1; j0 -= grow; j1 += grow; }   // east
+  if (j0 == j1 && j0 == 0) { j0 = 1 - eW; i0 -= grow; i1 += grow; }       // south
+  if (j0 == j1 && j0 > 1) { j1 = j1 + eW - 1; i0 -= grow; i1 += grow; }   // north
+  r[0] = i0; r[1] = i1; r[2] = j0; r[3] = j1;
+}
+
+// provenance of every cell of a (nT, sNy+2*OL, sNx+2*OL) array after the exchange
+static bool compile_gather(const E2Tables &T, int sNx, int sNy, int OL, int eW, bool twoPass,
+                           std::vector<int> &prov) {
+  const int PX = sNx + 2 * OL, PY = sNy + 2 * OL;
+  auto flat = [&](int t, int i, int j) { return (t * PY + (j + OL - 1)) * PX + (i + OL - 1); };
+  prov.resize((size_t)T.nT * PX * PY);
+  for (size_t q = 0; q < prov.size(); q++) prov[q] = (int)q;
+  for (int pass = 0; pass < (twoPass ? 2 : 1); pass++) {
+    std::vector<int> nw(prov);
+    for (int t = 0; t < T.nT; t++)
+      for (int n = 0; n < T.N(t); n++) {
+        const int s = T.at(T.nid, n, t) - 1, m = T.at(T.opp, n, t) - 1;
+        int r[4];
+        target_range(T, n, t, eW, pass == 1, r);
+        for (int j = r[2]; j <= r[3]; j++)
+          for (int i = r[0]; i <= r[1]; i++) {
+            const int ic = i + T.bx[t], jc = j + T.by[t];
+            const int si = T.P(0, m, s) * ic + T.P(1, m, s) * jc + T.at(T.oi, m, s) - T.bx[s];
+            const int sj = T.P(2, m, s) * ic + T.P(3, m, s) * jc + T.at(T.oj, m, s) - T.by[s];
+            if (si < 1 - OL || si > sNx + OL || sj < 1 - OL || sj > sNy + OL || i < 1 - OL || i > sNx + OL ||
+                j < 1 - OL || j > sNy + OL)
+              return fail(71, "exch2: index map leaves the tile array (inconsistent topology tables)");
+            nw[flat(t, i, j)] = prov[flat(s, si, sj)];
+          }
+      }
+    prov.swap(nw);
+  }
+  return true;
+}
+
+__global__ void gather_kernel(double *f, const int2 *lst, int n, int nz, size_t slab) {
+  const size_t total = (size_t)n * nz;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(q % n), k = (int)(q / n);
+    const int2 ds = lst[e];   // (dst, src) as tile*slab + cell of a 2-D array; the level offset is added here
+    const size_t dt = (size_t)ds.x / slab, dc = (size_t)ds.x % slab;
+    const size_t st = (size_t)ds.y / slab, sc = (size_t)ds.y % slab;
+    f[dc + slab * (k + (size_t)nz * dt)] = f[sc + slab * (k + (size_t)nz * st)];
+  }
+}
+
+bool exch2_active() { return ctx().e2Count > 0; }
+
+bool exch2_field(double *f, int nz) {
+  Ctx &c = ctx();
+  const size_t total = (size_t)c.e2Count * nz;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  c.launches++;
+  gather_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(f, reinterpret_cast<const int2 *>(c.e2List), c.e2Count, nz, c.g.slab);
+  MG_CUDA(cudaGetLastError());
+  return true;
+}
+
+static bool set_topology(const E2Tables &T) {
+  Ctx &c = ctx();
+  const Geom &g = c.g;
+  // ---- full-width scalar exchange: gather list over halo cells -------------------------------
+  std::vector<int> prov;
+  if (!compile_gather(T, g.sNx, g.sNy, g.OLx, g.OLx, true, prov)) return false;
+  std::vector<int> lst;
+  for (size_t q = 0; q < prov.size(); q++)
+    if (prov[q] != (int)q) {
+      // tile ids -> positions of the tiles in this process's (bi,bj) order
+      const int dt = (int)(q / g.slab), st = prov[q] / (int)g.slab;
+      lst.push_back(T.local[dt] * (int)g.slab + (int)(q % g.slab));
+      lst.push_back(T.local[st] * (int)g.slab + prov[q] % (int)g.slab);
+    }
+  if (c.e2List) cudaFree(c.e2List);
+  MG_CUDA(cudaMalloc(&c.e2List, std::max<size_t>(lst.size(), 2) * sizeof(int)));
+  MG_CUDA(cudaMemcpy(c.e2List, lst.data(), lst.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c.e2Count = (int)(lst.size() / 2);
+  // ---- width-1 exchange of CG2D: the push table ------------------------------------------------
+  std::vector<int> p1;
+  if (!compile_gather(T, g.sNx, g.sNy, 1, 1, false, p1)) return false;
+  const int per = 2 * g.sNy + 2 * g.sNx, P1X = g.sNx + 2, P1Y = g.sNy + 2;
+  std::vector<int> tab((size_t)per * g.nTiles, -1);
+  auto idx = [&](int i, int j, int tile) {
+    return (int)((size_t)(i + g.OLx - 1) + (size_t)g.PX * (size_t)(j + g.OLy - 1) + g.slab * (size_t)tile);
+  };
+  for (int t = 0; t < T.nT; t++)
+    for (int n = 0; n < T.N(t); n++) {
+      const int s = T.at(T.nid, n, t) - 1, m = T.at(T.opp, n, t) - 1;
+      const int sdir = T.at(T.ndir, m, s);     // edge of the source tile this entry leaves through
+      int r[4];
+      target_range(T, n, t, 1, false, r);
+      for (int j = r[2]; j <= r[3]; j++)
+        for (int i = r[0]; i <= r[1]; i++) {
+          const int src = p1[(t * P1Y + j) * P1X + i];
+          if (src / (P1X * P1Y) != s) return fail(72, "exch2: width-1 map is not a single-source copy");
+          const int si = src % P1X, sj = (src / P1X) % P1Y;   // 0-based in the (0:sNx+1) frame = Fortran index
+          int slot;
+          if (sdir == 4) slot = sj - 1;                         // west edge, by j
+          else if (sdir == 3) slot = g.sNy + sj - 1;            // east edge
+          else if (sdir == 2) slot = 2 * g.sNy + si - 1;        // south edge, by i
+          else slot = 2 * g.sNy + g.sNx + si - 1;               // north edge
+          int &e = tab[(size_t)per * T.local[s] + slot];
+          if (e != -1) return fail(72, "exch2: an edge point feeds two halo cells through one edge");
+          e = idx(i, j, T.local[t]);
+        }
+    }
+  for (int v : tab)
+    if (v < 0) return fail(72, "exch2: an edge point has no neighbour (open edges are not supported)");
+  MG_CUDA(cudaMemcpy(c.pushTab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return true;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" void mitgcm_b200_set_exch2_topology_(
+    const int *nTiles, const int *maxNeighbours, const int *nNeighbours, const int *neighbourId,
+    const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
+    const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex, const int *tBasey,
+    const int *myTileList, int *ierr) {
+  Ctx &c = ctx();
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  if (g.nPx != 1 || g.nPy != 1) { fail(70, "exch2 topology: one process (one GPU) holds all tiles"); return; }
+  if (*nTiles != g.nTiles) { fail(70, "exch2 topology: nTiles must equal nSx*nSy of this process"); return; }
+  if (g.OLx != g.OLy) { fail(70, "exch2 topology: OLx must equal OLy"); return; }
+  if ((size_t)g.n2 >= ((size_t)1 << 31)) { fail(70, "exch2 topology: tile2d array too large for the gather list"); return; }
+  E2Tables T;
+  T.nT = *nTiles; T.maxN = *maxNeighbours;
+  const size_t nn = (size_t)T.nT * T.maxN;
+  T.nN.assign(nNeighbours, nNeighbours + T.nT);
+  T.nid.assign(neighbourId, neighbourId + nn); T.opp.assign(opposingSend, opposingSend + nn);
+  T.ndir.assign(neighbourDir, neighbourDir + nn); T.pij.assign(pij, pij + 4 * nn);
+  T.oi.assign(oi, oi + nn); T.oj.assign(oj, oj + nn);
+  T.iLo.assign(iLo, iLo + nn); T.iHi.assign(iHi, iHi + nn); T.jLo.assign(jLo, jLo + nn); T.jHi.assign(jHi, jHi + nn);
+  T.bx.assign(tBasex, tBasex + T.nT); T.by.assign(tBasey, tBasey + T.nT);
+  T.local.assign(T.nT, -1);
+  for (int l = 0; l < g.nTiles; l++) {
+    const int id = myTileList[l];
+    if (id < 1 || id > T.nT || T.local[id - 1] != -1) { fail(70, "exch2 topology: bad W2_myTileList"); return; }
+    T.local[id - 1] = l;
+  }
+  for (int t = 0; t < T.nT; t++) {
+    if (T.nN[t] < 0 || T.nN[t] > T.maxN) { fail(70, "exch2 topology: bad exch2_nNeighbours"); return; }
+    for (int n = 0; n < T.nN[t]; n++) {
+      const int s = T.at(T.nid, n, t), m = T.at(T.opp, n, t);
+      if (s < 1 || s > T.nT || m < 1 || m > T.nN[s - 1]) { fail(70, "exch2 topology: bad neighbour tables"); return; }
+    }
+  }
+  if (!set_topology(T)) return;
+  *ierr = 0;
+}

@@ -61,6 +61,7 @@ __global__ void exch_kernel(double *f, int nz, int sNx, int sNy, int OLx, int OL
 bool exch_field(double *f, int nz) {
   Ctx &c = ctx();
   const Geom &g = c.g;
+  if (exch2_active()) return exch2_field(f, nz);
   if (g.nPx != 1 || g.nPy != 1) return fail(60, "exch: multi-process exchange goes through the distributed driver");
   const size_t total = (size_t)(g.PX * g.PY - g.sNx * g.sNy) * nz * g.nTiles;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);

@@ -336,6 +336,98 @@ def set_hfac(g: Grid, hFacC, hFacW, hFacS) -> None:
 
 
 def global_area(g: Grid) -> float:
+    """globalArea of INI_MASKS_ETC (ini_masks_etc.F:430-450): per-tile sums of rA*maskInC over the
+    interior, i fastest then j, tiles added in (bi, bj) order (GLOBAL_SUM_TILE_RL)."""
     d = g.d
     jj, ii = d.interior()
-    return float((g.a["rA"][:, :, jj, ii] * g.a["maskC"][:, :, 0, jj, ii]).sum())
+    tot = 0.0
+    for bj in range(d.nSy):
+        for bi in range(d.nSx):
+            x = (g.a["rA"][bj, bi, jj, ii] * g.a["maskC"][bj, bi, 0, jj, ii]).ravel()
+            tot = tot + (float(np.cumsum(x)[-1]) if x.size else 0.0)
+    return tot
+
+
+# ---- curvilinear (cubed-sphere) grids --------------------------------------------------------------
+MITGRID_FIELDS = ("xC yC dxF dyF rA xG yG dxV dyU rAz dxC dyC rAw rAs dxG dyG angleCosC angleSinC").split()
+
+
+def read_mitgrid_faces(prefix: str, nFace: int, nFacets: int = 6):
+    """horizGridFile face files `<prefix>.face00N.bin`: 18 records of (nFace+1) x (nFace+1) big-endian
+    float64 in the order INI_CURVILINEAR_GRID reads them (model/src/ini_curvilinear_grid.F:318-352).
+    Returns a list (one per facet) of dicts name -> (nFace+1, nFace+1) array [j, i]."""
+    faces = []
+    for f in range(1, nFacets + 1):
+        a = np.fromfile(f"{prefix}.face{f:03d}.bin", dtype=">f8")
+        assert a.size == len(MITGRID_FIELDS) * (nFace + 1) ** 2, "unexpected mitgrid file size"
+        a = a.reshape(len(MITGRID_FIELDS), nFace + 1, nFace + 1).astype(np.float64)
+        faces.append({n: a[q] for q, n in enumerate(MITGRID_FIELDS)})
+    return faces
+
+
+def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=86164.0) -> Grid:
+    """usingCurvilinearGrid with pkg/exch2: tiles laid out as one row (nSx = nTiles, nSy = 1, the
+    reference's own cs32 SIZE.h), metrics from the face files.  Each tile takes its interior plus the
+    (sNx+1, sNy+1) row and column the files carry (MDS_FACEF_READ); cell-centred scalars (xC, yC, rA)
+    then get their halos from the scalar exch2 exchange as in ini_curvilinear_grid.F:360-363.  The
+    vector-pair exchanges of the reference (dxC/dyC, rAw/rAs, dxG/dyG: :364-370) are NOT done: beyond
+    index sN+1 those arrays stay zero, which is all the CG2D operator and the KATs need."""
+    from .exch2 import exchange, halo_gather_map
+    assert d.nSy == 1 and d.nSx == topo.nTiles and d.OLx == d.OLy
+    g = Grid(d)
+    for n in GRID2D:
+        g.a[n] = np.zeros(d.shape2)
+    for n in ("xC", "yC", "xG", "yG", "angleCosC", "angleSinC"):
+        g.a[n] = np.zeros(d.shape2)
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    for t in range(topo.nTiles):
+        F = faces[int(topo.myFace[t]) - 1]
+        bx, by = int(topo.tBasex[t]), int(topo.tBasey[t])
+        for n in MITGRID_FIELDS:
+            if n in F:      # a reduced set of records is enough for the CG2D operator
+                g.a[n][0, t, oy:oy + sy + 1, ox:ox + sx + 1] = F[n][by:by + sy + 1, bx:bx + sx + 1]
+    gm = halo_gather_map(topo, ox)
+    for n in ("xC", "yC", "rA"):
+        exchange(topo, g.a[n][0], ox, gm)
+    PI = 3.14159265358979323844
+    omega = 2.0 * PI / rotationPeriod
+    import math
+    g.a["fCori"] = 2.0 * omega * np.vectorize(math.sin)(g.a["yC"] * (2.0 * PI / 360.0))
+    g.a["fCoriG"] = 2.0 * omega * np.vectorize(math.sin)(g.a["yG"] * (2.0 * PI / 360.0))
+    g.a["Bo_surf"] = np.full(d.shape2, gBaro)
+    g.a["recip_Bo"] = np.full(d.shape2, 1.0 / gBaro)
+    g.a["cosFacU"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.a["cosFacV"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.set_recips()
+    set_vertical(g, delR)
+    return g
+
+
+def cube_masks_from_depth(g: Grid, topo, depth_xstack: np.ndarray, hFacMin=1.0, hFacMinDr=0.0) -> None:
+    """INI_DEPTHS + INI_MASKS_ETC on the tile graph: bathymetry in the exch2 global-IO layout
+    (W2_mapIO = -1: facets stacked along x, shape (nFace, 6*nFace)), R_low halos by the scalar exch2
+    exchange (ini_depths.F: _EXCH_XY_RS(R_low)), hFacC by the hFacMin / hFacMinDr rule, hFacW/S as the
+    minimum of the two neighbouring cells wherever both are known (ini_masks_etc.F:238-262)."""
+    from .exch2 import exchange
+    d = g.d
+    ox, oy, sx, sy = d.OLx, d.OLy, d.sNx, d.sNy
+    nFace = depth_xstack.shape[0]
+    R_low = np.zeros(d.shape2)
+    for t in range(topo.nTiles):
+        f = int(topo.myFace[t]) - 1
+        bx, by = int(topo.tBasex[t]), int(topo.tBasey[t])
+        R_low[0, t, oy:oy + sy, ox:ox + sx] = depth_xstack[by:by + sy, f * nFace + bx:f * nFace + bx + sx]
+    exchange(topo, R_low[0], ox)
+    drF, rdrF, rF = g.a["drF"], g.a["recip_drF"], g.a["rF"]
+    hFacC = np.zeros(d.shape3)
+    for k in range(d.Nr):
+        mn = max(hFacMin, min(hFacMinDr * rdrF[k], 1.0))
+        h = (rF[k] - R_low) * rdrF[k]
+        h = np.minimum(np.maximum(h, 0.0), 1.0)
+        hFacC[:, :, k] = np.where((h < mn * 0.5) | (R_low >= 0.0), 0.0, np.maximum(h, mn))
+    hFacW = np.zeros(d.shape3)
+    hFacS = np.zeros(d.shape3)
+    hFacW[..., :, 1:] = np.minimum(hFacC[..., :, 1:], hFacC[..., :, :-1])
+    hFacS[..., 1:, :] = np.minimum(hFacC[..., 1:, :], hFacC[..., :-1, :])
+    g.a["R_low"] = R_low
+    set_hfac(g, hFacC, hFacW, hFacS)

@@ -27,6 +27,19 @@
 
 static int wrap(int b, int n) { return b < 1 ? b + n : (b > n ? b - n : b); }
 
+/* ---- pkg/exch2 hook -------------------------------------------------------------------------
+ * When a tile graph is installed (og_set_exch2_maps), EXCH_XY(Z)_RL and EXCH_S3D_RL follow it
+ * instead of the periodic nSx x nSy tiling.  The maps are (dst, src) flat-index lists over a
+ * (tiles, PY, PX) array (full width) and a (tiles, sNy+2, sNx+2) array (S3D); oracle/exch2_oracle.py
+ * derives them by running its literal restatement of EXCH2_RX1_CUBE on an index-valued field. */
+static int e2_nFull = 0, e2_nS3d = 0;
+static const long long *e2_dFull = 0, *e2_sFull = 0, *e2_dS3d = 0, *e2_sS3d = 0;
+void og_set_exch2_maps(int nFull, const long long *dFull, const long long *sFull,
+                       int nS3d, const long long *dS3d, const long long *sS3d) {
+  e2_nFull = nFull; e2_dFull = dFull; e2_sFull = sFull;
+  e2_nS3d = nS3d; e2_dS3d = dS3d; e2_sS3d = sS3d;
+}
+
 /* EXCH1_RX forward mode with EXCH_UPDATE_CORNERS on a single periodic process:
  * X edges are put and received first, then Y edges over the full X range
  * (including the freshly filled X halos), exch1_rx.template:170-201,
@@ -34,6 +47,16 @@ static int wrap(int b, int n) { return b < 1 ? b + n : (b > n ? b - n : b); }
 void og_exch_xyz(const og_dims *d, double *a, int nz) {
   const int sNx = d->sNx, sNy = d->sNy, OLx = d->OLx, OLy = d->OLy;
   const size_t px = PX, py = PY;
+  if (e2_nFull > 0) {   /* tile graph: all sources are interior cells, so the gather is order-free */
+    const size_t slab = px * py;
+    for (int k = 0; k < nz; k++)
+      for (int q = 0; q < e2_nFull; q++) {
+        const size_t dt = (size_t)e2_dFull[q] / slab, dc = (size_t)e2_dFull[q] % slab;
+        const size_t st = (size_t)e2_sFull[q] / slab, sc = (size_t)e2_sFull[q] % slab;
+        a[dc + slab * ((size_t)k + (size_t)nz * dt)] = a[sc + slab * ((size_t)k + (size_t)nz * st)];
+      }
+    return;
+  }
 #define A(i, j, k, bi, bj) \
   a[(size_t)((i) + OLx - 1) + px * ((size_t)((j) + OLy - 1) + py * ((size_t)(k) + (size_t)nz * ((size_t)((bi)-1) + (size_t)d->nSx * ((bj)-1))))]
   for (int bj = 1; bj <= d->nSy; bj++)
@@ -67,6 +90,10 @@ void og_exch_uv_xyz(const og_dims *d, double *u, double *v, int nz) {
 /* EXCH_S3D_RL(phi,1): EXCH1_RX with overlap 1 and EXCH_IGNORE_CORNERS. */
 void og_exch_s3d(const og_dims *d, double *a) {
   const int sNx = d->sNx, sNy = d->sNy;
+  if (e2_nS3d > 0) {
+    for (int q = 0; q < e2_nS3d; q++) a[e2_dS3d[q]] = a[e2_sS3d[q]];
+    return;
+  }
   for (int bj = 1; bj <= d->nSy; bj++)
     for (int bi = 1; bi <= d->nSx; bi++) {
       int bw = wrap(bi - 1, d->nSx), be = wrap(bi + 1, d->nSx);

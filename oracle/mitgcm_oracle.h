@@ -82,6 +82,9 @@ void og_exch_uv_xyz(const og_dims *d, double *u, double *v, int nz);
 /* EXCH_S3D_RL(phi,1): width-1 halo, no corners, on a (0:sNx+1,0:sNy+1) array
  * (eesupp/src/exch_s3d_rx.template:8-78). */
 void og_exch_s3d(const og_dims *d, double *a);
+/* pkg/exch2 tile graph for the three exchanges above (NULL / 0 restores the periodic tiling) */
+void og_set_exch2_maps(int nFull, const long long *dFull, const long long *sFull,
+                       int nS3d, const long long *dS3d, const long long *sS3d);
 /* GLOBAL_SUM_TILE_RL: tiles summed bi fast, bj slow (global_sum_tile.F:185-191) */
 double og_global_sum_tile(const og_dims *d, const double *tile);
 

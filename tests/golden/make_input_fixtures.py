@@ -1,0 +1,35 @@
+"""Copies the small binary INPUT vectors of the reference's verification experiments that the
+CPU tests need (run in the build container, where /root/reference exists; the GPU box has no
+reference tree).  Outputs go to tests/golden/inputs/.  Usage: python tests/golden/make_input_fixtures.py"""
+import os
+import shutil
+
+REF = "/root/reference/verification"
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "inputs")
+FILES = {
+    # config 3 (global_ocean.90x40x15 links its *.bin from tutorial_global_oce_latlon, input/prepare_run)
+    "global_oce_latlon_bathymetry.bin": "tutorial_global_oce_latlon/input/bathymetry.bin",
+}
+
+def cs32_fixture():
+    """Config 4 (global_ocean.cs32x15): the records of grid_cs32.face00N.bin (horizGridFile, taken from
+    tutorial_held_suarez_cs/input by prepare_run) that the CG2D operator needs, and bathy_Hmin50.bin,
+    as one compressed npz (float64, exact)."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    from mitgcm_b200.grid import read_mitgrid_faces
+    faces = read_mitgrid_faces(os.path.join(REF, "tutorial_held_suarez_cs/input/grid_cs32"), 32)
+    keep = "xC yC rA xG yG dxC dyC dxG dyG".split()
+    out = {f"{n}_{f}": faces[f][n] for f in range(6) for n in keep}
+    out["bathy_Hmin50"] = np.fromfile(os.path.join(REF, "global_ocean.cs32x15/input/bathy_Hmin50.bin"), ">f8").reshape(32, 192).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "cs32_grid_bathy.npz"), **out)
+    print("wrote cs32_grid_bathy.npz")
+
+
+if __name__ == "__main__":
+    os.makedirs(HERE, exist_ok=True)
+    cs32_fixture()
+    for dst, src in FILES.items():
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+        print("copied", src, "->", dst)

@@ -75,3 +75,22 @@ class CudaEngine:
         if not self.use_cg2d:
             return self.fb.cg2d(op, b, x, numIters, nIterMin, sr=sr)
         return self.rt.cg2d(b, x, numIters, nIterMin, sr=sr)
+
+
+def load_cs32():
+    """Config 4 geometry from the committed fixture (tests/golden/inputs/cs32_grid_bathy.npz, made by
+    tests/golden/make_input_fixtures.py from the reference's grid_cs32.face00N.bin and bathy_Hmin50.bin):
+    returns (topology, grid with masks, params)."""
+    import os
+    from mitgcm_b200.grid import cubed_sphere_grid, cube_masks_from_depth
+    from mitgcm_b200.exch2 import cubed_sphere_topology
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "inputs", "cs32_grid_bathy.npz"))
+    keep = "xC yC rA xG yG dxC dyC dxG dyG".split()
+    faces = [{n: z[f"{n}_{f}"] for n in keep} for f in range(6)]
+    T = cubed_sphere_topology(32, 32, 16)
+    d = Dims(sNx=32, sNy=16, OLx=4, OLy=4, nSx=12, nSy=1, Nr=15)
+    delR = [50., 70., 100., 140., 190., 240., 290., 340., 390., 440., 490., 540., 590., 640., 690.]
+    g = cubed_sphere_grid(d, T, faces, delR)
+    cube_masks_from_depth(g, T, z["bathy_Hmin50"], hFacMin=0.1, hFacMinDr=20.0)
+    P = dict(deltaTMom=1200.0, deltaTFreeSurf=86400.0, cg2dTargetResWunit=1e-14, globalArea=global_area(g))
+    return T, g, P

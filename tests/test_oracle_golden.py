@@ -131,3 +131,51 @@ def test_config2_monitor_dynstats(bc10, fld, st):
     for r, gv in zip(out, gold):
         assert fmt(r[fld][st], 13) == gv.replace("-0.0000000000000E+00", "0.0000000000000E+00") or \
             r[fld][st] == pytest.approx(float(gv), rel=5e-13, abs=1e-30), (fld, st)
+
+
+# ---------------------------------------------------------------------------------------
+# Config 3: verification/global_ocean.90x40x15 -- operator level: the CG2D
+# operator built by INI_CG2D from the experiment's real bathymetry (partial cells,
+# hFacMin = 0.05, hFacMinDr = 50 m) on the 4-degree spherical-polar grid, 9x4 tiles of 10x10.
+# ---------------------------------------------------------------------------------------
+def config3_grid():
+    from mitgcm_b200.grid import Dims, spherical_polar_grid, masks_from_depth
+    d = Dims(sNx=10, sNy=10, OLx=3, OLy=3, nSx=9, nSy=4, Nr=15)
+    delR = [50., 70., 100., 140., 190., 240., 290., 340., 390., 440., 490., 540., 590., 640., 690.]
+    g = spherical_polar_grid(d, [4.0] * 90, [4.0] * 40, delR, xgOrigin=0.0, ygOrigin=-80.0)
+    f = os.path.join(os.path.dirname(__file__), "golden", "inputs", "global_oce_latlon_bathymetry.bin")
+    bathy = np.fromfile(f, ">f4").reshape(40, 90).astype(np.float64)
+    masks_from_depth(g, bathy, hFacMin=0.05, hFacMinDr=50.0)
+    return g
+
+
+def test_config3_cg2d_norm_and_area_from_real_bathymetry():
+    from mitgcm_b200.grid import global_area
+    from oracle.pyoracle import Oracle
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "global_ocean.90x40x15.json")))
+    g = config3_grid()
+    area = global_area(g)
+    assert area == pytest.approx(3.450614146649756E+14, rel=1e-15)   # results/output.txt:1897
+    o = Oracle(g, dict(deltaTMom=1800.0, deltaTFreeSurf=86400.0, cg2dTargetResidual=1e-13, globalArea=area))
+    op = o.ini_cg2d()
+    assert fmt(op["cg2dNorm"], 16) == gold["cg2dNorm"]               # 6.5682677425711703E-05, :766
+
+
+def test_config3_operator_solve_converges_like_the_reference():
+    """CG2D on the real-bathymetry operator with the experiment's tolerance (1e-13): the golden run
+    needs 122-128 iterations per step (results/output.txt:2208-2484); a smooth random right-hand
+    side on the same operator must converge in a comparable count."""
+    from mitgcm_b200.grid import global_area
+    from oracle.pyoracle import Oracle
+    g = config3_grid()
+    d = g.d
+    o = Oracle(g, dict(deltaTMom=1800.0, deltaTFreeSurf=86400.0, cg2dTargetResidual=1e-13, globalArea=global_area(g)))
+    op = o.ini_cg2d()
+    rng = np.random.default_rng(3)
+    jj, ii = d.interior()
+    b = np.zeros(d.shape2)
+    b[:, :, jj, ii] = rng.standard_normal((d.nSy, d.nSx, d.sNy, d.sNx))
+    b *= g.maskC[:, :, 0] * g.rA / 1800.0
+    x = np.zeros(d.shape2)
+    r = o.cg2d(op, b, x, 500, -1)
+    assert 80 <= r["numIters"] <= 200 and r["lastResidual"] < 1e-13
