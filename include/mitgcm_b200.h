@@ -32,19 +32,20 @@ enum {
   MG_FCORI, MG_FCORIG, MG_TANPHIATU, MG_TANPHIATV, MG_RECIP_BO, MG_BO_SURF,
   MG_AW2D, MG_AS2D, MG_AC2D, MG_PW, MG_PS, MG_PC,
   MG_ETAN, MG_SURFFORCU, MG_SURFFORCV, MG_SURFFORCT, MG_CG2D_B, MG_CG2D_X,
+  MG_ETAH, MG_DETAHDT, MG_SST, MG_LAMBDATHETACLIMRELAX,   /* SURFACE.h, FFIELDS.h */
   MG_N2D,
   /* 3-D tile arrays (Nr levels), GRID.h, DYNVARS.h */
   MG_HFACC = 100, MG_HFACW, MG_HFACS, MG_RECIP_HFACC, MG_RECIP_HFACW, MG_RECIP_HFACS,
   MG_MASKC, MG_MASKW, MG_MASKS,
   MG_UVEL, MG_VVEL, MG_WVEL, MG_THETA, MG_SALT, MG_GU, MG_GV, MG_GUNM1, MG_GVNM1,
-  MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART, MG_THETA2,
+  MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART, MG_THETA2, MG_RHOINSITU,
   MG_N3D_END,
   /* (Nr+1)-level tile arrays */
   MG_KAPPARU = 200, MG_KAPPARV, MG_N3DP_END,
   /* per-row arrays (1-OLy:sNy+OLy,nSx,nSy) */
   MG_COSFACU = 300, MG_COSFACV, MG_NJ_END,
   /* vertical arrays: drF,recip_drF (Nr); drC,recip_drC (Nr+1) */
-  MG_DRF = 400, MG_DRC, MG_RECIP_DRF, MG_RECIP_DRC, MG_TREF, MG_NK_END
+  MG_DRF = 400, MG_DRC, MG_RECIP_DRF, MG_RECIP_DRC, MG_TREF, MG_SREF, MG_RF, MG_RC, MG_NK_END
 };
 
 /* ---- run-time parameter ids (model/inc/PARAMS.h) ---------------------------- */
@@ -54,7 +55,7 @@ enum {
   MP_VISCAHD, MP_VISCAHZ, MP_VISCA4D, MP_VISCA4Z, MP_SIDEDRAGFACTOR, MP_BOTTOMDRAGLINEAR,
   MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
   MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
-  MP_DIFFKRT, MP_VISCAR,
+  MP_DIFFKRT, MP_VISCAR, MP_SBETA, MP_IVDC_KAPPA,
   MP_ND,
   MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
   MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
@@ -63,6 +64,7 @@ enum {
   MI_USINGSPHERICALPOLARGRID, MI_RIGIDLID, MI_SELECT_RSTAR, MI_IMPLICITDIFFUSION,
   MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
   MI_TEMPSTEPPING, MI_NITER0, MI_PROFILE,
+  MI_EXACTCONSERV, MI_BUOYANCYLINEAR, MI_DOTHETACLIMRELAX,
   MI_NI_END
 };
 
@@ -147,7 +149,13 @@ void mom_fluxform_b200_(const int *bi, const int *bj, const int *k, const int *i
  * THERMODYNAMICS (TEMP_INTEGRATE: CALC_ADV_FLOW + GAD_CALC_RHS + ADAMS_BASHFORTH2 + TIMESTEP_TRACER
  * + CYCLE_TRACER), DYNAMICS (MOM_FLUXFORM + TIMESTEP), SOLVE_FOR_PRESSURE (CALC_DIV_GHAT + CG2D),
  * MOMENTUM_CORRECTION_STEP, INTEGR_CONTINUITY, DO_FIELDS_BLOCKING_EXCHANGES.  State and forcing
- * are the mirrors MG_UVEL.. MG_ETAN, MG_SURFFORCU/V; nothing crosses PCIe.  The solver scalars of
+ * are the mirrors MG_UVEL.. MG_ETAN, MG_SURFFORCU/V; nothing crosses PCIe.
+ * Optional physics of the wider configurations (verification/tutorial_baroclinic_gyre), each switched by
+ * its PARAMS.h flag: MI_BUOYANCYLINEAR (eosType = 'LINEAR': DO_OCEANIC_PHYS density + CALC_IVDC when
+ * MP_IVDC_KAPPA != 0, CALC_PHI_HYD + CALC_GRAD_PHI_HYD in DYNAMICS), MI_DOTHETACLIMRELAX (FORCING_SURF_RELAX
+ * towards MG_SST with MG_LAMBDATHETACLIMRELAX, APPLY_FORCING_T), MI_IMPLICITDIFFUSION (GAD_IMPLICIT_R +
+ * SOLVE_TRIDIAGONAL), MI_EXACTCONSERV (etaH in the solver right-hand side, dEtaHdt / etaN / etaH update
+ * of INTEGR_CONTINUITY + UPDATE_ETAH).  The solver scalars of
  * the step are returned like SOLVE_FOR_PRESSURE prints them (solve_for_pressure.F:337-348). */
 void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg2d_iters,
                                double *cg2d_last_res, int *ierr);

@@ -13,6 +13,7 @@
 // no CD scheme, z coordinates, buoyancy decoupled (dPhiHyd = 0), surface stress forcing only.
 #include <cstdlib>
 #include "step_fast.cuh"
+#include "phys.cuh"
 
 namespace mg {
 
@@ -103,7 +104,7 @@ struct FusedAcc {
 #endif
 __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, const double *u, const double *v, const double *w,
                                                      const double *theta, const double *kapT, double *thetaNew,
-                                                     double *gtNm1, GadPar p0, double abFac) {
+                                                     double *gtNm1, GadPar p0, double abFac, const double *sfT) {
   const int i = 1 + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 + blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx || j > g.sNy) return;
@@ -118,6 +119,11 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
     const double fvu = gad_fver(g, a, p, i, j);
     double gT = gad_tendency(g, a, p, i, j, 0., fz0, fz1, fm0, fm1, fvu, fVdn);
     const size_t s3 = g.s3(i, j, k);
+    if (sfT) {    // APPLY_FORCING_T (apply_forcing.F, k = kSurface), tracForcingOutAB = 0 (temp_integrate.F:392-398)
+      double gtForc = 0.;
+      if (k == 1) gtForc = gtForc + sfT[g.s(i, j)] * g.recip_drF[0] * g.recip_hFacC[s3];
+      gT = gT + gtForc;
+    }
     const double ab = abFac * (gT - gtNm1[s3]);            // ADAMS_BASHFORTH2
     gtNm1[s3] = gT;
     gT = gT + ab;
@@ -132,7 +138,8 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
 #endif
 __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
                                                   double *gU, double *gV, double *guNm1, double *gvNm1,
-                                                  double deltaTMom, double abFac, int momForcing, int dissInAB) {
+                                                  double deltaTMom, double abFac, int momForcing, int dissInAB,
+                                                  const double *phiHyd) {
   const int i = blockIdx.x * 32 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
   const int j = blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx + 1 || j > g.sNy + 1) return;
@@ -145,8 +152,14 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
     MomOut o = mom_cell(g, st, p, k, i, j, ukm, ukp, vkm, vkp);
     const size_t s3 = g.s3(i, j, k);
     double gu = o.gU, gv = o.gV;
-    // timestep.F:120-121 with dPhiHydX = dPhiHydY = 0 (buoyancy decoupled): gU - phFac*0
-    gu = gu - 0.; gv = gv - 0.;
+    // timestep.F:120-121: gU - phFac*dPhiHydX with CALC_GRAD_PHI_HYD (calc_grad_phi_hyd.F:150-165) on
+    // i = iMin+1..iMax, j = jMin+1..jMax; zero when the buoyancy is decoupled (phiHyd == nullptr)
+    double dpx = 0., dpy = 0.;
+    if (phiHyd) {
+      if (i >= 1) dpx = g.recip_dxC[s] * 1. * (phiHyd[s3] - phiHyd[s3 - 1]) * 1.;
+      if (j >= 1) dpy = g.recip_dyC[s] * 1. * (phiHyd[s3] - phiHyd[s3 - g.PX]) * 1.;
+    }
+    gu = gu - 1. * dpx; gv = gv - 1. * dpy;
     if (p.momViscosity && dissInAB) { gu = gu + o.guDiss; gv = gv + o.gvDiss; }
     if (momForcing) {       // apply_forcing.F:142-148: surface stress in the top level
       double ge = 0., he = 0.;
@@ -171,7 +184,8 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
 
 // ---- surface pressure right-hand side -----------------------------------------------------------
 __global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
-                                                  const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
+                                                  const double *__restrict__ etaN, const double *__restrict__ etaFS,
+                                                  const double *__restrict__ Bo_surf,
                                                   double *__restrict__ cg2d_b, double *__restrict__ cg2d_x,
                                                   double deltaTMom, double deltaTFreeSurf, double freeSurfFac) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
@@ -195,7 +209,8 @@ __global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *__re
       b = b + px1 - px0;
       b = b + py1 - py0;
     }
-    b = b - freeSurfFac * g.rA[s] / deltaTMom / deltaTFreeSurf * etaN[s];
+    // free-surface term on etaH (exactConserv, solve_for_pressure.F:213-222) or etaN (:224-233)
+    b = b - freeSurfFac * g.rA[s] * 1. / deltaTMom / deltaTFreeSurf * etaFS[s];
   }
   cg2d_b[s] = b;
 }
@@ -276,6 +291,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   if (!u || !v || !w || !gU || !gV || !guN || !gvN || !eta || !b || !x || !sfU || !sfV || !Bo || !rBo || !kapU || !kapV) return false;
   const size_t ns = g.slab;
   dim3 blk(32, 4);
+  // optional physics of the wider configurations (see include/mitgcm_b200.h, forward step)
+  const bool buoy = q.I(MI_BUOYANCYLINEAR) != 0, relaxT = q.I(MI_DOTHETACLIMRELAX) != 0;
+  const bool exactConserv = q.I(MI_EXACTCONSERV) != 0, implDiff = q.I(MI_IMPLICITDIFFUSION) != 0;
+  if ((buoy || relaxT || exactConserv) && g.nPx * g.nPy > 1)
+    return fail(61, "forward_step: buoyancy / relaxation / exactConserv are single-rank for now");
+  if (g.Nr > PHYS_NRMAX && implDiff) return fail(61, "forward_step: implicit diffusion supports Nr <= 64");
+  double *rho = nullptr, *phiHyd = nullptr, *sfT = nullptr, *etaH = nullptr;
+  if (buoy && (!(rho = field(MG_RHOINSITU)) || !(phiHyd = field(MG_PHIHYD)))) return false;
+  if (relaxT && !(sfT = field(MG_SURFFORCT))) return false;
+  if (exactConserv && !(etaH = field(MG_ETAH))) return false;
   const bool prof = q.I(MI_PROFILE) != 0;
   auto mark = [&](int n) {
     if (!prof) return;
@@ -284,6 +309,27 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   };
   if (part == 0) {
   mark(0);
+  // DO_OCEANIC_PHYS: surface relaxation forcing, in-situ density, convective flag -> kappaRT
+  if (buoy || relaxT) {
+    double *th = field(MG_THETA), *sa = field(MG_SALT), *sst = field(MG_SST), *lam = field(MG_LAMBDATHETACLIMRELAX);
+    double *tRef = field(MG_TREF), *sRef = field(MG_SREF), *kapT = field(MG_KAPPART), *sf = field(MG_SURFFORCT);
+    double *rh = field(MG_RHOINSITU);
+    if (!th || !sa || !sst || !lam || !tRef || !sRef || !kapT || !sf || !rh) return false;
+    EosLinear e{q.D(MP_RHONIL), q.D(MP_RHOCONST), q.D(MP_TALPHA), q.D(MP_SBETA)};
+    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
+        size_t o3 = ns * g.Nr * t, o2 = ns * t;
+        c.launches++;
+        ocean_phys_kernel<<<grd, blk, 0, c.stream>>>(tg, th + o3, sa + o3, sst + o2, lam + o2, tRef, sRef, e, q.D(MP_RKSIGN),
+                                                     q.D(MP_IVDC_KAPPA), q.D(MP_DIFFKRT), relaxT ? 1 : 0, buoy ? 1 : 0,
+                                                     sf + o2, rh + o3, kapT + o3);
+      }
+    MG_CUDA(cudaGetLastError());
+  }
   // THERMODYNAMICS
   if (q.I(MI_TEMPSTEPPING)) {
     double *th = field(MG_THETA), *th2 = field(MG_THETA2), *gtN = field(MG_GTNM1), *kapT = field(MG_KAPPART);
@@ -299,13 +345,18 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
       for (int bi = 1; bi <= g.nSx; bi++) {
         TileGrid tg;
         if (!make_tile_grid(bi, bj, tg)) return false;
-        size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
+        size_t o2 = ns * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1)), o3 = o2 * g.Nr;
         c.launches++;
         if (thermo_fast_ok(g, p))
           thermo_fast_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
-              tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
+              tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr);
         else
-          thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac);
+          thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac,
+                                                   sfT ? sfT + o2 : nullptr);
+        if (implDiff) {      // GAD_IMPLICIT_R on theta* (temp_integrate.F:495-503)
+          c.launches++;
+          impldiff_kernel<<<grd, blk, 0, c.stream>>>(tg, kapT + o3, th2 + o3, p.deltaT);
+        }
       }
     MG_CUDA(cudaGetLastError());
     // CYCLE_TRACER: theta <- theta** (interior); halos follow in the blocking exchange below
@@ -313,6 +364,20 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   }
   mark(1);
   // DYNAMICS
+  if (buoy) {     // CALC_PHI_HYD for all levels (dynamics.F:436-441 marches it level by level)
+    double *rF = field(MG_RF), *rC = field(MG_RC);
+    if (!rF || !rC) return false;
+    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
+        c.launches++;
+        phihyd_kernel<<<grd, blk, 0, c.stream>>>(tg, rho + o3, rF, rC, q.D(MP_GRAVITY), 1.0 / q.D(MP_RHOCONST), phiHyd + o3);
+      }
+    MG_CUDA(cudaGetLastError());
+  }
   {
     dim3 grd((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 3) / 4);
     for (int bj = 1; bj <= g.nSy; bj++)
@@ -323,7 +388,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        if (dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
+        if (!buoy && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
           static bool attr = false;
           if (!attr) {
             cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
@@ -332,13 +397,14 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
           dyn_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(DynPipeSmem),
                             c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
                                         abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
-        } else if (dyn_fast_ok(g, mp))
+        } else if (!buoy && dyn_fast_ok(g, mp))
           dyn_fast_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
         else
           dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
-                                                q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+                                                q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
+                                                buoy ? phiHyd + o3 : nullptr);
       }
     MG_CUDA(cudaGetLastError());
   }
@@ -353,7 +419,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
-        rhs_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
+        rhs_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
                                               q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC));
       }
     MG_CUDA(cudaGetLastError());
@@ -391,6 +457,32 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   return true;
 }
 
+// INTEGR_CONTINUITY, exactConserv part (integr_continuity.F:120-215) + _EXCH_XY_RL(etaN) (:331-333) +
+// UPDATE_ETAH (update_etah.F: etaH = etaN for implicDiv2DFlow = 1).  The reference runs it on velocities
+// that CORRECTION_STEP has already updated over the whole halo'd slab; here the correction kernel writes
+// the interior only, so this runs after the u, v halo exchange (same values).
+static bool etah_update() {
+  Ctx &c = ctx();
+  const Geom &g = c.g;
+  const Params &q = c.p;
+  double *u = field(MG_UVEL), *v = field(MG_VVEL), *eta = field(MG_ETAN), *etaH = field(MG_ETAH), *dEtaHdt = field(MG_DETAHDT);
+  if (!u || !v || !eta || !etaH || !dEtaHdt) return false;
+  dim3 blk(32, 4), grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
+  for (int bj = 1; bj <= g.nSy; bj++)
+    for (int bi = 1; bi <= g.nSx; bi++) {
+      TileGrid tg;
+      if (!make_tile_grid(bi, bj, tg)) return false;
+      size_t o2 = g.slab * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1)), o3 = o2 * g.Nr;
+      c.launches++;
+      etah_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, etaH + o2, dEtaHdt + o2, eta + o2, q.D(MP_IMPLICDIV2DFLOW),
+                                             q.D(MP_DELTATFREESURF));
+    }
+  MG_CUDA(cudaGetLastError());
+  if (!exch_field(eta, 1)) return false;
+  MG_CUDA(cudaMemcpyAsync(etaH, eta, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  return true;
+}
+
 static bool forward_step(int myIter, double *initRes, int *iters, double *lastRes) {
   Ctx &c = ctx();
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
@@ -406,8 +498,10 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
     if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
     cudaEventRecord(c.pev[n], c.stream);
   };
-  // DO_FIELDS_BLOCKING_EXCHANGES
-  if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr) || !exch_field(field(MG_WVEL), g.Nr)) return false;
+  // DO_FIELDS_BLOCKING_EXCHANGES (u, v first: the exactConserv update of etaN reads their halos)
+  if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr)) return false;
+  if (q.I(MI_EXACTCONSERV) && !etah_update()) return false;
+  if (!exch_field(field(MG_WVEL), g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
   mark(7);
   return true;

@@ -506,7 +506,7 @@ struct ThermoSmem {
 __global__ void __launch_bounds__(FT_X *FT_Y, 3)
     thermo_fast_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
                        const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
-                       double *__restrict__ gtNm1, GadPar p, double abFac) {
+                       double *__restrict__ gtNm1, GadPar p, double abFac, const double *__restrict__ sfT) {
   __shared__ ThermoSmem sm;
   __shared__ VertSmem vs;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FT_X + tx;
@@ -586,6 +586,11 @@ __global__ void __launch_bounds__(FT_X *FT_Y, 3)
                            ((fz1 - fz0) + (fm1 - fm0) + (fVdn - fvu) * p.rkSign -
                             T00 * ((SM(uT, 1, 0) - SM(uT, 0, 0)) * advFac + (SM(vT, 0, 1) - SM(vT, 0, 0)) * advFac +
                                    (rTransKp1 - rTrans) * rAdvFac));
+      if (sfT) {   // APPLY_FORCING_T at k = kSurface, inside Adams-Bashforth (tracForcingOutAB = 0)
+        double gtForc = 0.;
+        if (k == 1) gtForc = gtForc + sfT[g.s(i, j)] * vs.rdrF[0] * rhC;
+        gT = gT + gtForc;
+      }
       const double ab = abFac * (gT - gtOld);
       gtNm1[s3] = gT;
       gT = gT + ab;

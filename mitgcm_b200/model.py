@@ -19,7 +19,8 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "bottomDragQuadratic no_slip_sides no_slip_bottom bottomVisc_pCell selectBotDragQuadr "
               "useBiharmonicVisc implicitViscosity selectCoriScheme rigidLid momAdvection momViscosity "
               "diffKhT diffK4T diffKrT viscAr tempStepping cg2dMaxIters momForcing momDissip_In_AB "
-              "implicitDiffusion useSRCGSolver").split()
+              "implicitDiffusion useSRCGSolver usingSphericalPolarGrid selectMetricTerms recip_rSphere "
+              "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa").split()
 
 
 def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
@@ -92,6 +93,16 @@ class Model:
         for n, fid in (("uVel", "uVel"), ("vVel", "vVel"), ("wVel", "wVel"), ("theta", "theta"), ("etaN", "etaN"),
                        ("surfForcU", "surfForcU"), ("surfForcV", "surfForcV")):
             rt.set_field(fid, np.ascontiguousarray(state[n]))
+        # optional physics of the wider configurations (include/mitgcm_b200.h, forward step)
+        for n in ("salt", "SST", "lambdaThetaClimRelax", "etaH"):
+            if n in state:
+                rt.set_field(n, np.ascontiguousarray(state[n]))
+        for n in ("tRef", "sRef", "rF", "rC"):
+            src = state.get(n, g.a.get(n))
+            if src is not None:
+                v = np.zeros(g.d.Nr + 1)
+                v[:len(src)] = src
+                rt.set_field(n, v)
         rt.fill_field("kappaRU", P.get("viscAr", 0.0))
         rt.fill_field("kappaRV", P.get("viscAr", 0.0))
         rt.fill_field("kappaRT", P.get("diffKrT", 0.0))
