@@ -174,7 +174,22 @@ void mitgcm_b200_set_exch2_topology_(
     const int *nTiles, const int *maxNeighbours, const int *nNeighbours, const int *neighbourId,
     const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
     const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex, const int *tBasey,
+    const int *isNedge, const int *isSedge, const int *isEedge, const int *isWedge,
     const int *myTileList, int *ierr);
+/* EXCH_UV_XY_RL/RS, EXCH_UV_XYZ_RL/RS on a pair of mirrors (eesupp/src/exch_uv_xyz_rx.template): on an exch2
+ * tile graph EXCH2_UV_3D_RX (pkg/exch2/exch2_uv_3d_rx.template: two EXCH2_RX2_CUBE passes with the C-grid index
+ * offsets of exch2_get_uv_bounds.F, u/v swapped and, when withSigns, negated across rotated facet edges, then
+ * the cube-corner fix-ups); on the plain periodic tiling two scalar exchanges. */
+void mitgcm_b200_exch_uv_(const int *idU, const int *idV, const int *withSigns, int *ierr);
+/* Host-only helper (no device needed): the compiled vector-pair exchange of a tile graph as a list of 4-int
+ * entries (dst array 0/1, dst flat cell, src array << 1 | negate, src flat cell) over (nTiles, sNy+2*OL,
+ * sNx+2*OL) arrays; dims3 = {sNx, sNy, OL}.  Used by the host set-up code and the CPU tests. */
+void mitgcm_b200_exch2_uv_map_(
+    const int *dims3, const int *withSigns, const int *nTiles, const int *maxNeighbours, const int *nNeighbours,
+    const int *neighbourId, const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi,
+    const int *oj, const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex,
+    const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge, const int *isWedge,
+    const int *maxEntries, int *nEntries, int *out4, int *ierr);
 
 /* ---- multi-GPU (one process per GPU on one NVSwitch domain) --------------------------------
  * CG2D: every rank exports its solver workspace as a CUDA IPC handle (64 bytes) and, after the

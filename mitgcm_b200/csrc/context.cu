@@ -168,6 +168,11 @@ void mitgcm_b200_finalize_(void) {
   if (c.e2List) cudaFree(c.e2List);
   c.e2List = nullptr;
   c.e2Count = 0;
+  for (int w = 0; w < 2; w++) {
+    if (c.e2UvList[w]) cudaFree(c.e2UvList[w]);
+    c.e2UvList[w] = nullptr;
+    c.e2UvCount[w] = 0;
+  }
   cg2d_free_workspace();
   for (auto &e : c.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto &e : c.pev) if (e) { cudaEventDestroy(e); e = nullptr; }

@@ -47,6 +47,8 @@ struct Ctx {
   // pkg/exch2 tile graph (exch2.cu): gather list (dst, src) pairs of the full-width scalar exchange
   int *e2List = nullptr;
   int e2Count = 0;
+  int *e2UvList[2] = {nullptr, nullptr};   // vector-pair exchange, [withSigns]: 4 ints per entry
+  int e2UvCount[2] = {0, 0};
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;
@@ -76,5 +78,7 @@ double *to_device(const double *p, size_t n, int slot, bool upload);
 bool from_device(double *hostOrDev, const double *dev, size_t n);  // no-op when same pointer
 bool exch2_active();                                   // a pkg/exch2 topology has been set
 bool exch2_field(double *f, int nz);                   // EXCH2_3D_RX as one gather
+bool exch2_uv_field(double *u, double *v, int nz, bool withSigns);   // EXCH2_UV_3D_RX as one gather
+bool exch_field(double *f, int nz);                    // EXCH_XY(Z)_RL on a mirror (step.cu)
 
 }  // namespace mg

@@ -18,6 +18,7 @@ namespace mg {
 struct E2Tables {
   int nT = 0, maxN = 0;
   std::vector<int> nN, nid, opp, ndir, pij, oi, oj, iLo, iHi, jLo, jHi, bx, by, local;
+  std::vector<int> isN, isS, isE, isW;   // exch2_isNedge .. exch2_isWedge
   int N(int t) const { return nN[t]; }
   int at(const std::vector<int> &a, int n, int t) const { return a[n + maxN * t]; }
   int P(int k, int n, int t) const { return pij[k + 4 * (n + maxN * t)]; }
@@ -73,6 +74,147 @@ __global__ void gather_kernel(double *f, const int2 *lst, int n, int nz, size_t 
     const size_t st = (size_t)ds.y / slab, sc = (size_t)ds.y % slab;
     f[dc + slab * (k + (size_t)nz * dt)] = f[sc + slab * (k + (size_t)nz * st)];
   }
+}
+
+// ---- vector pairs on the C grid: EXCH2_UV_3D_RX -------------------------------------------------------
+// EXCH2_GET_UV_BOUNDS with fCode 'Cg' (exch2_get_uv_bounds.F:60-262): target ranges of the two components
+// through neighbour entry n of tile t and the index offsets of the source entry.
+struct UvBounds { int r1[4], r2[4], o[4]; };
+static UvBounds uv_bounds(const E2Tables &T, int n, int t, int eW, bool corners) {
+  UvBounds b;
+  const int tIlo = T.at(T.iLo, n, t), tIhi = T.at(T.iHi, n, t), tJlo = T.at(T.jLo, n, t), tJhi = T.at(T.jHi, n, t);
+  const int s = T.at(T.nid, n, t) - 1, m = T.at(T.opp, n, t) - 1;
+  int oi1 = T.at(T.oi, m, s), oj1 = T.at(T.oj, m, s);
+  const int p0 = T.P(0, m, s), p1 = T.P(1, m, s), p2 = T.P(2, m, s), p3 = T.P(3, m, s);
+  int i0 = 0, i1 = 0, j0 = 0, j1 = 0;
+  const int grow = corners ? eW - 1 : -1;
+  if (tIlo == tIhi && tIlo == 0) { i0 = 1 - eW; i1 = 0; j0 = tJlo - grow; j1 = tJhi + grow; }
+  if (tIlo == tIhi && tIlo > 1) { i0 = tIlo; i1 = tIhi + eW - 1; j0 = tJlo - grow; j1 = tJhi + grow; }
+  if (tJlo == tJhi && tJlo == 0) { j0 = 1 - eW; j1 = 0; i0 = tIlo - grow; i1 = tIhi + grow; }
+  if (tJlo == tJhi && tJlo > 1) { j0 = tJlo; j1 = tJhi + eW - 1; i0 = tIlo - grow; i1 = tIhi + grow; }
+  int a[4] = {i0, i1, j0, j1}, c[4] = {i0, i1, j0, j1};
+  int oi2 = oi1, oj2 = oj1;
+  if (p0 == -1) oi1++;
+  if (p2 == -1) oj1++;
+  if (p1 == -1) oi2++;
+  if (p3 == -1) oj2++;
+  if (corners) {
+    if (p0 == -1 || p2 == -1) a[0]++;
+    if (p1 == -1 || p3 == -1) c[2]++;
+    if (tIlo == tIhi && tIlo > 1) {           // east edge of a tile on the face S / N edge
+      if (T.isS[t] == 1) { a[2] = tJlo + 1; c[2] = tJlo + 1; }
+      if (T.isN[t] == 1) { a[3] = tJhi - 1; c[3] = tJhi; }
+    }
+    if (tJlo == tJhi && tJlo > 1) {           // north edge of a tile on the face W / E edge
+      if (T.isW[t] == 1) { a[0] = tIlo + 1; c[0] = tIlo + 1; }
+      if (T.isE[t] == 1) { a[1] = tIhi; c[1] = tIhi - 1; }
+    }
+  } else {
+    if (p0 == -1 || p2 == -1) { a[0]++; a[1]++; }
+    if (p1 == -1 || p3 == -1) { c[2]++; c[3]++; }
+  }
+  for (int q = 0; q < 4; q++) { b.r1[q] = a[q]; b.r2[q] = c[q]; }
+  b.o[0] = oi1; b.o[1] = oj1; b.o[2] = oi2; b.o[3] = oj2;
+  return b;
+}
+
+struct Prov { int arr, cell, sign; };   // which array (0 = u, 1 = v), flat cell, +-1
+
+// Both passes of EXCH2_RX2_CUBE (exch2_rx2_cube.template, exch2_put_rx2.template:150-260: the value put
+// for a target cell is sa1*u(src) + sa2*v(src) with (sa1, sa2) = (pij1, pij3) for the first component and
+// (pij2, pij4) for the second, absolute values when withSigns is false) and the four cube-corner fix-ups of
+// exch2_uv_3d_rx.template:117-230, composed cell by cell into provenances.
+static bool compile_uv(const E2Tables &T, int sNx, int sNy, int OL, bool withSigns, std::vector<Prov> pr[2]) {
+  const int PX = sNx + 2 * OL, PY = sNy + 2 * OL;
+  auto flat = [&](int t, int i, int j) { return (t * PY + (j + OL - 1)) * PX + (i + OL - 1); };
+  const size_t n = (size_t)T.nT * PX * PY;
+  for (int a = 0; a < 2; a++) {
+    pr[a].resize(n);
+    for (size_t q = 0; q < n; q++) pr[a][q] = Prov{a, (int)q, 1};
+  }
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<Prov> nw[2] = {pr[0], pr[1]};
+    for (int t = 0; t < T.nT; t++)
+      for (int e = 0; e < T.N(t); e++) {
+        const int s = T.at(T.nid, e, t) - 1, m = T.at(T.opp, e, t) - 1;
+        const UvBounds b = uv_bounds(T, e, t, OL, pass == 1);
+        const int p0 = T.P(0, m, s), p1 = T.P(1, m, s), p2 = T.P(2, m, s), p3 = T.P(3, m, s);
+        for (int comp = 0; comp < 2; comp++) {
+          const int *r = comp == 0 ? b.r1 : b.r2;
+          const int oi = b.o[2 * comp], oj = b.o[2 * comp + 1];
+          int sa1 = comp == 0 ? p0 : p1, sa2 = comp == 0 ? p2 : p3;
+          if (!withSigns) { sa1 = abs(sa1); sa2 = abs(sa2); }
+          if ((sa1 != 0) == (sa2 != 0)) return fail(73, "exch2: vector index map is not a signed permutation");
+          for (int j = r[2]; j <= r[3]; j++)
+            for (int i = r[0]; i <= r[1]; i++) {
+              const int ic = i + T.bx[t], jc = j + T.by[t];
+              const int si = p0 * ic + p1 * jc + oi - T.bx[s], sj = p2 * ic + p3 * jc + oj - T.by[s];
+              if (si < 1 - OL || si > sNx + OL || sj < 1 - OL || sj > sNy + OL || i < 1 - OL || i > sNx + OL ||
+                  j < 1 - OL || j > sNy + OL)
+                return fail(71, "exch2: vector index map leaves the tile array");
+              Prov src = pr[sa1 != 0 ? 0 : 1][flat(s, si, sj)];
+              src.sign *= (sa1 != 0 ? sa1 : sa2);
+              nw[comp][flat(t, i, j)] = src;
+            }
+        }
+      }
+    pr[0].swap(nw[0]);
+    pr[1].swap(nw[1]);
+  }
+  if (OL >= 2) {
+    const int sg = withSigns ? -1 : 1;
+    auto cp = [&](int da, int t, int di, int dj, int sa, int si, int sj, int sign) {
+      Prov v = pr[sa][flat(t, si, sj)];
+      v.sign *= sign;
+      pr[da][flat(t, di, dj)] = v;
+    };
+    for (int t = 0; t < T.nT; t++) {
+      const bool W = T.isW[t] == 1, E = T.isE[t] == 1, S = T.isS[t] == 1, N = T.isN[t] == 1;
+      if (W && S) { cp(0, t, 0, 0, 1, 1, 0, 1); cp(1, t, 0, 0, 0, 0, 1, 1); }
+      if (W && N) { cp(0, t, 0, sNy + 1, 1, 1, sNy + 2, sg); cp(1, t, 0, sNy + 2, 0, 0, sNy, sg); }
+      if (E && S) { cp(0, t, sNx + 2, 0, 1, sNx, 0, sg); cp(1, t, sNx + 1, 0, 0, sNx + 2, 1, sg); }
+      if (E && N) { cp(0, t, sNx + 2, sNy + 1, 1, sNx, sNy + 2, 1); cp(1, t, sNx + 1, sNy + 2, 0, sNx + 2, sNy, 1); }
+    }
+  }
+  return true;
+}
+
+// list entries: 4 ints (dst array, dst tile*slab+cell, src array << 1 | (sign < 0), src tile*slab+cell)
+static void uv_list(const std::vector<Prov> pr[2], const std::vector<int> &local, size_t slab, std::vector<int> &lst) {
+  lst.clear();
+  for (int a = 0; a < 2; a++)
+    for (size_t q = 0; q < pr[a].size(); q++) {
+      const Prov &v = pr[a][q];
+      if (v.arr == a && v.cell == (int)q && v.sign == 1) continue;
+      lst.push_back(a);
+      lst.push_back(local[q / slab] * (int)slab + (int)(q % slab));
+      lst.push_back((v.arr << 1) | (v.sign < 0 ? 1 : 0));
+      lst.push_back(local[v.cell / (int)slab] * (int)slab + v.cell % (int)slab);
+    }
+}
+
+__global__ void gather_uv_kernel(double *u, double *v, const int4 *lst, int n, int nz, size_t slab) {
+  const size_t total = (size_t)n * nz;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(q % n), k = (int)(q / n);
+    const int4 d = lst[e];
+    const size_t dt = (size_t)d.y / slab, dc = (size_t)d.y % slab, st = (size_t)d.w / slab, sc = (size_t)d.w % slab;
+    const double *src = (d.z >> 1) ? v : u;
+    double val = src[sc + slab * (k + (size_t)nz * st)];
+    if (d.z & 1) val = -val;
+    (d.x ? v : u)[dc + slab * (k + (size_t)nz * dt)] = val;
+  }
+}
+
+bool exch2_uv_field(double *u, double *v, int nz, bool withSigns) {
+  Ctx &c = ctx();
+  const int w = withSigns ? 1 : 0;
+  const size_t total = (size_t)c.e2UvCount[w] * nz;
+  int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  c.launches++;
+  gather_uv_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(u, v, reinterpret_cast<const int4 *>(c.e2UvList[w]), c.e2UvCount[w], nz, c.g.slab);
+  MG_CUDA(cudaGetLastError());
+  return true;
 }
 
 bool exch2_active() { return ctx().e2Count > 0; }
@@ -137,6 +279,49 @@ static bool set_topology(const E2Tables &T) {
   for (int v : tab)
     if (v < 0) return fail(72, "exch2: an edge point has no neighbour (open edges are not supported)");
   MG_CUDA(cudaMemcpy(c.pushTab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // ---- vector-pair exchange (EXCH_UV_XY / EXCH_UV_XYZ), unsigned and signed ----------------------------
+  for (int w = 0; w < 2; w++) {
+    std::vector<Prov> pr[2];
+    if (!compile_uv(T, g.sNx, g.sNy, g.OLx, w == 1, pr)) return false;
+    std::vector<int> ul;
+    uv_list(pr, T.local, g.slab, ul);
+    if (c.e2UvList[w]) cudaFree(c.e2UvList[w]);
+    MG_CUDA(cudaMalloc(&c.e2UvList[w], std::max<size_t>(ul.size(), 4) * sizeof(int)));
+    MG_CUDA(cudaMemcpy(c.e2UvList[w], ul.data(), ul.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c.e2UvCount[w] = (int)(ul.size() / 4);
+  }
+  return true;
+}
+
+static bool load_tables(E2Tables &T, int nT, int maxN, int nLocal, const int *nNeighbours, const int *neighbourId,
+                        const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
+                        const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex,
+                        const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge,
+                        const int *isWedge, const int *myTileList) {
+  T.nT = nT; T.maxN = maxN;
+  const size_t nn = (size_t)T.nT * T.maxN;
+  T.nN.assign(nNeighbours, nNeighbours + T.nT);
+  T.nid.assign(neighbourId, neighbourId + nn); T.opp.assign(opposingSend, opposingSend + nn);
+  T.ndir.assign(neighbourDir, neighbourDir + nn); T.pij.assign(pij, pij + 4 * nn);
+  T.oi.assign(oi, oi + nn); T.oj.assign(oj, oj + nn);
+  T.iLo.assign(iLo, iLo + nn); T.iHi.assign(iHi, iHi + nn); T.jLo.assign(jLo, jLo + nn); T.jHi.assign(jHi, jHi + nn);
+  T.bx.assign(tBasex, tBasex + T.nT); T.by.assign(tBasey, tBasey + T.nT);
+  T.isN.assign(isNedge, isNedge + T.nT); T.isS.assign(isSedge, isSedge + T.nT);
+  T.isE.assign(isEedge, isEedge + T.nT); T.isW.assign(isWedge, isWedge + T.nT);
+  T.local.assign(T.nT, -1);
+  for (int l = 0; l < nLocal; l++) {
+    const int id = myTileList[l];
+    if (id < 1 || id > T.nT || T.local[id - 1] != -1) return fail(70, "exch2 topology: bad W2_myTileList");
+    T.local[id - 1] = l;
+  }
+  for (int t = 0; t < T.nT; t++) {
+    if (T.local[t] < 0) return fail(70, "exch2 topology: every tile must be in W2_myTileList (one process)");
+    if (T.nN[t] < 0 || T.nN[t] > T.maxN) return fail(70, "exch2 topology: bad exch2_nNeighbours");
+    for (int n = 0; n < T.nN[t]; n++) {
+      const int s = T.at(T.nid, n, t), m = T.at(T.opp, n, t);
+      if (s < 1 || s > T.nT || m < 1 || m > T.nN[s - 1]) return fail(70, "exch2 topology: bad neighbour tables");
+    }
+  }
   return true;
 }
 
@@ -148,6 +333,7 @@ extern "C" void mitgcm_b200_set_exch2_topology_(
     const int *nTiles, const int *maxNeighbours, const int *nNeighbours, const int *neighbourId,
     const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
     const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex, const int *tBasey,
+    const int *isNedge, const int *isSedge, const int *isEedge, const int *isWedge,
     const int *myTileList, int *ierr) {
   Ctx &c = ctx();
   *ierr = 1;
@@ -158,27 +344,33 @@ extern "C" void mitgcm_b200_set_exch2_topology_(
   if (g.OLx != g.OLy) { fail(70, "exch2 topology: OLx must equal OLy"); return; }
   if ((size_t)g.n2 >= ((size_t)1 << 31)) { fail(70, "exch2 topology: tile2d array too large for the gather list"); return; }
   E2Tables T;
-  T.nT = *nTiles; T.maxN = *maxNeighbours;
-  const size_t nn = (size_t)T.nT * T.maxN;
-  T.nN.assign(nNeighbours, nNeighbours + T.nT);
-  T.nid.assign(neighbourId, neighbourId + nn); T.opp.assign(opposingSend, opposingSend + nn);
-  T.ndir.assign(neighbourDir, neighbourDir + nn); T.pij.assign(pij, pij + 4 * nn);
-  T.oi.assign(oi, oi + nn); T.oj.assign(oj, oj + nn);
-  T.iLo.assign(iLo, iLo + nn); T.iHi.assign(iHi, iHi + nn); T.jLo.assign(jLo, jLo + nn); T.jHi.assign(jHi, jHi + nn);
-  T.bx.assign(tBasex, tBasex + T.nT); T.by.assign(tBasey, tBasey + T.nT);
-  T.local.assign(T.nT, -1);
-  for (int l = 0; l < g.nTiles; l++) {
-    const int id = myTileList[l];
-    if (id < 1 || id > T.nT || T.local[id - 1] != -1) { fail(70, "exch2 topology: bad W2_myTileList"); return; }
-    T.local[id - 1] = l;
-  }
-  for (int t = 0; t < T.nT; t++) {
-    if (T.nN[t] < 0 || T.nN[t] > T.maxN) { fail(70, "exch2 topology: bad exch2_nNeighbours"); return; }
-    for (int n = 0; n < T.nN[t]; n++) {
-      const int s = T.at(T.nid, n, t), m = T.at(T.opp, n, t);
-      if (s < 1 || s > T.nT || m < 1 || m > T.nN[s - 1]) { fail(70, "exch2 topology: bad neighbour tables"); return; }
-    }
-  }
+  if (!load_tables(T, *nTiles, *maxNeighbours, g.nTiles, nNeighbours, neighbourId, opposingSend, neighbourDir, pij, oi, oj,
+                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, myTileList)) return;
   if (!set_topology(T)) return;
+  *ierr = 0;
+}
+
+// Host-only: the compiled vector-pair exchange as a list of (dst array, dst flat cell, src array << 1 | negate,
+// src flat cell) over (nTiles, sNy+2*OL, sNx+2*OL) arrays, tiles in id order.  No device needed: lets the host
+// set-up code (grid metrics, operator halos) and the CPU tests use exactly what the GPU runs.
+extern "C" void mitgcm_b200_exch2_uv_map_(
+    const int *dims3, const int *withSigns, const int *nTiles, const int *maxNeighbours, const int *nNeighbours,
+    const int *neighbourId, const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi,
+    const int *oj, const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex,
+    const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge, const int *isWedge,
+    const int *maxEntries, int *nEntries, int *out4, int *ierr) {
+  *ierr = 1;
+  E2Tables T;
+  std::vector<int> ids(*nTiles);
+  for (int t = 0; t < *nTiles; t++) ids[t] = t + 1;
+  if (!load_tables(T, *nTiles, *maxNeighbours, *nTiles, nNeighbours, neighbourId, opposingSend, neighbourDir, pij, oi, oj,
+                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, ids.data())) return;
+  std::vector<Prov> pr[2];
+  if (!compile_uv(T, dims3[0], dims3[1], dims3[2], *withSigns != 0, pr)) return;
+  std::vector<int> lst;
+  uv_list(pr, T.local, (size_t)(dims3[0] + 2 * dims3[2]) * (dims3[1] + 2 * dims3[2]), lst);
+  *nEntries = (int)(lst.size() / 4);
+  if (*nEntries > *maxEntries) { fail(74, "exch2_uv_map: output buffer too small"); return; }
+  std::copy(lst.begin(), lst.end(), out4);
   *ierr = 0;
 }

@@ -77,7 +77,7 @@ bool make_tile_grid(int bi, int bj, TileGrid &t) {
 
 static bool supported_scheme(int s) {
   return s == ADV_UPWIND_1RST || s == ADV_CENTERED_2ND || s == ADV_UPWIND_3RD || s == ADV_CENTERED_4TH ||
-         s == ADV_DST2 || s == ADV_FLUX_LIMIT || s == ADV_DST3 || s == ADV_DST3_FLUX_LIMIT;
+         s == ADV_DST2 || s == ADV_FLUX_LIMIT || s == ADV_DST3 || s == ADV_DST3_FLUX_LIMIT || s == ADV_OS7MP;
 }
 
 }  // namespace mg
@@ -107,6 +107,10 @@ extern "C" void gad_calc_rhs_b200_(
     return;
   }
   const Geom &g = c.g;
+  if (*calcAdvection && *advectionSchArg == ADV_OS7MP && (g.OLx < 4 || g.OLy < 4)) {
+    fail(42, "gad_calc_rhs_b200_: OS7MP needs OLx, OLy >= 4 (gad_check.F overlap test)");
+    return;
+  }
   const int K = *k, Nr = g.Nr;
   if (K < 1 || K > Nr || *kUp < 1 || *kUp > 2 || *kDown < 1 || *kDown > 2) { fail(40, "bad level index"); return; }
   TileGrid tg;
@@ -122,8 +126,10 @@ extern "C" void gad_calc_rhs_b200_(
   }
   a.xA_ = dev[0]; a.yA_ = dev[1]; a.maskUp_ = dev[2]; a.uFld_ = dev[3]; a.vFld_ = dev[4]; a.wFld_ = dev[5];
   a.uTrans_ = dev[6]; a.vTrans_ = dev[7]; a.rTrans_ = dev[8]; a.rTransKp1_ = dev[9]; a.KappaR_ = dev[10];
-  // tracer levels the stencils can touch: k-2 .. k+1 (k-3 .. k+2 is a safe superset)
-  const int kLo = std::max(1, K - 3), kHi = std::min(Nr, K + 2);
+  // tracer levels the stencils can touch: k-2 .. k+1 (k-3 .. k+2 is a safe superset); the 7-point
+  // OS7MP stencil reaches k-4 .. k+3 (gad_os7mp_adv_r.F:100-107)
+  const int reach = (*vertAdvecSchArg == ADV_OS7MP) ? 4 : 3;
+  const int kLo = std::max(1, K - reach), kHi = std::min(Nr, K + reach - 1);
   auto stage3 = [&](const double *h, int slot) -> double * {
     if (is_device_ptr(h)) return const_cast<double *>(h);
     double *d = to_device(h, ns * Nr, slot, false);

@@ -14,7 +14,7 @@
 namespace mg {
 
 enum { ADV_UPWIND_1RST = 1, ADV_CENTERED_2ND = 2, ADV_UPWIND_3RD = 3, ADV_CENTERED_4TH = 4, ADV_DST2 = 20,
-       ADV_FLUX_LIMIT = 77, ADV_DST3 = 30, ADV_DST3_FLUX_LIMIT = 33 };
+       ADV_FLUX_LIMIT = 77, ADV_DST3 = 30, ADV_DST3_FLUX_LIMIT = 33, ADV_OS7MP = 7 };
 
 // Device views of the GRID.h mirrors for one tile (pointers already offset to the tile).
 struct TileGrid {
@@ -43,11 +43,95 @@ struct GadPar {
 
 __device__ __forceinline__ double gad_limiter(double Cr) { return fmax(0., fmax(fmin(1., 2. * Cr), fmin(2., Cr))); }
 
+// 7th-order one-step method with monotonicity-preserving limiter: the arithmetic shared by
+// GAD_OS7MP_ADV_X / _Y / _R (pkg/generic_advdiff/gad_os7mp_adv_x.F:132-206).  q[0..6] = the seven
+// values along the flow (q[3] = Qi, the cell upstream of the face; q[0] = Qippp ... q[6] = Qimmm),
+// m[0..5] = MskIpp, MskIp, MskI, MskIm, MskImm, MskImmm.  Returns trans*(Qi + Psi*DelIp).
+__device__ inline double gad_os7mp(double trans, double cfl, const double q[7], const double m[6]) {
+  const double Eps = 1.e-20;
+  const double Qipp = q[1], Qip = q[2], Qi = q[3], Qim = q[4], Qimm = q[5], Qimmm = q[6];
+  const double MskIp = m[1], MskI = m[2], MskIm = m[3], MskImm = m[4], MskImmm = m[5];
+  double Fac = 1.;
+  const double DelP = (Qip - Qi) * MskI;
+  double Phi = Fac * DelP;
+  Fac = Fac * (cfl + 1.) / 3.;
+  const double DelM = (Qi - Qim) * MskIm;
+  const double Del2 = DelP - DelM;
+  Phi = Phi - Fac * Del2;
+  Fac = Fac * (cfl - 2.) / 4.;
+  const double DelPP = (Qipp - Qip) * MskIp * MskI;
+  const double Del2P = DelPP - DelP;
+  const double Del3P = Del2P - Del2;
+  Phi = Phi + Fac * Del3P;
+  Fac = Fac * (cfl - 3.) / 5.;
+  const double DelMM = (Qim - Qimm) * MskImm * MskIm;
+  const double Del2M = DelM - DelMM;
+  const double Del3M = Del2 - Del2M;
+  const double Del4 = Del3P - Del3M;
+  Phi = Phi + Fac * Del4;
+  Fac = Fac * (cfl + 2.) / 6.;
+  const double Del2PP = DelPP - DelP;          // as coded in the reference (:151): DelPPP is not used
+  const double Del3PP = Del2PP - Del2P;
+  const double Del4P = Del3PP - Del3P;
+  const double Del5P = Del4P - Del4;
+  Phi = Phi + Fac * Del5P;
+  Fac = Fac * (cfl + 2.) / 7.;
+  const double DelMMM = (Qimm - Qimmm) * MskImmm * MskImm * MskIm;
+  const double Del2MM = DelMM - DelMMM;
+  const double Del3MM = Del2M - Del2MM;
+  const double Del4M = Del3M - Del3MM;
+  const double Del5M = Del4 - Del4M;
+  const double Del6 = Del5P - Del5M;
+  Phi = Phi - Fac * Del6;
+  const double DelIp = (Qip - Qi) * MskI;
+  const double recip_DelIp = copysign(1., DelIp) / fmax(fabs(DelIp), Eps);
+  Phi = Phi * recip_DelIp;
+  const double DelI = (Qi - Qim) * MskIm;
+  const double recip_DelI = copysign(1., DelI) / fmax(fabs(DelI), Eps);
+  const double rp1h = DelI * recip_DelIp;
+  const double rp1h_cfl = rp1h / (cfl + Eps);
+  const double d2 = Del2, d2p1 = Del2P, d2m1 = Del2M;
+  double A = 4. * d2 - d2p1, B = 4. * d2p1 - d2, C = d2, D = d2p1;
+  const double dp1h = fmax(fmin(fmin(A, B), fmin(C, D)), 0.) + fmin(fmax(fmax(A, B), fmax(C, D)), 0.);
+  A = 4. * d2m1 - d2; B = 4. * d2 - d2m1; C = d2m1; D = d2;
+  const double dm1h = fmax(fmin(fmin(A, B), fmin(C, D)), 0.) + fmin(fmax(fmax(A, B), fmax(C, D)), 0.);
+  const double PhiMD = 1. / (1. - cfl) * (DelIp - dp1h) * recip_DelIp;
+  const double PhiLC = rp1h_cfl * (1. + dm1h * recip_DelI);
+  const double PhiMin = fmax(fmin(0., PhiMD), fmin(fmin(0., 2. * rp1h_cfl), PhiLC));
+  const double PhiMax = fmin(fmax(2. / (1. - cfl), PhiMD), fmax(fmax(0., 2. * rp1h_cfl), PhiLC));
+  Phi = fmax(PhiMin, fmin(Phi, PhiMax));
+  const double Psi = Phi * 0.5 * (1. - cfl);
+  return trans * (Qi + Psi * DelIp);
+}
+
 // gad_*_adv_x.F / gad_*_adv_y.F: advective flux through the west (dir 0) / south (dir 1) face.
 template <class A>
 __device__ double gad_adv_h(const TileGrid &g, const A &a, const GadPar &p, int dir, int i, int j) {
   const int di = dir == 0, dj = dir == 1;
   const int scheme = p.advScheme;
+  if (scheme == ADV_OS7MP) {   // gad_os7mp_adv_x.F:96-214 / gad_os7mp_adv_y.F: zero outside 5-OL .. sN+OL-3
+    const int c = dir == 0 ? i : j, lo = 1 - (dir == 0 ? g.OLx : g.OLy) + 4, hi = (dir == 0 ? g.sNx + g.OLx : g.sNy + g.OLy) - 3;
+    if (c < lo || c > hi) return 0.;
+    const double uT = dir == 0 ? a.uTrans(i, j) : a.vTrans(i, j);
+    if (uT == 0.) return 0.;
+    const double vel = dir == 0 ? a.uFld(i, j) : a.vFld(i, j);
+    const double cfl = fabs(vel * p.deltaT * (dir == 0 ? g.recip_dxC[g.s(i, j)] : g.recip_dyC[g.s(i, j)]));
+    const double *mk = dir == 0 ? g.maskW : g.maskS;
+    double q[7], m[6];
+    const int sg = uT > 0. ? 1 : -1;     // upstream side: q[n] = Q(c + sg*(2-n)) (+1 shift when flowing backwards)
+    const int sh = uT > 0. ? 0 : -1;
+#pragma unroll
+    for (int n = 0; n < 7; n++) {
+      const int o = sg * (2 - n) + sh;
+      q[n] = a.TA(i + o * di, j + o * dj, p.k);
+    }
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+      const int o = sg * (2 - n);
+      m[n] = mk[g.s3(i + o * di, j + o * dj, p.k)];
+    }
+    return gad_os7mp(uT, cfl, q, m);
+  }
   const bool narrow = scheme == ADV_CENTERED_2ND || scheme == ADV_UPWIND_1RST || scheme == ADV_DST2;
   // rows/columns the reference leaves at zero
   if (dir == 0) {
@@ -161,6 +245,32 @@ __device__ double gad_adv_r(const TileGrid &g, const A &a, const GadPar &p, int 
   const double oneSixth = 1.0 / 6.0;
   const double Tk = a.TA(i, j, k), Tkm1 = a.TA(i, j, km1);
   const double rT = a.rTrans(i, j);
+  if (scheme == ADV_OS7MP) {   // gad_os7mp_adv_r.F:96-210 (rT < 0: upward flow, upstream cell is k-1)
+    if (rT == 0.) return 0.;
+    const double cfl = fabs(a.wFld(i, j) * p.deltaT * g.recip_drC[k - 1]);
+    auto cl = [&](int kk) { return min(Nr, max(1, kk)); };
+    double q[7], m[6];
+    if (rT < 0.) {
+      const int ks[8] = {cl(k + 2), cl(k + 1), k, cl(k - 1), cl(k - 2), cl(k - 3), cl(k - 4), 0};
+#pragma unroll
+      for (int n = 0; n < 7; n++) q[n] = a.TA(i, j, ks[n]);
+#pragma unroll
+      for (int n = 0; n < 6; n++) m[n] = g.maskC[g.s3(i, j, ks[n])] * (double)(ks[n] - ks[n + 1]);
+    } else {
+      const int ks[8] = {cl(k - 3), cl(k - 2), cl(k - 1), k, cl(k + 1), cl(k + 2), cl(k + 3), 0};
+#pragma unroll
+      for (int n = 0; n < 7; n++) q[n] = a.TA(i, j, ks[n]);
+      // MskIpp = maskC(km2)*(km2-km3), MskIp = maskC(km1)*(km1-km2), MskI = maskC(k)*(k-km1),
+      // MskIm = maskC(kp1)*(kp1-k), MskImm = maskC(kp2)*(kp2-kp1), MskImmm = maskC(kp3)*(kp3-kp2)
+      m[0] = g.maskC[g.s3(i, j, ks[1])] * (double)(ks[1] - ks[0]);
+      m[1] = g.maskC[g.s3(i, j, ks[2])] * (double)(ks[2] - ks[1]);
+      m[2] = g.maskC[g.s3(i, j, ks[3])] * (double)(ks[3] - ks[2]);
+      m[3] = g.maskC[g.s3(i, j, ks[4])] * (double)(ks[4] - ks[3]);
+      m[4] = g.maskC[g.s3(i, j, ks[5])] * (double)(ks[5] - ks[4]);
+      m[5] = g.maskC[g.s3(i, j, ks[6])] * (double)(ks[6] - ks[5]);
+    }
+    return gad_os7mp(rT, cfl, q, m);
+  }
   const double mkm1 = g.maskC[g.s3(i, j, km1)];
   if (scheme == ADV_CENTERED_2ND) return mkm1 * rT * (Tk + Tkm1) * 0.5;
   if (scheme == ADV_UPWIND_1RST || scheme == ADV_DST2) {

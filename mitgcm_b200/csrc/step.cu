@@ -622,4 +622,22 @@ void mitgcm_b200_exch_(const int *id, int *ierr) {
   *ierr = 0;
 }
 
+void mitgcm_b200_exch_uv_(const int *idU, const int *idV, const int *withSigns, int *ierr) {
+  Ctx &c = ctx();
+  c.lastError = 0;
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  double *u = field(*idU), *v = field(*idV);
+  if (!u || !v) return;
+  const int nz = field_nz(*idU);
+  if (nz == 0 || nz != field_nz(*idV)) { fail(2, "exch_uv: not a pair of like tile arrays"); return; }
+  if (exch2_active()) {
+    if (!exch2_uv_field(u, v, nz, *withSigns != 0)) return;
+  } else {   // no vector rotation on a plain periodic tiling: two scalar exchanges (exch_uv_xyz_rx.template:86-96)
+    if (!exch_field(u, nz) || !exch_field(v, nz)) return;
+  }
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "exch_uv: stream error"); return; }
+  *ierr = 0;
+}
+
 }  // extern "C"

@@ -92,7 +92,8 @@ class Exch2Topology:
         return dict(nNeighbours=self.nNeighbours.astype(np.int32), neighbourId=f(self.neighbourId),
                     opposingSend=f(self.opposingSend), neighbourDir=f(self.neighbourDir), pij=f(self.pij),
                     oi=f(self.oi), oj=f(self.oj), iLo=f(self.iLo), iHi=f(self.iHi), jLo=f(self.jLo),
-                    jHi=f(self.jHi), tBasex=self.tBasex.astype(np.int32), tBasey=self.tBasey.astype(np.int32))
+                    jHi=f(self.jHi), tBasex=self.tBasex.astype(np.int32), tBasey=self.tBasey.astype(np.int32),
+                    **{"is" + k + "edge": np.ascontiguousarray(self.isEdge[k], dtype=np.int32) for k in "NSEW"})
 
 
 def cubed_sphere_topology(nFace: int, sNx: int, sNy: int, maxNeighbours: int = 8) -> Exch2Topology:
@@ -204,7 +205,8 @@ def set_topology(topo: Exch2Topology, myTileList=None):
         C.byref(C.c_int(topo.nTiles)), C.byref(C.c_int(topo.maxNeighbours)), ip(tb["nNeighbours"]),
         ip(tb["neighbourId"]), ip(tb["opposingSend"]), ip(tb["neighbourDir"]), ip(tb["pij"]), ip(tb["oi"]),
         ip(tb["oj"]), ip(tb["iLo"]), ip(tb["iHi"]), ip(tb["jLo"]), ip(tb["jHi"]), ip(tb["tBasex"]),
-        ip(tb["tBasey"]), ip(tl), C.byref(ierr))
+        ip(tb["tBasey"]), ip(tb["isNedge"]), ip(tb["isSedge"]), ip(tb["isEedge"]), ip(tb["isWedge"]), ip(tl),
+        C.byref(ierr))
     if ierr.value:
         raise RuntimeError(f"set_exch2_topology failed: {L.mitgcm_b200_last_error_string().decode()}")
 
@@ -276,3 +278,46 @@ def exchange(T: Exch2Topology, a: np.ndarray, OL: int, gmap=None) -> np.ndarray:
         v[:, dst] = v[:, src]
         a[...] = v.reshape(nz, nT, PY, PX).transpose(1, 0, 2, 3)
     return a
+
+
+def uv_gather_map(T: Exch2Topology, OL: int, withSigns: bool):
+    """EXCH_UV_XY / EXCH_UV_XYZ on the tile graph (EXCH2_UV_3D_RX) as one gather, compiled by the library
+    (mitgcm_b200_exch2_uv_map_, host code: works without a GPU).  Returns int arrays
+    (dstArr, dst, srcArr, neg, src): component 0 = u, 1 = v; flat indices into (nTiles, PY, PX)."""
+    from . import _lib
+    L = _lib.lib()
+    tb = T.tables()
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    cap = 2 * T.nTiles * (T.sNx + 2 * OL) * (T.sNy + 2 * OL)
+    out = np.zeros(4 * cap, dtype=np.int32)
+    n, ierr = C.c_int(0), C.c_int(0)
+    dims3 = (C.c_int * 3)(T.sNx, T.sNy, OL)
+    L.mitgcm_b200_exch2_uv_map_(
+        dims3, C.byref(C.c_int(int(withSigns))), C.byref(C.c_int(T.nTiles)), C.byref(C.c_int(T.maxNeighbours)),
+        ip(tb["nNeighbours"]), ip(tb["neighbourId"]), ip(tb["opposingSend"]), ip(tb["neighbourDir"]), ip(tb["pij"]),
+        ip(tb["oi"]), ip(tb["oj"]), ip(tb["iLo"]), ip(tb["iHi"]), ip(tb["jLo"]), ip(tb["jHi"]), ip(tb["tBasex"]),
+        ip(tb["tBasey"]), ip(tb["isNedge"]), ip(tb["isSedge"]), ip(tb["isEedge"]), ip(tb["isWedge"]),
+        C.byref(C.c_int(cap)), C.byref(n), ip(out), C.byref(ierr))
+    if ierr.value:
+        raise RuntimeError(f"exch2_uv_map failed: {L.mitgcm_b200_last_error_string().decode()}")
+    e = out[:4 * n.value].reshape(-1, 4)
+    return e[:, 0].copy(), e[:, 1].astype(np.int64), e[:, 2] >> 1, (e[:, 2] & 1).astype(bool), e[:, 3].astype(np.int64)
+
+
+def exchange_uv(T: Exch2Topology, u: np.ndarray, v: np.ndarray, OL: int, withSigns: bool, gmap=None):
+    """In-place EXCH_UV_XY(Z) of host arrays (nTiles, [nz,] PY, PX)."""
+    da, d, sa, neg, s = gmap if gmap is not None else uv_gather_map(T, OL, withSigns)
+    two_d = u.ndim == 3
+    U = u[:, None] if two_d else u
+    V = v[:, None] if two_d else v
+    nT, nz, PY, PX = U.shape
+    fu = U.transpose(1, 0, 2, 3).reshape(nz, -1).copy()
+    fv = V.transpose(1, 0, 2, 3).reshape(nz, -1).copy()
+    src = np.where(sa[None, :] == 0, fu[:, s], fv[:, s])
+    src = np.where(neg[None, :], -src, src)
+    mu, mv = da == 0, da == 1
+    fu[:, d[mu]] = src[:, mu]
+    fv[:, d[mv]] = src[:, mv]
+    U[...] = fu.reshape(nz, nT, PY, PX).transpose(1, 0, 2, 3)
+    V[...] = fv.reshape(nz, nT, PY, PX).transpose(1, 0, 2, 3)
+    return u, v

@@ -189,6 +189,14 @@ def exch(name: str):
     _check(ierr)
 
 
+def exch_uv(nameU: str, nameV: str, withSigns: bool = True):
+    """_EXCH_UV_XY_RL / _EXCH_UV_XYZ_RL on a pair of device mirrors."""
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_exch_uv_(C.byref(C.c_int(field_id(nameU))), C.byref(C.c_int(field_id(nameV))),
+                                    C.byref(C.c_int(int(withSigns))), C.byref(ierr))
+    _check(ierr)
+
+
 def forward_step(myIter: int):
     """One FORWARD_STEP on the resident state; returns the three numbers SOLVE_FOR_PRESSURE
     prints (cg2d_init_res, cg2d_iters, cg2d_last_res)."""

@@ -1,9 +1,9 @@
 /* gad_oracle.c -- CPU restatement of GAD_CALC_RHS, its leaf stencils and
  * CALC_ADV_FLOW.  TEST INFRASTRUCTURE ONLY (see mitgcm_oracle.h).
  * Follows pkg/generic_advdiff/gad_calc_rhs.F:193-781 and the leaves
- * gad_{c2,dst2u1,u3,c4,dst3,dst3fl,fluxlimit}_adv_{x,y,r}.F, gad_diff_{x,y,r}.F,
+ * gad_{c2,dst2u1,u3,c4,dst3,dst3fl,fluxlimit,os7mp}_adv_{x,y,r}.F, gad_diff_{x,y,r}.F,
  * gad_grad_{x,y}.F, gad_del2.F, gad_biharm_{x,y,r}.F (loop ranges as in the
- * reference).  Not restated: GM/Redi, KPP, OBCS, Smolarkiewicz hack, OS7MP,
+ * reference).  Not restated: GM/Redi, KPP, OBCS, Smolarkiewicz hack,
  * SMAG_3D diffusivity, cubed-sphere corner fill; maskInC == 1; deepFac/rhoFac == 1.
  */
 #include <math.h>
@@ -26,7 +26,7 @@
   (void)Nr; (void)off2; (void)off3; (void)offc;
 
 enum { UPWIND_1RST = 1, CENTERED_2ND = 2, UPWIND_3RD = 3, CENTERED_4TH = 4, DST2 = 20,
-       FLUX_LIMIT = 77, DST3 = 30, DST3_FLUX_LIMIT = 33 };
+       FLUX_LIMIT = 77, DST3 = 30, DST3_FLUX_LIMIT = 33, OS7MP = 7 };
 
 static const double oneSixth = 1.0 / 6.0;
 
@@ -65,6 +65,69 @@ void og_calc_adv_flow(const og_grid *g, int bi, int bj, int k,
   }
 }
 
+/* Core of the 7th-order one-step method with the monotonicity-preserving limiter, shared by
+ * GAD_OS7MP_ADV_X / _Y / _R (gad_os7mp_adv_x.F:132-206): Q are the seven values along the flow
+ * (Qi = upstream of the face), M the six face masks, trans the volume transport through the face.
+ * Returns trans*(Qi + Psi*DelIp). */
+static double os7mp_core(double trans, double cfl, double Qippp, double Qipp, double Qip, double Qi, double Qim,
+                         double Qimm, double Qimmm, double MskIpp, double MskIp, double MskI, double MskIm,
+                         double MskImm, double MskImmm) {
+  const double Eps = 1.e-20;
+  double Fac = 1.;
+  const double DelP = (Qip - Qi) * MskI;
+  double Phi = Fac * DelP;
+  Fac = Fac * (cfl + 1.) / 3.;
+  const double DelM = (Qi - Qim) * MskIm;
+  const double Del2 = DelP - DelM;
+  Phi = Phi - Fac * Del2;
+  Fac = Fac * (cfl - 2.) / 4.;
+  const double DelPP = (Qipp - Qip) * MskIp * MskI;
+  const double Del2P = DelPP - DelP;
+  const double Del3P = Del2P - Del2;
+  Phi = Phi + Fac * Del3P;
+  Fac = Fac * (cfl - 3.) / 5.;
+  const double DelMM = (Qim - Qimm) * MskImm * MskIm;
+  const double Del2M = DelM - DelMM;
+  const double Del3M = Del2 - Del2M;
+  const double Del4 = Del3P - Del3M;
+  Phi = Phi + Fac * Del4;
+  Fac = Fac * (cfl + 2.) / 6.;
+  const double DelPPP = (Qippp - Qipp) * MskIpp * MskIp * MskI;
+  (void)DelPPP;                       /* computed but unused by the reference (:150) */
+  const double Del2PP = DelPP - DelP;
+  const double Del3PP = Del2PP - Del2P;
+  const double Del4P = Del3PP - Del3P;
+  const double Del5P = Del4P - Del4;
+  Phi = Phi + Fac * Del5P;
+  Fac = Fac * (cfl + 2.) / 7.;
+  const double DelMMM = (Qimm - Qimmm) * MskImmm * MskImm * MskIm;
+  const double Del2MM = DelMM - DelMMM;
+  const double Del3MM = Del2M - Del2MM;
+  const double Del4M = Del3M - Del3MM;
+  const double Del5M = Del4 - Del4M;
+  const double Del6 = Del5P - Del5M;
+  Phi = Phi - Fac * Del6;
+  const double DelIp = (Qip - Qi) * MskI;
+  const double recip_DelIp = copysign(1., DelIp) / fmax(fabs(DelIp), Eps);
+  Phi = Phi * recip_DelIp;
+  const double DelI = (Qi - Qim) * MskIm;
+  const double recip_DelI = copysign(1., DelI) / fmax(fabs(DelI), Eps);
+  const double rp1h = DelI * recip_DelIp;
+  const double rp1h_cfl = rp1h / (cfl + Eps);
+  const double d2 = Del2, d2p1 = Del2P, d2m1 = Del2M;
+  double A = 4. * d2 - d2p1, B = 4. * d2p1 - d2, C = d2, D = d2p1;
+  const double dp1h = fmax(fmin(fmin(A, B), fmin(C, D)), 0.) + fmin(fmax(fmax(A, B), fmax(C, D)), 0.);
+  A = 4. * d2m1 - d2; B = 4. * d2 - d2m1; C = d2m1; D = d2;
+  const double dm1h = fmax(fmin(fmin(A, B), fmin(C, D)), 0.) + fmin(fmax(fmax(A, B), fmax(C, D)), 0.);
+  const double PhiMD = 1. / (1. - cfl) * (DelIp - dp1h) * recip_DelIp;
+  const double PhiLC = rp1h_cfl * (1. + dm1h * recip_DelI);
+  const double PhiMin = fmax(fmin(0., PhiMD), fmin(fmin(0., 2. * rp1h_cfl), PhiLC));
+  const double PhiMax = fmin(fmax(2. / (1. - cfl), PhiMD), fmax(fmax(0., 2. * rp1h_cfl), PhiLC));
+  Phi = fmax(PhiMin, fmin(Phi, PhiMax));
+  const double Psi = Phi * 0.5 * (1. - cfl);
+  return trans * (Qi + Psi * DelIp);
+}
+
 /* horizontal advective flux, direction dir = 0 (x) / 1 (y).
  * gad_*_adv_x.F / gad_*_adv_y.F */
 static void adv_h(const og_grid *g, int bi, int bj, int k, int dir, int scheme, double deltaTloc,
@@ -73,6 +136,28 @@ static void adv_h(const og_grid *g, int bi, int bj, int k, int dir, int scheme, 
   SETUP
   const int di = dir == 0, dj = dir == 1;
   const double *recip_dC = dir == 0 ? g->recip_dxC : g->recip_dyC;
+  if (scheme == OS7MP) {   /* gad_os7mp_adv_x.F:96-214, gad_os7mp_adv_y.F: seven-point stencil along dir */
+    FORALL af[S(i, j)] = 0.;
+    const int i0 = 1 - OLx + (di ? 4 : 0), i1 = sNx + OLx - (di ? 3 : 0);
+    const int j0 = 1 - OLy + (dj ? 4 : 0), j1 = sNy + OLy - (dj ? 3 : 0);
+    for (int j = j0; j <= j1; j++)
+      for (int i = i0; i <= i1; i++) {
+        const double uT = trans[S(i, j)];
+        if (uT == 0.) { af[S(i, j)] = 0.; continue; }
+        const double cfl = fabs(vel[S(i, j)] * deltaTloc * G2(recip_dC, i, j));
+#define Q_(o) tr[S(i + (o) * di, j + (o) * dj)]
+#define M_(o) maskLoc[S(i + (o) * di, j + (o) * dj)]
+        if (uT > 0.)
+          af[S(i, j)] = os7mp_core(uT, cfl, Q_(2), Q_(1), Q_(0), Q_(-1), Q_(-2), Q_(-3), Q_(-4),
+                                   M_(2), M_(1), M_(0), M_(-1), M_(-2), M_(-3));
+        else
+          af[S(i, j)] = os7mp_core(uT, cfl, Q_(-3), Q_(-2), Q_(-1), Q_(0), Q_(1), Q_(2), Q_(3),
+                                   M_(-2), M_(-1), M_(0), M_(1), M_(2), M_(3));
+#undef Q_
+#undef M_
+      }
+    return;
+  }
   /* leading rows/columns the reference zeroes explicitly */
   if (scheme == CENTERED_2ND || scheme == UPWIND_1RST || scheme == DST2) {
     if (dir == 0) for (int j = 1 - OLy; j <= sNy + OLy; j++) af[S(1 - OLx, j)] = 0.;
@@ -157,6 +242,28 @@ static void adv_r(const og_grid *g, const og_params *p, int bi, int bj, int k, i
                   double *wT) {
   SETUP
   const int km2 = k - 2 > 1 ? k - 2 : 1, km1 = k - 1 > 1 ? k - 1 : 1, kp1 = k + 1 < Nr ? k + 1 : Nr;
+  if (scheme == OS7MP) {   /* gad_os7mp_adv_r.F:96-210 */
+    const int km4 = k - 4 > 1 ? k - 4 : 1, km3 = k - 3 > 1 ? k - 3 : 1, kp2 = k + 2 < Nr ? k + 2 : Nr,
+              kp3 = k + 3 < Nr ? k + 3 : Nr;
+    FORALL {
+      const double rT = rTrans[S(i, j)];
+      if (rT == 0.) { wT[S(i, j)] = 0.; continue; }
+      const double cfl = fabs(wFld[S(i, j)] * dTarg * g->recip_drC[k - 1]);
+#define QK(kk) K3(tr, i, j, kk)
+#define MK(kk, f) (G3(g->maskC, i, j, kk) * (double)(f))
+      if (rT < 0.)
+        wT[S(i, j)] = os7mp_core(rT, cfl, QK(kp2), QK(kp1), QK(k), QK(km1), QK(km2), QK(km3), QK(km4),
+                                 MK(kp2, kp2 - kp1), MK(kp1, kp1 - k), MK(k, k - km1), MK(km1, km1 - km2),
+                                 MK(km2, km2 - km3), MK(km3, km3 - km4));
+      else
+        wT[S(i, j)] = os7mp_core(rT, cfl, QK(km3), QK(km2), QK(km1), QK(k), QK(kp1), QK(kp2), QK(kp3),
+                                 MK(km2, km2 - km3), MK(km1, km1 - km2), MK(k, k - km1), MK(kp1, kp1 - k),
+                                 MK(kp2, kp2 - kp1), MK(kp3, kp3 - kp2));
+#undef QK
+#undef MK
+    }
+    return;
+  }
   const int zeroTop = (k == 1 || k > Nr);
   if ((scheme == CENTERED_2ND || scheme == UPWIND_1RST || scheme == DST2 || scheme == UPWIND_3RD ||
        scheme == CENTERED_4TH) && zeroTop) {

@@ -119,3 +119,46 @@ def test_oracle_cg2d_on_the_cube_converges_to_the_configs_tolerance():
         assert 30 <= r["numIters"] <= 200
     finally:
         hook.close()
+
+
+@pytest.mark.parametrize("nf,sx,sy,OL", [(8, 4, 4, 2), (32, 32, 16, 4), (6, 6, 6, 3), (16, 8, 4, 2)])
+@pytest.mark.parametrize("withSigns", [True, False])
+def test_compiled_vector_gather_equals_exch2_uv_3d(nf, sx, sy, OL, withSigns):
+    """The library's one-gather form of EXCH_UV_XY(Z) (mitgcm_b200_exch2_uv_map_, host code) against the
+    literal restatement of EXCH2_UV_3D_RX: two buffered EXCH2_RX2_CUBE passes with the C-grid offsets of
+    EXCH2_GET_UV_BOUNDS, u/v swap and sign across rotated edges, cube-corner fix-ups.  Bit for bit."""
+    from mitgcm_b200.exch2 import exchange_uv
+    T = cubed_sphere_topology(nf, sx, sy)
+    rng = np.random.default_rng(1)
+    u = rng.standard_normal((T.nTiles, 2, sy + 2 * OL, sx + 2 * OL))
+    v = rng.standard_normal(u.shape)
+    u2, v2 = u.copy(), v.copy()
+    eo.exch2_uv_3d(T, u, v, OL, withSigns)
+    exchange_uv(T, u2, v2, OL, withSigns)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2)
+
+
+def test_cs32_vector_exchange_keeps_a_streamfunction_flow_nondivergent():
+    """Pins the vector exchange (swap + sign conventions) on the reference's grid files: volume transports
+    derived from a corner streamfunction psi = sin(lat) are set on the interior faces only; after
+    EXCH_UV_XYZ(withSigns) the east-halo u-transport and north-halo v-transport of every tile must equal the
+    values computed directly from that facet's own corner row/column (index sN+1 of the files), i.e. the
+    first ring of cells stays exactly non-divergent across all 12 cube edges."""
+    from mitgcm_b200.exch2 import exchange_uv
+    T, g, _ = load_cs32()
+    o, sx, sy = 4, 32, 16
+    psi = np.sin(np.deg2rad(g.yG[0]))                       # (tile, PY, PX), valid on 1..sN+1
+    uT = np.zeros_like(psi)
+    vT = np.zeros_like(psi)
+    uT[:, o:o + sy, o:o + sx + 1] = -(psi[:, o + 1:o + sy + 1, o:o + sx + 1] - psi[:, o:o + sy, o:o + sx + 1])
+    vT[:, o:o + sy + 1, o:o + sx] = psi[:, o:o + sy + 1, o + 1:o + sx + 1] - psi[:, o:o + sy + 1, o:o + sx]
+    uE, vN = uT[:, o:o + sy, o + sx].copy(), vT[:, o + sy, o:o + sx].copy()    # direct values on index sN+1
+    uT[:, :, o + sx:] = 0.0                                 # keep the interior only
+    vT[:, o + sy:, :] = 0.0
+    exchange_uv(T, uT, vT, o, True)
+    scale = np.abs(uE).max()
+    assert np.abs(uT[:, o:o + sy, o + sx] - uE).max() < 1e-12 * scale
+    assert np.abs(vT[:, o + sy, o:o + sx] - vN).max() < 1e-12 * scale
+    div = (uT[:, o:o + sy, o + 1:o + sx + 1] - uT[:, o:o + sy, o:o + sx]) + \
+          (vT[:, o + 1:o + sy + 1, o:o + sx] - vT[:, o:o + sy, o:o + sx])
+    assert np.abs(div).max() < 1e-12 * scale

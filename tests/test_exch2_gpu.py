@@ -115,3 +115,35 @@ def test_cg2d_config3_real_bathymetry_operator(rt):
     assert rg["firstResidual"] == pytest.approx(ro["firstResidual"], rel=1e-12)
     sc = np.abs(xo[:, :, jj, ii]).max()
     assert np.abs(xg[:, :, jj, ii] - xo[:, :, jj, ii]).max() <= 1e-9 * sc
+
+
+@pytest.mark.parametrize("withSigns", [True, False])
+@pytest.mark.parametrize("nf,sx,sy,OL,Nr", [(32, 32, 16, 4, 3), (8, 4, 4, 2, 2), (6, 6, 6, 3, 1)])
+def test_device_vector_exchange_is_bit_identical_to_exch2_uv_3d(rt, nf, sx, sy, OL, Nr, withSigns):
+    """EXCH_UV_XYZ_RL on device mirrors (one gather launch for both components) against the literal
+    restatement of EXCH2_UV_3D_RX (two EXCH2_RX2_CUBE passes + cube-corner fix-ups)."""
+    T = cubed_sphere_topology(nf, sx, sy)
+    d = Dims(sNx=sx, sNy=sy, OLx=OL, OLy=OL, nSx=T.nTiles, nSy=1, Nr=Nr)
+    rt.init(d)
+    set_topology(T)
+    rng = np.random.default_rng(11)
+    u, v = rng.standard_normal(d.shape3), rng.standard_normal(d.shape3)
+    rt.set_field("uVel", u)
+    rt.set_field("vVel", v)
+    rt.exch_uv("uVel", "vVel", withSigns)
+    gu, gv = rt.get_field("uVel", np.zeros(d.shape3)), rt.get_field("vVel", np.zeros(d.shape3))
+    eo.exch2_uv_3d(T, u[0], v[0], OL, withSigns)
+    assert np.array_equal(gu, u) and np.array_equal(gv, v)
+
+
+def test_vector_exchange_on_the_periodic_tiling_is_two_scalar_exchanges(rt):
+    from mitgcm_b200.grid import exch_xyz
+    d = Dims(sNx=12, sNy=8, OLx=3, OLy=3, nSx=2, nSy=2, Nr=2)
+    rt.init(d)
+    rng = np.random.default_rng(2)
+    u, v = rng.standard_normal(d.shape3), rng.standard_normal(d.shape3)
+    rt.set_field("uVel", u)
+    rt.set_field("vVel", v)
+    rt.exch_uv("uVel", "vVel", True)
+    assert np.array_equal(rt.get_field("uVel", np.zeros(d.shape3)), exch_xyz(d, u))
+    assert np.array_equal(rt.get_field("vVel", np.zeros(d.shape3)), exch_xyz(d, v))

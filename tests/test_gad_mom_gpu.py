@@ -46,6 +46,8 @@ GAD_CASES = [
     dict(scheme=33, diffKh=1e2, diffK4=0.0, ab=False),
     dict(scheme=77, diffKh=1e2, diffK4=0.0, ab=False, kr4=True),
     dict(scheme=2, diffKh=1e3, diffK4=0.0, ab=False, implDiff=True, implAdv=True),
+    dict(scheme=7, diffKh=1e2, diffK4=0.0, ab=False),
+    dict(scheme=7, diffKh=0.0, diffK4=0.0, ab=True),
 ]
 
 
@@ -102,8 +104,8 @@ def test_gad_rejects_unsupported_options(rt):
     base = [1, 1, 1, 8, 1, 8, 1, 1, 1, 2, z, z, z, z, z, z, z, z, z, z, 0.0, 0.0, z, np.zeros(2), z3, z3, np.ones(2), 1]
     with pytest.raises(rt.B200Error):      # GM/Redi
         rt.gad_calc_rhs(*base, 2, 2, 1, 0, 0, 0, 1, 0, 0, z.copy(), z.copy(), np.zeros((2, d.PY, d.PX)), z3.copy())
-    with pytest.raises(rt.B200Error):      # OS7MP not on the path
-        rt.gad_calc_rhs(*base, 7, 7, 1, 0, 0, 0, 0, 0, 0, z.copy(), z.copy(), np.zeros((2, d.PY, d.PX)), z3.copy())
+    with pytest.raises(rt.B200Error):      # not an advection scheme of GAD.h
+        rt.gad_calc_rhs(*base, 99, 99, 1, 0, 0, 0, 0, 0, 0, z.copy(), z.copy(), np.zeros((2, d.PY, d.PX)), z3.copy())
 
 
 MOM_CASES = [
