@@ -11,9 +11,13 @@
 //   exch_kernel   : EXCH_XYZ_RL with corners on one periodic process (exch1_rx.template:170-201)
 // Assumptions of this driver (checked): linear free surface, implicSurfPress = implicDiv2DFlow = 1,
 // no CD scheme, z coordinates, buoyancy decoupled (dPhiHyd = 0), surface stress forcing only.
+#include <cstdio>
 #include <cstdlib>
 #include "step_fast.cuh"
 #include "phys.cuh"
+
+#define MG_DO_PRAGMA(x) _Pragma(#x)
+#define UNROLL_N(n) MG_DO_PRAGMA(unroll n)
 
 namespace mg {
 
@@ -183,13 +187,22 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
 }
 
 // ---- surface pressure right-hand side -----------------------------------------------------------
-__global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+// Tuned on B200 at 2048x2048x50 (build variants, scripts/phase_times.sh): 16 CTAs/SM (32 registers,
+// full occupancy) and 10 levels of loads in flight: 2.20 -> 1.71 ms.  The kernel is latency-bound
+// (long-scoreboard stalls), so resident warps matter more than registers.
+#ifndef RHS_MINB
+#define RHS_MINB 16
+#endif
+#ifndef RHS_UNROLL
+#define RHS_UNROLL 10
+#endif
+__global__ void __launch_bounds__(128, RHS_MINB) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
                                                   const double *__restrict__ etaN, const double *__restrict__ etaFS,
                                                   const double *__restrict__ Bo_surf,
                                                   double *__restrict__ cg2d_b, double *__restrict__ cg2d_x,
                                                   double deltaTMom, double deltaTFreeSurf, double freeSurfFac) {
-  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
-  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  const int i = 1 - g.OLx + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
   const size_t s = g.s(i, j);
   cg2d_x[s] = Bo_surf[s] * etaN[s];                       // solve_for_pressure.F:129 (full halo range)
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(128) rhs_kernel(TileGrid g, const double *__re
     const int PX = g.PX;
     const double dyG0 = g.dyG[s], dyG1 = g.dyG[s + 1], dxG0 = g.dxG[s], dxG1 = g.dxG[s + PX];
     const double *__restrict__ hW = g.hFacW, *__restrict__ hS = g.hFacS;
-#pragma unroll 5
+UNROLL_N(RHS_UNROLL)
     for (int k = g.Nr; k >= 1; k--) {
       const size_t q = s + slab * (size_t)(k - 1);
       const double drFk = g.drF[k - 1];
@@ -221,19 +234,26 @@ __global__ void eta_kernel(size_t n, const double *recip_Bo, const double *x, do
 }
 
 // ---- correction step + continuity ---------------------------------------------------------------
-__global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+// 8 CTAs/SM (64 registers): 4.05 -> 3.22 ms; more CTAs spill, fewer leave too few loads in flight.
+#ifndef CORR_MINB
+#define CORR_MINB 8
+#endif
+#ifndef CORR_UNROLL
+#define CORR_UNROLL 5
+#endif
+__global__ void __launch_bounds__(128, CORR_MINB) corr_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
                                                    const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
                                                    double *__restrict__ uVel, double *__restrict__ vVel, double *__restrict__ wVel,
                                                    double deltaTMom, double implicSurfPress, int rigidLid) {
-  const int i = 1 + blockIdx.x * 32 + threadIdx.x;
-  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > g.sNx || j > g.sNy) return;
   const double psFac = 1. * implicSurfPress;
   auto phiX = [&](int ii) { return g.recip_dxC[g.s(ii, j)] * (Bo_surf[g.s(ii, j)] * etaN[g.s(ii, j)] - Bo_surf[g.s(ii - 1, j)] * etaN[g.s(ii - 1, j)]); };
   auto phiY = [&](int jj) { return g.recip_dyC[g.s(i, jj)] * (Bo_surf[g.s(i, jj)] * etaN[g.s(i, jj)] - Bo_surf[g.s(i, jj - 1)] * etaN[g.s(i, jj - 1)]); };
   const double px0 = phiX(i), px1 = phiX(i + 1), py0 = phiY(j), py1 = phiY(j + 1);
   double wKp1 = 0.;
-#pragma unroll 5
+UNROLL_N(CORR_UNROLL)
   for (int k = g.Nr; k >= 1; k--) {
     auto uNew = [&](int ii, double px) {
       size_t q = g.s3(ii, j, k);
@@ -267,6 +287,20 @@ __global__ void __launch_bounds__(128) corr_kernel(TileGrid g, const double *__r
     wVel[s3] = wv;
     wKp1 = wv;
   }
+}
+
+// Thread-block shape of the column-marching kernels (rhs, corr): x extent = contiguous bytes per level
+// and array a block touches.  MITGCM_B200_COLBLK="bx,by" overrides (tuning aid).
+static dim3 col_block() {
+  static dim3 b(0, 0);
+  if (b.x == 0) {
+    b = dim3(32, 4);
+    if (const char *e = getenv("MITGCM_B200_COLBLK")) {
+      int x = 0, y = 0;
+      if (sscanf(e, "%d,%d", &x, &y) == 2 && x >= 32 && x % 32 == 0 && y >= 1 && x * y <= 128) b = dim3(x, y);
+    }
+  }
+  return b;
 }
 
 // part 0: THERMODYNAMICS, DYNAMICS, SOLVE_FOR_PRESSURE up to and including CG2D
@@ -411,7 +445,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   mark(2);
   // SOLVE_FOR_PRESSURE
   {
-    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
+    const dim3 cb = col_block();
+    dim3 grd((g.PX + cb.x - 1) / cb.x, (g.PY + cb.y - 1) / cb.y);
     for (int bj = 1; bj <= g.nSy; bj++)
       for (int bi = 1; bi <= g.nSx; bi++) {
         TileGrid tg;
@@ -419,7 +454,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
-        rhs_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
+        rhs_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
                                               q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC));
       }
     MG_CUDA(cudaGetLastError());
@@ -440,7 +475,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   mark(5);
   // MOMENTUM_CORRECTION_STEP + INTEGR_CONTINUITY
   {
-    dim3 grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
+    const dim3 cb = col_block();
+    dim3 grd((g.sNx + cb.x - 1) / cb.x, (g.sNy + cb.y - 1) / cb.y);
     for (int bj = 1; bj <= g.nSy; bj++)
       for (int bi = 1; bi <= g.nSx; bi++) {
         TileGrid tg;
@@ -448,7 +484,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
-        corr_kernel<<<grd, blk, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
+        corr_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
                                                q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS), q.I(MI_RIGIDLID));
       }
     MG_CUDA(cudaGetLastError());

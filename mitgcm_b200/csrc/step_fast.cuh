@@ -266,7 +266,10 @@ __device__ __forceinline__ void dyn_pipe_prefetch(DynPipeSmem &sm, int slot, int
   }
 }
 
-__global__ void __launch_bounds__(FT_X *FT_Y, 2)
+#ifndef DYNP_MINB
+#define DYNP_MINB 2
+#endif
+__global__ void __launch_bounds__(FT_X *FT_Y, DYNP_MINB)
     dyn_pipe_kernel(TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU, const double *__restrict__ sfV,
                     double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
                     double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB) {
@@ -503,7 +506,10 @@ struct ThermoSmem {
 };
 
 // TEMP_INTEGRATE for centred 2nd-order advection + Laplacian diffusion, k = Nr..1 (see thermo_kernel).
-__global__ void __launch_bounds__(FT_X *FT_Y, 3)
+#ifndef THF_MINB
+#define THF_MINB 3
+#endif
+__global__ void __launch_bounds__(FT_X *FT_Y, THF_MINB)
     thermo_fast_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
                        const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
                        double *__restrict__ gtNm1, GadPar p, double abFac, const double *__restrict__ sfT) {
