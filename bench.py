@@ -2,7 +2,8 @@
 """bench.py -- headline benchmark of the B200-native MITgcm hot path.
 
 Workload (BASELINE.json configs[4]): synthetic doubly-periodic channel, 2048 x 2048 x 50 cells PER
-GPU (weak scaling), FP64, flat bottom, wind-driven, c2 advection of theta, harmonic viscosity,
+GPU (weak scaling), FP64, flat bottom, wind-driven, c2 advection of theta, linear equation of state
+(theta feeds back on the flow through the hydrostatic pressure gradient), harmonic viscosity,
 implicit free surface solved by CG2D to 1e-7 every step.  A "step" is one FORWARD_STEP on the
 resident state: THERMODYNAMICS (GAD_CALC_RHS) + DYNAMICS (MOM_FLUXFORM) + SOLVE_FOR_PRESSURE (CG2D)
 + correction/continuity + halo exchanges (mitgcm_b200_forward_step_).
@@ -33,8 +34,9 @@ sys.path.insert(0, ROOT)
 
 CG2D_BYTES_PER_POINT_ITER = 136.0     # 17 words, the minimum of the three-sync CG2D structure
                                       # (this implementation moves 14-16 words: DESIGN.md section 5)
-DYN_BYTES_PER_CELL = 152.0            # 19 words (MOM_FLUXFORM + TIMESTEP fused)
-THERMO_BYTES_PER_CELL = 96.0          # 12 words (GAD_CALC_RHS + AB2 + TIMESTEP_TRACER fused)
+DYN_BYTES_PER_CELL = 160.0            # 20 words (MOM_FLUXFORM + TIMESTEP fused: 19, + phiHyd of CALC_GRAD_PHI_HYD)
+THERMO_BYTES_PER_CELL = 112.0         # thermo phase: 12 words (GAD_CALC_RHS + AB2 + TIMESTEP_TRACER fused) + 2 words
+                                      # (phihyd_kernel: R theta, W phiHyd; linear EOS evaluated on the fly)
 
 
 def measured_peak():
@@ -83,7 +85,9 @@ def params(nr):
     from mitgcm_b200.model import DEFAULTS
     P = dict(DEFAULTS)
     P.update(deltaTMom=1200.0, deltaTFreeSurf=1200.0, deltaTtracer=1200.0, cg2dMaxIters=1000,
-             cg2dTargetResidual=1e-7, viscAhD=400.0, viscAhZ=400.0, viscAr=1e-2, diffKhT=1e3, diffKrT=1e-5)
+             cg2dTargetResidual=1e-7, viscAhD=400.0, viscAhZ=400.0, viscAr=1e-2, diffKhT=1e3, diffKrT=1e-5,
+             # eosType = 'LINEAR' (SURVEY.md section 8(d)): theta drives the flow through CALC_PHI_HYD
+             buoyancyLinear=1, gravity=9.81, tAlpha=2e-4, sBeta=0.0, rhoNil=1000.0, rhoConst=1000.0)
     return P
 
 
@@ -152,6 +156,12 @@ def run_cuda(args, rank, world):
     rt.fill_field("kappaRU", P["viscAr"])
     rt.fill_field("kappaRV", P["viscAr"])
     rt.fill_field("kappaRT", P["diffKrT"])
+    # linear equation of state: reference profile and the vertical grid CALC_PHI_HYD integrates over
+    vert = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(NR + 1 - len(a))])
+    rt.set_field("tRef", vert(np.linspace(20.0, 2.0, NR)))
+    rt.set_field("sRef", vert(np.zeros(NR)))
+    rt.set_field("rF", vert(g.a["rF"]))
+    rt.set_field("rC", vert(g.a["rC"]))
     tau = (-0.1 * torch.cos(two_pi * YY) * (1.0 / 1000.0)).contiguous()
     sfU_host = tau.cpu().pin_memory()
     sfV_host = torch.zeros_like(sfU_host).pin_memory()

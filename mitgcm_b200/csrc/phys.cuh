@@ -115,13 +115,20 @@ impldiff_kernel(TileGrid g, const double *__restrict__ kapT, double *__restrict_
 }
 
 // phiHydC for every level; range = the whole slab (the gradient needs (i-1,j) and (i,j-1)).
-__global__ void __launch_bounds__(128)
-phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restrict__ rF, const double *__restrict__ rC,
+// rho == nullptr: the in-situ density anomaly is evaluated on the fly from theta (and salt when
+// sBeta != 0) with FIND_RHO_2D 'LINEAR' -- same expression as ocean_phys_kernel, so nothing but
+// theta is read when no other consumer of rhoInSitu (IVDC) is active: R{theta} W{phiHyd}.
+__global__ void __launch_bounds__(128, 8)
+phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restrict__ theta,
+              const double *__restrict__ salt, const double *__restrict__ tRef, const double *__restrict__ sRef,
+              EosLinear e, const double *__restrict__ rF, const double *__restrict__ rC,
               double gravity, double recip_rhoConst, double *__restrict__ phiHyd) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const double dRho = e.rhoNil - e.rhoConst;
   double phiF = 0.;
+#pragma unroll 5
   for (int k = 1; k <= g.Nr; k++) {
     const size_t s3 = g.s3(i, j, k);
     double dRlocM = 0.5 * g.drC[k - 1] * 1.;
@@ -129,7 +136,12 @@ phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restri
     double dRlocP;
     if (k == g.Nr) dRlocP = (rC[k - 1] - rF[k]) * 1.;
     else dRlocP = 0.5 * g.drC[k] * 1.;
-    const double a = rho[s3];
+    double a;
+    if (rho) a = rho[s3];
+    else {
+      const double sTerm = e.sBeta != 0. ? e.sBeta * (salt[s3] - sRef[k - 1]) : 0.;
+      a = e.rhoNil * (sTerm - e.tAlpha * (theta[s3] - tRef[k - 1])) + dRho;
+    }
     const double phiC = phiF + dRlocM * gravity * a * recip_rhoConst;
     phiF = phiC + dRlocP * gravity * a * recip_rhoConst;
     phiHyd[s3] = phiC;

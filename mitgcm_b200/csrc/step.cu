@@ -328,11 +328,14 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   // optional physics of the wider configurations (see include/mitgcm_b200.h, forward step)
   const bool buoy = q.I(MI_BUOYANCYLINEAR) != 0, relaxT = q.I(MI_DOTHETACLIMRELAX) != 0;
   const bool exactConserv = q.I(MI_EXACTCONSERV) != 0, implDiff = q.I(MI_IMPLICITDIFFUSION) != 0;
-  if ((buoy || relaxT || exactConserv) && g.nPx * g.nPy > 1)
-    return fail(61, "forward_step: buoyancy / relaxation / exactConserv are single-rank for now");
+  // buoyancy and relaxation work on the halo'd slab of each rank (theta halos are exchanged every step);
+  // the exactConserv update needs the u, v halo exchange in the middle of the continuity step
+  if (exactConserv && g.nPx * g.nPy > 1) return fail(61, "forward_step: exactConserv is single-rank for now");
   if (g.Nr > PHYS_NRMAX && implDiff) return fail(61, "forward_step: implicit diffusion supports Nr <= 64");
   double *rho = nullptr, *phiHyd = nullptr, *sfT = nullptr, *etaH = nullptr;
-  if (buoy && (!(rho = field(MG_RHOINSITU)) || !(phiHyd = field(MG_PHIHYD)))) return false;
+  const bool ivdc = q.D(MP_IVDC_KAPPA) != 0.;
+  if (buoy && !(phiHyd = field(MG_PHIHYD))) return false;
+  if (buoy && ivdc && !(rho = field(MG_RHOINSITU))) return false;
   if (relaxT && !(sfT = field(MG_SURFFORCT))) return false;
   if (exactConserv && !(etaH = field(MG_ETAH))) return false;
   const bool prof = q.I(MI_PROFILE) != 0;
@@ -344,10 +347,10 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   if (part == 0) {
   mark(0);
   // DO_OCEANIC_PHYS: surface relaxation forcing, in-situ density, convective flag -> kappaRT
-  if (buoy || relaxT) {
+  if (relaxT || (buoy && ivdc)) {
     double *th = field(MG_THETA), *sa = field(MG_SALT), *sst = field(MG_SST), *lam = field(MG_LAMBDATHETACLIMRELAX);
     double *tRef = field(MG_TREF), *sRef = field(MG_SREF), *kapT = field(MG_KAPPART), *sf = field(MG_SURFFORCT);
-    double *rh = field(MG_RHOINSITU);
+    double *rh = (buoy && ivdc) ? field(MG_RHOINSITU) : th;     // written only when the density is needed
     if (!th || !sa || !sst || !lam || !tRef || !sRef || !kapT || !sf || !rh) return false;
     EosLinear e{q.D(MP_RHONIL), q.D(MP_RHOCONST), q.D(MP_TALPHA), q.D(MP_SBETA)};
     dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
@@ -359,8 +362,28 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
         ocean_phys_kernel<<<grd, blk, 0, c.stream>>>(tg, th + o3, sa + o3, sst + o2, lam + o2, tRef, sRef, e, q.D(MP_RKSIGN),
-                                                     q.D(MP_IVDC_KAPPA), q.D(MP_DIFFKRT), relaxT ? 1 : 0, buoy ? 1 : 0,
+                                                     q.D(MP_IVDC_KAPPA), q.D(MP_DIFFKRT), relaxT ? 1 : 0, (buoy && ivdc) ? 1 : 0,
                                                      sf + o2, rh + o3, kapT + o3);
+      }
+    MG_CUDA(cudaGetLastError());
+  }
+  // CALC_PHI_HYD for all levels (dynamics.F:436-441 marches it level by level inside DYNAMICS; it only
+  // depends on the density of DO_OCEANIC_PHYS, i.e. on theta BEFORE the thermodynamics step, so it runs here).
+  // Without IVDC nobody else needs rhoInSitu and the EOS is evaluated on the fly.
+  if (buoy) {
+    double *rF = field(MG_RF), *rC = field(MG_RC), *th = field(MG_THETA), *sa = field(MG_SALT);
+    double *tRef = field(MG_TREF), *sRef = field(MG_SREF);
+    if (!rF || !rC || !th || !sa || !tRef || !sRef) return false;
+    EosLinear e{q.D(MP_RHONIL), q.D(MP_RHOCONST), q.D(MP_TALPHA), q.D(MP_SBETA)};
+    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
+    for (int bj = 1; bj <= g.nSy; bj++)
+      for (int bi = 1; bi <= g.nSx; bi++) {
+        TileGrid tg;
+        if (!make_tile_grid(bi, bj, tg)) return false;
+        size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
+        c.launches++;
+        phihyd_kernel<<<grd, blk, 0, c.stream>>>(tg, ivdc ? rho + o3 : nullptr, th + o3, sa + o3, tRef, sRef, e, rF, rC,
+                                                 q.D(MP_GRAVITY), 1.0 / q.D(MP_RHOCONST), phiHyd + o3);
       }
     MG_CUDA(cudaGetLastError());
   }
@@ -398,20 +421,6 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   }
   mark(1);
   // DYNAMICS
-  if (buoy) {     // CALC_PHI_HYD for all levels (dynamics.F:436-441 marches it level by level)
-    double *rF = field(MG_RF), *rC = field(MG_RC);
-    if (!rF || !rC) return false;
-    dim3 grd((g.PX + 31) / 32, (g.PY + 3) / 4);
-    for (int bj = 1; bj <= g.nSy; bj++)
-      for (int bi = 1; bi <= g.nSx; bi++) {
-        TileGrid tg;
-        if (!make_tile_grid(bi, bj, tg)) return false;
-        size_t o3 = ns * g.Nr * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1));
-        c.launches++;
-        phihyd_kernel<<<grd, blk, 0, c.stream>>>(tg, rho + o3, rF, rC, q.D(MP_GRAVITY), 1.0 / q.D(MP_RHOCONST), phiHyd + o3);
-      }
-    MG_CUDA(cudaGetLastError());
-  }
   {
     dim3 grd((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 3) / 4);
     for (int bj = 1; bj <= g.nSy; bj++)
@@ -422,7 +431,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        if (!buoy && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
+        if (dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
           static bool attr = false;
           if (!attr) {
             cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
@@ -430,7 +439,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
           }
           dyn_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(DynPipeSmem),
                             c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
-                                        abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
+                                        abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr);
         } else if (!buoy && dyn_fast_ok(g, mp))
           dyn_fast_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,

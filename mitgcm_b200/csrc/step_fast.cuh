@@ -272,7 +272,8 @@ __device__ __forceinline__ void dyn_pipe_prefetch(DynPipeSmem &sm, int slot, int
 __global__ void __launch_bounds__(FT_X *FT_Y, DYNP_MINB)
     dyn_pipe_kernel(TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU, const double *__restrict__ sfV,
                     double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
-                    double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB) {
+                    double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB,
+                    const double *__restrict__ phiHyd) {
   extern __shared__ __align__(16) unsigned char dyn_pipe_smem[];
   DynPipeSmem &sm = *reinterpret_cast<DynPipeSmem *>(dyn_pipe_smem);
   __shared__ VertSmem vs;
@@ -317,6 +318,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNP_MINB)
   const double fC00 = g.fCori[s], fCm0 = g.fCori[s - 1], fC0m = g.fCori[s - PX];
   const double sfu = sfU[s], sfv = sfV[s];
   const double uDudxFac = p.afFacMom, AhFac = p.vfFacMom, ArFac = p.implicitViscosity ? 0. : p.vfFacMom;
+  // CALC_GRAD_PHI_HYD (calc_grad_phi_hyd.F:150-165) is defined on i >= iMin+1, j >= jMin+1
+  const double gpx = (phiHyd && i >= 1) ? g.recip_dxC[s] : 0., gpy = (phiHyd && j >= 1) ? g.recip_dyC[s] : 0.;
 
   // own-column values carried between levels
   const size_t slab = g.slab;
@@ -354,6 +357,12 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNP_MINB)
     if (below) { uKp1 = st.u[s3 + slab]; vKp1 = st.v[s3 + slab]; mWkp1 = g.maskW[s3 + slab]; mSkp1 = g.maskS[s3 + slab]; }
     const double rhW = g.recip_hFacW[s3], rhS = g.recip_hFacS[s3];
     const double guOld = guNm1[s3], gvOld = gvNm1[s3];
+    double dpx = 0., dpy = 0.;
+    if (phiHyd) {
+      const double ph = phiHyd[s3];
+      dpx = gpx * 1. * (ph - phiHyd[s3 - 1]) * 1.;
+      dpy = gpy * 1. * (ph - phiHyd[s3 - PX]) * 1.;
+    }
     // ---- level k has been prefetched into ring slot rb (cp.async); derive what the fluxes share ----
     __pipeline_wait_prior(0);
     __syncthreads();
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNP_MINB)
       }
       gu = gu * mWk; guD = guD * mWk; gv = gv * mSk; gvD = gvD * mSk;   // mom_fluxform.F:1044-1051
       // ---- TIMESTEP (timestep.F:95-385), as in dyn_kernel ----
-      gu = gu - 0.; gv = gv - 0.;
+      gu = gu - 1. * dpx; gv = gv - 1. * dpy;      // timestep.F:120-121, phFac = pfFacMom = 1
       if (p.momViscosity && dissInAB) { gu = gu + guD; gv = gv + gvD; }
       if (momForcing) {
         double ge = 0., he = 0.;

@@ -13,7 +13,9 @@ DEFAULTS = dict(deltaTMom=1200.0, deltaTFreeSurf=1200.0, deltaTtracer=1200.0, ab
                 viscAhD=400.0, viscAhZ=400.0, viscAr=1e-2, diffKhT=1e3, diffK4T=0.0, diffKrT=1e-5,
                 no_slip_sides=1, no_slip_bottom=1, sideDragFactor=2.0, selectBotDragQuadr=-1,
                 tempAdvScheme=2, tempStepping=1, cg2dTargetResidual=1e-7, cg2dMaxIters=1000,
-                momForcing=1, momDissip_In_AB=1, useSRCGSolver=0)
+                momForcing=1, momDissip_In_AB=1, useSRCGSolver=0,
+                # eosType = 'LINEAR' (SURVEY.md section 8(d)); coupled to the momentum equations when buoyancyLinear = 1
+                buoyancyLinear=0, gravity=9.81, tAlpha=2e-4, sBeta=0.0, rhoNil=1000.0, rhoConst=1000.0, ivdc_kappa=0.0)
 
 LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z sideDragFactor bottomDragLinear "
               "bottomDragQuadratic no_slip_sides no_slip_bottom bottomVisc_pCell selectBotDragQuadr "
@@ -58,6 +60,8 @@ def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
     s["etaN"] = tile(eta) * g.maskC[:, :, 0]
     s["surfForcU"] = tile(tau) * (1.0 / rhoConst)
     s["surfForcV"] = np.zeros(d.shape2)
+    s["tRef"] = np.linspace(20.0, 2.0, Nr)       # reference profile of the linear equation of state
+    s["sRef"] = np.zeros(Nr)
     return s
 
 

@@ -23,7 +23,8 @@ class ChannelOracle:
         self.g, self.d = grid, grid.d
         self.P = dict(abEps=0.01, deltaTtracer=params.get("deltaTMom", 1200.0), diffKhT=0.0, diffK4T=0.0,
                       diffKrT=0.0, viscAr=0.0, tempAdvScheme=2, tempStepping=1, cg2dMaxIters=150,
-                      momForcing=1, momDissip_In_AB=1, useSRCGSolver=0)
+                      momForcing=1, momDissip_In_AB=1, useSRCGSolver=0, buoyancyLinear=0, gravity=9.81,
+                      tAlpha=2e-4, sBeta=0.0, rhoNil=999.8, rhoConst=999.8, ivdc_kappa=0.0)
         extra = {k: params[k] for k in list(params) if k in self.P}
         self.P.update(extra)
         self.o = Oracle(grid, {k: v for k, v in params.items() if k not in self.P})
@@ -36,6 +37,16 @@ class ChannelOracle:
         self.kapT = np.full((d.PY, d.PX), float(self.P["diffKrT"]))
         self.threads = threads
         self.it = 0
+        # coupled buoyancy (eosType = 'LINEAR'): FIND_RHO_2D before the thermodynamics, CALC_PHI_HYD in DYNAMICS
+        if self.P["buoyancyLinear"]:
+            from .pyoracle import Eos
+            self.eos = Eos(self.P["rhoNil"], self.P["rhoConst"], self.P["tAlpha"], self.P["sBeta"])
+            self.tRef = np.ascontiguousarray(self.s.pop("tRef"), dtype=np.float64)
+            self.sRef = np.ascontiguousarray(self.s.pop("sRef", np.zeros(d.Nr)), dtype=np.float64)
+            if "salt" not in self.s:
+                self.s["salt"] = np.zeros(d.shape3)
+            self.rho, self.ivdc = np.zeros(d.shape3), np.zeros(d.shape3)
+            self.phi0 = np.zeros(d.shape2)
 
     def _tiles(self):
         return [(bi, bj) for bj in range(1, self.d.nSy + 1) for bi in range(1, self.d.nSx + 1)]
@@ -63,13 +74,17 @@ class ChannelOracle:
             rTrans = np.zeros(ns)
             sl = {n: np.zeros(ns) for n in "xA yA maskUp uFld vFld wFld uTrans vTrans rTransKp1 fZon fMer".split()}
             theta = np.ascontiguousarray(s["theta"][ti])
+            kapK = None
+            if P["buoyancyLinear"] and P["ivdc_kappa"] != 0.0:     # CALC_3D_DIFFUSIVITY with the convective flag
+                kapK = np.zeros((d.Nr,) + ns)
+                o.calc_3d_diffusivity(bi, bj, self.ivdc, float(P["ivdc_kappa"]), zr, np.full(d.Nr, float(P["diffKrT"])), kapK)
             for k in range(d.Nr, 0, -1):
                 kUp, kDown = 1 + (k + 1) % 2, 1 + k % 2
                 o.calc_adv_flow(bi, bj, k, s["uVel"], s["vVel"], s["wVel"], sl["xA"], sl["yA"], sl["maskUp"],
                                 sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans, sl["rTransKp1"])
                 o.gad_calc_rhs(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, max(1, k - 1), kUp, kDown, sl["xA"], sl["yA"],
                                sl["maskUp"], sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans,
-                               sl["rTransKp1"], P["diffKhT"], P["diffK4T"], self.kapT, zr, theta, theta, dT,
+                               sl["rTransKp1"], P["diffKhT"], P["diffK4T"], self.kapT if kapK is None else kapK[k - 1], zr, theta, theta, dT,
                                P["tempAdvScheme"], P["tempAdvScheme"], 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
                 # ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86)
                 gNm1 = s["gtNm1"][ti][k - 1]
@@ -79,19 +94,30 @@ class ChannelOracle:
             # TIMESTEP_TRACER + CYCLE_TRACER
             s["theta"][ti] = theta + dT[:, None, None] * gT
 
+        buoy = bool(P["buoyancyLinear"])
+
         def dyn(t):
             bi, bj = t
             fU, fVv = np.zeros((2,) + ns), np.zeros((2,) + ns)
             z = np.zeros(ns)
+            zy = z
+            if buoy:
+                phiF, phiC, z, zy = (np.zeros(ns) for _ in range(4))
             for k in range(1, d.Nr + 1):
                 kUp, kDown = 1 + (k + 1) % 2, 1 + k % 2
                 gd, hd = np.zeros(ns), np.zeros(ns)
+                if buoy:
+                    o.calc_phi_hyd(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, self.rho, self.g.rF, self.g.rC,
+                                   P["gravity"], 1.0 / P["rhoConst"], self.phi0, phiF, phiC, z, zy)
                 o.mom_fluxform(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, self.kapU, self.kapU, fU[kUp - 1], fVv[kUp - 1],
                                fU[kDown - 1], fVv[kDown - 1], gd, hd, s["uVel"], s["vVel"], s["wVel"], s["gU"], s["gV"])
-                o.timestep(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, z, z, gd, hd, s["surfForcU"], s["surfForcV"],
+                o.timestep(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, z, zy, gd, hd, s["surfForcU"], s["surfForcV"],
                            P["momForcing"], P["momDissip_In_AB"], abFac, s["uVel"], s["vVel"], s["gU"], s["gV"],
                            s["guNm1"], s["gvNm1"])
 
+        if buoy:      # DO_OCEANIC_PHYS: density of theta(n), before the thermodynamics updates theta
+            self._map(lambda t: o.density_ivdc(self.eos, t[0], t[1], s["theta"], s["salt"], self.tRef, self.sRef,
+                                               self.rho, self.ivdc))
         if P["tempStepping"]:
             self._map(thermo)
         self._map(dyn)

@@ -22,7 +22,13 @@ def rel(a, b):
     dict(sNx=62, sNy=62, Nr=1, land_frac=0.0, tempStepping=0),
     dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, OL=3, tempAdvScheme=33, viscA4D=1e10, viscA4Z=1e10, useBiharmonicVisc=1),
     dict(sNx=32, sNy=32, Nr=5, land_frac=0.0, momDissip_In_AB=0, selectCoriScheme=1, rigidLid=0),
-], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat"])
+    # eosType = 'LINEAR' coupled to the momentum equations (CALC_PHI_HYD): pipelined dyn kernel, on-the-fly EOS
+    dict(sNx=64, sNy=40, Nr=7, land_frac=0.0, buoyancyLinear=1),
+    # same with land / partial cells and 2x2 tiles (generic dyn kernel is not used: fast path handles masks)
+    dict(sNx=24, sNy=16, Nr=4, nSx=2, nSy=2, land_frac=0.2, buoyancyLinear=1),
+    # IVDC on: density array + convective diffusivity feed the (explicit) vertical diffusion
+    dict(sNx=32, sNy=24, Nr=6, land_frac=0.1, buoyancyLinear=1, ivdc_kappa=1.0, selectCoriScheme=1),
+], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat", "buoyancy-flat", "buoyancy-land", "buoyancy-ivdc"])
 def test_forward_step_matches_oracle(cfg):
     g, P, s = make_channel(**cfg)
     co = ChannelOracle(g, P, s)
