@@ -369,10 +369,12 @@ def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=861
     """usingCurvilinearGrid with pkg/exch2: tiles laid out as one row (nSx = nTiles, nSy = 1, the
     reference's own cs32 SIZE.h), metrics from the face files.  Each tile takes its interior plus the
     (sNx+1, sNy+1) row and column the files carry (MDS_FACEF_READ); cell-centred scalars (xC, yC, rA)
-    then get their halos from the scalar exch2 exchange as in ini_curvilinear_grid.F:360-363.  The
-    vector-pair exchanges of the reference (dxC/dyC, rAw/rAs, dxG/dyG: :364-370) are NOT done: beyond
-    index sN+1 those arrays stay zero, which is all the CG2D operator and the KATs need."""
-    from .exch2 import exchange, halo_gather_map
+    then get their halos from the scalar exch2 exchange and the C-grid pairs (dxC, dyC), (rAw, rAs),
+    (dyG, dxG) from the unsigned vector-pair exchange, as in ini_curvilinear_grid.F:360-370.  The A-grid
+    (dxF, dyF), B-grid (dxV, dyU) and corner-point (xG, yG, rAz) exchanges of the reference are NOT done:
+    those arrays are valid on 1..sN+1 only (enough for the hot path without viscosity / advection on the
+    cube; MOM_VECINV, which config 4 would need, is not built)."""
+    from .exch2 import exchange, exchange_uv, halo_gather_map, uv_gather_map
     assert d.nSy == 1 and d.nSx == topo.nTiles and d.OLx == d.OLy
     g = Grid(d)
     for n in GRID2D:
@@ -389,6 +391,10 @@ def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=861
     gm = halo_gather_map(topo, ox)
     for n in ("xC", "yC", "rA"):
         exchange(topo, g.a[n][0], ox, gm)
+    gmuv = uv_gather_map(topo, ox, False)
+    for a, b in (("dxC", "dyC"), ("rAw", "rAs"), ("dyG", "dxG")):
+        if g.a[a].any():
+            exchange_uv(topo, g.a[a][0], g.a[b][0], ox, False, gmuv)
     PI = 3.14159265358979323844
     omega = 2.0 * PI / rotationPeriod
     import math
@@ -429,5 +435,7 @@ def cube_masks_from_depth(g: Grid, topo, depth_xstack: np.ndarray, hFacMin=1.0, 
     hFacS = np.zeros(d.shape3)
     hFacW[..., :, 1:] = np.minimum(hFacC[..., :, 1:], hFacC[..., :, :-1])
     hFacS[..., 1:, :] = np.minimum(hFacC[..., 1:, :], hFacC[..., :-1, :])
+    from .exch2 import exchange_uv
+    exchange_uv(topo, hFacW[0], hFacS[0], ox, False)       # EXCH_UV_XYZ_RS(hFacW, hFacS, .FALSE.), ini_masks_etc.F:402
     g.a["R_low"] = R_low
     set_hfac(g, hFacC, hFacW, hFacS)

@@ -128,15 +128,20 @@ class Model:
         rt.finalize()
 
 
-def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None, exch=None) -> dict:
+def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None, exch=None, exch_uv=None) -> dict:
     """INI_CG2D (model/src/ini_cg2d.F:76-234) vectorised over the horizontal, level loop kept in
     order so the sums are bit-identical to the Fortran.  hfac_flat: use hFacW = hFacS = const
     instead of the 3-D arrays (flat-bottom set-ups whose masks live only on the device).
     This is model set-up (it runs once, or once per step under NLFS), not the hot path.
-    exch(d, a): halo update used for aW/aS and pC/pW/pS (EXCH_UV_XY_RS / EXCH_XY_RS); defaults to
-    the single-process periodic exchange."""
+    exch(d, a): halo update used for pC (EXCH_XY_RS); exch_uv(d, a, b): unsigned vector-pair update used for
+    (aW2d, aS2d) and (pW, pS) (EXCH_UV_XY_RS(.., .FALSE.), ini_cg2d.F:133, 233).  Defaults: the single-process
+    periodic exchange, where a vector-pair exchange is two scalar ones."""
     d = g.d
     exch_xyz = exch or globals()["exch_xyz"]
+    if exch_uv is None:
+        def exch_uv(dd, a, b):
+            exch_xyz(dd, a)
+            exch_xyz(dd, b)
     jj, ii = d.interior()
     I = (slice(None), slice(None), jj, ii)
     aW, aS = np.zeros(d.shape2), np.zeros(d.shape2)
@@ -150,8 +155,7 @@ def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None, exch=None) -> dic
     myNorm = 1.0 / myNorm if myNorm != 0 else 1.0
     aW[I] = aW[I] * myNorm
     aS[I] = aS[I] * myNorm
-    exch_xyz(d, aW)
-    exch_xyz(d, aS)
+    exch_uv(d, aW, aS)
     normalise = P.get("cg2dTargetResWunit", -1.0) <= 0.0
     tol = P.get("cg2dTargetResidual", 1e-7) if normalise else \
         myNorm * P["cg2dTargetResWunit"] * P["globalArea"] / P["deltaTMom"]
@@ -172,56 +176,26 @@ def ini_cg2d(g: Grid, P: dict, hfac_flat: float | None = None, exch=None) -> dic
         pW[I] = np.where(aC[I] + aC[W] == 0.0, 0.0, -aW[I] / (tw * tw))
         ts = off * (aC[S] + aC[I])
         pS[I] = np.where(aC[I] + aC[S] == 0.0, 0.0, -aS[I] / (ts * ts))
-    for a in (pC, pW, pS):
-        exch_xyz(d, a)
+    exch_xyz(d, pC)
+    exch_uv(d, pW, pS)
     return dict(aW2d=aW, aS2d=aS, aC2d=aC, pW=pW, pS=pS, pC=pC, cg2dNorm=myNorm, cg2dTolerance_sq=tol * tol,
                 cg2dNormaliseRHS=normalise)
 
 
 def ini_cg2d_tilegraph(g: Grid, P: dict, topo) -> dict:
-    """INI_CG2D on a pkg/exch2 tile graph (cubed sphere).  Same arithmetic as ini_cg2d above on the
-    interior.  The ring entries CG2D reads (aW2d(sNx+1,j), aS2d(i,sNy+1), pW/pS likewise, aC2d/pC on
-    ring 0 and sN+1) come from the reference's EXCH_UV_XY_RS / EXCH_XY_RS (ini_cg2d.F:133, 231-233);
-    here aW/aS/pW/pS on index sN+1 are computed in place from the metrics the grid files carry for
-    that row/column and aC/pC get their ring from the scalar exch2 exchange.  Same values; at face
-    edges the last bit may differ from the Fortran (the neighbour facet sums its four coefficients in
-    its own orientation)."""
-    from .exch2 import exchange, halo_gather_map
-    d = g.d
-    oy, ox = d.OLy, d.OLx
-    jj, ii = d.interior()
-    I = (slice(None), slice(None), jj, ii)
-    XW = (slice(None), slice(None), jj, slice(ox, ox + d.sNx + 1))             # i = 1..sNx+1, j interior
-    YS = (slice(None), slice(None), slice(oy, oy + d.sNy + 1), ii)             # j = 1..sNy+1, i interior
-    aW, aS = np.zeros(d.shape2), np.zeros(d.shape2)
-    fac = P.get("implicSurfPress", 1.0) * P.get("implicDiv2DFlow", 1.0)
-    for k in range(d.Nr):
-        aW[XW] = aW[XW] + fac * (g.dyG[XW] * g.drF[k] * g.hFacW[:, :, k][XW]) * g.recip_dxC[XW]
-        aS[YS] = aS[YS] + fac * (g.dxG[YS] * g.drF[k] * g.hFacS[:, :, k][YS]) * g.recip_dyC[YS]
-    myNorm = max(np.abs(aW[I]).max(), np.abs(aS[I]).max())
-    myNorm = 1.0 / myNorm if myNorm != 0 else 1.0
-    aW[XW] = aW[XW] * myNorm
-    aS[YS] = aS[YS] * myNorm
-    normalise = P.get("cg2dTargetResWunit", -1.0) <= 0.0
-    tol = P.get("cg2dTargetResidual", 1e-7) if normalise else \
-        myNorm * P["cg2dTargetResWunit"] * P["globalArea"] / P["deltaTMom"]
-    E = (slice(None), slice(None), jj, slice(ox + 1, ox + d.sNx + 1))          # i+1
-    N = (slice(None), slice(None), slice(oy + 1, oy + d.sNy + 1), ii)          # j+1
-    aC = np.zeros(d.shape2)
-    aC[I] = -((((aW[I] + aW[E]) + aS[I]) + aS[N]) +
-              P.get("freeSurfFac", 1.0) * myNorm * g.recip_Bo[I] * g.rA[I] / P["deltaTMom"] / P["deltaTFreeSurf"])
-    gm = halo_gather_map(topo, ox)
-    exchange(topo, aC[0], ox, gm)
-    off = P.get("cg2dpcOffDFac", 0.51)
-    pC, pW, pS = np.zeros(d.shape2), np.zeros(d.shape2), np.zeros(d.shape2)
-    Wm = (slice(None), slice(None), jj, slice(ox - 1, ox + d.sNx))              # i-1 for i = 1..sNx+1
-    Sm = (slice(None), slice(None), slice(oy - 1, oy + d.sNy), ii)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        pC[I] = np.where(aC[I] == 0.0, 1.0, 1.0 / aC[I])
-        tw = off * (aC[Wm] + aC[XW])
-        pW[XW] = np.where(aC[XW] + aC[Wm] == 0.0, 0.0, -aW[XW] / (tw * tw))
-        ts = off * (aC[Sm] + aC[YS])
-        pS[YS] = np.where(aC[YS] + aC[Sm] == 0.0, 0.0, -aS[YS] / (ts * ts))
-    exchange(topo, pC[0], ox, gm)
-    return dict(aW2d=aW, aS2d=aS, aC2d=aC, pW=pW, pS=pS, pC=pC, cg2dNorm=myNorm, cg2dTolerance_sq=tol * tol,
-                cg2dNormaliseRHS=normalise)
+    """INI_CG2D on a pkg/exch2 tile graph (cubed sphere): the same arithmetic as ini_cg2d with the
+    reference's halo updates done on the tile graph -- EXCH_UV_XY_RS(aW2d, aS2d, .FALSE.) and
+    EXCH_UV_XY_RS(pW, pS, .FALSE.) as unsigned vector-pair exchanges (u/v swap across rotated facet
+    edges), EXCH_XY_RS(pC) as a scalar one (ini_cg2d.F:133, 231-233)."""
+    from .exch2 import exchange, exchange_uv, halo_gather_map, uv_gather_map
+    ol = g.d.OLx
+    gm, gmuv = halo_gather_map(topo, ol), uv_gather_map(topo, ol, False)
+    assert g.d.nSy == 1
+
+    def ex(d, a):
+        exchange(topo, a[0], ol, gm)
+        return a
+
+    def ex_uv(d, a, b):
+        exchange_uv(topo, a[0], b[0], ol, False, gmuv)
+    return ini_cg2d(g, P, exch=ex, exch_uv=ex_uv)

@@ -33,7 +33,8 @@ void og_timestep(const og_grid *g, const og_params *p, int bi, int bj, int k,
                  const double *surfaceForcingU, const double *surfaceForcingV,
                  int momForcing, int momDissip_In_AB, double abFac,
                  const double *uVel, const double *vVel,
-                 double *gU, double *gV, double *guNm1, double *gvNm1) {
+                 double *gU, double *gV, double *guNm1, double *gvNm1,
+                 const double *phiSurfX, const double *phiSurfY) {
   SETUP
   const size_t ns = px * py;
   double *guExt = (double *)calloc(ns * 4, sizeof(double));
@@ -86,8 +87,13 @@ void og_timestep(const og_grid *g, const og_params *p, int bi, int bj, int k,
       }
   for (int j = jMin; j <= jMax; j++)
     for (int i = iMin; i <= iMax; i++) {
-      G3(gU, i, j, k) = G3(uVel, i, j, k) + p->deltaTMom * (gUtmp[S(i, j)] + 0.) * G3(g->maskW, i, j, k);
-      G3(gV, i, j, k) = G3(vVel, i, j, k) + p->deltaTMom * (gVtmp[S(i, j)] + 0.) * G3(g->maskS, i, j, k);
+      /* gUdPx = -psFac*phiSurfX with psFac = pfFacMom*(1 - implicSurfPress) (timestep.F:95-97, 230-236);
+       * phiSurf is only computed by the caller when implicSurfPress != 1 (dynamics.F:249-255) */
+      const double psFac = 1. * (1. - p->implicSurfPress) * 1. * 1.;
+      const double gUdPx = phiSurfX ? -psFac * phiSurfX[S(i, j)] : 0.;
+      const double gVdPy = phiSurfY ? -psFac * phiSurfY[S(i, j)] : 0.;
+      G3(gU, i, j, k) = G3(uVel, i, j, k) + p->deltaTMom * (gUtmp[S(i, j)] + gUdPx) * G3(g->maskW, i, j, k);
+      G3(gV, i, j, k) = G3(vVel, i, j, k) + p->deltaTMom * (gVtmp[S(i, j)] + gVdPy) * G3(g->maskS, i, j, k);
     }
   free(guExt);
 }
@@ -113,12 +119,19 @@ void og_solve_rhs(const og_grid *g, const og_params *p, int bi, int bj, const do
         xA[S(i, j)] = G2(g->dyG, i, j) * g->drF[k - 1] * G3(g->hFacW, i, j, k);
         yA[S(i, j)] = G2(g->dxG, i, j) * g->drF[k - 1] * G3(g->hFacS, i, j, k);
       }
+    /* calc_div_ghat.F:75-98: implicDiv2DFlow = 1, or < 1 with exactConserv (the (1-implicDiv2DFlow)*uVel part
+     * then lives in etaH); the third branch (no exactConserv) is not restated */
+    const int full = p->implicDiv2DFlow == 1.;
     for (int j = 1; j <= sNy; j++)
-      for (int i = 1; i <= sNx + 1; i++) pf[S(i, j)] = xA[S(i, j)] * G3(gU, i, j, k) / p->deltaTMom;
+      for (int i = 1; i <= sNx + 1; i++)
+        pf[S(i, j)] = full ? xA[S(i, j)] * G3(gU, i, j, k) / p->deltaTMom
+                           : p->implicDiv2DFlow * xA[S(i, j)] * G3(gU, i, j, k) / p->deltaTMom;
     for (int j = 1; j <= sNy; j++)
       for (int i = 1; i <= sNx; i++) G2(cg2d_b, i, j) = G2(cg2d_b, i, j) + pf[S(i + 1, j)] - pf[S(i, j)];
     for (int j = 1; j <= sNy + 1; j++)
-      for (int i = 1; i <= sNx; i++) pf[S(i, j)] = yA[S(i, j)] * G3(gV, i, j, k) / p->deltaTMom;
+      for (int i = 1; i <= sNx; i++)
+        pf[S(i, j)] = full ? yA[S(i, j)] * G3(gV, i, j, k) / p->deltaTMom
+                           : p->implicDiv2DFlow * yA[S(i, j)] * G3(gV, i, j, k) / p->deltaTMom;
     for (int j = 1; j <= sNy; j++)
       for (int i = 1; i <= sNx; i++) G2(cg2d_b, i, j) = G2(cg2d_b, i, j) + pf[S(i, j + 1)] - pf[S(i, j)];
   }
@@ -189,4 +202,17 @@ void og_integrate_for_w(const og_grid *g, const og_params *p, int bi, int bj,
       }
   }
   free(uTrans);
+}
+
+/* CALC_GRAD_PHI_SURF (model/src/calc_grad_phi_surf.F) for one tile on iMin..iMax x jMin..jMax. */
+void og_calc_grad_phi_surf(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax,
+                           const double *Bo_surf, const double *etaFld, double *phiSurfX, double *phiSurfY) {
+  SETUP
+  for (int j = jMin; j <= jMax; j++)
+    for (int i = iMin; i <= iMax; i++) {
+      phiSurfX[S(i, j)] = G2(g->recip_dxC, i, j)
+          * (G2(Bo_surf, i, j) * G2(etaFld, i, j) - G2(Bo_surf, i - 1, j) * G2(etaFld, i - 1, j));
+      phiSurfY[S(i, j)] = G2(g->recip_dyC, i, j)
+          * (G2(Bo_surf, i, j) * G2(etaFld, i, j) - G2(Bo_surf, i, j - 1) * G2(etaFld, i, j - 1));
+    }
 }

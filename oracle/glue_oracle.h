@@ -12,7 +12,10 @@ void og_timestep(const og_grid *g, const og_params *p, int bi, int bj, int k,
                  const double *surfaceForcingU, const double *surfaceForcingV,
                  int momForcing, int momDissip_In_AB, double abFac,
                  const double *uVel, const double *vVel,
-                 double *gU, double *gV, double *guNm1, double *gvNm1);
+                 double *gU, double *gV, double *guNm1, double *gvNm1,
+                 const double *phiSurfX, const double *phiSurfY);   /* NULL unless implicSurfPress != 1 */
+void og_calc_grad_phi_surf(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax,
+                           const double *Bo_surf, const double *etaFld, double *phiSurfX, double *phiSurfY);
 /* etaFS = the field of the free-surface term: etaH when exactConserv (solve_for_pressure.F:213-222),
  * else etaN (:224-233). */
 void og_solve_rhs(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf,

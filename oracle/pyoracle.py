@@ -164,11 +164,17 @@ class Oracle:
 
     # ---- glue ----
     def timestep(self, bi, bj, k, iMin, iMax, jMin, jMax, dPhiHydX, dPhiHydY, guDiss, gvDiss, sfU, sfV,
-                 momForcing, momDissip_In_AB, abFac, uVel, vVel, gU, gV, guNm1, gvNm1):
+                 momForcing, momDissip_In_AB, abFac, uVel, vVel, gU, gV, guNm1, gvNm1, phiSurfX=None, phiSurfY=None):
         self.lib.og_timestep(C.byref(self.g), C.byref(self.p), bi, bj, k, iMin, iMax, jMin, jMax,
                              ptr(dPhiHydX), ptr(dPhiHydY), ptr(guDiss), ptr(gvDiss), ptr(sfU), ptr(sfV),
                              int(momForcing), int(momDissip_In_AB), C.c_double(abFac), ptr(uVel), ptr(vVel),
-                             ptr(gU), ptr(gV), ptr(guNm1), ptr(gvNm1))
+                             ptr(gU), ptr(gV), ptr(guNm1), ptr(gvNm1),
+                             ptr(phiSurfX) if phiSurfX is not None else None,
+                             ptr(phiSurfY) if phiSurfY is not None else None)
+
+    def calc_grad_phi_surf(self, bi, bj, iMin, iMax, jMin, jMax, etaFld, phiSurfX, phiSurfY):
+        self.lib.og_calc_grad_phi_surf(C.byref(self.g), bi, bj, iMin, iMax, jMin, jMax,
+                                       ptr(self.grid.a["Bo_surf"]), ptr(etaFld), ptr(phiSurfX), ptr(phiSurfY))
 
     def solve_rhs(self, bi, bj, etaN, gU, gV, b, x, etaH=None):
         """etaH given = exactConserv (solve_for_pressure.F:213-222)."""

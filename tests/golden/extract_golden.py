@@ -20,6 +20,9 @@ def parse(exp, out="results/output.txt"):
     g["cg2d_init_res"] = re.findall(r"cg2d_init_res =\s*" + NUM, txt)
     g["cg2d_iters"] = [int(x) for x in re.findall(r"cg2d_iters\(min,last\) =\s*-?\d+\s+(\d+)", txt)]
     g["cg2d_last_res"] = re.findall(r"cg2d_last_res =\s*" + NUM, txt)
+    if not g["cg2d_iters"]:      # output written by an older SOLVE_FOR_PRESSURE: "cg2d_iters =  5", "cg2d_res = ..."
+        g["cg2d_iters"] = [int(x) for x in re.findall(r"cg2d_iters =\s*(\d+)", txt)]
+        g["cg2d_last_res"] = re.findall(r"cg2d_res =\s*" + NUM, txt)
     for fld in ("eta", "uvel", "vvel", "wvel", "theta", "salt"):
         for st in ("max", "min", "mean", "sd"):
             g[f"dynstat_{fld}_{st}"] = re.findall(rf"%MON dynstat_{fld}_{st}\s+=\s*" + NUM, txt)
@@ -28,7 +31,7 @@ def parse(exp, out="results/output.txt"):
 
 if __name__ == "__main__":
     for exp in ("tutorial_barotropic_gyre", "tutorial_baroclinic_gyre", "global_ocean.90x40x15",
-                "global_ocean.cs32x15"):
+                "global_ocean.cs32x15", "adjustment.cs-32x32x1"):
         with open(os.path.join(HERE, exp + ".json"), "w") as f:
             json.dump(parse(exp), f, indent=1)
         print("wrote", exp)

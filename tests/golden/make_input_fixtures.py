@@ -20,9 +20,13 @@ def cs32_fixture():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
     from mitgcm_b200.grid import read_mitgrid_faces
     faces = read_mitgrid_faces(os.path.join(REF, "tutorial_held_suarez_cs/input/grid_cs32"), 32)
-    keep = "xC yC rA xG yG dxC dyC dxG dyG".split()
+    keep = "xC yC rA xG yG dxC dyC dxG dyG rAw rAs".split()
     out = {f"{n}_{f}": faces[f][n] for f in range(6) for n in keep}
     out["bathy_Hmin50"] = np.fromfile(os.path.join(REF, "global_ocean.cs32x15/input/bathy_Hmin50.bin"), ">f8").reshape(32, 192).astype(np.float64)
+    # adjustment.cs-32x32x1 (same grid): flat 1366 m bathymetry and the initial free-surface bump
+    adj = os.path.join(REF, "adjustment.cs-32x32x1/input")
+    out["adj_bathy_f2"] = np.fromfile(os.path.join(adj, "bathy_f2.bin"), ">f8").reshape(32, 192).astype(np.float64)
+    out["adj_ssh_eq"] = np.fromfile(os.path.join(adj, "ssh_eq.bin"), ">f8").reshape(32, 192).astype(np.float64)
     np.savez_compressed(os.path.join(HERE, "cs32_grid_bathy.npz"), **out)
     print("wrote cs32_grid_bathy.npz")
 

@@ -47,11 +47,14 @@ class CudaEngine:
         self.rt, self.fb = rt, fallback
         self.use_gad, self.use_mom, self.use_cg2d = use_gad, use_mom, use_cg2d
 
-    def setup(self, g, params, op):
+    def setup(self, g, params, op, topo=None):
         from mitgcm_b200 import _lib
         rt = self.rt
         rt.init(g.d)
         rt.set_grid(g)
+        if topo is not None:            # pkg/exch2 tile graph (cubed sphere)
+            from mitgcm_b200.exch2 import set_topology
+            set_topology(topo)
         known = {k: v for k, v in params.items() if "MP_" + k.upper() in _lib.ENUMS or "MI_" + k.upper() in _lib.ENUMS}
         rt.set_params(**known)
         rt.set_cg2d_operator(op)
@@ -85,7 +88,7 @@ def load_cs32():
     from mitgcm_b200.grid import cubed_sphere_grid, cube_masks_from_depth
     from mitgcm_b200.exch2 import cubed_sphere_topology
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "inputs", "cs32_grid_bathy.npz"))
-    keep = "xC yC rA xG yG dxC dyC dxG dyG".split()
+    keep = "xC yC rA xG yG dxC dyC dxG dyG rAw rAs".split()
     faces = [{n: z[f"{n}_{f}"] for n in keep} for f in range(6)]
     T = cubed_sphere_topology(32, 32, 16)
     d = Dims(sNx=32, sNy=16, OLx=4, OLy=4, nSx=12, nSy=1, Nr=15)

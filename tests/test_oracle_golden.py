@@ -179,3 +179,53 @@ def test_config3_operator_solve_converges_like_the_reference():
     x = np.zeros(d.shape2)
     r = o.cg2d(op, b, x, 500, -1)
     assert 80 <= r["numIters"] <= 200 and r["lastResidual"] < 1e-13
+
+
+# ---------------------------------------------------------------------------------------
+# verification/adjustment.cs-32x32x1: barotropic adjustment on the cs32 cubed sphere (48 tiles,
+# pkg/exch2).  Pins the exch2 exchanges (scalar, signed and unsigned vector), CG2D on the cube,
+# the Crank-Nicolson free surface (implicSurfPress = implicDiv2DFlow = 0.5, exactConserv) and
+# MOM_FLUXFORM's Coriolis term on a curvilinear grid against results/output.txt, 24 steps.
+# ---------------------------------------------------------------------------------------
+from oracle import adjustment_cs as ac
+
+GOLDA = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "adjustment.cs-32x32x1.json")))
+
+
+@pytest.fixture(scope="module")
+def ac24():
+    return ac.run(24)
+
+
+def test_adjustment_cs_cg2d_lines_all_steps(ac24):
+    """Iteration counts identical for all 24 steps; cg2d_init_res, Sum(rhs), rhsMax to >= 13 digits
+    (all 15 printed digits except a last-digit flip at step 21; the reference's own pass rule is 10)."""
+    norm, out = ac24
+    assert fmt(norm, 16) == GOLDA["cg2dNorm"]          # 2.9024774185495597E-03
+    assert [r["numIters"] for r in out] == GOLDA["cg2d_iters"]
+    exact = 0
+    for r, ir, (sr, rm) in zip(out, GOLDA["cg2d_init_res"], GOLDA["sumRHS_rhsMax"]):
+        assert r["firstResidual"] == pytest.approx(float(ir), rel=1e-13)
+        assert r["rhsMax"] == pytest.approx(float(rm), rel=1e-13)
+        assert r["sumRHS"] == pytest.approx(float(sr), rel=1e-12)
+        exact += fmt(r["firstResidual"], 14) == ir
+    assert exact >= 22
+    # cg2d_res (the last residual, ~1e-14 = round-off of a 1e-13 solve): same magnitude
+    for r, lr in zip(out, GOLDA["cg2d_last_res"]):
+        assert r["lastResidual"] == pytest.approx(float(lr), rel=1e-3)
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel"])
+@pytest.mark.parametrize("st", ["max", "min", "mean", "sd"])
+def test_adjustment_cs_monitor_dynstats(ac24, fld, st):
+    """max / min / sd and the mean of eta: every printed digit (13) for the 24 steps, allowing one unit in
+    the last place.  The means of u, v, w are sums that cancel to round-off on the symmetric cube (1e-19 at
+    step 1, amplified by the flow): they are compared absolutely against 1e-12 of the field's magnitude."""
+    _, out = ac24
+    gold = GOLDA[f"dynstat_{fld}_{st}"][1:]
+    for r, gv in zip(out, gold):
+        if st == "mean" and fld != "eta":
+            scale = max(abs(r[fld]["max"]), abs(r[fld]["min"]))
+            assert abs(r[fld][st] - float(gv)) < 1e-12 * scale, (fld, st)
+        else:
+            assert r[fld][st] == pytest.approx(float(gv), rel=2e-13, abs=1e-30), (fld, st)
