@@ -29,3 +29,16 @@ def test_no_gpu_means_loud_failure():
     from mitgcm_b200.grid import Dims
     with pytest.raises(runtime.B200Error):
         runtime.init(Dims(8, 8, 2, 2))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under mitgcm_b200/ may import, load or execute it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(__file__), "..", "mitgcm_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt, f
