@@ -148,9 +148,11 @@ phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restri
   }
 }
 
-// exactConserv: dEtaHdt and the conserving update of etaN on the interior (levels summed k = 1..Nr).
+// exactConserv: dEtaHdt, the conserving update of etaN (integr_continuity.F:120-215) and UPDATE_ETAH
+// (update_etah.F:52-68) on the interior; levels summed k = 1..Nr.  Reads u(sNx+1), v(sNy+1), which the
+// correction kernel has stored.  The caller exchanges etaN and etaH afterwards.
 __global__ void __launch_bounds__(128)
-etah_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ etaH,
+etah_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ etaH,
             double *__restrict__ dEtaHdt, double *__restrict__ etaN, double implicDiv2DFlow, double deltaTFreeSurf) {
   const int i = 1 + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 + blockIdx.y * 4 + threadIdx.y;
@@ -168,7 +170,10 @@ etah_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__
   }
   const double d = -h * g.recip_rA[s] * 1. - 0.;
   dEtaHdt[s] = d;
-  etaN[s] = etaH[s] + implicDiv2DFlow * d * deltaTFreeSurf;
+  const double eN = etaH[s] + implicDiv2DFlow * d * deltaTFreeSurf;
+  etaN[s] = eN;
+  // UPDATE_ETAH: etaH = etaN for implicDiv2DFlow = 1, else etaN + (1 - implicDiv2DFlow)*dEtaHdt*deltaTFreeSurf
+  etaH[s] = implicDiv2DFlow == 1. ? eN : eN + (1. - implicDiv2DFlow) * d * deltaTFreeSurf;
 }
 
 }  // namespace mg

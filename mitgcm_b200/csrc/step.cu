@@ -9,8 +9,9 @@
 //   corr_kernel   : MOMENTUM_CORRECTION_STEP (calc_grad_phi_surf.F, correction_step.F:152-231) +
 //                   INTEGRATE_FOR_W (integrate_for_w.F), k = Nr..1 per column
 //   exch_kernel   : EXCH_XYZ_RL with corners on one periodic process (exch1_rx.template:170-201)
-// Assumptions of this driver (checked): linear free surface, implicSurfPress = implicDiv2DFlow = 1,
-// no CD scheme, z coordinates, buoyancy decoupled (dPhiHyd = 0), surface stress forcing only.
+// Assumptions of this driver (checked): linear free surface, no CD scheme, z coordinates, linear EOS,
+// surface stress + SST-relaxation forcing; implicSurfPress / implicDiv2DFlow < 1 go through the generic
+// dynamics kernel; tile graphs (pkg/exch2) on one GPU.
 #include <cstdio>
 #include <cstdlib>
 #include "step_fast.cuh"
@@ -143,13 +144,23 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
 __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
                                                   double *gU, double *gV, double *guNm1, double *gvNm1,
                                                   double deltaTMom, double abFac, int momForcing, int dissInAB,
-                                                  const double *phiHyd) {
+                                                  const double *phiHyd, const double *etaN, const double *Bo_surf,
+                                                  double psFacTS) {
   const int i = blockIdx.x * 32 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
   const int j = blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx + 1 || j > g.sNy + 1) return;
   double ukm = 0., vkm = 0.;
   if (p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
   const size_t s = g.s(i, j);
+  // CALC_GRAD_PHI_SURF (calc_grad_phi_surf.F) when implicSurfPress != 1 (dynamics.F:249-255); the explicit
+  // part of the surface pressure gradient enters TIMESTEP as gUdPx = -psFac*phiSurfX, psFac = 1 - implicSurfPress
+  double gUdPx = 0., gVdPy = 0.;
+  if (etaN) {
+    const double phiSurfX = g.recip_dxC[s] * (Bo_surf[s] * etaN[s] - Bo_surf[s - 1] * etaN[s - 1]);
+    const double phiSurfY = g.recip_dyC[s] * (Bo_surf[s] * etaN[s] - Bo_surf[s - g.PX] * etaN[s - g.PX]);
+    gUdPx = -psFacTS * phiSurfX;
+    gVdPy = -psFacTS * phiSurfY;
+  }
   for (int k = 1; k <= g.Nr; k++) {
     double ukp = 0., vkp = 0.;
     if (p.momAdvection) { ukp = mom_adv_wu(g, st, p, k + 1, i, j); vkp = mom_adv_wv(g, st, p, k + 1, i, j); }
@@ -180,8 +191,8 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
     gvNm1[s3] = gv;
     gv = gv + ab;
     if (p.momViscosity && !dissInAB) { gu = gu + o.guDiss; gv = gv + o.gvDiss; }
-    gU[s3] = st.u[s3] + deltaTMom * (gu + 0.) * g.maskW[s3];   // timestep.F:375-384
-    gV[s3] = st.v[s3] + deltaTMom * (gv + 0.) * g.maskS[s3];
+    gU[s3] = st.u[s3] + deltaTMom * (gu + gUdPx) * g.maskW[s3];   // timestep.F:375-384
+    gV[s3] = st.v[s3] + deltaTMom * (gv + gVdPy) * g.maskS[s3];
     ukm = ukp; vkm = vkp;
   }
 }
@@ -200,7 +211,9 @@ __global__ void __launch_bounds__(128, RHS_MINB) rhs_kernel(TileGrid g, const do
                                                   const double *__restrict__ etaN, const double *__restrict__ etaFS,
                                                   const double *__restrict__ Bo_surf,
                                                   double *__restrict__ cg2d_b, double *__restrict__ cg2d_x,
-                                                  double deltaTMom, double deltaTFreeSurf, double freeSurfFac) {
+                                                  double deltaTMom, double deltaTFreeSurf, double freeSurfFac,
+                                                  double implicDiv2DFlow, const double *__restrict__ uVel,
+                                                  const double *__restrict__ vVel) {
   const int i = 1 - g.OLx + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
@@ -217,8 +230,22 @@ UNROLL_N(RHS_UNROLL)
       const size_t q = s + slab * (size_t)(k - 1);
       const double drFk = g.drF[k - 1];
       // calc_div_ghat.F:64-167: pf = xA*gU/deltaTMom with xA = dyG*drF*hFacW
-      const double px1 = dyG1 * drFk * hW[q + 1] * gU[q + 1] / deltaTMom, px0 = dyG0 * drFk * hW[q] * gU[q] / deltaTMom;
-      const double py1 = dxG1 * drFk * hS[q + PX] * gV[q + PX] / deltaTMom, py0 = dxG0 * drFk * hS[q] * gV[q] / deltaTMom;
+      double px1, px0, py1, py0;
+      if (implicDiv2DFlow == 1.) {
+        px1 = dyG1 * drFk * hW[q + 1] * gU[q + 1] / deltaTMom; px0 = dyG0 * drFk * hW[q] * gU[q] / deltaTMom;
+        py1 = dxG1 * drFk * hS[q + PX] * gV[q + PX] / deltaTMom; py0 = dxG0 * drFk * hS[q] * gV[q] / deltaTMom;
+      } else if (!uVel) {      // exactConserv (calc_div_ghat.F:81-87): the explicit part lives in etaH
+        px1 = implicDiv2DFlow * (dyG1 * drFk * hW[q + 1]) * gU[q + 1] / deltaTMom;
+        px0 = implicDiv2DFlow * (dyG0 * drFk * hW[q]) * gU[q] / deltaTMom;
+        py1 = implicDiv2DFlow * (dxG1 * drFk * hS[q + PX]) * gV[q + PX] / deltaTMom;
+        py0 = implicDiv2DFlow * (dxG0 * drFk * hS[q]) * gV[q] / deltaTMom;
+      } else {                 // calc_div_ghat.F:88-95
+        const double om = 1. - implicDiv2DFlow;
+        px1 = (implicDiv2DFlow * gU[q + 1] + om * uVel[q + 1]) * (dyG1 * drFk * hW[q + 1]) / deltaTMom;
+        px0 = (implicDiv2DFlow * gU[q] + om * uVel[q]) * (dyG0 * drFk * hW[q]) / deltaTMom;
+        py1 = (implicDiv2DFlow * gV[q + PX] + om * vVel[q + PX]) * (dxG1 * drFk * hS[q + PX]) / deltaTMom;
+        py0 = (implicDiv2DFlow * gV[q] + om * vVel[q]) * (dxG0 * drFk * hS[q]) / deltaTMom;
+      }
       b = b + px1 - px0;
       b = b + py1 - py0;
     }
@@ -269,6 +296,10 @@ UNROLL_N(CORR_UNROLL)
     const size_t s3 = g.s3(i, j, k);
     uVel[s3] = u0;
     vVel[s3] = v0;
+    // CORRECTION_STEP covers the halo'd slab (momentum_correction_step.F:60-63); INTEGR_CONTINUITY's
+    // exactConserv sum reads u(sNx+1), v(sNy+1) before the exchange, so the edge threads store them too
+    if (i == g.sNx) uVel[s3 + 1] = u1;
+    if (j == g.sNy) vVel[s3 + g.PX] = v1;
     // INTEGRATE_FOR_W
     const double uT0 = u0 * g.dyG[g.s(i, j)] * g.drF[k - 1] * g.hFacW[s3];
     const double uT1 = u1 * g.dyG[g.s(i + 1, j)] * g.drF[k - 1] * g.hFacW[g.s3(i + 1, j, k)];
@@ -312,8 +343,9 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   const Geom &g = c.g;
   const Params &q = c.p;
-  if (q.D(MP_IMPLICSURFPRESS) != 1.0 || q.D(MP_IMPLICDIV2DFLOW) != 1.0 || q.I(MI_USECDSCHEME))
-    return fail(61, "forward_step: needs implicSurfPress = implicDiv2DFlow = 1 and no CD scheme");
+  if (q.I(MI_USECDSCHEME)) return fail(61, "forward_step: the CD scheme is not supported");
+  const bool semiImpl = q.D(MP_IMPLICSURFPRESS) != 1.0 || q.D(MP_IMPLICDIV2DFLOW) != 1.0;
+  if (semiImpl && g.nPx * g.nPy > 1) return fail(61, "forward_step: implicSurfPress/implicDiv2DFlow < 1 is single-rank for now");
   MomPar mp;
   if (!make_mom_par(mp)) return false;
   const double abFac = (myIter == q.I(MI_NITER0)) ? 0.0 : 0.5 + q.D(MP_ABEPS);
@@ -431,7 +463,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        if (dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
+        if (!semiImpl && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
           static bool attr = false;
           if (!attr) {
             cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
@@ -440,14 +472,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
           dyn_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(DynPipeSmem),
                             c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
                                         abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr);
-        } else if (!buoy && dyn_fast_ok(g, mp))
+        } else if (!buoy && !semiImpl && dyn_fast_ok(g, mp))
           dyn_fast_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
         else
           dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
                                                 q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
-                                                buoy ? phiHyd + o3 : nullptr);
+                                                buoy ? phiHyd + o3 : nullptr,
+                                                q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
+                                                1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
       }
     MG_CUDA(cudaGetLastError());
   }
@@ -464,7 +498,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
         rhs_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
-                                              q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC));
+                                              q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC), q.D(MP_IMPLICDIV2DFLOW),
+                                              exactConserv ? nullptr : u + o3, exactConserv ? nullptr : v + o3);
       }
     MG_CUDA(cudaGetLastError());
     mark(3);
@@ -503,9 +538,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
 }
 
 // INTEGR_CONTINUITY, exactConserv part (integr_continuity.F:120-215) + _EXCH_XY_RL(etaN) (:331-333) +
-// UPDATE_ETAH (update_etah.F: etaH = etaN for implicDiv2DFlow = 1).  The reference runs it on velocities
-// that CORRECTION_STEP has already updated over the whole halo'd slab; here the correction kernel writes
-// the interior only, so this runs after the u, v halo exchange (same values).
+// UPDATE_ETAH (update_etah.F) with its EXCH_XY_RL(etaH); runs right after the correction kernel, which
+// stores u(sNx+1), v(sNy+1) for it, and before the blocking exchanges, as in the reference.
 static bool etah_update() {
   Ctx &c = ctx();
   const Geom &g = c.g;
@@ -523,9 +557,7 @@ static bool etah_update() {
                                              q.D(MP_DELTATFREESURF));
     }
   MG_CUDA(cudaGetLastError());
-  if (!exch_field(eta, 1)) return false;
-  MG_CUDA(cudaMemcpyAsync(etaH, eta, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-  return true;
+  return exch_field(eta, 1) && exch_field(etaH, 1);
 }
 
 static bool forward_step(int myIter, double *initRes, int *iters, double *lastRes) {
@@ -543,9 +575,12 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
     if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
     cudaEventRecord(c.pev[n], c.stream);
   };
-  // DO_FIELDS_BLOCKING_EXCHANGES (u, v first: the exactConserv update of etaN reads their halos)
-  if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr)) return false;
   if (q.I(MI_EXACTCONSERV) && !etah_update()) return false;
+  // DO_FIELDS_BLOCKING_EXCHANGES: EXCH_UV_XYZ_RL(uVel, vVel, .TRUE.) -- on an exch2 tile graph the vector
+  // exchange swaps / negates components across rotated facet edges -- then the scalars
+  if (exch2_active()) {
+    if (!exch2_uv_field(field(MG_UVEL), field(MG_VVEL), g.Nr, true)) return false;
+  } else if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr)) return false;
   if (!exch_field(field(MG_WVEL), g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
   mark(7);

@@ -22,7 +22,8 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "useBiharmonicVisc implicitViscosity selectCoriScheme rigidLid momAdvection momViscosity "
               "diffKhT diffK4T diffKrT viscAr tempStepping cg2dMaxIters momForcing momDissip_In_AB "
               "implicitDiffusion useSRCGSolver usingSphericalPolarGrid selectMetricTerms recip_rSphere "
-              "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa").split()
+              "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa "
+              "implicSurfPress implicDiv2DFlow").split()
 
 
 def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
@@ -86,10 +87,13 @@ def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=
 class Model:
     """Device-resident model: Model(grid, params, state).step() == one FORWARD_STEP."""
 
-    def __init__(self, g: Grid, P: dict, state: dict, op: dict, device=-1):
+    def __init__(self, g: Grid, P: dict, state: dict, op: dict, device=-1, topo=None):
         self.g, self.d, self.P = g, g.d, P
         rt.init(g.d, device)
         rt.set_grid(g)
+        if topo is not None:          # pkg/exch2 tile graph (cubed sphere): all exchanges follow it
+            from .exch2 import set_topology
+            set_topology(topo)
         rt.set_params(**{k: P[k] for k in LIB_PARAMS if k in P})
         rt.set_params(deltaTtracer=P.get("deltaTtracer", P["deltaTMom"]), tempAdvScheme=P.get("tempAdvScheme", 2),
                       tempVertAdvScheme=P.get("tempAdvScheme", 2), nIter0=0)
