@@ -64,7 +64,7 @@ enum {
   MI_USINGSPHERICALPOLARGRID, MI_RIGIDLID, MI_SELECT_RSTAR, MI_IMPLICITDIFFUSION,
   MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
   MI_TEMPSTEPPING, MI_NITER0, MI_PROFILE,
-  MI_EXACTCONSERV, MI_BUOYANCYLINEAR, MI_DOTHETACLIMRELAX,
+  MI_EXACTCONSERV, MI_BUOYANCYLINEAR, MI_DOTHETACLIMRELAX, MI_GAD_MULTIDIM_COMPRESSIBLE,
   MI_NI_END
 };
 
@@ -130,6 +130,18 @@ void gad_calc_rhs_b200_(const int *bi, const int *bj, const int *iMin, const int
                         const int *trUseKPP, const int *trUseSmolHack,
                         double *fZon, double *fMer, double *fVerT, double *gTracer,
                         const double *myTime, const int *myIter, const int *myThid);
+
+/* ---- GAD_ADVECTION ---------------------------------------------------------------
+ * Multi-dimensional advection of one tracer on one tile, all levels: same argument list as
+ * pkg/generic_advdiff/gad_advection.F:11-17 (callers temp_integrate.F:283, salt_integrate.F:275,
+ * ptracers_integrate.F).  uFld, vFld, wFld, gTracer are (slab, Nr) arrays of the tile, tracer the
+ * full (.., Nr, nSx, nSy) array.  The GAD_MULTIDIM_COMPRESSIBLE build option (GAD_OPTIONS.h:44) is
+ * the run-time parameter MI_GAD_MULTIDIM_COMPRESSIBLE.  Non-cube topology only. */
+void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchArg, const int *vertAdvecSchArg,
+                         const int *trIdentity, const double *deltaTLev, const double *uFld,
+                         const double *vFld, const double *wFld, const double *tracer, double *gTracer,
+                         const int *bi, const int *bj, const double *myTime, const int *myIter,
+                         const int *myThid);
 
 /* ---- MOM_FLUXFORM -----------------------------------------------------------------
  * Same argument list as pkg/mom_fluxform/mom_fluxform.F:42-48 (caller dynamics.F:517),

@@ -1,0 +1,182 @@
+// gad_advection.cu -- GAD_ADVECTION drop-in (pkg/generic_advdiff/gad_advection.F:11-1097): the
+// multi-dimensional ("direct space-time") advection of one tracer on one tile, all levels per call,
+// with the reference argument list (callers temp_integrate.F:283, salt_integrate.F:275,
+// ptracers_integrate.F).  The reference sweeps the halo'd slab level by level: an X pass and a Y pass
+// that update a local copy of the tracer in sequence (each pass = one flux sweep + one update sweep),
+// then a vertical pass k = Nr..1 with a two-slab flux ring.  Here every level is independent in the
+// horizontal passes and the vertical flux at both interfaces of a cell is recomputed by its own
+// thread, so the whole routine is three launches over (i, j, k):
+//   md_pass_kernel<0>  T0 -> T1 (+ local volume)   fluxes from the tracer                 R{T,u,hFacW,hFacC}  W{T1,V1}
+//   md_pass_kernel<1>  T1 -> T2 (+ local volume)   fluxes from the X-updated field        R{T1,V1,v,hFacS}    W{T2,V2}
+//   md_vert_kernel     gTracer from T2             4..8-level stencil in k                R{T2,V2,w,T,maskC}  W{gTracer}
+// Non-cube topology (npass = 2).  Flux formulas are the leaves of gad.cuh shared with GAD_CALC_RHS
+// (schemes 1, 20, 77, 30, 33, 7).  MI_GAD_MULTIDIM_COMPRESSIBLE selects the GAD_MULTIDIM_COMPRESSIBLE
+// build variant (gad_advection.F:480-490, :1018-1032) at run time.  -fmad=false, reference operation
+// order: bit-identical to the oracle, which is pinned to verification/advect_xy.
+#include "gad.cuh"
+
+namespace mg {
+
+// accessor the flux leaves read through: tracer values from the current pass's input, transports
+// derived from the velocity of level k
+struct MdAcc {
+  TileGrid g;
+  const double *T_, *u, *v, *w;   // per-tile (slab, Nr)
+  int k;
+  __device__ __forceinline__ double TA(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
+  __device__ __forceinline__ double T(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
+  __device__ __forceinline__ double xA(int i, int j) const { return g.dyG[g.s(i, j)] * 1. * g.drF[k - 1] * g.hFacW[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double yA(int i, int j) const { return g.dxG[g.s(i, j)] * 1. * g.drF[k - 1] * g.hFacS[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double uFld(int i, int j) const { return u[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double vFld(int i, int j) const { return v[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double wFld(int i, int j) const { return w[g.s3(i, j, k)]; }
+  __device__ __forceinline__ double uTrans(int i, int j) const { return u[g.s3(i, j, k)] * xA(i, j) * 1.; }
+  __device__ __forceinline__ double vTrans(int i, int j) const { return v[g.s3(i, j, k)] * yA(i, j) * 1.; }
+  __device__ __forceinline__ double rTrans(int i, int j) const {
+    return k == 1 ? 0. : w[g.s3(i, j, k)] * g.rA[g.s(i, j)] * 1. * 1. * g.maskC[g.s3(i, j, k - 1)];
+  }
+  __device__ __forceinline__ double maskUp(int, int) const { return 0.; }
+  __device__ __forceinline__ double rTransKp1(int, int) const { return 0.; }
+  __device__ __forceinline__ double KappaR(int, int) const { return 0.; }
+};
+
+// One horizontal pass (DIR 0: X, gad_advection.F:376-560; DIR 1: Y, :597-790) over the halo'd slab of
+// every level.  Tin / Vin: tracer and local volume before the pass (Vin == nullptr: the volume of the
+// undisturbed cell, first pass); tracer0: the tracer at time n (the -T*div(U) correction of the default form).
+template <int DIR>
+__global__ void __launch_bounds__(128) md_pass_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
+                                                      const double *__restrict__ tracer0, double *__restrict__ Tout,
+                                                      double *__restrict__ Vout, int compressible, const double *dTLev) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  a.k = k; p.k = k; p.deltaT = dTLev[k - 1];
+  const size_t s3 = g.s3(i, j, k);
+  double T = a.T_[s3];
+  double V = Vin ? Vin[s3] : g.rA[g.s(i, j)] * 1. * 1. * g.drF[k - 1] * g.hFacC[s3] + (1. - g.maskC[s3]);
+  const bool upd = DIR == 0 ? (i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1) : (j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1);
+  if (upd) {
+    const int di = DIR == 0, dj = DIR == 1;
+    const double af0 = gad_adv_h(g, a, p, DIR, i, j), af1 = gad_adv_h(g, a, p, DIR, i + di, j + dj);
+    const double tr0 = DIR == 0 ? a.uTrans(i, j) : a.vTrans(i, j);
+    const double tr1 = DIR == 0 ? a.uTrans(i + 1, j) : a.vTrans(i, j + 1);
+    if (compressible) {
+      const double tmpTrac = T * V - p.deltaT * (af1 - af0) * 1.;
+      V = V - p.deltaT * (tr1 - tr0) * 1.;
+      T = tmpTrac / V;
+    } else {
+      T = T - p.deltaT * 1. * g.recip_hFacC[s3] * g.recip_drF[k - 1] * g.recip_rA[g.s(i, j)] * 1. *
+                  (af1 - af0 - tracer0[s3] * (tr1 - tr0)) * 1.;
+    }
+  }
+  Tout[s3] = T;
+  if (Vout) Vout[s3] = V;
+}
+
+// X+Y passes only (implicitAdvection): gTracer = (T2 - tracer)/deltaT (gad_advection.F:815-823)
+__global__ void md_implicit_kernel(TileGrid g, const double *__restrict__ T2, const double *__restrict__ tracer0,
+                                   double *__restrict__ gTracer, const double *dTLev) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s3 = g.s3(i, j, k);
+  gTracer[s3] = (T2[s3] - tracer0[s3]) / dTLev[k - 1];
+}
+
+// Vertical pass (gad_advection.F:886-1050): fVerT at the upper (k) and lower (k+1) interface of the
+// cell from the Y-updated field, then the tendency.
+__global__ void __launch_bounds__(128) md_vert_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ V2,
+                                                      const double *__restrict__ tracer0, double *__restrict__ gTracer,
+                                                      int compressible, const double *dTLev) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s3 = g.s3(i, j, k);
+  p.deltaT = dTLev[k - 1];
+  // upper interface (kUp): zero at k = 1
+  a.k = k; p.k = k;
+  double fUp = 0., rTrans = 0.;
+  if (k >= 2) { rTrans = a.rTrans(i, j); fUp = gad_adv_r(g, a, p, i, j); }
+  // lower interface (kDown) = upper interface of level k+1, left by the previous level of the k = Nr..1 march;
+  // its CFL number uses deltaTLev(k+1) (the leaf is called for level k+1)
+  double fDn = 0., rTransKp = 0.;
+  if (k < g.Nr) {
+    MdAcc b = a;
+    GadPar q = p;
+    b.k = k + 1; q.k = k + 1; q.deltaT = dTLev[k];
+    rTransKp = b.rTrans(i, j);
+    fDn = gad_adv_r(g, b, q, i, j);
+  }
+  const double T2 = a.T_[s3];
+  if (compressible) {
+    const double tmpTrac = T2 * V2[s3] - p.deltaT * (fDn - fUp) * p.rkSign * 1.;
+    const double vol = V2[s3] - p.deltaT * (rTransKp - rTrans) * p.rkSign * 1.;
+    gTracer[s3] = (tmpTrac - tracer0[s3] * vol) * g.recip_rA[g.s(i, j)] * 1. * g.recip_drF[k - 1] * g.recip_hFacC[s3] * 1. /
+                  p.deltaT;
+  } else {
+    const double lt = T2 - p.deltaT * 1. * g.recip_hFacC[s3] * g.recip_drF[k - 1] * g.recip_rA[g.s(i, j)] * 1. *
+                               (fDn - fUp - tracer0[s3] * (rTransKp - rTrans)) * p.rkSign * 1.;
+    gTracer[s3] = (lt - tracer0[s3]) / p.deltaT;
+  }
+}
+
+static bool md_scheme(int s) {
+  return s == ADV_UPWIND_1RST || s == ADV_DST2 || s == ADV_FLUX_LIMIT || s == ADV_DST3 || s == ADV_DST3_FLUX_LIMIT ||
+         s == ADV_OS7MP;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchArg, const int *vertAdvecSchArg,
+                                    const int *trIdentity, const double *deltaTLev, const double *uFld,
+                                    const double *vFld, const double *wFld, const double *tracer, double *gTracer,
+                                    const int *bi, const int *bj, const double *myTime, const int *myIter,
+                                    const int *myThid) {
+  (void)trIdentity; (void)myTime; (void)myIter; (void)myThid;
+  Ctx &c = ctx();
+  c.lastError = 0;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  const int compressible = c.p.I(MI_GAD_MULTIDIM_COMPRESSIBLE);
+  if (!md_scheme(*advectionSchArg) || (!*implicitAdvection && !md_scheme(*vertAdvecSchArg))) {
+    fail(42, "gad_advection_b200_: advection scheme incompatible with multi-dim advection");
+    return;
+  }
+  if (*implicitAdvection && compressible) { fail(42, "gad_advection_b200_: implicitAdvection with GAD_MULTIDIM_COMPRESSIBLE"); return; }
+  if (exch2_active()) { fail(44, "gad_advection_b200_: the 3-pass cubed-sphere form is not built"); return; }
+  if (*advectionSchArg == ADV_OS7MP && (g.OLx < 4 || g.OLy < 4)) { fail(42, "gad_advection_b200_: OS7MP needs OLx, OLy >= 4"); return; }
+  TileGrid tg;
+  if (!make_tile_grid(*bi, *bj, tg)) { if (!c.lastError) fail(43, "grid mirrors not set"); return; }
+  const size_t ns = g.slab, n3 = ns * g.Nr;
+  const size_t tile = (size_t)(*bi - 1) + (size_t)g.nSx * (size_t)(*bj - 1);
+  const double *u = to_device(uFld, n3, 40, true), *v = to_device(vFld, n3, 41, true), *w = to_device(wFld, n3, 42, true);
+  // tracer is the full (.., Nr, nSx, nSy) array of the caller; only this tile is needed
+  const double *tr = is_device_ptr(tracer) ? tracer + n3 * tile : to_device(tracer + n3 * tile, n3, 43, true);
+  double *gT = is_device_ptr(gTracer) ? gTracer : to_device(gTracer, n3, 44, false);
+  double *T1 = to_device(nullptr, n3, 45, false), *V1 = to_device(nullptr, n3, 46, false);
+  double *T2 = to_device(nullptr, n3, 47, false), *V2 = to_device(nullptr, n3, 48, false);
+  double *dT = to_device(deltaTLev, (size_t)g.Nr, 49, true);
+  if (!u || !v || !w || !tr || !gT || !T1 || !V1 || !T2 || !V2 || !dT) return;
+  GadPar p{};
+  p.advScheme = *advectionSchArg;
+  // GAD_DST2U1_ADV_R is handed advectionScheme, not vertAdvecScheme (gad_advection.F:976)
+  p.vertAdvScheme = (*vertAdvecSchArg == ADV_UPWIND_1RST || *vertAdvecSchArg == ADV_DST2) ? *advectionSchArg : *vertAdvecSchArg;
+  p.calcAdvection = 1; p.rkSign = c.p.D(MP_RKSIGN);
+  MdAcc a{tg, tr, u, v, w, 1};
+  dim3 blk(32, 4), grd((g.PX + 31) / 32, (g.PY + 3) / 4, g.Nr);
+  c.launches += 3;
+  md_pass_kernel<0><<<grd, blk, 0, c.stream>>>(tg, a, p, nullptr, tr, T1, V1, compressible, dT);
+  a.T_ = T1;
+  md_pass_kernel<1><<<grd, blk, 0, c.stream>>>(tg, a, p, V1, tr, T2, V2, compressible, dT);
+  a.T_ = T2;
+  if (*implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, T2, tr, gT, dT);
+  else md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, V2, tr, gT, compressible, dT);
+  if (cudaGetLastError() != cudaSuccess) { fail(5, "gad_advection_b200_: launch failed"); return; }
+  if (!from_device(gTracer, gT, n3)) return;
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) fail(6, "gad_advection_b200_: stream error");
+}

@@ -164,6 +164,18 @@ def gad_calc_rhs(bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, mas
     _check()
 
 
+def gad_advection(implicitAdvection, advectionSchArg, vertAdvecSchArg, trIdentity, deltaTLev, uFld, vFld, wFld,
+                  tracer, gTracer, bi, bj, myTime=0.0, myIter=0, myThid=1):
+    """CALL GAD_ADVECTION(...) -- pkg/generic_advdiff/gad_advection.F:11-17, same argument order.
+    uFld, vFld, wFld, gTracer: (Nr, PY, PX) arrays of tile (bi, bj); tracer: the full tiled array."""
+    L = _lib.lib()
+    L.gad_advection_b200_(_i(implicitAdvection), _i(advectionSchArg), _i(vertAdvecSchArg), _i(trIdentity),
+                          _addr(np.ascontiguousarray(deltaTLev, dtype=np.float64)), _addr(uFld), _addr(vFld),
+                          _addr(wFld), _addr(tracer), _addr(gTracer), _i(bi), _i(bj), _d(myTime), _i(myIter),
+                          _i(myThid))
+    _check()
+
+
 def mom_fluxform(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm, fVerUkp, fVerVkp,
                  guDiss, gvDiss, uVel, vVel, wVel, gU, gV, myTime=0.0, myIter=0, myThid=1):
     """CALL MOM_FLUXFORM(...) -- pkg/mom_fluxform/mom_fluxform.F:42-48, followed by the COMMON

@@ -478,3 +478,124 @@ void og_gad_calc_rhs(const og_grid *g, const og_params *p, int bi, int bj,
                                 + (rTransKp1[S(i, j)] - rTrans[S(i, j)]) * rAdvFac));
   free(buf);
 }
+
+/* ---- GAD_ADVECTION (pkg/generic_advdiff/gad_advection.F:240-1097), multi-dimensional
+ * direct-space-time advection of one tracer on one tile, non-cube topology (npass = 2: X pass then
+ * Y pass, each updating localTij over the halo'd slab), then the vertical flux pass k = Nr..1.
+ * compressible != 0 selects the GAD_MULTIDIM_COMPRESSIBLE form (local volume updated with the
+ * transport divergence, :480-490, :1018-1032), else the default form (-T*div(U) correction,
+ * :491-499, :1034-1046).  Schemes: 1, 20, 77, 30, 33, 7.  uFld, vFld, wFld, tracer are tile3d;
+ * gTracer is a per-tile (slab, Nr) array.  implicitAdvection (vertical part left to GAD_IMPLICIT_R)
+ * only in the default form, as in the reference.  Returns 0, or 1 for an unsupported scheme. */
+int og_gad_advection(const og_grid *g, const og_params *p, int bi, int bj, int advectionScheme,
+                     int vertAdvecScheme, int implicitAdvection, int compressible,
+                     const double *deltaTLev, const double *uFld, const double *vFld, const double *wFld,
+                     const double *tracer, double *gTracer) {
+  SETUP
+  const size_t ns = px * py;
+  const int ok = advectionScheme == UPWIND_1RST || advectionScheme == DST2 || advectionScheme == FLUX_LIMIT ||
+                 advectionScheme == DST3 || advectionScheme == DST3_FLUX_LIMIT || advectionScheme == OS7MP;
+  const int okv = vertAdvecScheme == UPWIND_1RST || vertAdvecScheme == DST2 || vertAdvecScheme == FLUX_LIMIT ||
+                  vertAdvecScheme == DST3 || vertAdvecScheme == DST3_FLUX_LIMIT || vertAdvecScheme == OS7MP;
+  if (!ok || (!implicitAdvection && !okv) || (implicitAdvection && compressible)) return 1;
+  double *buf = (double *)calloc(ns * (12 + 2 * (size_t)Nr), sizeof(double));
+  double *xA = buf, *yA = buf + ns, *uTrans = buf + 2 * ns, *vTrans = buf + 3 * ns, *localTij = buf + 4 * ns,
+         *localVol = buf + 5 * ns, *maskLocW = buf + 6 * ns, *maskLocS = buf + 7 * ns, *af = buf + 8 * ns,
+         *rTrans = buf + 9 * ns, *rTransKp = buf + 10 * ns;
+  double *localT3d = buf + 12 * ns, *locVol3d = buf + (12 + (size_t)Nr) * ns;
+  double *fVerT = (double *)calloc(2 * ns, sizeof(double));
+  for (int k = 1; k <= Nr; k++) {
+    const double *uK = &G3(uFld, 1 - OLx, 1 - OLy, k), *vK = &G3(vFld, 1 - OLx, 1 - OLy, k);
+    FORALL {
+      xA[S(i, j)] = G2(g->dyG, i, j) * 1. * g->drF[k - 1] * G3(g->hFacW, i, j, k);
+      yA[S(i, j)] = G2(g->dxG, i, j) * 1. * g->drF[k - 1] * G3(g->hFacS, i, j, k);
+    }
+    FORALL {
+      uTrans[S(i, j)] = G3(uFld, i, j, k) * xA[S(i, j)] * 1.;
+      vTrans[S(i, j)] = G3(vFld, i, j, k) * yA[S(i, j)] * 1.;
+    }
+    FORALL {
+      localTij[S(i, j)] = G3(tracer, i, j, k);
+      localVol[S(i, j)] = G2(g->rA, i, j) * 1. * 1. * g->drF[k - 1] * G3(g->hFacC, i, j, k) + (1. - G3(g->maskC, i, j, k));
+      maskLocW[S(i, j)] = G3(g->maskW, i, j, k);
+      maskLocS[S(i, j)] = G3(g->maskS, i, j, k);
+    }
+    for (int ipass = 1; ipass <= 2; ipass++) {
+      const int fluxX = ipass % 2 == 1;
+      FORALL af[S(i, j)] = 0.;
+      if (fluxX) {
+        adv_h(g, bi, bj, k, 0, advectionScheme, deltaTLev[k - 1], uTrans, uK, maskLocW, localTij, af);
+        for (int j = 1 - OLy; j <= sNy + OLy; j++)
+          for (int i = 1 - OLx + 1; i <= sNx + OLx - 1; i++) {
+            if (compressible) {
+              const double tmpTrac = localTij[S(i, j)] * localVol[S(i, j)]
+                                     - deltaTLev[k - 1] * (af[S(i + 1, j)] - af[S(i, j)]) * 1.;
+              localVol[S(i, j)] = localVol[S(i, j)] - deltaTLev[k - 1] * (uTrans[S(i + 1, j)] - uTrans[S(i, j)]) * 1.;
+              localTij[S(i, j)] = tmpTrac / localVol[S(i, j)];
+            } else {
+              localTij[S(i, j)] = localTij[S(i, j)]
+                  - deltaTLev[k - 1] * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.
+                        * (af[S(i + 1, j)] - af[S(i, j)] - G3(tracer, i, j, k) * (uTrans[S(i + 1, j)] - uTrans[S(i, j)])) * 1.;
+            }
+          }
+      } else {
+        adv_h(g, bi, bj, k, 1, advectionScheme, deltaTLev[k - 1], vTrans, vK, maskLocS, localTij, af);
+        for (int j = 1 - OLy + 1; j <= sNy + OLy - 1; j++)
+          for (int i = 1 - OLx; i <= sNx + OLx; i++) {
+            if (compressible) {
+              const double tmpTrac = localTij[S(i, j)] * localVol[S(i, j)]
+                                     - deltaTLev[k - 1] * (af[S(i, j + 1)] - af[S(i, j)]) * 1.;
+              localVol[S(i, j)] = localVol[S(i, j)] - deltaTLev[k - 1] * (vTrans[S(i, j + 1)] - vTrans[S(i, j)]) * 1.;
+              localTij[S(i, j)] = tmpTrac / localVol[S(i, j)];
+            } else {
+              localTij[S(i, j)] = localTij[S(i, j)]
+                  - deltaTLev[k - 1] * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.
+                        * (af[S(i, j + 1)] - af[S(i, j)] - G3(tracer, i, j, k) * (vTrans[S(i, j + 1)] - vTrans[S(i, j)])) * 1.;
+            }
+          }
+      }
+    }
+    if (implicitAdvection) {
+      FORALL K3(gTracer, i, j, k) = (localTij[S(i, j)] - G3(tracer, i, j, k)) / deltaTLev[k - 1];
+    } else {
+      FORALL { K3(locVol3d, i, j, k) = localVol[S(i, j)]; K3(localT3d, i, j, k) = localTij[S(i, j)]; }
+    }
+  }
+  if (!implicitAdvection) {
+    FORALL { fVerT[S(i, j)] = 0.; fVerT[ns + S(i, j)] = 0.; rTrans[S(i, j)] = 0.; }
+    for (int k = Nr; k >= 1; k--) {
+      const int kUp = 1 + (k + 1) % 2, kDown = 1 + k % 2;
+      const double kp1Msk = k == Nr ? 0. : 1.;
+      double *fUp = fVerT + ns * (size_t)(kUp - 1), *fDn = fVerT + ns * (size_t)(kDown - 1);
+      if (k == 1) {
+        FORALL { rTransKp[S(i, j)] = kp1Msk * rTrans[S(i, j)]; rTrans[S(i, j)] = 0.; fUp[S(i, j)] = 0.; }
+      } else {
+        FORALL {
+          rTransKp[S(i, j)] = kp1Msk * rTrans[S(i, j)];
+          rTrans[S(i, j)] = G3(wFld, i, j, k) * G2(g->rA, i, j) * 1. * 1. * G3(g->maskC, i, j, k - 1);
+          fUp[S(i, j)] = 0.;
+        }
+        /* GAD_DST2U1_ADV_R is called with advectionScheme, not vertAdvecScheme (gad_advection.F:976) */
+        const int vs = (vertAdvecScheme == UPWIND_1RST || vertAdvecScheme == DST2) ? advectionScheme : vertAdvecScheme;
+        adv_r(g, p, bi, bj, k, vs, deltaTLev[k - 1], rTrans, &G3(wFld, 1 - OLx, 1 - OLy, k), localT3d, fUp);
+      }
+      FORALL {
+        if (compressible) {
+          const double tmpTrac = K3(localT3d, i, j, k) * K3(locVol3d, i, j, k)
+                                 - deltaTLev[k - 1] * (fDn[S(i, j)] - fUp[S(i, j)]) * p->rkSign * 1.;
+          localVol[S(i, j)] = K3(locVol3d, i, j, k) - deltaTLev[k - 1] * (rTransKp[S(i, j)] - rTrans[S(i, j)]) * p->rkSign * 1.;
+          K3(gTracer, i, j, k) = (tmpTrac - G3(tracer, i, j, k) * localVol[S(i, j)])
+                                 * G2(g->recip_rA, i, j) * 1. * g->recip_drF[k - 1] * G3(g->recip_hFacC, i, j, k) * 1. / deltaTLev[k - 1];
+        } else {
+          const double lt = K3(localT3d, i, j, k)
+              - deltaTLev[k - 1] * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.
+                    * (fDn[S(i, j)] - fUp[S(i, j)] - G3(tracer, i, j, k) * (rTransKp[S(i, j)] - rTrans[S(i, j)])) * p->rkSign * 1.;
+          K3(gTracer, i, j, k) = (lt - G3(tracer, i, j, k)) / deltaTLev[k - 1];
+        }
+      }
+    }
+  }
+  free(buf);
+  free(fVerT);
+  return 0;
+}

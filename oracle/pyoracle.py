@@ -162,6 +162,13 @@ class Oracle:
             int(calcAdvection), int(implicitAdvection), int(applyAB_onTracer), int(trUseDiffKr4),
             ptr(fZon), ptr(fMer), ptr(fVerT), ptr(gTracer))
 
+    def gad_advection(self, bi, bj, advScheme, vertAdvScheme, implicitAdvection, compressible, deltaTLev,
+                      uFld, vFld, wFld, tracer, gTracer):
+        """GAD_ADVECTION (multi-dimensional advection) for one tile; gTracer is (Nr, PY, PX)."""
+        return self.lib.og_gad_advection(C.byref(self.g), C.byref(self.p), bi, bj, int(advScheme), int(vertAdvScheme),
+                                         int(implicitAdvection), int(compressible), ptr(deltaTLev), ptr(uFld), ptr(vFld),
+                                         ptr(wFld), ptr(tracer), ptr(gTracer))
+
     # ---- glue ----
     def timestep(self, bi, bj, k, iMin, iMax, jMin, jMax, dPhiHydX, dPhiHydY, guDiss, gvDiss, sfU, sfV,
                  momForcing, momDissip_In_AB, abFac, uVel, vVel, gU, gV, guNm1, gvNm1, phiSurfX=None, phiSurfY=None):

@@ -22,7 +22,8 @@ NXg, NYg, NR, nsteps = (int(a) for a in (sys.argv[1:5] + ["64", "48", "4", "3"][
 nPx, nPy = process_grid(world)
 sNx, sNy = NXg // nPx, NYg // nPy
 # the single-process reference set-up of the same global domain, tiled nPx x nPy
-gG, P, sG = make_channel(sNx, sNy, NR, nSx=nPx, nSy=nPy, land_frac=0.15)
+BUOY = int(os.environ.get("DIST_CHECK_BUOYANCY", "1"))      # the bench workload couples theta to the flow
+gG, P, sG = make_channel(sNx, sNy, NR, nSx=nPx, nSy=nPy, land_frac=0.15, buoyancyLinear=BUOY)
 opG = ini_cg2d(gG, P)
 px, py = rank % nPx, rank // nPx
 d = Dims(sNx=sNx, sNy=sNy, OLx=2, OLy=2, Nr=NR, nPx=nPx, nPy=nPy, myPx=px, myPy=py)
@@ -47,6 +48,11 @@ rt.set_cg2d_operator({k: (mine(v) if isinstance(v, np.ndarray) else v) for k, v 
 for n in ("uVel", "vVel", "wVel", "theta", "etaN", "surfForcU", "surfForcV"):
     rt.set_field(n, mine(sG[n]))
 rt.fill_field("kappaRU", P["viscAr"]); rt.fill_field("kappaRV", P["viscAr"]); rt.fill_field("kappaRT", P["diffKrT"])
+for n in ("tRef", "sRef", "rF", "rC"):      # linear EOS + CALC_PHI_HYD inputs
+    src = sG.get(n, gG.a.get(n))
+    v = np.zeros(NR + 1)
+    v[:len(src)] = src
+    rt.set_field(n, v)
 for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1", "theta2", "cg2d_b", "cg2d_x"):
     rt.fill_field(n, 0.0)
 res = [distributed.forward_step(it) for it in range(nsteps)]

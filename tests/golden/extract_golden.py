@@ -15,7 +15,7 @@ def parse(exp, out="results/output.txt"):
     txt = open(os.path.join(REF, exp, out)).read()
     g = {}
     m = re.search(r"CG2D normalisation factor =\s*" + NUM, txt)
-    g["cg2dNorm"] = m.group(1)
+    g["cg2dNorm"] = m.group(1) if m else None
     g["sumRHS_rhsMax"] = re.findall(r"cg2d: Sum\(rhs\),rhsMax =\s*" + NUM + r"\s+" + NUM, txt)
     g["cg2d_init_res"] = re.findall(r"cg2d_init_res =\s*" + NUM, txt)
     g["cg2d_iters"] = [int(x) for x in re.findall(r"cg2d_iters\(min,last\) =\s*-?\d+\s+(\d+)", txt)]
@@ -31,7 +31,7 @@ def parse(exp, out="results/output.txt"):
 
 if __name__ == "__main__":
     for exp in ("tutorial_barotropic_gyre", "tutorial_baroclinic_gyre", "global_ocean.90x40x15",
-                "global_ocean.cs32x15", "adjustment.cs-32x32x1"):
+                "global_ocean.cs32x15", "adjustment.cs-32x32x1", "advect_xy"):
         with open(os.path.join(HERE, exp + ".json"), "w") as f:
             json.dump(parse(exp), f, indent=1)
         print("wrote", exp)

@@ -229,3 +229,26 @@ def test_adjustment_cs_monitor_dynstats(ac24, fld, st):
             assert abs(r[fld][st] - float(gv)) < 1e-12 * scale, (fld, st)
         else:
             assert r[fld][st] == pytest.approx(float(gv), rel=2e-13, abs=1e-30), (fld, st)
+
+
+# ---------------------------------------------------------------------------------------
+# verification/advect_xy (salt): multi-dimensional advection GAD_ADVECTION, scheme 33 (DST3 flux limiter),
+# GAD_MULTIDIM_COMPRESSIBLE build, uniform diagonal flow on a doubly periodic grid, 80 steps.
+# ---------------------------------------------------------------------------------------
+def test_advect_xy_salt_statistics_every_printed_digit():
+    from oracle import advect_xy as ax
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "advect_xy.json")))
+    out = ax.run(80)
+    assert len(out) == len(gold["dynstat_salt_sd"]) == 6          # steps 0, 16, ..., 80
+    for r, mx, mn, me, sd in zip(out, gold["dynstat_salt_max"], gold["dynstat_salt_min"], gold["dynstat_salt_mean"],
+                                 gold["dynstat_salt_sd"]):
+        assert (fmt(r["max"], 13), fmt(r["min"], 13), fmt(r["mean"], 13), fmt(r["sd"], 13)) == (mx, mn, me, sd)
+
+
+def test_advect_xy_is_independent_of_the_tiling():
+    """2 x 2 tiles of 10 x 10 instead of 1 x 2 tiles of 20 x 10: same field statistics (the passes only
+    read what the halo exchange provides)."""
+    from oracle import advect_xy as ax
+    a, b = ax.run(32), ax.run(32, nSx=2, nSy=2)
+    for ra, rb in zip(a, b):
+        assert ra["sd"] == pytest.approx(rb["sd"], rel=1e-13) and ra["max"] == rb["max"]
