@@ -833,6 +833,155 @@ __device__ void sr_phase_update(const Cg2dArgs &a, double *r, double beta, doubl
   }
 }
 
+// ---- vectorised CG2D_SR phases: two columns per lane (double2), neighbours by shuffle ------------------
+// Same arithmetic and operation order as the scalar phases above; used when a.vec2 (OLx, PX, sNx even).
+// A 5-point apply of one row: out(i) = W(i)*f(i-1) + W(i+1)*f(i+1) + S(j)*f(j-1) + S(j+1)*f(j+1) + C*f,
+// in the operand order of cg2d_sr.F:340-346 (A) / :307-313 (M: C first).
+struct Row2 {
+  double2 fC, fS, Sj;   // field at rows j, j-1 and the south coefficient S(j), carried down the strip
+};
+
+template <bool CFIRST>
+__device__ __forceinline__ double2 apply5(const Cg2dArgs &a, const Item2 &it, const double *__restrict__ f,
+                                          const double *__restrict__ W, const double *__restrict__ S,
+                                          const double *__restrict__ Cc, size_t idx, Row2 &rw, double2 &fN_out) {
+  const int PX = a.PX;
+  double2 fN = make_double2(0., 0.), Wv = fN, SN = fN, Cv = fN;
+  double fWm = 0., fEm = 0., WEm = 0.;
+  if (it.active) {
+    fN = ld2(f + idx + PX);
+    Wv = ldg2(W + idx);
+    SN = ldg2(S + idx + PX);
+    Cv = ldg2(Cc + idx);
+    if (it.edgeW) fWm = f[idx - 1];
+    if (it.edgeE) { fEm = f[idx + 2]; WEm = __ldg(W + idx + 2); }
+  }
+  double fW = __shfl_up_sync(0xffffffffu, rw.fC.y, 1);
+  double fE = __shfl_down_sync(0xffffffffu, rw.fC.x, 1);
+  double WE = __shfl_down_sync(0xffffffffu, Wv.x, 1);
+  if (it.edgeW) fW = fWm;
+  if (it.edgeE) { fE = fEm; WE = WEm; }
+  double2 o;
+  if (CFIRST) {
+    o.x = Cv.x * rw.fC.x + Wv.x * fW + Wv.y * rw.fC.y + rw.Sj.x * rw.fS.x + SN.x * fN.x;
+    o.y = Cv.y * rw.fC.y + Wv.y * rw.fC.x + WE * fE + rw.Sj.y * rw.fS.y + SN.y * fN.y;
+  } else {
+    o.x = Wv.x * fW + Wv.y * rw.fC.y + rw.Sj.x * rw.fS.x + SN.x * fN.x + Cv.x * rw.fC.x;
+    o.y = Wv.y * rw.fC.x + WE * fE + rw.Sj.y * rw.fS.y + SN.y * fN.y + Cv.y * rw.fC.y;
+  }
+  fN_out = fN;
+  rw.Sj = SN;
+  return o;
+}
+
+__device__ void sr_phase_v2(const Cg2dArgs &a, const double *__restrict__ y, const double *__restrict__ r, double *sm) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  const int PX = a.PX;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    size_t idx = it.base;
+    Row2 rw;
+    rw.fC = rw.fS = rw.Sj = make_double2(0., 0.);
+    if (it.active) { rw.fS = ld2(y + idx - PX); rw.fC = ld2(y + idx); rw.Sj = ldg2(a.aS + idx); }
+    for (int j = it.j0; j <= it.j1; j++, idx += PX) {
+      double2 yN;
+      const double2 vv = apply5<false>(a, it, y, a.aW, a.aS, a.aC, idx, rw, yN);
+      if (it.active) {
+        const double2 rv = ld2(r + idx);
+        st2(a.v + idx, vv);
+        acc[0] += rw.fC.x * rv.x; acc[0] += rw.fC.y * rv.y;
+        acc[1] += rw.fC.x * vv.x; acc[1] += rw.fC.y * vv.y;
+        acc[2] += rv.x * rv.x; acc[2] += rv.y * rv.y;
+      }
+      rw.fS = rw.fC; rw.fC = yN;
+    }
+  }
+  block_partials<3, false>(a, acc, sm);
+}
+
+__device__ void sr_phase_y2(const Cg2dArgs &a, const double *__restrict__ r, double *__restrict__ y,
+                            double *__restrict__ sCopy, double *sm, bool withEta) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  const int PX = a.PX;
+  double acc[1] = {0.0};
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    size_t idx = it.base;
+    Row2 rw;
+    rw.fC = rw.fS = rw.Sj = make_double2(0., 0.);
+    if (it.active) { rw.fS = ld2(r + idx - PX); rw.fC = ld2(r + idx); rw.Sj = ldg2(a.pS + idx); }
+    for (int j = it.j0; j <= it.j1; j++, idx += PX) {
+      double2 rN;
+      const double2 yv = apply5<true>(a, it, r, a.pW, a.pS, a.pC, idx, rw, rN);
+      if (it.active) {
+        st2(y + idx, yv);
+        if (sCopy) { st2(sCopy + idx, yv); push2v(a, it, j, y, yv, sCopy, yv); }
+        else push2v(a, it, j, y, yv, y, yv);
+        acc[0] += yv.x * rw.fC.x; acc[0] += yv.y * rw.fC.y;
+      }
+      rw.fS = rw.fC; rw.fC = rN;
+    }
+  }
+  if (withEta) block_partials<1, false>(a, acc, sm);
+}
+
+__device__ void sr_phase_as2(const Cg2dArgs &a, const double *__restrict__ s, double *sm) {   // q = A s, <s,q>
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  const int PX = a.PX;
+  double acc[1] = {0.0};
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    size_t idx = it.base;
+    Row2 rw;
+    rw.fC = rw.fS = rw.Sj = make_double2(0., 0.);
+    if (it.active) { rw.fS = ld2(s + idx - PX); rw.fC = ld2(s + idx); rw.Sj = ldg2(a.aS + idx); }
+    for (int j = it.j0; j <= it.j1; j++, idx += PX) {
+      double2 sN;
+      const double2 qv = apply5<false>(a, it, s, a.aW, a.aS, a.aC, idx, rw, sN);
+      if (it.active) {
+        st2(a.q + idx, qv);
+        acc[0] += rw.fC.x * qv.x; acc[0] += rw.fC.y * qv.y;
+      }
+      rw.fS = rw.fC; rw.fC = sN;
+    }
+  }
+  block_partials<1, false>(a, acc, sm);
+}
+
+__device__ void sr_phase_update2(const Cg2dArgs &a, double *__restrict__ r, double beta, double sigma, bool startup,
+                                 bool saveMin) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
+  double *s = a.s[0];
+  for (int item = gw; item < a.nItems2; item += nw) {
+    Item2 it = decode_item2(a, item, lane);
+    if (!it.active) continue;           // point-wise: no shuffles in this phase
+    size_t idx = it.base;
+    SR_UNROLL_LOOP
+    for (int j = it.j0; j <= it.j1; j++, idx += a.PX) {
+      double2 xv = ld2(a.x + idx);
+      if (saveMin) st2(a.xmin + idx, xv);
+      double2 sv = ld2(s + idx), qv = ld2(a.q + idx);
+      if (!startup) {
+        const double2 zv = ld2(a.z + idx), vv = ld2(a.v + idx);
+        sv = make_double2(zv.x + beta * sv.x, zv.y + beta * sv.y);
+        qv = make_double2(vv.x + beta * qv.x, vv.y + beta * qv.y);
+        st2(s + idx, sv);
+        st2(a.q + idx, qv);
+      }
+      st2(a.x + idx, make_double2(xv.x + sigma * sv.x, xv.y + sigma * sv.y));
+      const double2 ro = ld2(r + idx);
+      const double2 rv = make_double2(ro.x - sigma * qv.x, ro.y - sigma * qv.y);
+      st2(r + idx, rv);
+      push2v(a, it, j, r, rv, r, rv);
+    }
+  }
+}
+
 __device__ void sr_phase_err(const Cg2dArgs &a, const double *r, double *sm) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
@@ -884,23 +1033,23 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
 
   if (!(err_sq < a.tolSq)) {
     // start-up iteration, cg2d_sr.F:220-291
-    sr_phase_y(a, r, y, s, sm, true);
+    if (a.vec2) sr_phase_y2(a, r, y, s, sm, true); else sr_phase_y(a, r, y, s, sm, true);
     grid.sync();
     grid_totals<1, false>(a, t1, sm, rseq);
     double eta_qrN = t1[0];
     double eta_qrNM1 = eta_qrN;
-    sr_phase_as(a, s, sm);
+    if (a.vec2) sr_phase_as2(a, s, sm); else sr_phase_as(a, s, sm);
     grid.sync();
     grid_totals<1, false>(a, t1, sm, rseq);
     double alpha = t1[0];
     double sigma = eta_qrN / alpha;
-    sr_phase_update(a, r, 0.0, sigma, true, false);
+    if (a.vec2) sr_phase_update2(a, r, 0.0, sigma, true, false); else sr_phase_update(a, r, 0.0, sigma, true, false);
     grid.sync();
     bool converged = false;
     for (it2d = 1; it2d <= a.maxIters - 1; it2d++) {
-      sr_phase_y(a, r, y, nullptr, sm, false);
+      if (a.vec2) sr_phase_y2(a, r, y, nullptr, sm, false); else sr_phase_y(a, r, y, nullptr, sm, false);
       grid.sync();
-      sr_phase_v(a, y, r, sm);
+      if (a.vec2) sr_phase_v2(a, y, r, sm); else sr_phase_v(a, y, r, sm);
       grid.sync();
       grid_totals<3, false>(a, t3, sm, rseq);
       eta_qrN = t3[0];
@@ -914,7 +1063,7 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
       eta_qrNM1 = eta_qrN;
       alpha = delta - (cgBeta * cgBeta) * alpha;
       sigma = eta_qrN / alpha;
-      sr_phase_update(a, r, cgBeta, sigma, false, saveMin);
+      if (a.vec2) sr_phase_update2(a, r, cgBeta, sigma, false, saveMin); else sr_phase_update(a, r, cgBeta, sigma, false, saveMin);
       grid.sync();
     }
     if (!converged) {
@@ -1071,7 +1220,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
     nItems = g.nTiles * nIB * nJB;
   };
   decomp(32, a.nIB, a.nJB, a.RY, a.nItems);
-  a.vec2 = (!sr && g.OLx % 2 == 0 && g.PX % 2 == 0 && g.sNx % 2 == 0 && g.slab % 2 == 0) ? 1 : 0;
+  a.vec2 = (g.OLx % 2 == 0 && g.PX % 2 == 0 && g.sNx % 2 == 0 && g.slab % 2 == 0) ? 1 : 0;
   if (getenv("MITGCM_B200_CG2D_SCALAR")) a.vec2 = 0;
   decomp(64, a.nIB2, a.nJB2, a.RY2, a.nItems2);
   int blocks = std::min(maxBlocks, (std::max(a.nItems, a.vec2 ? a.nItems2 : 0) + CG_WARPS - 1) / CG_WARPS);
@@ -1079,7 +1228,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   a.resident = 0;
   a.resRows = 0;
   size_t dynSmem = 0;
-  if (a.vec2 && a.nItems2 <= blocks * CG_WARPS && !getenv("MITGCM_B200_CG2D_NORESIDENT")) {
+  if (!sr && a.vec2 && a.nItems2 <= blocks * CG_WARPS && !getenv("MITGCM_B200_CG2D_NORESIDENT")) {
     // as many rows of each strip as fit next to a second CTA on the SM (a whole vector of a
     // 2048^2 tile is 227 KB per SM and does not fit: half of every strip stays resident there)
     // (larger carve-outs starve the L1: 100 KB per CTA was measured 25 % slower than none)
