@@ -365,15 +365,18 @@ def read_mitgrid_faces(prefix: str, nFace: int, nFacets: int = 6):
     return faces
 
 
-def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=86164.0) -> Grid:
+def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=86164.0, rSphereFac=1.0,
+                      Bo_surf=None) -> Grid:
     """usingCurvilinearGrid with pkg/exch2: tiles laid out as one row (nSx = nTiles, nSy = 1, the
     reference's own cs32 SIZE.h), metrics from the face files.  Each tile takes its interior plus the
     (sNx+1, sNy+1) row and column the files carry (MDS_FACEF_READ); cell-centred scalars (xC, yC, rA)
     then get their halos from the scalar exch2 exchange and the C-grid pairs (dxC, dyC), (rAw, rAs),
     (dyG, dxG) from the unsigned vector-pair exchange, as in ini_curvilinear_grid.F:360-370.  The A-grid
     (dxF, dyF), B-grid (dxV, dyU) and corner-point (xG, yG, rAz) exchanges of the reference are NOT done:
-    those arrays are valid on 1..sN+1 only (enough for the hot path without viscosity / advection on the
-    cube; MOM_VECINV, which config 4 would need, is not built)."""
+    those arrays are valid on 1..sN+1 only: enough for every interior tendency of MOM_FLUXFORM without
+    viscosity and of MOM_VECINV (vorticity points 1..sN+1; pinned by solid-body.cs-32x32x1).
+    rSphereFac = rSphere / radius_fromHorizGrid rescales lengths and areas (ini_curvilinear_grid.F:375-398);
+    Bo_surf overrides gBaro (uniformLin_PhiSurf in p coordinates: 1/rhoConst, ini_linear_phisurf.F:63-73)."""
     from .exch2 import exchange, exchange_uv, halo_gather_map, uv_gather_map
     assert d.nSy == 1 and d.nSx == topo.nTiles and d.OLx == d.OLy
     g = Grid(d)
@@ -395,18 +398,34 @@ def cubed_sphere_grid(d: Dims, topo, faces, delR, gBaro=9.81, rotationPeriod=861
     for a, b in (("dxC", "dyC"), ("rAw", "rAs"), ("dyG", "dxG")):
         if g.a[a].any():
             exchange_uv(topo, g.a[a][0], g.a[b][0], ox, False, gmuv)
+    if rSphereFac != 1.0:
+        for n in "dxC dyC dxG dyG dxF dyF dxV dyU".split():
+            g.a[n] = g.a[n] * rSphereFac
+        fac2 = rSphereFac * rSphereFac
+        for n in "rA rAz rAw rAs".split():
+            g.a[n] = g.a[n] * fac2
     PI = 3.14159265358979323844
     omega = 2.0 * PI / rotationPeriod
     import math
     g.a["fCori"] = 2.0 * omega * np.vectorize(math.sin)(g.a["yC"] * (2.0 * PI / 360.0))
     g.a["fCoriG"] = 2.0 * omega * np.vectorize(math.sin)(g.a["yG"] * (2.0 * PI / 360.0))
-    g.a["Bo_surf"] = np.full(d.shape2, gBaro)
-    g.a["recip_Bo"] = np.full(d.shape2, 1.0 / gBaro)
+    bo = gBaro if Bo_surf is None else Bo_surf
+    g.a["Bo_surf"] = np.full(d.shape2, bo)
+    g.a["recip_Bo"] = np.full(d.shape2, 1.0 / bo)
     g.a["cosFacU"] = np.ones((d.nSy, d.nSx, d.PY))
     g.a["cosFacV"] = np.ones((d.nSy, d.nSx, d.PY))
+    g.a["omega"] = omega
     g.set_recips()
     set_vertical(g, delR)
     return g
+
+
+def cs_corner_flags(topo):
+    """Per tile: bit mask of the facet corners it owns (1 SW, 2 SE, 4 NE, 8 NW), the test
+    mom_calc_relvort3.F:79-97 / fill_cs_corner_tr_rl.F:62-72 makes from exch2_is{N,S,E,W}edge."""
+    tb = topo.tables()
+    N, S_, E, W = (np.asarray(tb[n]) for n in ("isNedge", "isSedge", "isEedge", "isWedge"))
+    return ((W & S_) * 1 + (E & S_) * 2 + (E & N) * 4 + (W & N) * 8).astype(np.int32)
 
 
 def cube_masks_from_depth(g: Grid, topo, depth_xstack: np.ndarray, hFacMin=1.0, hFacMinDr=0.0) -> None:

@@ -70,6 +70,9 @@ typedef struct {
   int selectKEscheme;
   /* tracers */
   int implicitDiffusion;
+  /* vector-invariant momentum (pkg/mom_vecinv) */
+  int useCoriolis, useAbsVorticity, selectVortScheme, useJamartMomAdv, upwindShear;
+  int highOrderVorticity, upwindVorticity, momImplVertAdv;
 } og_params;
 
 /* ---- eesupp primitives (single process, periodic; nPx=nPy=1) ------------- */
@@ -120,6 +123,18 @@ void og_mom_fluxform(const og_grid *g, const og_params *p, int bi, int bj, int k
                      double *guDiss, double *gvDiss,
                      const double *uVel, const double *vVel, const double *wVel,
                      double *gU, double *gV);
+
+/* ---- MOM_VECINV (pkg/mom_vecinv/mom_vecinv.F:10-1009) ------------------- */
+/* Same conventions as og_mom_fluxform.  csCorners: bit mask of the facet corners this tile owns on
+ * the cubed sphere (1 SW, 2 SE, 4 NE, 8 NW; 0 = not a cube), myFace the facet number.  Returns
+ * non-zero for options that are not restated. */
+int og_mom_vecinv(const og_grid *g, const og_params *p, int bi, int bj, int k,
+                  int iMin, int iMax, int jMin, int jMax,
+                  const double *kappaRU, const double *kappaRV,
+                  const double *fVerUkm, const double *fVerVkm, double *fVerUkp, double *fVerVkp,
+                  double *guDiss, double *gvDiss,
+                  const double *uVel, const double *vVel, const double *wVel,
+                  double *gU, double *gV, int csCorners, int myFace);
 
 /* ---- GAD_CALC_RHS (pkg/generic_advdiff/gad_calc_rhs.F:10-795) ------------ */
 /* One tile, one level, one tracer.  Slab args are PX*PY; TracerN, TracAB,

@@ -540,3 +540,472 @@ void og_mom_fluxform(const og_grid *g, const og_params *p, int bi, int bj, int k
     }
   free(buf);
 }
+
+/* ======================================================================================
+ * MOM_VECINV (pkg/mom_vecinv/mom_vecinv.F:10-1009) and its leaves.  Same scope limits as
+ * above plus: highOrderVorticity / upwindVorticity (MOM_VI_{U,V}_CORIOLIS_C4), variable
+ * viscosity, strain-tension viscosity, Leith-QG, GGL90-Langmuir, NH Coriolis / metric
+ * terms and momImplVertAdv are not restated (the product rejects them).
+ * Cubed sphere: csCorners is a bit mask of the tile's facet corners (1 SW, 2 SE, 4 NE,
+ * 8 NW; 0 on a non-cube topology), myFace the facet number (mom_calc_relvort3.F:79-97).
+ * ====================================================================================== */
+
+/* FILL_CS_CORNER_TR_RL (eesupp/src/fill_cs_corner_tr_rl.F), withSigns = .FALSE. */
+static void fill_cs_corner_tr(const og_dims *d, int fill4dir, int csCorners, double *f) {
+  const int sNx = d->sNx, sNy = d->sNy, OLx = d->OLx, OLy = d->OLy;
+  const size_t px = PXd;
+  if (!csCorners) return;
+  for (int j = 1; j <= OLy; j++)
+    for (int i = 1; i <= OLx; i++) {
+      if (fill4dir == 1) {
+        if (csCorners & 1) f[S(1 - i, 1 - j)] = f[S(1 - j, i)];
+        if (csCorners & 2) f[S(sNx + i, 1 - j)] = f[S(sNx + j, i)];
+        if (csCorners & 8) f[S(1 - i, sNy + j)] = f[S(1 - j, sNy + 1 - i)];
+        if (csCorners & 4) f[S(sNx + i, sNy + j)] = f[S(sNx + j, sNy + 1 - i)];
+      } else {
+        if (csCorners & 1) f[S(1 - i, 1 - j)] = f[S(j, 1 - i)];
+        if (csCorners & 2) f[S(sNx + i, 1 - j)] = f[S(sNx + 1 - j, 1 - i)];
+        if (csCorners & 8) f[S(1 - i, sNy + j)] = f[S(j, sNy + i)];
+        if (csCorners & 4) f[S(sNx + i, sNy + j)] = f[S(sNx + 1 - j, sNy + i)];
+      }
+    }
+}
+
+/* MOM_CALC_HDIV, hDivScheme = 2 (pkg/mom_common/mom_calc_hdiv.F:56-72) */
+static void mom_calc_hdiv2(const og_grid *g, int bi, int bj, int k, const double *uFld, const double *vFld,
+                           double *hDiv) {
+  SETUP
+  for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 1 - OLx; i <= sNx + OLx - 1; i++)
+      hDiv[S(i, j)] = ((uFld[S(i + 1, j)] * G2(g->dyG, i + 1, j) * G3(g->hFacW, i + 1, j, k)
+                      - uFld[S(i, j)] * G2(g->dyG, i, j) * G3(g->hFacW, i, j, k))
+                     + (vFld[S(i, j + 1)] * G2(g->dxG, i, j + 1) * G3(g->hFacS, i, j + 1, k)
+                      - vFld[S(i, j)] * G2(g->dxG, i, j) * G3(g->hFacS, i, j, k)))
+                    * G2(g->recip_rA, i, j) * G3(g->recip_hFacC, i, j, k);
+}
+
+/* MOM_CALC_RELVORT3 (pkg/mom_common/mom_calc_relvort3.F:64-304), CALC_CS_CORNER_EXTENDED undefined */
+static void mom_calc_relvort3(const og_grid *g, int bi, int bj, int k, const double *uFld, const double *vFld,
+                              double *vort3, int csCorners, int myFace) {
+  SETUP
+  (void)k;
+#define VDY(i, j) (vFld[S(i, j)] * G2(g->dyC, i, j))
+#define UDX(i, j) (uFld[S(i, j)] * G2(g->dxC, i, j))
+  for (int j = 2 - OLy; j <= sNy + OLy; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx; i++)
+      vort3[S(i, j)] = G2(g->recip_rAz, i, j) * ((VDY(i, j) - VDY(i - 1, j)) - (UDX(i, j) - UDX(i, j - 1)));
+  if (csCorners & 1) {
+    const int i = 1, j = 1;
+    vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((VDY(i, j) - UDX(i, j)) + UDX(i, j - 1));
+  }
+  if (csCorners & 2) {
+    const int i = sNx + 1, j = 1;
+    if (myFace == 2)
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((-UDX(i, j) - VDY(i - 1, j)) + UDX(i, j - 1));
+    else if (myFace == 4)
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((-VDY(i - 1, j) + UDX(i, j - 1)) - UDX(i, j));
+    else
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((+UDX(i, j - 1) - UDX(i, j)) - VDY(i - 1, j));
+  }
+  if (csCorners & 8) {
+    const int i = 1, j = sNy + 1;
+    if (myFace == 1)
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((+UDX(i, j - 1) + VDY(i, j)) - UDX(i, j));
+    else if (myFace == 3)
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((-UDX(i, j) + UDX(i, j - 1)) + VDY(i, j));
+    else
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((+VDY(i, j) - UDX(i, j)) + UDX(i, j - 1));
+  }
+  if (csCorners & 4) {
+    const int i = sNx + 1, j = sNy + 1;
+    if (myFace % 2 == 1)
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((-UDX(i, j) - VDY(i - 1, j)) + UDX(i, j - 1));
+    else
+      vort3[S(i, j)] = +G2(g->recip_rAz, i, j) * ((+UDX(i, j - 1) - UDX(i, j)) - VDY(i - 1, j));
+  }
+#undef VDY
+#undef UDX
+}
+
+/* MOM_VI_DEL2UV (pkg/mom_vecinv/mom_vi_del2uv.F:78-124); hDiv's facet corners are refilled in place */
+static void mom_vi_del2uv(const og_grid *g, int bi, int bj, int k, double *hDiv, const double *vort3,
+                          const double *hFacZ, double *del2u, double *del2v, int csCorners) {
+  SETUP
+  fill_cs_corner_tr(d, 1, csCorners, hDiv);
+  for (int j = 2 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx - 1; i++)
+      del2u[S(i, j)] = ((hDiv[S(i, j)] - hDiv[S(i - 1, j)]) * G2(g->recip_dxC, i, j)
+                        - G3(g->recip_hFacW, i, j, k)
+                            * (hFacZ[S(i, j + 1)] * vort3[S(i, j + 1)] - hFacZ[S(i, j)] * vort3[S(i, j)])
+                            * G2(g->recip_dyG, i, j))
+                       * G3(g->maskW, i, j, k);
+  fill_cs_corner_tr(d, 2, csCorners, hDiv);
+  for (int j = 2 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx - 1; i++)
+      del2v[S(i, j)] = ((hDiv[S(i, j)] - hDiv[S(i, j - 1)]) * G2(g->recip_dyC, i, j)
+                        + G3(g->recip_hFacS, i, j, k)
+                            * (hFacZ[S(i + 1, j)] * vort3[S(i + 1, j)] - hFacZ[S(i, j)] * vort3[S(i, j)])
+                            * G2(g->recip_dxG, i, j))
+                       * G3(g->maskS, i, j, k);
+}
+
+/* MOM_VI_HDISSIP (pkg/mom_vecinv/mom_vi_hdissip.F:60-271), constant coefficients,
+ * MOM_VI_ORIGINAL_VISCA4 and ISOTROPIC_COS_SCALING undefined */
+static void mom_vi_hdissip(const og_grid *g, const og_params *p, int bi, int bj, int k, const double *hDiv,
+                           const double *vort3, const double *dStar, const double *zStar, const double *hFacZ,
+                           int harmonic, int biharmonic, double *uDissip, double *vDissip) {
+  SETUP
+  for (int j = 2 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx - 1; i++) {
+      const double cU = g->cosFacU[(j + OLy - 1) + offc], cV = g->cosFacV[(j + OLy - 1) + offc];
+      if (harmonic) {
+        const double Dim = hDiv[S(i, j - 1)], Dij = hDiv[S(i, j)], Dmj = hDiv[S(i - 1, j)];
+        const double Zip = hFacZ[S(i, j + 1)] * vort3[S(i, j + 1)], Zij = hFacZ[S(i, j)] * vort3[S(i, j)],
+                     Zpj = hFacZ[S(i + 1, j)] * vort3[S(i + 1, j)];
+        const double uD2 = p->viscAhD * cU * (Dij - Dmj) * G2(g->recip_dxC, i, j)
+                         - p->viscAhZ * G3(g->recip_hFacW, i, j, k) * (Zip - Zij) * G2(g->recip_dyG, i, j);
+        const double vD2 = p->viscAhZ * G3(g->recip_hFacS, i, j, k) * cV * (Zpj - Zij) * G2(g->recip_dxG, i, j)
+                         + p->viscAhD * (Dij - Dim) * G2(g->recip_dyC, i, j);
+        uDissip[S(i, j)] = uD2 * G3(g->maskW, i, j, k);
+        vDissip[S(i, j)] = vD2 * G3(g->maskS, i, j, k);
+      } else {
+        uDissip[S(i, j)] = 0.;
+        vDissip[S(i, j)] = 0.;
+      }
+    }
+  if (biharmonic) {
+    for (int j = 2 - OLy; j <= sNy + OLy - 1; j++)
+      for (int i = 2 - OLx; i <= sNx + OLx - 1; i++) {
+        const double cU = g->cosFacU[(j + OLy - 1) + offc], cV = g->cosFacV[(j + OLy - 1) + offc];
+        const double Dim = dStar[S(i, j - 1)], Dij = dStar[S(i, j)], Dmj = dStar[S(i - 1, j)];
+        const double Zip = hFacZ[S(i, j + 1)] * zStar[S(i, j + 1)], Zij = hFacZ[S(i, j)] * zStar[S(i, j)],
+                     Zpj = hFacZ[S(i + 1, j)] * zStar[S(i + 1, j)];
+        double uD4 = p->viscA4D * cU * (Dij - Dmj) * G2(g->recip_dxC, i, j)
+                   - p->viscA4Z * G3(g->recip_hFacW, i, j, k) * (Zip - Zij) * G2(g->recip_dyG, i, j);
+        double vD4 = p->viscA4Z * G3(g->recip_hFacS, i, j, k) * cV * (Zpj - Zij) * G2(g->recip_dxG, i, j)
+                   + p->viscA4D * (Dij - Dim) * G2(g->recip_dyC, i, j);
+        uD4 = -uD4 * G3(g->maskW, i, j, k);
+        vD4 = -vD4 * G3(g->maskS, i, j, k);
+        uDissip[S(i, j)] = uDissip[S(i, j)] + uD4;
+        vDissip[S(i, j)] = vDissip[S(i, j)] + vD4;
+      }
+  }
+}
+
+/* MOM_VI_CORIOLIS (pkg/mom_vecinv/mom_vi_coriolis.F:48-190) */
+static void mom_vi_coriolis(const og_grid *g, const og_params *p, int bi, int bj, int k, const double *uFld,
+                            const double *vFld, double *uCf, double *vCf) {
+  SETUP
+  const double epsil = 1e-9;
+  const int sch = p->selectCoriScheme;
+#define VDXH(i, j) (vFld[S(i, j)] * G2(g->dxG, i, j) * G3(g->hFacS, i, j, k))
+#define UDYH(i, j) (uFld[S(i, j)] * G2(g->dyG, i, j) * G3(g->hFacW, i, j, k))
+  for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx; i++) {
+      const double f0 = G2(g->fCoriG, i, j), f1 = G2(g->fCoriG, i, j + 1);
+      if (sch == 0) {
+        const double vBarXY = 0.25 * ((vFld[S(i, j)] * G2(g->dxG, i, j) + vFld[S(i - 1, j)] * G2(g->dxG, i - 1, j))
+                                    + (vFld[S(i, j + 1)] * G2(g->dxG, i, j + 1) + vFld[S(i - 1, j + 1)] * G2(g->dxG, i - 1, j + 1)));
+        uCf[S(i, j)] = +0.5 * (f0 + f1) * vBarXY * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      } else if (sch == 1) {
+        const double vBarXY = ((VDXH(i, j) + VDXH(i - 1, j)) + (VDXH(i, j + 1) + VDXH(i - 1, j + 1)))
+            / fmax(epsil, (G3(g->hFacS, i, j, k) + G3(g->hFacS, i - 1, j, k))
+                        + (G3(g->hFacS, i, j + 1, k) + G3(g->hFacS, i - 1, j + 1, k)));
+        uCf[S(i, j)] = +0.5 * (f0 + f1) * vBarXY * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      } else if (sch == 2) {
+        const double vBarXY = 0.25 * ((VDXH(i, j) + VDXH(i - 1, j)) + (VDXH(i, j + 1) + VDXH(i - 1, j + 1)));
+        uCf[S(i, j)] = +0.5 * (f0 + f1) * vBarXY * G2(g->recip_dxC, i, j) * G3(g->recip_hFacW, i, j, k);
+      } else {
+        const double vBarXm = 0.5 * (VDXH(i, j) + VDXH(i - 1, j)), vBarXp = 0.5 * (VDXH(i, j + 1) + VDXH(i - 1, j + 1));
+        uCf[S(i, j)] = +0.5 * (vBarXm * f0 + vBarXp * f1) * G2(g->recip_dxC, i, j) * G3(g->recip_hFacW, i, j, k);
+      }
+    }
+  for (int j = 2 - OLy; j <= sNy + OLy; j++)
+    for (int i = 1 - OLx; i <= sNx + OLx - 1; i++) {
+      const double f0 = G2(g->fCoriG, i, j), f1 = G2(g->fCoriG, i + 1, j);
+      if (sch == 0) {
+        const double uBarXY = 0.25 * ((uFld[S(i, j)] * G2(g->dyG, i, j) + uFld[S(i, j - 1)] * G2(g->dyG, i, j - 1))
+                                    + (uFld[S(i + 1, j)] * G2(g->dyG, i + 1, j) + uFld[S(i + 1, j - 1)] * G2(g->dyG, i + 1, j - 1)));
+        vCf[S(i, j)] = -0.5 * (f0 + f1) * uBarXY * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      } else if (sch == 1) {
+        const double uBarXY = ((UDYH(i, j) + UDYH(i, j - 1)) + (UDYH(i + 1, j) + UDYH(i + 1, j - 1)))
+            / fmax(epsil, (G3(g->hFacW, i, j, k) + G3(g->hFacW, i, j - 1, k))
+                        + (G3(g->hFacW, i + 1, j, k) + G3(g->hFacW, i + 1, j - 1, k)));
+        vCf[S(i, j)] = -0.5 * (f0 + f1) * uBarXY * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      } else if (sch == 2) {
+        const double uBarXY = 0.25 * ((UDYH(i, j) + UDYH(i, j - 1)) + (UDYH(i + 1, j) + UDYH(i + 1, j - 1)));
+        vCf[S(i, j)] = -0.5 * (f0 + f1) * uBarXY * G2(g->recip_dyC, i, j) * G3(g->recip_hFacS, i, j, k);
+      } else {
+        const double uBarYm = 0.5 * (UDYH(i, j) + UDYH(i, j - 1)), uBarYp = 0.5 * (UDYH(i + 1, j) + UDYH(i + 1, j - 1));
+        vCf[S(i, j)] = -0.5 * (uBarYm * f0 + uBarYp * f1) * G2(g->recip_dyC, i, j) * G3(g->recip_hFacS, i, j, k);
+      }
+    }
+}
+
+/* MOM_VI_U_CORIOLIS (pkg/mom_vecinv/mom_vi_u_coriolis.F:54-197), upwindVort3 = .FALSE. */
+static void mom_vi_u_coriolis(const og_grid *g, const og_params *p, int bi, int bj, int k, const double *vFld,
+                              const double *omega3, const double *hFacZ, const double *r_hFacZ, double *uCf) {
+  SETUP
+  const double epsil = 1e-9, oneThird = 1. / 3.;
+  const int sch = p->selectVortScheme;
+  for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+    for (int i = 2 - OLx; i <= sNx + OLx - (sch == 3 ? 1 : 0); i++) {
+      if (sch == 0) {
+        const double vBarXY = 0.25 * ((VDXH(i, j) + VDXH(i - 1, j)) + (VDXH(i, j + 1) + VDXH(i - 1, j + 1)));
+        const double vort3u = 0.5 * (omega3[S(i, j)] * r_hFacZ[S(i, j)] + omega3[S(i, j + 1)] * r_hFacZ[S(i, j + 1)]);
+        uCf[S(i, j)] = +vort3u * vBarXY * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      } else if (sch == 1) {
+        const double vBarXY = 0.5 * ((vFld[S(i, j)] * G2(g->dxG, i, j) * hFacZ[S(i, j)]
+                                    + vFld[S(i - 1, j)] * G2(g->dxG, i - 1, j) * hFacZ[S(i, j)])
+                                   + (vFld[S(i, j + 1)] * G2(g->dxG, i, j + 1) * hFacZ[S(i, j + 1)]
+                                    + vFld[S(i - 1, j + 1)] * G2(g->dxG, i - 1, j + 1) * hFacZ[S(i, j + 1)]))
+                              / fmax(epsil, hFacZ[S(i, j)] + hFacZ[S(i, j + 1)]);
+        const double vort3u = 0.5 * (omega3[S(i, j)] + omega3[S(i, j + 1)]);
+        uCf[S(i, j)] = +vort3u * vBarXY * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      } else if (sch == 2) {
+        const double vBarXm = 0.5 * (VDXH(i, j) + VDXH(i - 1, j)), vBarXp = 0.5 * (VDXH(i, j + 1) + VDXH(i - 1, j + 1));
+        const double vort3u = (vBarXm * r_hFacZ[S(i, j)] * omega3[S(i, j)]
+                             + vBarXp * r_hFacZ[S(i, j + 1)] * omega3[S(i, j + 1)]) * 0.5;
+        uCf[S(i, j)] = +vort3u * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      } else {
+#define RZ(i, j) (r_hFacZ[S(i, j)] * omega3[S(i, j)])
+        const double vort3mj = (RZ(i, j) + (RZ(i, j + 1) + RZ(i - 1, j))) * oneThird * VDXH(i - 1, j);
+        const double vort3ij = (RZ(i, j) + (RZ(i, j + 1) + RZ(i + 1, j))) * oneThird * VDXH(i, j);
+        const double vort3mp = (RZ(i, j + 1) + (RZ(i, j) + RZ(i - 1, j + 1))) * oneThird * VDXH(i - 1, j + 1);
+        const double vort3ip = (RZ(i, j + 1) + (RZ(i, j) + RZ(i + 1, j + 1))) * oneThird * VDXH(i, j + 1);
+        uCf[S(i, j)] = +((vort3mj + vort3ij) + (vort3mp + vort3ip)) * 0.25 * G2(g->recip_dxC, i, j) * G3(g->maskW, i, j, k);
+      }
+    }
+  if (p->useJamartMomAdv)
+    for (int j = 1 - OLy; j <= sNy + OLy - 1; j++)
+      for (int i = 2 - OLx; i <= sNx + OLx - 1; i++)
+        uCf[S(i, j)] = uCf[S(i, j)] * 4. * G3(g->hFacW, i, j, k)
+            / fmax(epsil, (G3(g->hFacS, i, j, k) + G3(g->hFacS, i - 1, j, k))
+                        + (G3(g->hFacS, i, j + 1, k) + G3(g->hFacS, i - 1, j + 1, k)));
+}
+
+/* MOM_VI_V_CORIOLIS (pkg/mom_vecinv/mom_vi_v_coriolis.F:54-197), upwindVort3 = .FALSE. */
+static void mom_vi_v_coriolis(const og_grid *g, const og_params *p, int bi, int bj, int k, const double *uFld,
+                              const double *omega3, const double *hFacZ, const double *r_hFacZ, double *vCf) {
+  SETUP
+  const double epsil = 1e-9, oneThird = 1. / 3.;
+  const int sch = p->selectVortScheme;
+  for (int j = 2 - OLy; j <= sNy + OLy - (sch == 3 ? 1 : 0); j++)
+    for (int i = 1 - OLx; i <= sNx + OLx - 1; i++) {
+      if (sch == 0) {
+        const double uBarXY = 0.25 * ((UDYH(i, j) + UDYH(i, j - 1)) + (UDYH(i + 1, j) + UDYH(i + 1, j - 1)));
+        const double vort3v = 0.5 * (omega3[S(i, j)] * r_hFacZ[S(i, j)] + omega3[S(i + 1, j)] * r_hFacZ[S(i + 1, j)]);
+        vCf[S(i, j)] = -vort3v * uBarXY * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      } else if (sch == 1) {
+        const double uBarXY = 0.5 * ((uFld[S(i, j)] * G2(g->dyG, i, j) * hFacZ[S(i, j)]
+                                    + uFld[S(i, j - 1)] * G2(g->dyG, i, j - 1) * hFacZ[S(i, j)])
+                                   + (uFld[S(i + 1, j)] * G2(g->dyG, i + 1, j) * hFacZ[S(i + 1, j)]
+                                    + uFld[S(i + 1, j - 1)] * G2(g->dyG, i + 1, j - 1) * hFacZ[S(i + 1, j)]))
+                              / fmax(epsil, hFacZ[S(i, j)] + hFacZ[S(i + 1, j)]);
+        const double vort3v = 0.5 * (omega3[S(i, j)] + omega3[S(i + 1, j)]);
+        vCf[S(i, j)] = -vort3v * uBarXY * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      } else if (sch == 2) {
+        const double uBarYm = 0.5 * (UDYH(i, j) + UDYH(i, j - 1)), uBarYp = 0.5 * (UDYH(i + 1, j) + UDYH(i + 1, j - 1));
+        const double vort3v = (uBarYm * r_hFacZ[S(i, j)] * omega3[S(i, j)]
+                             + uBarYp * r_hFacZ[S(i + 1, j)] * omega3[S(i + 1, j)]) * 0.5;
+        vCf[S(i, j)] = -vort3v * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      } else {
+        const double vort3im = (RZ(i, j) + (RZ(i + 1, j) + RZ(i, j - 1))) * oneThird * UDYH(i, j - 1);
+        const double vort3ij = (RZ(i, j) + (RZ(i + 1, j) + RZ(i, j + 1))) * oneThird * UDYH(i, j);
+        const double vort3pm = (RZ(i + 1, j) + (RZ(i, j) + RZ(i + 1, j - 1))) * oneThird * UDYH(i + 1, j - 1);
+        const double vort3pj = (RZ(i + 1, j) + (RZ(i, j) + RZ(i + 1, j + 1))) * oneThird * UDYH(i + 1, j);
+        vCf[S(i, j)] = -((vort3im + vort3ij) + (vort3pm + vort3pj)) * 0.25 * G2(g->recip_dyC, i, j) * G3(g->maskS, i, j, k);
+      }
+    }
+  if (p->useJamartMomAdv)
+    for (int j = 2 - OLy; j <= sNy + OLy - 1; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx - 1; i++)
+        vCf[S(i, j)] = vCf[S(i, j)] * 4. * G3(g->hFacS, i, j, k)
+            / fmax(epsil, (G3(g->hFacW, i, j, k) + G3(g->hFacW, i, j - 1, k))
+                        + (G3(g->hFacW, i + 1, j, k) + G3(g->hFacW, i + 1, j - 1, k)));
+}
+#undef RZ
+#undef VDXH
+#undef UDYH
+
+/* MOM_VI_U_VERTSHEAR / MOM_VI_V_VERTSHEAR (pkg/mom_vecinv/mom_vi_{u,v}_vertshear.F:41-133) */
+static void mom_vi_vertshear(const og_grid *g, const og_params *p, int bi, int bj, int k, int isV,
+                             const double *fld, const double *wVel, double *shear) {
+  SETUP
+  const int rAdvAreaWeight = !(p->selectKEscheme == 1 || p->selectKEscheme == 3);
+  const int Kp1 = (k + 1 < Nr) ? k + 1 : Nr, Km1 = (k - 1 > 1) ? k - 1 : 1;
+  const double mask_Kp1 = (k == Nr) ? 0. : 1., mask_Km1 = (k == 1) ? 0. : 1.;
+  const int di = isV ? 0 : 1, dj = isV ? 1 : 0;
+  const double *rrA = isV ? g->recip_rAs : g->recip_rAw;
+  const double *rh = isV ? g->recip_hFacS : g->recip_hFacW;
+  for (int j = 1 - OLy + dj; j <= sNy + OLy; j++)
+    for (int i = 1 - OLx + di; i <= sNx + OLx; i++) {
+      double wBm, wBp;
+      if (rAdvAreaWeight) {
+        wBm = 0.5 * (G3(wVel, i, j, k) * G2(g->rA, i, j) * G3(g->maskC, i, j, Km1)
+                   + G3(wVel, i - di, j - dj, k) * G2(g->rA, i - di, j - dj) * G3(g->maskC, i - di, j - dj, Km1))
+              * mask_Km1 * G2(rrA, i, j);
+        wBp = 0.5 * (G3(wVel, i, j, Kp1) * G2(g->rA, i, j) + G3(wVel, i - di, j - dj, Kp1) * G2(g->rA, i - di, j - dj))
+              * mask_Kp1 * G2(rrA, i, j);
+      } else {
+        wBm = 0.5 * (G3(wVel, i, j, k) * G3(g->maskC, i, j, Km1)
+                   + G3(wVel, i - di, j - dj, k) * G3(g->maskC, i - di, j - dj, Km1)) * mask_Km1;
+        wBp = 0.5 * (G3(wVel, i, j, Kp1) + G3(wVel, i - di, j - dj, Kp1)) * mask_Kp1;
+      }
+      const double fZm = (G3(fld, i, j, k) - mask_Km1 * G3(fld, i, j, Km1)) * p->rkSign;
+      const double fZp = (mask_Kp1 * G3(fld, i, j, Kp1) - G3(fld, i, j, k)) * p->rkSign;
+      if (p->upwindShear)
+        shear[S(i, j)] = -0.5 * ((wBp * fZp + wBm * fZm) + (fabs(wBp) * fZp - fabs(wBm) * fZm))
+                         * G3(rh, i, j, k) * g->recip_drF[k - 1];
+      else
+        shear[S(i, j)] = -0.5 * (wBp * fZp + wBm * fZm) * G3(rh, i, j, k) * g->recip_drF[k - 1];
+    }
+}
+
+int og_mom_vecinv(const og_grid *g, const og_params *p, int bi, int bj, int k,
+                  int iMin, int iMax, int jMin, int jMax,
+                  const double *kappaRU, const double *kappaRV,
+                  const double *fVerUkm, const double *fVerVkm, double *fVerUkp, double *fVerVkp,
+                  double *guDiss, double *gvDiss,
+                  const double *uVel, const double *vVel, const double *wVel,
+                  double *gU, double *gV, int csCorners, int myFace) {
+  SETUP
+  if (p->highOrderVorticity || p->upwindVorticity || p->momImplVertAdv) return 1;
+  if (p->selectVortScheme < 0 || p->selectVortScheme > 3 || p->selectCoriScheme < 0 || p->selectCoriScheme > 3) return 2;
+  const size_t ns = px * py;
+  double *buf = (double *)calloc(ns * 19, sizeof(double));
+  double *vF = buf, *vrF = buf + ns, *uCf = buf + 2 * ns, *vCf = buf + 3 * ns, *del2u = buf + 4 * ns,
+         *del2v = buf + 5 * ns, *dStar = buf + 6 * ns, *zStar = buf + 7 * ns, *hFacZ = buf + 8 * ns,
+         *h0FacZ = buf + 9 * ns, *r_hFacZ = buf + 10 * ns, *uFld = buf + 11 * ns, *vFld = buf + 12 * ns,
+         *cDrag = buf + 13 * ns, *KE = buf + 14 * ns, *omega3 = buf + 15 * ns, *vort3 = buf + 16 * ns,
+         *vort3BC = buf + 17 * ns, *hDiv = buf + 18 * ns;
+  /* mom_vecinv.F:196-250 */
+  FORALL { guDiss[S(i, j)] = 0.; gvDiss[S(i, j)] = 0.; }
+  const double ArDudrFac = p->vfFacMom * 1., ArDvdrFac = p->vfFacMom * 1.;
+  const double sideMaskFac = p->no_slip_sides ? p->sideDragFactor : 0.;
+  const int bottomDragTerms = (p->selectImplicitDrag == 0 &&
+      (p->no_slip_bottom || p->selectBotDragQuadr >= 0 || p->bottomDragLinear != 0.));
+  const int harmonic = (p->viscAhD != 0. || p->viscAhZ != 0.);     /* useHarmonicVisc, ini_parms / set_parms */
+  const int biharmonic = p->useBiharmonicVisc;
+
+  mom_calc_hfacz(g, bi, bj, k, hFacZ, r_hFacZ);                    /* :266 */
+  FORALL { uFld[S(i, j)] = G3(uVel, i, j, k); vFld[S(i, j)] = G3(vVel, i, j, k); }
+  mom_calc_ke(g, bi, bj, k, p->selectKEscheme, uFld, vFld, KE);    /* :287 */
+  mom_calc_relvort3(g, bi, bj, k, uFld, vFld, vort3, csCorners, myFace);
+  FORALL {                                                         /* :292-300 */
+    vort3BC[S(i, j)] = vort3[S(i, j)];
+    if (hFacZ[S(i, j)] == 0.) { vort3BC[S(i, j)] = sideMaskFac * vort3BC[S(i, j)]; vort3[S(i, j)] = 0.; }
+  }
+
+  if (p->momViscosity) {                                           /* :308-663 */
+    FORALL h0FacZ[S(i, j)] = hFacZ[S(i, j)];
+    mom_calc_hdiv2(g, bi, bj, k, uFld, vFld, hDiv);
+    if (biharmonic) {
+      mom_vi_del2uv(g, bi, bj, k, hDiv, vort3, hFacZ, del2u, del2v, csCorners);
+      mom_calc_hdiv2(g, bi, bj, k, del2u, del2v, dStar);
+      mom_calc_relvort3(g, bi, bj, k, del2u, del2v, zStar, csCorners, myFace);
+    }
+    mom_vi_hdissip(g, p, bi, bj, k, hDiv, vort3, dStar, zStar, hFacZ, harmonic, biharmonic, guDiss, gvDiss);
+    /* ---- U */
+    if (!p->implicitViscosity) {
+      mom_rviscflux(g, p, bi, bj, k + 1, 0, uVel, kappaRU, vrF);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) fVerUkp[S(i, j)] = ArDudrFac * vrF[S(i, j)];
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++)
+          guDiss[S(i, j)] = guDiss[S(i, j)] - G3(g->recip_hFacW, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rAw, i, j)
+                                                  * (fVerUkp[S(i, j)] - fVerUkm[S(i, j)]) * p->rkSign;
+    }
+    if (p->no_slip_sides) {
+      mom_sidedrag(g, p, bi, bj, k, 0, uFld, del2u, h0FacZ, vF);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) guDiss[S(i, j)] = guDiss[S(i, j)] + vF[S(i, j)];
+    }
+    if (bottomDragTerms) {
+      mom_botdrag_coeff(g, p, bi, bj, k, 0, uFld, vFld, kappaRU, KE, cDrag);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) {
+          vF[S(i, j)] = -cDrag[S(i, j)] * uFld[S(i, j)] * G3(g->recip_hFacW, i, j, k) * g->recip_drF[k - 1];
+          guDiss[S(i, j)] = guDiss[S(i, j)] + vF[S(i, j)];
+        }
+    }
+    /* ---- V */
+    if (!p->implicitViscosity) {
+      mom_rviscflux(g, p, bi, bj, k + 1, 1, vVel, kappaRV, vrF);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) fVerVkp[S(i, j)] = ArDvdrFac * vrF[S(i, j)];
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++)
+          gvDiss[S(i, j)] = gvDiss[S(i, j)] - G3(g->recip_hFacS, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rAs, i, j)
+                                                  * (fVerVkp[S(i, j)] - fVerVkm[S(i, j)]) * p->rkSign;
+    }
+    if (p->no_slip_sides) {
+      mom_sidedrag(g, p, bi, bj, k, 1, vFld, del2v, h0FacZ, vF);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) gvDiss[S(i, j)] = gvDiss[S(i, j)] + vF[S(i, j)];
+    }
+    if (bottomDragTerms) {
+      mom_botdrag_coeff(g, p, bi, bj, k, 1, uFld, vFld, kappaRV, KE, cDrag);
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++) {
+          vF[S(i, j)] = -cDrag[S(i, j)] * vFld[S(i, j)] * G3(g->recip_hFacS, i, j, k) * g->recip_drF[k - 1];
+          gvDiss[S(i, j)] = gvDiss[S(i, j)] + vF[S(i, j)];
+        }
+    }
+  }
+
+  /* :672-673 MOM_CALC_ABSVORT3 */
+  if (p->useAbsVorticity) {
+    const double nonLinFac = p->momAdvection ? 1. : 0., useCoriolisFac = p->useCoriolis ? 1. : 0.;
+    FORALL omega3[S(i, j)] = G2(g->fCoriG, i, j) * useCoriolisFac + vort3[S(i, j)] * nonLinFac;
+  }
+  /* :683-738 Coriolis */
+  if (p->useCoriolis && !(p->useCDscheme || (p->useAbsVorticity && p->momAdvection))) {
+    if (p->useAbsVorticity) {
+      mom_vi_u_coriolis(g, p, bi, bj, k, vFld, omega3, hFacZ, r_hFacZ, uCf);
+      mom_vi_v_coriolis(g, p, bi, bj, k, uFld, omega3, hFacZ, r_hFacZ, vCf);
+    } else {
+      mom_vi_coriolis(g, p, bi, bj, k, uFld, vFld, uCf, vCf);
+    }
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) { G3(gU, i, j, k) = uCf[S(i, j)]; G3(gV, i, j, k) = vCf[S(i, j)]; }
+  } else {
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) { G3(gU, i, j, k) = 0.; G3(gV, i, j, k) = 0.; }
+  }
+  /* :745-884 advection */
+  if (p->momAdvection) {
+    const double *w3 = p->useAbsVorticity ? omega3 : vort3;
+    mom_vi_u_coriolis(g, p, bi, bj, k, vFld, w3, hFacZ, r_hFacZ, uCf);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gU, i, j, k) = G3(gU, i, j, k) + uCf[S(i, j)];
+    mom_vi_v_coriolis(g, p, bi, bj, k, uFld, w3, hFacZ, r_hFacZ, vCf);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gV, i, j, k) = G3(gV, i, j, k) + vCf[S(i, j)];
+    mom_vi_vertshear(g, p, bi, bj, k, 0, uVel, wVel, uCf);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gU, i, j, k) = G3(gU, i, j, k) + uCf[S(i, j)];
+    mom_vi_vertshear(g, p, bi, bj, k, 1, vVel, wVel, vCf);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gV, i, j, k) = G3(gV, i, j, k) + vCf[S(i, j)];
+    /* MOM_VI_{U,V}_GRAD_KE */
+    for (int j = 1 - OLy; j <= sNy + OLy; j++)
+      for (int i = 2 - OLx; i <= sNx + OLx; i++)
+        uCf[S(i, j)] = -G2(g->recip_dxC, i, j) * (KE[S(i, j)] - KE[S(i - 1, j)]) * G3(g->maskW, i, j, k);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gU, i, j, k) = G3(gU, i, j, k) + uCf[S(i, j)];
+    for (int j = 2 - OLy; j <= sNy + OLy; j++)
+      for (int i = 1 - OLx; i <= sNx + OLx; i++)
+        vCf[S(i, j)] = -G2(g->recip_dyC, i, j) * (KE[S(i, j)] - KE[S(i, j - 1)]) * G3(g->maskS, i, j, k);
+    for (int j = jMin; j <= jMax; j++)
+      for (int i = iMin; i <= iMax; i++) G3(gV, i, j, k) = G3(gV, i, j, k) + vCf[S(i, j)];
+  }
+  /* :922-927 */
+  for (int j = jMin; j <= jMax; j++)
+    for (int i = iMin; i <= iMax; i++) {
+      G3(gU, i, j, k) = G3(gU, i, j, k) * G3(g->maskW, i, j, k);
+      G3(gV, i, j, k) = G3(gV, i, j, k) * G3(g->maskS, i, j, k);
+    }
+  free(buf);
+  return 0;
+}

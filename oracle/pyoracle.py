@@ -44,7 +44,8 @@ PARAM_D = ("deltaTMom deltaTFreeSurf freeSurfFac implicSurfPress implicDiv2DFlow
 PARAM_I = ("momAdvection momViscosity useBiharmonicVisc implicitViscosity no_slip_sides no_slip_bottom "
            "bottomVisc_pCell selectBotDragQuadr selectImplicitDrag useCDscheme selectCoriScheme "
            "selectMetricTerms usingSphericalPolarGrid rigidLid select_rStar selectKEscheme "
-           "implicitDiffusion").split()
+           "implicitDiffusion useCoriolis useAbsVorticity selectVortScheme useJamartMomAdv upwindShear "
+           "highOrderVorticity upwindVorticity momImplVertAdv").split()
 
 
 class ParamS(C.Structure):
@@ -64,7 +65,8 @@ DEFAULT_PARAMS = dict(
     mtFacMom=1.0, momAdvection=1, momViscosity=1, useBiharmonicVisc=0, implicitViscosity=0,
     no_slip_sides=1, no_slip_bottom=1, bottomVisc_pCell=0, selectBotDragQuadr=-1, selectImplicitDrag=0,
     useCDscheme=0, selectCoriScheme=0, selectMetricTerms=0, usingSphericalPolarGrid=0, rigidLid=0,
-    select_rStar=0, selectKEscheme=0, implicitDiffusion=0)
+    select_rStar=0, selectKEscheme=0, implicitDiffusion=0, useCoriolis=1, useAbsVorticity=0, selectVortScheme=1,
+    useJamartMomAdv=0, upwindShear=0, highOrderVorticity=0, upwindVorticity=0, momImplVertAdv=0)
 
 
 def ptr(a):
@@ -142,6 +144,15 @@ class Oracle:
                                  ptr(kappaRU), ptr(kappaRV), ptr(fVerUkm), ptr(fVerVkm), ptr(fVerUkp),
                                  ptr(fVerVkp), ptr(guDiss), ptr(gvDiss), ptr(uVel), ptr(vVel), ptr(wVel),
                                  ptr(gU), ptr(gV))
+
+    def mom_vecinv(self, bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm,
+                   fVerUkp, fVerVkp, guDiss, gvDiss, uVel, vVel, wVel, gU, gV, csCorners=0, myFace=0):
+        rc = self.lib.og_mom_vecinv(C.byref(self.g), C.byref(self.p), bi, bj, k, iMin, iMax, jMin, jMax,
+                                    ptr(kappaRU), ptr(kappaRV), ptr(fVerUkm), ptr(fVerVkm), ptr(fVerUkp),
+                                    ptr(fVerVkp), ptr(guDiss), ptr(gvDiss), ptr(uVel), ptr(vVel), ptr(wVel),
+                                    ptr(gU), ptr(gV), int(csCorners), int(myFace))
+        if rc:
+            raise ValueError(f"og_mom_vecinv: option not restated (rc={rc})")
 
     # ---- tracers ----
     def calc_adv_flow(self, bi, bj, k, uVel, vVel, wVel, xA, yA, maskUp, uFld, vFld, wFld,

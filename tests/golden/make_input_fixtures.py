@@ -31,9 +31,26 @@ def cs32_fixture():
     print("wrote cs32_grid_bathy.npz")
 
 
+def solid_body_fixture():
+    """solid-body.cs-32x32x1: its own tile00N.mitgrid files (16 records, no angles; a different cs32
+    grid from grid_cs32.face00N.bin) and the initial tracer S_init.bin, as one compressed npz."""
+    import numpy as np
+    sb = os.path.join(REF, "solid-body.cs-32x32x1/input")
+    names = "xC yC dxF dyF rA xG yG dxV dyU rAz dxC dyC rAw rAs dxG dyG".split()
+    out = {}
+    for f in range(6):
+        a = np.fromfile(os.path.join(sb, f"tile{f + 1:03d}.mitgrid"), ">f8").reshape(16, 33, 33).astype(np.float64)
+        for q, n in enumerate(names):
+            out[f"{n}_{f}"] = a[q]
+    out["S_init"] = np.fromfile(os.path.join(sb, "S_init.bin"), ">f8").reshape(192, 32).astype(np.float64)   # W2_mapIO = 1: facets stacked along y
+    np.savez_compressed(os.path.join(HERE, "solid_body_cs32.npz"), **out)
+    print("wrote solid_body_cs32.npz")
+
+
 if __name__ == "__main__":
     os.makedirs(HERE, exist_ok=True)
     cs32_fixture()
+    solid_body_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

@@ -252,3 +252,50 @@ def test_advect_xy_is_independent_of_the_tiling():
     a, b = ax.run(32), ax.run(32, nSx=2, nSy=2)
     for ra, rb in zip(a, b):
         assert ra["sd"] == pytest.approx(rb["sd"], rel=1e-13) and ra["max"] == rb["max"]
+
+
+# ---------------------------------------------------------------------------------------
+# verification/solid-body.cs-32x32x1: solid-body rotation of a one-layer atmosphere on the cs32 cube,
+# vectorInvariantMomentum = T.  Pins MOM_VECINV (relative vorticity with the three-cell facet corners,
+# KE gradient, vorticity advection, Coriolis) and GAD_CALC_RHS on the cube (passive salt), 25 steps.
+# ---------------------------------------------------------------------------------------
+from oracle import solid_body_cs as sbc
+
+GOLDS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solid-body.cs-32x32x1.json")))
+
+
+@pytest.fixture(scope="module")
+def sb25():
+    return sbc.run(25)
+
+
+def test_solid_body_cs_cg2d_lines_all_steps(sb25):
+    """cg2dNorm, iteration counts, cg2d_init_res and rhsMax: every printed digit for all 25 steps
+    (one unit in the last place allowed); Sum(rhs) is round-off of a 7e4 field and compared absolutely."""
+    norm, out = sb25
+    assert fmt(norm, 16) == GOLDS["cg2dNorm"]          # 9.8929536739060584E-06
+    assert [r["numIters"] for r in out[1:]] == GOLDS["cg2d_iters"]
+    exact = 0
+    for r, ir, (sr, rm) in zip(out[1:], GOLDS["cg2d_init_res"], GOLDS["sumRHS_rhsMax"]):
+        assert r["firstResidual"] == pytest.approx(float(ir), rel=2e-14)
+        assert r["rhsMax"] == pytest.approx(float(rm), rel=2e-14)
+        assert abs(r["sumRHS"] - float(sr)) < 1e-15 * 7.4e4 * 6144
+        exact += fmt(r["firstResidual"], 14) == ir and fmt(r["rhsMax"], 14) == rm
+    assert exact >= 23
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel", "salt"])
+@pytest.mark.parametrize("st", ["max", "min", "mean", "sd"])
+def test_solid_body_cs_monitor_dynstats(sb25, fld, st):
+    """Initial state and 25 steps: max / min / sd and the means of u, v, salt to every printed digit (one
+    unit in the 13th place allowed); the means of eta and w cancel to round-off (1e-11 of 1e4, 1e-17) and
+    are compared absolutely against 1e-13 of the field's magnitude."""
+    _, out = sb25
+    gold = GOLDS[f"dynstat_{fld}_{st}"]
+    assert len(gold) == len(out) == 26
+    for r, gv in zip(out, gold):
+        if st == "mean" and fld in ("eta", "wvel"):
+            scale = max(abs(r[fld]["max"]), abs(r[fld]["min"]), 1e-300)
+            assert abs(r[fld][st] - float(gv)) < 1e-13 * scale, (fld, st)
+        else:
+            assert r[fld][st] == pytest.approx(float(gv), rel=2e-13, abs=1e-30), (fld, st)
