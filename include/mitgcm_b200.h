@@ -65,6 +65,9 @@ enum {
   MI_MOMFORCING, MI_MOMDISSIP_IN_AB, MI_TEMPADVSCHEME, MI_TEMPVERTADVSCHEME, MI_USESRCGSOLVER,
   MI_TEMPSTEPPING, MI_NITER0, MI_PROFILE,
   MI_EXACTCONSERV, MI_BUOYANCYLINEAR, MI_DOTHETACLIMRELAX, MI_GAD_MULTIDIM_COMPRESSIBLE,
+  /* pkg/mom_vecinv */
+  MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
+  MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
   MI_NI_END
 };
 
@@ -155,6 +158,23 @@ void mom_fluxform_b200_(const int *bi, const int *bj, const int *k, const int *i
                         const double *myTime, const int *myIter, const int *myThid,
                         const double *uVel, const double *vVel, const double *wVel,
                         double *gU, double *gV);
+
+/* ---- MOM_VECINV ------------------------------------------
+ * Same argument list as pkg/mom_vecinv/mom_vecinv.F:10-16 (caller dynamics.F:527), followed by the
+ * COMMON /DYNVARS_R/ arrays and by what MOM_CALC_RELVORT3 (mom_calc_relvort3.F:79-97) and
+ * FILL_CS_CORNER_TR_RL read from W2_EXCH2_TOPOLOGY.h for this tile: csCorners = bit mask of the
+ * facet corners it owns (1 SW, 2 SE, 4 NE, 8 NW; 0 when .NOT.useCubedSphereExchange) and
+ * myFace = exch2_myFace(W2_myTileList(bi,bj)).  Run-time switches: MI_USECORIOLIS,
+ * MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_SELECTKESCHEME, MI_SELECTCORISCHEME,
+ * MI_USEJAMARTMOMADV, MI_UPWINDSHEAR and the viscosity / drag parameters of MOM_FLUXFORM. */
+void mom_vecinv_b200_(const int *bi, const int *bj, const int *k, const int *iMin, const int *iMax,
+                      const int *jMin, const int *jMax,
+                      const double *kappaRU, const double *kappaRV,
+                      const double *fVerUkm, const double *fVerVkm, double *fVerUkp, double *fVerVkp,
+                      double *guDiss, double *gvDiss,
+                      const double *myTime, const int *myIter, const int *myThid,
+                      const double *uVel, const double *vVel, const double *wVel,
+                      double *gU, double *gV, const int *csCorners, const int *myFace);
 
 /* ---- resident time step ----------------------------------
  * One model step on the device mirrors in the order of model/src/forward_step.F (non-staggered):

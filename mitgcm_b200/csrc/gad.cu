@@ -64,6 +64,7 @@ bool make_tile_grid(int bi, int bj, TileGrid &t) {
   t.recip_dxC = f2(MG_RECIP_DXC); t.recip_dyC = f2(MG_RECIP_DYC); t.recip_dxF = f2(MG_RECIP_DXF);
   t.recip_dyF = f2(MG_RECIP_DYF); t.recip_dxV = f2(MG_RECIP_DXV); t.recip_dyU = f2(MG_RECIP_DYU);
   t.recip_rA = f2(MG_RECIP_RA); t.recip_rAw = f2(MG_RECIP_RAW); t.recip_rAs = f2(MG_RECIP_RAS);
+  t.recip_dxG = f2(MG_RECIP_DXG); t.recip_dyG = f2(MG_RECIP_DYG); t.recip_rAz = f2(MG_RECIP_RAZ); t.fCoriG = f2(MG_FCORIG);
   t.fCori = f2(MG_FCORI); t.tanPhiAtU = f2(MG_TANPHIATU); t.tanPhiAtV = f2(MG_TANPHIATV);
   double *cu = field(MG_COSFACU), *cv = field(MG_COSFACV);
   t.cosFacU = cu ? cu + (size_t)g.PY * tile : nullptr;

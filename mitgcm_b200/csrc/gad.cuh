@@ -23,6 +23,7 @@ struct TileGrid {
   const double *dxC, *dyC, *dxG, *dyG, *dxF, *dyF, *dxV, *dyU, *rA, *rAw, *rAs;
   const double *recip_dxC, *recip_dyC, *recip_dxF, *recip_dyF, *recip_dxV, *recip_dyU, *recip_rA, *recip_rAw,
       *recip_rAs;
+  const double *recip_dxG, *recip_dyG, *recip_rAz, *fCoriG;   // vorticity-point metrics (MOM_VECINV)
   const double *fCori, *tanPhiAtU, *tanPhiAtV;
   const double *cosFacU, *cosFacV;                        // (PY) per tile
   const double *drF, *drC, *recip_drF, *recip_drC;        // vertical

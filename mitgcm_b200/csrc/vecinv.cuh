@@ -1,0 +1,412 @@
+// vecinv.cuh -- MOM_VECINV (pkg/mom_vecinv/mom_vecinv.F:10-1009) and the leaves it calls
+// (pkg/mom_vecinv: mom_vi_coriolis.F, mom_vi_{u,v}_coriolis.F, mom_vi_{u,v}_grad_ke.F,
+// mom_vi_{u,v}_vertshear.F, mom_vi_hdissip.F, mom_vi_del2uv.F; pkg/mom_common: mom_calc_hfacz.F,
+// mom_calc_ke.F, mom_calc_relvort3.F, mom_calc_hdiv.F, mom_calc_absvort3.F, mom_{u,v}_rviscflux.F,
+// mom_{u,v}_sidedrag.F, mom_{u,v}_botdrag_coeff.F; eesupp/src/fill_cs_corner_tr_rl.F).
+// SURVEY.md section 8(f) rank 2.  Two stencil levels (vorticity / KE / divergence, then the tendencies)
+// are staged through per-level scratch slabs, two more (del2u/del2v, then dStar/zStar) with
+// biharmonic viscosity: the slabs of one level stay in L2 between the launches.
+// Expression order follows the Fortran (-fmad=false): bit-identical to oracle/mom_oracle.c
+// (og_mom_vecinv), which is pinned to verification/solid-body.cs-32x32x1/results/output.txt.
+// Not on the B200 path (rejected by the entry point): highOrderVorticity / upwindVorticity
+// (MOM_VI_{U,V}_CORIOLIS_C4), momImplVertAdv, variable and strain-tension viscosity, Leith-QG,
+// NH Coriolis / metric terms, GGL90-Langmuir, r* and sigma coordinates, OBCS, shelf ice.
+#pragma once
+#include "mom.cuh"
+
+namespace mg {
+
+struct ViPar {
+  MomPar m;
+  int useCoriolis, useAbsVorticity, selectVortScheme, useJamartMomAdv, upwindShear, selectKEscheme;
+  int harmonic;             // useHarmonicVisc: viscAh != 0
+  int csCorners, myFace;    // facet corners this tile owns (1 SW, 2 SE, 4 NE, 8 NW), facet number
+  int iMin, iMax, jMin, jMax;
+};
+
+// per-level scratch slabs (PX*PY each)
+struct ViScratch {
+  double *hFacZ, *KE, *vort3, *hDiv, *del2u, *del2v, *dStar, *zStar, *omega3;
+};
+
+#define VU(i, j) st.u[g.s3(i, j, k)]
+#define VV(i, j) st.v[g.s3(i, j, k)]
+
+// MOM_CALC_KE (mom_calc_ke.F:55-125), zero outside 1-OL..sN+OL-1 like the zero-initialised slab
+__device__ inline double vi_ke(const TileGrid &g, const MomState &st, int KEscheme, int k, int i, int j) {
+  if (i > g.sNx + g.OLx - 1 || j > g.sNy + g.OLy - 1) return 0.;
+  const double u0 = VU(i, j), u1 = VU(i + 1, j), v0 = VV(i, j), v1 = VV(i, j + 1);
+  if (KEscheme == -1) return 0.125 * ((u0 + u1) * (u0 + u1) + (v0 + v1) * (v0 + v1));
+  if (KEscheme == 0) return 0.25 * ((u0 * u0 + u1 * u1) + (v0 * v0 + v1 * v1));
+  if (KEscheme == 1)
+    return 0.25 * ((u0 * u0 * g.rAw[g.s(i, j)] + u1 * u1 * g.rAw[g.s(i + 1, j)]) +
+                   (v0 * v0 * g.rAs[g.s(i, j)] + v1 * v1 * g.rAs[g.s(i, j + 1)])) * g.recip_rA[g.s(i, j)];
+  if (KEscheme == 2)
+    return 0.25 * ((u0 * u0 * g.hFacW[g.s3(i, j, k)] + u1 * u1 * g.hFacW[g.s3(i + 1, j, k)]) +
+                   (v0 * v0 * g.hFacS[g.s3(i, j, k)] + v1 * v1 * g.hFacS[g.s3(i, j + 1, k)])) * g.recip_hFacC[g.s3(i, j, k)];
+  return 0.25 * ((u0 * u0 * g.hFacW[g.s3(i, j, k)] * g.rAw[g.s(i, j)] + u1 * u1 * g.hFacW[g.s3(i + 1, j, k)] * g.rAw[g.s(i + 1, j)]) +
+                 (v0 * v0 * g.hFacS[g.s3(i, j, k)] * g.rAs[g.s(i, j)] + v1 * v1 * g.hFacS[g.s3(i, j + 1, k)] * g.rAs[g.s(i, j + 1)])) *
+         g.recip_hFacC[g.s3(i, j, k)] * g.recip_rA[g.s(i, j)];
+}
+
+// MOM_CALC_RELVORT3 (mom_calc_relvort3.F:64-304) of a slab pair (uF, vF), CALC_CS_CORNER_EXTENDED undefined
+__device__ inline double vi_relvort3(const TileGrid &g, const double *uF, const double *vF, int csCorners, int myFace, int i, int j) {
+  if (i < 2 - g.OLx || j < 2 - g.OLy) return 0.;
+  const double rz = g.recip_rAz[g.s(i, j)];
+  const double vdy = vF[g.s(i, j)] * g.dyC[g.s(i, j)], vdym = vF[g.s(i - 1, j)] * g.dyC[g.s(i - 1, j)];
+  const double udx = uF[g.s(i, j)] * g.dxC[g.s(i, j)], udxm = uF[g.s(i, j - 1)] * g.dxC[g.s(i, j - 1)];
+  if ((csCorners & 1) && i == 1 && j == 1) return +rz * ((vdy - udx) + udxm);
+  if ((csCorners & 2) && i == g.sNx + 1 && j == 1) {
+    if (myFace == 2) return +rz * ((-udx - vdym) + udxm);
+    if (myFace == 4) return +rz * ((-vdym + udxm) - udx);
+    return +rz * ((+udxm - udx) - vdym);
+  }
+  if ((csCorners & 8) && i == 1 && j == g.sNy + 1) {
+    if (myFace == 1) return +rz * ((+udxm + vdy) - udx);
+    if (myFace == 3) return +rz * ((-udx + udxm) + vdy);
+    return +rz * ((+vdy - udx) + udxm);
+  }
+  if ((csCorners & 4) && i == g.sNx + 1 && j == g.sNy + 1) {
+    if (myFace % 2 == 1) return +rz * ((-udx - vdym) + udxm);
+    return +rz * ((+udxm - udx) - vdym);
+  }
+  return rz * ((vdy - vdym) - (udx - udxm));
+}
+
+// MOM_CALC_HDIV, hDivScheme = 2 (mom_calc_hdiv.F:56-72) of a slab pair
+__device__ inline double vi_hdiv(const TileGrid &g, const double *uF, const double *vF, int k, int i, int j) {
+  if (i > g.sNx + g.OLx - 1 || j > g.sNy + g.OLy - 1) return 0.;
+  return ((uF[g.s(i + 1, j)] * g.dyG[g.s(i + 1, j)] * g.hFacW[g.s3(i + 1, j, k)] - uF[g.s(i, j)] * g.dyG[g.s(i, j)] * g.hFacW[g.s3(i, j, k)]) +
+          (vF[g.s(i, j + 1)] * g.dxG[g.s(i, j + 1)] * g.hFacS[g.s3(i, j + 1, k)] - vF[g.s(i, j)] * g.dxG[g.s(i, j)] * g.hFacS[g.s3(i, j, k)])) *
+         g.recip_rA[g.s(i, j)] * g.recip_hFacC[g.s3(i, j, k)];
+}
+
+// FILL_CS_CORNER_TR_RL (fill_cs_corner_tr_rl.F:74-156) as a read map: the value the slab holds at (i,j)
+// after the facet corners this tile owns were refilled for direction `dir` (1: x, 2: y); 0: untouched.
+__device__ inline double vi_corner_read(const TileGrid &g, const double *f, int csCorners, int dir, int i, int j) {
+  if (dir && csCorners) {
+    const int sNx = g.sNx, sNy = g.sNy;
+    if (i < 1 && j < 1 && (csCorners & 1)) {
+      const int a = 1 - i, b = 1 - j;
+      return dir == 1 ? f[g.s(1 - b, a)] : f[g.s(b, 1 - a)];
+    }
+    if (i > sNx && j < 1 && (csCorners & 2)) {
+      const int a = i - sNx, b = 1 - j;
+      return dir == 1 ? f[g.s(sNx + b, a)] : f[g.s(sNx + 1 - b, 1 - a)];
+    }
+    if (i < 1 && j > sNy && (csCorners & 8)) {
+      const int a = 1 - i, b = j - sNy;
+      return dir == 1 ? f[g.s(1 - b, sNy + 1 - a)] : f[g.s(b, sNy + a)];
+    }
+    if (i > sNx && j > sNy && (csCorners & 4)) {
+      const int a = i - sNx, b = j - sNy;
+      return dir == 1 ? f[g.s(sNx + b, sNy + 1 - a)] : f[g.s(sNx + 1 - b, sNy + a)];
+    }
+  }
+  return f[g.s(i, j)];
+}
+
+// ---- stage 1: hFacZ, KE, vort3 (masked at hFacZ = 0), hDiv over the whole slab -----------------
+__global__ void __launch_bounds__(256) vi_stage1_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j);
+  const double hz = mom_hfacz(g, k, i, j);
+  w.hFacZ[s] = hz;
+  w.KE[s] = vi_ke(g, st, p.selectKEscheme, k, i, j);
+  const double *uF = st.u + g.slab * (size_t)(k - 1), *vF = st.v + g.slab * (size_t)(k - 1);
+  double z = vi_relvort3(g, uF, vF, p.csCorners, p.myFace, i, j);
+  if (hz == 0.) z = 0.;                                   // mom_vecinv.F:292-300
+  w.vort3[s] = z;
+  // MOM_CALC_ABSVORT3 (mom_calc_absvort3.F:34-46)
+  w.omega3[s] = g.fCoriG[s] * (p.useCoriolis ? 1. : 0.) + z * (p.m.momAdvection ? 1. : 0.);
+  w.hDiv[s] = p.m.momViscosity ? vi_hdiv(g, uF, vF, k, i, j) : 0.;
+}
+
+// ---- stage 2 (biharmonic): MOM_VI_DEL2UV (mom_vi_del2uv.F:78-124) --------------------------------
+__global__ void __launch_bounds__(256) vi_del2_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j);
+  double du = 0., dv = 0.;
+  if (i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1 && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1) {
+    const size_t s3 = g.s3(i, j, k);
+    const int c = p.csCorners;
+    du = ((vi_corner_read(g, w.hDiv, c, 1, i, j) - vi_corner_read(g, w.hDiv, c, 1, i - 1, j)) * g.recip_dxC[s] -
+          g.recip_hFacW[s3] * (w.hFacZ[g.s(i, j + 1)] * w.vort3[g.s(i, j + 1)] - w.hFacZ[s] * w.vort3[s]) * g.recip_dyG[s]) *
+         g.maskW[s3];
+    dv = ((vi_corner_read(g, w.hDiv, c, 2, i, j) - vi_corner_read(g, w.hDiv, c, 2, i, j - 1)) * g.recip_dyC[s] +
+          g.recip_hFacS[s3] * (w.hFacZ[g.s(i + 1, j)] * w.vort3[g.s(i + 1, j)] - w.hFacZ[s] * w.vort3[s]) * g.recip_dxG[s]) *
+         g.maskS[s3];
+  }
+  w.del2u[s] = du;
+  w.del2v[s] = dv;
+}
+
+// ---- stage 3 (biharmonic): dStar, zStar (mom_vecinv.F:390-395) ----------------------------------
+__global__ void __launch_bounds__(256) vi_star_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j);
+  w.dStar[s] = vi_hdiv(g, w.del2u, w.del2v, k, i, j);
+  w.zStar[s] = vi_relvort3(g, w.del2u, w.del2v, p.csCorners, p.myFace, i, j);
+}
+
+// MOM_VI_U_CORIOLIS / MOM_VI_V_CORIOLIS (mom_vi_{u,v}_coriolis.F:54-197), upwindVort3 = .FALSE.
+__device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const double *om,
+                                       const double *hFacZ, int k, int i, int j) {
+  const double epsil = 1e-9, oneThird = 1. / 3.;
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  auto vdxh = [&](int ii, int jj) { return VV(ii, jj) * g.dxG[g.s(ii, jj)] * g.hFacS[g.s3(ii, jj, k)]; };
+  auto rz = [&](int ii, int jj) {
+    const double h = hFacZ[g.s(ii, jj)];
+    return (h == 0. ? 0. : 1. / h) * om[g.s(ii, jj)];
+  };
+  auto rh = [&](int ii, int jj) { const double h = hFacZ[g.s(ii, jj)]; return h == 0. ? 0. : 1. / h; };
+  double r;
+  const int sch = p.selectVortScheme;
+  if (sch == 3 && i > g.sNx + g.OLx - 1) return 0.;
+  if (sch == 0) {
+    const double vBarXY = 0.25 * ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1)));
+    const double vort3u = 0.5 * (om[s] * rh(i, j) + om[g.s(i, j + 1)] * rh(i, j + 1));
+    r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
+  } else if (sch == 1) {
+    const double h0 = hFacZ[s], h1 = hFacZ[g.s(i, j + 1)];
+    const double vBarXY = 0.5 * ((VV(i, j) * g.dxG[s] * h0 + VV(i - 1, j) * g.dxG[g.s(i - 1, j)] * h0) +
+                                 (VV(i, j + 1) * g.dxG[g.s(i, j + 1)] * h1 + VV(i - 1, j + 1) * g.dxG[g.s(i - 1, j + 1)] * h1)) /
+                          fmax(epsil, h0 + h1);
+    const double vort3u = 0.5 * (om[s] + om[g.s(i, j + 1)]);
+    r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
+  } else if (sch == 2) {
+    const double vBarXm = 0.5 * (vdxh(i, j) + vdxh(i - 1, j)), vBarXp = 0.5 * (vdxh(i, j + 1) + vdxh(i - 1, j + 1));
+    const double vort3u = (vBarXm * rh(i, j) * om[s] + vBarXp * rh(i, j + 1) * om[g.s(i, j + 1)]) * 0.5;
+    r = +vort3u * g.recip_dxC[s] * g.maskW[s3];
+  } else {
+    const double vort3mj = (rz(i, j) + (rz(i, j + 1) + rz(i - 1, j))) * oneThird * vdxh(i - 1, j);
+    const double vort3ij = (rz(i, j) + (rz(i, j + 1) + rz(i + 1, j))) * oneThird * vdxh(i, j);
+    const double vort3mp = (rz(i, j + 1) + (rz(i, j) + rz(i - 1, j + 1))) * oneThird * vdxh(i - 1, j + 1);
+    const double vort3ip = (rz(i, j + 1) + (rz(i, j) + rz(i + 1, j + 1))) * oneThird * vdxh(i, j + 1);
+    r = +((vort3mj + vort3ij) + (vort3mp + vort3ip)) * 0.25 * g.recip_dxC[s] * g.maskW[s3];
+  }
+  if (p.useJamartMomAdv && i <= g.sNx + g.OLx - 1)
+    r = r * 4. * g.hFacW[s3] /
+        fmax(epsil, (g.hFacS[s3] + g.hFacS[g.s3(i - 1, j, k)]) + (g.hFacS[g.s3(i, j + 1, k)] + g.hFacS[g.s3(i - 1, j + 1, k)]));
+  return r;
+}
+__device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const double *om,
+                                       const double *hFacZ, int k, int i, int j) {
+  const double epsil = 1e-9, oneThird = 1. / 3.;
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  auto udyh = [&](int ii, int jj) { return VU(ii, jj) * g.dyG[g.s(ii, jj)] * g.hFacW[g.s3(ii, jj, k)]; };
+  auto rh = [&](int ii, int jj) { const double h = hFacZ[g.s(ii, jj)]; return h == 0. ? 0. : 1. / h; };
+  auto rz = [&](int ii, int jj) { return rh(ii, jj) * om[g.s(ii, jj)]; };
+  double r;
+  const int sch = p.selectVortScheme;
+  if (sch == 3 && j > g.sNy + g.OLy - 1) return 0.;
+  if (sch == 0) {
+    const double uBarXY = 0.25 * ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1)));
+    const double vort3v = 0.5 * (om[s] * rh(i, j) + om[g.s(i + 1, j)] * rh(i + 1, j));
+    r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
+  } else if (sch == 1) {
+    const double h0 = hFacZ[s], h1 = hFacZ[g.s(i + 1, j)];
+    const double uBarXY = 0.5 * ((VU(i, j) * g.dyG[s] * h0 + VU(i, j - 1) * g.dyG[g.s(i, j - 1)] * h0) +
+                                 (VU(i + 1, j) * g.dyG[g.s(i + 1, j)] * h1 + VU(i + 1, j - 1) * g.dyG[g.s(i + 1, j - 1)] * h1)) /
+                          fmax(epsil, h0 + h1);
+    const double vort3v = 0.5 * (om[s] + om[g.s(i + 1, j)]);
+    r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
+  } else if (sch == 2) {
+    const double uBarYm = 0.5 * (udyh(i, j) + udyh(i, j - 1)), uBarYp = 0.5 * (udyh(i + 1, j) + udyh(i + 1, j - 1));
+    const double vort3v = (uBarYm * rh(i, j) * om[s] + uBarYp * rh(i + 1, j) * om[g.s(i + 1, j)]) * 0.5;
+    r = -vort3v * g.recip_dyC[s] * g.maskS[s3];
+  } else {
+    const double vort3im = (rz(i, j) + (rz(i + 1, j) + rz(i, j - 1))) * oneThird * udyh(i, j - 1);
+    const double vort3ij = (rz(i, j) + (rz(i + 1, j) + rz(i, j + 1))) * oneThird * udyh(i, j);
+    const double vort3pm = (rz(i + 1, j) + (rz(i, j) + rz(i + 1, j - 1))) * oneThird * udyh(i + 1, j - 1);
+    const double vort3pj = (rz(i + 1, j) + (rz(i, j) + rz(i + 1, j + 1))) * oneThird * udyh(i + 1, j);
+    r = -((vort3im + vort3ij) + (vort3pm + vort3pj)) * 0.25 * g.recip_dyC[s] * g.maskS[s3];
+  }
+  if (p.useJamartMomAdv && j <= g.sNy + g.OLy - 1)
+    r = r * 4. * g.hFacS[s3] /
+        fmax(epsil, (g.hFacW[s3] + g.hFacW[g.s3(i, j - 1, k)]) + (g.hFacW[g.s3(i + 1, j, k)] + g.hFacW[g.s3(i + 1, j - 1, k)]));
+  return r;
+}
+
+// MOM_VI_CORIOLIS (mom_vi_coriolis.F:48-190)
+__device__ inline void vi_coriolis(const TileGrid &g, const MomState &st, int sch, int k, int i, int j, double &uCf, double &vCf) {
+  const double epsil = 1e-9;
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  auto vdxh = [&](int ii, int jj) { return VV(ii, jj) * g.dxG[g.s(ii, jj)] * g.hFacS[g.s3(ii, jj, k)]; };
+  auto udyh = [&](int ii, int jj) { return VU(ii, jj) * g.dyG[g.s(ii, jj)] * g.hFacW[g.s3(ii, jj, k)]; };
+  {
+    const double f0 = g.fCoriG[s], f1 = g.fCoriG[g.s(i, j + 1)];
+    if (sch == 0) {
+      const double vBarXY = 0.25 * ((VV(i, j) * g.dxG[s] + VV(i - 1, j) * g.dxG[g.s(i - 1, j)]) +
+                                    (VV(i, j + 1) * g.dxG[g.s(i, j + 1)] + VV(i - 1, j + 1) * g.dxG[g.s(i - 1, j + 1)]));
+      uCf = +0.5 * (f0 + f1) * vBarXY * g.recip_dxC[s] * g.maskW[s3];
+    } else if (sch == 1) {
+      const double vBarXY = ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1))) /
+                            fmax(epsil, (g.hFacS[s3] + g.hFacS[g.s3(i - 1, j, k)]) + (g.hFacS[g.s3(i, j + 1, k)] + g.hFacS[g.s3(i - 1, j + 1, k)]));
+      uCf = +0.5 * (f0 + f1) * vBarXY * g.recip_dxC[s] * g.maskW[s3];
+    } else if (sch == 2) {
+      const double vBarXY = 0.25 * ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1)));
+      uCf = +0.5 * (f0 + f1) * vBarXY * g.recip_dxC[s] * g.recip_hFacW[s3];
+    } else {
+      const double vBarXm = 0.5 * (vdxh(i, j) + vdxh(i - 1, j)), vBarXp = 0.5 * (vdxh(i, j + 1) + vdxh(i - 1, j + 1));
+      uCf = +0.5 * (vBarXm * f0 + vBarXp * f1) * g.recip_dxC[s] * g.recip_hFacW[s3];
+    }
+  }
+  {
+    const double f0 = g.fCoriG[s], f1 = g.fCoriG[g.s(i + 1, j)];
+    if (sch == 0) {
+      const double uBarXY = 0.25 * ((VU(i, j) * g.dyG[s] + VU(i, j - 1) * g.dyG[g.s(i, j - 1)]) +
+                                    (VU(i + 1, j) * g.dyG[g.s(i + 1, j)] + VU(i + 1, j - 1) * g.dyG[g.s(i + 1, j - 1)]));
+      vCf = -0.5 * (f0 + f1) * uBarXY * g.recip_dyC[s] * g.maskS[s3];
+    } else if (sch == 1) {
+      const double uBarXY = ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1))) /
+                            fmax(epsil, (g.hFacW[s3] + g.hFacW[g.s3(i, j - 1, k)]) + (g.hFacW[g.s3(i + 1, j, k)] + g.hFacW[g.s3(i + 1, j - 1, k)]));
+      vCf = -0.5 * (f0 + f1) * uBarXY * g.recip_dyC[s] * g.maskS[s3];
+    } else if (sch == 2) {
+      const double uBarXY = 0.25 * ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1)));
+      vCf = -0.5 * (f0 + f1) * uBarXY * g.recip_dyC[s] * g.recip_hFacS[s3];
+    } else {
+      const double uBarYm = 0.5 * (udyh(i, j) + udyh(i, j - 1)), uBarYp = 0.5 * (udyh(i + 1, j) + udyh(i + 1, j - 1));
+      vCf = -0.5 * (uBarYm * f0 + uBarYp * f1) * g.recip_dyC[s] * g.recip_hFacS[s3];
+    }
+  }
+}
+
+// MOM_VI_U_VERTSHEAR / MOM_VI_V_VERTSHEAR (mom_vi_{u,v}_vertshear.F:41-133)
+__device__ inline double vi_vertshear(const TileGrid &g, const MomState &st, const ViPar &p, int isV, int k, int i, int j) {
+  const int Nr = g.Nr;
+  const bool rAdvAreaWeight = !(p.selectKEscheme == 1 || p.selectKEscheme == 3);
+  const int Kp1 = min(k + 1, Nr), Km1 = max(k - 1, 1);
+  const double mask_Kp1 = (k == Nr) ? 0. : 1., mask_Km1 = (k == 1) ? 0. : 1.;
+  const int di = isV ? 0 : 1, dj = isV ? 1 : 0;
+  const double *fld = isV ? st.v : st.u;
+  const double rrA = (isV ? g.recip_rAs : g.recip_rAw)[g.s(i, j)];
+  const double rh = (isV ? g.recip_hFacS : g.recip_hFacW)[g.s3(i, j, k)];
+  double wBm, wBp;
+  if (rAdvAreaWeight) {
+    wBm = 0.5 * (st.w[g.s3(i, j, k)] * g.rA[g.s(i, j)] * g.maskC[g.s3(i, j, Km1)] +
+                 st.w[g.s3(i - di, j - dj, k)] * g.rA[g.s(i - di, j - dj)] * g.maskC[g.s3(i - di, j - dj, Km1)]) * mask_Km1 * rrA;
+    wBp = 0.5 * (st.w[g.s3(i, j, Kp1)] * g.rA[g.s(i, j)] + st.w[g.s3(i - di, j - dj, Kp1)] * g.rA[g.s(i - di, j - dj)]) * mask_Kp1 * rrA;
+  } else {
+    wBm = 0.5 * (st.w[g.s3(i, j, k)] * g.maskC[g.s3(i, j, Km1)] + st.w[g.s3(i - di, j - dj, k)] * g.maskC[g.s3(i - di, j - dj, Km1)]) * mask_Km1;
+    wBp = 0.5 * (st.w[g.s3(i, j, Kp1)] + st.w[g.s3(i - di, j - dj, Kp1)]) * mask_Kp1;
+  }
+  const double fZm = (fld[g.s3(i, j, k)] - mask_Km1 * fld[g.s3(i, j, Km1)]) * p.m.rkSign;
+  const double fZp = (mask_Kp1 * fld[g.s3(i, j, Kp1)] - fld[g.s3(i, j, k)]) * p.m.rkSign;
+  if (p.upwindShear)
+    return -0.5 * ((wBp * fZp + wBm * fZm) + (fabs(wBp) * fZp - fabs(wBm) * fZm)) * rh * g.recip_drF[k - 1];
+  return -0.5 * (wBp * fZp + wBm * fZm) * rh * g.recip_drF[k - 1];
+}
+
+// MOM_{U,V}_SIDEDRAG with the vector-invariant del2u / del2v slabs (sideDragFactor > 0, constant viscosity)
+__device__ inline double vi_sidedrag(const TileGrid &g, const MomState &st, const ViPar &p, const ViScratch &w, int isV, int k, int i, int j) {
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  if (!isV) {
+    const double hS = g.hFacW[s3] - w.hFacZ[s], hN = g.hFacW[s3] - w.hFacZ[g.s(i, j + 1)];
+    const double d2 = p.m.useBiharmonicVisc ? w.del2u[s] : 0.;
+    const double t = p.m.viscAhZ * VU(i, j) - p.m.viscA4Z * d2;
+    return -g.recip_hFacW[s3] * g.recip_drF[k - 1] * g.recip_rAw[s] *
+           (hS * g.dxV[s] * g.recip_dyU[s] * t + hN * g.dxV[g.s(i, j + 1)] * g.recip_dyU[g.s(i, j + 1)] * t) * g.drF[k - 1] *
+           p.m.sideDragFactor;
+  }
+  const double cf = g.cosFacV[j + g.OLy - 1];
+  const double hW = g.hFacS[s3] - w.hFacZ[s], hE = g.hFacS[s3] - w.hFacZ[g.s(i + 1, j)];
+  const double d2 = p.m.useBiharmonicVisc ? w.del2v[s] : 0.;
+  const double t = p.m.viscAhZ * VV(i, j) * cf - p.m.viscA4Z * d2 * cf;
+  return -g.recip_hFacS[s3] * g.recip_drF[k - 1] * g.recip_rAs[s] *
+         (hW * g.dyU[s] * g.recip_dxV[s] * t + hE * g.dyU[g.s(i + 1, j)] * g.recip_dxV[g.s(i + 1, j)] * t) * g.drF[k - 1] *
+         p.m.sideDragFactor;
+}
+
+// ---- final stage: tendencies (mom_vecinv.F:308-927) ------------------------------------------------
+__global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w,
+                                                      const double *fVerUkm, const double *fVerVkm, double *fVerUkp,
+                                                      double *fVerVkp, double *guDiss, double *gvDiss, double *gU, double *gV) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  const MomPar &m = p.m;
+  const bool inRange = i >= p.iMin && i <= p.iMax && j >= p.jMin && j <= p.jMax;
+  double uD = 0., vD = 0.;
+  if (m.momViscosity) {
+    // MOM_VI_HDISSIP (mom_vi_hdissip.F:60-271) on its own range, constant coefficients
+    if (i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1 && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1) {
+      const double cU = g.cosFacU[j + g.OLy - 1], cV = g.cosFacV[j + g.OLy - 1];
+      const int dir = (m.useBiharmonicVisc && p.csCorners) ? 2 : 0;   // hDiv keeps MOM_VI_DEL2UV's last corner fill
+      if (p.harmonic) {
+        const double Dim = vi_corner_read(g, w.hDiv, p.csCorners, dir, i, j - 1), Dij = vi_corner_read(g, w.hDiv, p.csCorners, dir, i, j),
+                     Dmj = vi_corner_read(g, w.hDiv, p.csCorners, dir, i - 1, j);
+        const double Zip = w.hFacZ[g.s(i, j + 1)] * w.vort3[g.s(i, j + 1)], Zij = w.hFacZ[s] * w.vort3[s],
+                     Zpj = w.hFacZ[g.s(i + 1, j)] * w.vort3[g.s(i + 1, j)];
+        const double uD2 = m.viscAhD * cU * (Dij - Dmj) * g.recip_dxC[s] - m.viscAhZ * g.recip_hFacW[s3] * (Zip - Zij) * g.recip_dyG[s];
+        const double vD2 = m.viscAhZ * g.recip_hFacS[s3] * cV * (Zpj - Zij) * g.recip_dxG[s] + m.viscAhD * (Dij - Dim) * g.recip_dyC[s];
+        uD = uD2 * g.maskW[s3];
+        vD = vD2 * g.maskS[s3];
+      }
+      if (m.useBiharmonicVisc) {
+        const double Dim = w.dStar[g.s(i, j - 1)], Dij = w.dStar[s], Dmj = w.dStar[g.s(i - 1, j)];
+        const double Zip = w.hFacZ[g.s(i, j + 1)] * w.zStar[g.s(i, j + 1)], Zij = w.hFacZ[s] * w.zStar[s],
+                     Zpj = w.hFacZ[g.s(i + 1, j)] * w.zStar[g.s(i + 1, j)];
+        double uD4 = m.viscA4D * cU * (Dij - Dmj) * g.recip_dxC[s] - m.viscA4Z * g.recip_hFacW[s3] * (Zip - Zij) * g.recip_dyG[s];
+        double vD4 = m.viscA4Z * g.recip_hFacS[s3] * cV * (Zpj - Zij) * g.recip_dxG[s] + m.viscA4D * (Dij - Dim) * g.recip_dyC[s];
+        uD4 = -uD4 * g.maskW[s3];
+        vD4 = -vD4 * g.maskS[s3];
+        uD = uD + uD4;
+        vD = vD + vD4;
+      }
+    }
+    if (inRange) {
+      const double rhW = g.recip_hFacW[s3], rhS = g.recip_hFacS[s3], rdrF = g.recip_drF[k - 1];
+      if (!m.implicitViscosity) {
+        const double up = m.vfFacMom * 1. * mom_u_rvisc(g, st, m, k + 1, i, j);
+        fVerUkp[s] = up;
+        uD = uD - rhW * rdrF * g.recip_rAw[s] * (up - fVerUkm[s]) * m.rkSign;
+      }
+      if (m.no_slip_sides) uD = uD + vi_sidedrag(g, st, p, w, 0, k, i, j);
+      if (m.bottomDragTerms) uD = uD + (-mom_botdrag(g, st, m, k, 0, i, j, w.KE) * VU(i, j) * rhW * rdrF);
+      if (!m.implicitViscosity) {
+        const double vp = m.vfFacMom * 1. * mom_v_rvisc(g, st, m, k + 1, i, j);
+        fVerVkp[s] = vp;
+        vD = vD - rhS * rdrF * g.recip_rAs[s] * (vp - fVerVkm[s]) * m.rkSign;
+      }
+      if (m.no_slip_sides) vD = vD + vi_sidedrag(g, st, p, w, 1, k, i, j);
+      if (m.bottomDragTerms) vD = vD + (-mom_botdrag(g, st, m, k, 1, i, j, w.KE) * VV(i, j) * rhS * rdrF);
+    }
+  }
+  guDiss[s] = uD;
+  gvDiss[s] = vD;
+  if (!inRange) return;
+  // ---- Coriolis and advection (mom_vecinv.F:672-884)
+  double tU = 0., tV = 0.;
+  if (p.useCoriolis && !(m.useCDscheme || (p.useAbsVorticity && m.momAdvection))) {
+    if (p.useAbsVorticity) {
+      tU = vi_u_coriolis(g, st, p, w.omega3, w.hFacZ, k, i, j);
+      tV = vi_v_coriolis(g, st, p, w.omega3, w.hFacZ, k, i, j);
+    } else {
+      vi_coriolis(g, st, m.selectCoriScheme, k, i, j, tU, tV);
+    }
+  }
+  if (m.momAdvection) {
+    const double *w3 = p.useAbsVorticity ? w.omega3 : w.vort3;
+    tU = tU + vi_u_coriolis(g, st, p, w3, w.hFacZ, k, i, j);
+    tV = tV + vi_v_coriolis(g, st, p, w3, w.hFacZ, k, i, j);
+    tU = tU + vi_vertshear(g, st, p, 0, k, i, j);
+    tV = tV + vi_vertshear(g, st, p, 1, k, i, j);
+    tU = tU + (-g.recip_dxC[s] * (w.KE[s] - w.KE[g.s(i - 1, j)]) * g.maskW[s3]);
+    tV = tV + (-g.recip_dyC[s] * (w.KE[s] - w.KE[g.s(i, j - 1)]) * g.maskS[s3]);
+  }
+  gU[s3] = tU * g.maskW[s3];
+  gV[s3] = tV * g.maskS[s3];
+}
+
+#undef VU
+#undef VV
+
+}  // namespace mg

@@ -188,6 +188,18 @@ def mom_fluxform(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, f
     _check()
 
 
+def mom_vecinv(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm, fVerUkp, fVerVkp,
+               guDiss, gvDiss, uVel, vVel, wVel, gU, gV, csCorners=0, myFace=0, myTime=0.0, myIter=0, myThid=1):
+    """CALL MOM_VECINV(...) -- pkg/mom_vecinv/mom_vecinv.F:10-16, followed by the COMMON /DYNVARS_R/
+    arrays and the tile's facet-corner mask / facet number (cubed sphere; 0, 0 otherwise)."""
+    L = _lib.lib()
+    L.mom_vecinv_b200_(_i(bi), _i(bj), _i(k), _i(iMin), _i(iMax), _i(jMin), _i(jMax), _addr(kappaRU),
+                       _addr(kappaRV), _addr(fVerUkm), _addr(fVerVkm), _addr(fVerUkp), _addr(fVerVkp),
+                       _addr(guDiss), _addr(gvDiss), _d(myTime), _i(myIter), _i(myThid), _addr(uVel),
+                       _addr(vVel), _addr(wVel), _addr(gU), _addr(gV), _i(csCorners), _i(myFace))
+    _check()
+
+
 def fill_field(name: str, value: float):
     ierr = C.c_int(0)
     _lib.lib().mitgcm_b200_fill_field_(C.byref(C.c_int(field_id(name))), _d(value), C.byref(ierr))

@@ -74,6 +74,9 @@ class CudaEngine:
     def mom_fluxform(self, *a):
         return (self.rt if self.use_mom else self.fb).mom_fluxform(*a)
 
+    def mom_vecinv(self, *a):
+        return (self.rt if self.use_mom else self.fb).mom_vecinv(*a)
+
     def cg2d(self, op, b, x, numIters, nIterMin=-1, sr=False):
         if not self.use_cg2d:
             return self.fb.cg2d(op, b, x, numIters, nIterMin, sr=sr)
