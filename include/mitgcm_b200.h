@@ -68,6 +68,7 @@ enum {
   /* pkg/mom_vecinv */
   MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
   MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
+  MI_VECTORINVARIANTMOMENTUM,
   MI_NI_END
 };
 
@@ -175,6 +176,10 @@ void mom_vecinv_b200_(const int *bi, const int *bj, const int *k, const int *iMi
                       const double *myTime, const int *myIter, const int *myThid,
                       const double *uVel, const double *vVel, const double *wVel,
                       double *gU, double *gV, const int *csCorners, const int *myFace);
+
+/* Facet data of the local tiles for the resident step with MI_VECTORINVARIANTMOMENTUM on the cubed
+ * sphere: csCorners(nSx*nSy) and myFace(nSx*nSy) as in mom_vecinv_b200_ (tiles bi fast). */
+void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr);
 
 /* ---- resident time step ----------------------------------
  * One model step on the device mirrors in the order of model/src/forward_step.F (non-staggered):

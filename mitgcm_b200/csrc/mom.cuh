@@ -198,9 +198,9 @@ __device__ inline double mom_v_sidedrag(const TileGrid &g, const MomState &st, c
          g.drF[k - 1] * p.sideDragFactor;
 }
 // MOM_U_BOTDRAG_COEFF / MOM_V_BOTDRAG_COEFF (z coordinates, inp_KE = .TRUE.)
-// KEslab: MOM_VECINV passes the KE it computed with selectKEscheme; MOM_FLUXFORM (nullptr) uses KEscheme = 2
+// haveKs: MOM_VECINV passes KE(i,j) + KE(i-di,j-dj) computed with selectKEscheme; MOM_FLUXFORM uses KEscheme = 2
 __device__ inline double mom_botdrag(const TileGrid &g, const MomState &st, const MomPar &p, int k, int isV, int i, int j,
-                                 const double *KEslab = nullptr) {
+                                 bool haveKs = false, double ksIn = 0.) {
   const int Nr = g.Nr;
   const double viscFac = p.no_slip_bottom ? 2. : 0.;
   const int kDown = min(k + 1, Nr), kLowF = k + 1;
@@ -214,7 +214,7 @@ __device__ inline double mom_botdrag(const TileGrid &g, const MomState &st, cons
   else if (p.no_slip_bottom)
     c = c + kap * recDrC * viscFac;
   if (p.selectBotDragQuadr == 0) {
-    double ks = KEslab ? KEslab[g.s(i, j)] + KEslab[g.s(i - di, j - dj)] : mom_ke(g, st, k, i, j) + mom_ke(g, st, k, i - di, j - dj);
+    double ks = haveKs ? ksIn : mom_ke(g, st, k, i, j) + mom_ke(g, st, k, i - di, j - dj);
     if (ks > 0.) c = c + p.bottomDragQuadratic * sqrt(ks) * 1.;
   } else if (p.selectBotDragQuadr == 1 || p.selectBotDragQuadr == 2) {
     double uSq;

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "step_fast.cuh"
+#include "vecinv.cuh"
 #include "phys.cuh"
 
 #define MG_DO_PRAGMA(x) _Pragma(#x)
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
 #ifndef DYN_MINB
 #define DYN_MINB 4
 #endif
-__global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, const double *sfU, const double *sfV,
+// VI: MOM_VECINV (vecinv.cuh, re-evaluating form) instead of MOM_FLUXFORM; the values carried down the
+// column are then the viscous vertical fluxes fVerU/V (dynamics.F:527-533).
+template <bool VI>
+__global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, ViPar vp, const double *sfU, const double *sfV,
                                                   double *gU, double *gV, double *guNm1, double *gvNm1,
                                                   double deltaTMom, double abFac, int momForcing, int dissInAB,
                                                   const double *phiHyd, const double *etaN, const double *Bo_surf,
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
   const int j = blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx + 1 || j > g.sNy + 1) return;
   double ukm = 0., vkm = 0.;
-  if (p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
+  if (!VI && p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
   const size_t s = g.s(i, j);
   // CALC_GRAD_PHI_SURF (calc_grad_phi_surf.F) when implicSurfPress != 1 (dynamics.F:249-255); the explicit
   // part of the surface pressure gradient enters TIMESTEP as gUdPx = -psFac*phiSurfX, psFac = 1 - implicSurfPress
@@ -163,8 +167,15 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
   }
   for (int k = 1; k <= g.Nr; k++) {
     double ukp = 0., vkp = 0.;
-    if (p.momAdvection) { ukp = mom_adv_wu(g, st, p, k + 1, i, j); vkp = mom_adv_wv(g, st, p, k + 1, i, j); }
-    MomOut o = mom_cell(g, st, p, k, i, j, ukm, ukp, vkm, vkp);
+    MomOut o;
+    if (VI) {
+      const ViOut vo = vi_cell(g, st, vp, ViFusedAcc{g, st, vp, k}, k, i, j, true, ukm, vkm);
+      o.gU = vo.gU; o.gV = vo.gV; o.guDiss = vo.guDiss; o.gvDiss = vo.gvDiss;
+      ukp = vo.fVerUkp; vkp = vo.fVerVkp;
+    } else {
+      if (p.momAdvection) { ukp = mom_adv_wu(g, st, p, k + 1, i, j); vkp = mom_adv_wv(g, st, p, k + 1, i, j); }
+      o = mom_cell(g, st, p, k, i, j, ukm, ukp, vkm, vkp);
+    }
     const size_t s3 = g.s3(i, j, k);
     double gu = o.gU, gv = o.gV;
     // timestep.F:120-121: gU - phFac*dPhiHydX with CALC_GRAD_PHI_HYD (calc_grad_phi_hyd.F:150-165) on
@@ -348,6 +359,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   if (semiImpl && g.nPx * g.nPy > 1) return fail(61, "forward_step: implicSurfPress/implicDiv2DFlow < 1 is single-rank for now");
   MomPar mp;
   if (!make_mom_par(mp)) return false;
+  const bool vecinv = q.I(MI_VECTORINVARIANTMOMENTUM) != 0;
+  ViPar vp{};
+  if (vecinv) {
+    if (!make_vi_par(vp)) return false;
+    if (mp.momViscosity && mp.useBiharmonicVisc) return fail(61, "forward_step: MOM_VECINV with biharmonic viscosity is per-level only (mom_vecinv_b200_)");
+    if (g.OLx < 2 || g.OLy < 2) return fail(61, "forward_step: MOM_VECINV needs OLx, OLy >= 2");
+    if (!field(MG_RECIP_RAZ, false) || !field(MG_FCORIG, false)) return fail(43, "forward_step: rAz / fCoriG mirrors not set");
+    vp.iMin = 0; vp.iMax = g.sNx + 1; vp.jMin = 0; vp.jMax = g.sNy + 1;
+    if (exch2_active() && (int)c.csCorners.size() != g.nTiles) return fail(61, "forward_step: mitgcm_b200_set_cs_tiles_ not called");
+  }
   const double abFac = (myIter == q.I(MI_NITER0)) ? 0.0 : 0.5 + q.D(MP_ABEPS);
   double *u = field(MG_UVEL), *v = field(MG_VVEL), *w = field(MG_WVEL);
   double *gU = field(MG_GU), *gV = field(MG_GV), *guN = field(MG_GUNM1), *gvN = field(MG_GVNM1);
@@ -463,7 +484,15 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t o3 = ns * g.Nr * t, o3p = ns * (g.Nr + 1) * t, o2 = ns * t;
         MomState st{u + o3, v + o3, w + o3, kapU + o3p, kapV + o3p};
         c.launches++;
-        if (!semiImpl && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
+        if (vecinv) {
+          vp.csCorners = c.csCorners.empty() ? 0 : c.csCorners[t];
+          vp.myFace = c.csFace.empty() ? 0 : c.csFace[t];
+          dyn_kernel<true><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+                                                      q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
+                                                      buoy ? phiHyd + o3 : nullptr,
+                                                      q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
+                                                      1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
+        } else if (!semiImpl && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
           static bool attr = false;
           if (!attr) {
             cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
@@ -477,7 +506,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
         else
-          dyn_kernel<<<grd, blk, 0, c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+          dyn_kernel<false><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
                                                 q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
                                                 buoy ? phiHyd + o3 : nullptr,
                                                 q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
@@ -699,6 +728,17 @@ void mitgcm_b200_exch_(const int *id, int *ierr) {
   if (nz == 0) { fail(2, "exch: not a tile array"); return; }
   if (!exch_field(f, nz)) return;
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "exch: stream error"); return; }
+  *ierr = 0;
+}
+
+void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr) {
+  Ctx &c = ctx();
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  for (int t = 0; t < c.g.nTiles; t++)
+    if (csCorners[t] < 0 || csCorners[t] > 15 || (csCorners[t] && myFace[t] < 1)) { fail(70, "set_cs_tiles: bad corner mask / facet number"); return; }
+  c.csCorners.assign(csCorners, csCorners + c.g.nTiles);
+  c.csFace.assign(myFace, myFace + c.g.nTiles);
   *ierr = 0;
 }
 

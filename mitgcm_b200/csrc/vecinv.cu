@@ -3,12 +3,13 @@
 // two facts MOM_CALC_RELVORT3 / FILL_CS_CORNER_TR_RL read from W2_EXCH2_TOPOLOGY.h (facet corners,
 // facet number).  2 launches per call, 4 with biharmonic viscosity; see vecinv.cuh.
 #include <algorithm>
+#include <cstdlib>
 #include "vecinv.cuh"
 
 namespace mg {
 bool make_mom_par(MomPar &p);
 
-static bool make_vi_par(ViPar &p) {
+bool make_vi_par(ViPar &p) {
   const Params &q = ctx().p;
   if (!make_mom_par(p.m)) return false;
   p.useCoriolis = q.I(MI_USECORIOLIS); p.useAbsVorticity = q.I(MI_USEABSVORTICITY);
@@ -89,16 +90,23 @@ extern "C" void mom_vecinv_b200_(const int *bi, const int *bj, const int *k, con
     cudaMemcpyAsync(dgV + off3 + ns * (K - 1), gV + off3 + ns * (K - 1), ns * sizeof(double), cudaMemcpyHostToDevice, c.stream);
   }
   dim3 blk(32, 8), grd((g.PX + 31) / 32, (g.PY + 7) / 8);
-  c.launches++;
-  vi_stage1_kernel<<<grd, blk, 0, c.stream>>>(tg, st, p, K, w);
-  if (p.m.momViscosity && p.m.useBiharmonicVisc) {
+  const bool biharm = p.m.momViscosity && p.m.useBiharmonicVisc;
+  if (!biharm && !getenv("MITGCM_B200_VI_STAGED")) {
+    // one launch: vorticity, KE and divergence are re-evaluated where they are read
+    c.launches++;
+    vi_tend_kernel<true><<<grd, blk, 0, c.stream>>>(tg, st, p, K, w, slabD[0], slabD[1], slabD[2], slabD[3], slabD[4],
+                                                    slabD[5], dgU + off3, dgV + off3);
+  } else {
     c.launches += 2;
-    vi_del2_kernel<<<grd, blk, 0, c.stream>>>(tg, p, K, w);
-    vi_star_kernel<<<grd, blk, 0, c.stream>>>(tg, p, K, w);
+    vi_stage1_kernel<<<grd, blk, 0, c.stream>>>(tg, st, p, K, w);
+    if (biharm) {
+      c.launches += 2;
+      vi_del2_kernel<<<grd, blk, 0, c.stream>>>(tg, p, K, w);
+      vi_star_kernel<<<grd, blk, 0, c.stream>>>(tg, p, K, w);
+    }
+    vi_tend_kernel<false><<<grd, blk, 0, c.stream>>>(tg, st, p, K, w, slabD[0], slabD[1], slabD[2], slabD[3], slabD[4],
+                                                     slabD[5], dgU + off3, dgV + off3);
   }
-  c.launches++;
-  vi_tend_kernel<<<grd, blk, 0, c.stream>>>(tg, st, p, K, w, slabD[0], slabD[1], slabD[2], slabD[3], slabD[4], slabD[5],
-                                            dgU + off3, dgV + off3);
   if (cudaGetLastError() != cudaSuccess) { fail(5, "mom_vecinv kernel launch failed"); return; }
   double *slabOut[4] = {fVerUkp, fVerVkp, guDiss, gvDiss};
   for (int n = 0; n < 4; n++)

@@ -24,6 +24,8 @@ struct ViPar {
   int iMin, iMax, jMin, jMax;
 };
 
+bool make_vi_par(ViPar &p);   // host: from the run-time parameters; false + error for options not on the path
+
 // per-level scratch slabs (PX*PY each)
 struct ViScratch {
   double *hFacZ, *KE, *vort3, *hDiv, *del2u, *del2v, *dStar, *zStar, *omega3;
@@ -107,7 +109,7 @@ __device__ inline double vi_corner_read(const TileGrid &g, const double *f, int 
 }
 
 // ---- stage 1: hFacZ, KE, vort3 (masked at hFacZ = 0), hDiv over the whole slab -----------------
-__global__ void __launch_bounds__(256) vi_stage1_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w) {
+static __global__ void __launch_bounds__(256) vi_stage1_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256) vi_stage1_kernel(TileGrid g, MomState st,
 }
 
 // ---- stage 2 (biharmonic): MOM_VI_DEL2UV (mom_vi_del2uv.F:78-124) --------------------------------
-__global__ void __launch_bounds__(256) vi_del2_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
+static __global__ void __launch_bounds__(256) vi_del2_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256) vi_del2_kernel(TileGrid g, ViPar p, int k
 }
 
 // ---- stage 3 (biharmonic): dStar, zStar (mom_vecinv.F:390-395) ----------------------------------
-__global__ void __launch_bounds__(256) vi_star_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
+static __global__ void __launch_bounds__(256) vi_star_kernel(TileGrid g, ViPar p, int k, ViScratch w) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
@@ -155,34 +157,68 @@ __global__ void __launch_bounds__(256) vi_star_kernel(TileGrid g, ViPar p, int k
   w.zStar[s] = vi_relvort3(g, w.del2u, w.del2v, p.csCorners, p.myFace, i, j);
 }
 
-// MOM_VI_U_CORIOLIS / MOM_VI_V_CORIOLIS (mom_vi_{u,v}_coriolis.F:54-197), upwindVort3 = .FALSE.
-__device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const double *om,
-                                       const double *hFacZ, int k, int i, int j) {
+// ---- accessors of the level's intermediate fields ------------------------------------------------
+// ViSlabAcc reads them from the scratch slabs the staging kernels wrote; ViFusedAcc re-evaluates them
+// from u, v where they are read (no scratch traffic; everything but biharmonic viscosity).
+struct ViSlabAcc {
+  const TileGrid &g; ViScratch w; int csCorners, dirH;
+  __device__ double hFacZ(int i, int j) const { return w.hFacZ[g.s(i, j)]; }
+  __device__ double vort3(int i, int j) const { return w.vort3[g.s(i, j)]; }
+  __device__ double omega3(int i, int j) const { return w.omega3[g.s(i, j)]; }
+  __device__ double KE(int i, int j) const { return w.KE[g.s(i, j)]; }
+  __device__ double hDiv(int i, int j) const { return vi_corner_read(g, w.hDiv, csCorners, dirH, i, j); }
+  __device__ double del2u(int i, int j) const { return w.del2u[g.s(i, j)]; }
+  __device__ double del2v(int i, int j) const { return w.del2v[g.s(i, j)]; }
+  __device__ double dStar(int i, int j) const { return w.dStar[g.s(i, j)]; }
+  __device__ double zStar(int i, int j) const { return w.zStar[g.s(i, j)]; }
+};
+struct ViFusedAcc {
+  const TileGrid &g; const MomState &st; const ViPar &p; int k;
+  __device__ double hFacZ(int i, int j) const { return mom_hfacz(g, k, i, j); }
+  __device__ double vort3(int i, int j) const {
+    if (mom_hfacz(g, k, i, j) == 0.) return 0.;
+    return vi_relvort3(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), p.csCorners, p.myFace, i, j);
+  }
+  __device__ double omega3(int i, int j) const {
+    return g.fCoriG[g.s(i, j)] * (p.useCoriolis ? 1. : 0.) + vort3(i, j) * (p.m.momAdvection ? 1. : 0.);
+  }
+  __device__ double KE(int i, int j) const { return vi_ke(g, st, p.selectKEscheme, k, i, j); }
+  __device__ double hDiv(int i, int j) const {
+    return vi_hdiv(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k, i, j);
+  }
+  __device__ double del2u(int, int) const { return 0.; }
+  __device__ double del2v(int, int) const { return 0.; }
+  __device__ double dStar(int, int) const { return 0.; }
+  __device__ double zStar(int, int) const { return 0.; }
+};
+
+// MOM_VI_U_CORIOLIS / MOM_VI_V_CORIOLIS (mom_vi_{u,v}_coriolis.F:54-197), upwindVort3 = .FALSE.;
+// absV selects omega3 (absolute) or vort3 (relative) as the advected vorticity
+template <class A>
+__device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
   const double epsil = 1e-9, oneThird = 1. / 3.;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
   auto vdxh = [&](int ii, int jj) { return VV(ii, jj) * g.dxG[g.s(ii, jj)] * g.hFacS[g.s3(ii, jj, k)]; };
-  auto rz = [&](int ii, int jj) {
-    const double h = hFacZ[g.s(ii, jj)];
-    return (h == 0. ? 0. : 1. / h) * om[g.s(ii, jj)];
-  };
-  auto rh = [&](int ii, int jj) { const double h = hFacZ[g.s(ii, jj)]; return h == 0. ? 0. : 1. / h; };
+  auto om = [&](int ii, int jj) { return absV ? a.omega3(ii, jj) : a.vort3(ii, jj); };
+  auto rh = [&](int ii, int jj) { const double h = a.hFacZ(ii, jj); return h == 0. ? 0. : 1. / h; };
+  auto rz = [&](int ii, int jj) { return rh(ii, jj) * om(ii, jj); };
   double r;
   const int sch = p.selectVortScheme;
   if (sch == 3 && i > g.sNx + g.OLx - 1) return 0.;
   if (sch == 0) {
     const double vBarXY = 0.25 * ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1)));
-    const double vort3u = 0.5 * (om[s] * rh(i, j) + om[g.s(i, j + 1)] * rh(i, j + 1));
+    const double vort3u = 0.5 * (om(i, j) * rh(i, j) + om(i, j + 1) * rh(i, j + 1));
     r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
   } else if (sch == 1) {
-    const double h0 = hFacZ[s], h1 = hFacZ[g.s(i, j + 1)];
+    const double h0 = a.hFacZ(i, j), h1 = a.hFacZ(i, j + 1);
     const double vBarXY = 0.5 * ((VV(i, j) * g.dxG[s] * h0 + VV(i - 1, j) * g.dxG[g.s(i - 1, j)] * h0) +
                                  (VV(i, j + 1) * g.dxG[g.s(i, j + 1)] * h1 + VV(i - 1, j + 1) * g.dxG[g.s(i - 1, j + 1)] * h1)) /
                           fmax(epsil, h0 + h1);
-    const double vort3u = 0.5 * (om[s] + om[g.s(i, j + 1)]);
+    const double vort3u = 0.5 * (om(i, j) + om(i, j + 1));
     r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
   } else if (sch == 2) {
     const double vBarXm = 0.5 * (vdxh(i, j) + vdxh(i - 1, j)), vBarXp = 0.5 * (vdxh(i, j + 1) + vdxh(i - 1, j + 1));
-    const double vort3u = (vBarXm * rh(i, j) * om[s] + vBarXp * rh(i, j + 1) * om[g.s(i, j + 1)]) * 0.5;
+    const double vort3u = (vBarXm * rh(i, j) * om(i, j) + vBarXp * rh(i, j + 1) * om(i, j + 1)) * 0.5;
     r = +vort3u * g.recip_dxC[s] * g.maskW[s3];
   } else {
     const double vort3mj = (rz(i, j) + (rz(i, j + 1) + rz(i - 1, j))) * oneThird * vdxh(i - 1, j);
@@ -196,30 +232,31 @@ __device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, co
         fmax(epsil, (g.hFacS[s3] + g.hFacS[g.s3(i - 1, j, k)]) + (g.hFacS[g.s3(i, j + 1, k)] + g.hFacS[g.s3(i - 1, j + 1, k)]));
   return r;
 }
-__device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const double *om,
-                                       const double *hFacZ, int k, int i, int j) {
+template <class A>
+__device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
   const double epsil = 1e-9, oneThird = 1. / 3.;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
   auto udyh = [&](int ii, int jj) { return VU(ii, jj) * g.dyG[g.s(ii, jj)] * g.hFacW[g.s3(ii, jj, k)]; };
-  auto rh = [&](int ii, int jj) { const double h = hFacZ[g.s(ii, jj)]; return h == 0. ? 0. : 1. / h; };
-  auto rz = [&](int ii, int jj) { return rh(ii, jj) * om[g.s(ii, jj)]; };
+  auto om = [&](int ii, int jj) { return absV ? a.omega3(ii, jj) : a.vort3(ii, jj); };
+  auto rh = [&](int ii, int jj) { const double h = a.hFacZ(ii, jj); return h == 0. ? 0. : 1. / h; };
+  auto rz = [&](int ii, int jj) { return rh(ii, jj) * om(ii, jj); };
   double r;
   const int sch = p.selectVortScheme;
   if (sch == 3 && j > g.sNy + g.OLy - 1) return 0.;
   if (sch == 0) {
     const double uBarXY = 0.25 * ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1)));
-    const double vort3v = 0.5 * (om[s] * rh(i, j) + om[g.s(i + 1, j)] * rh(i + 1, j));
+    const double vort3v = 0.5 * (om(i, j) * rh(i, j) + om(i + 1, j) * rh(i + 1, j));
     r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
   } else if (sch == 1) {
-    const double h0 = hFacZ[s], h1 = hFacZ[g.s(i + 1, j)];
+    const double h0 = a.hFacZ(i, j), h1 = a.hFacZ(i + 1, j);
     const double uBarXY = 0.5 * ((VU(i, j) * g.dyG[s] * h0 + VU(i, j - 1) * g.dyG[g.s(i, j - 1)] * h0) +
                                  (VU(i + 1, j) * g.dyG[g.s(i + 1, j)] * h1 + VU(i + 1, j - 1) * g.dyG[g.s(i + 1, j - 1)] * h1)) /
                           fmax(epsil, h0 + h1);
-    const double vort3v = 0.5 * (om[s] + om[g.s(i + 1, j)]);
+    const double vort3v = 0.5 * (om(i, j) + om(i + 1, j));
     r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
   } else if (sch == 2) {
     const double uBarYm = 0.5 * (udyh(i, j) + udyh(i, j - 1)), uBarYp = 0.5 * (udyh(i + 1, j) + udyh(i + 1, j - 1));
-    const double vort3v = (uBarYm * rh(i, j) * om[s] + uBarYp * rh(i + 1, j) * om[g.s(i + 1, j)]) * 0.5;
+    const double vort3v = (uBarYm * rh(i, j) * om(i, j) + uBarYp * rh(i + 1, j) * om(i + 1, j)) * 0.5;
     r = -vort3v * g.recip_dyC[s] * g.maskS[s3];
   } else {
     const double vort3im = (rz(i, j) + (rz(i + 1, j) + rz(i, j - 1))) * oneThird * udyh(i, j - 1);
@@ -304,56 +341,57 @@ __device__ inline double vi_vertshear(const TileGrid &g, const MomState &st, con
   return -0.5 * (wBp * fZp + wBm * fZm) * rh * g.recip_drF[k - 1];
 }
 
-// MOM_{U,V}_SIDEDRAG with the vector-invariant del2u / del2v slabs (sideDragFactor > 0, constant viscosity)
-__device__ inline double vi_sidedrag(const TileGrid &g, const MomState &st, const ViPar &p, const ViScratch &w, int isV, int k, int i, int j) {
+// MOM_{U,V}_SIDEDRAG with the vector-invariant del2u / del2v (sideDragFactor > 0, constant viscosity)
+template <class A>
+__device__ inline double vi_sidedrag(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, int isV, int k, int i, int j) {
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
   if (!isV) {
-    const double hS = g.hFacW[s3] - w.hFacZ[s], hN = g.hFacW[s3] - w.hFacZ[g.s(i, j + 1)];
-    const double d2 = p.m.useBiharmonicVisc ? w.del2u[s] : 0.;
+    const double hS = g.hFacW[s3] - a.hFacZ(i, j), hN = g.hFacW[s3] - a.hFacZ(i, j + 1);
+    const double d2 = p.m.useBiharmonicVisc ? a.del2u(i, j) : 0.;
     const double t = p.m.viscAhZ * VU(i, j) - p.m.viscA4Z * d2;
     return -g.recip_hFacW[s3] * g.recip_drF[k - 1] * g.recip_rAw[s] *
            (hS * g.dxV[s] * g.recip_dyU[s] * t + hN * g.dxV[g.s(i, j + 1)] * g.recip_dyU[g.s(i, j + 1)] * t) * g.drF[k - 1] *
            p.m.sideDragFactor;
   }
   const double cf = g.cosFacV[j + g.OLy - 1];
-  const double hW = g.hFacS[s3] - w.hFacZ[s], hE = g.hFacS[s3] - w.hFacZ[g.s(i + 1, j)];
-  const double d2 = p.m.useBiharmonicVisc ? w.del2v[s] : 0.;
+  const double hW = g.hFacS[s3] - a.hFacZ(i, j), hE = g.hFacS[s3] - a.hFacZ(i + 1, j);
+  const double d2 = p.m.useBiharmonicVisc ? a.del2v(i, j) : 0.;
   const double t = p.m.viscAhZ * VV(i, j) * cf - p.m.viscA4Z * d2 * cf;
   return -g.recip_hFacS[s3] * g.recip_drF[k - 1] * g.recip_rAs[s] *
          (hW * g.dyU[s] * g.recip_dxV[s] * t + hE * g.dyU[g.s(i + 1, j)] * g.recip_dxV[g.s(i + 1, j)] * t) * g.drF[k - 1] *
          p.m.sideDragFactor;
 }
 
-// ---- final stage: tendencies (mom_vecinv.F:308-927) ------------------------------------------------
-__global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w,
-                                                      const double *fVerUkm, const double *fVerVkm, double *fVerUkp,
-                                                      double *fVerVkp, double *guDiss, double *gvDiss, double *gU, double *gV) {
-  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
-  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
-  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+struct ViOut { double gU, gV, guDiss, gvDiss, fVerUkp, fVerVkp; };
+
+// Tendencies of one point (mom_vecinv.F:308-927).  inRange: the point is inside iMin..iMax x jMin..jMax
+// (outside, only MOM_VI_HDISSIP's own range is written); fVer?km: viscous vertical flux at the upper
+// interface; o.fVer?kp is valid only when inRange, momViscosity and not implicitViscosity.
+template <class A>
+__device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, int k, int i, int j,
+                                bool inRange, double fVerUkm, double fVerVkm) {
+  ViOut o;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
   const MomPar &m = p.m;
-  const bool inRange = i >= p.iMin && i <= p.iMax && j >= p.jMin && j <= p.jMax;
   double uD = 0., vD = 0.;
+  o.fVerUkp = 0.; o.fVerVkp = 0.;
   if (m.momViscosity) {
     // MOM_VI_HDISSIP (mom_vi_hdissip.F:60-271) on its own range, constant coefficients
     if (i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1 && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1) {
       const double cU = g.cosFacU[j + g.OLy - 1], cV = g.cosFacV[j + g.OLy - 1];
-      const int dir = (m.useBiharmonicVisc && p.csCorners) ? 2 : 0;   // hDiv keeps MOM_VI_DEL2UV's last corner fill
       if (p.harmonic) {
-        const double Dim = vi_corner_read(g, w.hDiv, p.csCorners, dir, i, j - 1), Dij = vi_corner_read(g, w.hDiv, p.csCorners, dir, i, j),
-                     Dmj = vi_corner_read(g, w.hDiv, p.csCorners, dir, i - 1, j);
-        const double Zip = w.hFacZ[g.s(i, j + 1)] * w.vort3[g.s(i, j + 1)], Zij = w.hFacZ[s] * w.vort3[s],
-                     Zpj = w.hFacZ[g.s(i + 1, j)] * w.vort3[g.s(i + 1, j)];
+        const double Dim = a.hDiv(i, j - 1), Dij = a.hDiv(i, j), Dmj = a.hDiv(i - 1, j);
+        const double Zip = a.hFacZ(i, j + 1) * a.vort3(i, j + 1), Zij = a.hFacZ(i, j) * a.vort3(i, j),
+                     Zpj = a.hFacZ(i + 1, j) * a.vort3(i + 1, j);
         const double uD2 = m.viscAhD * cU * (Dij - Dmj) * g.recip_dxC[s] - m.viscAhZ * g.recip_hFacW[s3] * (Zip - Zij) * g.recip_dyG[s];
         const double vD2 = m.viscAhZ * g.recip_hFacS[s3] * cV * (Zpj - Zij) * g.recip_dxG[s] + m.viscAhD * (Dij - Dim) * g.recip_dyC[s];
         uD = uD2 * g.maskW[s3];
         vD = vD2 * g.maskS[s3];
       }
       if (m.useBiharmonicVisc) {
-        const double Dim = w.dStar[g.s(i, j - 1)], Dij = w.dStar[s], Dmj = w.dStar[g.s(i - 1, j)];
-        const double Zip = w.hFacZ[g.s(i, j + 1)] * w.zStar[g.s(i, j + 1)], Zij = w.hFacZ[s] * w.zStar[s],
-                     Zpj = w.hFacZ[g.s(i + 1, j)] * w.zStar[g.s(i + 1, j)];
+        const double Dim = a.dStar(i, j - 1), Dij = a.dStar(i, j), Dmj = a.dStar(i - 1, j);
+        const double Zip = a.hFacZ(i, j + 1) * a.zStar(i, j + 1), Zij = a.hFacZ(i, j) * a.zStar(i, j),
+                     Zpj = a.hFacZ(i + 1, j) * a.zStar(i + 1, j);
         double uD4 = m.viscA4D * cU * (Dij - Dmj) * g.recip_dxC[s] - m.viscA4Z * g.recip_hFacW[s3] * (Zip - Zij) * g.recip_dyG[s];
         double vD4 = m.viscA4Z * g.recip_hFacS[s3] * cV * (Zpj - Zij) * g.recip_dxG[s] + m.viscA4D * (Dij - Dim) * g.recip_dyC[s];
         uD4 = -uD4 * g.maskW[s3];
@@ -364,46 +402,78 @@ __global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, V
     }
     if (inRange) {
       const double rhW = g.recip_hFacW[s3], rhS = g.recip_hFacS[s3], rdrF = g.recip_drF[k - 1];
+      const bool quad0 = m.bottomDragTerms && m.selectBotDragQuadr == 0;
       if (!m.implicitViscosity) {
-        const double up = m.vfFacMom * 1. * mom_u_rvisc(g, st, m, k + 1, i, j);
-        fVerUkp[s] = up;
-        uD = uD - rhW * rdrF * g.recip_rAw[s] * (up - fVerUkm[s]) * m.rkSign;
+        o.fVerUkp = m.vfFacMom * 1. * mom_u_rvisc(g, st, m, k + 1, i, j);
+        uD = uD - rhW * rdrF * g.recip_rAw[s] * (o.fVerUkp - fVerUkm) * m.rkSign;
       }
-      if (m.no_slip_sides) uD = uD + vi_sidedrag(g, st, p, w, 0, k, i, j);
-      if (m.bottomDragTerms) uD = uD + (-mom_botdrag(g, st, m, k, 0, i, j, w.KE) * VU(i, j) * rhW * rdrF);
+      if (m.no_slip_sides) uD = uD + vi_sidedrag(g, st, p, a, 0, k, i, j);
+      if (m.bottomDragTerms)
+        uD = uD + (-mom_botdrag(g, st, m, k, 0, i, j, true, quad0 ? a.KE(i, j) + a.KE(i - 1, j) : 0.) * VU(i, j) * rhW * rdrF);
       if (!m.implicitViscosity) {
-        const double vp = m.vfFacMom * 1. * mom_v_rvisc(g, st, m, k + 1, i, j);
-        fVerVkp[s] = vp;
-        vD = vD - rhS * rdrF * g.recip_rAs[s] * (vp - fVerVkm[s]) * m.rkSign;
+        o.fVerVkp = m.vfFacMom * 1. * mom_v_rvisc(g, st, m, k + 1, i, j);
+        vD = vD - rhS * rdrF * g.recip_rAs[s] * (o.fVerVkp - fVerVkm) * m.rkSign;
       }
-      if (m.no_slip_sides) vD = vD + vi_sidedrag(g, st, p, w, 1, k, i, j);
-      if (m.bottomDragTerms) vD = vD + (-mom_botdrag(g, st, m, k, 1, i, j, w.KE) * VV(i, j) * rhS * rdrF);
+      if (m.no_slip_sides) vD = vD + vi_sidedrag(g, st, p, a, 1, k, i, j);
+      if (m.bottomDragTerms)
+        vD = vD + (-mom_botdrag(g, st, m, k, 1, i, j, true, quad0 ? a.KE(i, j) + a.KE(i, j - 1) : 0.) * VV(i, j) * rhS * rdrF);
     }
   }
-  guDiss[s] = uD;
-  gvDiss[s] = vD;
-  if (!inRange) return;
+  o.guDiss = uD;
+  o.gvDiss = vD;
+  o.gU = 0.; o.gV = 0.;
+  if (!inRange) return o;
   // ---- Coriolis and advection (mom_vecinv.F:672-884)
   double tU = 0., tV = 0.;
   if (p.useCoriolis && !(m.useCDscheme || (p.useAbsVorticity && m.momAdvection))) {
     if (p.useAbsVorticity) {
-      tU = vi_u_coriolis(g, st, p, w.omega3, w.hFacZ, k, i, j);
-      tV = vi_v_coriolis(g, st, p, w.omega3, w.hFacZ, k, i, j);
+      tU = vi_u_coriolis(g, st, p, a, true, k, i, j);
+      tV = vi_v_coriolis(g, st, p, a, true, k, i, j);
     } else {
       vi_coriolis(g, st, m.selectCoriScheme, k, i, j, tU, tV);
     }
   }
   if (m.momAdvection) {
-    const double *w3 = p.useAbsVorticity ? w.omega3 : w.vort3;
-    tU = tU + vi_u_coriolis(g, st, p, w3, w.hFacZ, k, i, j);
-    tV = tV + vi_v_coriolis(g, st, p, w3, w.hFacZ, k, i, j);
+    tU = tU + vi_u_coriolis(g, st, p, a, p.useAbsVorticity != 0, k, i, j);
+    tV = tV + vi_v_coriolis(g, st, p, a, p.useAbsVorticity != 0, k, i, j);
     tU = tU + vi_vertshear(g, st, p, 0, k, i, j);
     tV = tV + vi_vertshear(g, st, p, 1, k, i, j);
-    tU = tU + (-g.recip_dxC[s] * (w.KE[s] - w.KE[g.s(i - 1, j)]) * g.maskW[s3]);
-    tV = tV + (-g.recip_dyC[s] * (w.KE[s] - w.KE[g.s(i, j - 1)]) * g.maskS[s3]);
+    const double ke = a.KE(i, j);
+    tU = tU + (-g.recip_dxC[s] * (ke - a.KE(i - 1, j)) * g.maskW[s3]);
+    tV = tV + (-g.recip_dyC[s] * (ke - a.KE(i, j - 1)) * g.maskS[s3]);
   }
-  gU[s3] = tU * g.maskW[s3];
-  gV[s3] = tV * g.maskS[s3];
+  o.gU = tU * g.maskW[s3];
+  o.gV = tV * g.maskS[s3];
+  return o;
+}
+
+// ---- final stage of the per-level entry point ----------------------------------------------------
+template <bool FUSED>
+__global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, ViPar p, int k, ViScratch w,
+                                                      const double *fVerUkm, const double *fVerVkm, double *fVerUkp,
+                                                      double *fVerVkp, double *guDiss, double *gvDiss, double *gU, double *gV) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  const bool inRange = i >= p.iMin && i <= p.iMax && j >= p.jMin && j <= p.jMax;
+  ViOut o;
+  if (FUSED) {
+    // outside MOM_VI_HDISSIP's range nothing is evaluated (the accessors would read past the slab)
+    const bool inner = i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1 && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1;
+    if (inner) o = vi_cell(g, st, p, ViFusedAcc{g, st, p, k}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
+    else { o.guDiss = 0.; o.gvDiss = 0.; }
+  } else {
+    // hDiv keeps MOM_VI_DEL2UV's last facet-corner fill (direction 2) when that routine ran
+    const int dirH = (p.m.useBiharmonicVisc && p.csCorners) ? 2 : 0;
+    o = vi_cell(g, st, p, ViSlabAcc{g, w, p.csCorners, dirH}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
+  }
+  guDiss[s] = o.guDiss;
+  gvDiss[s] = o.gvDiss;
+  if (!inRange) return;
+  if (p.m.momViscosity && !p.m.implicitViscosity) { fVerUkp[s] = o.fVerUkp; fVerVkp[s] = o.fVerVkp; }
+  gU[s3] = o.gU;
+  gV[s3] = o.gV;
 }
 
 #undef VU

@@ -209,6 +209,13 @@ def set_topology(topo: Exch2Topology, myTileList=None):
         C.byref(ierr))
     if ierr.value:
         raise RuntimeError(f"set_exch2_topology failed: {L.mitgcm_b200_last_error_string().decode()}")
+    # facet corners / facet numbers of the local tiles (resident MOM_VECINV: mom_calc_relvort3.F:79-97)
+    N, S_, E, W = (np.asarray(tb[n]) for n in ("isNedge", "isSedge", "isEedge", "isWedge"))
+    corners = ((W & S_) * 1 + (E & S_) * 2 + (E & N) * 4 + (W & N) * 8).astype(np.int32)[tl - 1]
+    faces = np.ascontiguousarray(np.asarray(topo.myFace, dtype=np.int32)[tl - 1])
+    L.mitgcm_b200_set_cs_tiles_(ip(np.ascontiguousarray(corners)), ip(faces), C.byref(ierr))
+    if ierr.value:
+        raise RuntimeError(f"set_cs_tiles failed: {L.mitgcm_b200_last_error_string().decode()}")
 
 
 # ---- the exchange as a gather ----------------------------------------------------------------------

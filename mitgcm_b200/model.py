@@ -23,7 +23,8 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "diffKhT diffK4T diffKrT viscAr tempStepping cg2dMaxIters momForcing momDissip_In_AB "
               "implicitDiffusion useSRCGSolver usingSphericalPolarGrid selectMetricTerms recip_rSphere "
               "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa "
-              "implicSurfPress implicDiv2DFlow").split()
+              "implicSurfPress implicDiv2DFlow rkSign vectorInvariantMomentum useCoriolis useAbsVorticity "
+              "selectVortScheme selectKEscheme useJamartMomAdv upwindShear").split()
 
 
 def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
