@@ -142,17 +142,23 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
 #ifndef DYN_MINB
 #define DYN_MINB 4
 #endif
-// VI: MOM_VECINV (vecinv.cuh, re-evaluating form) instead of MOM_FLUXFORM; the values carried down the
-// column are then the viscous vertical fluxes fVerU/V (dynamics.F:527-533).
-template <bool VI>
-__global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, ViPar vp, const double *sfU, const double *sfV,
+// VI = 1: MOM_VECINV (vecinv.cuh) instead of MOM_FLUXFORM, vorticity / KE / divergence re-evaluated where
+// they are read; VI = 2: the CTA (32 x 8) evaluates them once per level for its patch into shared memory.
+// The values carried down the column are then the viscous vertical fluxes fVerU/V (dynamics.F:527-533).
+template <int VI>
+__global__ void __launch_bounds__(VI == 2 ? 256 : 128, VI == 2 ? 2 : DYN_MINB) dyn_kernel(TileGrid g, MomState st, MomPar p, ViPar vp, const double *sfU, const double *sfV,
                                                   double *gU, double *gV, double *guNm1, double *gvNm1,
                                                   double deltaTMom, double abFac, int momForcing, int dissInAB,
                                                   const double *phiHyd, const double *etaN, const double *Bo_surf,
                                                   double psFacTS) {
-  const int i = blockIdx.x * 32 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
-  const int j = blockIdx.y * 4 + threadIdx.y;
-  if (i > g.sNx + 1 || j > g.sNy + 1) return;
+  __shared__ double vtRaw[VI == 2 ? sizeof(ViTile) / sizeof(double) : 1];
+  ViTile &vt = *reinterpret_cast<ViTile *>(vtRaw);
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * blockDim.y;
+  int i = i0 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
+  int j = j0 + threadIdx.y;
+  const bool active = i <= g.sNx + 1 && j <= g.sNy + 1;
+  if (VI != 2 && !active) return;
+  if (!active) { i = 0; j = 0; }
   double ukm = 0., vkm = 0.;
   if (!VI && p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
   const size_t s = g.s(i, j);
@@ -168,8 +174,15 @@ __global__ void __launch_bounds__(128, DYN_MINB) dyn_kernel(TileGrid g, MomState
   for (int k = 1; k <= g.Nr; k++) {
     double ukp = 0., vkp = 0.;
     MomOut o;
+    if (VI == 2) {
+      __syncthreads();
+      vi_fill_tile(vt, g, st, vp, k, i0, j0, threadIdx.y * 32 + threadIdx.x);
+      __syncthreads();
+      if (!active) continue;
+    }
     if (VI) {
-      const ViOut vo = vi_cell(g, st, vp, ViFusedAcc{g, st, vp, k}, k, i, j, true, ukm, vkm);
+      const ViOut vo = VI == 2 ? vi_cell(g, st, vp, ViTileAcc{vt, i0, j0}, k, i, j, true, ukm, vkm)
+                               : vi_cell(g, st, vp, ViFusedAcc{g, st, vp, k}, k, i, j, true, ukm, vkm);
       o.gU = vo.gU; o.gV = vo.gV; o.guDiss = vo.guDiss; o.gvDiss = vo.gvDiss;
       ukp = vo.fVerUkp; vkp = vo.fVerVkp;
     } else {
@@ -271,6 +284,31 @@ __global__ void eta_kernel(size_t n, const double *recip_Bo, const double *x, do
   if (t < n) etaN[t] = recip_Bo[t] * x[t];               // solve_for_pressure.F:377-385
 }
 
+// CORRECTION_STEP covers the halo'd slab (momentum_correction_step.F:60-63); INTEGR_CONTINUITY's exactConserv
+// sum reads u(sNx+1,j), v(i,sNy+1) before the exchange.  Launched only with exactConserv: keeping the two
+// predicated stores in corr_kernel's level loop cost 0.6 ms of 3.2 at 2048^2 x 50.
+__global__ void corr_edge_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+                                 const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
+                                 double *__restrict__ uVel, double *__restrict__ vVel, double deltaTMom, double implicSurfPress) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;      // 0..sNy-1: east edge, sNy..sNy+sNx-1: north edge
+  const int k = 1 + blockIdx.y;
+  if (n >= g.sNy + g.sNx) return;
+  const double psFac = 1. * implicSurfPress;
+  if (n < g.sNy) {
+    const int i = g.sNx + 1, j = 1 + n;
+    const size_t s = g.s(i, j), q = g.s3(i, j, k);
+    const double px = g.recip_dxC[s] * (Bo_surf[s] * etaN[s] - Bo_surf[s - 1] * etaN[s - 1]);
+    const double dpx = -psFac * px * g.maskW[q];
+    uVel[q] = (gU[q] + deltaTMom * dpx) * g.maskW[q];
+  } else {
+    const int i = 1 + n - g.sNy, j = g.sNy + 1;
+    const size_t s = g.s(i, j), q = g.s3(i, j, k);
+    const double py = g.recip_dyC[s] * (Bo_surf[s] * etaN[s] - Bo_surf[s - g.PX] * etaN[s - g.PX]);
+    const double dpy = -psFac * py * g.maskS[q];
+    vVel[q] = (gV[q] + deltaTMom * dpy) * g.maskS[q];
+  }
+}
+
 // ---- correction step + continuity ---------------------------------------------------------------
 // 8 CTAs/SM (64 registers): 4.05 -> 3.22 ms; more CTAs spill, fewer leave too few loads in flight.
 #ifndef CORR_MINB
@@ -307,10 +345,6 @@ UNROLL_N(CORR_UNROLL)
     const size_t s3 = g.s3(i, j, k);
     uVel[s3] = u0;
     vVel[s3] = v0;
-    // CORRECTION_STEP covers the halo'd slab (momentum_correction_step.F:60-63); INTEGR_CONTINUITY's
-    // exactConserv sum reads u(sNx+1), v(sNy+1) before the exchange, so the edge threads store them too
-    if (i == g.sNx) uVel[s3 + 1] = u1;
-    if (j == g.sNy) vVel[s3 + g.PX] = v1;
     // INTEGRATE_FOR_W
     const double uT0 = u0 * g.dyG[g.s(i, j)] * g.drF[k - 1] * g.hFacW[s3];
     const double uT1 = u1 * g.dyG[g.s(i + 1, j)] * g.drF[k - 1] * g.hFacW[g.s3(i + 1, j, k)];
@@ -487,7 +521,13 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         if (vecinv) {
           vp.csCorners = c.csCorners.empty() ? 0 : c.csCorners[t];
           vp.myFace = c.csFace.empty() ? 0 : c.csFace[t];
-          dyn_kernel<true><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+          if (!getenv("MITGCM_B200_VI_NOTILE"))
+            dyn_kernel<2><<<dim3((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 7) / 8), dim3(32, 8), 0, c.stream>>>(
+                tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
+                q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr,
+                q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2, 1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
+          else
+          dyn_kernel<1><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
                                                       q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
                                                       buoy ? phiHyd + o3 : nullptr,
                                                       q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
@@ -506,7 +546,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
               tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB));
         else
-          dyn_kernel<false><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
+          dyn_kernel<0><<<grd, blk, 0, c.stream>>>(tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3,
                                                 q.D(MP_DELTATMOM), abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB),
                                                 buoy ? phiHyd + o3 : nullptr,
                                                 q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
@@ -559,6 +599,11 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         c.launches++;
         corr_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
                                                q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS), q.I(MI_RIGIDLID));
+        if (q.I(MI_EXACTCONSERV)) {
+          c.launches++;
+          corr_edge_kernel<<<dim3((g.sNx + g.sNy + 127) / 128, g.Nr), 128, 0, c.stream>>>(
+              tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS));
+        }
       }
     MG_CUDA(cudaGetLastError());
   }

@@ -192,6 +192,40 @@ struct ViFusedAcc {
   __device__ double zStar(int, int) const { return 0.; }
 };
 
+// ViTileAcc: the CTA has evaluated them once per level for its 34 x 10 patch of columns (one-point rim)
+// into shared memory; what the resident step uses.
+constexpr int VT_X = 32, VT_Y = 8, VT_W = VT_X + 2, VT_H = VT_Y + 2, VT_N = VT_W * VT_H;
+struct ViTile { double hFacZ[VT_N], vort3[VT_N], omega3[VT_N], KE[VT_N], hDiv[VT_N]; };
+struct ViTileAcc {
+  const ViTile &t; int i0, j0;      // patch origin: cell (li, lj) is column (i0 - 1 + li, j0 - 1 + lj)
+  __device__ int e(int i, int j) const { return (j - j0 + 1) * VT_W + (i - i0 + 1); }
+  __device__ double hFacZ(int i, int j) const { return t.hFacZ[e(i, j)]; }
+  __device__ double vort3(int i, int j) const { return t.vort3[e(i, j)]; }
+  __device__ double omega3(int i, int j) const { return t.omega3[e(i, j)]; }
+  __device__ double KE(int i, int j) const { return t.KE[e(i, j)]; }
+  __device__ double hDiv(int i, int j) const { return t.hDiv[e(i, j)]; }
+  __device__ double del2u(int, int) const { return 0.; }
+  __device__ double del2v(int, int) const { return 0.; }
+  __device__ double dStar(int, int) const { return 0.; }
+  __device__ double zStar(int, int) const { return 0.; }
+};
+// fills the patch for level k (all threads of a VT_X x VT_Y CTA; caller synchronises)
+__device__ inline void vi_fill_tile(ViTile &t, const TileGrid &g, const MomState &st, const ViPar &p, int k, int i0, int j0, int tid) {
+  const ViFusedAcc a{g, st, p, k};
+  for (int e = tid; e < VT_N; e += VT_X * VT_Y) {
+    const int i = i0 - 1 + e % VT_W, j = j0 - 1 + e / VT_W;
+    double hz = 0., z = 0., om = 0., ke = 0., hd = 0.;
+    if (i <= g.sNx + g.OLx && j <= g.sNy + g.OLy) {
+      hz = a.hFacZ(i, j);
+      z = hz == 0. ? 0. : vi_relvort3(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), p.csCorners, p.myFace, i, j);
+      om = g.fCoriG[g.s(i, j)] * (p.useCoriolis ? 1. : 0.) + z * (p.m.momAdvection ? 1. : 0.);
+      ke = a.KE(i, j);
+      if (p.m.momViscosity) hd = a.hDiv(i, j);
+    }
+    t.hFacZ[e] = hz; t.vort3[e] = z; t.omega3[e] = om; t.KE[e] = ke; t.hDiv[e] = hd;
+  }
+}
+
 // MOM_VI_U_CORIOLIS / MOM_VI_V_CORIOLIS (mom_vi_{u,v}_coriolis.F:54-197), upwindVort3 = .FALSE.;
 // absV selects omega3 (absolute) or vort3 (relative) as the advected vorticity
 template <class A>
