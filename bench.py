@@ -277,7 +277,7 @@ def run_cuda(args, rank, world):
         "gpu_launches": launches, "clocks": clocks, "setup_s": t_setup, "finite": finite,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, quick=True)
+        out["cpu_baseline"] = cpu_baseline(args, quick=False, steps=4)   # 512x512x50: 10-20 s of host work
     print(json.dumps(out))
     rt.finalize()
 
@@ -303,11 +303,13 @@ def cpu_baseline(args, quick=False, steps=None, warmup=1):
     co = ChannelOracle(g, P2, s, threads=nt)
     for _ in range(warmup):
         co.step()
-    n = steps or (2 if quick else 3)
+    n_min = steps or (2 if quick else 3)
     t0 = time.perf_counter()
     its = []
-    for _ in range(n):
+    # at least n_min steps, and (full-size sample) on until ~10 s of host work, bounded at 24 steps
+    while len(its) < n_min or (not quick and steps is not None and time.perf_counter() - t0 < 10.0 and len(its) < 24):
         its.append(co.step()["numIters"])
+    n = len(its)
     dt = time.perf_counter() - t0
     cells = sNx * nSx * sNy * nSy * args.nr
     scale = cells / float(args.nx * args.ny * args.nr)
@@ -322,7 +324,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    cb = cpu_baseline(args, quick=False, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    cb = cpu_baseline(args, quick=False, steps=None if args.steps < 3 else args.steps, warmup=max(1, min(args.warmup, 2)))
     out = {"impl": "reference",
            "metric": "timesteps/s at 2048x2048x50 (per-GPU block of the weak-scaled channel; aggregate = ranks x steps/s)",
            "value": cb["value"], "unit": "block-timesteps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
