@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include "step_fast.cuh"
 #include "vecinv.cuh"
+#include "vecinv_fast.cuh"
 #include "phys.cuh"
 
 #define MG_DO_PRAGMA(x) _Pragma(#x)
@@ -151,14 +152,16 @@ __global__ void __launch_bounds__(VI == 2 ? 256 : 128, VI == 2 ? 2 : DYN_MINB) d
                                                   double deltaTMom, double abFac, int momForcing, int dissInAB,
                                                   const double *phiHyd, const double *etaN, const double *Bo_surf,
                                                   double psFacTS) {
-  __shared__ double vtRaw[VI == 2 ? sizeof(ViTile) / sizeof(double) : 1];
+  __shared__ double vtRaw[VI == 2 ? (sizeof(ViTile) + sizeof(ViPatch)) / sizeof(double) : 1];
   ViTile &vt = *reinterpret_cast<ViTile *>(vtRaw);
+  ViPatch &vpt = *reinterpret_cast<ViPatch *>(vtRaw + (VI == 2 ? sizeof(ViTile) / sizeof(double) : 0));
   const int i0 = blockIdx.x * 32, j0 = blockIdx.y * blockDim.y;
   int i = i0 + threadIdx.x;        // 0 .. sNx+1 (dynamics.F:191-192)
   int j = j0 + threadIdx.y;
   const bool active = i <= g.sNx + 1 && j <= g.sNy + 1;
   if (VI != 2 && !active) return;
   if (!active) { i = 0; j = 0; }
+  if (VI == 2) vi_fill_patch_metrics(vpt, g, i0, j0, threadIdx.y * 32 + threadIdx.x);
   double ukm = 0., vkm = 0.;
   if (!VI && p.momAdvection && !p.rigidLid) { ukm = mom_adv_wu(g, st, p, 1, i, j); vkm = mom_adv_wv(g, st, p, 1, i, j); }
   const size_t s = g.s(i, j);
@@ -176,13 +179,16 @@ __global__ void __launch_bounds__(VI == 2 ? 256 : 128, VI == 2 ? 2 : DYN_MINB) d
     MomOut o;
     if (VI == 2) {
       __syncthreads();
-      vi_fill_tile(vt, g, st, vp, k, i0, j0, threadIdx.y * 32 + threadIdx.x);
+      vi_fill_patch(vpt, g, st, k, i0, j0, threadIdx.y * 32 + threadIdx.x);
+      __syncthreads();
+      vi_fill_tile(vt, vpt, g, st, vp, k, i0, j0, threadIdx.y * 32 + threadIdx.x);
       __syncthreads();
       if (!active) continue;
     }
     if (VI) {
-      const ViOut vo = VI == 2 ? vi_cell(g, st, vp, ViTileAcc{vt, i0, j0}, k, i, j, true, ukm, vkm)
-                               : vi_cell(g, st, vp, ViFusedAcc{g, st, vp, k}, k, i, j, true, ukm, vkm);
+      const ViGlobalSrc fg{g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k};
+      const ViOut vo = VI == 2 ? vi_cell(g, st, ViPatchSrc{vpt, i0, j0}, vp, ViTileAcc{vt, i0, j0}, k, i, j, true, ukm, vkm)
+                               : vi_cell(g, st, fg, vp, ViFusedAcc<ViGlobalSrc>{g, fg, vp, k}, k, i, j, true, ukm, vkm);
       o.gU = vo.gU; o.gV = vo.gV; o.guDiss = vo.guDiss; o.gvDiss = vo.gvDiss;
       ukp = vo.fVerUkp; vkp = vo.fVerVkp;
     } else {
@@ -521,7 +527,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         if (vecinv) {
           vp.csCorners = c.csCorners.empty() ? 0 : c.csCorners[t];
           vp.myFace = c.csFace.empty() ? 0 : c.csFace[t];
-          if (!getenv("MITGCM_B200_VI_NOTILE"))
+          if (!semiImpl && vi_fast_ok(g, vp)) {
+            static bool attrV = false;
+            if (!attrV) {
+              MG_CUDA(cudaFuncSetAttribute(vi_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViPipeSmem)));
+              attrV = true;
+            }
+            vi_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ViPipeSmem),
+                             c.stream>>>(tg, st, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
+                                         abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr);
+          } else if (!getenv("MITGCM_B200_VI_NOTILE"))
             dyn_kernel<2><<<dim3((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 7) / 8), dim3(32, 8), 0, c.stream>>>(
                 tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
                 q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr,

@@ -31,32 +31,72 @@ struct ViScratch {
   double *hFacZ, *KE, *vort3, *hDiv, *del2u, *del2v, *dStar, *zStar, *omega3;
 };
 
-#define VU(i, j) st.u[g.s3(i, j, k)]
-#define VV(i, j) st.v[g.s3(i, j, k)]
+// ---- sources of the level's raw fields and of the metrics that are read at neighbouring points ----
+// ViGlobalSrc: straight from global memory (through L1); uF, vF may be any slab pair (u, v of the level, or
+// del2u, del2v).  ViPatchSrc: from the CTA's shared-memory patch (resident step).
+struct ViGlobalSrc {
+  const TileGrid &g; const double *uF, *vF; int k;
+  __device__ double u(int i, int j) const { return uF[g.s(i, j)]; }
+  __device__ double v(int i, int j) const { return vF[g.s(i, j)]; }
+  __device__ double hW(int i, int j) const { return g.hFacW[g.s3(i, j, k)]; }
+  __device__ double hS(int i, int j) const { return g.hFacS[g.s3(i, j, k)]; }
+  __device__ double dxG(int i, int j) const { return g.dxG[g.s(i, j)]; }
+  __device__ double dyG(int i, int j) const { return g.dyG[g.s(i, j)]; }
+  __device__ double dxC(int i, int j) const { return g.dxC[g.s(i, j)]; }
+  __device__ double dyC(int i, int j) const { return g.dyC[g.s(i, j)]; }
+  __device__ double rAzI(int i, int j) const { return g.recip_rAz[g.s(i, j)]; }
+};
+constexpr int VT_X = 32, VT_Y = 8, VT_W = VT_X + 2, VT_H = VT_Y + 2, VT_N = VT_W * VT_H;
+struct ViPatch { double u[VT_N], v[VT_N], hW[VT_N], hS[VT_N], dxG[VT_N], dyG[VT_N], dxC[VT_N], dyC[VT_N], rAzI[VT_N]; };
+struct ViPatchSrc {
+  const ViPatch &p; int i0, j0;      // patch origin: cell (li, lj) is column (i0 - 1 + li, j0 - 1 + lj)
+  __device__ int e(int i, int j) const { return (j - j0 + 1) * VT_W + (i - i0 + 1); }
+  __device__ double u(int i, int j) const { return p.u[e(i, j)]; }
+  __device__ double v(int i, int j) const { return p.v[e(i, j)]; }
+  __device__ double hW(int i, int j) const { return p.hW[e(i, j)]; }
+  __device__ double hS(int i, int j) const { return p.hS[e(i, j)]; }
+  __device__ double dxG(int i, int j) const { return p.dxG[e(i, j)]; }
+  __device__ double dyG(int i, int j) const { return p.dyG[e(i, j)]; }
+  __device__ double dxC(int i, int j) const { return p.dxC[e(i, j)]; }
+  __device__ double dyC(int i, int j) const { return p.dyC[e(i, j)]; }
+  __device__ double rAzI(int i, int j) const { return p.rAzI[e(i, j)]; }
+};
+
+// MOM_CALC_HFACZ (hZoption = 0): open-water fraction at the vorticity point
+template <class F>
+__device__ inline double vi_hfacz(const TileGrid &g, const F &f, int i, int j) {
+  if (i < 2 - g.OLx || j < 2 - g.OLy) return 0.;
+  double h = fmin(f.hW(i, j), f.hW(i, j - 1));
+  h = fmin(f.hS(i, j), h);
+  h = fmin(f.hS(i - 1, j), h);
+  return h;
+}
 
 // MOM_CALC_KE (mom_calc_ke.F:55-125), zero outside 1-OL..sN+OL-1 like the zero-initialised slab
-__device__ inline double vi_ke(const TileGrid &g, const MomState &st, int KEscheme, int k, int i, int j) {
+template <class F>
+__device__ inline double vi_ke(const TileGrid &g, const F &f, int KEscheme, int k, int i, int j) {
   if (i > g.sNx + g.OLx - 1 || j > g.sNy + g.OLy - 1) return 0.;
-  const double u0 = VU(i, j), u1 = VU(i + 1, j), v0 = VV(i, j), v1 = VV(i, j + 1);
+  const double u0 = f.u(i, j), u1 = f.u(i + 1, j), v0 = f.v(i, j), v1 = f.v(i, j + 1);
   if (KEscheme == -1) return 0.125 * ((u0 + u1) * (u0 + u1) + (v0 + v1) * (v0 + v1));
   if (KEscheme == 0) return 0.25 * ((u0 * u0 + u1 * u1) + (v0 * v0 + v1 * v1));
   if (KEscheme == 1)
     return 0.25 * ((u0 * u0 * g.rAw[g.s(i, j)] + u1 * u1 * g.rAw[g.s(i + 1, j)]) +
                    (v0 * v0 * g.rAs[g.s(i, j)] + v1 * v1 * g.rAs[g.s(i, j + 1)])) * g.recip_rA[g.s(i, j)];
   if (KEscheme == 2)
-    return 0.25 * ((u0 * u0 * g.hFacW[g.s3(i, j, k)] + u1 * u1 * g.hFacW[g.s3(i + 1, j, k)]) +
-                   (v0 * v0 * g.hFacS[g.s3(i, j, k)] + v1 * v1 * g.hFacS[g.s3(i, j + 1, k)])) * g.recip_hFacC[g.s3(i, j, k)];
-  return 0.25 * ((u0 * u0 * g.hFacW[g.s3(i, j, k)] * g.rAw[g.s(i, j)] + u1 * u1 * g.hFacW[g.s3(i + 1, j, k)] * g.rAw[g.s(i + 1, j)]) +
-                 (v0 * v0 * g.hFacS[g.s3(i, j, k)] * g.rAs[g.s(i, j)] + v1 * v1 * g.hFacS[g.s3(i, j + 1, k)] * g.rAs[g.s(i, j + 1)])) *
+    return 0.25 * ((u0 * u0 * f.hW(i, j) + u1 * u1 * f.hW(i + 1, j)) + (v0 * v0 * f.hS(i, j) + v1 * v1 * f.hS(i, j + 1))) *
+           g.recip_hFacC[g.s3(i, j, k)];
+  return 0.25 * ((u0 * u0 * f.hW(i, j) * g.rAw[g.s(i, j)] + u1 * u1 * f.hW(i + 1, j) * g.rAw[g.s(i + 1, j)]) +
+                 (v0 * v0 * f.hS(i, j) * g.rAs[g.s(i, j)] + v1 * v1 * f.hS(i, j + 1) * g.rAs[g.s(i, j + 1)])) *
          g.recip_hFacC[g.s3(i, j, k)] * g.recip_rA[g.s(i, j)];
 }
 
-// MOM_CALC_RELVORT3 (mom_calc_relvort3.F:64-304) of a slab pair (uF, vF), CALC_CS_CORNER_EXTENDED undefined
-__device__ inline double vi_relvort3(const TileGrid &g, const double *uF, const double *vF, int csCorners, int myFace, int i, int j) {
+// MOM_CALC_RELVORT3 (mom_calc_relvort3.F:64-304), CALC_CS_CORNER_EXTENDED undefined
+template <class F>
+__device__ inline double vi_relvort3(const TileGrid &g, const F &f, int csCorners, int myFace, int i, int j) {
   if (i < 2 - g.OLx || j < 2 - g.OLy) return 0.;
-  const double rz = g.recip_rAz[g.s(i, j)];
-  const double vdy = vF[g.s(i, j)] * g.dyC[g.s(i, j)], vdym = vF[g.s(i - 1, j)] * g.dyC[g.s(i - 1, j)];
-  const double udx = uF[g.s(i, j)] * g.dxC[g.s(i, j)], udxm = uF[g.s(i, j - 1)] * g.dxC[g.s(i, j - 1)];
+  const double rz = f.rAzI(i, j);
+  const double vdy = f.v(i, j) * f.dyC(i, j), vdym = f.v(i - 1, j) * f.dyC(i - 1, j);
+  const double udx = f.u(i, j) * f.dxC(i, j), udxm = f.u(i, j - 1) * f.dxC(i, j - 1);
   if ((csCorners & 1) && i == 1 && j == 1) return +rz * ((vdy - udx) + udxm);
   if ((csCorners & 2) && i == g.sNx + 1 && j == 1) {
     if (myFace == 2) return +rz * ((-udx - vdym) + udxm);
@@ -75,11 +115,12 @@ __device__ inline double vi_relvort3(const TileGrid &g, const double *uF, const 
   return rz * ((vdy - vdym) - (udx - udxm));
 }
 
-// MOM_CALC_HDIV, hDivScheme = 2 (mom_calc_hdiv.F:56-72) of a slab pair
-__device__ inline double vi_hdiv(const TileGrid &g, const double *uF, const double *vF, int k, int i, int j) {
+// MOM_CALC_HDIV, hDivScheme = 2 (mom_calc_hdiv.F:56-72)
+template <class F>
+__device__ inline double vi_hdiv(const TileGrid &g, const F &f, int k, int i, int j) {
   if (i > g.sNx + g.OLx - 1 || j > g.sNy + g.OLy - 1) return 0.;
-  return ((uF[g.s(i + 1, j)] * g.dyG[g.s(i + 1, j)] * g.hFacW[g.s3(i + 1, j, k)] - uF[g.s(i, j)] * g.dyG[g.s(i, j)] * g.hFacW[g.s3(i, j, k)]) +
-          (vF[g.s(i, j + 1)] * g.dxG[g.s(i, j + 1)] * g.hFacS[g.s3(i, j + 1, k)] - vF[g.s(i, j)] * g.dxG[g.s(i, j)] * g.hFacS[g.s3(i, j, k)])) *
+  return ((f.u(i + 1, j) * f.dyG(i + 1, j) * f.hW(i + 1, j) - f.u(i, j) * f.dyG(i, j) * f.hW(i, j)) +
+          (f.v(i, j + 1) * f.dxG(i, j + 1) * f.hS(i, j + 1) - f.v(i, j) * f.dxG(i, j) * f.hS(i, j))) *
          g.recip_rA[g.s(i, j)] * g.recip_hFacC[g.s3(i, j, k)];
 }
 
@@ -114,16 +155,16 @@ static __global__ void __launch_bounds__(256) vi_stage1_kernel(TileGrid g, MomSt
   const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
   const size_t s = g.s(i, j);
-  const double hz = mom_hfacz(g, k, i, j);
+  const ViGlobalSrc f{g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k};
+  const double hz = vi_hfacz(g, f, i, j);
   w.hFacZ[s] = hz;
-  w.KE[s] = vi_ke(g, st, p.selectKEscheme, k, i, j);
-  const double *uF = st.u + g.slab * (size_t)(k - 1), *vF = st.v + g.slab * (size_t)(k - 1);
-  double z = vi_relvort3(g, uF, vF, p.csCorners, p.myFace, i, j);
+  w.KE[s] = vi_ke(g, f, p.selectKEscheme, k, i, j);
+  double z = vi_relvort3(g, f, p.csCorners, p.myFace, i, j);
   if (hz == 0.) z = 0.;                                   // mom_vecinv.F:292-300
   w.vort3[s] = z;
   // MOM_CALC_ABSVORT3 (mom_calc_absvort3.F:34-46)
   w.omega3[s] = g.fCoriG[s] * (p.useCoriolis ? 1. : 0.) + z * (p.m.momAdvection ? 1. : 0.);
-  w.hDiv[s] = p.m.momViscosity ? vi_hdiv(g, uF, vF, k, i, j) : 0.;
+  w.hDiv[s] = p.m.momViscosity ? vi_hdiv(g, f, k, i, j) : 0.;
 }
 
 // ---- stage 2 (biharmonic): MOM_VI_DEL2UV (mom_vi_del2uv.F:78-124) --------------------------------
@@ -153,8 +194,9 @@ static __global__ void __launch_bounds__(256) vi_star_kernel(TileGrid g, ViPar p
   const int j = 1 - g.OLy + blockIdx.y * 8 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
   const size_t s = g.s(i, j);
-  w.dStar[s] = vi_hdiv(g, w.del2u, w.del2v, k, i, j);
-  w.zStar[s] = vi_relvort3(g, w.del2u, w.del2v, p.csCorners, p.myFace, i, j);
+  const ViGlobalSrc f{g, w.del2u, w.del2v, k};
+  w.dStar[s] = vi_hdiv(g, f, k, i, j);
+  w.zStar[s] = vi_relvort3(g, f, p.csCorners, p.myFace, i, j);
 }
 
 // ---- accessors of the level's intermediate fields ------------------------------------------------
@@ -172,20 +214,19 @@ struct ViSlabAcc {
   __device__ double dStar(int i, int j) const { return w.dStar[g.s(i, j)]; }
   __device__ double zStar(int i, int j) const { return w.zStar[g.s(i, j)]; }
 };
+template <class F>
 struct ViFusedAcc {
-  const TileGrid &g; const MomState &st; const ViPar &p; int k;
-  __device__ double hFacZ(int i, int j) const { return mom_hfacz(g, k, i, j); }
+  const TileGrid &g; const F &f; const ViPar &p; int k;
+  __device__ double hFacZ(int i, int j) const { return vi_hfacz(g, f, i, j); }
   __device__ double vort3(int i, int j) const {
-    if (mom_hfacz(g, k, i, j) == 0.) return 0.;
-    return vi_relvort3(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), p.csCorners, p.myFace, i, j);
+    if (vi_hfacz(g, f, i, j) == 0.) return 0.;
+    return vi_relvort3(g, f, p.csCorners, p.myFace, i, j);
   }
   __device__ double omega3(int i, int j) const {
     return g.fCoriG[g.s(i, j)] * (p.useCoriolis ? 1. : 0.) + vort3(i, j) * (p.m.momAdvection ? 1. : 0.);
   }
-  __device__ double KE(int i, int j) const { return vi_ke(g, st, p.selectKEscheme, k, i, j); }
-  __device__ double hDiv(int i, int j) const {
-    return vi_hdiv(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k, i, j);
-  }
+  __device__ double KE(int i, int j) const { return vi_ke(g, f, p.selectKEscheme, k, i, j); }
+  __device__ double hDiv(int i, int j) const { return vi_hdiv(g, f, k, i, j); }
   __device__ double del2u(int, int) const { return 0.; }
   __device__ double del2v(int, int) const { return 0.; }
   __device__ double dStar(int, int) const { return 0.; }
@@ -194,10 +235,9 @@ struct ViFusedAcc {
 
 // ViTileAcc: the CTA has evaluated them once per level for its 34 x 10 patch of columns (one-point rim)
 // into shared memory; what the resident step uses.
-constexpr int VT_X = 32, VT_Y = 8, VT_W = VT_X + 2, VT_H = VT_Y + 2, VT_N = VT_W * VT_H;
 struct ViTile { double hFacZ[VT_N], vort3[VT_N], omega3[VT_N], KE[VT_N], hDiv[VT_N]; };
 struct ViTileAcc {
-  const ViTile &t; int i0, j0;      // patch origin: cell (li, lj) is column (i0 - 1 + li, j0 - 1 + lj)
+  const ViTile &t; int i0, j0;
   __device__ int e(int i, int j) const { return (j - j0 + 1) * VT_W + (i - i0 + 1); }
   __device__ double hFacZ(int i, int j) const { return t.hFacZ[e(i, j)]; }
   __device__ double vort3(int i, int j) const { return t.vort3[e(i, j)]; }
@@ -209,18 +249,35 @@ struct ViTileAcc {
   __device__ double dStar(int, int) const { return 0.; }
   __device__ double zStar(int, int) const { return 0.; }
 };
-// fills the patch for level k (all threads of a VT_X x VT_Y CTA; caller synchronises)
-__device__ inline void vi_fill_tile(ViTile &t, const TileGrid &g, const MomState &st, const ViPar &p, int k, int i0, int j0, int tid) {
-  const ViFusedAcc a{g, st, p, k};
+// k-invariant metrics of the patch (once per CTA) and the raw fields of level k (all threads of a
+// VT_X x VT_Y CTA; caller synchronises).  Columns past the halo'd slab are clamped; they are never consumed.
+__device__ inline void vi_fill_patch_metrics(ViPatch &pt, const TileGrid &g, int i0, int j0, int tid) {
   for (int e = tid; e < VT_N; e += VT_X * VT_Y) {
-    const int i = i0 - 1 + e % VT_W, j = j0 - 1 + e / VT_W;
+    const size_t s = g.s(min(i0 - 1 + e % VT_W, g.sNx + g.OLx), min(j0 - 1 + e / VT_W, g.sNy + g.OLy));
+    pt.dxG[e] = g.dxG[s]; pt.dyG[e] = g.dyG[s]; pt.dxC[e] = g.dxC[s]; pt.dyC[e] = g.dyC[s]; pt.rAzI[e] = g.recip_rAz[s];
+  }
+}
+__device__ inline void vi_fill_patch(ViPatch &pt, const TileGrid &g, const MomState &st, int k, int i0, int j0, int tid) {
+  for (int e = tid; e < VT_N; e += VT_X * VT_Y) {
+    const size_t q = g.s3(min(i0 - 1 + e % VT_W, g.sNx + g.OLx), min(j0 - 1 + e / VT_W, g.sNy + g.OLy), k);
+    pt.u[e] = st.u[q]; pt.v[e] = st.v[q]; pt.hW[e] = g.hFacW[q]; pt.hS[e] = g.hFacS[q];
+  }
+}
+// derived fields of the patch from its raw fields; the rim cells whose stencil leaves the patch read global memory
+__device__ inline void vi_fill_tile(ViTile &t, const ViPatch &pt, const TileGrid &g, const MomState &st, const ViPar &p, int k,
+                                    int i0, int j0, int tid) {
+  const ViPatchSrc fp{pt, i0, j0};
+  const ViGlobalSrc fg{g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k};
+  for (int e = tid; e < VT_N; e += VT_X * VT_Y) {
+    const int li = e % VT_W, lj = e / VT_W, i = i0 - 1 + li, j = j0 - 1 + lj;
     double hz = 0., z = 0., om = 0., ke = 0., hd = 0.;
     if (i <= g.sNx + g.OLx && j <= g.sNy + g.OLy) {
-      hz = a.hFacZ(i, j);
-      z = hz == 0. ? 0. : vi_relvort3(g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), p.csCorners, p.myFace, i, j);
+      const bool lo = li >= 1 && lj >= 1, hi = li <= VT_W - 2 && lj <= VT_H - 2;
+      hz = lo ? vi_hfacz(g, fp, i, j) : vi_hfacz(g, fg, i, j);
+      if (hz != 0.) z = lo ? vi_relvort3(g, fp, p.csCorners, p.myFace, i, j) : vi_relvort3(g, fg, p.csCorners, p.myFace, i, j);
       om = g.fCoriG[g.s(i, j)] * (p.useCoriolis ? 1. : 0.) + z * (p.m.momAdvection ? 1. : 0.);
-      ke = a.KE(i, j);
-      if (p.m.momViscosity) hd = a.hDiv(i, j);
+      ke = hi ? vi_ke(g, fp, p.selectKEscheme, k, i, j) : vi_ke(g, fg, p.selectKEscheme, k, i, j);
+      if (p.m.momViscosity) hd = hi ? vi_hdiv(g, fp, k, i, j) : vi_hdiv(g, fg, k, i, j);
     }
     t.hFacZ[e] = hz; t.vort3[e] = z; t.omega3[e] = om; t.KE[e] = ke; t.hDiv[e] = hd;
   }
@@ -228,11 +285,11 @@ __device__ inline void vi_fill_tile(ViTile &t, const TileGrid &g, const MomState
 
 // MOM_VI_U_CORIOLIS / MOM_VI_V_CORIOLIS (mom_vi_{u,v}_coriolis.F:54-197), upwindVort3 = .FALSE.;
 // absV selects omega3 (absolute) or vort3 (relative) as the advected vorticity
-template <class A>
-__device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
+template <class F, class A>
+__device__ inline double vi_u_coriolis(const TileGrid &g, const F &f, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
   const double epsil = 1e-9, oneThird = 1. / 3.;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
-  auto vdxh = [&](int ii, int jj) { return VV(ii, jj) * g.dxG[g.s(ii, jj)] * g.hFacS[g.s3(ii, jj, k)]; };
+  auto vdxh = [&](int ii, int jj) { return f.v(ii, jj) * f.dxG(ii, jj) * f.hS(ii, jj); };
   auto om = [&](int ii, int jj) { return absV ? a.omega3(ii, jj) : a.vort3(ii, jj); };
   auto rh = [&](int ii, int jj) { const double h = a.hFacZ(ii, jj); return h == 0. ? 0. : 1. / h; };
   auto rz = [&](int ii, int jj) { return rh(ii, jj) * om(ii, jj); };
@@ -245,8 +302,8 @@ __device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, co
     r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
   } else if (sch == 1) {
     const double h0 = a.hFacZ(i, j), h1 = a.hFacZ(i, j + 1);
-    const double vBarXY = 0.5 * ((VV(i, j) * g.dxG[s] * h0 + VV(i - 1, j) * g.dxG[g.s(i - 1, j)] * h0) +
-                                 (VV(i, j + 1) * g.dxG[g.s(i, j + 1)] * h1 + VV(i - 1, j + 1) * g.dxG[g.s(i - 1, j + 1)] * h1)) /
+    const double vBarXY = 0.5 * ((f.v(i, j) * f.dxG(i, j) * h0 + f.v(i - 1, j) * f.dxG(i - 1, j) * h0) +
+                                 (f.v(i, j + 1) * f.dxG(i, j + 1) * h1 + f.v(i - 1, j + 1) * f.dxG(i - 1, j + 1) * h1)) /
                           fmax(epsil, h0 + h1);
     const double vort3u = 0.5 * (om(i, j) + om(i, j + 1));
     r = +vort3u * vBarXY * g.recip_dxC[s] * g.maskW[s3];
@@ -262,15 +319,15 @@ __device__ inline double vi_u_coriolis(const TileGrid &g, const MomState &st, co
     r = +((vort3mj + vort3ij) + (vort3mp + vort3ip)) * 0.25 * g.recip_dxC[s] * g.maskW[s3];
   }
   if (p.useJamartMomAdv && i <= g.sNx + g.OLx - 1)
-    r = r * 4. * g.hFacW[s3] /
-        fmax(epsil, (g.hFacS[s3] + g.hFacS[g.s3(i - 1, j, k)]) + (g.hFacS[g.s3(i, j + 1, k)] + g.hFacS[g.s3(i - 1, j + 1, k)]));
+    r = r * 4. * f.hW(i, j) /
+        fmax(epsil, (f.hS(i, j) + f.hS(i - 1, j)) + (f.hS(i, j + 1) + f.hS(i - 1, j + 1)));
   return r;
 }
-template <class A>
-__device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
+template <class F, class A>
+__device__ inline double vi_v_coriolis(const TileGrid &g, const F &f, const ViPar &p, const A &a, bool absV, int k, int i, int j) {
   const double epsil = 1e-9, oneThird = 1. / 3.;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
-  auto udyh = [&](int ii, int jj) { return VU(ii, jj) * g.dyG[g.s(ii, jj)] * g.hFacW[g.s3(ii, jj, k)]; };
+  auto udyh = [&](int ii, int jj) { return f.u(ii, jj) * f.dyG(ii, jj) * f.hW(ii, jj); };
   auto om = [&](int ii, int jj) { return absV ? a.omega3(ii, jj) : a.vort3(ii, jj); };
   auto rh = [&](int ii, int jj) { const double h = a.hFacZ(ii, jj); return h == 0. ? 0. : 1. / h; };
   auto rz = [&](int ii, int jj) { return rh(ii, jj) * om(ii, jj); };
@@ -283,8 +340,8 @@ __device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, co
     r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
   } else if (sch == 1) {
     const double h0 = a.hFacZ(i, j), h1 = a.hFacZ(i + 1, j);
-    const double uBarXY = 0.5 * ((VU(i, j) * g.dyG[s] * h0 + VU(i, j - 1) * g.dyG[g.s(i, j - 1)] * h0) +
-                                 (VU(i + 1, j) * g.dyG[g.s(i + 1, j)] * h1 + VU(i + 1, j - 1) * g.dyG[g.s(i + 1, j - 1)] * h1)) /
+    const double uBarXY = 0.5 * ((f.u(i, j) * f.dyG(i, j) * h0 + f.u(i, j - 1) * f.dyG(i, j - 1) * h0) +
+                                 (f.u(i + 1, j) * f.dyG(i + 1, j) * h1 + f.u(i + 1, j - 1) * f.dyG(i + 1, j - 1) * h1)) /
                           fmax(epsil, h0 + h1);
     const double vort3v = 0.5 * (om(i, j) + om(i + 1, j));
     r = -vort3v * uBarXY * g.recip_dyC[s] * g.maskS[s3];
@@ -300,26 +357,27 @@ __device__ inline double vi_v_coriolis(const TileGrid &g, const MomState &st, co
     r = -((vort3im + vort3ij) + (vort3pm + vort3pj)) * 0.25 * g.recip_dyC[s] * g.maskS[s3];
   }
   if (p.useJamartMomAdv && j <= g.sNy + g.OLy - 1)
-    r = r * 4. * g.hFacS[s3] /
-        fmax(epsil, (g.hFacW[s3] + g.hFacW[g.s3(i, j - 1, k)]) + (g.hFacW[g.s3(i + 1, j, k)] + g.hFacW[g.s3(i + 1, j - 1, k)]));
+    r = r * 4. * f.hS(i, j) /
+        fmax(epsil, (f.hW(i, j) + f.hW(i, j - 1)) + (f.hW(i + 1, j) + f.hW(i + 1, j - 1)));
   return r;
 }
 
 // MOM_VI_CORIOLIS (mom_vi_coriolis.F:48-190)
-__device__ inline void vi_coriolis(const TileGrid &g, const MomState &st, int sch, int k, int i, int j, double &uCf, double &vCf) {
+template <class F>
+__device__ inline void vi_coriolis(const TileGrid &g, const F &f, int sch, int k, int i, int j, double &uCf, double &vCf) {
   const double epsil = 1e-9;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
-  auto vdxh = [&](int ii, int jj) { return VV(ii, jj) * g.dxG[g.s(ii, jj)] * g.hFacS[g.s3(ii, jj, k)]; };
-  auto udyh = [&](int ii, int jj) { return VU(ii, jj) * g.dyG[g.s(ii, jj)] * g.hFacW[g.s3(ii, jj, k)]; };
+  auto vdxh = [&](int ii, int jj) { return f.v(ii, jj) * f.dxG(ii, jj) * f.hS(ii, jj); };
+  auto udyh = [&](int ii, int jj) { return f.u(ii, jj) * f.dyG(ii, jj) * f.hW(ii, jj); };
   {
     const double f0 = g.fCoriG[s], f1 = g.fCoriG[g.s(i, j + 1)];
     if (sch == 0) {
-      const double vBarXY = 0.25 * ((VV(i, j) * g.dxG[s] + VV(i - 1, j) * g.dxG[g.s(i - 1, j)]) +
-                                    (VV(i, j + 1) * g.dxG[g.s(i, j + 1)] + VV(i - 1, j + 1) * g.dxG[g.s(i - 1, j + 1)]));
+      const double vBarXY = 0.25 * ((f.v(i, j) * f.dxG(i, j) + f.v(i - 1, j) * f.dxG(i - 1, j)) +
+                                    (f.v(i, j + 1) * f.dxG(i, j + 1) + f.v(i - 1, j + 1) * f.dxG(i - 1, j + 1)));
       uCf = +0.5 * (f0 + f1) * vBarXY * g.recip_dxC[s] * g.maskW[s3];
     } else if (sch == 1) {
       const double vBarXY = ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1))) /
-                            fmax(epsil, (g.hFacS[s3] + g.hFacS[g.s3(i - 1, j, k)]) + (g.hFacS[g.s3(i, j + 1, k)] + g.hFacS[g.s3(i - 1, j + 1, k)]));
+                            fmax(epsil, (f.hS(i, j) + f.hS(i - 1, j)) + (f.hS(i, j + 1) + f.hS(i - 1, j + 1)));
       uCf = +0.5 * (f0 + f1) * vBarXY * g.recip_dxC[s] * g.maskW[s3];
     } else if (sch == 2) {
       const double vBarXY = 0.25 * ((vdxh(i, j) + vdxh(i - 1, j)) + (vdxh(i, j + 1) + vdxh(i - 1, j + 1)));
@@ -332,12 +390,12 @@ __device__ inline void vi_coriolis(const TileGrid &g, const MomState &st, int sc
   {
     const double f0 = g.fCoriG[s], f1 = g.fCoriG[g.s(i + 1, j)];
     if (sch == 0) {
-      const double uBarXY = 0.25 * ((VU(i, j) * g.dyG[s] + VU(i, j - 1) * g.dyG[g.s(i, j - 1)]) +
-                                    (VU(i + 1, j) * g.dyG[g.s(i + 1, j)] + VU(i + 1, j - 1) * g.dyG[g.s(i + 1, j - 1)]));
+      const double uBarXY = 0.25 * ((f.u(i, j) * f.dyG(i, j) + f.u(i, j - 1) * f.dyG(i, j - 1)) +
+                                    (f.u(i + 1, j) * f.dyG(i + 1, j) + f.u(i + 1, j - 1) * f.dyG(i + 1, j - 1)));
       vCf = -0.5 * (f0 + f1) * uBarXY * g.recip_dyC[s] * g.maskS[s3];
     } else if (sch == 1) {
       const double uBarXY = ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1))) /
-                            fmax(epsil, (g.hFacW[s3] + g.hFacW[g.s3(i, j - 1, k)]) + (g.hFacW[g.s3(i + 1, j, k)] + g.hFacW[g.s3(i + 1, j - 1, k)]));
+                            fmax(epsil, (f.hW(i, j) + f.hW(i, j - 1)) + (f.hW(i + 1, j) + f.hW(i + 1, j - 1)));
       vCf = -0.5 * (f0 + f1) * uBarXY * g.recip_dyC[s] * g.maskS[s3];
     } else if (sch == 2) {
       const double uBarXY = 0.25 * ((udyh(i, j) + udyh(i, j - 1)) + (udyh(i + 1, j) + udyh(i + 1, j - 1)));
@@ -376,21 +434,21 @@ __device__ inline double vi_vertshear(const TileGrid &g, const MomState &st, con
 }
 
 // MOM_{U,V}_SIDEDRAG with the vector-invariant del2u / del2v (sideDragFactor > 0, constant viscosity)
-template <class A>
-__device__ inline double vi_sidedrag(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, int isV, int k, int i, int j) {
+template <class F, class A>
+__device__ inline double vi_sidedrag(const TileGrid &g, const F &f, const ViPar &p, const A &a, int isV, int k, int i, int j) {
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
   if (!isV) {
-    const double hS = g.hFacW[s3] - a.hFacZ(i, j), hN = g.hFacW[s3] - a.hFacZ(i, j + 1);
+    const double hS = f.hW(i, j) - a.hFacZ(i, j), hN = f.hW(i, j) - a.hFacZ(i, j + 1);
     const double d2 = p.m.useBiharmonicVisc ? a.del2u(i, j) : 0.;
-    const double t = p.m.viscAhZ * VU(i, j) - p.m.viscA4Z * d2;
+    const double t = p.m.viscAhZ * f.u(i, j) - p.m.viscA4Z * d2;
     return -g.recip_hFacW[s3] * g.recip_drF[k - 1] * g.recip_rAw[s] *
            (hS * g.dxV[s] * g.recip_dyU[s] * t + hN * g.dxV[g.s(i, j + 1)] * g.recip_dyU[g.s(i, j + 1)] * t) * g.drF[k - 1] *
            p.m.sideDragFactor;
   }
   const double cf = g.cosFacV[j + g.OLy - 1];
-  const double hW = g.hFacS[s3] - a.hFacZ(i, j), hE = g.hFacS[s3] - a.hFacZ(i + 1, j);
+  const double hW = f.hS(i, j) - a.hFacZ(i, j), hE = f.hS(i, j) - a.hFacZ(i + 1, j);
   const double d2 = p.m.useBiharmonicVisc ? a.del2v(i, j) : 0.;
-  const double t = p.m.viscAhZ * VV(i, j) * cf - p.m.viscA4Z * d2 * cf;
+  const double t = p.m.viscAhZ * f.v(i, j) * cf - p.m.viscA4Z * d2 * cf;
   return -g.recip_hFacS[s3] * g.recip_drF[k - 1] * g.recip_rAs[s] *
          (hW * g.dyU[s] * g.recip_dxV[s] * t + hE * g.dyU[g.s(i + 1, j)] * g.recip_dxV[g.s(i + 1, j)] * t) * g.drF[k - 1] *
          p.m.sideDragFactor;
@@ -401,8 +459,8 @@ struct ViOut { double gU, gV, guDiss, gvDiss, fVerUkp, fVerVkp; };
 // Tendencies of one point (mom_vecinv.F:308-927).  inRange: the point is inside iMin..iMax x jMin..jMax
 // (outside, only MOM_VI_HDISSIP's own range is written); fVer?km: viscous vertical flux at the upper
 // interface; o.fVer?kp is valid only when inRange, momViscosity and not implicitViscosity.
-template <class A>
-__device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const ViPar &p, const A &a, int k, int i, int j,
+template <class F, class A>
+__device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const F &f, const ViPar &p, const A &a, int k, int i, int j,
                                 bool inRange, double fVerUkm, double fVerVkm) {
   ViOut o;
   const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
@@ -441,16 +499,16 @@ __device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const ViP
         o.fVerUkp = m.vfFacMom * 1. * mom_u_rvisc(g, st, m, k + 1, i, j);
         uD = uD - rhW * rdrF * g.recip_rAw[s] * (o.fVerUkp - fVerUkm) * m.rkSign;
       }
-      if (m.no_slip_sides) uD = uD + vi_sidedrag(g, st, p, a, 0, k, i, j);
+      if (m.no_slip_sides) uD = uD + vi_sidedrag(g, f, p, a, 0, k, i, j);
       if (m.bottomDragTerms)
-        uD = uD + (-mom_botdrag(g, st, m, k, 0, i, j, true, quad0 ? a.KE(i, j) + a.KE(i - 1, j) : 0.) * VU(i, j) * rhW * rdrF);
+        uD = uD + (-mom_botdrag(g, st, m, k, 0, i, j, true, quad0 ? a.KE(i, j) + a.KE(i - 1, j) : 0.) * f.u(i, j) * rhW * rdrF);
       if (!m.implicitViscosity) {
         o.fVerVkp = m.vfFacMom * 1. * mom_v_rvisc(g, st, m, k + 1, i, j);
         vD = vD - rhS * rdrF * g.recip_rAs[s] * (o.fVerVkp - fVerVkm) * m.rkSign;
       }
-      if (m.no_slip_sides) vD = vD + vi_sidedrag(g, st, p, a, 1, k, i, j);
+      if (m.no_slip_sides) vD = vD + vi_sidedrag(g, f, p, a, 1, k, i, j);
       if (m.bottomDragTerms)
-        vD = vD + (-mom_botdrag(g, st, m, k, 1, i, j, true, quad0 ? a.KE(i, j) + a.KE(i, j - 1) : 0.) * VV(i, j) * rhS * rdrF);
+        vD = vD + (-mom_botdrag(g, st, m, k, 1, i, j, true, quad0 ? a.KE(i, j) + a.KE(i, j - 1) : 0.) * f.v(i, j) * rhS * rdrF);
     }
   }
   o.guDiss = uD;
@@ -461,15 +519,15 @@ __device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const ViP
   double tU = 0., tV = 0.;
   if (p.useCoriolis && !(m.useCDscheme || (p.useAbsVorticity && m.momAdvection))) {
     if (p.useAbsVorticity) {
-      tU = vi_u_coriolis(g, st, p, a, true, k, i, j);
-      tV = vi_v_coriolis(g, st, p, a, true, k, i, j);
+      tU = vi_u_coriolis(g, f, p, a, true, k, i, j);
+      tV = vi_v_coriolis(g, f, p, a, true, k, i, j);
     } else {
-      vi_coriolis(g, st, m.selectCoriScheme, k, i, j, tU, tV);
+      vi_coriolis(g, f, m.selectCoriScheme, k, i, j, tU, tV);
     }
   }
   if (m.momAdvection) {
-    tU = tU + vi_u_coriolis(g, st, p, a, p.useAbsVorticity != 0, k, i, j);
-    tV = tV + vi_v_coriolis(g, st, p, a, p.useAbsVorticity != 0, k, i, j);
+    tU = tU + vi_u_coriolis(g, f, p, a, p.useAbsVorticity != 0, k, i, j);
+    tV = tV + vi_v_coriolis(g, f, p, a, p.useAbsVorticity != 0, k, i, j);
     tU = tU + vi_vertshear(g, st, p, 0, k, i, j);
     tV = tV + vi_vertshear(g, st, p, 1, k, i, j);
     const double ke = a.KE(i, j);
@@ -495,12 +553,14 @@ __global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, V
   if (FUSED) {
     // outside MOM_VI_HDISSIP's range nothing is evaluated (the accessors would read past the slab)
     const bool inner = i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1 && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1;
-    if (inner) o = vi_cell(g, st, p, ViFusedAcc{g, st, p, k}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
+    const ViGlobalSrc f{g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k};
+    if (inner) o = vi_cell(g, st, f, p, ViFusedAcc<ViGlobalSrc>{g, f, p, k}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
     else { o.guDiss = 0.; o.gvDiss = 0.; }
   } else {
     // hDiv keeps MOM_VI_DEL2UV's last facet-corner fill (direction 2) when that routine ran
     const int dirH = (p.m.useBiharmonicVisc && p.csCorners) ? 2 : 0;
-    o = vi_cell(g, st, p, ViSlabAcc{g, w, p.csCorners, dirH}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
+    const ViGlobalSrc f{g, st.u + g.slab * (size_t)(k - 1), st.v + g.slab * (size_t)(k - 1), k};
+    o = vi_cell(g, st, f, p, ViSlabAcc{g, w, p.csCorners, dirH}, k, i, j, inRange, fVerUkm[s], fVerVkm[s]);
   }
   guDiss[s] = o.guDiss;
   gvDiss[s] = o.gvDiss;
@@ -510,7 +570,5 @@ __global__ void __launch_bounds__(256) vi_tend_kernel(TileGrid g, MomState st, V
   gV[s3] = o.gV;
 }
 
-#undef VU
-#undef VV
 
 }  // namespace mg

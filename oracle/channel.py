@@ -24,7 +24,8 @@ class ChannelOracle:
         self.P = dict(abEps=0.01, deltaTtracer=params.get("deltaTMom", 1200.0), diffKhT=0.0, diffK4T=0.0,
                       diffKrT=0.0, viscAr=0.0, tempAdvScheme=2, tempStepping=1, cg2dMaxIters=150,
                       momForcing=1, momDissip_In_AB=1, useSRCGSolver=0, buoyancyLinear=0, gravity=9.81,
-                      tAlpha=2e-4, sBeta=0.0, rhoNil=999.8, rhoConst=999.8, ivdc_kappa=0.0)
+                      tAlpha=2e-4, sBeta=0.0, rhoNil=999.8, rhoConst=999.8, ivdc_kappa=0.0,
+                      vectorInvariantMomentum=0)
         extra = {k: params[k] for k in list(params) if k in self.P}
         self.P.update(extra)
         self.o = Oracle(grid, {k: v for k, v in params.items() if k not in self.P})
@@ -109,8 +110,10 @@ class ChannelOracle:
                 if buoy:
                     o.calc_phi_hyd(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, self.rho, self.g.rF, self.g.rC,
                                    P["gravity"], 1.0 / P["rhoConst"], self.phi0, phiF, phiC, z, zy)
-                o.mom_fluxform(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, self.kapU, self.kapU, fU[kUp - 1], fVv[kUp - 1],
-                               fU[kDown - 1], fVv[kDown - 1], gd, hd, s["uVel"], s["vVel"], s["wVel"], s["gU"], s["gV"])
+                # dynamics.F:517-533: MOM_FLUXFORM or, with vectorInvariantMomentum, MOM_VECINV
+                mom = o.mom_vecinv if P["vectorInvariantMomentum"] else o.mom_fluxform
+                mom(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, self.kapU, self.kapU, fU[kUp - 1], fVv[kUp - 1],
+                    fU[kDown - 1], fVv[kDown - 1], gd, hd, s["uVel"], s["vVel"], s["wVel"], s["gU"], s["gV"])
                 o.timestep(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, z, zy, gd, hd, s["surfForcU"], s["surfForcV"],
                            P["momForcing"], P["momDissip_In_AB"], abFac, s["uVel"], s["vVel"], s["gU"], s["gV"],
                            s["guNm1"], s["gvNm1"])

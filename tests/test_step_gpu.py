@@ -28,7 +28,15 @@ def rel(a, b):
     dict(sNx=24, sNy=16, Nr=4, nSx=2, nSy=2, land_frac=0.2, buoyancyLinear=1),
     # IVDC on: density array + convective diffusivity feed the (explicit) vertical diffusion
     dict(sNx=32, sNy=24, Nr=6, land_frac=0.1, buoyancyLinear=1, ivdc_kappa=1.0, selectCoriScheme=1),
-], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat", "buoyancy-flat", "buoyancy-land", "buoyancy-ivdc"])
+    # MOM_VECINV in the dynamics: pipelined kernel (defaults), with land / partial cells / tiles / buoyancy,
+    # absolute vorticity + Jamart + upwind shear + free slip, and the generic kernel (vorticity scheme 3, KE scheme 1)
+    dict(sNx=64, sNy=40, Nr=7, land_frac=0.0, vectorInvariantMomentum=1),
+    dict(sNx=24, sNy=16, Nr=4, nSx=2, nSy=2, land_frac=0.2, vectorInvariantMomentum=1, buoyancyLinear=1),
+    dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, vectorInvariantMomentum=1, useAbsVorticity=1, useJamartMomAdv=1, upwindShear=1,
+         selectVortScheme=2, selectKEscheme=2, selectCoriScheme=3, no_slip_sides=0, no_slip_bottom=0, bottomDragLinear=1e-3),
+    dict(sNx=32, sNy=24, Nr=5, land_frac=0.1, vectorInvariantMomentum=1, selectVortScheme=3, selectKEscheme=1, momDissip_In_AB=0),
+], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat", "buoyancy-flat", "buoyancy-land", "buoyancy-ivdc",
+        "vecinv-flat", "vecinv-land-tiles-buoyancy", "vecinv-absvort", "vecinv-generic"])
 def test_forward_step_matches_oracle(cfg):
     g, P, s = make_channel(**cfg)
     co = ChannelOracle(g, P, s)
@@ -52,6 +60,30 @@ def test_forward_step_matches_oracle(cfg):
                     assert rel(m.get("gtNm1")[..., jj, ii], co.s["gtNm1"][..., jj, ii]) < 1e-14
     finally:
         m.close()
+
+
+def test_vecinv_pipelined_kernel_is_bit_identical_to_the_generic_kernels(monkeypatch):
+    """The same 3 steps with the cp.async pipelined MOM_VECINV kernel, the shared-memory patch kernel and the
+    re-evaluating kernel: the fields must be bit-identical (same expression order everywhere)."""
+    outs = []
+    for env in ({}, {"MITGCM_B200_VI_NOPIPE": "1"}, {"MITGCM_B200_VI_NOPIPE": "1", "MITGCM_B200_VI_NOTILE": "1"}):
+        for k in ("MITGCM_B200_VI_NOPIPE", "MITGCM_B200_VI_NOTILE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g, P, s = make_channel(sNx=48, sNy=40, Nr=6, nSx=2, nSy=1, land_frac=0.15, vectorInvariantMomentum=1, buoyancyLinear=1,
+                               selectVortScheme=0, selectCoriScheme=1)
+        co = ChannelOracle(g, P, s)
+        m = Model(g, P, s, co.op)
+        try:
+            for _ in range(3):
+                m.step()
+            outs.append({n: m.get(n) for n in ("uVel", "vVel", "wVel", "etaN", "gU", "gV", "guNm1", "gvNm1")})
+        finally:
+            m.close()
+    for o in outs[1:]:
+        for n in o:
+            assert np.array_equal(o[n], outs[0][n]), n
 
 
 @pytest.mark.parametrize("shape", [(10, 7, 3, 3, 2, 4), (33, 18, 4, 1, 1, 2), (8, 8, 2, 2, 3, 1)])
