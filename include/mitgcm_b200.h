@@ -177,6 +177,15 @@ void mom_vecinv_b200_(const int *bi, const int *bj, const int *k, const int *iMi
                       const double *uVel, const double *vVel, const double *wVel,
                       double *gU, double *gV, const int *csCorners, const int *myFace);
 
+/* ---- MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R --------------------------
+ * Argument list of pkg/mom_common/mom_{u,v}_implicit_r.F:6-8 (caller dynamics.F:576-579) followed by the COMMON
+ * /DYNVARS_R/ array the routine solves in place (u* in gU, v* in gV).  implicitViscosity only: the tridiagonal of
+ * the vertical viscosity, SOLVE_TRIDIAGONAL per column; momImplVertAdv / selectImplicitDrag >= 1 are refused. */
+void mom_u_implicit_r_b200_(const double *kappaRU, const int *bi, const int *bj, const double *myTime,
+                            const int *myIter, const int *myThid, double *gU);
+void mom_v_implicit_r_b200_(const double *kappaRV, const int *bi, const int *bj, const double *myTime,
+                            const int *myIter, const int *myThid, double *gV);
+
 /* Facet data of the local tiles for the resident step with MI_VECTORINVARIANTMOMENTUM on the cubed
  * sphere: csCorners(nSx*nSy) and myFace(nSx*nSy) as in mom_vecinv_b200_ (tiles bi fast). */
 void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr);

@@ -114,6 +114,59 @@ impldiff_kernel(TileGrid g, const double *__restrict__ kapT, double *__restrict_
   }
 }
 
+// MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R with implicitViscosity (pkg/mom_common/mom_{u,v}_implicit_r.F:100-300;
+// momImplVertAdv = F, selectImplicitDrag = 0) + SOLVE_TRIDIAGONAL: u* (in gU) on i = 1..sNx+1, j = 1..sNy and
+// v* (in gV) on i = 1..sNx, j = 1..sNy+1, one thread per column.   R{g?,kappaR?,recip_hFac?,mask?} W{g?}
+__device__ inline void momimpl_column(const TileGrid &g, const double *__restrict__ kap, const double *__restrict__ rhF,
+                                      const double *__restrict__ mask, double *__restrict__ y, size_t s, double deltaTMom) {
+  const int Nr = g.Nr;
+  double cp[PHYS_NRMAX], yp[PHYS_NRMAX];
+  double cpm = 0., ypm = 0.;
+  size_t s3 = s;
+  double mKm1 = 0., mK = mask[s3];
+  for (int k = 1; k <= Nr; k++) {
+    const double mKp1 = k < Nr ? mask[s3 + g.slab] : 0.;
+    const double rh = rhF[s3];
+    double b5 = 0., d5 = 0.;
+    if (k >= 2 && mKm1 == 1.) b5 = -deltaTMom * rh * g.recip_drF[k - 1] * kap[s3] * g.recip_drC[k - 1];
+    if (k <= Nr - 1 && mKp1 == 1.) d5 = -deltaTMom * rh * g.recip_drF[k - 1] * kap[s3 + g.slab] * g.recip_drC[k];
+    const double c5 = 1. - (b5 + d5);
+    const double yk = y[s3];
+    double cpk, ypk;
+    if (k == 1) {
+      if (c5 != 0.) { const double rec = 1. / c5; cpk = d5 * rec; ypk = yk * rec; }
+      else { cpk = 0.; ypk = 0.; }
+    } else {
+      const double tmp = c5 - b5 * cpm;
+      if (tmp != 0.) { const double rec = 1. / tmp; cpk = d5 * rec; ypk = (yk - b5 * ypm) * rec; }
+      else { cpk = 0.; ypk = 0.; }
+    }
+    cp[k - 1] = cpk; yp[k - 1] = ypk;
+    cpm = cpk; ypm = ypk;
+    mKm1 = mK; mK = mKp1;
+    s3 += g.slab;
+  }
+  s3 = s + g.slab * (size_t)(Nr - 1);
+  double yk = yp[Nr - 1];
+  y[s3] = yk;
+  for (int k = Nr - 1; k >= 1; k--) {
+    s3 -= g.slab;
+    yk = yp[k - 1] - cp[k - 1] * yk;
+    y[s3] = yk;
+  }
+}
+// which: 1 = U, 2 = V, 3 = both
+__global__ void __launch_bounds__(128)
+momimpl_kernel(TileGrid g, const double *__restrict__ kapU, const double *__restrict__ kapV, double *__restrict__ gU,
+               double *__restrict__ gV, double deltaTMom, int which) {
+  const int i = 1 + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 + blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx + 1 || j > g.sNy + 1 || g.Nr <= 1) return;
+  const size_t s = g.s(i, j);
+  if ((which & 1) && j <= g.sNy) momimpl_column(g, kapU, g.recip_hFacW, g.maskW, gU, s, deltaTMom);
+  if ((which & 2) && i <= g.sNx) momimpl_column(g, kapV, g.recip_hFacS, g.maskS, gV, s, deltaTMom);
+}
+
 // phiHydC for every level; range = the whole slab (the gradient needs (i-1,j) and (i,j-1)).
 // rho == nullptr: the in-situ density anomaly is evaluated on the fly from theta (and salt when
 // sBeta != 0) with FIND_RHO_2D 'LINEAR' -- same expression as ocean_phys_kernel, so nothing but

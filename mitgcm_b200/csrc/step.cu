@@ -425,6 +425,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   // the exactConserv update needs the u, v halo exchange in the middle of the continuity step
   if (exactConserv && g.nPx * g.nPy > 1) return fail(61, "forward_step: exactConserv is single-rank for now");
   if (g.Nr > PHYS_NRMAX && implDiff) return fail(61, "forward_step: implicit diffusion supports Nr <= 64");
+  if (g.Nr > PHYS_NRMAX && mp.momViscosity && mp.implicitViscosity) return fail(61, "forward_step: implicit viscosity supports Nr <= 64");
   double *rho = nullptr, *phiHyd = nullptr, *sfT = nullptr, *etaH = nullptr;
   const bool ivdc = q.D(MP_IVDC_KAPPA) != 0.;
   if (buoy && !(phiHyd = field(MG_PHIHYD))) return false;
@@ -566,6 +567,11 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                                 buoy ? phiHyd + o3 : nullptr,
                                                 q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
                                                 1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
+        if (mp.momViscosity && mp.implicitViscosity && g.Nr > 1) {     // dynamics.F:572-579: MOM_{U,V}_IMPLICIT_R on u*, v*
+          c.launches++;
+          momimpl_kernel<<<dim3((g.sNx + 1 + 31) / 32, (g.sNy + 1 + 3) / 4), blk, 0, c.stream>>>(tg, kapU + o3p, kapV + o3p, gU + o3, gV + o3,
+                                                                                              q.D(MP_DELTATMOM), 3);
+        }
       }
     MG_CUDA(cudaGetLastError());
   }
@@ -789,6 +795,42 @@ void mitgcm_b200_exch_(const int *id, int *ierr) {
   if (!exch_field(f, nz)) return;
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "exch: stream error"); return; }
   *ierr = 0;
+}
+
+// MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R (pkg/mom_common/mom_{u,v}_implicit_r.F:6-8; caller dynamics.F:576-579): reference
+// argument list + the COMMON array the routine solves in place (gU / gV).  implicitViscosity only.
+static void mom_implicit_r(const double *kappaR, const int *bi, const int *bj, double *gFld, int which) {
+  Ctx &c = ctx();
+  c.lastError = 0;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  const Params &q = c.p;
+  if (!q.I(MI_IMPLICITVISCOSITY)) { fail(54, "mom_implicit_r_b200_: only implicitViscosity is on the B200 path (momImplVertAdv, selectImplicitDrag are not)"); return; }
+  if (g.Nr > PHYS_NRMAX) { fail(54, "mom_implicit_r_b200_: Nr exceeds PHYS_NRMAX"); return; }
+  TileGrid tg;
+  if (!make_tile_grid(*bi, *bj, tg)) { if (!c.lastError) fail(43, "grid mirrors not set"); return; }
+  const size_t ns = g.slab, tile = (size_t)(*bi - 1) + (size_t)g.nSx * (size_t)(*bj - 1), off3 = ns * g.Nr * tile;
+  double *dK = to_device(kappaR, ns * (g.Nr + 1), 43, true);
+  double *dG = to_device(gFld, g.n3, 45, false);
+  if (!dK || !dG) return;
+  if (!is_device_ptr(gFld) &&
+      cudaMemcpyAsync(dG + off3, gFld + off3, ns * g.Nr * sizeof(double), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) { fail(4, "H2D copy failed"); return; }
+  c.launches++;
+  momimpl_kernel<<<dim3((g.sNx + 1 + 31) / 32, (g.sNy + 1 + 3) / 4), dim3(32, 4), 0, c.stream>>>(tg, dK, dK, dG + off3, dG + off3,
+                                                                                              q.D(MP_DELTATMOM), which);
+  if (cudaGetLastError() != cudaSuccess) { fail(5, "momimpl_kernel launch failed"); return; }
+  if (!is_device_ptr(gFld)) cudaMemcpyAsync(gFld + off3, dG + off3, ns * g.Nr * sizeof(double), cudaMemcpyDeviceToHost, c.stream);
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) fail(6, "mom_implicit_r_b200_: stream error");
+}
+void mom_u_implicit_r_b200_(const double *kappaRU, const int *bi, const int *bj, const double *myTime, const int *myIter,
+                            const int *myThid, double *gU) {
+  (void)myTime; (void)myIter; (void)myThid;
+  mom_implicit_r(kappaRU, bi, bj, gU, 1);
+}
+void mom_v_implicit_r_b200_(const double *kappaRV, const int *bi, const int *bj, const double *myTime, const int *myIter,
+                            const int *myThid, double *gV) {
+  (void)myTime; (void)myIter; (void)myThid;
+  mom_implicit_r(kappaRV, bi, bj, gV, 2);
 }
 
 void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr) {

@@ -200,6 +200,15 @@ def mom_vecinv(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVe
     _check()
 
 
+def mom_implicit_r(kappaR, bi, bj, gFld, isV=False, myTime=0.0, myIter=0, myThid=1):
+    """CALL MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R(kappaR?, bi, bj, ...) -- pkg/mom_common/mom_{u,v}_implicit_r.F:6-8,
+    followed by the COMMON array solved in place (gU / gV)."""
+    L = _lib.lib()
+    fn = L.mom_v_implicit_r_b200_ if isV else L.mom_u_implicit_r_b200_
+    fn(_addr(kappaR), _i(bi), _i(bj), _d(myTime), _i(myIter), _i(myThid), _addr(gFld))
+    _check()
+
+
 def fill_field(name: str, value: float):
     ierr = C.c_int(0)
     _lib.lib().mitgcm_b200_fill_field_(C.byref(C.c_int(field_id(name))), _d(value), C.byref(ierr))

@@ -117,6 +117,9 @@ class ChannelOracle:
                 o.timestep(bi, bj, k, 0, d.sNx + 1, 0, d.sNy + 1, z, zy, gd, hd, s["surfForcU"], s["surfForcV"],
                            P["momForcing"], P["momDissip_In_AB"], abFac, s["uVel"], s["vVel"], s["gU"], s["gV"],
                            s["guNm1"], s["gvNm1"])
+            if o.params["implicitViscosity"] and o.params["momViscosity"]:      # dynamics.F:572-579
+                o.mom_implicit_r(bi, bj, 0, self.kapU, s["gU"])
+                o.mom_implicit_r(bi, bj, 1, self.kapU, s["gV"])
 
         if buoy:      # DO_OCEANIC_PHYS: density of theta(n), before the thermodynamics updates theta
             self._map(lambda t: o.density_ivdc(self.eos, t[0], t[1], s["theta"], s["salt"], self.tRef, self.sRef,

@@ -38,6 +38,7 @@ void og_forcing_surf_relax_T(const og_grid *g, int bi, int bj, const double *the
 void og_apply_forcing_T(const og_grid *g, int bi, int bj, int k, const double *surfaceForcingT, double *gtForc);
 void og_calc_3d_diffusivity(const og_grid *g, int bi, int bj, const double *IVDConvCount, double ivdc_kappa,
                             const double *KbryanLewis79, const double *diffKrNrT, double *kappaRk);
+int og_mom_implicit_r(const og_grid *g, const og_params *p, int bi, int bj, int isV, const double *kappaR, double *gFld);
 int og_gad_implicit_r(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax,
                       const double *deltaTLev, const double *kappaRX, const double *recip_hFac, double *gTracer);
 void og_calc_phi_hyd(const og_grid *g, int bi, int bj, int iMin, int iMax, int jMin, int jMax, int k,

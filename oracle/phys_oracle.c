@@ -185,6 +185,41 @@ int og_gad_implicit_r(const og_grid *g, int bi, int bj, int iMin, int iMax, int 
   return err;
 }
 
+/* MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R (pkg/mom_common/mom_{u,v}_implicit_r.F:100-300) with implicitViscosity = T,
+ * momImplVertAdv = F, selectImplicitDrag = 0: b5d(k) = -deltaTMom recip_hFac(k) recip_drF(k) kappaR(k) recip_drC(k)
+ * where mask(k-1) = 1, d5d(k) likewise with kappaR(k+1) recip_drC(k+1) where mask(k+1) = 1, c5d = 1 - (b5d + d5d),
+ * on U: i = 1..sNx+1, j = 1..sNy; V: i = 1..sNx, j = 1..sNy+1 (identity elsewhere); SOLVE_TRIDIAGONAL on gU / gV.
+ * kappaR is the per-tile (slab, Nr+1) array; gFld is tile3d.  Returns the solver's errCode. */
+int og_mom_implicit_r(const og_grid *g, const og_params *p, int bi, int bj, int isV, const double *kappaR, double *gFld) {
+  SETUP
+  const size_t n = px * py * (size_t)Nr;
+  const int iMin = 1, iMax = isV ? sNx : sNx + 1, jMin = 1, jMax = isV ? sNy + 1 : sNy;
+  const double *mask = isV ? g->maskS : g->maskW, *rh = isV ? g->recip_hFacS : g->recip_hFacW;
+  double *b5d = (double *)calloc(3 * n, sizeof(double));
+  double *c5d = b5d + n, *d5d = b5d + 2 * n;
+  for (size_t q = 0; q < n; q++) c5d[q] = 1.;
+  int err = 0;
+  if (Nr > 1) {
+    for (int k = 2; k <= Nr; k++)
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++)
+          if (G3(mask, i, j, k - 1) == 1.)
+            L3(b5d, i, j, k) = -p->deltaTMom * G3(rh, i, j, k) * g->recip_drF[k - 1] * L3(kappaR, i, j, k) * g->recip_drC[k - 1];
+    for (int k = 1; k <= Nr - 1; k++)
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++)
+          if (G3(mask, i, j, k + 1) == 1.)
+            L3(d5d, i, j, k) = -p->deltaTMom * G3(rh, i, j, k) * g->recip_drF[k - 1] * L3(kappaR, i, j, k + 1) * g->recip_drC[k];
+    for (int k = 1; k <= Nr; k++)
+      for (int j = jMin; j <= jMax; j++)
+        for (int i = iMin; i <= iMax; i++)
+          L3(c5d, i, j, k) = 1. - (L3(b5d, i, j, k) + L3(d5d, i, j, k));
+    err = solve_tridiagonal(d, b5d, c5d, d5d, gFld + off3);
+  }
+  free(b5d);
+  return err;
+}
+
 /* CALC_PHI_HYD, buoyancyRelation 'OCEANIC', integr_GeoPot = 2 (finite volume), uniformFreeSurfLev,
  * linear free surface, followed by CALC_GRAD_PHI_HYD (phi0surf = 0): one tile, one level.
  * rhoInSitu is tile3d; rF has Nr+1, rC Nr entries; phiHydF/phiHydC/dPhiHydX/dPhiHydY are slabs. */

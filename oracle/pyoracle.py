@@ -222,6 +222,10 @@ class Oracle:
         self.lib.og_calc_3d_diffusivity(C.byref(self.g), bi, bj, ptr(IVDConvCount), C.c_double(ivdc_kappa),
                                         ptr(KbryanLewis79), ptr(diffKrNrT), ptr(kappaRk))
 
+    def mom_implicit_r(self, bi, bj, isV, kappaR, gFld):
+        """MOM_U_IMPLICIT_R (isV = 0, on gU) / MOM_V_IMPLICIT_R (isV = 1, on gV), implicitViscosity only."""
+        return self.lib.og_mom_implicit_r(C.byref(self.g), C.byref(self.p), bi, bj, int(isV), ptr(kappaR), ptr(gFld))
+
     def gad_implicit_r(self, bi, bj, iMin, iMax, jMin, jMax, deltaTLev, kappaRX, recip_hFac, gTracer):
         return self.lib.og_gad_implicit_r(C.byref(self.g), bi, bj, iMin, iMax, jMin, jMax, ptr(deltaTLev),
                                           ptr(kappaRX), ptr(recip_hFac), ptr(gTracer))
