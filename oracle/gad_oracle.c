@@ -479,6 +479,49 @@ void og_gad_calc_rhs(const og_grid *g, const og_params *p, int bi, int bj,
   free(buf);
 }
 
+/* FILL_CS_CORNER_TR_RL (eesupp/src/fill_cs_corner_tr_rl.F:74-156), withSigns = .FALSE.; corners: 1 SW, 2 SE, 4 NE, 8 NW */
+static void gad_fill_cs_corner_tr(const og_dims *d, int fill4dir, int corners, double *f) {
+  const int sNx = d->sNx, sNy = d->sNy, OLx = d->OLx, OLy = d->OLy;
+  const size_t px = (size_t)(sNx + 2 * OLx);
+  if (!corners) return;
+  for (int j = 1; j <= OLy; j++)
+    for (int i = 1; i <= OLx; i++) {
+      if (fill4dir == 1) {
+        if (corners & 1) f[S(1 - i, 1 - j)] = f[S(1 - j, i)];
+        if (corners & 2) f[S(sNx + i, 1 - j)] = f[S(sNx + j, i)];
+        if (corners & 8) f[S(1 - i, sNy + j)] = f[S(1 - j, sNy + 1 - i)];
+        if (corners & 4) f[S(sNx + i, sNy + j)] = f[S(sNx + j, sNy + 1 - i)];
+      } else {
+        if (corners & 1) f[S(1 - i, 1 - j)] = f[S(j, 1 - i)];
+        if (corners & 2) f[S(sNx + i, 1 - j)] = f[S(sNx + 1 - j, 1 - i)];
+        if (corners & 8) f[S(1 - i, sNy + j)] = f[S(j, sNy + i)];
+        if (corners & 4) f[S(sNx + i, sNy + j)] = f[S(sNx + 1 - j, sNy + i)];
+      }
+    }
+}
+
+/* FILL_CS_CORNER_UV_RS (eesupp/src/fill_cs_corner_uv_rs.F:46-108), withSigns = .FALSE. (negOne = 1) */
+static void gad_fill_cs_corner_uv(const og_dims *d, int corners, double *uF, double *vF) {
+  const int sNx = d->sNx, sNy = d->sNy, OLx = d->OLx, OLy = d->OLy;
+  const size_t px = (size_t)(sNx + 2 * OLx);
+  if (corners & 1) {
+    for (int j = 1; j <= OLy; j++) for (int i = 1; i <= OLx; i++) uF[S(1 - i, 1 - j)] = vF[S(1 - j, 1 + i)];
+    for (int j = 1; j <= OLy; j++) for (int i = 1; i <= OLx; i++) vF[S(1 - i, 1 - j)] = uF[S(1 + j, 1 - i)];
+  }
+  if (corners & 2) {
+    for (int j = 1; j <= OLy; j++) for (int i = 2; i <= OLx; i++) uF[S(sNx + i, 1 - j)] = vF[S(sNx + j, i)];
+    for (int j = 1; j <= OLy; j++) for (int i = 1; i <= OLx; i++) vF[S(sNx + i, 1 - j)] = uF[S(sNx + 1 - j, 1 - i)];
+  }
+  if (corners & 8) {
+    for (int j = 1; j <= OLy; j++) for (int i = 1; i <= OLx; i++) uF[S(1 - i, sNy + j)] = vF[S(1 - j, sNy + 1 - i)];
+    for (int j = 2; j <= OLy; j++) for (int i = 1; i <= OLx; i++) vF[S(1 - i, sNy + j)] = uF[S(j, sNy + i)];
+  }
+  if (corners & 4) {
+    for (int j = 1; j <= OLy; j++) for (int i = 2; i <= OLx; i++) uF[S(sNx + i, sNy + j)] = vF[S(sNx + j, sNy + 2 - i)];
+    for (int j = 2; j <= OLy; j++) for (int i = 1; i <= OLx; i++) vF[S(sNx + i, sNy + j)] = uF[S(sNx + 2 - j, sNy + i)];
+  }
+}
+
 /* ---- GAD_ADVECTION (pkg/generic_advdiff/gad_advection.F:240-1097), multi-dimensional
  * direct-space-time advection of one tracer on one tile, non-cube topology (npass = 2: X pass then
  * Y pass, each updating localTij over the halo'd slab), then the vertical flux pass k = Nr..1.
@@ -490,9 +533,13 @@ void og_gad_calc_rhs(const og_grid *g, const og_params *p, int bi, int bj,
 int og_gad_advection(const og_grid *g, const og_params *p, int bi, int bj, int advectionScheme,
                      int vertAdvecScheme, int implicitAdvection, int compressible,
                      const double *deltaTLev, const double *uFld, const double *vFld, const double *wFld,
-                     const double *tracer, double *gTracer) {
+                     const double *tracer, double *gTracer, int nCFace, int edges) {
   SETUP
   const size_t ns = px * py;
+  /* cubed sphere (gad_advection.F:249-272): nCFace = exch2_myFace, edges = 1 N | 2 S | 4 E | 8 W of the facet */
+  const int cube = nCFace > 0, npass = cube ? 3 : 2;
+  const int N_edge = cube && (edges & 1), S_edge = cube && (edges & 2), E_edge = cube && (edges & 4), W_edge = cube && (edges & 8);
+  const int corners = (W_edge && S_edge ? 1 : 0) | (E_edge && S_edge ? 2 : 0) | (E_edge && N_edge ? 4 : 0) | (W_edge && N_edge ? 8 : 0);
   const int ok = advectionScheme == UPWIND_1RST || advectionScheme == DST2 || advectionScheme == FLUX_LIMIT ||
                  advectionScheme == DST3 || advectionScheme == DST3_FLUX_LIMIT || advectionScheme == OS7MP;
   const int okv = vertAdvecScheme == UPWIND_1RST || vertAdvecScheme == DST2 || vertAdvecScheme == FLUX_LIMIT ||
@@ -520,40 +567,79 @@ int og_gad_advection(const og_grid *g, const og_params *p, int bi, int bj, int a
       maskLocW[S(i, j)] = G3(g->maskW, i, j, k);
       maskLocS[S(i, j)] = G3(g->maskS, i, j, k);
     }
-    for (int ipass = 1; ipass <= 2; ipass++) {
-      const int fluxX = ipass % 2 == 1;
+    if (cube) gad_fill_cs_corner_uv(d, corners, maskLocW, maskLocS);       /* :329-334 */
+    for (int ipass = 1; ipass <= npass; ipass++) {
+      int interiorOnly = 0, overlapOnly = 0, fluxX, fluxY;
+      if (cube) {                                                          /* :346-362 */
+        if (ipass == 1) {
+          overlapOnly = nCFace % 3 == 0; interiorOnly = nCFace % 3 != 0;
+          fluxX = nCFace == 6 || nCFace == 1 || nCFace == 2; fluxY = nCFace == 3 || nCFace == 4 || nCFace == 5;
+        } else if (ipass == 2) {
+          overlapOnly = nCFace % 3 == 2; interiorOnly = nCFace % 3 == 1;
+          fluxX = nCFace == 2 || nCFace == 3 || nCFace == 4; fluxY = nCFace == 5 || nCFace == 6 || nCFace == 1;
+        } else {
+          interiorOnly = 1;
+          fluxX = nCFace == 5 || nCFace == 6; fluxY = nCFace == 2 || nCFace == 3;
+        }
+      } else { fluxX = ipass % 2 == 1; fluxY = !fluxX; }
+      const double dT = deltaTLev[k - 1];
+#define MD_UPDATE(i, j, trA, trB, afA, afB)                                                                          \
+      do {                                                                                                           \
+        if (compressible) {                                                                                          \
+          const double tmpTrac = localTij[S(i, j)] * localVol[S(i, j)] - dT * ((afB) - (afA)) * 1.;                  \
+          localVol[S(i, j)] = localVol[S(i, j)] - dT * ((trB) - (trA)) * 1.;                                         \
+          localTij[S(i, j)] = tmpTrac / localVol[S(i, j)];                                                           \
+        } else {                                                                                                     \
+          localTij[S(i, j)] = localTij[S(i, j)]                                                                      \
+              - dT * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.            \
+                    * ((afB) - (afA) - G3(tracer, i, j, k) * ((trB) - (trA))) * 1.;                                  \
+        }                                                                                                            \
+      } while (0)
       FORALL af[S(i, j)] = 0.;
       if (fluxX) {
-        adv_h(g, bi, bj, k, 0, advectionScheme, deltaTLev[k - 1], uTrans, uK, maskLocW, localTij, af);
-        for (int j = 1 - OLy; j <= sNy + OLy; j++)
-          for (int i = 1 - OLx + 1; i <= sNx + OLx - 1; i++) {
-            if (compressible) {
-              const double tmpTrac = localTij[S(i, j)] * localVol[S(i, j)]
-                                     - deltaTLev[k - 1] * (af[S(i + 1, j)] - af[S(i, j)]) * 1.;
-              localVol[S(i, j)] = localVol[S(i, j)] - deltaTLev[k - 1] * (uTrans[S(i + 1, j)] - uTrans[S(i, j)]) * 1.;
-              localTij[S(i, j)] = tmpTrac / localVol[S(i, j)];
-            } else {
-              localTij[S(i, j)] = localTij[S(i, j)]
-                  - deltaTLev[k - 1] * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.
-                        * (af[S(i + 1, j)] - af[S(i, j)] - G3(tracer, i, j, k) * (uTrans[S(i + 1, j)] - uTrans[S(i, j)])) * 1.;
-            }
-          }
-      } else {
-        adv_h(g, bi, bj, k, 1, advectionScheme, deltaTLev[k - 1], vTrans, vK, maskLocS, localTij, af);
-        for (int j = 1 - OLy + 1; j <= sNy + OLy - 1; j++)
-          for (int i = 1 - OLx; i <= sNx + OLx; i++) {
-            if (compressible) {
-              const double tmpTrac = localTij[S(i, j)] * localVol[S(i, j)]
-                                     - deltaTLev[k - 1] * (af[S(i, j + 1)] - af[S(i, j)]) * 1.;
-              localVol[S(i, j)] = localVol[S(i, j)] - deltaTLev[k - 1] * (vTrans[S(i, j + 1)] - vTrans[S(i, j)]) * 1.;
-              localTij[S(i, j)] = tmpTrac / localVol[S(i, j)];
-            } else {
-              localTij[S(i, j)] = localTij[S(i, j)]
-                  - deltaTLev[k - 1] * 1. * G3(g->recip_hFacC, i, j, k) * g->recip_drF[k - 1] * G2(g->recip_rA, i, j) * 1.
-                        * (af[S(i, j + 1)] - af[S(i, j)] - G3(tracer, i, j, k) * (vTrans[S(i, j + 1)] - vTrans[S(i, j)])) * 1.;
-            }
-          }
+        if (!overlapOnly || N_edge || S_edge) {
+          if (overlapOnly) gad_fill_cs_corner_tr(d, 1, corners, localTij);
+          FORALL af[S(i, j)] = 0.;
+          adv_h(g, bi, bj, k, 0, advectionScheme, dT, uTrans, uK, maskLocW, localTij, af);
+          if (overlapOnly && ipass == 1) gad_fill_cs_corner_tr(d, 2, corners, localTij);
+        }
+        if (overlapOnly) {                                                 /* :471-546 */
+          const int iMinUpd = W_edge ? 1 : 1 - OLx + 1, iMaxUpd = E_edge ? sNx : sNx + OLx - 1;
+          if (S_edge)
+            for (int j = 1 - OLy; j <= 0; j++)
+              for (int i = iMinUpd; i <= iMaxUpd; i++) MD_UPDATE(i, j, uTrans[S(i, j)], uTrans[S(i + 1, j)], af[S(i, j)], af[S(i + 1, j)]);
+          if (N_edge)
+            for (int j = sNy + 1; j <= sNy + OLy; j++)
+              for (int i = iMinUpd; i <= iMaxUpd; i++) MD_UPDATE(i, j, uTrans[S(i, j)], uTrans[S(i + 1, j)], af[S(i, j)], af[S(i + 1, j)]);
+        } else {                                                           /* :547-600 */
+          const int jMinUpd = (interiorOnly && S_edge) ? 1 : 1 - OLy, jMaxUpd = (interiorOnly && N_edge) ? sNy : sNy + OLy;
+          for (int j = jMinUpd; j <= jMaxUpd; j++)
+            for (int i = 1 - OLx + 1; i <= sNx + OLx - 1; i++) MD_UPDATE(i, j, uTrans[S(i, j)], uTrans[S(i + 1, j)], af[S(i, j)], af[S(i + 1, j)]);
+        }
       }
+      FORALL af[S(i, j)] = 0.;
+      if (fluxY) {
+        if (!overlapOnly || E_edge || W_edge) {
+          if (overlapOnly) gad_fill_cs_corner_tr(d, 2, corners, localTij);
+          FORALL af[S(i, j)] = 0.;
+          adv_h(g, bi, bj, k, 1, advectionScheme, dT, vTrans, vK, maskLocS, localTij, af);
+          if (overlapOnly && ipass == 1) gad_fill_cs_corner_tr(d, 1, corners, localTij);
+        }
+        if (overlapOnly) {                                                 /* :692-768 */
+          const int jMinUpd = S_edge ? 1 : 1 - OLy + 1, jMaxUpd = N_edge ? sNy : sNy + OLy - 1;
+          if (W_edge)
+            for (int j = jMinUpd; j <= jMaxUpd; j++)
+              for (int i = 1 - OLx; i <= 0; i++) MD_UPDATE(i, j, vTrans[S(i, j)], vTrans[S(i, j + 1)], af[S(i, j)], af[S(i, j + 1)]);
+          if (E_edge)
+            for (int j = jMinUpd; j <= jMaxUpd; j++)
+              for (int i = sNx + 1; i <= sNx + OLx; i++) MD_UPDATE(i, j, vTrans[S(i, j)], vTrans[S(i, j + 1)], af[S(i, j)], af[S(i, j + 1)]);
+        } else {                                                           /* :769-812 */
+          const int iMinUpd = (interiorOnly && W_edge) ? 1 : 1 - OLx, iMaxUpd = (interiorOnly && E_edge) ? sNx : sNx + OLx;
+          for (int j = 1 - OLy + 1; j <= sNy + OLy - 1; j++)
+            for (int i = iMinUpd; i <= iMaxUpd; i++) MD_UPDATE(i, j, vTrans[S(i, j)], vTrans[S(i, j + 1)], af[S(i, j)], af[S(i, j + 1)]);
+        }
+      }
+#undef MD_UPDATE
     }
     if (implicitAdvection) {
       FORALL K3(gTracer, i, j, k) = (localTij[S(i, j)] - G3(tracer, i, j, k)) / deltaTLev[k - 1];

@@ -152,11 +152,13 @@ void og_gad_calc_rhs(const og_grid *g, const og_params *p, int bi, int bj,
                      int trUseDiffKr4,
                      double *fZon, double *fMer, double *fVerT, double *gTracer);
 
-/* GAD_ADVECTION (pkg/generic_advdiff/gad_advection.F): multi-dimensional advection, one tile, all levels */
+/* GAD_ADVECTION (pkg/generic_advdiff/gad_advection.F): multi-dimensional advection, one tile, all levels.
+ * Cubed sphere (3 passes): nCFace = exch2_myFace of the tile, edges = 1 N | 2 S | 4 E | 8 W facet edges it touches;
+ * 0, 0 otherwise (2 passes). */
 int og_gad_advection(const og_grid *g, const og_params *p, int bi, int bj, int advectionScheme,
                      int vertAdvecScheme, int implicitAdvection, int compressible,
                      const double *deltaTLev, const double *uFld, const double *vFld, const double *wFld,
-                     const double *tracer, double *gTracer);
+                     const double *tracer, double *gTracer, int nCFace, int edges);
 
 /* CALC_ADV_FLOW (model/src/calc_adv_flow.F) for one tile, one level */
 void og_calc_adv_flow(const og_grid *g, int bi, int bj, int k,

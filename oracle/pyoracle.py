@@ -174,11 +174,12 @@ class Oracle:
             ptr(fZon), ptr(fMer), ptr(fVerT), ptr(gTracer))
 
     def gad_advection(self, bi, bj, advScheme, vertAdvScheme, implicitAdvection, compressible, deltaTLev,
-                      uFld, vFld, wFld, tracer, gTracer):
-        """GAD_ADVECTION (multi-dimensional advection) for one tile; gTracer is (Nr, PY, PX)."""
+                      uFld, vFld, wFld, tracer, gTracer, nCFace=0, edges=0):
+        """GAD_ADVECTION (multi-dimensional advection) for one tile; gTracer is (Nr, PY, PX).
+        Cubed sphere: nCFace = facet number, edges = 1 N | 2 S | 4 E | 8 W facet edges the tile touches."""
         return self.lib.og_gad_advection(C.byref(self.g), C.byref(self.p), bi, bj, int(advScheme), int(vertAdvScheme),
                                          int(implicitAdvection), int(compressible), ptr(deltaTLev), ptr(uFld), ptr(vFld),
-                                         ptr(wFld), ptr(tracer), ptr(gTracer))
+                                         ptr(wFld), ptr(tracer), ptr(gTracer), int(nCFace), int(edges))
 
     # ---- glue ----
     def timestep(self, bi, bj, k, iMin, iMax, jMin, jMax, dPhiHydX, dPhiHydY, guDiss, gvDiss, sfU, sfV,

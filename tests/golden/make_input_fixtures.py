@@ -27,6 +27,8 @@ def cs32_fixture():
     adj = os.path.join(REF, "adjustment.cs-32x32x1/input")
     out["adj_bathy_f2"] = np.fromfile(os.path.join(adj, "bathy_f2.bin"), ">f8").reshape(32, 192).astype(np.float64)
     out["adj_ssh_eq"] = np.fromfile(os.path.join(adj, "ssh_eq.bin"), ">f8").reshape(32, 192).astype(np.float64)
+    # advect_cs (same grid): initial tracer (W2_mapIO = -1: facets stacked along x)
+    out["advcs_T_init"] = np.fromfile(os.path.join(REF, "advect_cs/input/T.init"), ">f8").reshape(32, 192).astype(np.float64)
     np.savez_compressed(os.path.join(HERE, "cs32_grid_bathy.npz"), **out)
     print("wrote cs32_grid_bathy.npz")
 

@@ -299,3 +299,17 @@ def test_solid_body_cs_monitor_dynstats(sb25, fld, st):
             assert abs(r[fld][st] - float(gv)) < 1e-13 * scale, (fld, st)
         else:
             assert r[fld][st] == pytest.approx(float(gv), rel=2e-13, abs=1e-30), (fld, st)
+
+
+# ---------------------------------------------------------------------------------------
+# verification/advect_cs (theta): GAD_ADVECTION on the cs32 cubed sphere -- three facet-dependent passes with
+# FILL_CS_CORNER_TR_RL / _UV_RS, scheme 33, GAD_MULTIDIM_COMPRESSIBLE build; 192 steps, monitor every 8.
+# ---------------------------------------------------------------------------------------
+def test_advect_cs_theta_statistics_every_printed_digit():
+    from oracle import advect_cs as acs
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "advect_cs.json")))
+    out = acs.run(192)
+    assert len(out) == len(gold["dynstat_theta_sd"]) == 25          # steps 0, 8, ..., 192
+    for r, mx, mn, me, sd in zip(out, gold["dynstat_theta_max"], gold["dynstat_theta_min"], gold["dynstat_theta_mean"],
+                                 gold["dynstat_theta_sd"]):
+        assert (fmt(r["max"], 13), fmt(r["min"], 13), fmt(r["mean"], 13), fmt(r["sd"], 13)) == (mx, mn, me, sd)
