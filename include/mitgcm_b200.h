@@ -140,7 +140,8 @@ void gad_calc_rhs_b200_(const int *bi, const int *bj, const int *iMin, const int
  * pkg/generic_advdiff/gad_advection.F:11-17 (callers temp_integrate.F:283, salt_integrate.F:275,
  * ptracers_integrate.F).  uFld, vFld, wFld, gTracer are (slab, Nr) arrays of the tile, tracer the
  * full (.., Nr, nSx, nSy) array.  The GAD_MULTIDIM_COMPRESSIBLE build option (GAD_OPTIONS.h:44) is
- * the run-time parameter MI_GAD_MULTIDIM_COMPRESSIBLE.  Non-cube topology only. */
+ * the run-time parameter MI_GAD_MULTIDIM_COMPRESSIBLE.  With a pkg/exch2 topology (mitgcm_b200_set_exch2_topology_
+ * + mitgcm_b200_set_cs_tiles_) the three facet-dependent passes of the cubed sphere run. */
 void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchArg, const int *vertAdvecSchArg,
                          const int *trIdentity, const double *deltaTLev, const double *uFld,
                          const double *vFld, const double *wFld, const double *tracer, double *gTracer,
@@ -186,9 +187,11 @@ void mom_u_implicit_r_b200_(const double *kappaRU, const int *bi, const int *bj,
 void mom_v_implicit_r_b200_(const double *kappaRV, const int *bi, const int *bj, const double *myTime,
                             const int *myIter, const int *myThid, double *gV);
 
-/* Facet data of the local tiles for the resident step with MI_VECTORINVARIANTMOMENTUM on the cubed
- * sphere: csCorners(nSx*nSy) and myFace(nSx*nSy) as in mom_vecinv_b200_ (tiles bi fast). */
-void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr);
+/* Facet data of the local tiles (tiles bi fast) for the entry points that cannot take them as arguments -- the
+ * resident step with MI_VECTORINVARIANTMOMENTUM and gad_advection_b200_ on the cubed sphere: csCorners and
+ * myFace as in mom_vecinv_b200_, edges = 1 N | 2 S | 4 E | 8 W facet edges the tile touches
+ * (exch2_is{N,S,E,W}edge, gad_advection.F:253-257). */
+void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, const int *edges, int *ierr);
 
 /* ---- resident time step ----------------------------------
  * One model step on the device mirrors in the order of model/src/forward_step.F (non-staggered):

@@ -50,7 +50,7 @@ struct Ctx {
   int *e2UvList[2] = {nullptr, nullptr};   // vector-pair exchange, [withSigns]: 4 ints per entry
   int e2UvCount[2] = {0, 0};
   // cubed sphere: facet corners each local tile owns (1 SW, 2 SE, 4 NE, 8 NW) and its facet number
-  std::vector<int> csCorners, csFace;
+  std::vector<int> csCorners, csFace, csEdges;    // csEdges: 1 N | 2 S | 4 E | 8 W facet edges the tile touches
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;

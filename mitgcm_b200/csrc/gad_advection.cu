@@ -9,22 +9,58 @@
 //   md_pass_kernel<0>  T0 -> T1 (+ local volume)   fluxes from the tracer                 R{T,u,hFacW,hFacC}  W{T1,V1}
 //   md_pass_kernel<1>  T1 -> T2 (+ local volume)   fluxes from the X-updated field        R{T1,V1,v,hFacS}    W{T2,V2}
 //   md_vert_kernel     gTracer from T2             4..8-level stencil in k                R{T2,V2,w,T,maskC}  W{gTracer}
-// Non-cube topology (npass = 2).  Flux formulas are the leaves of gad.cuh shared with GAD_CALC_RHS
+// Cubed sphere (pkg/exch2 topology set): the three facet-dependent passes of gad_advection.F:339-812 -- which
+// direction a facet sweeps in which pass, interior-only / overlap-only update ranges, FILL_CS_CORNER_TR_RL as a
+// read map of the pass input (and of its output corners), FILL_CS_CORNER_UV_RS on copies of the masks.
+// Flux formulas are the leaves of gad.cuh shared with GAD_CALC_RHS
 // (schemes 1, 20, 77, 30, 33, 7).  MI_GAD_MULTIDIM_COMPRESSIBLE selects the GAD_MULTIDIM_COMPRESSIBLE
 // build variant (gad_advection.F:480-490, :1018-1032) at run time.  -fmad=false, reference operation
-// order: bit-identical to the oracle, which is pinned to verification/advect_xy.
+// order: bit-identical to the oracle, which is pinned to verification/advect_xy and verification/advect_cs.
 #include "gad.cuh"
 
 namespace mg {
 
 // accessor the flux leaves read through: tracer values from the current pass's input, transports
 // derived from the velocity of level k
+// FILL_CS_CORNER_TR_RL (eesupp/src/fill_cs_corner_tr_rl.F:74-156) as an index map: the cell whose value (i,j) holds
+// after the facet corners in `corners` (1 SW, 2 SE, 4 NE, 8 NW) were refilled for direction dir (1: x, 2: y).
+__device__ __forceinline__ bool cs_corner_src(const TileGrid &g, int corners, int dir, int i, int j, int &ii, int &jj) {
+  if (!dir || !corners) return false;
+  const int sNx = g.sNx, sNy = g.sNy;
+  if (i < 1 && j < 1 && (corners & 1)) {
+    const int a = 1 - i, b = 1 - j;
+    if (dir == 1) { ii = 1 - b; jj = a; } else { ii = b; jj = 1 - a; }
+    return true;
+  }
+  if (i > sNx && j < 1 && (corners & 2)) {
+    const int a = i - sNx, b = 1 - j;
+    if (dir == 1) { ii = sNx + b; jj = a; } else { ii = sNx + 1 - b; jj = 1 - a; }
+    return true;
+  }
+  if (i < 1 && j > sNy && (corners & 8)) {
+    const int a = 1 - i, b = j - sNy;
+    if (dir == 1) { ii = 1 - b; jj = sNy + 1 - a; } else { ii = b; jj = sNy + a; }
+    return true;
+  }
+  if (i > sNx && j > sNy && (corners & 4)) {
+    const int a = i - sNx, b = j - sNy;
+    if (dir == 1) { ii = sNx + b; jj = sNy + 1 - a; } else { ii = sNx + 1 - b; jj = sNy + a; }
+    return true;
+  }
+  return false;
+}
+
 struct MdAcc {
   TileGrid g;
   const double *T_, *u, *v, *w;   // per-tile (slab, Nr)
   int k;
-  __device__ __forceinline__ double TA(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
-  __device__ __forceinline__ double T(int i, int j, int kk) const { return T_[g.s3(i, j, kk)]; }
+  int corners, dirIn;             // cube: the pass input is read through the corner fill of direction dirIn (0: as stored)
+  __device__ __forceinline__ double TA(int i, int j, int kk) const {
+    int ii, jj;
+    if (cs_corner_src(g, corners, dirIn, i, j, ii, jj)) return T_[g.s3(ii, jj, kk)];
+    return T_[g.s3(i, j, kk)];
+  }
+  __device__ __forceinline__ double T(int i, int j, int kk) const { return TA(i, j, kk); }
   __device__ __forceinline__ double xA(int i, int j) const { return g.dyG[g.s(i, j)] * 1. * g.drF[k - 1] * g.hFacW[g.s3(i, j, k)]; }
   __device__ __forceinline__ double yA(int i, int j) const { return g.dxG[g.s(i, j)] * 1. * g.drF[k - 1] * g.hFacS[g.s3(i, j, k)]; }
   __device__ __forceinline__ double uFld(int i, int j) const { return u[g.s3(i, j, k)]; }
@@ -43,19 +79,43 @@ struct MdAcc {
 // One horizontal pass (DIR 0: X, gad_advection.F:376-560; DIR 1: Y, :597-790) over the halo'd slab of
 // every level.  Tin / Vin: tracer and local volume before the pass (Vin == nullptr: the volume of the
 // undisturbed cell, first pass); tracer0: the tracer at time n (the -T*div(U) correction of the default form).
+struct MdUpd {
+  int cube, overlapOnly, interiorOnly, N, S, E, W;   // gad_advection.F:339-362
+  int dirOut;                                        // corner fill applied to the field after the fluxes (ipass = 1), 0: none
+};
+
 template <int DIR>
 __global__ void __launch_bounds__(128) md_pass_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
                                                       const double *__restrict__ tracer0, double *__restrict__ Tout,
-                                                      double *__restrict__ Vout, int compressible, const double *dTLev) {
+                                                      double *__restrict__ Vout, int compressible, const double *dTLev,
+                                                      MdUpd q) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
   const int k = 1 + blockIdx.z;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
   a.k = k; p.k = k; p.deltaT = dTLev[k - 1];
   const size_t s3 = g.s3(i, j, k);
-  double T = a.T_[s3];
+  double T = a.TA(i, j, k);
   double V = Vin ? Vin[s3] : g.rA[g.s(i, j)] * 1. * 1. * g.drF[k - 1] * g.hFacC[s3] + (1. - g.maskC[s3]);
-  const bool upd = DIR == 0 ? (i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1) : (j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1);
+  // update range of this pass (gad_advection.F:471-600 for X, :692-812 for Y)
+  bool upd;
+  if (DIR == 0) {
+    if (q.overlapOnly) {
+      const int iLo = q.W ? 1 : 2 - g.OLx, iHi = q.E ? g.sNx : g.sNx + g.OLx - 1;
+      upd = i >= iLo && i <= iHi && ((q.S && j <= 0) || (q.N && j >= g.sNy + 1));
+    } else {
+      const int jLo = (q.interiorOnly && q.S) ? 1 : 1 - g.OLy, jHi = (q.interiorOnly && q.N) ? g.sNy : g.sNy + g.OLy;
+      upd = j >= jLo && j <= jHi && i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1;
+    }
+  } else {
+    if (q.overlapOnly) {
+      const int jLo = q.S ? 1 : 2 - g.OLy, jHi = q.N ? g.sNy : g.sNy + g.OLy - 1;
+      upd = j >= jLo && j <= jHi && ((q.W && i <= 0) || (q.E && i >= g.sNx + 1));
+    } else {
+      const int iLo = (q.interiorOnly && q.W) ? 1 : 1 - g.OLx, iHi = (q.interiorOnly && q.E) ? g.sNx : g.sNx + g.OLx;
+      upd = i >= iLo && i <= iHi && j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1;
+    }
+  }
   if (upd) {
     const int di = DIR == 0, dj = DIR == 1;
     const double af0 = gad_adv_h(g, a, p, DIR, i, j), af1 = gad_adv_h(g, a, p, DIR, i + di, j + dj);
@@ -69,9 +129,43 @@ __global__ void __launch_bounds__(128) md_pass_kernel(TileGrid g, MdAcc a, GadPa
       T = T - p.deltaT * 1. * g.recip_hFacC[s3] * g.recip_drF[k - 1] * g.recip_rA[g.s(i, j)] * 1. *
                   (af1 - af0 - tracer0[s3] * (tr1 - tr0)) * 1.;
     }
+  } else if (q.dirOut) {     // FILL_CS_CORNER_TR_RL for the other direction after the fluxes (:456-459, :677-680)
+    int ii, jj;
+    if (cs_corner_src(g, a.corners, q.dirOut, i, j, ii, jj)) T = a.T_[g.s3(ii, jj, k)];
   }
   Tout[s3] = T;
   if (Vout) Vout[s3] = V;
+}
+
+// FILL_CS_CORNER_UV_RS (eesupp/src/fill_cs_corner_uv_rs.F:46-108, withSigns = .FALSE.) on copies of maskW, maskS of
+// one tile (gad_advection.F:329-334); every source is a non-corner cell, so the fill is a pure gather.
+__global__ void md_mask_kernel(TileGrid g, int corners, double *__restrict__ mW, double *__restrict__ mS) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const size_t s3 = g.s3(i, j, k);
+  double w = g.maskW[s3], s = g.maskS[s3];
+  const int sNx = g.sNx, sNy = g.sNy;
+  auto W = [&](int ii, int jj) { return g.maskW[g.s3(ii, jj, k)]; };
+  auto S = [&](int ii, int jj) { return g.maskS[g.s3(ii, jj, k)]; };
+  if (i < 1 && j < 1 && (corners & 1)) {
+    const int a = 1 - i, b = 1 - j;
+    w = S(1 - b, 1 + a); s = W(1 + b, 1 - a);
+  } else if (i > sNx && j < 1 && (corners & 2)) {
+    const int a = i - sNx, b = 1 - j;
+    if (a >= 2) w = S(sNx + b, a);
+    s = W(sNx + 1 - b, 1 - a);
+  } else if (i < 1 && j > sNy && (corners & 8)) {
+    const int a = 1 - i, b = j - sNy;
+    w = S(1 - b, sNy + 1 - a);
+    if (b >= 2) s = W(b, sNy + a);
+  } else if (i > sNx && j > sNy && (corners & 4)) {
+    const int a = i - sNx, b = j - sNy;
+    if (a >= 2) w = S(sNx + b, sNy + 2 - a);
+    if (b >= 2) s = W(sNx + 2 - b, sNy + a);
+  }
+  mW[s3] = w; mS[s3] = s;
 }
 
 // X+Y passes only (implicitAdvection): gTracer = (T2 - tracer)/deltaT (gad_advection.F:815-823)
@@ -148,34 +242,81 @@ extern "C" void gad_advection_b200_(const int *implicitAdvection, const int *adv
     return;
   }
   if (*implicitAdvection && compressible) { fail(42, "gad_advection_b200_: implicitAdvection with GAD_MULTIDIM_COMPRESSIBLE"); return; }
-  if (exch2_active()) { fail(44, "gad_advection_b200_: the 3-pass cubed-sphere form is not built"); return; }
   if (*advectionSchArg == ADV_OS7MP && (g.OLx < 4 || g.OLy < 4)) { fail(42, "gad_advection_b200_: OS7MP needs OLx, OLy >= 4"); return; }
   TileGrid tg;
   if (!make_tile_grid(*bi, *bj, tg)) { if (!c.lastError) fail(43, "grid mirrors not set"); return; }
   const size_t ns = g.slab, n3 = ns * g.Nr;
   const size_t tile = (size_t)(*bi - 1) + (size_t)g.nSx * (size_t)(*bj - 1);
+  // cubed sphere: facet number and facet edges of this tile (gad_advection.F:249-258)
+  const bool cube = exch2_active();
+  int nCFace = 0, edges = 0;
+  if (cube) {
+    if ((int)c.csFace.size() != g.nTiles || (int)c.csEdges.size() != g.nTiles) { fail(44, "gad_advection_b200_: mitgcm_b200_set_cs_tiles_ not called"); return; }
+    if (g.OLx != g.OLy) { fail(44, "gad_advection_b200_: the cubed-sphere form needs OLx = OLy"); return; }
+    nCFace = c.csFace[tile]; edges = c.csEdges[tile];
+  }
+  const int eN = edges & 1, eS = (edges >> 1) & 1, eE = (edges >> 2) & 1, eW = (edges >> 3) & 1;
+  const int corners = (eW && eS ? 1 : 0) | (eE && eS ? 2 : 0) | (eE && eN ? 4 : 0) | (eW && eN ? 8 : 0);
   const double *u = to_device(uFld, n3, 40, true), *v = to_device(vFld, n3, 41, true), *w = to_device(wFld, n3, 42, true);
   // tracer is the full (.., Nr, nSx, nSy) array of the caller; only this tile is needed
   const double *tr = is_device_ptr(tracer) ? tracer + n3 * tile : to_device(tracer + n3 * tile, n3, 43, true);
   double *gT = is_device_ptr(gTracer) ? gTracer : to_device(gTracer, n3, 44, false);
-  double *T1 = to_device(nullptr, n3, 45, false), *V1 = to_device(nullptr, n3, 46, false);
-  double *T2 = to_device(nullptr, n3, 47, false), *V2 = to_device(nullptr, n3, 48, false);
+  double *Tb[2] = {to_device(nullptr, n3, 45, false), to_device(nullptr, n3, 47, false)};
+  double *Vb[2] = {to_device(nullptr, n3, 46, false), to_device(nullptr, n3, 48, false)};
   double *dT = to_device(deltaTLev, (size_t)g.Nr, 49, true);
-  if (!u || !v || !w || !tr || !gT || !T1 || !V1 || !T2 || !V2 || !dT) return;
+  if (!u || !v || !w || !tr || !gT || !Tb[0] || !Vb[0] || !Tb[1] || !Vb[1] || !dT) return;
+  dim3 blk(32, 4), grd((g.PX + 31) / 32, (g.PY + 3) / 4, g.Nr);
+  if (cube && corners) {     // maskLocW / maskLocS with their facet corners filled
+    double *mW = to_device(nullptr, n3, 54, false), *mS = to_device(nullptr, n3, 55, false);
+    if (!mW || !mS) return;
+    c.launches++;
+    md_mask_kernel<<<grd, blk, 0, c.stream>>>(tg, corners, mW, mS);
+    tg.maskW = mW; tg.maskS = mS;
+  }
   GadPar p{};
   p.advScheme = *advectionSchArg;
   // GAD_DST2U1_ADV_R is handed advectionScheme, not vertAdvecScheme (gad_advection.F:976)
   p.vertAdvScheme = (*vertAdvecSchArg == ADV_UPWIND_1RST || *vertAdvecSchArg == ADV_DST2) ? *advectionSchArg : *vertAdvecSchArg;
   p.calcAdvection = 1; p.rkSign = c.p.D(MP_RKSIGN);
-  MdAcc a{tg, tr, u, v, w, 1};
-  dim3 blk(32, 4), grd((g.PX + 31) / 32, (g.PY + 3) / 4, g.Nr);
-  c.launches += 3;
-  md_pass_kernel<0><<<grd, blk, 0, c.stream>>>(tg, a, p, nullptr, tr, T1, V1, compressible, dT);
-  a.T_ = T1;
-  md_pass_kernel<1><<<grd, blk, 0, c.stream>>>(tg, a, p, V1, tr, T2, V2, compressible, dT);
-  a.T_ = T2;
-  if (*implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, T2, tr, gT, dT);
-  else md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, V2, tr, gT, compressible, dT);
+  MdAcc a{tg, tr, u, v, w, 1, corners, 0};
+  const double *Tin = tr, *Vin = nullptr;
+  int cur = 0;
+  const int npass = cube ? 3 : 2;
+  for (int ipass = 1; ipass <= npass; ipass++) {
+    MdUpd q{};
+    bool fluxX, fluxY;
+    if (cube) {
+      q.cube = 1; q.N = eN; q.S = eS; q.E = eE; q.W = eW;
+      if (ipass == 1) {
+        q.overlapOnly = nCFace % 3 == 0; q.interiorOnly = nCFace % 3 != 0;
+        fluxX = nCFace == 6 || nCFace == 1 || nCFace == 2; fluxY = nCFace == 3 || nCFace == 4 || nCFace == 5;
+      } else if (ipass == 2) {
+        q.overlapOnly = nCFace % 3 == 2; q.interiorOnly = nCFace % 3 == 1;
+        fluxX = nCFace == 2 || nCFace == 3 || nCFace == 4; fluxY = nCFace == 5 || nCFace == 6 || nCFace == 1;
+      } else {
+        q.interiorOnly = 1;
+        fluxX = nCFace == 5 || nCFace == 6; fluxY = nCFace == 2 || nCFace == 3;
+      }
+    } else { fluxX = ipass % 2 == 1; fluxY = !fluxX; }
+    for (int dir = 0; dir < 2; dir++) {
+      if (!(dir == 0 ? fluxX : fluxY)) continue;
+      // overlap-only passes touch nothing unless the tile lies on the relevant facet edges (:386, :607)
+      const bool edgeOk = dir == 0 ? (eN || eS) : (eE || eW);
+      if (q.overlapOnly && !edgeOk) continue;
+      a.T_ = Tin;
+      a.dirIn = q.overlapOnly ? (dir == 0 ? 1 : 2) : 0;
+      q.dirOut = (q.overlapOnly && ipass == 1) ? (dir == 0 ? 2 : 1) : 0;
+      c.launches++;
+      if (dir == 0) md_pass_kernel<0><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+      else md_pass_kernel<1><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+      Tin = Tb[cur]; Vin = Vb[cur];
+      cur ^= 1;
+    }
+  }
+  a.T_ = Tin; a.dirIn = 0;
+  c.launches++;
+  if (*implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, Tin, tr, gT, dT);
+  else md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, gT, compressible, dT);
   if (cudaGetLastError() != cudaSuccess) { fail(5, "gad_advection_b200_: launch failed"); return; }
   if (!from_device(gTracer, gT, n3)) return;
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) fail(6, "gad_advection_b200_: stream error");

@@ -833,7 +833,7 @@ void mom_v_implicit_r_b200_(const double *kappaRV, const int *bi, const int *bj,
   mom_implicit_r(kappaRV, bi, bj, gV, 2);
 }
 
-void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ierr) {
+void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, const int *edges, int *ierr) {
   Ctx &c = ctx();
   *ierr = 1;
   if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
@@ -841,6 +841,7 @@ void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, int *ier
     if (csCorners[t] < 0 || csCorners[t] > 15 || (csCorners[t] && myFace[t] < 1)) { fail(70, "set_cs_tiles: bad corner mask / facet number"); return; }
   c.csCorners.assign(csCorners, csCorners + c.g.nTiles);
   c.csFace.assign(myFace, myFace + c.g.nTiles);
+  c.csEdges.assign(edges, edges + c.g.nTiles);
   *ierr = 0;
 }
 

@@ -213,7 +213,8 @@ def set_topology(topo: Exch2Topology, myTileList=None):
     N, S_, E, W = (np.asarray(tb[n]) for n in ("isNedge", "isSedge", "isEedge", "isWedge"))
     corners = ((W & S_) * 1 + (E & S_) * 2 + (E & N) * 4 + (W & N) * 8).astype(np.int32)[tl - 1]
     faces = np.ascontiguousarray(np.asarray(topo.myFace, dtype=np.int32)[tl - 1])
-    L.mitgcm_b200_set_cs_tiles_(ip(np.ascontiguousarray(corners)), ip(faces), C.byref(ierr))
+    edges = np.ascontiguousarray((N * 1 + S_ * 2 + E * 4 + W * 8).astype(np.int32)[tl - 1])
+    L.mitgcm_b200_set_cs_tiles_(ip(np.ascontiguousarray(corners)), ip(faces), ip(edges), C.byref(ierr))
     if ierr.value:
         raise RuntimeError(f"set_cs_tiles failed: {L.mitgcm_b200_last_error_string().decode()}")
 

@@ -86,3 +86,71 @@ def test_advect_xy_golden_with_the_cuda_kernel(rt):
     for r, mx, mn, me, sd in zip(out, gold["dynstat_salt_max"], gold["dynstat_salt_min"], gold["dynstat_salt_mean"],
                                  gold["dynstat_salt_sd"]):
         assert (f"{r['max']:.13E}", f"{r['min']:.13E}", f"{r['mean']:.13E}", f"{r['sd']:.13E}") == (mx, mn, me, sd)
+
+
+class _CubeEngine:
+    """gad_advection with the Oracle's signature, routed to gad_advection_b200_ (the facet number and the facet
+    edges come from the topology handed to the library, as the reference reads W2_EXCH2_TOPOLOGY.h)."""
+
+    def __init__(self, rt):
+        self.rt = rt
+
+    def setup(self, g, params, op, topo):
+        from mitgcm_b200.exch2 import set_topology
+        self.rt.init(g.d)
+        self.rt.set_grid(g)
+        set_topology(topo)
+        self.rt.set_params(rkSign=params["rkSign"])
+
+    def gad_advection(self, bi, bj, scheme, vscheme, implicitAdvection, compressible, dT, u, v, w, tracer, gT, nCFace=0, edges=0):
+        t = (bj - 1, bi - 1)
+        self.rt.set_params(gad_multidim_compressible=int(compressible))
+        self.rt.gad_advection(implicitAdvection, scheme, vscheme, 1, dT, np.ascontiguousarray(u[t]), np.ascontiguousarray(v[t]),
+                              np.ascontiguousarray(w[t]), tracer, gT, bi, bj)
+        return 0
+
+
+@pytest.mark.parametrize("compressible", [0, 1], ids=["default", "compressible"])
+@pytest.mark.parametrize("scheme", [33, 7, 1])
+def test_gad_advection_on_the_cubed_sphere_matches_oracle(rt, scheme, compressible):
+    """The three facet-dependent passes on 24 tiles of 16x16 (cs32 grid files, random land): interior tiles, edge
+    tiles and corner tiles of every facet; whole halo'd slab of the tendency <= 1e-13."""
+    from oracle import advect_cs as acs
+    from mitgcm_b200.grid import cube_masks_from_depth
+    T, d, g, _, _, _ = acs.setup(16, 16)
+    rng = np.random.default_rng(11)
+    depth = np.where(rng.random((32, 192)) < 0.1, 0.0, -1.0e5)
+    g.a["rF"] = np.array([0.0, -1.0e5])
+    cube_masks_from_depth(g, T, depth, hFacMin=1.0, hFacMinDr=0.0)
+    o = Oracle(g, dict(rkSign=-1.0))
+    eng = _CubeEngine(rt)
+    eng.setup(g, o.params, None, T)
+    edges = acs.tile_edges(T)
+    u = 0.5 * rng.standard_normal(d.shape3) * g.maskW
+    v = 0.5 * rng.standard_normal(d.shape3) * g.maskS
+    w = np.zeros(d.shape3)
+    tr = (1.0 + rng.random(d.shape3)) * g.maskC
+    dT = np.full(d.Nr, 2700.0)
+    seen = set()
+    for bi in range(1, d.nSx + 1):
+        a, b = np.zeros((d.Nr, d.PY, d.PX)), np.zeros((d.Nr, d.PY, d.PX))
+        assert o.gad_advection(bi, 1, scheme, scheme, 0, compressible, dT, u, v, w, tr, a, int(T.myFace[bi - 1]), int(edges[bi - 1])) == 0
+        eng.gad_advection(bi, 1, scheme, scheme, 0, compressible, dT, u, v, w, tr, b)
+        fin = np.isfinite(a)
+        assert np.array_equal(fin, np.isfinite(b)), bi
+        scale = max(np.abs(a[fin]).max(), 1e-300)
+        assert np.abs(a[fin] - b[fin]).max() <= 1e-13 * scale, (bi, int(T.myFace[bi - 1]), int(edges[bi - 1]))
+        seen.add((int(T.myFace[bi - 1]), int(edges[bi - 1])))
+    assert len(seen) == 24
+
+
+def test_advect_cs_golden_with_the_cuda_kernel(rt):
+    """verification/advect_cs (theta, scheme 33 on the cs32 cube) with gad_advection_b200_ in the loop: every
+    printed digit of %MON dynstat_theta_* at steps 0, 8, ..., 192."""
+    from oracle import advect_cs as acs
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "advect_cs.json")))
+    out = acs.run(192, engine=_CubeEngine(rt))
+    assert len(out) == 25
+    for r, mx, mn, me, sd in zip(out, gold["dynstat_theta_max"], gold["dynstat_theta_min"], gold["dynstat_theta_mean"],
+                                 gold["dynstat_theta_sd"]):
+        assert (f"{r['max']:.13E}", f"{r['min']:.13E}", f"{r['mean']:.13E}", f"{r['sd']:.13E}") == (mx, mn, me, sd)
