@@ -39,6 +39,8 @@ enum {
   MG_MASKC, MG_MASKW, MG_MASKS,
   MG_UVEL, MG_VVEL, MG_WVEL, MG_THETA, MG_SALT, MG_GU, MG_GV, MG_GUNM1, MG_GVNM1,
   MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART, MG_THETA2, MG_RHOINSITU,
+  /* CG3D operators and preconditioner, COMMON /CG3D_R/ (model/inc/CG3D.h:30-48) */
+  MG_AW3D, MG_AS3D, MG_AV3D, MG_AC3D, MG_ZMC, MG_ZML, MG_ZMU,
   MG_N3D_END,
   /* (Nr+1)-level tile arrays */
   MG_KAPPARU = 200, MG_KAPPARV, MG_N3DP_END,
@@ -55,7 +57,7 @@ enum {
   MP_VISCAHD, MP_VISCAHZ, MP_VISCA4D, MP_VISCA4Z, MP_SIDEDRAGFACTOR, MP_BOTTOMDRAGLINEAR,
   MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
   MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
-  MP_DIFFKRT, MP_VISCAR, MP_SBETA, MP_IVDC_KAPPA,
+  MP_DIFFKRT, MP_VISCAR, MP_SBETA, MP_IVDC_KAPPA, MP_CG3DNORM, MP_CG3DTOLERANCE_SQ,
   MP_ND,
   MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
   MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
@@ -68,7 +70,7 @@ enum {
   /* pkg/mom_vecinv */
   MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
   MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
-  MI_VECTORINVARIANTMOMENTUM,
+  MI_VECTORINVARIANTMOMENTUM, MI_CG3DNORMALISERHS,
   MI_NI_END
 };
 
@@ -147,6 +149,17 @@ void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchAr
                          const double *vFld, const double *wFld, const double *tracer, double *gTracer,
                          const int *bi, const int *bj, const double *myTime, const int *myIter,
                          const int *myThid);
+
+/* ---- CG3D ---------------------------------------------------
+ * Same argument list as SUBROUTINE CG3D (model/src/cg3d.F:13-17; caller solve_for_pressure.F:427).  Operators and
+ * preconditioner come from the mirrors MG_AW3D .. MG_ZMU of COMMON /CG3D_R/ (model/inc/CG3D.h:30-48, full-halo
+ * tile3d as INI_CG3D leaves them), maskC from MG_MASKC, cg3dNorm / cg3dTolerance_sq / cg3dNormaliseRHS from the
+ * parameters.  cg3d_b returns normalised, cg3d_x the interior solution, as in the reference.  Single rank,
+ * select_rStar = 0. */
+void cg3d_b200_(double *cg3d_b, double *cg3d_x, double *firstResidual, double *lastResidual, int *numIters,
+                const int *myIter, const int *myThid);
+/* the values cg3d.F:243-244 prints inside the solver (`cg3d: Sum(rhs),rhsMax`) */
+void mitgcm_b200_cg3d_rhs_stats_(double *sumRHS, double *rhsMax);
 
 /* ---- MOM_FLUXFORM -----------------------------------------------------------------
  * Same argument list as pkg/mom_fluxform/mom_fluxform.F:42-48 (caller dynamics.F:517),

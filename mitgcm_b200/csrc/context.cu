@@ -169,6 +169,7 @@ void mitgcm_b200_finalize_(void) {
   if (c.e2List) cudaFree(c.e2List);
   c.e2List = nullptr;
   c.csCorners.clear(); c.csFace.clear(); c.csEdges.clear();
+  cg3d_free_workspace();
   c.e2Count = 0;
   for (int w = 0; w < 2; w++) {
     if (c.e2UvList[w]) cudaFree(c.e2UvList[w]);

@@ -81,6 +81,7 @@ bool from_device(double *hostOrDev, const double *dev, size_t n);  // no-op when
 bool exch2_active();                                   // a pkg/exch2 topology has been set
 bool exch2_field(double *f, int nz);                   // EXCH2_3D_RX as one gather
 bool exch2_uv_field(double *u, double *v, int nz, bool withSigns);   // EXCH2_UV_3D_RX as one gather
-bool exch_field(double *f, int nz);                    // EXCH_XY(Z)_RL on a mirror (step.cu)
+bool exch_field(double *f, int nz);
+void cg3d_free_workspace();                            // cg3d.cu                    // EXCH_XY(Z)_RL on a mirror (step.cu)
 
 }  // namespace mg

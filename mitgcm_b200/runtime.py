@@ -200,6 +200,27 @@ def mom_vecinv(bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVe
     _check()
 
 
+def set_cg3d_operator(op: dict):
+    """Uploads INI_CG3D's output: aW3d, aS3d, aV3d, aC3d, zMC, zML, zMU (full-halo tile3d) and cg3dNorm,
+    cg3dTolerance_sq, cg3dNormaliseRHS."""
+    for n in "aW3d aS3d aV3d aC3d zMC zML zMU".split():
+        set_field(n, np.ascontiguousarray(op[n]))
+    set_params(cg3dNorm=op["cg3dNorm"], cg3dTolerance_sq=op["cg3dTolerance_sq"], cg3dNormaliseRHS=int(op["cg3dNormaliseRHS"]))
+
+
+def cg3d(b, x, numIters, myIter=0, myThid=1):
+    """CALL CG3D(cg3d_b, cg3d_x, firstResidual, lastResidual, numIters, myIter, myThid) -- model/src/cg3d.F:13-17.
+    Returns dict(firstResidual, lastResidual, numIters, sumRHS, rhsMax); b and x are updated in place."""
+    L = _lib.lib()
+    f, l = C.c_double(), C.c_double()
+    ni = C.c_int(numIters)
+    L.cg3d_b200_(_addr(b), _addr(x), C.byref(f), C.byref(l), C.byref(ni), _i(myIter), _i(myThid))
+    _check()
+    s, r = C.c_double(), C.c_double()
+    L.mitgcm_b200_cg3d_rhs_stats_(C.byref(s), C.byref(r))
+    return dict(firstResidual=f.value, lastResidual=l.value, numIters=ni.value, sumRHS=s.value, rhsMax=r.value)
+
+
 def mom_implicit_r(kappaR, bi, bj, gFld, isV=False, myTime=0.0, myIter=0, myThid=1):
     """CALL MOM_U_IMPLICIT_R / MOM_V_IMPLICIT_R(kappaR?, bi, bj, ...) -- pkg/mom_common/mom_{u,v}_implicit_r.F:6-8,
     followed by the COMMON array solved in place (gU / gV)."""

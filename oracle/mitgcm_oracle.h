@@ -113,6 +113,17 @@ void og_cg2d_sr(const og_dims *d, const og_cg2d_op *op, double *cg2d_b, double *
                 int *numIters, int *nIterMin, double *sumRHS, double *rhsMax,
                 double *resHist);
 
+/* ---- CG3D (model/src/cg3d.F:13-545, model/src/ini_cg3d.F, model/inc/CG3D.h) -- see cg3d_oracle.c ---------- */
+typedef struct {
+  double *aW3d, *aS3d, *aV3d, *aC3d, *zMC, *zML, *zMU;   /* tile3d */
+  double cg3dNorm, cg3dTolerance_sq;
+  int cg3dNormaliseRHS;
+} og_cg3d_op;
+void og_ini_cg3d(const og_grid *g, const og_params *p, double vertFac, double cg3dTargetResidual,
+                 double cg3dTargetResWunit, og_cg3d_op *op);
+void og_cg3d(const og_dims *d, const og_cg3d_op *op, const double *maskC, double *cg3d_b, double *cg3d_x,
+             double *firstResidual, double *lastResidual, int *numIters, double *sumRHS, double *rhsMax);
+
 /* ---- MOM_FLUXFORM (pkg/mom_fluxform/mom_fluxform.F:42-1064) ------------- */
 /* One tile, one level.  uVel,vVel,wVel,gU,gV are tile3d (COMMON DYNVARS.h);
  * kappaRU/V are (PX*PY*(Nr+1)) per-tile arrays; the six slabs are PX*PY. */

@@ -57,6 +57,11 @@ class Cg2dOp(C.Structure):
                [("cg2dNorm", C.c_double), ("cg2dTolerance_sq", C.c_double), ("cg2dNormaliseRHS", C.c_int)]
 
 
+class Cg3dOp(C.Structure):
+    _fields_ = [(n, P) for n in "aW3d aS3d aV3d aC3d zMC zML zMU".split()] + \
+               [("cg3dNorm", C.c_double), ("cg3dTolerance_sq", C.c_double), ("cg3dNormaliseRHS", C.c_int)]
+
+
 DEFAULT_PARAMS = dict(
     deltaTMom=1200.0, deltaTFreeSurf=1200.0, freeSurfFac=1.0, implicSurfPress=1.0, implicDiv2DFlow=1.0,
     rkSign=-1.0, cg2dpcOffDFac=0.51, cg2dTargetResidual=1e-7, cg2dTargetResWunit=-1.0, globalArea=0.0,
@@ -136,6 +141,28 @@ class Oracle:
         if history:
             out["hist"] = hist[:ni.value]
         return out
+
+    # ---- cg3d ----
+    def ini_cg3d(self, vertFac=1.0, cg3dTargetResidual=1e-7, cg3dTargetResWunit=-1.0):
+        """INI_CG3D: operators aW3d..aC3d and the preconditioner zMC, zML, zMU (tile3d) + cg3dNorm, tolerance."""
+        d = self.grid.d
+        arrs = {n: np.zeros(d.shape3) for n in "aW3d aS3d aV3d aC3d zMC zML zMU".split()}
+        op = Cg3dOp(**{n: ptr(a) for n, a in arrs.items()})
+        self.lib.og_ini_cg3d(C.byref(self.g), C.byref(self.p), C.c_double(vertFac), C.c_double(cg3dTargetResidual),
+                             C.c_double(cg3dTargetResWunit), C.byref(op))
+        arrs.update(cg3dNorm=op.cg3dNorm, cg3dTolerance_sq=op.cg3dTolerance_sq, cg3dNormaliseRHS=bool(op.cg3dNormaliseRHS))
+        return arrs
+
+    def cg3d(self, op, b, x, numIters):
+        """CG3D; b and x are updated in place as the reference does.  Returns dict(firstResidual, lastResidual,
+        numIters, sumRHS, rhsMax)."""
+        cop = Cg3dOp(**{n: ptr(op[n]) for n in "aW3d aS3d aV3d aC3d zMC zML zMU".split()}, cg3dNorm=op["cg3dNorm"],
+                     cg3dTolerance_sq=op["cg3dTolerance_sq"], cg3dNormaliseRHS=int(op["cg3dNormaliseRHS"]))
+        f, l, s, r = (C.c_double() for _ in range(4))
+        ni = C.c_int(numIters)
+        self.lib.og_cg3d(C.byref(self.d), C.byref(cop), ptr(self.grid.a["maskC"]), ptr(b), ptr(x), C.byref(f), C.byref(l),
+                         C.byref(ni), C.byref(s), C.byref(r))
+        return dict(firstResidual=f.value, lastResidual=l.value, numIters=ni.value, sumRHS=s.value, rhsMax=r.value)
 
     # ---- momentum ----
     def mom_fluxform(self, bi, bj, k, iMin, iMax, jMin, jMax, kappaRU, kappaRV, fVerUkm, fVerVkm,

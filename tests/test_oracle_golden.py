@@ -313,3 +313,26 @@ def test_advect_cs_theta_statistics_every_printed_digit():
     for r, mx, mn, me, sd in zip(out, gold["dynstat_theta_max"], gold["dynstat_theta_min"], gold["dynstat_theta_mean"],
                                  gold["dynstat_theta_sd"]):
         assert (fmt(r["max"], 13), fmt(r["min"], 13), fmt(r["mean"], 13), fmt(r["sd"], 13)) == (mx, mn, me, sd)
+
+
+# ---------------------------------------------------------------------------------------
+# CG3D: operator-level known answer only (the solver lines need the whole non-hydrostatic step).
+# verification/tutorial_deep_convection: 100 x 100 x 50 cells of 20 m, 2 x 2 tiles of 50 x 50.
+# ---------------------------------------------------------------------------------------
+def test_ini_cg3d_normalisation_factor_of_tutorial_deep_convection():
+    from mitgcm_b200.grid import Dims, cartesian_grid, masks_from_depth, global_area
+    from oracle.pyoracle import Oracle
+    d = Dims(sNx=50, sNy=50, OLx=2, OLy=2, nSx=2, nSy=2, Nr=50)
+    g = cartesian_grid(d, [20.0] * 100, [20.0] * 100, [20.0] * 50, f0=1e-4, beta=0.0, gBaro=10.0)
+    masks_from_depth(g, -1000.0 * np.ones((100, 100)), hFacMin=1.0)
+    o = Oracle(g, dict(deltaTMom=20.0, deltaTFreeSurf=20.0, globalArea=global_area(g)))
+    op = o.ini_cg3d(1.0, 1e-9, -1.0)
+    assert fmt(op["cg3dNorm"], 16) == "5.0000000000000003E-02"      # results/output.txt: INI_CG3D: CG3D normalisation factor
+    # the operator is symmetric-negative-definite on the wet cells: CG reduces the residual monotonically enough
+    rng = np.random.default_rng(0)
+    jj, ii = d.interior()
+    b = np.zeros(d.shape3)
+    b[..., jj, ii] = rng.standard_normal(b[..., jj, ii].shape)
+    x = np.zeros(d.shape3)
+    r = o.cg3d(op, b, x, 40)
+    assert r["lastResidual"] < 0.02 * r["firstResidual"]
