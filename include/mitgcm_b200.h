@@ -70,7 +70,7 @@ enum {
   /* pkg/mom_vecinv */
   MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
   MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
-  MI_VECTORINVARIANTMOMENTUM, MI_CG3DNORMALISERHS,
+  MI_VECTORINVARIANTMOMENTUM, MI_CG3DNORMALISERHS, MI_MULTIDIMADVECTION,
   MI_NI_END
 };
 

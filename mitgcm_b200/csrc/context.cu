@@ -151,6 +151,7 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.p.i[MI_MOMDISSIP_IN_AB - 100] = 1; c.p.i[MI_TEMPADVSCHEME - 100] = 2;
   c.p.i[MI_TEMPVERTADVSCHEME - 100] = 2;
   c.p.i[MI_USECORIOLIS - 100] = 1; c.p.i[MI_SELECTVORTSCHEME - 100] = 1;
+  c.p.i[MI_MULTIDIMADVECTION - 100] = 1;
   if (!build_push_tables()) return;
   c.ready = true;
   *ierr = 0;

@@ -35,6 +35,9 @@ struct TileGrid {
 };
 
 bool make_tile_grid(int bi, int bj, TileGrid &tg);   // host: fills pointers from the mirrors
+// host: GAD_ADVECTION of one tile on device pointers (gad_advection.cu); dT = deltaTLev(Nr) on the device
+bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme, int implicitAdvection, const double *u,
+                        const double *v, const double *w, const double *tr, double *gT, const double *dT);
 
 struct GadPar {
   int k, advScheme, vertAdvScheme, calcAdvection, implicitAdvection, applyAB, useDiffKr4, implicitDiffusion;

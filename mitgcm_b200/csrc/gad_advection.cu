@@ -226,57 +226,45 @@ static bool md_scheme(int s) {
 
 using namespace mg;
 
-extern "C" void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchArg, const int *vertAdvecSchArg,
-                                    const int *trIdentity, const double *deltaTLev, const double *uFld,
-                                    const double *vFld, const double *wFld, const double *tracer, double *gTracer,
-                                    const int *bi, const int *bj, const double *myTime, const int *myIter,
-                                    const int *myThid) {
-  (void)trIdentity; (void)myTime; (void)myIter; (void)myThid;
+namespace mg {
+
+// GAD_ADVECTION for one tile on device pointers: u, v, w, tr, gT are the (slab, Nr) arrays of the tile, dT the
+// deltaTLev(Nr) array.  Shared by the per-call entry point and the resident step (multi-dimensional advection of theta).
+bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme, int implicitAdvection, const double *u,
+                        const double *v, const double *w, const double *tr, double *gT, const double *dT) {
   Ctx &c = ctx();
-  c.lastError = 0;
-  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
   const Geom &g = c.g;
   const int compressible = c.p.I(MI_GAD_MULTIDIM_COMPRESSIBLE);
-  if (!md_scheme(*advectionSchArg) || (!*implicitAdvection && !md_scheme(*vertAdvecSchArg))) {
-    fail(42, "gad_advection_b200_: advection scheme incompatible with multi-dim advection");
-    return;
-  }
-  if (*implicitAdvection && compressible) { fail(42, "gad_advection_b200_: implicitAdvection with GAD_MULTIDIM_COMPRESSIBLE"); return; }
-  if (*advectionSchArg == ADV_OS7MP && (g.OLx < 4 || g.OLy < 4)) { fail(42, "gad_advection_b200_: OS7MP needs OLx, OLy >= 4"); return; }
-  TileGrid tg;
-  if (!make_tile_grid(*bi, *bj, tg)) { if (!c.lastError) fail(43, "grid mirrors not set"); return; }
-  const size_t ns = g.slab, n3 = ns * g.Nr;
-  const size_t tile = (size_t)(*bi - 1) + (size_t)g.nSx * (size_t)(*bj - 1);
+  if (!md_scheme(advScheme) || (!implicitAdvection && !md_scheme(vertScheme)))
+    return fail(42, "gad_advection: advection scheme incompatible with multi-dim advection");
+  if (implicitAdvection && compressible) return fail(42, "gad_advection: implicitAdvection with GAD_MULTIDIM_COMPRESSIBLE");
+  if (advScheme == ADV_OS7MP && (g.OLx < 4 || g.OLy < 4)) return fail(42, "gad_advection: OS7MP needs OLx, OLy >= 4");
+  const size_t n3 = g.slab * g.Nr;
   // cubed sphere: facet number and facet edges of this tile (gad_advection.F:249-258)
   const bool cube = exch2_active();
   int nCFace = 0, edges = 0;
   if (cube) {
-    if ((int)c.csFace.size() != g.nTiles || (int)c.csEdges.size() != g.nTiles) { fail(44, "gad_advection_b200_: mitgcm_b200_set_cs_tiles_ not called"); return; }
-    if (g.OLx != g.OLy) { fail(44, "gad_advection_b200_: the cubed-sphere form needs OLx = OLy"); return; }
+    if ((int)c.csFace.size() != g.nTiles || (int)c.csEdges.size() != g.nTiles) return fail(44, "gad_advection: mitgcm_b200_set_cs_tiles_ not called");
+    if (g.OLx != g.OLy) return fail(44, "gad_advection: the cubed-sphere form needs OLx = OLy");
     nCFace = c.csFace[tile]; edges = c.csEdges[tile];
   }
   const int eN = edges & 1, eS = (edges >> 1) & 1, eE = (edges >> 2) & 1, eW = (edges >> 3) & 1;
   const int corners = (eW && eS ? 1 : 0) | (eE && eS ? 2 : 0) | (eE && eN ? 4 : 0) | (eW && eN ? 8 : 0);
-  const double *u = to_device(uFld, n3, 40, true), *v = to_device(vFld, n3, 41, true), *w = to_device(wFld, n3, 42, true);
-  // tracer is the full (.., Nr, nSx, nSy) array of the caller; only this tile is needed
-  const double *tr = is_device_ptr(tracer) ? tracer + n3 * tile : to_device(tracer + n3 * tile, n3, 43, true);
-  double *gT = is_device_ptr(gTracer) ? gTracer : to_device(gTracer, n3, 44, false);
   double *Tb[2] = {to_device(nullptr, n3, 45, false), to_device(nullptr, n3, 47, false)};
   double *Vb[2] = {to_device(nullptr, n3, 46, false), to_device(nullptr, n3, 48, false)};
-  double *dT = to_device(deltaTLev, (size_t)g.Nr, 49, true);
-  if (!u || !v || !w || !tr || !gT || !Tb[0] || !Vb[0] || !Tb[1] || !Vb[1] || !dT) return;
+  if (!Tb[0] || !Vb[0] || !Tb[1] || !Vb[1]) return false;
   dim3 blk(32, 4), grd((g.PX + 31) / 32, (g.PY + 3) / 4, g.Nr);
   if (cube && corners) {     // maskLocW / maskLocS with their facet corners filled
     double *mW = to_device(nullptr, n3, 54, false), *mS = to_device(nullptr, n3, 55, false);
-    if (!mW || !mS) return;
+    if (!mW || !mS) return false;
     c.launches++;
     md_mask_kernel<<<grd, blk, 0, c.stream>>>(tg, corners, mW, mS);
     tg.maskW = mW; tg.maskS = mS;
   }
   GadPar p{};
-  p.advScheme = *advectionSchArg;
+  p.advScheme = advScheme;
   // GAD_DST2U1_ADV_R is handed advectionScheme, not vertAdvecScheme (gad_advection.F:976)
-  p.vertAdvScheme = (*vertAdvecSchArg == ADV_UPWIND_1RST || *vertAdvecSchArg == ADV_DST2) ? *advectionSchArg : *vertAdvecSchArg;
+  p.vertAdvScheme = (vertScheme == ADV_UPWIND_1RST || vertScheme == ADV_DST2) ? advScheme : vertScheme;
   p.calcAdvection = 1; p.rkSign = c.p.D(MP_RKSIGN);
   MdAcc a{tg, tr, u, v, w, 1, corners, 0};
   const double *Tin = tr, *Vin = nullptr;
@@ -315,9 +303,35 @@ extern "C" void gad_advection_b200_(const int *implicitAdvection, const int *adv
   }
   a.T_ = Tin; a.dirIn = 0;
   c.launches++;
-  if (*implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, Tin, tr, gT, dT);
+  if (implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, Tin, tr, gT, dT);
   else md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, gT, compressible, dT);
-  if (cudaGetLastError() != cudaSuccess) { fail(5, "gad_advection_b200_: launch failed"); return; }
+  if (cudaGetLastError() != cudaSuccess) return fail(5, "gad_advection: launch failed");
+  return true;
+}
+
+}  // namespace mg
+
+extern "C" void gad_advection_b200_(const int *implicitAdvection, const int *advectionSchArg, const int *vertAdvecSchArg,
+                                    const int *trIdentity, const double *deltaTLev, const double *uFld,
+                                    const double *vFld, const double *wFld, const double *tracer, double *gTracer,
+                                    const int *bi, const int *bj, const double *myTime, const int *myIter,
+                                    const int *myThid) {
+  (void)trIdentity; (void)myTime; (void)myIter; (void)myThid;
+  Ctx &c = ctx();
+  c.lastError = 0;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  const Geom &g = c.g;
+  TileGrid tg;
+  if (!make_tile_grid(*bi, *bj, tg)) { if (!c.lastError) fail(43, "grid mirrors not set"); return; }
+  const size_t n3 = g.slab * g.Nr;
+  const size_t tile = (size_t)(*bi - 1) + (size_t)g.nSx * (size_t)(*bj - 1);
+  const double *u = to_device(uFld, n3, 40, true), *v = to_device(vFld, n3, 41, true), *w = to_device(wFld, n3, 42, true);
+  // tracer is the full (.., Nr, nSx, nSy) array of the caller; only this tile is needed
+  const double *tr = is_device_ptr(tracer) ? tracer + n3 * tile : to_device(tracer + n3 * tile, n3, 43, true);
+  double *gT = is_device_ptr(gTracer) ? gTracer : to_device(gTracer, n3, 44, false);
+  double *dT = to_device(deltaTLev, (size_t)g.Nr, 49, true);
+  if (!u || !v || !w || !tr || !gT || !dT) return;
+  if (!gad_advection_tile(tg, tile, *advectionSchArg, *vertAdvecSchArg, *implicitAdvection, u, v, w, tr, gT, dT)) return;
   if (!from_device(gTracer, gT, n3)) return;
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) fail(6, "gad_advection_b200_: stream error");
 }

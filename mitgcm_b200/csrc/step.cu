@@ -111,7 +111,10 @@ struct FusedAcc {
 #endif
 __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, const double *u, const double *v, const double *w,
                                                      const double *theta, const double *kapT, double *thetaNew,
-                                                     double *gtNm1, GadPar p0, double abFac, const double *sfT) {
+                                                     double *gtNm1, GadPar p0, double abFac, const double *sfT,
+                                                     const double *gT0, int doAB) {
+  // gT0: tendency to start from (the multi-dimensional advection of GAD_ADVECTION, temp_integrate.F:276-290);
+  // doAB: AdamsBashforthGt (gad_init_fixed.F: only the centred / 3rd-order upwind schemes 2, 3, 4)
   const int i = 1 + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 + blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx || j > g.sNy) return;
@@ -124,16 +127,18 @@ __global__ void __launch_bounds__(128, THERMO_MINB) thermo_kernel(TileGrid g, co
     const double fz0 = gad_fzon(g, a, p, i, j), fz1 = gad_fzon(g, a, p, i + 1, j);
     const double fm0 = gad_fmer(g, a, p, i, j), fm1 = gad_fmer(g, a, p, i, j + 1);
     const double fvu = gad_fver(g, a, p, i, j);
-    double gT = gad_tendency(g, a, p, i, j, 0., fz0, fz1, fm0, fm1, fvu, fVdn);
     const size_t s3 = g.s3(i, j, k);
+    double gT = gad_tendency(g, a, p, i, j, gT0 ? gT0[s3] : 0., fz0, fz1, fm0, fm1, fvu, fVdn);
     if (sfT) {    // APPLY_FORCING_T (apply_forcing.F, k = kSurface), tracForcingOutAB = 0 (temp_integrate.F:392-398)
       double gtForc = 0.;
       if (k == 1) gtForc = gtForc + sfT[g.s(i, j)] * g.recip_drF[0] * g.recip_hFacC[s3];
       gT = gT + gtForc;
     }
-    const double ab = abFac * (gT - gtNm1[s3]);            // ADAMS_BASHFORTH2
-    gtNm1[s3] = gT;
-    gT = gT + ab;
+    if (doAB) {
+      const double ab = abFac * (gT - gtNm1[s3]);          // ADAMS_BASHFORTH2
+      gtNm1[s3] = gT;
+      gT = gT + ab;
+    }
     thetaNew[s3] = theta[s3] + p.deltaT * gT;              // TIMESTEP_TRACER + CYCLE_TRACER
     fVdn = fvu;
   }
@@ -491,19 +496,34 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
     p.implicitDiffusion = q.I(MI_IMPLICITDIFFUSION);
     p.diffKh = q.D(MP_DIFFKHT); p.diffK4 = q.D(MP_DIFFK4T); p.rkSign = q.D(MP_RKSIGN);
     p.deltaT = q.D(MP_DELTATTRACER); p.diffKr4k = 0.;
+    // gad_init_fixed.F:100-131: Adams-Bashforth on gT and the 1-D form only for schemes 2, 3, 4; every other scheme
+    // is stepped forward in time and, unless multiDimAdvection = F, advected by GAD_ADVECTION
+    const bool abScheme = p.advScheme == ADV_CENTERED_2ND || p.advScheme == ADV_UPWIND_3RD || p.advScheme == ADV_CENTERED_4TH;
+    const bool multiDim = q.I(MI_MULTIDIMADVECTION) && !abScheme;
+    double *gTadv = nullptr, *dTdev = nullptr;
+    if (multiDim) {
+      gTadv = field(MG_GT);
+      std::vector<double> dTl((size_t)g.Nr, q.D(MP_DELTATTRACER));
+      dTdev = to_device(dTl.data(), (size_t)g.Nr, 56, true);
+      if (!gTadv || !dTdev) return false;
+      MG_CUDA(cudaStreamSynchronize(c.stream));     // dTl is a local
+      p.calcAdvection = 0;
+    }
     dim3 grd((g.sNx + 31) / 32, (g.sNy + 3) / 4);
     for (int bj = 1; bj <= g.nSy; bj++)
       for (int bi = 1; bi <= g.nSx; bi++) {
         TileGrid tg;
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t o2 = ns * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1)), o3 = o2 * g.Nr;
+        if (multiDim && !gad_advection_tile(tg, o2 / ns, q.I(MI_TEMPADVSCHEME), q.I(MI_TEMPVERTADVSCHEME), 0, u + o3, v + o3,
+                                            w + o3, th + o3, gTadv + o3, dTdev)) return false;
         c.launches++;
-        if (thermo_fast_ok(g, p))
+        if (!multiDim && thermo_fast_ok(g, p))
           thermo_fast_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr);
         else
           thermo_kernel<<<grd, blk, 0, c.stream>>>(tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac,
-                                                   sfT ? sfT + o2 : nullptr);
+                                                   sfT ? sfT + o2 : nullptr, multiDim ? gTadv + o3 : nullptr, abScheme ? 1 : 0);
         if (implDiff) {      // GAD_IMPLICIT_R on theta* (temp_integrate.F:495-503)
           c.launches++;
           impldiff_kernel<<<grd, blk, 0, c.stream>>>(tg, kapT + o3, th2 + o3, p.deltaT);

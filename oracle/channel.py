@@ -25,7 +25,7 @@ class ChannelOracle:
                       diffKrT=0.0, viscAr=0.0, tempAdvScheme=2, tempStepping=1, cg2dMaxIters=150,
                       momForcing=1, momDissip_In_AB=1, useSRCGSolver=0, buoyancyLinear=0, gravity=9.81,
                       tAlpha=2e-4, sBeta=0.0, rhoNil=999.8, rhoConst=999.8, ivdc_kappa=0.0,
-                      vectorInvariantMomentum=0)
+                      vectorInvariantMomentum=0, multiDimAdvection=1, gad_multidim_compressible=0)
         extra = {k: params[k] for k in list(params) if k in self.P}
         self.P.update(extra)
         self.o = Oracle(grid, {k: v for k, v in params.items() if k not in self.P})
@@ -75,6 +75,13 @@ class ChannelOracle:
             rTrans = np.zeros(ns)
             sl = {n: np.zeros(ns) for n in "xA yA maskUp uFld vFld wFld uTrans vTrans rTransKp1 fZon fMer".split()}
             theta = np.ascontiguousarray(s["theta"][ti])
+            # gad_init_fixed.F:100-131: AB on gT and the 1-D advection only for schemes 2, 3, 4
+            sch = P["tempAdvScheme"]
+            abScheme = sch in (2, 3, 4)
+            multiDim = bool(P["multiDimAdvection"]) and not abScheme
+            if multiDim:       # temp_integrate.F:276-290: GAD_ADVECTION gives the advective tendency
+                o.gad_advection(bi, bj, sch, sch, 0, P["gad_multidim_compressible"], dT, s["uVel"], s["vVel"], s["wVel"],
+                                s["theta"], gT)
             kapK = None
             if P["buoyancyLinear"] and P["ivdc_kappa"] != 0.0:     # CALC_3D_DIFFUSIVITY with the convective flag
                 kapK = np.zeros((d.Nr,) + ns)
@@ -86,12 +93,13 @@ class ChannelOracle:
                 o.gad_calc_rhs(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, max(1, k - 1), kUp, kDown, sl["xA"], sl["yA"],
                                sl["maskUp"], sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans,
                                sl["rTransKp1"], P["diffKhT"], P["diffK4T"], self.kapT if kapK is None else kapK[k - 1], zr, theta, theta, dT,
-                               P["tempAdvScheme"], P["tempAdvScheme"], 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
-                # ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86)
-                gNm1 = s["gtNm1"][ti][k - 1]
-                ab = abFac * (gT[k - 1] - gNm1)
-                gNm1[...] = gT[k - 1]
-                gT[k - 1] = gT[k - 1] + ab
+                               P["tempAdvScheme"], P["tempAdvScheme"], 0 if multiDim else 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
+                if abScheme:
+                    # ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86)
+                    gNm1 = s["gtNm1"][ti][k - 1]
+                    ab = abFac * (gT[k - 1] - gNm1)
+                    gNm1[...] = gT[k - 1]
+                    gT[k - 1] = gT[k - 1] + ab
             # TIMESTEP_TRACER + CYCLE_TRACER
             s["theta"][ti] = theta + dT[:, None, None] * gT
 
