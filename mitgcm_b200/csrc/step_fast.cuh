@@ -618,6 +618,143 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THF_MINB)
 #undef SM
 }
 
+// ---- pipelined variant: level k-1 (theta, u, v, hFacW, hFacS of the patch) is fetched with cp.async into a two-slot
+// ring while level k is computed; same arithmetic as thermo_fast_kernel (bit-identical results).
+enum { TR_T = 0, TR_U, TR_V, TR_HW, TR_HS, TR_N };
+struct ThermoPipeSmem {
+  double raw[2][TR_N][FT_N];
+  double T[FT_N], xA[FT_N], yA[FT_N], uT[FT_N], vT[FT_N], dyG[FT_N], dxG[FT_N];
+};
+__device__ __forceinline__ void thermo_pipe_prefetch(ThermoPipeSmem &sm, int slot, int e, size_t q, const TileGrid &g,
+                                                     const double *u, const double *v, const double *theta) {
+  __pipeline_memcpy_async(&sm.raw[slot][TR_T][e], theta + q, 8);
+  __pipeline_memcpy_async(&sm.raw[slot][TR_U][e], u + q, 8);
+  __pipeline_memcpy_async(&sm.raw[slot][TR_V][e], v + q, 8);
+  __pipeline_memcpy_async(&sm.raw[slot][TR_HW][e], g.hFacW + q, 8);
+  __pipeline_memcpy_async(&sm.raw[slot][TR_HS][e], g.hFacS + q, 8);
+}
+#ifndef THP_MINB
+#define THP_MINB 3
+#endif
+__global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
+    thermo_pipe_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
+                       const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
+                       double *__restrict__ gtNm1, GadPar p, double abFac, const double *__restrict__ sfT) {
+  extern __shared__ __align__(16) unsigned char thermo_pipe_smem[];
+  ThermoPipeSmem &sm = *reinterpret_cast<ThermoPipeSmem *>(thermo_pipe_smem);
+  __shared__ VertSmem vs;
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FT_X + tx;
+  stage_vert(vs, g, t, FT_X * FT_Y);
+  __syncthreads();
+  const int i0 = 1 + blockIdx.x * FT_X, j0 = 1 + blockIdx.y * FT_Y;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = i <= g.sNx && j <= g.sNy;
+  const int c = (ty + 1) * FT_W + (tx + 1);
+#define SM(a, di, dj) sm.a[c + (dj)*FT_W + (di)]
+  int se[2];
+  size_t sg[2];
+  bool sv_[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    int e = t + r * FT_X * FT_Y;
+    sv_[r] = e < FT_N;
+    int li = sv_[r] ? e % FT_W : 0, lj = sv_[r] ? e / FT_W : 0;
+    int gi = min(i0 - 1 + li, g.sNx + g.OLx), gj = min(j0 - 1 + lj, g.sNy + g.OLy);
+    se[r] = e;
+    sg[r] = g.s(gi, gj);
+  }
+  const size_t s = active ? g.s(i, j) : g.s(1, 1);
+  const size_t slab = g.slab;
+  const int PX = g.PX;
+  const double rdxC0 = g.recip_dxC[s], rdxC1 = g.recip_dxC[s + 1], rdyC0 = g.recip_dyC[s], rdyC1 = g.recip_dyC[s + PX];
+  const double rA = g.rA[s], r_rA = g.recip_rA[s], cfU = g.cosFacU[active ? j + g.OLy - 1 : 0];
+  const double advFac = p.calcAdvection ? 1. : 0.;
+  double rAdvFac = p.rkSign * advFac;
+  if (p.implicitAdvection) rAdvFac = p.rkSign;
+  double fVdn = 0., rTransKp1 = 0.;
+  // k-invariant patch metrics and the prefetch of the bottom level into ring slot 0
+  int rb = 0;
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+    if (sv_[r]) {
+      sm.dyG[se[r]] = g.dyG[sg[r]]; sm.dxG[se[r]] = g.dxG[sg[r]];
+      thermo_pipe_prefetch(sm, 0, se[r], sg[r] + slab * (size_t)(g.Nr - 1), g, u, v, theta);
+    }
+  __pipeline_commit();
+  for (int k = g.Nr; k >= 1; k--) {
+    const size_t ko = slab * (size_t)(k - 1);
+    const double drFk = vs.drF[k - 1];
+    // own-column loads first: one exposed memory latency per level
+    const size_t s3 = s + ko;
+    const double Tkm1 = k >= 2 ? theta[s3 - slab] : 0., mC = g.maskC[s3], mCm1 = k >= 2 ? g.maskC[s3 - slab] : 0.;
+    const double wK = w[s3], kapK = kapT[s3], rhC = g.recip_hFacC[s3], gtOld = gtNm1[s3];
+    __pipeline_wait_prior(0);
+    __syncthreads();             // level k has landed in slot rb; everybody is done with the previous level's tiles
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (sv_[r]) {
+        const int e = se[r];
+        const double xA = sm.dyG[e] * drFk * sm.raw[rb][TR_HW][e], yA = sm.dxG[e] * drFk * sm.raw[rb][TR_HS][e];
+        sm.T[e] = sm.raw[rb][TR_T][e]; sm.xA[e] = xA; sm.yA[e] = yA;
+        sm.uT[e] = sm.raw[rb][TR_U][e] * xA; sm.vT[e] = sm.raw[rb][TR_V][e] * yA;
+      }
+    __syncthreads();
+    if (k >= 2) {                // fetch level k-1 into the other slot while this level is computed
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        if (sv_[r]) thermo_pipe_prefetch(sm, rb ^ 1, se[r], sg[r] + ko - slab, g, u, v, theta);
+    }
+    __pipeline_commit();
+    if (active) {
+      const double T00 = SM(T, 0, 0);
+      // X / Y fluxes (GAD_C2_ADV_X/Y, GAD_DIFF_X/Y), west+east and south+north faces
+      double fz0 = 0., fz1 = 0., fm0 = 0., fm1 = 0.;
+      if (p.calcAdvection) {
+        fz0 = fz0 + SM(uT, 0, 0) * (T00 + SM(T, -1, 0)) * 0.5;
+        fz1 = fz1 + SM(uT, 1, 0) * (SM(T, 1, 0) + T00) * 0.5;
+        fm0 = fm0 + SM(vT, 0, 0) * (T00 + SM(T, 0, -1)) * 0.5;
+        fm1 = fm1 + SM(vT, 0, 1) * (SM(T, 0, 1) + T00) * 0.5;
+      }
+      double dz0 = 0., dz1 = 0., dm0 = 0., dm1 = 0.;
+      if (p.diffKh != 0.) {
+        dz0 = -p.diffKh * SM(xA, 0, 0) * rdxC0 * (T00 - SM(T, -1, 0)) * cfU;
+        dz1 = -p.diffKh * SM(xA, 1, 0) * rdxC1 * (SM(T, 1, 0) - T00) * cfU;
+        dm0 = -p.diffKh * SM(yA, 0, 0) * rdyC0 * (T00 - SM(T, 0, -1));
+        dm1 = -p.diffKh * SM(yA, 0, 1) * rdyC1 * (SM(T, 0, 1) - T00);
+      }
+      fz0 = fz0 + dz0; fz1 = fz1 + dz1; fm0 = fm0 + dm0; fm1 = fm1 + dm1;
+      // vertical flux at the upper interface of level k (GAD_C2_ADV_R, GAD_DIFF_R)
+      double fvu = 0., rTrans = 0.;
+      if (k >= 2) {
+        const double maskUp = mCm1 * mC;
+        rTrans = wK * rA * maskUp;
+        if (p.calcAdvection && !p.implicitAdvection) fvu = fvu + mCm1 * rTrans * (T00 + Tkm1) * 0.5;
+        double df = 0.;
+        if (!p.implicitDiffusion) df = -kapK * maskUp * rA * vs.rdrC[k - 1] * (T00 - Tkm1) * p.rkSign;
+        fvu = fvu + df;
+      }
+      double gT = 0. - rhC * vs.rdrF[k - 1] * r_rA *
+                           ((fz1 - fz0) + (fm1 - fm0) + (fVdn - fvu) * p.rkSign -
+                            T00 * ((SM(uT, 1, 0) - SM(uT, 0, 0)) * advFac + (SM(vT, 0, 1) - SM(vT, 0, 0)) * advFac +
+                                   (rTransKp1 - rTrans) * rAdvFac));
+      if (sfT) {   // APPLY_FORCING_T at k = kSurface, inside Adams-Bashforth (tracForcingOutAB = 0)
+        double gtForc = 0.;
+        if (k == 1) gtForc = gtForc + sfT[g.s(i, j)] * vs.rdrF[0] * rhC;
+        gT = gT + gtForc;
+      }
+      const double ab = abFac * (gT - gtOld);
+      gtNm1[s3] = gT;
+      gT = gT + ab;
+      thetaNew[s3] = T00 + p.deltaT * gT;
+      fVdn = fvu;
+      rTransKp1 = rTrans;
+    }
+    rb ^= 1;
+  }
+#undef SM
+}
+
+
 inline bool thermo_fast_ok(const Geom &g, const GadPar &p) {
   return p.advScheme == ADV_CENTERED_2ND && p.vertAdvScheme == ADV_CENTERED_2ND && p.diffK4 == 0. && !p.useDiffKr4 &&
          g.OLx >= 2 && g.OLy >= 2 && g.Nr < FT_NRMAX && !getenv("MITGCM_B200_GENERIC_STEP");

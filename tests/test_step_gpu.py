@@ -94,6 +94,28 @@ def test_vecinv_pipelined_kernel_is_bit_identical_to_the_generic_kernels(monkeyp
             assert np.array_equal(o[n], outs[0][n]), n
 
 
+def test_thermo_pipelined_kernel_is_bit_identical_to_the_staged_kernel(monkeypatch):
+    """thermo_pipe_kernel (cp.async ring) vs thermo_fast_kernel vs the generic thermo_kernel: same fields after 3 steps."""
+    outs = []
+    for env in ({}, {"MITGCM_B200_THERMO_NOPIPE": "1"}, {"MITGCM_B200_GENERIC_STEP": "1"}):
+        for k in ("MITGCM_B200_THERMO_NOPIPE", "MITGCM_B200_GENERIC_STEP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g, P, s = make_channel(sNx=48, sNy=40, Nr=6, nSx=2, nSy=1, land_frac=0.15, buoyancyLinear=1)
+        co = ChannelOracle(g, P, s)
+        m = Model(g, P, s, co.op)
+        try:
+            for _ in range(3):
+                m.step()
+            outs.append({n: m.get(n) for n in ("theta", "gtNm1", "uVel", "etaN")})
+        finally:
+            m.close()
+    for o in outs[1:]:
+        for n in o:
+            assert np.array_equal(o[n], outs[0][n]), n
+
+
 def test_mom_implicit_r_matches_oracle():
     """mom_{u,v}_implicit_r_b200_ through the C ABI (reference argument list + gU / gV, host buffers) against the
     oracle on a masked partial-cell grid: bit-identical (same recurrences, no reductions)."""
