@@ -48,6 +48,8 @@ GAD_CASES = [
     dict(scheme=2, diffKh=1e3, diffK4=0.0, ab=False, implDiff=True, implAdv=True),
     dict(scheme=7, diffKh=1e2, diffK4=0.0, ab=False),
     dict(scheme=7, diffKh=0.0, diffK4=0.0, ab=True),
+    # calcAdvection = F (the call temp_integrate.F makes after GAD_ADVECTION): diffusion on top of a given tendency
+    dict(scheme=33, diffKh=1e3, diffK4=1e11, ab=False, calcAdv=0, gT0=1e-6),
 ]
 
 
@@ -70,7 +72,8 @@ def test_gad_calc_rhs_matches_oracle(rt, case, shape):
     for bj in range(1, d.nSy + 1):
         for bi in range(1, d.nSx + 1):
             t = (bj - 1, bi - 1)
-            gT_o, gT_g = np.zeros((d.Nr,) + ns), np.zeros((d.Nr,) + ns)
+            gT_o = case.get("gT0", 0.0) * rng.standard_normal((d.Nr,) + ns)
+            gT_g = gT_o.copy()
             fV_o, fV_g = np.zeros((2,) + ns), np.zeros((2,) + ns)
             rTrans = np.zeros(ns)
             for k in range(d.Nr, 0, -1):
@@ -84,9 +87,9 @@ def test_gad_calc_rhs_matches_oracle(rt, case, shape):
                         case["diffKh"], case["diffK4"], KappaR, kr4, np.ascontiguousarray(T[t]),
                         np.ascontiguousarray(TAB[t]), dT)
                 fZo, fMo, fZg, fMg = (np.zeros(ns) for _ in range(4))
-                o.gad_calc_rhs(*args, case["scheme"], case["scheme"], 1, int(case.get("implAdv", False)),
+                o.gad_calc_rhs(*args, case["scheme"], case["scheme"], case.get("calcAdv", 1), int(case.get("implAdv", False)),
                                int(case["ab"]), int(bool(case.get("kr4"))), fZo, fMo, fV_o, gT_o)
-                rt.gad_calc_rhs(*args, 1, case["scheme"], case["scheme"], 1, int(case.get("implAdv", False)),
+                rt.gad_calc_rhs(*args, 1, case["scheme"], case["scheme"], case.get("calcAdv", 1), int(case.get("implAdv", False)),
                                 int(case["ab"]), int(bool(case.get("kr4"))), 0, 0, 0, fZg, fMg, fV_g, gT_g)
                 assert close(fZg, fZo) and close(fMg, fMo), (k, "horizontal fluxes")
                 assert close(fV_g[kUp - 1], fV_o[kUp - 1]), (k, "vertical flux")
