@@ -336,3 +336,21 @@ def test_ini_cg3d_normalisation_factor_of_tutorial_deep_convection():
     x = np.zeros(d.shape3)
     r = o.cg3d(op, b, x, 40)
     assert r["lastResidual"] < 0.02 * r["firstResidual"]
+
+
+# ---------------------------------------------------------------------------------------
+# verification/adjustment.128x64x1: gravity-wave adjustment of a one-layer atmosphere (p coordinates) on the global
+# lat-lon grid, pole to pole (zero-width faces closed by ADD_WALLS2MASKS), 2 x 2 tiles, 24 steps.  The golden was
+# written by an older model version (older SOLVE_FOR_PRESSURE print-out): agreement is >= 11 digits, not every digit.
+# ---------------------------------------------------------------------------------------
+def test_adjustment_128x64_lat_lon_all_steps():
+    from oracle import adjustment_latlon as al
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "adjustment.128x64x1.json")))
+    norm, out = al.run(24)
+    assert fmt(norm, 15) == "2.454122852291226E-07"            # golden: 0.2454122852291226263129944E-06
+    assert [r["numIters"] for r in out] == gold["cg2d_iters"]
+    for n, r in enumerate(out):
+        assert r["firstResidual"] == pytest.approx(float(gold["cg2d_init_res"][n]), rel=1e-11)
+        for f in ("eta", "uvel", "vvel"):
+            for st in ("max", "min", "mean", "sd"):
+                assert r[f][st] == pytest.approx(float(gold[f"dynstat_{f}_{st}"][n + 1]), rel=2e-11, abs=1e-12), (n, f, st)
