@@ -41,6 +41,7 @@ enum {
   MG_GT, MG_GTNM1, MG_GS, MG_GSNM1, MG_PHIHYD, MG_KAPPART, MG_THETA2, MG_RHOINSITU,
   /* CG3D operators and preconditioner, COMMON /CG3D_R/ (model/inc/CG3D.h:30-48) */
   MG_AW3D, MG_AS3D, MG_AV3D, MG_AC3D, MG_ZMC, MG_ZML, MG_ZMU,
+  MG_SALT2, MG_KAPPARS,
   MG_N3D_END,
   /* (Nr+1)-level tile arrays */
   MG_KAPPARU = 200, MG_KAPPARV, MG_N3DP_END,
@@ -58,6 +59,7 @@ enum {
   MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
   MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
   MP_DIFFKRT, MP_VISCAR, MP_SBETA, MP_IVDC_KAPPA, MP_CG3DNORM, MP_CG3DTOLERANCE_SQ,
+  MP_DIFFKHS, MP_DIFFK4S, MP_DIFFKRS,
   MP_ND,
   MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
   MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
@@ -71,6 +73,7 @@ enum {
   MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
   MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
   MI_VECTORINVARIANTMOMENTUM, MI_CG3DNORMALISERHS, MI_MULTIDIMADVECTION,
+  MI_SALTSTEPPING, MI_SALTADVSCHEME, MI_SALTVERTADVSCHEME,
   MI_NI_END
 };
 

@@ -152,6 +152,7 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.p.i[MI_TEMPVERTADVSCHEME - 100] = 2;
   c.p.i[MI_USECORIOLIS - 100] = 1; c.p.i[MI_SELECTVORTSCHEME - 100] = 1;
   c.p.i[MI_MULTIDIMADVECTION - 100] = 1;
+  c.p.i[MI_SALTADVSCHEME - 100] = 2; c.p.i[MI_SALTVERTADVSCHEME - 100] = 2;
   if (!build_push_tables()) return;
   c.ready = true;
   *ierr = 0;

@@ -33,7 +33,8 @@ ocean_phys_kernel(TileGrid g, const double *__restrict__ theta, const double *__
                   const double *__restrict__ SST, const double *__restrict__ lambdaT,
                   const double *__restrict__ tRef, const double *__restrict__ sRef, EosLinear e, double rkSign,
                   double ivdc_kappa, double diffKrT, int doRelax, int doRho,
-                  double *__restrict__ sfT, double *__restrict__ rho, double *__restrict__ kapT) {
+                  double *__restrict__ sfT, double *__restrict__ rho, double *__restrict__ kapT,
+                  double diffKrS, double *__restrict__ kapS) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
   const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
@@ -63,8 +64,10 @@ ocean_phys_kernel(TileGrid g, const double *__restrict__ theta, const double *__
       conv = (-sigmaR * gravitySign > 0.) ? 1. : 0.;
     }
     double kap = conv * ivdc_kappa + 0.;     // + KbryanLewis79 (diffKrBL79surf = diffKrBL79deep = 0)
+    const double kap0 = kap;
     kap = kap + diffKrT;                     // + diffKrNrT(k)
     kapT[s3] = kap;
+    if (kapS) kapS[s3] = kap0 + diffKrS;     // CALC_3D_DIFFUSIVITY for salt: + diffKrNrS(k)
     Tk = Tm; Sk = Sm;
   }
 }

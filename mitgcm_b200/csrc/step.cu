@@ -462,7 +462,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         c.launches++;
         ocean_phys_kernel<<<grd, blk, 0, c.stream>>>(tg, th + o3, sa + o3, sst + o2, lam + o2, tRef, sRef, e, q.D(MP_RKSIGN),
                                                      q.D(MP_IVDC_KAPPA), q.D(MP_DIFFKRT), relaxT ? 1 : 0, (buoy && ivdc) ? 1 : 0,
-                                                     sf + o2, rh + o3, kapT + o3);
+                                                     sf + o2, rh + o3, kapT + o3, q.D(MP_DIFFKRS),
+                                                     (q.I(MI_SALTSTEPPING) && field(MG_KAPPARS)) ? field(MG_KAPPARS) + o3 : nullptr);
       }
     MG_CUDA(cudaGetLastError());
   }
@@ -486,15 +487,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
       }
     MG_CUDA(cudaGetLastError());
   }
-  // THERMODYNAMICS
-  if (q.I(MI_TEMPSTEPPING)) {
-    double *th = field(MG_THETA), *th2 = field(MG_THETA2), *gtN = field(MG_GTNM1), *kapT = field(MG_KAPPART);
+  // THERMODYNAMICS: TEMP_INTEGRATE, then SALT_INTEGRATE (thermodynamics.F:268-300), the same kernels on another field
+  auto step_tracer = [&](int idT, int idT2, int idGN, int idKap, int advS, int vertS, double diffKh, double diffK4,
+                         const double *sfT) -> bool {
+    double *th = field(idT), *th2 = field(idT2), *gtN = field(idGN), *kapT = field(idKap);
     if (!th || !th2 || !gtN || !kapT) return false;
     GadPar p;
-    p.k = 0; p.advScheme = q.I(MI_TEMPADVSCHEME); p.vertAdvScheme = q.I(MI_TEMPVERTADVSCHEME);
+    p.k = 0; p.advScheme = advS; p.vertAdvScheme = vertS;
     p.calcAdvection = 1; p.implicitAdvection = 0; p.applyAB = 0; p.useDiffKr4 = 0;
     p.implicitDiffusion = q.I(MI_IMPLICITDIFFUSION);
-    p.diffKh = q.D(MP_DIFFKHT); p.diffK4 = q.D(MP_DIFFK4T); p.rkSign = q.D(MP_RKSIGN);
+    p.diffKh = diffKh; p.diffK4 = diffK4; p.rkSign = q.D(MP_RKSIGN);
     p.deltaT = q.D(MP_DELTATTRACER); p.diffKr4k = 0.;
     // gad_init_fixed.F:100-131: Adams-Bashforth on gT and the 1-D form only for schemes 2, 3, 4; every other scheme
     // is stepped forward in time and, unless multiDimAdvection = F, advected by GAD_ADVECTION
@@ -515,7 +517,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         TileGrid tg;
         if (!make_tile_grid(bi, bj, tg)) return false;
         size_t o2 = ns * ((size_t)(bi - 1) + (size_t)g.nSx * (bj - 1)), o3 = o2 * g.Nr;
-        if (multiDim && !gad_advection_tile(tg, o2 / ns, q.I(MI_TEMPADVSCHEME), q.I(MI_TEMPVERTADVSCHEME), 0, u + o3, v + o3,
+        if (multiDim && !gad_advection_tile(tg, o2 / ns, advS, vertS, 0, u + o3, v + o3,
                                             w + o3, th + o3, gTadv + o3, dTdev)) return false;
         c.launches++;
         if (!multiDim && thermo_fast_ok(g, p) && !getenv("MITGCM_B200_THERMO_NOPIPE")) {
@@ -539,8 +541,13 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
       }
     MG_CUDA(cudaGetLastError());
     // CYCLE_TRACER: theta <- theta** (interior); halos follow in the blocking exchange below
-    std::swap(c.fields[MG_THETA], c.fields[MG_THETA2]);
-  }
+    std::swap(c.fields[idT], c.fields[idT2]);
+    return true;
+  };
+  if (q.I(MI_TEMPSTEPPING) && !step_tracer(MG_THETA, MG_THETA2, MG_GTNM1, MG_KAPPART, q.I(MI_TEMPADVSCHEME), q.I(MI_TEMPVERTADVSCHEME),
+                                           q.D(MP_DIFFKHT), q.D(MP_DIFFK4T), sfT)) return false;
+  if (q.I(MI_SALTSTEPPING) && !step_tracer(MG_SALT, MG_SALT2, MG_GSNM1, MG_KAPPARS, q.I(MI_SALTADVSCHEME), q.I(MI_SALTVERTADVSCHEME),
+                                           q.D(MP_DIFFKHS), q.D(MP_DIFFK4S), nullptr)) return false;
   mark(1);
   // DYNAMICS
   {
@@ -706,6 +713,7 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   } else if (!exch_field(field(MG_UVEL), g.Nr) || !exch_field(field(MG_VVEL), g.Nr)) return false;
   if (!exch_field(field(MG_WVEL), g.Nr)) return false;
   if (q.I(MI_TEMPSTEPPING) && !exch_field(field(MG_THETA), g.Nr)) return false;
+  if (q.I(MI_SALTSTEPPING) && !exch_field(field(MG_SALT), g.Nr)) return false;
   mark(7);
   return true;
 }

@@ -96,6 +96,15 @@ def exchange(*names: str):
     rt.sync()
 
 
+_salt_stepping = False
+
+
+def set_salt_stepping(on: bool):
+    """The blocking exchange at the end of the step includes salt when saltStepping is on."""
+    global _salt_stepping
+    _salt_stepping = bool(on)
+
+
 def forward_step(myIter: int):
     """FORWARD_STEP across ranks: part 0 (thermodynamics, dynamics, CG2D with in-kernel peer
     communication), halo of cg2d_x, part 1 (eta, correction step, continuity), blocking exchanges."""
@@ -106,5 +115,5 @@ def forward_step(myIter: int):
     exchange("cg2d_x")
     L.mitgcm_b200_step_part_(C.byref(C.c_int(1)), C.byref(C.c_int(myIter)), C.byref(f), C.byref(n), C.byref(l), C.byref(ierr))
     rt._check(ierr)
-    exchange("uVel", "vVel", "wVel", "theta")
+    exchange(*(("uVel", "vVel", "wVel", "theta") + (("salt",) if _salt_stepping else ())))
     return dict(firstResidual=f.value, numIters=n.value, lastResidual=l.value)

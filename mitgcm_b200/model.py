@@ -25,7 +25,7 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa "
               "implicSurfPress implicDiv2DFlow rkSign vectorInvariantMomentum useCoriolis useAbsVorticity "
               "selectVortScheme selectKEscheme useJamartMomAdv upwindShear multiDimAdvection "
-              "gad_multidim_compressible").split()
+              "gad_multidim_compressible saltStepping diffKhS diffK4S diffKrS").split()
 
 
 def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
@@ -98,7 +98,8 @@ class Model:
             set_topology(topo)
         rt.set_params(**{k: P[k] for k in LIB_PARAMS if k in P})
         rt.set_params(deltaTtracer=P.get("deltaTtracer", P["deltaTMom"]), tempAdvScheme=P.get("tempAdvScheme", 2),
-                      tempVertAdvScheme=P.get("tempAdvScheme", 2), nIter0=0)
+                      tempVertAdvScheme=P.get("tempAdvScheme", 2), saltAdvScheme=P.get("saltAdvScheme", 2),
+                      saltVertAdvScheme=P.get("saltAdvScheme", 2), nIter0=0)
         rt.set_cg2d_operator(op)
         for n, fid in (("uVel", "uVel"), ("vVel", "vVel"), ("wVel", "wVel"), ("theta", "theta"), ("etaN", "etaN"),
                        ("surfForcU", "surfForcU"), ("surfForcV", "surfForcV")):
@@ -118,6 +119,10 @@ class Model:
         rt.fill_field("kappaRT", P.get("diffKrT", 0.0))
         for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1", "theta2", "cg2d_b", "cg2d_x"):
             rt.fill_field(n, 0.0)
+        if P.get("saltStepping"):
+            rt.fill_field("kappaRS", P.get("diffKrS", 0.0))
+            rt.fill_field("gsNm1", 0.0)
+            rt.fill_field("salt2", 0.0)
         self.it = 0
 
     def step(self):

@@ -25,15 +25,19 @@ class ChannelOracle:
                       diffKrT=0.0, viscAr=0.0, tempAdvScheme=2, tempStepping=1, cg2dMaxIters=150,
                       momForcing=1, momDissip_In_AB=1, useSRCGSolver=0, buoyancyLinear=0, gravity=9.81,
                       tAlpha=2e-4, sBeta=0.0, rhoNil=999.8, rhoConst=999.8, ivdc_kappa=0.0,
-                      vectorInvariantMomentum=0, multiDimAdvection=1, gad_multidim_compressible=0)
+                      vectorInvariantMomentum=0, multiDimAdvection=1, gad_multidim_compressible=0,
+                      saltStepping=0, saltAdvScheme=2, diffKhS=0.0, diffK4S=0.0, diffKrS=0.0)
         extra = {k: params[k] for k in list(params) if k in self.P}
         self.P.update(extra)
         self.o = Oracle(grid, {k: v for k, v in params.items() if k not in self.P})
         self.op = self.o.ini_cg2d()
         d = self.d
         self.s = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in state.items()}
-        for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1"):
+        for n in ("gU", "gV", "guNm1", "gvNm1", "gtNm1", "gsNm1"):
             self.s[n] = np.zeros(d.shape3)
+        if self.P["saltStepping"] and "salt" not in self.s:
+            self.s["salt"] = np.zeros(d.shape3)
+        self.kapS = np.full((d.PY, d.PX), float(self.P["diffKrS"]))
         self.kapU = np.full((d.Nr + 1, d.PY, d.PX), float(self.P["viscAr"]))
         self.kapT = np.full((d.PY, d.PX), float(self.P["diffKrT"]))
         self.threads = threads
@@ -67,41 +71,45 @@ class ChannelOracle:
         dT = np.full(d.Nr, float(P["deltaTtracer"]))
         zr = np.zeros(d.Nr)
 
-        def thermo(t):
+        def thermo(t, trc="theta", gNm1name="gtNm1", schName="tempAdvScheme", kh="diffKhT", k4="diffK4T", kr="diffKrT", kap2d=None):
             bi, bj = t
+            kap2d = self.kapT if kap2d is None else kap2d
             ti = (bj - 1, bi - 1)
             gT = np.zeros((d.Nr,) + ns)
             fV = np.zeros((2,) + ns)
             rTrans = np.zeros(ns)
             sl = {n: np.zeros(ns) for n in "xA yA maskUp uFld vFld wFld uTrans vTrans rTransKp1 fZon fMer".split()}
-            theta = np.ascontiguousarray(s["theta"][ti])
+            theta = np.ascontiguousarray(s[trc][ti])
             # gad_init_fixed.F:100-131: AB on gT and the 1-D advection only for schemes 2, 3, 4
-            sch = P["tempAdvScheme"]
+            sch = P[schName]
             abScheme = sch in (2, 3, 4)
             multiDim = bool(P["multiDimAdvection"]) and not abScheme
             if multiDim:       # temp_integrate.F:276-290: GAD_ADVECTION gives the advective tendency
                 o.gad_advection(bi, bj, sch, sch, 0, P["gad_multidim_compressible"], dT, s["uVel"], s["vVel"], s["wVel"],
-                                s["theta"], gT)
+                                s[trc], gT)
             kapK = None
             if P["buoyancyLinear"] and P["ivdc_kappa"] != 0.0:     # CALC_3D_DIFFUSIVITY with the convective flag
                 kapK = np.zeros((d.Nr,) + ns)
-                o.calc_3d_diffusivity(bi, bj, self.ivdc, float(P["ivdc_kappa"]), zr, np.full(d.Nr, float(P["diffKrT"])), kapK)
+                o.calc_3d_diffusivity(bi, bj, self.ivdc, float(P["ivdc_kappa"]), zr, np.full(d.Nr, float(P[kr])), kapK)
             for k in range(d.Nr, 0, -1):
                 kUp, kDown = 1 + (k + 1) % 2, 1 + k % 2
                 o.calc_adv_flow(bi, bj, k, s["uVel"], s["vVel"], s["wVel"], sl["xA"], sl["yA"], sl["maskUp"],
                                 sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans, sl["rTransKp1"])
                 o.gad_calc_rhs(bi, bj, 0, d.sNx + 1, 0, d.sNy + 1, k, max(1, k - 1), kUp, kDown, sl["xA"], sl["yA"],
                                sl["maskUp"], sl["uFld"], sl["vFld"], sl["wFld"], sl["uTrans"], sl["vTrans"], rTrans,
-                               sl["rTransKp1"], P["diffKhT"], P["diffK4T"], self.kapT if kapK is None else kapK[k - 1], zr, theta, theta, dT,
-                               P["tempAdvScheme"], P["tempAdvScheme"], 0 if multiDim else 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
+                               sl["rTransKp1"], P[kh], P[k4], kap2d if kapK is None else kapK[k - 1], zr, theta, theta, dT,
+                               sch, sch, 0 if multiDim else 1, 0, 0, 0, sl["fZon"], sl["fMer"], fV, gT)
                 if abScheme:
                     # ADAMS_BASHFORTH2 (adams_bashforth2.F:84-86)
-                    gNm1 = s["gtNm1"][ti][k - 1]
+                    gNm1 = s[gNm1name][ti][k - 1]
                     ab = abFac * (gT[k - 1] - gNm1)
                     gNm1[...] = gT[k - 1]
                     gT[k - 1] = gT[k - 1] + ab
             # TIMESTEP_TRACER + CYCLE_TRACER
-            s["theta"][ti] = theta + dT[:, None, None] * gT
+            s[trc][ti] = theta + dT[:, None, None] * gT
+
+        def thermo_salt(t):
+            thermo(t, "salt", "gsNm1", "saltAdvScheme", "diffKhS", "diffK4S", "diffKrS", self.kapS)
 
         buoy = bool(P["buoyancyLinear"])
 
@@ -134,6 +142,8 @@ class ChannelOracle:
                                                self.rho, self.ivdc))
         if P["tempStepping"]:
             self._map(thermo)
+        if P["saltStepping"]:
+            self._map(thermo_salt)
         self._map(dyn)
         b, x = np.zeros(d.shape2), np.zeros(d.shape2)
         self._map(lambda t: o.solve_rhs(t[0], t[1], s["etaN"], s["gU"], s["gV"], b, x))
@@ -149,5 +159,7 @@ class ChannelOracle:
             o.exch_xyz(s[n], d.Nr)
         if P["tempStepping"]:
             o.exch_xyz(s["theta"], d.Nr)
+        if P["saltStepping"]:
+            o.exch_xyz(s["salt"], d.Nr)
         self.it += 1
         return res

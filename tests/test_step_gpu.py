@@ -39,14 +39,25 @@ def rel(a, b):
     dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, OL=4, tempAdvScheme=7),
     dict(sNx=24, sNy=16, Nr=4, nSx=2, nSy=2, land_frac=0.2, OL=3, tempAdvScheme=77, gad_multidim_compressible=1, buoyancyLinear=1),
     dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, OL=3, tempAdvScheme=33, multiDimAdvection=0),
+    # SALT_INTEGRATE beside TEMP_INTEGRATE: its own scheme (multi-dimensional DST3), diffusivities, and sBeta in the EOS
+    dict(sNx=24, sNy=16, Nr=5, nSx=2, nSy=2, land_frac=0.2, OL=3, saltStepping=1, saltAdvScheme=33, diffKhS=5e2, diffKrS=2e-5,
+         buoyancyLinear=1, sBeta=7.4e-4, salt=True),
+    dict(sNx=40, sNy=24, Nr=6, land_frac=0.1, saltStepping=1, diffKhS=1e3, diffKrS=1e-5, buoyancyLinear=1, sBeta=7.4e-4,
+         ivdc_kappa=1.0, salt=True),
     # implicitViscosity: MOM_{U,V}_IMPLICIT_R on u*, v* after the explicit tendencies (flux form and vector invariant)
     dict(sNx=24, sNy=16, Nr=6, nSx=2, nSy=2, land_frac=0.2, implicitViscosity=1, viscAr=5e-2),
     dict(sNx=40, sNy=24, Nr=5, land_frac=0.1, implicitViscosity=1, viscAr=5e-2, vectorInvariantMomentum=1, buoyancyLinear=1),
 ], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat", "buoyancy-flat", "buoyancy-land", "buoyancy-ivdc",
         "vecinv-flat", "vecinv-land-tiles-buoyancy", "vecinv-absvort", "vecinv-generic", "multidim-os7mp",
-        "multidim-dst3-compressible-tiles", "dst3fl-1d", "implvisc-fluxform", "implvisc-vecinv"])
+        "multidim-dst3-compressible-tiles", "dst3fl-1d", "salt-dst3-tiles", "salt-c2-ivdc", "implvisc-fluxform", "implvisc-vecinv"])
 def test_forward_step_matches_oracle(cfg):
+    cfg = dict(cfg)
+    with_salt = cfg.pop("salt", False)
     g, P, s = make_channel(**cfg)
+    if with_salt:      # salinity: smooth stratification + noise, wet points only
+        rng = np.random.default_rng(77)
+        s["salt"] = (35.0 + np.linspace(-0.5, 0.5, g.d.Nr)[None, None, :, None, None] + 0.05 * rng.standard_normal(g.d.shape3)) * g.maskC
+        s["sRef"] = np.full(g.d.Nr, 35.0)
     co = ChannelOracle(g, P, s)
     m = Model(g, P, s, co.op)
     try:
@@ -56,7 +67,7 @@ def test_forward_step_matches_oracle(cfg):
             rg = m.step()
             assert abs(rg["numIters"] - ro["numIters"]) <= 1, it
             assert rg["firstResidual"] == pytest.approx(ro["firstResidual"], rel=1e-9), it
-            for n in ("uVel", "vVel", "wVel", "etaN") + (("theta",) if P["tempStepping"] else ()):
+            for n in ("uVel", "vVel", "wVel", "etaN") + (("theta",) if P["tempStepping"] else ()) + (("salt",) if with_salt else ()):
                 a, b = m.get(n), co.s[n]
                 assert rel(a[..., jj, ii], b[..., jj, ii]) < 1e-9, (it, n, "interior")
                 assert rel(a, b) < 1e-9, (it, n, "halo")
