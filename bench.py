@@ -120,7 +120,8 @@ def run_cuda(args, rank, world):
     for n in "hFacC hFacW hFacS recip_hFacC recip_hFacW recip_hFacS maskC maskW maskS".split():
         rt.fill_field(n, 1.0)
     rt.set_params(**{k: P[k] for k in LIB_PARAMS if k in P})
-    rt.set_params(deltaTtracer=P["deltaTtracer"], tempAdvScheme=2, tempVertAdvScheme=2, nIter0=0, profile=1)
+    rt.set_params(deltaTtracer=P["deltaTtracer"], tempAdvScheme=args.temp_adv_scheme, tempVertAdvScheme=args.temp_adv_scheme,
+                  nIter0=0, profile=1)
     if world > 1:
         from mitgcm_b200 import distributed
         distributed.setup(d)
@@ -261,7 +262,8 @@ def run_cuda(args, rank, world):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic doubly-periodic channel {NX}x{NY}x{NR} per GPU, FP64, flat bottom, "
                                f"c2 advection + harmonic viscosity, cg2dTargetResidual 1e-7"
-                               + (", MOM_VECINV dynamics" if args.momentum == "vecinv" else ""),
+                               + (", MOM_VECINV dynamics" if args.momentum == "vecinv" else "")
+                               + (f", tempAdvScheme {args.temp_adv_scheme}" if args.temp_adv_scheme != 2 else ""),
                    "process_grid": f"{nPx}x{nPy}", "l2_policy": "working set 30 GB per GPU >> 126 MB L2, no flush needed",
                    "cells_per_gpu": cells},
         "cg2d": {"iters_per_step": tot_iters / K, "iters_per_s": tot_iters / max(phase[3] * 1e-3, 1e-12),
@@ -347,6 +349,8 @@ def main():
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--nr", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--temp-adv-scheme", type=int, default=2,
+                    help="tempAdvScheme (33, 77, 7, ...: GAD_ADVECTION multi-dimensional advection; not the headline workload)")
     ap.add_argument("--momentum", default="fluxform", choices=["fluxform", "vecinv"],
                     help="vecinv: MOM_VECINV instead of MOM_FLUXFORM in the dynamics (not the headline workload)")
     args = ap.parse_args()

@@ -520,14 +520,15 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         if (multiDim && !gad_advection_tile(tg, o2 / ns, advS, vertS, 0, u + o3, v + o3,
                                             w + o3, th + o3, gTadv + o3, dTdev)) return false;
         c.launches++;
-        if (!multiDim && thermo_fast_ok(g, p) && !getenv("MITGCM_B200_THERMO_NOPIPE")) {
+        if (thermo_fast_ok(g, p) && !(getenv("MITGCM_B200_THERMO_NOPIPE") && !multiDim)) {
           static bool attrT = false;
           if (!attrT) {
             MG_CUDA(cudaFuncSetAttribute(thermo_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThermoPipeSmem)));
             attrT = true;
           }
           thermo_pipe_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ThermoPipeSmem), c.stream>>>(
-              tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr);
+              tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr,
+              multiDim ? gTadv + o3 : nullptr, abScheme ? 1 : 0);
         } else if (!multiDim && thermo_fast_ok(g, p))
           thermo_fast_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), 0, c.stream>>>(
               tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr);

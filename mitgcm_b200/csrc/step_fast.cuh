@@ -639,7 +639,9 @@ __device__ __forceinline__ void thermo_pipe_prefetch(ThermoPipeSmem &sm, int slo
 __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
     thermo_pipe_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
                        const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
-                       double *__restrict__ gtNm1, GadPar p, double abFac, const double *__restrict__ sfT) {
+                       double *__restrict__ gtNm1, GadPar p, double abFac, const double *__restrict__ sfT,
+                       const double *__restrict__ gT0, int doAB) {
+  // gT0: tendency to start from (GAD_ADVECTION's, with calcAdvection = F); doAB: AdamsBashforthGt
   extern __shared__ __align__(16) unsigned char thermo_pipe_smem[];
   ThermoPipeSmem &sm = *reinterpret_cast<ThermoPipeSmem *>(thermo_pipe_smem);
   __shared__ VertSmem vs;
@@ -687,7 +689,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
     // own-column loads first: one exposed memory latency per level
     const size_t s3 = s + ko;
     const double Tkm1 = k >= 2 ? theta[s3 - slab] : 0., mC = g.maskC[s3], mCm1 = k >= 2 ? g.maskC[s3 - slab] : 0.;
-    const double wK = w[s3], kapK = kapT[s3], rhC = g.recip_hFacC[s3], gtOld = gtNm1[s3];
+    const double wK = w[s3], kapK = kapT[s3], rhC = g.recip_hFacC[s3], gtOld = doAB ? gtNm1[s3] : 0.;
+    const double gTin = gT0 ? gT0[s3] : 0.;
     __pipeline_wait_prior(0);
     __syncthreads();             // level k has landed in slot rb; everybody is done with the previous level's tiles
 #pragma unroll
@@ -733,7 +736,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
         if (!p.implicitDiffusion) df = -kapK * maskUp * rA * vs.rdrC[k - 1] * (T00 - Tkm1) * p.rkSign;
         fvu = fvu + df;
       }
-      double gT = 0. - rhC * vs.rdrF[k - 1] * r_rA *
+      double gT = gTin - rhC * vs.rdrF[k - 1] * r_rA *
                            ((fz1 - fz0) + (fm1 - fm0) + (fVdn - fvu) * p.rkSign -
                             T00 * ((SM(uT, 1, 0) - SM(uT, 0, 0)) * advFac + (SM(vT, 0, 1) - SM(vT, 0, 0)) * advFac +
                                    (rTransKp1 - rTrans) * rAdvFac));
@@ -742,9 +745,11 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
         if (k == 1) gtForc = gtForc + sfT[g.s(i, j)] * vs.rdrF[0] * rhC;
         gT = gT + gtForc;
       }
-      const double ab = abFac * (gT - gtOld);
-      gtNm1[s3] = gT;
-      gT = gT + ab;
+      if (doAB) {
+        const double ab = abFac * (gT - gtOld);
+        gtNm1[s3] = gT;
+        gT = gT + ab;
+      }
       thetaNew[s3] = T00 + p.deltaT * gT;
       fVdn = fvu;
       rTransKp1 = rTrans;
@@ -756,7 +761,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
 
 
 inline bool thermo_fast_ok(const Geom &g, const GadPar &p) {
-  return p.advScheme == ADV_CENTERED_2ND && p.vertAdvScheme == ADV_CENTERED_2ND && p.diffK4 == 0. && !p.useDiffKr4 &&
+  // with calcAdvection = F (multi-dimensional advection done by GAD_ADVECTION) the scheme does not matter
+  return ((p.advScheme == ADV_CENTERED_2ND && p.vertAdvScheme == ADV_CENTERED_2ND) || !p.calcAdvection) && p.diffK4 == 0. && !p.useDiffKr4 &&
          g.OLx >= 2 && g.OLy >= 2 && g.Nr < FT_NRMAX && !getenv("MITGCM_B200_GENERIC_STEP");
 }
 

@@ -105,15 +105,17 @@ def test_vecinv_pipelined_kernel_is_bit_identical_to_the_generic_kernels(monkeyp
             assert np.array_equal(o[n], outs[0][n]), n
 
 
-def test_thermo_pipelined_kernel_is_bit_identical_to_the_staged_kernel(monkeypatch):
-    """thermo_pipe_kernel (cp.async ring) vs thermo_fast_kernel vs the generic thermo_kernel: same fields after 3 steps."""
+@pytest.mark.parametrize("scheme", [2, 33])
+def test_thermo_pipelined_kernel_is_bit_identical_to_the_staged_kernel(monkeypatch, scheme):
+    """thermo_pipe_kernel (cp.async ring) vs thermo_fast_kernel vs the generic thermo_kernel: same fields after 3 steps
+    (scheme 33: the diffusion step on top of GAD_ADVECTION's tendency, calcAdvection = F)."""
     outs = []
     for env in ({}, {"MITGCM_B200_THERMO_NOPIPE": "1"}, {"MITGCM_B200_GENERIC_STEP": "1"}):
         for k in ("MITGCM_B200_THERMO_NOPIPE", "MITGCM_B200_GENERIC_STEP"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        g, P, s = make_channel(sNx=48, sNy=40, Nr=6, nSx=2, nSy=1, land_frac=0.15, buoyancyLinear=1)
+        g, P, s = make_channel(sNx=48, sNy=40, Nr=6, nSx=2, nSy=1, land_frac=0.15, buoyancyLinear=1, OL=3, tempAdvScheme=scheme)
         co = ChannelOracle(g, P, s)
         m = Model(g, P, s, co.op)
         try:

@@ -144,16 +144,17 @@ def test_mom_vecinv_staged_path_matches_oracle(rt, case, monkeypatch):
 def test_resident_solid_body_cs_step_matches_the_golden():
     """solid-body.cs-32x32x1 stepped ENTIRELY on the device (mitgcm_b200_forward_step_ with
     MI_VECTORINVARIANTMOMENTUM on the exch2 tile graph, p coordinates: rkSign = -1, Bo_surf = 1/rhoConst).
-    The passive tracer of the experiment (salt, centred advection, Adams-Bashforth on the tendency) rides in
-    the library's tracer slot (theta; the buoyancy is decoupled).  25 steps against the golden output."""
+    The passive tracer of the experiment is salt (SALT_INTEGRATE: centred advection, Adams-Bashforth on the tendency);
+    theta is not stepped, as in the experiment.  25 steps against the golden output."""
     from mitgcm_b200.model import Model, ini_cg2d_tilegraph
     from oracle.baroclinic_gyre import mon_stats
     from oracle import solid_body_cs as sbc
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "solid-body.cs-32x32x1.json")))
     T, d, g, P, salt = sbc.setup()
     P = dict(P)
-    P.update(abEps=0.1, deltaTtracer=450.0, viscAr=0.0, tempStepping=1, tempAdvScheme=2, cg2dMaxIters=600, momForcing=1,
-             momDissip_In_AB=1, diffKhT=0.0, diffK4T=0.0, diffKrT=0.0, vectorInvariantMomentum=1)
+    P.update(abEps=0.1, deltaTtracer=450.0, viscAr=0.0, tempStepping=0, saltStepping=1, saltAdvScheme=2, cg2dMaxIters=600,
+             momForcing=1, momDissip_In_AB=1, diffKhT=0.0, diffK4T=0.0, diffKrT=0.0, diffKhS=0.0, diffK4S=0.0, diffKrS=0.0,
+             vectorInvariantMomentum=1)
     op = ini_cg2d_tilegraph(g, P, T)
     uVel, vVel, etaN = sbc.initial_state(T, d, g)
     sbc.eo.exch2_3d(T, salt[0], d.OLx)
@@ -162,7 +163,7 @@ def test_resident_solid_body_cs_step_matches_the_golden():
     for bi in range(1, d.nSx + 1):
         o.integrate_for_w(bi, 1, uVel, vVel, wVel)
     sbc.eo.exch2_3d(T, wVel[0], d.OLx)
-    state = dict(uVel=uVel, vVel=vVel, wVel=wVel, theta=salt, etaN=etaN, surfForcU=np.zeros(d.shape2),
+    state = dict(uVel=uVel, vVel=vVel, wVel=wVel, theta=np.zeros(d.shape3), salt=salt, etaN=etaN, surfForcU=np.zeros(d.shape2),
                  surfForcV=np.zeros(d.shape2))
     m = Model(g, P, state, op, device=0, topo=T)
     maskInC, maskInW, maskInS = g.maskC[:, :, 0], g.maskW[:, :, 0], g.maskS[:, :, 0]
@@ -175,7 +176,7 @@ def test_resident_solid_body_cs_step_matches_the_golden():
                       uvel=mon_stats(d, m.get("uVel"), g.hFacW, maskInW, g.rAw, g.drF),
                       vvel=mon_stats(d, m.get("vVel"), g.hFacS, maskInS, g.rAs, g.drF),
                       wvel=mon_stats(d, m.get("wVel"), g.maskC, maskInC, g.rA, g.drC[:1]),
-                      salt=mon_stats(d, m.get("theta"), g.hFacC, maskInC, g.rA, g.drF))
+                      salt=mon_stats(d, m.get("salt"), g.hFacC, maskInC, g.rA, g.drF))
             for f in ("eta", "uvel", "vvel", "wvel", "salt"):
                 for s in ("max", "min", "sd"):
                     assert st[f][s] == pytest.approx(float(gold[f"dynstat_{f}_{s}"][it + 1]), rel=1e-10, abs=1e-13), (it, f, s)
