@@ -573,7 +573,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
             vi_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ViPipeSmem),
                              c.stream>>>(tg, st, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
                                          abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr);
-          } else if (!getenv("MITGCM_B200_VI_NOTILE"))
+          } else if (!getenv("MITGCM_B200_VI_NOTILE") && !vp.highOrderVorticity && !vp.upwindVorticity)   // C4 reads j+2: past the patch
             dyn_kernel<2><<<dim3((g.sNx + 2 + 31) / 32, (g.sNy + 2 + 7) / 8), dim3(32, 8), 0, c.stream>>>(
                 tg, st, mp, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
                 q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr,

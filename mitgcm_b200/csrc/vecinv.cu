@@ -16,8 +16,9 @@ bool make_vi_par(ViPar &p) {
   p.selectVortScheme = q.I(MI_SELECTVORTSCHEME); p.useJamartMomAdv = q.I(MI_USEJAMARTMOMADV);
   p.upwindShear = q.I(MI_UPWINDSHEAR); p.selectKEscheme = q.I(MI_SELECTKESCHEME);
   p.harmonic = (p.m.viscAhD != 0. || p.m.viscAhZ != 0.) ? 1 : 0;
-  if (q.I(MI_HIGHORDERVORTICITY) || q.I(MI_UPWINDVORTICITY))
-    return fail(53, "mom_vecinv_b200_: highOrderVorticity / upwindVorticity (MOM_VI_*_CORIOLIS_C4) are not on the B200 path");
+  p.highOrderVorticity = q.I(MI_HIGHORDERVORTICITY); p.upwindVorticity = q.I(MI_UPWINDVORTICITY);
+  if ((p.highOrderVorticity || p.upwindVorticity) && p.selectVortScheme != 0 && p.selectVortScheme != 2)
+    return fail(53, "mom_vecinv_b200_: MOM_VI_*_CORIOLIS_C4 implements selectVortScheme 0 and 2 only");
   if (q.I(MI_MOMIMPLVERTADV)) return fail(53, "mom_vecinv_b200_: momImplVertAdv is not on the B200 path");
   if (p.selectVortScheme < 0 || p.selectVortScheme > 3) return fail(53, "mom_vecinv_b200_: selectVortScheme not implemented");
   if (p.m.selectCoriScheme < 0 || p.m.selectCoriScheme > 3) return fail(53, "mom_vecinv_b200_: invalid selectCoriScheme");

@@ -8,8 +8,7 @@
 // biharmonic viscosity: the slabs of one level stay in L2 between the launches.
 // Expression order follows the Fortran (-fmad=false): bit-identical to oracle/mom_oracle.c
 // (og_mom_vecinv), which is pinned to verification/solid-body.cs-32x32x1/results/output.txt.
-// Not on the B200 path (rejected by the entry point): highOrderVorticity / upwindVorticity
-// (MOM_VI_{U,V}_CORIOLIS_C4), momImplVertAdv, variable and strain-tension viscosity, Leith-QG,
+// Not on the B200 path (rejected by the entry point): momImplVertAdv, variable and strain-tension viscosity, Leith-QG,
 // NH Coriolis / metric terms, GGL90-Langmuir, r* and sigma coordinates, OBCS, shelf ice.
 #pragma once
 #include "mom.cuh"
@@ -19,6 +18,7 @@ namespace mg {
 struct ViPar {
   MomPar m;
   int useCoriolis, useAbsVorticity, selectVortScheme, useJamartMomAdv, upwindShear, selectKEscheme;
+  int highOrderVorticity, upwindVorticity;   // MOM_VI_{U,V}_CORIOLIS_C4 instead of MOM_VI_{U,V}_CORIOLIS
   int harmonic;             // useHarmonicVisc: viscAh != 0
   int csCorners, myFace;    // facet corners this tile owns (1 SW, 2 SE, 4 NE, 8 NW), facet number
   int iMin, iMax, jMin, jMax;
@@ -362,6 +362,68 @@ __device__ inline double vi_v_coriolis(const TileGrid &g, const F &f, const ViPa
   return r;
 }
 
+// MOM_VI_U_CORIOLIS_C4 / MOM_VI_V_CORIOLIS_C4 (mom_vi_{u,v}_coriolis_c4.F:60-215): 4th-order (fourthVort3) or upwind
+// interpolation of vort3r = r_hFacZ*omega3 along j (U) / i (V); selectVortScheme 0 and 2.  Defined on U: i = 1..sNx+1,
+// j = 1..sNy, V: i = 1..sNx, j = 1..sNy+1 (the caller keeps the array's previous content elsewhere).
+template <class F, class A>
+__device__ inline double vi_coriolis_c4(const TileGrid &g, const F &f, const ViPar &p, const A &a, bool absV, int isV, int k, int i, int j) {
+  const double oneSixth = 1. / 6., oneTwelve = 1. / 12.;
+  const int sNx = g.sNx, sNy = g.sNy;
+  auto base = [&](int ii, int jj) {
+    const double h = a.hFacZ(ii, jj);
+    return (h == 0. ? 0. : 1. / h) * (absV ? a.omega3(ii, jj) : a.vort3(ii, jj));
+  };
+  auto v3 = [&](int ii, int jj) {      // with the facet-corner averaging of the cube (highOrderVorticity only)
+    if (p.csCorners && p.highOrderVorticity) {
+      if (!isV) {
+        if ((p.csCorners & 1) && ii == 1 && jj == 0) return (base(1, 0) + base(2, 1)) * 0.5;
+        if ((p.csCorners & 2) && ii == sNx + 1 && jj == 0) return (base(sNx + 1, 0) + base(sNx, 1)) * 0.5;
+        if ((p.csCorners & 8) && ii == 1 && jj == sNy + 2) return (base(1, sNy + 2) + base(2, sNy + 1)) * 0.5;
+        if ((p.csCorners & 4) && ii == sNx + 1 && jj == sNy + 2) return (base(sNx + 1, sNy + 2) + base(sNx, sNy + 1)) * 0.5;
+      } else {
+        if ((p.csCorners & 1) && ii == 0 && jj == 1) return (base(0, 1) + base(1, 2)) * 0.5;
+        if ((p.csCorners & 2) && ii == sNx + 2 && jj == 1) return (base(sNx + 2, 1) + base(sNx + 1, 2)) * 0.5;
+        if ((p.csCorners & 8) && ii == 0 && jj == sNy + 1) return (base(0, sNy + 1) + base(1, sNy)) * 0.5;
+        if ((p.csCorners & 4) && ii == sNx + 2 && jj == sNy + 1) return (base(sNx + 2, sNy + 1) + base(sNx + 1, sNy)) * 0.5;
+      }
+    }
+    return base(ii, jj);
+  };
+  double bm, bp;
+  if (!isV) {
+    bm = f.v(i, j) * f.dxG(i, j) * f.hS(i, j) + f.v(i - 1, j) * f.dxG(i - 1, j) * f.hS(i - 1, j);
+    bp = f.v(i, j + 1) * f.dxG(i, j + 1) * f.hS(i, j + 1) + f.v(i - 1, j + 1) * f.dxG(i - 1, j + 1) * f.hS(i - 1, j + 1);
+  } else {
+    bm = f.u(i, j) * f.dyG(i, j) * f.hW(i, j) + f.u(i, j - 1) * f.dyG(i, j - 1) * f.hW(i, j - 1);
+    bp = f.u(i + 1, j) * f.dyG(i + 1, j) * f.hW(i + 1, j) + f.u(i + 1, j - 1) * f.dyG(i + 1, j - 1) * f.hW(i + 1, j - 1);
+  }
+  const int di = isV ? 1 : 0, dj = isV ? 0 : 1;
+  const double z0 = v3(i, j), z1 = v3(i + di, j + dj), zm = v3(i - di, j - dj), z2 = v3(i + 2 * di, j + 2 * dj);
+  const size_t s = g.s(i, j), s3 = g.s3(i, j, k);
+  const double rd = isV ? g.recip_dyC[s] : g.recip_dxC[s], mk = isV ? g.maskS[s3] : g.maskW[s3];
+  if (p.selectVortScheme == 0) {
+    const double bXY = 0.25 * (bm + bp);
+    double vort;
+    if (p.upwindVorticity) vort = bXY > 0. ? z0 : z1;
+    else {
+      const double Rjp = z2 - z1, Rjm = z0 - zm;
+      vort = 0.5 * ((z0 + z1) - oneTwelve * (Rjp - Rjm));
+    }
+    return isV ? -vort * bXY * rd * mk : vort * bXY * rd * mk;
+  }
+  const double bM = 0.5 * bm, bP = 0.5 * bp;
+  double vort;
+  if (p.upwindVorticity) vort = (bM + bP) > 0. ? bM * z0 : bP * z1;
+  else {
+    double Rjp = z2 - z1, Rjm = z0 - zm;
+    const double Rj = z1 - z0;
+    Rjp = z1 - oneSixth * (Rjp - Rj);
+    Rjm = z0 - oneSixth * (Rj - Rjm);
+    vort = 0.5 * (bM * Rjm + bP * Rjp);
+  }
+  return isV ? -vort * rd * mk : vort * rd * mk;
+}
+
 // MOM_VI_CORIOLIS (mom_vi_coriolis.F:48-190)
 template <class F>
 __device__ inline void vi_coriolis(const TileGrid &g, const F &f, int sch, int k, int i, int j, double &uCf, double &vCf) {
@@ -526,8 +588,16 @@ __device__ inline ViOut vi_cell(const TileGrid &g, const MomState &st, const F &
     }
   }
   if (m.momAdvection) {
+    if (p.highOrderVorticity || p.upwindVorticity) {
+      // mom_vecinv.F:746-757, :772-783: outside its own range the C4 routine leaves uCf / vCf as the Coriolis call left them
+      const bool inU = i >= 1 && i <= g.sNx + 1 && j >= 1 && j <= g.sNy, inV = i >= 1 && i <= g.sNx && j >= 1 && j <= g.sNy + 1;
+      const double staleU = tU, staleV = tV;
+      tU = tU + (inU ? vi_coriolis_c4(g, f, p, a, p.useAbsVorticity != 0, 0, k, i, j) : staleU);
+      tV = tV + (inV ? vi_coriolis_c4(g, f, p, a, p.useAbsVorticity != 0, 1, k, i, j) : staleV);
+    } else {
     tU = tU + vi_u_coriolis(g, f, p, a, p.useAbsVorticity != 0, k, i, j);
     tV = tV + vi_v_coriolis(g, f, p, a, p.useAbsVorticity != 0, k, i, j);
+    }
     tU = tU + vi_vertshear(g, st, p, 0, k, i, j);
     tV = tV + vi_vertshear(g, st, p, 1, k, i, j);
     const double ke = a.KE(i, j);

@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
 
 inline bool vi_fast_ok(const Geom &g, const ViPar &p) {
   return !p.m.useBiharmonicVisc && p.m.selectBotDragQuadr == -1 && p.selectVortScheme >= 0 && p.selectVortScheme <= 2 &&
+         !p.highOrderVorticity && !p.upwindVorticity &&
          (p.selectKEscheme == -1 || p.selectKEscheme == 0 || p.selectKEscheme == 2) && g.OLx >= 2 && g.OLy >= 2 &&
          g.Nr < FT_NRMAX && !getenv("MITGCM_B200_GENERIC_STEP") && !getenv("MITGCM_B200_VI_NOPIPE");
 }

@@ -25,7 +25,7 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "exactConserv buoyancyLinear doThetaClimRelax gravity tAlpha sBeta rhoNil rhoConst ivdc_kappa "
               "implicSurfPress implicDiv2DFlow rkSign vectorInvariantMomentum useCoriolis useAbsVorticity "
               "selectVortScheme selectKEscheme useJamartMomAdv upwindShear multiDimAdvection "
-              "gad_multidim_compressible saltStepping diffKhS diffK4S diffKrS").split()
+              "gad_multidim_compressible saltStepping diffKhS diffK4S diffKrS highOrderVorticity upwindVorticity").split()
 
 
 def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):

@@ -543,7 +543,7 @@ void og_mom_fluxform(const og_grid *g, const og_params *p, int bi, int bj, int k
 
 /* ======================================================================================
  * MOM_VECINV (pkg/mom_vecinv/mom_vecinv.F:10-1009) and its leaves.  Same scope limits as
- * above plus: highOrderVorticity / upwindVorticity (MOM_VI_{U,V}_CORIOLIS_C4), variable
+ * above plus: variable
  * viscosity, strain-tension viscosity, Leith-QG, GGL90-Langmuir, NH Coriolis / metric
  * terms and momImplVertAdv are not restated (the product rejects them).
  * Cubed sphere: csCorners is a bit mask of the tile's facet corners (1 SW, 2 SE, 4 NE,
@@ -828,6 +828,76 @@ static void mom_vi_v_coriolis(const og_grid *g, const og_params *p, int bi, int 
 #undef VDXH
 #undef UDYH
 
+/* MOM_VI_U_CORIOLIS_C4 / MOM_VI_V_CORIOLIS_C4 (pkg/mom_vecinv/mom_vi_{u,v}_coriolis_c4.F:60-215): 4th-order
+ * (fourthVort3 = .TRUE.) or upwind interpolation of the vorticity; selectVortScheme 0 and 2 only; written on
+ * U: i = 1..sNx+1, j = 1..sNy, V: i = 1..sNx, j = 1..sNy+1 -- elsewhere the output array keeps what it held. */
+static int mom_vi_coriolis_c4(const og_grid *g, const og_params *p, int bi, int bj, int k, int isV, const double *fld,
+                              const double *omega3, const double *r_hFacZ, double *cf, int csCorners) {
+  SETUP
+  const double oneSixth = 1. / 6., oneTwelve = 1. / 12.;
+  const int sch = p->selectVortScheme, upw = p->upwindVorticity;
+  if (sch != 0 && sch != 2) return 1;
+  double *v3 = (double *)calloc(px * py, sizeof(double));
+  FORALL v3[S(i, j)] = r_hFacZ[S(i, j)] * omega3[S(i, j)];
+  if (csCorners && p->highOrderVorticity) {
+    if (!isV) {
+      if (csCorners & 1) v3[S(1, 0)] = (v3[S(1, 0)] + v3[S(2, 1)]) * 0.5;
+      if (csCorners & 2) v3[S(sNx + 1, 0)] = (v3[S(sNx + 1, 0)] + v3[S(sNx, 1)]) * 0.5;
+      if (csCorners & 8) v3[S(1, sNy + 2)] = (v3[S(1, sNy + 2)] + v3[S(2, sNy + 1)]) * 0.5;
+      if (csCorners & 4) v3[S(sNx + 1, sNy + 2)] = (v3[S(sNx + 1, sNy + 2)] + v3[S(sNx, sNy + 1)]) * 0.5;
+    } else {
+      if (csCorners & 1) v3[S(0, 1)] = (v3[S(0, 1)] + v3[S(1, 2)]) * 0.5;
+      if (csCorners & 2) v3[S(sNx + 2, 1)] = (v3[S(sNx + 2, 1)] + v3[S(sNx + 1, 2)]) * 0.5;
+      if (csCorners & 8) v3[S(0, sNy + 1)] = (v3[S(0, sNy + 1)] + v3[S(1, sNy)]) * 0.5;
+      if (csCorners & 4) v3[S(sNx + 2, sNy + 1)] = (v3[S(sNx + 2, sNy + 1)] + v3[S(sNx + 1, sNy)]) * 0.5;
+    }
+  }
+  const int di = isV ? 1 : 0, dj = isV ? 0 : 1;          /* direction along which the vorticity is interpolated */
+  const int iHi = isV ? sNx : sNx + 1, jHi = isV ? sNy + 1 : sNy;
+  for (int j = 1; j <= jHi; j++)
+    for (int i = 1; i <= iHi; i++) {
+      double bm, bp;     /* transports on the two sides (vBarXm/p or uBarYm/p) */
+      if (!isV) {
+        bm = G3(fld, i, j, k) * G2(g->dxG, i, j) * G3(g->hFacS, i, j, k) + G3(fld, i - 1, j, k) * G2(g->dxG, i - 1, j) * G3(g->hFacS, i - 1, j, k);
+        bp = G3(fld, i, j + 1, k) * G2(g->dxG, i, j + 1) * G3(g->hFacS, i, j + 1, k)
+           + G3(fld, i - 1, j + 1, k) * G2(g->dxG, i - 1, j + 1) * G3(g->hFacS, i - 1, j + 1, k);
+      } else {
+        bm = G3(fld, i, j, k) * G2(g->dyG, i, j) * G3(g->hFacW, i, j, k) + G3(fld, i, j - 1, k) * G2(g->dyG, i, j - 1) * G3(g->hFacW, i, j - 1, k);
+        bp = G3(fld, i + 1, j, k) * G2(g->dyG, i + 1, j) * G3(g->hFacW, i + 1, j, k)
+           + G3(fld, i + 1, j - 1, k) * G2(g->dyG, i + 1, j - 1) * G3(g->hFacW, i + 1, j - 1, k);
+      }
+      const double z0 = v3[S(i, j)], z1 = v3[S(i + di, j + dj)], zm = v3[S(i - di, j - dj)], z2 = v3[S(i + 2 * di, j + 2 * dj)];
+      const double rd = isV ? G2(g->recip_dyC, i, j) : G2(g->recip_dxC, i, j);
+      const double mk = isV ? G3(g->maskS, i, j, k) : G3(g->maskW, i, j, k);
+      const double sgn = isV ? -1. : 1.;
+      if (sch == 0) {
+        const double bXY = 0.25 * (bm + bp);
+        double vort;
+        if (upw) vort = bXY > 0. ? z0 : z1;
+        else {
+          const double Rjp = z2 - z1, Rjm = z0 - zm;
+          vort = 0.5 * ((z0 + z1) - oneTwelve * (Rjp - Rjm));
+        }
+        cf[S(i, j)] = isV ? -vort * bXY * rd * mk : vort * bXY * rd * mk;
+      } else {
+        const double bM = 0.5 * bm, bP = 0.5 * bp;
+        double vort;
+        if (upw) vort = (bM + bP) > 0. ? bM * z0 : bP * z1;
+        else {
+          double Rjp = z2 - z1, Rjm = z0 - zm;
+          const double Rj = z1 - z0;
+          Rjp = z1 - oneSixth * (Rjp - Rj);
+          Rjm = z0 - oneSixth * (Rj - Rjm);
+          vort = 0.5 * (bM * Rjm + bP * Rjp);
+        }
+        cf[S(i, j)] = isV ? -vort * rd * mk : vort * rd * mk;
+      }
+      (void)sgn;
+    }
+  free(v3);
+  return 0;
+}
+
 /* MOM_VI_U_VERTSHEAR / MOM_VI_V_VERTSHEAR (pkg/mom_vecinv/mom_vi_{u,v}_vertshear.F:41-133) */
 static void mom_vi_vertshear(const og_grid *g, const og_params *p, int bi, int bj, int k, int isV,
                              const double *fld, const double *wVel, double *shear) {
@@ -870,7 +940,9 @@ int og_mom_vecinv(const og_grid *g, const og_params *p, int bi, int bj, int k,
                   const double *uVel, const double *vVel, const double *wVel,
                   double *gU, double *gV, int csCorners, int myFace) {
   SETUP
-  if (p->highOrderVorticity || p->upwindVorticity || p->momImplVertAdv) return 1;
+  if (p->momImplVertAdv) return 1;
+  const int c4 = p->highOrderVorticity || p->upwindVorticity;
+  if (c4 && p->selectVortScheme != 0 && p->selectVortScheme != 2) return 3;
   if (p->selectVortScheme < 0 || p->selectVortScheme > 3 || p->selectCoriScheme < 0 || p->selectCoriScheme > 3) return 2;
   const size_t ns = px * py;
   double *buf = (double *)calloc(ns * 19, sizeof(double));
@@ -976,10 +1048,12 @@ int og_mom_vecinv(const og_grid *g, const og_params *p, int bi, int bj, int k,
   /* :745-884 advection */
   if (p->momAdvection) {
     const double *w3 = p->useAbsVorticity ? omega3 : vort3;
-    mom_vi_u_coriolis(g, p, bi, bj, k, vFld, w3, hFacZ, r_hFacZ, uCf);
+    if (c4) mom_vi_coriolis_c4(g, p, bi, bj, k, 0, vVel, w3, r_hFacZ, uCf, csCorners);      /* :746-757 */
+    else mom_vi_u_coriolis(g, p, bi, bj, k, vFld, w3, hFacZ, r_hFacZ, uCf);
     for (int j = jMin; j <= jMax; j++)
       for (int i = iMin; i <= iMax; i++) G3(gU, i, j, k) = G3(gU, i, j, k) + uCf[S(i, j)];
-    mom_vi_v_coriolis(g, p, bi, bj, k, uFld, w3, hFacZ, r_hFacZ, vCf);
+    if (c4) mom_vi_coriolis_c4(g, p, bi, bj, k, 1, uVel, w3, r_hFacZ, vCf, csCorners);
+    else mom_vi_v_coriolis(g, p, bi, bj, k, uFld, w3, hFacZ, r_hFacZ, vCf);
     for (int j = jMin; j <= jMax; j++)
       for (int i = iMin; i <= iMax; i++) G3(gV, i, j, k) = G3(gV, i, j, k) + vCf[S(i, j)];
     mom_vi_vertshear(g, p, bi, bj, k, 0, uVel, wVel, uCf);

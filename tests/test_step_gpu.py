@@ -35,6 +35,7 @@ def rel(a, b):
     dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, vectorInvariantMomentum=1, useAbsVorticity=1, useJamartMomAdv=1, upwindShear=1,
          selectVortScheme=2, selectKEscheme=2, selectCoriScheme=3, no_slip_sides=0, no_slip_bottom=0, bottomDragLinear=1e-3),
     dict(sNx=32, sNy=24, Nr=5, land_frac=0.1, vectorInvariantMomentum=1, selectVortScheme=3, selectKEscheme=1, momDissip_In_AB=0),
+    dict(sNx=32, sNy=24, Nr=4, nSx=2, nSy=1, land_frac=0.1, vectorInvariantMomentum=1, selectVortScheme=2, highOrderVorticity=1),
     # non-AB advection schemes: GAD_ADVECTION (multi-dimensional, reference default) or the 1-D form, forward in time
     dict(sNx=40, sNy=36, Nr=6, land_frac=0.1, OL=4, tempAdvScheme=7),
     dict(sNx=24, sNy=16, Nr=4, nSx=2, nSy=2, land_frac=0.2, OL=3, tempAdvScheme=77, gad_multidim_compressible=1, buoyancyLinear=1),
@@ -48,7 +49,7 @@ def rel(a, b):
     dict(sNx=24, sNy=16, Nr=6, nSx=2, nSy=2, land_frac=0.2, implicitViscosity=1, viscAr=5e-2),
     dict(sNx=40, sNy=24, Nr=5, land_frac=0.1, implicitViscosity=1, viscAr=5e-2, vectorInvariantMomentum=1, buoyancyLinear=1),
 ], ids=["tiles-land", "barotropic", "dst3fl-biharm", "flat", "buoyancy-flat", "buoyancy-land", "buoyancy-ivdc",
-        "vecinv-flat", "vecinv-land-tiles-buoyancy", "vecinv-absvort", "vecinv-generic", "multidim-os7mp",
+        "vecinv-flat", "vecinv-land-tiles-buoyancy", "vecinv-absvort", "vecinv-generic", "vecinv-c4", "multidim-os7mp",
         "multidim-dst3-compressible-tiles", "dst3fl-1d", "salt-dst3-tiles", "salt-c2-ivdc", "implvisc-fluxform", "implvisc-vecinv"])
 def test_forward_step_matches_oracle(cfg):
     cfg = dict(cfg)

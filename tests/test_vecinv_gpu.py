@@ -49,6 +49,11 @@ VI_CASES = [
     dict(corners=15, face=2),
     dict(corners=6, face=4),
     dict(corners=9, face=6, viscAhD=400.0, viscAhZ=300.0),
+    # MOM_VI_{U,V}_CORIOLIS_C4: 4th-order / upwind interpolation of the vorticity
+    dict(highOrderVorticity=1, selectVortScheme=0),
+    dict(highOrderVorticity=1, selectVortScheme=2, useAbsVorticity=1, corners=15, face=2),
+    dict(upwindVorticity=1, selectVortScheme=2),
+    dict(upwindVorticity=1, selectVortScheme=0, corners=5, face=1, useCoriolis=0),
 ]
 
 
@@ -107,7 +112,7 @@ def test_mom_vecinv_rejects_unsupported_options(rt):
     with pytest.raises(rt.B200Error):          # range reaches the outermost halo ring
         rt.mom_vecinv(1, 1, 1, 1 - d.OLx, d.sNx + d.OLx, 0, 9, *args())
     rt.set_params(highOrderVorticity=1)
-    with pytest.raises(rt.B200Error):          # MOM_VI_U_CORIOLIS_C4
+    with pytest.raises(rt.B200Error):          # MOM_VI_U_CORIOLIS_C4 has no selectVortScheme = 1 (the default)
         rt.mom_vecinv(1, 1, 1, 0, 9, 0, 9, *args())
     rt.set_params(highOrderVorticity=0, selectVortScheme=4)
     with pytest.raises(rt.B200Error):
