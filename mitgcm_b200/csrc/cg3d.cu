@@ -12,7 +12,7 @@
 // Dot products: lane -> warp shuffle -> CTA -> ordered sum over CTAs (deterministic run to run; the order differs
 // from the reference's tile-ordered sum, as in CG2D).  Convergence is decided on the device.
 // Algorithmic bytes per cell per iteration: M 6, S 3, A 6 (+ neighbours from L1/L2), U 6 words = 21 words = 168 B.
-// First correct version: the four sweeps are not fused (S could ride on A by recomputing s at the 7 points).
+// The four sweeps are not fused yet (S could ride on A by recomputing s at the 7 points).
 // Single rank, select_rStar = 0 (no surface term), as the oracle.  -fmad=false, reference operation order.
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -110,7 +110,12 @@ __device__ __forceinline__ void push3(const Cg3dArgs &a, const Cell &c, double *
   if (c.j == a.sNy) put(t[2 * a.sNy + a.sNx + c.i - 1]);
 }
 
-__global__ void __launch_bounds__(C3_THREADS, 2) cg3d_kernel(Cg3dArgs a) {
+// Latency-bound streaming phases: occupancy is what counts (measured at 1024^2 x 50: 2 CTAs/SM 3955 us/iteration,
+// 3: 2928, 4: 2521, 6: 2266, 8 (32 registers, 80 B spilled): 2149).
+#ifndef C3_MINB
+#define C3_MINB 8
+#endif
+__global__ void __launch_bounds__(C3_THREADS, C3_MINB) cg3d_kernel(Cg3dArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[C3_WARPS + 1];
   const size_t tid = (size_t)blockIdx.x * C3_THREADS + threadIdx.x, nthr = (size_t)gridDim.x * C3_THREADS;
