@@ -84,8 +84,11 @@ struct MdUpd {
   int dirOut;                                        // corner fill applied to the field after the fluxes (ipass = 1), 0: none
 };
 
+#ifndef MD_MINB
+#define MD_MINB 16   // latency-bound point-wise kernels: full occupancy (32 registers) measured best: 32.0 -> 25.5 ms for the thermodynamics phase at 2048^2 x 50
+#endif
 template <int DIR>
-__global__ void __launch_bounds__(128) md_pass_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
+__global__ void __launch_bounds__(128, MD_MINB) md_pass_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
                                                       const double *__restrict__ tracer0, double *__restrict__ Tout,
                                                       double *__restrict__ Vout, int compressible, const double *dTLev,
                                                       MdUpd q) {
@@ -181,7 +184,7 @@ __global__ void md_implicit_kernel(TileGrid g, const double *__restrict__ T2, co
 
 // Vertical pass (gad_advection.F:886-1050): fVerT at the upper (k) and lower (k+1) interface of the
 // cell from the Y-updated field, then the tendency.
-__global__ void __launch_bounds__(128) md_vert_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ V2,
+__global__ void __launch_bounds__(128, MD_MINB) md_vert_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ V2,
                                                       const double *__restrict__ tracer0, double *__restrict__ gTracer,
                                                       int compressible, const double *dTLev) {
   const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
