@@ -174,7 +174,15 @@ momimpl_kernel(TileGrid g, const double *__restrict__ kapU, const double *__rest
 // rho == nullptr: the in-situ density anomaly is evaluated on the fly from theta (and salt when
 // sBeta != 0) with FIND_RHO_2D 'LINEAR' -- same expression as ocean_phys_kernel, so nothing but
 // theta is read when no other consumer of rhoInSitu (IVDC) is active: R{theta} W{phiHyd}.
-__global__ void __launch_bounds__(128, 8)
+#ifndef PHI_MINB
+#define PHI_MINB 8
+#endif
+#ifndef PHI_UNROLL
+#define PHI_UNROLL 5
+#endif
+#define PHI_DO_PRAGMA(x) _Pragma(#x)
+#define PHI_UNROLL_N(n) PHI_DO_PRAGMA(unroll n)
+__global__ void __launch_bounds__(128, PHI_MINB)
 phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restrict__ theta,
               const double *__restrict__ salt, const double *__restrict__ tRef, const double *__restrict__ sRef,
               EosLinear e, const double *__restrict__ rF, const double *__restrict__ rC,
@@ -184,7 +192,7 @@ phihyd_kernel(TileGrid g, const double *__restrict__ rho, const double *__restri
   if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
   const double dRho = e.rhoNil - e.rhoConst;
   double phiF = 0.;
-#pragma unroll 5
+  PHI_UNROLL_N(PHI_UNROLL)
   for (int k = 1; k <= g.Nr; k++) {
     const size_t s3 = g.s3(i, j, k);
     double dRlocM = 0.5 * g.drC[k - 1] * 1.;
