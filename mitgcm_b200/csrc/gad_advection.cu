@@ -220,6 +220,41 @@ __global__ void __launch_bounds__(128, MD_MINB) md_vert_kernel(TileGrid g, MdAcc
   }
 }
 
+// The same vertical pass as a column march: one thread per (i,j), k = 1..Nr.  The flux and transport of the lower
+// interface are carried to the next level as its upper interface (same leaf call, same deltaTLev: bit-identical to
+// md_vert_kernel), so every interface is evaluated once and the k-stencil re-reads hit L1 / L2 instead of DRAM
+// (ncu at 1024^2 x 50: the plane-parallel kernel moved 130 B/cell against 48 B/cell algorithmic).
+__global__ void __launch_bounds__(128, MD_MINB) md_vert_col_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ V2,
+                                                          const double *__restrict__ tracer0, double *__restrict__ gTracer,
+                                                          int compressible, const double *dTLev) {
+  const int i = 1 - g.OLx + blockIdx.x * 32 + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * 4 + threadIdx.y;
+  if (i > g.sNx + g.OLx || j > g.sNy + g.OLy) return;
+  const double recip_rA = g.recip_rA[g.s(i, j)];
+  double fUp = 0., rTrans = 0.;
+  for (int k = 1; k <= g.Nr; k++) {
+    const size_t s3 = g.s3(i, j, k);
+    const double dT = dTLev[k - 1];
+    double fDn = 0., rTransKp = 0.;
+    if (k < g.Nr) {
+      a.k = k + 1; p.k = k + 1; p.deltaT = dTLev[k];
+      rTransKp = a.rTrans(i, j);
+      fDn = gad_adv_r(g, a, p, i, j);
+    }
+    const double T2 = a.T_[s3];
+    if (compressible) {
+      const double tmpTrac = T2 * V2[s3] - dT * (fDn - fUp) * p.rkSign * 1.;
+      const double vol = V2[s3] - dT * (rTransKp - rTrans) * p.rkSign * 1.;
+      gTracer[s3] = (tmpTrac - tracer0[s3] * vol) * recip_rA * 1. * g.recip_drF[k - 1] * g.recip_hFacC[s3] * 1. / dT;
+    } else {
+      const double lt = T2 - dT * 1. * g.recip_hFacC[s3] * g.recip_drF[k - 1] * recip_rA * 1. *
+                                 (fDn - fUp - tracer0[s3] * (rTransKp - rTrans)) * p.rkSign * 1.;
+      gTracer[s3] = (lt - tracer0[s3]) / dT;
+    }
+    fUp = fDn; rTrans = rTransKp;
+  }
+}
+
 static bool md_scheme(int s) {
   return s == ADV_UPWIND_1RST || s == ADV_DST2 || s == ADV_FLUX_LIMIT || s == ADV_DST3 || s == ADV_DST3_FLUX_LIMIT ||
          s == ADV_OS7MP;
@@ -307,7 +342,8 @@ bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme,
   a.T_ = Tin; a.dirIn = 0;
   c.launches++;
   if (implicitAdvection) md_implicit_kernel<<<grd, blk, 0, c.stream>>>(tg, Tin, tr, gT, dT);
-  else md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, gT, compressible, dT);
+  else if (getenv("MITGCM_B200_MD_VERT_PLANE")) md_vert_kernel<<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, gT, compressible, dT);
+  else md_vert_col_kernel<<<dim3(grd.x, grd.y, 1), blk, 0, c.stream>>>(tg, a, p, Vin, tr, gT, compressible, dT);
   if (cudaGetLastError() != cudaSuccess) return fail(5, "gad_advection: launch failed");
   return true;
 }
