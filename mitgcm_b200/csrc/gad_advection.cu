@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(128, MD_MINB) md_pass_kernel(TileGrid g, MdAcc
   a.k = k; p.k = k; p.deltaT = dTLev[k - 1];
   const size_t s3 = g.s3(i, j, k);
   double T = a.TA(i, j, k);
-  double V = Vin ? Vin[s3] : g.rA[g.s(i, j)] * 1. * 1. * g.drF[k - 1] * g.hFacC[s3] + (1. - g.maskC[s3]);
+  // the local volume is carried only by the GAD_MULTIDIM_COMPRESSIBLE form; the default form never reads it
+  double V = 0.;
+  if (compressible) V = Vin ? Vin[s3] : g.rA[g.s(i, j)] * 1. * 1. * g.drF[k - 1] * g.hFacC[s3] + (1. - g.maskC[s3]);
   // update range of this pass (gad_advection.F:471-600 for X, :692-812 for Y)
   bool upd;
   if (DIR == 0) {
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(128, MD_MINB) md_pass_kernel(TileGrid g, MdAcc
     if (cs_corner_src(g, a.corners, q.dirOut, i, j, ii, jj)) T = a.T_[g.s3(ii, jj, k)];
   }
   Tout[s3] = T;
-  if (Vout) Vout[s3] = V;
+  if (compressible) Vout[s3] = V;
 }
 
 // FILL_CS_CORNER_UV_RS (eesupp/src/fill_cs_corner_uv_rs.F:46-108, withSigns = .FALSE.) on copies of maskW, maskS of
