@@ -142,6 +142,83 @@ __global__ void __launch_bounds__(128, MD_MINB) md_pass_kernel(TileGrid g, MdAcc
   if (compressible) Vout[s3] = V;
 }
 
+// The same pass with every face flux and transport evaluated once: the thread of cell (i,j) evaluates the face it owns
+// (west face for DIR 0, south face for DIR 1) and takes the far face from its neighbour -- by warp shuffle along x
+// (warps overlap by one cell: 31 cells per 32 lanes, so no lane evaluates a second face), through shared memory
+// along y (7 cell rows per 8 thread rows).  Same leaf, same arguments: bit-identical to md_pass_kernel.
+#define MDS_ROWS 8
+template <int DIR>
+__global__ void __launch_bounds__(32 * MDS_ROWS, 64 / MDS_ROWS) md_pass_share_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
+                                                      const double *__restrict__ tracer0, double *__restrict__ Tout,
+                                                      double *__restrict__ Vout, int compressible, const double *dTLev,
+                                                      MdUpd q) {
+  __shared__ double sAf[DIR == 1 ? MDS_ROWS : 1][32], sTr[DIR == 1 ? MDS_ROWS : 1][32];
+  const int i = 1 - g.OLx + blockIdx.x * (DIR == 0 ? 31 : 32) + threadIdx.x;
+  const int j = 1 - g.OLy + blockIdx.y * (DIR == 1 ? MDS_ROWS - 1 : MDS_ROWS) + threadIdx.y;
+  const int k = 1 + blockIdx.z;
+  const bool inb = i <= g.sNx + g.OLx && j <= g.sNy + g.OLy;
+  // the last lane (DIR 0) / thread row (DIR 1) only supplies its face to the neighbour; its cell belongs to the next block
+  const bool owner = inb && (DIR == 0 ? threadIdx.x < 31 : threadIdx.y < MDS_ROWS - 1);
+  a.k = k; p.k = k; p.deltaT = dTLev[k - 1];
+  // cells this pass updates (as md_pass_kernel), split into the part along the sweep and the part across it
+  bool along, across;
+  if (DIR == 0) {
+    if (q.overlapOnly) {
+      const int iLo = q.W ? 1 : 2 - g.OLx, iHi = q.E ? g.sNx : g.sNx + g.OLx - 1;
+      along = i >= iLo && i <= iHi; across = (q.S && j <= 0) || (q.N && j >= g.sNy + 1);
+    } else {
+      const int jLo = (q.interiorOnly && q.S) ? 1 : 1 - g.OLy, jHi = (q.interiorOnly && q.N) ? g.sNy : g.sNy + g.OLy;
+      across = j >= jLo && j <= jHi; along = i >= 2 - g.OLx && i <= g.sNx + g.OLx - 1;
+    }
+  } else {
+    if (q.overlapOnly) {
+      const int jLo = q.S ? 1 : 2 - g.OLy, jHi = q.N ? g.sNy : g.sNy + g.OLy - 1;
+      along = j >= jLo && j <= jHi; across = (q.W && i <= 0) || (q.E && i >= g.sNx + 1);
+    } else {
+      const int iLo = (q.interiorOnly && q.W) ? 1 : 1 - g.OLx, iHi = (q.interiorOnly && q.E) ? g.sNx : g.sNx + g.OLx;
+      across = i >= iLo && i <= iHi; along = j >= 2 - g.OLy && j <= g.sNy + g.OLy - 1;
+    }
+  }
+  const bool upd = along && across;
+  // own face: needed by this cell or by the previous one along the sweep; faces 2-OL .. sN+OL are the ones any update reads
+  const int c = DIR == 0 ? i : j, cHi = DIR == 0 ? g.sNx + g.OLx : g.sNy + g.OLy, OL = DIR == 0 ? g.OLx : g.OLy;
+  double af0 = 0., tr0 = 0.;
+  if (inb && across && c >= 2 - OL && c <= cHi) {
+    af0 = gad_adv_h(g, a, p, DIR, i, j);
+    tr0 = DIR == 0 ? a.uTrans(i, j) : a.vTrans(i, j);
+  }
+  double af1, tr1;
+  if (DIR == 0) {
+    af1 = __shfl_down_sync(0xffffffffu, af0, 1);
+    tr1 = __shfl_down_sync(0xffffffffu, tr0, 1);
+  } else {
+    sAf[threadIdx.y][threadIdx.x] = af0; sTr[threadIdx.y][threadIdx.x] = tr0;
+    __syncthreads();
+    const int ty = min((int)threadIdx.y + 1, MDS_ROWS - 1);
+    af1 = sAf[ty][threadIdx.x]; tr1 = sTr[ty][threadIdx.x];
+  }
+  if (!owner) return;
+  const size_t s3 = g.s3(i, j, k);
+  double T = a.TA(i, j, k);
+  double V = 0.;
+  if (compressible) V = Vin ? Vin[s3] : g.rA[g.s(i, j)] * 1. * 1. * g.drF[k - 1] * g.hFacC[s3] + (1. - g.maskC[s3]);
+  if (upd) {
+    if (compressible) {
+      const double tmpTrac = T * V - p.deltaT * (af1 - af0) * 1.;
+      V = V - p.deltaT * (tr1 - tr0) * 1.;
+      T = tmpTrac / V;
+    } else {
+      T = T - p.deltaT * 1. * g.recip_hFacC[s3] * g.recip_drF[k - 1] * g.recip_rA[g.s(i, j)] * 1. *
+                  (af1 - af0 - tracer0[s3] * (tr1 - tr0)) * 1.;
+    }
+  } else if (q.dirOut) {
+    int ii, jj;
+    if (cs_corner_src(g, a.corners, q.dirOut, i, j, ii, jj)) T = a.T_[g.s3(ii, jj, k)];
+  }
+  Tout[s3] = T;
+  if (compressible) Vout[s3] = V;
+}
+
 // FILL_CS_CORNER_UV_RS (eesupp/src/fill_cs_corner_uv_rs.F:46-108, withSigns = .FALSE.) on copies of maskW, maskS of
 // one tile (gad_advection.F:329-334); every source is a non-corner cell, so the fill is a pure gather.
 __global__ void md_mask_kernel(TileGrid g, int corners, double *__restrict__ mW, double *__restrict__ mS) {
@@ -310,6 +387,7 @@ bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme,
   const double *Tin = tr, *Vin = nullptr;
   int cur = 0;
   const int npass = cube ? 3 : 2;
+  const bool noShare = getenv("MITGCM_B200_MD_NOSHARE") != nullptr;      // per-cell evaluation of both faces (md_pass_kernel)
   for (int ipass = 1; ipass <= npass; ipass++) {
     MdUpd q{};
     bool fluxX, fluxY;
@@ -335,8 +413,16 @@ bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme,
       a.dirIn = q.overlapOnly ? (dir == 0 ? 1 : 2) : 0;
       q.dirOut = (q.overlapOnly && ipass == 1) ? (dir == 0 ? 2 : 1) : 0;
       c.launches++;
-      if (dir == 0) md_pass_kernel<0><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
-      else md_pass_kernel<1><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+      if (noShare) {
+        if (dir == 0) md_pass_kernel<0><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+        else md_pass_kernel<1><<<grd, blk, 0, c.stream>>>(tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+      } else {
+        const dim3 sblk(32, MDS_ROWS);
+        if (dir == 0) md_pass_share_kernel<0><<<dim3((g.PX + 30) / 31, (g.PY + MDS_ROWS - 1) / MDS_ROWS, g.Nr), sblk, 0, c.stream>>>(
+            tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+        else md_pass_share_kernel<1><<<dim3((g.PX + 31) / 32, (g.PY + MDS_ROWS - 2) / (MDS_ROWS - 1), g.Nr), sblk, 0, c.stream>>>(
+            tg, a, p, Vin, tr, Tb[cur], Vb[cur], compressible, dT, q);
+      }
       Tin = Tb[cur]; Vin = Vb[cur];
       cur ^= 1;
     }
