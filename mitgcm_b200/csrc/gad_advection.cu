@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(128, MD_MINB) md_pass_kernel(TileGrid g, MdAcc
 // (west face for DIR 0, south face for DIR 1) and takes the far face from its neighbour -- by warp shuffle along x
 // (warps overlap by one cell: 31 cells per 32 lanes, so no lane evaluates a second face), through shared memory
 // along y (7 cell rows per 8 thread rows).  Same leaf, same arguments: bit-identical to md_pass_kernel.
-#define MDS_ROWS 8
+#ifndef MDS_ROWS
+#define MDS_ROWS 8      // 16 measured the same (thermodynamics phase 16.79 vs 16.76 ms at 2048^2 x 50)
+#endif
 template <int DIR>
 __global__ void __launch_bounds__(32 * MDS_ROWS, 64 / MDS_ROWS) md_pass_share_kernel(TileGrid g, MdAcc a, GadPar p, const double *__restrict__ Vin,
                                                       const double *__restrict__ tracer0, double *__restrict__ Tout,
