@@ -90,7 +90,10 @@ void mitgcm_b200_set_param_d_(const int *id, const double *val, int *ierr);
 void mitgcm_b200_set_param_i_(const int *id, const int *val, int *ierr);
 
 /* device mirrors: host -> device (creates the mirror on first use), device -> host,
- * and the raw device address (for callers that keep state resident). */
+ * and the raw device address (for callers that keep state resident).  The address of a mirror is stable except
+ * for MG_THETA / MG_THETA2 and MG_SALT / MG_SALT2: CYCLE_TRACER (model/src/cycle_tracer.F) is a pointer swap,
+ * so these four addresses are INVALIDATED by mitgcm_b200_forward_step_ / _step_part_ -- query them again after
+ * every step (tests/test_step_gpu.py::test_theta_field_ptr_after_steps). */
 void mitgcm_b200_set_field_(const int *id, const double *host, int *ierr);
 void mitgcm_b200_get_field_(const int *id, double *host, int *ierr);
 double *mitgcm_b200_field_ptr(int id);
@@ -257,14 +260,26 @@ void mitgcm_b200_exch2_uv_map_(
     const int *maxEntries, int *nEntries, int *out4, int *ierr);
 
 /* ---- multi-GPU (one process per GPU on one NVSwitch domain) --------------------------------
- * CG2D: every rank exports its solver workspace as a CUDA IPC handle (64 bytes) and, after the
- * handles of all ranks have been gathered, maps its peers.  Edge values are then stored directly
- * into the neighbour's halo cells and dot products are combined through peer-mapped mailboxes
- * inside the persistent kernel (replaces EXCH_S3D_RL + GLOBAL_SUM_TILE_RL; no MPI, no host round
- * trips).  rank = myPx + nPx*myPy (MPI_CART_CREATE order, eesupp/src/ini_procs.F:145). */
-void mitgcm_b200_comm_handle_(unsigned char *handle64, int *ierr);
-void mitgcm_b200_comm_connect_(const int *nRanks, const int *myRank, const unsigned char *handles, int *ierr);
-/* Per-step halo exchange pieces for EXCH_XY_RL / EXCH_XYZ_RL over NCCL send/recv: pack the strip
+ * With nPx*nPy > 1 every rank keeps what its neighbours write into -- the exchanged state fields (uVel, vVel,
+ * wVel, theta, salt, cg2d_x, etaN, etaH) and the CG2D workspace -- in one allocation, the peer arena, exports it
+ * as a CUDA IPC handle (64 bytes + the 8-byte offset of the arena inside its allocation = 72 bytes) and, after
+ * the handles of all ranks have been gathered (MPI_Allgather in the Fortran model, torch.distributed here), maps
+ * its peers.  From then on
+ *   - CG2D stores edge values directly into the neighbour's halo cells and combines dot products through
+ *     peer-mapped mailboxes inside the persistent kernel (replaces EXCH_S3D_RL + GLOBAL_SUM_TILE_RL);
+ *   - mitgcm_b200_halo_exchange_ fills the full-width halos (with corners) of several mirrors at once by storing
+ *     edge strips and corner blocks into the 8 neighbours' halos over NVLink, ordered by peer-memory flags
+ *     (replaces EXCH_XY_RL / EXCH_XYZ_RL, eesupp/src/exch1_rx.template:170-201): no MPI, no host round trips;
+ *   - mitgcm_b200_forward_step_ runs across ranks, theta's halo travelling on a side stream under DYNAMICS.
+ * rank = myPx + nPx*myPy (MPI_CART_CREATE order, eesupp/src/ini_procs.F:145).  The caller barriers between
+ * connect and the first exchange. */
+void mitgcm_b200_comm_handle_(unsigned char *handle72, int *ierr);
+void mitgcm_b200_comm_connect_(const int *nRanks, const int *myRank, const unsigned char *handles72, int *ierr);
+void mitgcm_b200_halo_exchange_(const int *nFields, const int *ids, int *ierr);
+/* Unmaps the peers' arenas.  Shut-down order across ranks: disconnect on every rank, barrier, then
+ * mitgcm_b200_finalize_ (which frees the arena the peers had mapped). */
+void mitgcm_b200_comm_disconnect_(void);
+/* The same exchanges over NCCL send/recv (alternative transport, mitgcm_b200/distributed.py): pack the strip
  * to send towards dir (0 W, 1 E, 2 S, 3 N) into buf, or (unpack != 0) scatter a received strip
  * into the halo on side dir; exch_dir does one periodic direction locally (nPx or nPy == 1). */
 void mitgcm_b200_pack_(const int *id, const int *dir, double *buf, const int *unpack, int *ierr);

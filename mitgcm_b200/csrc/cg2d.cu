@@ -94,9 +94,8 @@ void cg2d_free_workspace() {
   Ctx &c = ctx();
   if (!c.cg2d) return;
   Cg2dWs *w = c.cg2d;
-  for (int r = 0; r < w->nRanks; r++)
-    if (r != w->myRank && w->peerBase[r]) cudaIpcCloseMemHandle(w->peerBase[r]);
-  for (double *p : {w->block, w->partials, w->resid})
+  // the peers' blocks are part of their arenas, which halo_free() unmaps; a block carved from my own arena goes with it
+  for (double *p : {in_arena(w->block) ? nullptr : w->block, w->partials, w->resid})
     if (p) cudaFree(p);
   if (w->out) cudaFree(w->out);
   delete w;
@@ -183,7 +182,11 @@ __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N]
 // several ranks, CTA 0 then exchanges the rank totals through the peer-mapped mailboxes
 // (replaces the MPI_Allreduce of global_sum_tile.F:182) and publishes the rank-ordered sum.
 // rseq counts reductions; it is uniform across all threads of all ranks.
+// (zeroed by the host before every launch; a rank that times out reports error 71 and the caller must re-connect)
 __device__ int g_cg2d_spin_error = 0;
+#ifndef CG2D_SPIN_LIMIT
+#define CG2D_SPIN_LIMIT (1LL << 31)
+#endif
 
 template <int N, bool MAXOP>
 __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N], double *sm, unsigned long long &rseq) {
@@ -218,7 +221,7 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
         Mail *mm = a.mail[a.myRank] + (size_t)r * 2 + par;
         long long spins = 0;
         while (*reinterpret_cast<volatile unsigned long long *>(&mm->seq) != rseq) {
-          if (++spins > (1LL << 31)) { g_cg2d_spin_error = 1; break; }
+          if (++spins > CG2D_SPIN_LIMIT) { g_cg2d_spin_error = 1; break; }
         }
         __threadfence_system();
         for (int k = 0; k < N; k++) sm[CG_WARPS + r * 3 + k] = *reinterpret_cast<volatile double *>(&mm->val[k]);
@@ -240,7 +243,7 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
     if (threadIdx.x == 0) {
       long long spins = 0;
       while (*reinterpret_cast<volatile unsigned long long *>(a.gflag) < rseq) {
-        if (++spins > (1LL << 31)) break;
+        if (++spins > 2 * CG2D_SPIN_LIMIT) { g_cg2d_spin_error = 2; break; }   // CTA 0 gives up first and still publishes
       }
     }
     __syncthreads();
@@ -713,7 +716,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     a.out->numIters = actualIts;
     a.out->nIterMin = nIterMin;
     a.out->seq = rseq;
-    a.out->error = g_cg2d_spin_error;
+    a.out->error = *reinterpret_cast<volatile int *>(&g_cg2d_spin_error);
   }
 }
 
@@ -1084,7 +1087,7 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
     a.out->numIters = it2d;
     a.out->nIterMin = nIterMin;
     a.out->seq = rseq;
-    a.out->error = g_cg2d_spin_error;
+    a.out->error = *reinterpret_cast<volatile int *>(&g_cg2d_spin_error);
   }
 }
 
@@ -1093,13 +1096,28 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
 static bool ensure_ws(int maxIters) {
   Ctx &c = ctx();
   if (!c.cg2d) {
-    Cg2dWs *w = new Cg2dWs();
-    c.cg2d = w;
+    // published in c.cg2d only when complete: a failed allocation must not leave a half-built workspace behind
+    struct Guard {
+      Cg2dWs *w;
+      ~Guard() {
+        if (!w) return;
+        for (double *p : {in_arena(w->block) ? nullptr : w->block, w->partials})
+          if (p) cudaFree(p);
+        if (w->out) cudaFree(w->out);
+        delete w;
+      }
+    } guard{new Cg2dWs()};
+    Cg2dWs *w = guard.w;
     const size_t n2 = c.g.n2;
     const size_t mailBytes = sizeof(Mail) * 8 * 2, totBytes = sizeof(double) * 8, flagBytes = 64;
     w->blockBytes = 9 * n2 * sizeof(double) + mailBytes + totBytes + flagBytes;
-    MG_CUDA(cudaMalloc(&w->block, w->blockBytes));
-    MG_CUDA(cudaMemset(w->block, 0, w->blockBytes));
+    // multi-rank: the block is part of the peer arena (zero-filled), which the neighbours map once (halo.cu)
+    w->block = static_cast<double *>(arena_alloc(w->blockBytes));
+    if (c.arena && !w->block) return fail(3, "cg2d: peer arena exhausted");
+    if (!w->block) {
+      MG_CUDA(cudaMalloc(&w->block, w->blockBytes));
+      MG_CUDA(cudaMemset(w->block, 0, w->blockBytes));
+    }
     double *p = w->block;
     for (double **q : {&w->r[0], &w->r[1], &w->s[0], &w->s[1], &w->q, &w->z, &w->v, &w->xmin, &w->xw}) { *q = p; p += n2; }
     w->mail = reinterpret_cast<Mail *>(p);
@@ -1113,6 +1131,8 @@ static bool ensure_ws(int maxIters) {
     w->maxBlocks = nb * c.numSMs;
     MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg2d_sr_kernel, CG_THREADS, 0));
     w->maxBlocksSR = nb * c.numSMs;
+    c.cg2d = w;
+    guard.w = nullptr;
   }
   Cg2dWs *w = c.cg2d;
   if (w->residCap < maxIters) {
@@ -1124,37 +1144,23 @@ static bool ensure_ws(int maxIters) {
 }
 
 // ---- multi-GPU wiring (one process per GPU, all on one NVSwitch domain) ------------------------
-// Every rank exports its workspace block as a CUDA IPC handle; after the handles have been
-// all-gathered (torch.distributed, see mitgcm_b200/distributed.py) each rank maps its peers'
-// blocks.  Edge pushes then store straight into the neighbour's halo cells and the dot products
-// are combined through the mailboxes -- EXCH_S3D_RL and GLOBAL_SUM_TILE_RL without MPI.
-bool cg2d_comm_handle(unsigned char *handle64) {
-  if (!ctx().ready) return fail(30, "mitgcm_b200_init_ not called");
-  if (!ensure_ws(1)) return false;
-  cudaIpcMemHandle_t h;
-  MG_CUDA(cudaIpcGetMemHandle(&h, ctx().cg2d->block));
-  static_assert(sizeof(h) == 64, "IPC handle size");
-  memcpy(handle64, &h, 64);
-  return true;
-}
-
-bool cg2d_comm_connect(int nRanks, int myRank, const unsigned char *handles) {
+// The workspace block lives in the rank's peer arena, which every rank exports as ONE CUDA IPC handle and maps
+// from its peers (halo.cu: mitgcm_b200_comm_handle_ / _connect_).  Edge pushes then store straight into the
+// neighbour's halo cells and the dot products are combined through the mailboxes -- EXCH_S3D_RL and
+// GLOBAL_SUM_TILE_RL without MPI.  Called by halo.cu once the peers' arenas are mapped.
+bool cg2d_comm_wire() {
   Ctx &c = ctx();
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   if (!ensure_ws(1)) return false;
   const Geom &g = c.g;
-  if (nRanks != g.nPx * g.nPy || nRanks > 8) return fail(70, "comm_connect: nRanks must equal nPx*nPy (<= 8)");
+  const int nRanks = c.nRanks, myRank = c.myRank;
+  if (nRanks > 8) return fail(70, "comm_connect: at most 8 ranks");
   if (g.nTiles != 1) return fail(70, "comm_connect: multi-rank runs use one tile per rank (nSx = nSy = 1)");
-  if (myRank != g.myPx + g.nPx * g.myPy) return fail(70, "comm_connect: rank must be myPx + nPx*myPy");
-  if (g.n2 >= (1u << 28)) return fail(70, "comm_connect: tile2d array too large for the push encoding");
   Cg2dWs *w = c.cg2d;
+  if (!in_arena(w->block)) return fail(70, "comm_connect: the CG2D workspace is not in the peer arena");
   w->nRanks = nRanks; w->myRank = myRank;
-  for (int r = 0; r < nRanks; r++) {
-    if (r == myRank) { w->peerBase[r] = w->block; continue; }
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handles + 64 * (size_t)r, 64);
-    MG_CUDA(cudaIpcOpenMemHandle(&w->peerBase[r], h, cudaIpcMemLazyEnablePeerAccess));
-  }
+  const size_t off = reinterpret_cast<char *>(w->block) - c.arena;
+  for (int r = 0; r < nRanks; r++) w->peerBase[r] = c.peerArena[r] + off;
   auto rk = [&](int px, int py) { return ((px % g.nPx) + g.nPx) % g.nPx + g.nPx * (((py % g.nPy) + g.nPy) % g.nPy); };
   w->nbrRank[0] = myRank;
   w->nbrRank[1] = rk(g.myPx - 1, g.myPy); w->nbrRank[2] = rk(g.myPx + 1, g.myPy);
@@ -1168,6 +1174,10 @@ bool cg2d_comm_connect(int nRanks, int myRank, const unsigned char *handles) {
     if (w->nbrRank[slot] != myRank) t[n] = (t[n] & 0x0FFFFFFF) | (slot << 28);
   }
   MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
+  // a fresh connection starts the reduction sequence over on every rank (also the recovery path after error 71)
+  w->seq = 0;
+  MG_CUDA(cudaMemset(w->mail, 0, sizeof(Mail) * 8 * 2));
+  MG_CUDA(cudaMemset(w->gflag, 0, 64));
   return true;
 }
 
@@ -1249,6 +1259,8 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   // zero-initialised work arrays incl. ring 0 / sN+1 (cg2d.F:142-147)
   size_t bytes = g.n2 * sizeof(double);
   for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->v}) MG_CUDA(cudaMemsetAsync(p, 0, bytes, c.stream));
+  static const int zero = 0;
+  MG_CUDA(cudaMemcpyToSymbolAsync(g_cg2d_spin_error, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, c.stream));
   void *args[] = {&a};
   c.launches++;
   MG_CUDA(cudaLaunchCooperativeKernel(sr ? (void *)cg2d_sr_kernel : (void *)cg2d_kernel, dim3(blocks), dim3(CG_THREADS),
@@ -1288,16 +1300,6 @@ void cg2d_sr_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double
   (void)myThid;
   mg::ctx().lastError = 0;
   mg::cg2d_run(true, cg2d_b, cg2d_x, firstResidual, minResidualSq, lastResidual, numIters, nIterMin);
-}
-
-void mitgcm_b200_comm_handle_(unsigned char *handle64, int *ierr) {
-  mg::ctx().lastError = 0;
-  *ierr = mg::cg2d_comm_handle(handle64) ? 0 : 1;
-}
-
-void mitgcm_b200_comm_connect_(const int *nRanks, const int *myRank, const unsigned char *handles, int *ierr) {
-  mg::ctx().lastError = 0;
-  *ierr = mg::cg2d_comm_connect(*nRanks, *myRank, handles) ? 0 : 1;
 }
 
 void mitgcm_b200_cg2d_stats_(double *sumRHS, double *rhsMax) {

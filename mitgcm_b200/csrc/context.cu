@@ -24,6 +24,18 @@ size_t field_elems(const Geom &g, int id) {
   return 0;
 }
 
+// DO_FIELDS_BLOCKING_EXCHANGES / SOLVE_FOR_PRESSURE exchange these (do_fields_blocking_exchanges.F:54-66,
+// solve_for_pressure.F:316); theta2 / salt2 because CYCLE_TRACER swaps the mirrors.
+static bool is_exchanged_field(int id) {
+  switch (id) {
+    case MG_UVEL: case MG_VVEL: case MG_WVEL: case MG_THETA: case MG_THETA2: case MG_SALT: case MG_SALT2:
+    case MG_CG2D_X: case MG_ETAN: case MG_ETAH:
+      return true;
+    default:
+      return false;
+  }
+}
+
 double *field(int id, bool create) {
   Ctx &c = g_ctx;
   auto it = c.fields.find(id);
@@ -32,10 +44,23 @@ double *field(int id, bool create) {
   size_t n = field_elems(c.g, id);
   if (n == 0) { fail(2, "unknown field id " + std::to_string(id)); return nullptr; }
   double *p = nullptr;
-  if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { fail(3, "cudaMalloc failed for field"); return nullptr; }
-  cudaMemsetAsync(p, 0, n * sizeof(double), c.stream);
+  // fields whose halos the neighbouring ranks fill live in the peer arena (zero-filled at creation)
+  if (c.arena && is_exchanged_field(id)) p = static_cast<double *>(arena_alloc(n * sizeof(double)));
+  if (!p) {
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { fail(3, "cudaMalloc failed for field"); return nullptr; }
+    cudaMemsetAsync(p, 0, n * sizeof(double), c.stream);
+  }
   c.fields[id] = p;
   return p;
+}
+
+void *arena_alloc(size_t bytes) {
+  Ctx &c = g_ctx;
+  if (!c.arena) return nullptr;
+  size_t off = (c.arenaUsed + 255) & ~(size_t)255;
+  if (off + bytes > c.arenaBytes) return nullptr;
+  c.arenaUsed = off + bytes;
+  return c.arena + off;
 }
 
 bool is_device_ptr(const void *p) {
@@ -122,7 +147,9 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   }
   g.PX = g.sNx + 2 * g.OLx; g.PY = g.sNy + 2 * g.OLy; g.nTiles = g.nSx * g.nSy;
   g.slab = (size_t)g.PX * g.PY; g.n2 = g.slab * g.nTiles; g.n3 = g.n2 * g.Nr;
-  if (g.n2 >= (size_t)1 << 31) { fail(10, "tile2d array exceeds 2^31 elements"); return; }
+  // the width-1 push tables (cg2d.cu, cg3d.cu, exch2.cu) keep the flat halo index in 28 bits next to the peer slot
+  if (g.n2 >= (size_t)1 << 28) { fail(10, "tile2d array exceeds 2^28 elements (push-table index range)"); return; }
+  if (g.nPx < 1 || g.nPy < 1 || g.myPx < 0 || g.myPx >= g.nPx || g.myPy < 0 || g.myPy >= g.nPy) { fail(10, "bad process grid"); return; }
   int dev = *device;
   if (dev < 0) {
     const char *lr = getenv("LOCAL_RANK");
@@ -133,8 +160,12 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
     fail(11, "no CUDA device: libmitgcm_b200 has no CPU fallback");
     return;
   }
-  if (cudaSetDevice(dev % ndev) != cudaSuccess) { fail(11, "cudaSetDevice failed"); return; }
-  c.device = dev % ndev;
+  if (dev >= ndev) {      // never wrap: two ranks on one GPU cannot co-run their spin-waiting cooperative kernels
+    fail(11, "device ordinal " + std::to_string(dev) + " out of range (" + std::to_string(ndev) + " visible)");
+    return;
+  }
+  if (cudaSetDevice(dev) != cudaSuccess) { fail(11, "cudaSetDevice failed"); return; }
+  c.device = dev;
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, c.device);
   c.numSMs = prop.multiProcessorCount;
@@ -154,6 +185,17 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.p.i[MI_MULTIDIMADVECTION - 100] = 1;
   c.p.i[MI_SALTADVSCHEME - 100] = 2; c.p.i[MI_SALTVERTADVSCHEME - 100] = 2;
   if (!build_push_tables()) return;
+  c.nRanks = g.nPx * g.nPy;
+  c.myRank = g.myPx + g.nPx * g.myPy;
+  c.attrDyn = c.attrThermo = c.attrVi = false;
+  if (c.nRanks > 1) {
+    // peer arena: header (flags) + 7 tile3d + 3 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
+    c.arenaBytes = 65536 + (7 * g.n3 + 3 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256;
+    if (cudaMalloc(&c.arena, c.arenaBytes) != cudaSuccess) { c.arena = nullptr; fail(3, "cudaMalloc failed for the peer arena"); return; }
+    if (cudaMemset(c.arena, 0, c.arenaBytes) != cudaSuccess) { fail(3, "peer arena memset"); return; }
+    c.arenaUsed = 4096;      // header: exchange flags (halo.cu)
+    c.peerArena[c.myRank] = c.arena;
+  }
   c.ready = true;
   *ierr = 0;
 }
@@ -162,7 +204,8 @@ void mitgcm_b200_finalize_(void) {
   Ctx &c = ctx();
   if (!c.ready) return;
   cudaStreamSynchronize(c.stream);
-  for (auto &f : c.fields) cudaFree(f.second);
+  for (auto &f : c.fields)
+    if (!in_arena(f.second)) cudaFree(f.second);
   c.fields.clear();
   for (auto &s : c.stage) cudaFree(s.second.first);
   c.stage.clear();
@@ -179,6 +222,12 @@ void mitgcm_b200_finalize_(void) {
     c.e2UvCount[w] = 0;
   }
   cg2d_free_workspace();
+  halo_free();               // unmaps the peers' arenas
+  if (c.arena) cudaFree(c.arena);
+  c.arena = nullptr;
+  c.arenaBytes = c.arenaUsed = 0;
+  for (auto &pa : c.peerArena) pa = nullptr;
+  c.nRanks = 1; c.myRank = 0;
   for (auto &e : c.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto &e : c.pev) if (e) { cudaEventDestroy(e); e = nullptr; }
   c.launches = 0;

@@ -51,6 +51,16 @@ struct Ctx {
   int e2UvCount[2] = {0, 0};
   // cubed sphere: facet corners each local tile owns (1 SW, 2 SE, 4 NE, 8 NW) and its facet number
   std::vector<int> csCorners, csFace, csEdges;    // csEdges: 1 N | 2 S | 4 E | 8 W facet edges the tile touches
+  // Peer arena (multi-rank runs only): ONE allocation per rank that holds everything the neighbouring GPUs
+  // write into -- the exchanged state fields (halo pushes), the CG2D workspace block (edge pushes, mailboxes) and
+  // the exchange flags -- so one CUDA IPC mapping per peer serves all of it (halo.cu).
+  char *arena = nullptr;
+  size_t arenaBytes = 0, arenaUsed = 0;
+  char *peerArena[8] = {};          // every rank's arena as mapped here (own arena for my rank)
+  int nRanks = 1, myRank = 0;
+  struct HaloWs *halo = nullptr;
+  // function attributes (dynamic shared memory opt-in) are per device: set once per init
+  bool attrDyn = false, attrThermo = false, attrVi = false;
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;
@@ -82,6 +92,16 @@ bool exch2_active();                                   // a pkg/exch2 topology h
 bool exch2_field(double *f, int nz);                   // EXCH2_3D_RX as one gather
 bool exch2_uv_field(double *u, double *v, int nz, bool withSigns);   // EXCH2_UV_3D_RX as one gather
 bool exch_field(double *f, int nz);
+void *arena_alloc(size_t bytes);                       // from the peer arena (zero-filled); nullptr when there is none / full
+inline bool in_arena(const void *p) {
+  const Ctx &c = ctx();
+  return c.arena && (const char *)p >= c.arena && (const char *)p < c.arena + c.arenaBytes;
+}
+bool halo_connected();                                 // halo.cu: peers mapped, exchanges go through peer pushes
+bool halo_exchange(const int *ids, int n, bool sideStream = false);   // EXCH_XY(Z)_RL of several mirrors across ranks
+bool halo_join();                                      // main stream waits for a side-stream exchange
+void halo_free();
+bool halo_check_error();
 void cg3d_free_workspace();                            // cg3d.cu                    // EXCH_XY(Z)_RL on a mirror (step.cu)
 
 }  // namespace mg

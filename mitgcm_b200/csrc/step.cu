@@ -394,7 +394,7 @@ static dim3 col_block() {
 // part 1: etaN = recip_Bo * cg2d_x (after the halo update of cg2d_x), MOMENTUM_CORRECTION_STEP, INTEGR_CONTINUITY
 // The halo exchanges between and after the parts are done by the caller: locally (one rank) or
 // over NCCL (mitgcm_b200/distributed.py).
-static bool step_part(int part, int myIter, double *initRes, int *iters, double *lastRes) {
+static bool step_part(int part, int myIter, double *initRes, int *iters, double *lastRes, bool peerHalo = false) {
   Ctx &c = ctx();
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   const Geom &g = c.g;
@@ -521,10 +521,9 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                             w + o3, th + o3, gTadv + o3, dTdev)) return false;
         c.launches++;
         if (thermo_fast_ok(g, p) && !(getenv("MITGCM_B200_THERMO_NOPIPE") && !multiDim)) {
-          static bool attrT = false;
-          if (!attrT) {
+          if (!c.attrThermo) {      // per device / context: reset by mitgcm_b200_init_
             MG_CUDA(cudaFuncSetAttribute(thermo_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThermoPipeSmem)));
-            attrT = true;
+            c.attrThermo = true;
           }
           thermo_pipe_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ThermoPipeSmem), c.stream>>>(
               tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr,
@@ -549,6 +548,14 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                            q.D(MP_DIFFKHT), q.D(MP_DIFFK4T), sfT)) return false;
   if (q.I(MI_SALTSTEPPING) && !step_tracer(MG_SALT, MG_SALT2, MG_GSNM1, MG_KAPPARS, q.I(MI_SALTADVSCHEME), q.I(MI_SALTVERTADVSCHEME),
                                            q.D(MP_DIFFKHS), q.D(MP_DIFFK4S), nullptr)) return false;
+  // multi-rank, peer pushes: the new theta / salt halos travel on the side stream while DYNAMICS and CG2D run
+  // (the NCCL path of mitgcm_b200/distributed.py exchanges them at the end of the step instead)
+  if (peerHalo) {
+    int ids[2], n = 0;
+    if (q.I(MI_TEMPSTEPPING)) ids[n++] = MG_THETA;
+    if (q.I(MI_SALTSTEPPING)) ids[n++] = MG_SALT;
+    if (n && !halo_exchange(ids, n, !getenv("MITGCM_B200_HALO_NOOVERLAP"))) return false;
+  }
   mark(1);
   // DYNAMICS
   {
@@ -565,10 +572,9 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
           vp.csCorners = c.csCorners.empty() ? 0 : c.csCorners[t];
           vp.myFace = c.csFace.empty() ? 0 : c.csFace[t];
           if (!semiImpl && vi_fast_ok(g, vp)) {
-            static bool attrV = false;
-            if (!attrV) {
+            if (!c.attrVi) {
               MG_CUDA(cudaFuncSetAttribute(vi_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViPipeSmem)));
-              attrV = true;
+              c.attrVi = true;
             }
             vi_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ViPipeSmem),
                              c.stream>>>(tg, st, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
@@ -585,10 +591,9 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                                       q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
                                                       1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
         } else if (!semiImpl && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
-          static bool attr = false;
-          if (!attr) {
-            cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem));
-            attr = true;
+          if (!c.attrDyn) {
+            MG_CUDA(cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem)));
+            c.attrDyn = true;
           }
           dyn_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(DynPipeSmem),
                             c.stream>>>(tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
@@ -696,16 +701,32 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   const Geom &g = c.g;
   const Params &q = c.p;
-  if (g.nPx * g.nPy > 1) return fail(62, "forward_step: multi-rank runs step through mitgcm_b200_step_part_ + NCCL exchanges");
-  if (!step_part(0, myIter, initRes, iters, lastRes)) return false;
-  if (!exch_field(field(MG_CG2D_X), 1)) return false;
-  if (!step_part(1, myIter, initRes, iters, lastRes)) return false;
+  const bool multi = g.nPx * g.nPy > 1;
+  if (multi && !halo_connected())
+    return fail(62, "forward_step: multi-rank runs need mitgcm_b200_comm_connect_ (or step through mitgcm_b200_step_part_ + NCCL exchanges)");
   const bool prof = q.I(MI_PROFILE) != 0;
   auto mark = [&](int n) {
     if (!prof) return;
     if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
     cudaEventRecord(c.pev[n], c.stream);
   };
+  if (multi) {
+    // Across ranks every exchange is a set of peer pushes on the stream (halo.cu).  theta (and salt) are final once
+    // THERMODYNAMICS has run, so their halos travel on the side stream while DYNAMICS and the solver run:
+    // step_part(0) calls halo_exchange(..., side) right after the tracer kernels (see there).
+    if (!step_part(0, myIter, initRes, iters, lastRes, true)) return false;
+    const int idx = MG_CG2D_X;
+    if (!halo_exchange(&idx, 1)) return false;
+    if (!step_part(1, myIter, initRes, iters, lastRes, true)) return false;
+    int ids[3] = {MG_UVEL, MG_VVEL, MG_WVEL};
+    if (!halo_exchange(ids, 3)) return false;
+    if (!halo_join()) return false;
+    mark(7);
+    return true;
+  }
+  if (!step_part(0, myIter, initRes, iters, lastRes)) return false;
+  if (!exch_field(field(MG_CG2D_X), 1)) return false;
+  if (!step_part(1, myIter, initRes, iters, lastRes)) return false;
   if (q.I(MI_EXACTCONSERV) && !etah_update()) return false;
   // DO_FIELDS_BLOCKING_EXCHANGES: EXCH_UV_XYZ_RL(uVel, vVel, .TRUE.) -- on an exch2 tile graph the vector
   // exchange swaps / negates components across rotated facet edges -- then the scalars

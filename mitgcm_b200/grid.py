@@ -107,9 +107,12 @@ class Grid:
 
 
 def cartesian_grid(d: Dims, delX, delY, delR, xgOrigin=0.0, ygOrigin=0.0,
-                   f0=1e-4, beta=1e-11, gBaro=9.81) -> Grid:
+                   f0=1e-4, beta=1e-11, gBaro=9.81, fsin=None) -> Grid:
     """usingCartesianGrid: INI_CARTESIAN_GRID + INI_CORI(selectCoriMap=1) +
-    INI_LINEAR_PHISURF.  delX/delY are the global spacings (length Nx/Ny)."""
+    INI_LINEAR_PHISURF.  delX/delY are the global spacings (length Nx/Ny).
+    fsin = (amplitude, period in m): f = f0 + amplitude * sin(2 pi y / period) instead of the beta plane -- what a
+    selectCoriMap = 3 run reads from fCoriC / fCoriG files (ini_cori.F:119-178); periodic in y, so a doubly
+    periodic domain has no jump of f across its seam."""
     delX = np.asarray(delX, dtype=np.float64)
     delY = np.asarray(delY, dtype=np.float64)
     delR = np.asarray(delR, dtype=np.float64)
@@ -166,8 +169,13 @@ def cartesian_grid(d: Dims, delX, delY, delR, xgOrigin=0.0, ygOrigin=0.0,
             g.a["rAs"][bj, bi] = dxF * g.a["dyC"][bj, bi]
             g.a["rAz"][bj, bi] = g.a["dxV"][bj, bi] * g.a["dyU"][bj, bi]
     g.a["xC"], g.a["yC"], g.a["xG"], g.a["yG"] = xC, yC, xG, yG
-    g.a["fCori"] = f0 + beta * yC * 1.0
-    g.a["fCoriG"] = f0 + beta * yG * 1.0
+    if fsin is None:
+        g.a["fCori"] = f0 + beta * yC * 1.0
+        g.a["fCoriG"] = f0 + beta * yG * 1.0
+    else:
+        amp, period = fsin
+        g.a["fCori"] = f0 + amp * np.sin(2.0 * np.pi * yC / period)
+        g.a["fCoriG"] = f0 + amp * np.sin(2.0 * np.pi * yG / period)
     g.a["Bo_surf"] = np.full(d.shape2, gBaro)
     g.a["recip_Bo"] = np.full(d.shape2, 1.0 / gBaro)
     g.a["cosFacU"] = np.ones((d.nSy, d.nSx, d.PY))

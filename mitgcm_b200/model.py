@@ -28,22 +28,30 @@ LIB_PARAMS = ("deltaTMom deltaTFreeSurf abEps viscAhD viscAhZ viscA4D viscA4Z si
               "gad_multidim_compressible saltStepping diffKhS diffK4S diffKrS highOrderVorticity upwindVorticity").split()
 
 
-def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
+def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0, period=None, tTop=20.0, tBot=2.0, tNoise=0.1):
     """Initial state and forcing of the synthetic channel: smooth multi-mode
     flow of 0.1 m/s + noise, theta = tRef(k) + 0.1 N(0,1), eta = 0.1 sin cos, zonal wind stress
-    -tau0 cos(2 pi y / Ly).  Generated per global index, so any tiling sees the same field."""
+    -tau0 cos(2 pi y / Ly).  Generated per global index, so any tiling sees the same field.
+    period = (cells in x, cells in y) of the smooth part (default: the global domain); the weak-scaled
+    bench keeps it at one per-GPU block and repeats the noise too, so the domain at N ranks is the exact
+    periodic tiling of the one-block problem: same flow, same CG2D iteration counts at every rank count."""
     d = g.d
     rng = np.random.default_rng(seed)
     Nx, Ny, Nr = d.Nx, d.Ny, d.Nr
-    X = (np.arange(Nx) + 0.5) / Nx
-    Y = (np.arange(Ny) + 0.5) / Ny
+    perx, pery = period or (Nx, Ny)
+    X = (np.arange(Nx) + 0.5) / perx
+    Y = (np.arange(Ny) + 0.5) / pery
     YY, XX = np.meshgrid(Y, X, indexing="ij")
     psi_u = 0.1 * np.sin(2 * np.pi * XX) * np.cos(4 * np.pi * YY) + 0.03 * np.cos(6 * np.pi * XX) * np.sin(2 * np.pi * YY)
     psi_v = 0.1 * np.cos(2 * np.pi * XX) * np.sin(4 * np.pi * YY) - 0.03 * np.sin(6 * np.pi * XX) * np.cos(2 * np.pi * YY)
+    def noise():
+        if period and Nx % perx == 0 and Ny % pery == 0:      # the same noise on every block: an exact periodic tiling
+            return np.tile(rng.standard_normal((Nr, pery, perx)), (1, Ny // pery, Nx // perx))
+        return rng.standard_normal((Nr, Ny, Nx))
     glob = {
-        "uVel": psi_u[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * rng.standard_normal((Nr, Ny, Nx)),
-        "vVel": psi_v[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * rng.standard_normal((Nr, Ny, Nx)),
-        "theta": np.linspace(20.0, 2.0, Nr)[:, None, None] + 0.1 * rng.standard_normal((Nr, Ny, Nx)),
+        "uVel": psi_u[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * noise(),
+        "vVel": psi_v[None] * np.linspace(1.0, 0.2, Nr)[:, None, None] + 1e-3 * noise(),
+        "theta": np.linspace(tTop, tBot, Nr)[:, None, None] + tNoise * noise(),
     }
     eta = 0.1 * np.sin(2 * np.pi * XX) * np.cos(2 * np.pi * YY)
     tau = -tau0 * np.cos(2 * np.pi * YY)
@@ -63,14 +71,21 @@ def channel_state(g: Grid, seed=20261018, tau0=0.1, rhoConst=1000.0):
     s["etaN"] = tile(eta) * g.maskC[:, :, 0]
     s["surfForcU"] = tile(tau) * (1.0 / rhoConst)
     s["surfForcV"] = np.zeros(d.shape2)
-    s["tRef"] = np.linspace(20.0, 2.0, Nr)       # reference profile of the linear equation of state
+    s["tRef"] = np.linspace(tTop, tBot, Nr)       # reference profile of the linear equation of state
     s["sRef"] = np.zeros(Nr)
     return s
 
 
-def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=0.0, seed=20261018, **params):
+BENCH_FSIN_AMP = 6.5e-5      # bench workload: f = 1e-4 + 6.5e-5 sin(2 pi y / block length): max f dt = 0.198
+
+
+def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=0.0, seed=20261018, block=None,
+                 **params):
+    """block = (cells in x, cells in y): the bench workload -- Coriolis parameter and smooth initial flow periodic
+    over one block (the per-GPU domain of the weak-scaled run); default: beta plane over the whole domain."""
     d = Dims(sNx=sNx, sNy=sNy, OLx=OL, OLy=OL, nSx=nSx, nSy=nSy, Nr=Nr)
-    g = cartesian_grid(d, [dx] * d.Nx, [dx] * d.Ny, [dz] * Nr, f0=1e-4, beta=1e-11, gBaro=9.81)
+    g = cartesian_grid(d, [dx] * d.Nx, [dx] * d.Ny, [dz] * Nr, f0=1e-4, beta=1e-11, gBaro=9.81,
+                       fsin=(BENCH_FSIN_AMP, block[1] * dx) if block else None)
     rng = np.random.default_rng(seed + 1)
     depth = -dz * Nr * np.ones((d.Ny, d.Nx))
     if land_frac > 0:
@@ -83,7 +98,8 @@ def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=
     P = dict(DEFAULTS)
     P.update(params)
     P["globalArea"] = global_area(g)
-    return g, P, channel_state(g, seed)
+    strat = {k: P.pop(k) for k in ("tTop", "tBot", "tNoise") if k in P}
+    return g, P, channel_state(g, seed, period=block, **strat)
 
 
 class Model:

@@ -58,7 +58,9 @@ def test_fixed_iterations_match_oracle(rt, case, sr):
         assert rg["rhsMax"] == ro["rhsMax"]
         assert rg["firstResidual"] == pytest.approx(ro["firstResidual"], rel=1e-13)
         assert rg["sumRHS"] == pytest.approx(ro["sumRHS"], rel=1e-9, abs=1e-12 * np.abs(bo).sum())
-        assert relerr(xg[:, :, jj, ii], xo[:, :, jj, ii]) < 1e-11 * max(1, nit)
+        # north-star tolerance (1e-12 on fields) where rounding has not been amplified by the recurrences yet;
+        # later iterates differ by the conditioning of the Krylov recurrences (dot products are summed in another order)
+        assert relerr(xg[:, :, jj, ii], xo[:, :, jj, ii]) < (1e-12 if nit <= 2 else 1e-11 * nit)
         assert rg["lastResidual"] == pytest.approx(ro["lastResidual"], rel=1e-9)
         nh = len(ro["hist"])
         np.testing.assert_allclose(rg["hist"][:nh], ro["hist"], rtol=1e-9)

@@ -75,9 +75,50 @@ def test_forward_step_matches_oracle(cfg):
             if it == 0:   # before CG2D feeds back: tendencies are point-wise identical
                 a, b = m.get("gU"), co.s["gU"]
                 sl = (Ellipsis, slice(g.d.OLy - 1, g.d.OLy + g.d.sNy + 1), slice(g.d.OLx - 1, g.d.OLx + g.d.sNx + 1))
-                assert rel(a[sl], b[sl]) < 1e-14
+                assert np.array_equal(a[sl], b[sl]), rel(a[sl], b[sl])      # point-wise code: bit-identical by design
                 if P["tempStepping"] and P.get("tempAdvScheme", 2) in (2, 3, 4):
-                    assert rel(m.get("gtNm1")[..., jj, ii], co.s["gtNm1"][..., jj, ii]) < 1e-14
+                    assert np.array_equal(m.get("gtNm1")[..., jj, ii], co.s["gtNm1"][..., jj, ii])
+                # after one solve the fields carry the solver's summation-order noise only: north-star tolerance
+                for n in ("uVel", "vVel", "etaN") + (("theta",) if P["tempStepping"] else ()):
+                    assert rel(m.get(n)[..., jj, ii], co.s[n][..., jj, ii]) < 1e-12, (n, "step 0")
+    finally:
+        m.close()
+
+
+def test_theta_field_ptr_after_steps():
+    """include/mitgcm_b200.h: CYCLE_TRACER is a pointer swap, so the device address of MG_THETA alternates between
+    two buffers and must be queried again after every step; the freshly queried address holds the current theta,
+    the one held from the step before holds the previous theta."""
+    import torch
+    from mitgcm_b200 import _lib, runtime as rt
+    g, P, s = make_channel(sNx=32, sNy=24, Nr=5, land_frac=0.1)
+    co = ChannelOracle(g, P, s)
+    m = Model(g, P, s, co.op)
+
+    def read_raw(ptr, n):          # what a resident caller does with the address: a device-to-device copy
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        from cuda.bindings import runtime as cudart
+        err, = cudart.cudaMemcpy(out.data_ptr(), ptr, n * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        assert err == cudart.cudaError_t.cudaSuccess, err
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+    try:
+        L = _lib.lib()
+        n3 = int(np.prod(g.d.shape3))
+        seen, prev_theta = [], m.get("theta")
+        for it in range(3):
+            held = L.mitgcm_b200_field_ptr(rt.field_id("theta"))
+            m.step()
+            rt.sync()
+            p = L.mitgcm_b200_field_ptr(rt.field_id("theta"))
+            seen.append(p)
+            cur = m.get("theta")
+            assert np.array_equal(read_raw(p, n3).reshape(g.d.shape3), cur)
+            jj, ii = g.d.interior()
+            assert np.array_equal(read_raw(held, n3).reshape(g.d.shape3)[..., jj, ii], prev_theta[..., jj, ii])
+            assert not np.array_equal(cur, prev_theta)
+            prev_theta = cur
+        assert seen[0] != seen[1] and seen[0] == seen[2], "theta / theta2 alternate with every step"
     finally:
         m.close()
 
