@@ -227,20 +227,34 @@ def run_cuda(args, rank, world):
         """max |u|, |v|, |eta| and finiteness over ALL ranks."""
         buf3 = torch.empty((NR, d.PY, d.PX), device=dev, dtype=torch.float64)
         buf2 = torch.empty((d.PY, d.PX), device=dev, dtype=torch.float64)
-        v = []
+        v, mism = [], torch.zeros((), device=dev, dtype=torch.float64)
+        oy, ox = d.OLy, d.OLx
         for n in ("uVel", "vVel", "theta", "etaN"):
             b = buf2 if n == "etaN" else buf3
-            rt.get_field(n, b)
+            rt.get_field(n, b)           # copy on the library's stream (synchronised); the reduction runs on torch's
             v.append(b.abs().max() if n != "theta" else (b - 5.0).abs().max())
+            if not strong:
+                # weak scaling: every block holds the same data bit for bit (same arithmetic on the same numbers, the
+                # rank-ordered global sums are identical everywhere), so a correct exchange -- whatever the transport
+                # and the rank count -- leaves in my halo exactly my own opposite edge
+                w = torch.maximum((b[..., oy:oy + NY, :ox] - b[..., oy:oy + NY, NX:NX + ox]).abs().max(),
+                                  (b[..., oy:oy + NY, ox + NX:] - b[..., oy:oy + NY, ox:2 * ox]).abs().max())
+                w = torch.maximum(w, (b[..., :oy, ox:ox + NX] - b[..., NY:NY + oy, ox:ox + NX]).abs().max())
+                w = torch.maximum(w, (b[..., oy + NY:, ox:ox + NX] - b[..., oy:2 * oy, ox:ox + NX]).abs().max())
+                w = torch.maximum(w, (b[..., :oy, :ox] - b[..., NY:NY + oy, NX:NX + ox]).abs().max())          # SW corner
+                w = torch.maximum(w, (b[..., oy + NY:, ox + NX:] - b[..., oy:2 * oy, ox:2 * ox]).abs().max())  # NE corner
+                mism = torch.maximum(mism, torch.nan_to_num(w, nan=1e300))
+            torch.cuda.synchronize()     # ... and must finish before the buffer is overwritten by the next field
         t = torch.stack(v)
         bad = (~torch.isfinite(t)).any().to(torch.float64).reshape(1)
-        t = torch.cat([torch.nan_to_num(t, nan=1e300, posinf=1e300), bad])
+        t = torch.cat([torch.nan_to_num(t, nan=1e300, posinf=1e300), bad, mism.reshape(1)])
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t = t.cpu().numpy()
         del buf3, buf2
         return {"max_abs_u": float(t[0]), "max_abs_v": float(t[1]), "max_abs_theta_minus_5": float(t[2]),
-                "max_abs_eta": float(t[3]), "finite": bool(t[4] == 0.0)}
+                "max_abs_eta": float(t[3]), "finite": bool(t[4] == 0.0),
+                "halo_vs_own_periodic_edge": (float(t[5]) if not strong else None)}
 
     it = 0
     for _ in range(args.warmup):
@@ -318,6 +332,8 @@ def run_cuda(args, rank, world):
     finite = h0["finite"] and h1["finite"] and bool(np.isfinite(eta_host.numpy()).all())
     if not finite:
         fail_run(rank, "non-finite model state", {"before": h0, "after": h1})
+    if not strong and max(h0["halo_vs_own_periodic_edge"], h1["halo_vs_own_periodic_edge"]) > 0.0:
+        fail_run(rank, "halo exchange left halos that differ from the periodic image of the block", {"before": h0, "after": h1})
     if worst_iters >= int(P["cg2dMaxIters"]):
         fail_run(rank, "CG2D hit cg2dMaxIters", {"iters": iters, "iters_e2e": iters_e2e})
     if rank != 0:

@@ -17,7 +17,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 NXg, NYg, NR, nsteps = (int(a) for a in (sys.argv[1:5] + ["64", "48", "4", "3"][len(sys.argv) - 1:]))
 r = distributed.selfcheck(NXg, NYg, NR, nsteps, wide=bool(int(os.environ.get("DIST_CHECK_WIDE", "0"))),
-                          buoyancy=bool(int(os.environ.get("DIST_CHECK_BUOYANCY", "1"))), verbose=True)
+                          buoyancy=bool(int(os.environ.get("DIST_CHECK_BUOYANCY", "1"))), verbose=True,
+                          land_frac=float(os.environ.get("DIST_CHECK_LAND", "0.15")))
 if dist.get_rank() == 0:
     print("DIST_CHECK", "PASS" if r["ok"] else "FAIL", json.dumps(r))
 dist.destroy_process_group()
