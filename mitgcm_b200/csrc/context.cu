@@ -187,7 +187,7 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   if (!build_push_tables()) return;
   c.nRanks = g.nPx * g.nPy;
   c.myRank = g.myPx + g.nPx * g.myPy;
-  c.attrDyn = c.attrThermo = c.attrVi = false;
+  c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false;
   if (c.nRanks > 1) {
     // peer arena: header (flags) + 7 tile3d + 3 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
     c.arenaBytes = 65536 + (7 * g.n3 + 3 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256;

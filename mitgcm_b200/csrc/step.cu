@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "step_fast.cuh"
+#include "dyn_tma.cuh"
 #include "vecinv.cuh"
 #include "vecinv_fast.cuh"
 #include "phys.cuh"
@@ -376,6 +377,34 @@ UNROLL_N(CORR_UNROLL)
   }
 }
 
+// Tensor maps of the arrays dyn_tma_kernel stages (one per array and tile; the encode is host-only and cached).
+static bool dyn_tma_maps(const TileGrid &tg, const MomState &st, const double *guN, const double *gvN, const double *phi,
+                         DynTmaMaps &m) {
+  struct Key {
+    const void *p; int PX, PY, nz, bx;
+    bool operator<(const Key &o) const { return std::tie(p, PX, PY, nz, bx) < std::tie(o.p, o.PX, o.PY, o.nz, o.bx); }
+  };
+  static std::map<Key, CUtensorMap> cache;
+  auto get = [&](CUtensorMap &out, const double *base, int nz, bool patch) -> bool {
+    Key k{base, tg.PX, tg.PY, nz, patch ? FT_H : FT_Y};
+    auto it = cache.find(k);
+    if (it == cache.end()) {
+      CUtensorMap t;
+      if (!make_tmap3(&t, base, tg.PX, tg.PY, (size_t)nz, FT_W, patch ? FT_H : FT_Y)) return false;
+      if (cache.size() > 4096) cache.clear();
+      it = cache.emplace(k, t).first;
+    }
+    out = it->second;
+    return true;
+  };
+  const int Nr = tg.Nr;
+  return get(m.u, st.u, Nr, true) && get(m.v, st.v, Nr, true) && get(m.hW, tg.hFacW, Nr, true) && get(m.hS, tg.hFacS, Nr, true) &&
+         get(m.hC, tg.hFacC, Nr, true) && get(m.w, st.w, Nr, true) && get(m.mC, tg.maskC, Nr, true) &&
+         get(m.phi, phi ? phi : st.u, Nr, true) && get(m.kU, st.kapU, Nr + 1, false) && get(m.kV, st.kapV, Nr + 1, false) &&
+         get(m.rhW, tg.recip_hFacW, Nr, false) && get(m.rhS, tg.recip_hFacS, Nr, false) && get(m.guO, guN, Nr, false) &&
+         get(m.gvO, gvN, Nr, false) && get(m.mW, tg.maskW, Nr, false) && get(m.mS, tg.maskS, Nr, false);
+}
+
 // Thread-block shape of the column-marching kernels (rhs, corr): x extent = contiguous bytes per level
 // and array a block touches.  MITGCM_B200_COLBLK="bx,by" overrides (tuning aid).
 static dim3 col_block() {
@@ -590,6 +619,18 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                                       buoy ? phiHyd + o3 : nullptr,
                                                       q.D(MP_IMPLICSURFPRESS) != 1.0 ? eta + o2 : nullptr, Bo + o2,
                                                       1.0 * (1.0 - q.D(MP_IMPLICSURFPRESS)));
+        } else if (!semiImpl && dyn_tma_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE") && !getenv("MITGCM_B200_DYN_NOTMA")) {
+          // operands staged by TMA (dyn_tma.cuh); the cp.async kernel below stays as the A/B reference
+          DynTmaMaps maps;
+          if (!dyn_tma_maps(tg, st, guN + o3, gvN + o3, buoy ? phiHyd + o3 : nullptr, maps)) return fail(63, "forward_step: cuTensorMapEncodeTiled failed");
+          const int smemBytes = (int)sizeof(DynTmaSmem) + 128;
+          if (!c.attrDynTma) {
+            MG_CUDA(cudaFuncSetAttribute(dyn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+            c.attrDynTma = true;
+          }
+          dyn_tma_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), smemBytes, c.stream>>>(
+              maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
+              q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0);
         } else if (!semiImpl && dyn_fast_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE")) {
           if (!c.attrDyn) {
             MG_CUDA(cudaFuncSetAttribute(dyn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DynPipeSmem)));

@@ -147,6 +147,35 @@ def test_vecinv_pipelined_kernel_is_bit_identical_to_the_generic_kernels(monkeyp
             assert np.array_equal(o[n], outs[0][n]), n
 
 
+@pytest.mark.parametrize("opts", [
+    dict(buoyancyLinear=1),
+    dict(buoyancyLinear=0, selectCoriScheme=2, momDissip_In_AB=0, no_slip_sides=0, bottomDragLinear=1e-3),
+    dict(buoyancyLinear=1, rigidLid=1, no_slip_bottom=0, implicitViscosity=1, viscAr=5e-2),
+], ids=["headline", "cori2-freeslip-botdrag", "rigidlid-implvisc"])
+def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeypatch, opts):
+    """dyn_tma_kernel (operands staged by TMA + mbarrier ring) vs dyn_pipe_kernel (cp.async ring) vs the generic
+    dyn_kernel<0>: the same fields after 3 steps on a partial-cell grid with land and 2 x 1 tiles (np.array_equal:
+    the TMA kernel skips the identically-zero biharmonic terms, which can only flip the sign of a zero)."""
+    outs = []
+    for env in ({}, {"MITGCM_B200_DYN_NOTMA": "1"}, {"MITGCM_B200_GENERIC_STEP": "1"}):
+        for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g, P, s = make_channel(sNx=70, sNy=44, Nr=7, nSx=2, nSy=1, land_frac=0.15, **opts)
+        co = ChannelOracle(g, P, s)
+        m = Model(g, P, s, co.op)
+        try:
+            for _ in range(3):
+                m.step()
+            outs.append({n: m.get(n) for n in ("uVel", "vVel", "wVel", "etaN", "theta", "gU", "gV", "guNm1", "gvNm1")})
+        finally:
+            m.close()
+    for o in outs[1:]:
+        for n in o:
+            assert np.array_equal(o[n], outs[0][n]), n
+
+
 @pytest.mark.parametrize("scheme", [2, 33])
 def test_thermo_pipelined_kernel_is_bit_identical_to_the_staged_kernel(monkeypatch, scheme):
     """thermo_pipe_kernel (cp.async ring) vs thermo_fast_kernel vs the generic thermo_kernel: same fields after 3 steps
