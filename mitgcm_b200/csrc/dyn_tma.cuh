@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
   const double dxF00 = g.dxF[s], dxF0m = g.dxF[s - PX], rdyF00 = g.recip_dyF[s], rdyF0m = g.recip_dyF[s - PX];
   const double cfU = g.cosFacU[j + g.OLy - 1 < g.PY ? j + g.OLy - 1 : 0], cfV = g.cosFacV[j + g.OLy - 1 < g.PY ? j + g.OLy - 1 : 0];
   const double fC00 = g.fCori[s], fCm0 = g.fCori[s - 1], fC0m = g.fCori[s - PX];
-  const double sfu = sfU[s], sfv = sfV[s];
   const double uDudxFac = p.afFacMom, AhFac = p.vfFacMom, ArFac = p.implicitViscosity ? 0. : p.vfFacMom;
   // CALC_GRAD_PHI_HYD (calc_grad_phi_hyd.F:150-165) is defined on i >= iMin+1, j >= jMin+1
   const double gpx = (hasPhi && i >= 1) ? g.recip_dxC[s] : 0., gpy = (hasPhi && j >= 1) ? g.recip_dyC[s] : 0.;
@@ -179,9 +178,11 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
         if (below) sm.wA[e] = S.patch[DP_W][e] * sm.rA[e];
         sm.mCk[e] = mCk1[e];
         if (hzok[r]) {                               // MOM_CALC_HFACZ at the south-west corner
-          double h = fmin(hW, S.patch[DP_HW][e - FT_W]);
-          h = fmin(hS, h);
-          h = fmin(S.patch[DP_HS][e - 1], h);
+          // MIN of finite open-water fractions: a compare + select (fmin's NaN handling costs 7 instructions a piece)
+          const double hWs = S.patch[DP_HW][e - FT_W], hSw = S.patch[DP_HS][e - 1];
+          double h = hW < hWs ? hW : hWs;
+          h = hS < h ? hS : h;
+          h = hSw < h ? hSw : h;
           sm.hZ[e] = h;
         }
       }
@@ -296,8 +297,8 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
       if (momForcing) {
         double ge = 0., he = 0.;
         if (k == 1) {
-          if (i >= 1 && i <= g.sNx + 1) ge = 0. + sfu * sm.vs.rdrF[0] * rhW;
-          if (j >= 1 && j <= g.sNy + 1) he = 0. + sfv * sm.vs.rdrF[0] * rhS;
+          if (i >= 1 && i <= g.sNx + 1) ge = 0. + sfU[s] * sm.vs.rdrF[0] * rhW;
+          if (j >= 1 && j <= g.sNy + 1) he = 0. + sfV[s] * sm.vs.rdrF[0] * rhS;
         }
         gu = gu + ge; gv = gv + he;
       }
