@@ -164,6 +164,12 @@ __device__ __forceinline__ double warp_max(double v) {
 template <int N, bool MAXOP>
 __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N], double *sm) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // Multi-rank: the edge pushes of this phase are stores into the PEER's memory; they are ordered before the flag
+  // CTA 0 raises after the grid barrier by causality (gpu-scope release/acquire through the barrier, then CTA 0's
+  // system-scope fence): no per-CTA system fence is needed (CG2D_PUSH_FENCE adds one, for experiments).
+#ifdef CG2D_PUSH_FENCE
+  if (a.nRanks > 1) __threadfence_system();
+#endif
 #pragma unroll
   for (int k = 0; k < N; k++) v[k] = MAXOP ? warp_max(v[k]) : warp_sum(v[k]);
   if (lane == 0)

@@ -674,6 +674,11 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                               exactConserv ? nullptr : u + o3, exactConserv ? nullptr : v + o3);
       }
     MG_CUDA(cudaGetLastError());
+    // The side-stream exchange must be over before the cooperative solver starts: cg2d_kernel takes every register
+    // of every SM and waits for its peers, so a spinning halo kernel that keeps one of its CTAs off the machine (or
+    // a push kernel that cannot get on it) closes a wait cycle across the ranks.  theta's halo has had the whole
+    // of DYNAMICS to travel.
+    if (peerHalo && !halo_join()) return false;
     mark(3);
     int numIters = q.I(MI_CG2DMAXITERS), nIterMin = q.I(MI_CG2DUSEMINRESSOL) - 1;
     double first, minsq, last;

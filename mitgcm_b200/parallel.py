@@ -7,7 +7,14 @@ import torch.distributed as dist
 
 
 def process_grid(world: int) -> tuple[int, int]:
-    """nPx x nPy for 1, 2, 4, 8 ranks: split y first (y-edge strips are contiguous rows)."""
+    """nPx x nPy for 1, 2, 4, 8 ranks: split y first (y-edge strips are contiguous rows).
+    MITGCM_B200_PGRID="2x1" overrides (tests of the x-split on two GPUs)."""
+    import os
+    o = os.environ.get("MITGCM_B200_PGRID")
+    if o:
+        px, py = (int(v) for v in o.lower().split("x"))
+        assert px * py == world, "MITGCM_B200_PGRID does not match the world size"
+        return px, py
     return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(world, (1, world))
 
 

@@ -29,6 +29,10 @@ def _addr(a):
     # torch tensor
     import torch
     assert isinstance(a, torch.Tensor) and a.dtype == torch.float64 and a.is_contiguous()
+    if a.is_cuda:
+        # the library works on its own stream: whatever torch still has in flight for this tensor must be done
+        # before the library reads it (bench.py once uploaded an eta that torch had not finished computing)
+        torch.cuda.current_stream(a.device).synchronize()
     return C.c_void_p(a.data_ptr())
 
 
