@@ -68,7 +68,9 @@ for it in range(a.steps):
     de = float((eN[it] - e1[it]).abs().max() / e1[it].abs().max())
     rows.append(dict(step=it, iters_1=r1[it][0], iters_N=rN[it][0], init_res_1=r1[it][1], init_res_N=rN[it][1],
                      eta_rel_diff=de, max_u_1=s1[it], max_u_N=sN[it]))
-    if not (de < a.tol) or rN[it][0] - r1[it][0] < 0 or rN[it][0] - r1[it][0] > max(3, 0.05 * r1[it][0]):
+    # CG2D stops on the GLOBAL sum of r^2 of the normalised system: N identical blocks carry N x the sum, so the
+    # N-rank solve needs the iterations that reduce the residual by another sqrt(N) (about +2 / +7 / +11 at N = 2 / 4 / 8)
+    if not (de < a.tol) or rN[it][0] - r1[it][0] < 0 or rN[it][0] - r1[it][0] > max(3, 0.10 * r1[it][0]):
         ok = False
 fin = {n: float((fN[n] - f1[n]).abs().max() / f1[n].abs().max()) for n in f1}
 if any(not (v < a.tol) for v in fin.values()):
