@@ -38,13 +38,16 @@ struct Cg2dOut {
   unsigned long long seq;
 };
 
-// Cross-GPU reduction mailbox: rank r writes val then seq into slot [r][parity] of EVERY rank's
-// array through peer-mapped memory (NVLink); the reader sums the slots in rank order, so every
-// rank forms bit-identical totals (GLOBAL_SUM_TILE_RL semantics, global_sum_tile.F:161-191).
+// Cross-GPU reduction mailbox, "LL" style (flag travels inside the data word, as in NCCL's low-latency protocol):
+// a value is posted as two 8-byte words {low half | flag << 32} and {high half | flag << 32}, flag = the low 32 bits
+// of the reduction sequence number.  8-byte stores are single-copy atomic, so a reader that sees the flag in both
+// words holds the whole value: no fence and no second round trip between value and flag.  Rank r writes its words
+// into slot [r][parity][k] of EVERY rank's array through peer-mapped memory (NVLink); the reader sums the slots in
+// rank order, so every rank forms bit-identical totals (GLOBAL_SUM_TILE_RL semantics, global_sum_tile.F:161-191).
 struct Mail {
-  double val[3];
-  unsigned long long seq;
+  unsigned long long w[2];
 };
+constexpr int MAIL_SLOTS = 8 * 2 * 4;      // ranks x parities x values
 
 struct Cg2dArgs {
   int sNx, sNy, OLx, OLy, PX, nTiles;
@@ -218,19 +221,26 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
       // flag also publishes this rank's halo pushes (ordered before us by the grid barrier).
       // (Letting every CTA poll the mailbox itself was measured slower: 128 vs 116 us/iteration
       // on 4 GPUs -- 296 CTAs of system-scope fences.)
-      if (threadIdx.x < a.nRanks) {
-        const int r = threadIdx.x;
-        Mail *m = a.mail[r] + (size_t)a.myRank * 2 + par;
-        for (int k = 0; k < N; k++) m->val[k] = sm[k];
+      if (threadIdx.x < a.nRanks * N) {
+        const int r = threadIdx.x / N, k = threadIdx.x - r * N;
+        // everything this rank pushed in the phase is ordered before us by the grid barrier; this fence orders it
+        // before the words below for every observer in the system
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&m->seq) = rseq;
-        Mail *mm = a.mail[a.myRank] + (size_t)r * 2 + par;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sm[k]);
+        const unsigned long long flag = (rseq & 0xffffffffull) << 32;
+        volatile unsigned long long *dst = a.mail[r][((size_t)a.myRank * 2 + par) * 4 + k].w;
+        dst[0] = (bits & 0xffffffffull) | flag;
+        dst[1] = (bits >> 32) | flag;
+        volatile unsigned long long *src = a.mail[a.myRank][((size_t)r * 2 + par) * 4 + k].w;
+        unsigned long long w0, w1;
         long long spins = 0;
-        while (*reinterpret_cast<volatile unsigned long long *>(&mm->seq) != rseq) {
+        for (;;) {
+          w0 = src[0]; w1 = src[1];
+          if ((w0 & 0xffffffff00000000ull) == flag && (w1 & 0xffffffff00000000ull) == flag) break;
           if (++spins > CG2D_SPIN_LIMIT) { g_cg2d_spin_error = 1; break; }
         }
-        __threadfence_system();
-        for (int k = 0; k < N; k++) sm[CG_WARPS + r * 3 + k] = *reinterpret_cast<volatile double *>(&mm->val[k]);
+        __threadfence_system();      // acquire: the peer's pushes that preceded its words
+        sm[CG_WARPS + r * 3 + k] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -1115,7 +1125,7 @@ static bool ensure_ws(int maxIters) {
     } guard{new Cg2dWs()};
     Cg2dWs *w = guard.w;
     const size_t n2 = c.g.n2;
-    const size_t mailBytes = sizeof(Mail) * 8 * 2, totBytes = sizeof(double) * 8, flagBytes = 64;
+    const size_t mailBytes = sizeof(Mail) * MAIL_SLOTS, totBytes = sizeof(double) * 8, flagBytes = 64;
     w->blockBytes = 9 * n2 * sizeof(double) + mailBytes + totBytes + flagBytes;
     // multi-rank: the block is part of the peer arena (zero-filled), which the neighbours map once (halo.cu)
     w->block = static_cast<double *>(arena_alloc(w->blockBytes));
@@ -1182,7 +1192,7 @@ bool cg2d_comm_wire() {
   MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
   // a fresh connection starts the reduction sequence over on every rank (also the recovery path after error 71)
   w->seq = 0;
-  MG_CUDA(cudaMemset(w->mail, 0, sizeof(Mail) * 8 * 2));
+  MG_CUDA(cudaMemset(w->mail, 0, sizeof(Mail) * MAIL_SLOTS));
   MG_CUDA(cudaMemset(w->gflag, 0, 64));
   return true;
 }

@@ -190,7 +190,9 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false;
   if (c.nRanks > 1) {
     // peer arena: header (flags) + 7 tile3d + 3 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
-    c.arenaBytes = 65536 + (7 * g.n3 + 3 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256;
+    // + the two strip buffers of halo.cu: (2 OLx sNy + 4 OLx OLy) x (4 Nr + 4) doubles each
+    c.arenaBytes = 65536 + (7 * g.n3 + 3 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256 +
+                   2 * (size_t)(2L * g.OLx * g.sNy + 4L * g.OLx * g.OLy) * (size_t)(4L * g.Nr + 4) * sizeof(double);
     if (cudaMalloc(&c.arena, c.arenaBytes) != cudaSuccess) { c.arena = nullptr; fail(3, "cudaMalloc failed for the peer arena"); return; }
     if (cudaMemset(c.arena, 0, c.arenaBytes) != cudaSuccess) { fail(3, "peer arena memset"); return; }
     c.arenaUsed = 4096;      // header: exchange flags (halo.cu)

@@ -10,6 +10,10 @@
 //           (the reference fills corners by doing X before Y; the diagonal neighbour's interior block is the same
 //           data, so one phase suffices), system-scope fence, the last CTA raises the "done" flags at the neighbours
 //   wait  : spin until all 8 neighbours have raised mine
+//   unpack: (only with remote west / east / diagonal neighbours) column strips and corner blocks are 16-byte
+//           pieces 16 KB apart in the halo -- stored directly over NVLink they cost 1.5 ms per exchange at 2048^2 x
+//           150 levels -- so those travel packed into the receiver's strip buffer (contiguous remote stores) and
+//           are scattered into the halo locally; south / north rows are contiguous and are stored directly
 // Several fields travel in one exchange (one set of flags).  A direction whose neighbour is this rank (nPx or
 // nPy = 1) is the local periodic wrap through the same code path.  An exchange can run on a side stream
 // (channel 1: own flags) while the main stream computes: theta's halo travels while DYNAMICS runs.
@@ -37,6 +41,8 @@ struct HaloWs {
   int *errHost = nullptr, *errDev = nullptr;   // mapped pinned word: a timed-out spin reports without a sync
   bool connected = false;
   void *ipcBase[8] = {};      // what cudaIpcOpenMemHandle returned per rank (the peer's whole allocation)
+  double *strip[2] = {nullptr, nullptr};   // per channel: receive buffer of the packed W / E / corner pieces (in the arena)
+  long stripLevels = 0;                    // levels a strip buffer holds
 };
 
 struct HaloArgs {
@@ -50,6 +56,7 @@ struct HaloArgs {
   unsigned long long *ready, *done;   // my flags (this channel)
   unsigned int *counter;
   int *err;
+  double *strip;                      // my strip buffer (this channel); the peer's is at the same arena offset
 };
 
 // direction d: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE, 6 NW, 7 NE
@@ -69,6 +76,12 @@ __global__ void halo_ready_kernel(HaloArgs a) {
     if (++spins > HALO_SPIN_LIMIT) { *a.err = 81; break; }
 }
 
+// Strip buffer layout for an exchange of L levels: [side W | side E | SW | SE | NW | NE], side = the receiver's halo
+// side; inside a side [level][row][column].
+__device__ __forceinline__ long strip_base(const HaloArgs &a, int side, long n0, long n4) {
+  return side < 2 ? side * n0 * a.totalNz : 2 * n0 * a.totalNz + (long)(side - 4) * n4 * a.totalNz;
+}
+
 __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
   const int w0 = a.OLx, h0 = a.sNy, w2 = a.sNx, h2 = a.OLy;
   // cells per level: W | E (OLx x sNy each), S | N (sNx x OLy each), 4 corners (OLx x OLy each)
@@ -76,7 +89,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
   const long perLevel = 2 * n0 + 2 * n2 + 4 * n4;
   const long total = perLevel * a.totalNz;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    long lev = t / perLevel, c = t - lev * perLevel;
+    const long levG = t / perLevel;
+    long lev = levG, c = t - levG * perLevel;
     int fi = 0;
     while (lev >= a.nz[fi]) { lev -= a.nz[fi]; fi++; }
     int d, w;
@@ -87,11 +101,18 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
     const int dx = dir_dx(d), dy = dir_dy(d);
     // source: my interior strip next to edge d (Fortran indices); destination: the same cells shifted by one tile
     const int i = (dx > 0 ? a.sNx - a.OLx + 1 : 1) + bI, j = (dy > 0 ? a.sNy - a.OLy + 1 : 1) + bJ;
-    const int iD = i - dx * a.sNx, jD = j - dy * a.sNy;
     const size_t src = (size_t)(i + a.OLx - 1) + (size_t)a.PX * (size_t)(j + a.OLy - 1) + a.slab * (size_t)lev;
-    const size_t dst = (size_t)(iD + a.OLx - 1) + (size_t)a.PX * (size_t)(jD + a.OLy - 1) + a.slab * (size_t)lev;
-    double *fd = reinterpret_cast<double *>(reinterpret_cast<char *>(a.f[fi]) + a.peerDelta[d]);
-    fd[dst] = a.f[fi][src];
+    const double v = a.f[fi][src];
+    if (dx != 0 && a.peerDelta[d] != 0) {      // remote column strip / corner: packed into the receiver's strip buffer
+      const int side = dir_opp(d);
+      double *sb = reinterpret_cast<double *>(reinterpret_cast<char *>(a.strip) + a.peerDelta[d]);
+      sb[strip_base(a, side, n0, n4) + levG * (side < 2 ? n0 : n4) + c] = v;
+    } else {
+      const int iD = i - dx * a.sNx, jD = j - dy * a.sNy;
+      const size_t dst = (size_t)(iD + a.OLx - 1) + (size_t)a.PX * (size_t)(jD + a.OLy - 1) + a.slab * (size_t)lev;
+      double *fd = reinterpret_cast<double *>(reinterpret_cast<char *>(a.f[fi]) + a.peerDelta[d]);
+      fd[dst] = v;
+    }
   }
   // publish: every thread's stores are ordered before this CTA's arrival; the last CTA to arrive raises the flags
   __threadfence_system();
@@ -121,6 +142,30 @@ __global__ void halo_wait_kernel(HaloArgs a) {
       if (++spins > HALO_SPIN_LIMIT) { *a.err = 82; break; }
   }
   __threadfence_system();
+}
+
+// strip buffer -> my west / east / corner halos (sides whose neighbour is another rank)
+__global__ void __launch_bounds__(256) halo_unpack_kernel(HaloArgs a) {
+  const long n0 = (long)a.OLx * a.sNy, n4 = (long)a.OLx * a.OLy;
+  const long perSideSet = 2 * n0 + 4 * n4;
+  const long total = perSideSet * a.totalNz;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    // t enumerates the buffer in its own order: side, level, cell
+    int side;
+    long r = t, cells;
+    if (r < 2 * n0 * a.totalNz) { side = (int)(r / (n0 * a.totalNz)); r -= side * n0 * a.totalNz; cells = n0; }
+    else { r -= 2 * n0 * a.totalNz; side = 4 + (int)(r / (n4 * a.totalNz)); r -= (long)(side - 4) * n4 * a.totalNz; cells = n4; }
+    if (a.peerDelta[side] == 0) continue;      // that neighbour is this rank: it wrote the halo directly
+    const long levG = r / cells, c = r - levG * cells;
+    long lev = levG;
+    int fi = 0;
+    while (lev >= a.nz[fi]) { lev -= a.nz[fi]; fi++; }
+    const int bI = (int)(c % a.OLx), bJ = (int)(c / a.OLx);
+    const int dx = dir_dx(side), dy = dir_dy(side);
+    const int iD = (dx < 0 ? 1 - a.OLx : a.sNx + 1) + bI;
+    const int jD = dy == 0 ? 1 + bJ : (dy < 0 ? 1 - a.OLy : a.sNy + 1) + bJ;
+    a.f[fi][(size_t)(iD + a.OLx - 1) + (size_t)a.PX * (size_t)(jD + a.OLy - 1) + a.slab * (size_t)lev] = a.strip[t];
+  }
 }
 
 bool halo_connected() { return ctx().halo && ctx().halo->connected; }
@@ -216,6 +261,12 @@ static bool comm_connect(int nRanks, int myRank, const unsigned char *handles) {
   *h->errHost = 0;
   MG_CUDA(cudaHostGetDevicePointer(&h->errDev, h->errHost, 0));
   MG_CUDA(cudaMemset(c.arena, 0, 4096));      // flags start over (the caller barriers before the first exchange)
+  h->stripLevels = 4L * g.Nr + 4;
+  const size_t stripBytes = (size_t)(2L * g.OLx * g.sNy + 4L * g.OLx * g.OLy) * (size_t)h->stripLevels * sizeof(double);
+  for (int ch = 0; ch < 2; ch++) {
+    h->strip[ch] = static_cast<double *>(arena_alloc(stripBytes));
+    if (!h->strip[ch]) return fail(3, "comm_connect: peer arena exhausted (strip buffers)");
+  }
   if (!cg2d_comm_wire()) return false;
   h->connected = true;
   return true;
@@ -249,6 +300,10 @@ bool halo_exchange(const int *ids, int n, bool sideStream) {
   a.done = reinterpret_cast<unsigned long long *>(hdr + 64);
   a.counter = reinterpret_cast<unsigned int *>(hdr + 128);
   a.err = h->errDev;
+  a.strip = h->strip[ch];
+  if (a.totalNz > h->stripLevels) return fail(70, "halo_exchange: more levels than the strip buffers hold (4 Nr + 4)");
+  bool remoteX = false;
+  for (int d = 0; d < 8; d++) remoteX = remoteX || (dir_dx(d) != 0 && h->peerDelta[d] != 0);
   cudaStream_t st = c.stream;
   if (sideStream) {
     MG_CUDA(cudaEventRecord(h->evFork, c.stream));
@@ -263,6 +318,11 @@ bool halo_exchange(const int *ids, int n, bool sideStream) {
   halo_ready_kernel<<<1, 32, 0, st>>>(a);
   halo_push_kernel<<<blocks, 256, 0, st>>>(a);
   halo_wait_kernel<<<1, 32, 0, st>>>(a);
+  if (remoteX) {
+    const long nu = (2L * g.OLx * g.sNy + 4L * g.OLx * g.OLy) * a.totalNz;
+    c.launches++;
+    halo_unpack_kernel<<<(int)std::min<long>((nu + 255) / 256, (long)c.numSMs * 4), 256, 0, st>>>(a);
+  }
   MG_CUDA(cudaGetLastError());
   if (sideStream) {
     MG_CUDA(cudaEventRecord(h->evJoin, h->side));
