@@ -59,7 +59,7 @@ enum {
   MP_BOTTOMDRAGQUADRATIC, MP_RECIP_RSPHERE, MP_AFFACMOM, MP_VFFACMOM, MP_CFFACMOM, MP_MTFACMOM,
   MP_ABEPS, MP_DELTATTRACER, MP_DIFFKHT, MP_DIFFK4T, MP_GRAVITY, MP_TALPHA, MP_RHONIL, MP_RHOCONST,
   MP_DIFFKRT, MP_VISCAR, MP_SBETA, MP_IVDC_KAPPA, MP_CG3DNORM, MP_CG3DTOLERANCE_SQ,
-  MP_DIFFKHS, MP_DIFFK4S, MP_DIFFKRS,
+  MP_DIFFKHS, MP_DIFFK4S, MP_DIFFKRS, MP_CG2DPCOFFDFAC,
   MP_ND,
   MI_CG2DNORMALISERHS = 100, MI_CG2DMAXITERS, MI_CG2DUSEMINRESSOL, MI_PRINTRESIDUALFREQ,
   MI_MOMADVECTION, MI_MOMVISCOSITY, MI_USEBIHARMONICVISC, MI_IMPLICITVISCOSITY,
@@ -73,7 +73,7 @@ enum {
   MI_USECORIOLIS, MI_USEABSVORTICITY, MI_SELECTVORTSCHEME, MI_USEJAMARTMOMADV, MI_UPWINDSHEAR,
   MI_SELECTKESCHEME, MI_HIGHORDERVORTICITY, MI_UPWINDVORTICITY, MI_MOMIMPLVERTADV,
   MI_VECTORINVARIANTMOMENTUM, MI_CG3DNORMALISERHS, MI_MULTIDIMADVECTION,
-  MI_SALTSTEPPING, MI_SALTADVSCHEME, MI_SALTVERTADVSCHEME,
+  MI_SALTSTEPPING, MI_SALTADVSCHEME, MI_SALTVERTADVSCHEME, MI_CG2DPRECONDFREQ,
   MI_NI_END
 };
 
@@ -118,6 +118,13 @@ void cg2d_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double *m
                 double *lastResidual, int *numIters, int *nIterMin, const int *myThid);
 void cg2d_sr_b200_(double *cg2d_b, double *cg2d_x, double *firstResidual, double *minResidualSq,
                    double *lastResidual, int *numIters, int *nIterMin, const int *myThid);
+/* UPDATE_CG2D, same argument list as model/src/update_cg2d.F:7 (caller: forward_step.F with the non-linear free
+ * surface, once per step): rebuilds the mirrors MG_AW2D, MG_AS2D, MG_AC2D and -- when myIter = nIter0 or
+ * MOD(myIter, cg2dPreCondFreq) = 0 (MI_CG2DPRECONDFREQ, default 1; MI_NITER0) -- MG_PC, MG_PW, MG_PS from the current
+ * mirrors MG_HFACW / MG_HFACS (the caller refreshes those after UPDATE_SURF_DR / r*) and the 2-D grid mirrors;
+ * MP_CG2DNORM, MP_CG2DPCOFFDFAC (default 0.51), implicSurfPress, implicDiv2DFlow, freeSurfFac and the time steps
+ * come from the parameters.  Errors are recorded for mitgcm_b200_last_error_(). */
+void update_cg2d_b200_(const double *myTime, const int *myIter, const int *myThid);
 /* The values cg2d.F:199-200 prints inside the solver (`cg2d: Sum(rhs),rhsMax`), and the
  * per-iteration residuals of cg2d.F:329-336 (n <= iterations run). */
 void mitgcm_b200_cg2d_stats_(double *sumRHS, double *rhsMax);

@@ -29,7 +29,7 @@ size_t field_elems(const Geom &g, int id) {
 static bool is_exchanged_field(int id) {
   switch (id) {
     case MG_UVEL: case MG_VVEL: case MG_WVEL: case MG_THETA: case MG_THETA2: case MG_SALT: case MG_SALT2:
-    case MG_CG2D_X: case MG_ETAN: case MG_ETAH:
+    case MG_CG2D_X: case MG_ETAN: case MG_ETAH: case MG_AC2D:
       return true;
     default:
       return false;
@@ -175,7 +175,8 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.p.d[MP_RKSIGN] = -1.0; c.p.d[MP_FREESURFFAC] = 1.0; c.p.d[MP_IMPLICSURFPRESS] = 1.0;
   c.p.d[MP_IMPLICDIV2DFLOW] = 1.0; c.p.d[MP_SIDEDRAGFACTOR] = 2.0;
   c.p.d[MP_AFFACMOM] = c.p.d[MP_VFFACMOM] = c.p.d[MP_CFFACMOM] = c.p.d[MP_MTFACMOM] = 1.0;
-  c.p.d[MP_ABEPS] = 0.01; c.p.d[MP_RECIP_RSPHERE] = 1.0 / 6370.0e3;
+  c.p.d[MP_ABEPS] = 0.01; c.p.d[MP_RECIP_RSPHERE] = 1.0 / 6370.0e3; c.p.d[MP_CG2DPCOFFDFAC] = 0.51;
+  c.p.i[MI_CG2DPRECONDFREQ - 100] = 1;
   c.p.i[MI_CG2DNORMALISERHS - 100] = 1; c.p.i[MI_CG2DMAXITERS - 100] = 150;
   c.p.i[MI_MOMADVECTION - 100] = 1; c.p.i[MI_MOMVISCOSITY - 100] = 1;
   c.p.i[MI_SELECTBOTDRAGQUADR - 100] = -1; c.p.i[MI_MOMFORCING - 100] = 1;
@@ -189,9 +190,9 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   c.myRank = g.myPx + g.nPx * g.myPy;
   c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false;
   if (c.nRanks > 1) {
-    // peer arena: header (flags) + 7 tile3d + 3 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
+    // peer arena: header (flags) + 7 tile3d + 4 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
     // + the two strip buffers of halo.cu: (2 OLx sNy + 4 OLx OLy) x (4 Nr + 4) doubles each
-    c.arenaBytes = 65536 + (7 * g.n3 + 3 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256 +
+    c.arenaBytes = 65536 + (7 * g.n3 + 4 * g.n2 + 9 * g.n2) * sizeof(double) + 32 * 256 +
                    2 * (size_t)(2L * g.OLx * g.sNy + 4L * g.OLx * g.OLy) * (size_t)(4L * g.Nr + 4) * sizeof(double);
     if (cudaMalloc(&c.arena, c.arenaBytes) != cudaSuccess) { c.arena = nullptr; fail(3, "cudaMalloc failed for the peer arena"); return; }
     if (cudaMemset(c.arena, 0, c.arenaBytes) != cudaSuccess) { fail(3, "peer arena memset"); return; }

@@ -71,7 +71,12 @@ bool exch_field(double *f, int nz) {
   Ctx &c = ctx();
   const Geom &g = c.g;
   if (exch2_active()) return exch2_field(f, nz);
-  if (g.nPx != 1 || g.nPy != 1) return fail(60, "exch: multi-process exchange goes through the distributed driver");
+  if (g.nPx != 1 || g.nPy != 1) {      // across ranks: peer pushes (the mirror must live in the peer arena)
+    if (halo_connected())
+      for (auto &kv : c.fields)
+        if (kv.second == f) { const int id = kv.first; return halo_exchange(&id, 1); }
+    return fail(60, "exch: multi-process exchange needs mitgcm_b200_comm_connect_ and a mirror in the peer arena");
+  }
   const size_t total = (size_t)(g.PX * g.PY - g.sNx * g.sNy) * nz * g.nTiles;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
   c.launches++;

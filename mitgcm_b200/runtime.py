@@ -118,6 +118,13 @@ def set_cg2d_operator(op: dict):
                cg2dNormaliseRHS=bool(op["cg2dNormaliseRHS"]))
 
 
+def update_cg2d(myIter: int, myTime: float = 0.0, myThid: int = 1):
+    """CALL UPDATE_CG2D( myTime, myIter, myThid ) -- model/src/update_cg2d.F:7: operator (and preconditioner) from
+    the current hFacW / hFacS mirrors."""
+    _lib.lib().update_cg2d_b200_(_d(myTime), _i(myIter), _i(myThid))
+    _check()
+
+
 def cg2d(cg2d_b, cg2d_x, numIters: int, nIterMin: int = -1, sr: bool = False, residuals: bool = False):
     """CALL CG2D( cg2d_b, cg2d_x, firstResidual, minResidualSq, lastResidual, numIters,
     nIterMin, myThid ) -- model/src/cg2d.F:13-17 (CG2D_SR when sr).  b and x are updated in

@@ -198,6 +198,68 @@ void og_ini_cg2d(const og_grid *g, const og_params *p, og_cg2d_op *op) {
 #undef I3
 }
 
+/* UPDATE_CG2D, update_cg2d.F:57-192 (non-linear free surface / r*: the column thickness changes every step).
+ * hFacW, hFacS of the grid are the CURRENT ones; cg2dNorm and the tolerance stay as INI_CG2D left them
+ * (update_cg2d.F:41-42).  No deepAtmosphere, no OBCS, selectImplicitDrag < 2.  updatePreCond as decided by the
+ * caller (update_cg2d.F:54-60: cg2dPreCondFreq). */
+void og_update_cg2d(const og_grid *g, const og_params *p, og_cg2d_op *op, int updatePreCond) {
+  const og_dims *d = &g->d;
+  const int sNx = d->sNx, sNy = d->sNy, Nr = d->Nr;
+#define I3(i, j, k, bi, bj) \
+  ((size_t)((i) + d->OLx - 1) + (size_t)PX * ((size_t)((j) + d->OLy - 1) + (size_t)PY * ((size_t)((k)-1) + (size_t)Nr * ((size_t)((bi)-1) + (size_t)d->nSx * ((bj)-1)))))
+  for (int bj = 1; bj <= d->nSy; bj++)
+    for (int bi = 1; bi <= d->nSx; bi++) {
+      for (int j = 1 - d->OLy; j <= sNy + d->OLy; j++)
+        for (int i = 1 - d->OLx; i <= sNx + d->OLx; i++) {
+          op->aW2d[I2(i, j, bi, bj)] = 0.;
+          op->aS2d[I2(i, j, bi, bj)] = 0.;
+        }
+      for (int k = 1; k <= Nr; k++)
+        for (int j = 1; j <= sNy + 1; j++)
+          for (int i = 1; i <= sNx + 1; i++) {
+            double faceArea = g->dyG[I2(i, j, bi, bj)] * g->drF[k - 1] * g->hFacW[I3(i, j, k, bi, bj)];
+            op->aW2d[I2(i, j, bi, bj)] = op->aW2d[I2(i, j, bi, bj)] + faceArea * g->recip_dxC[I2(i, j, bi, bj)];
+            faceArea = g->dxG[I2(i, j, bi, bj)] * g->drF[k - 1] * g->hFacS[I3(i, j, k, bi, bj)];
+            op->aS2d[I2(i, j, bi, bj)] = op->aS2d[I2(i, j, bi, bj)] + faceArea * g->recip_dyC[I2(i, j, bi, bj)];
+          }
+      for (int j = 1; j <= sNy + 1; j++)
+        for (int i = 1; i <= sNx + 1; i++) {
+          op->aW2d[I2(i, j, bi, bj)] = op->aW2d[I2(i, j, bi, bj)] * op->cg2dNorm * p->implicSurfPress * p->implicDiv2DFlow;
+          op->aS2d[I2(i, j, bi, bj)] = op->aS2d[I2(i, j, bi, bj)] * op->cg2dNorm * p->implicSurfPress * p->implicDiv2DFlow;
+        }
+      for (int j = 1; j <= sNy; j++)
+        for (int i = 1; i <= sNx; i++)
+          op->aC2d[I2(i, j, bi, bj)] = -(
+              op->aW2d[I2(i, j, bi, bj)] + op->aW2d[I2(i + 1, j, bi, bj)]
+            + op->aS2d[I2(i, j, bi, bj)] + op->aS2d[I2(i, j + 1, bi, bj)]
+            + p->freeSurfFac * op->cg2dNorm * g->recip_Bo[I2(i, j, bi, bj)]
+                * g->rA[I2(i, j, bi, bj)] / p->deltaTMom / p->deltaTFreeSurf);
+    }
+  if (!updatePreCond) return;
+  og_exch_xyz(d, op->aC2d, 1);
+  for (int bj = 1; bj <= d->nSy; bj++)
+    for (int bi = 1; bi <= d->nSx; bi++)
+      for (int j = 1; j <= sNy + 1; j++)
+        for (int i = 1; i <= sNx + 1; i++) {
+          const double aC = op->aC2d[I2(i, j, bi, bj)];
+          if (aC == 0.) op->pC[I2(i, j, bi, bj)] = 1.;
+          else op->pC[I2(i, j, bi, bj)] = 1. / aC;
+          const double pW_tmp = aC + op->aC2d[I2(i - 1, j, bi, bj)];
+          if (pW_tmp == 0.) op->pW[I2(i, j, bi, bj)] = 0.;
+          else {
+            const double t = p->cg2dpcOffDFac * pW_tmp;
+            op->pW[I2(i, j, bi, bj)] = -op->aW2d[I2(i, j, bi, bj)] / (t * t);
+          }
+          const double pS_tmp = aC + op->aC2d[I2(i, j - 1, bi, bj)];
+          if (pS_tmp == 0.) op->pS[I2(i, j, bi, bj)] = 0.;
+          else {
+            const double t = p->cg2dpcOffDFac * pS_tmp;
+            op->pS[I2(i, j, bi, bj)] = -op->aS2d[I2(i, j, bi, bj)] / (t * t);
+          }
+        }
+#undef I3
+}
+
 #define TILES for (int bj = 1; bj <= d->nSy; bj++) for (int bi = 1; bi <= d->nSx; bi++)
 /* Tiles are independent inside a sweep (per-tile partial sums), exactly the reference's
  * thread / MPI-rank parallelism over tiles; results do not depend on the thread count. */

@@ -100,6 +100,7 @@ typedef struct {
 
 /* INI_CG2D (model/src/ini_cg2d.F:76-234) */
 void og_ini_cg2d(const og_grid *g, const og_params *p, og_cg2d_op *op);
+void og_update_cg2d(const og_grid *g, const og_params *p, og_cg2d_op *op, int updatePreCond);
 
 /* CG2D (model/src/cg2d.F:13-415).  resHist (may be NULL) receives sqrt(err_sq)
  * after each iteration; sumRHS/rhsMax are the values cg2d.F:199-200 prints. */

@@ -121,6 +121,13 @@ class Oracle:
                     cg2dNormaliseRHS=bool(op.cg2dNormaliseRHS))
         return arrs
 
+    def update_cg2d(self, op, updatePreCond=True):
+        """UPDATE_CG2D (update_cg2d.F:57-192) on the grid's CURRENT hFacW / hFacS: rewrites aW2d, aS2d, aC2d (and the
+        preconditioner when updatePreCond) of `op` in place; cg2dNorm and the tolerance stay."""
+        cop = self._op(op)
+        self.lib.og_update_cg2d(C.byref(self.g), C.byref(self.p), C.byref(cop), C.c_int(int(updatePreCond)))
+        return op
+
     def _op(self, op):
         return Cg2dOp(**{n: ptr(op[n]) for n in "aW2d aS2d aC2d pW pS pC".split()},
                       cg2dNorm=op["cg2dNorm"], cg2dTolerance_sq=op["cg2dTolerance_sq"],
