@@ -70,6 +70,7 @@ struct Cg2dArgs {
   Cg2dOut *out;
   double cg2dNorm, tolSq;
   int normaliseRHS, maxIters, nIterMinIn;
+  int l2mask;            // L2 eviction-priority classes of the vector phases (see L2Pol)
 };
 
 struct Cg2dWs {
@@ -467,6 +468,37 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 #endif
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 
+// L2 eviction priorities per vector class (createpolicy + ld/st .L2::cache_hint).  One iteration streams 14 vectors
+// (470 MB at 2048^2) through a 126 MB L2, so without hints nothing survives from one phase to the next.  With the
+// short-lived vectors (the non-resident parts of q and z, and x, which is read and rewritten in place every
+// iteration) marked evict_last and everything else evict_first, those stay in L2 and never travel to HBM.
+struct L2Pol {
+  unsigned long long qz, x, s, r, c;
+};
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  unsigned long long p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else p = 0ull;      // plain ld / st
+  return p;
+}
+__device__ __forceinline__ double2 ld2h(const double *p, unsigned long long pol) {
+  double2 v;
+  if (pol == 0ull) return ld2(p);
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ldg2h(const double *p, unsigned long long pol) {
+  double2 v;
+  if (pol == 0ull) return ldg2(p);
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st2h(double *p, double2 v, unsigned long long pol) {
+  if (pol == 0ull) { st2(p, v); return; }
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol));
+}
+
 __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j, double *f0, double2 v0, double *f1,
                                        double2 v1) {
   const int per = 2 * a.sNy + 2 * a.sNx;
@@ -488,7 +520,7 @@ template <int R>
 __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew,
                                         double beta, bool saveMin, double alphaPrev, bool updX, const Item2 &it, size_t idx,
                                         int j, double2 &tS, double2 &tC, double2 &aSj, double2 &sC, double &acc,
-                                        double *wb, bool zRes) {
+                                        double *wb, bool zRes, const L2Pol &pl) {
   const int PX = a.PX;
   double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R];
   double zW[R], sW[R], zE[R], sE[R], aWEl[R];
@@ -498,12 +530,12 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
     zN[r] = sN[r] = aSN[r] = aWv[r] = aCv[r] = xv[r] = make_double2(0.0, 0.0);
     zW[r] = sW[r] = zE[r] = sE[r] = aWEl[r] = 0.0;
     if (it.active) {
-      zN[r] = (zRes && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2(a.z + id + PX);
-      sN[r] = ld2(sOld + id + PX);
-      aSN[r] = ldg2(a.aS + id + PX);
-      aWv[r] = ldg2(a.aW + id);
-      aCv[r] = ldg2(a.aC + id);
-      if (saveMin || updX) xv[r] = ld2(a.x + id);
+      zN[r] = (zRes && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2h(a.z + id + PX, pl.qz);
+      sN[r] = ld2h(sOld + id + PX, pl.s);
+      aSN[r] = ldg2h(a.aS + id + PX, pl.c);
+      aWv[r] = ldg2h(a.aW + id, pl.c);
+      aCv[r] = ldg2h(a.aC + id, pl.c);
+      if (saveMin || updX) xv[r] = ld2h(a.x + id, pl.x);
       if (it.edgeW) { zW[r] = a.z[id - 1]; sW[r] = sOld[id - 1]; }
       if (it.edgeE) { zE[r] = a.z[id + 2]; sE[r] = sOld[id + 2]; aWEl[r] = __ldg(a.aW + id + 2); }
     }
@@ -521,14 +553,14 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
     double q1 = aWv[r].y * tC.x + aWE * tE + aSj.y * tS.y + aSN[r].y * tN.y + aCv[r].y * tC.y;
     if (it.active) {
       double2 qv = make_double2(q0, q1);
-      st2(sNew + id, tC);
+      st2h(sNew + id, tC, pl.s);
       const bool inRes = wb && j + r - it.j0 < a.resRows;
       if (inRes) st2(wb + (size_t)(j + r - it.j0) * 64, qv);   // q replaces the dead z of this row in the resident strip
-      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2(a.q + id, qv);   // neighbours read the rim
+      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2h(a.q + id, qv, pl.qz);   // neighbours read the rim
       push2v(a, it, j + r, sNew, tC, a.q, qv);
       if (updX) {   // deferred x += alpha s of the previous iteration (sC = old s of this row)
         xv[r] = make_double2(xv[r].x + alphaPrev * sC.x, xv[r].y + alphaPrev * sC.y);
-        st2(a.x + id, xv[r]);
+        st2h(a.x + id, xv[r], pl.x);
       }
       if (saveMin) st2(a.xmin + id, xv[r]);
       acc += tC.x * q0;
@@ -539,7 +571,7 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
 }
 
 __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew, double beta,
-                         bool saveMin, double alphaPrev, bool updX, double *sm, double *wb, bool zRes) {
+                         bool saveMin, double alphaPrev, bool updX, double *sm, double *wb, bool zRes, const L2Pol &pl) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -549,15 +581,15 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
     size_t idx = it.base;
     double2 tS = make_double2(0.0, 0.0), tC = tS, aSj = tS, sC = tS;
     if (it.active) {
-      double2 z0 = ld2(a.z + idx - PX), s0 = ld2(sOld + idx - PX), z1 = zRes ? ld2(wb) : ld2(a.z + idx), s1 = ld2(sOld + idx);
+      double2 z0 = ld2h(a.z + idx - PX, pl.qz), s0 = ld2h(sOld + idx - PX, pl.s), z1 = zRes ? ld2(wb) : ld2h(a.z + idx, pl.qz), s1 = ld2h(sOld + idx, pl.s);
       tS = make_double2(z0.x + beta * s0.x, z0.y + beta * s0.y);
       tC = make_double2(z1.x + beta * s1.x, z1.y + beta * s1.y);
-      aSj = ldg2(a.aS + idx);
+      aSj = ldg2h(a.aS + idx, pl.c);
       sC = s1;
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes);
-    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
+    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
   }
   block_partials<1, false>(a, acc, sm);
 }
@@ -565,7 +597,8 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
 template <int R>
 __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
                                          const double *__restrict__ sCur, double alpha, const Item2 &it, size_t idx,
-                                         int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH, double *wb) {
+                                         int j, double2 &rS, double2 &rC, double2 &pSj, double &accE, double &accH, double *wb,
+                                         const L2Pol &pl) {
   const int PX = a.PX;
   double2 rN[R], qN[R], pCv[R], pWv[R], pSN[R];
   double rW[R], qW[R], rE[R], qE[R], pWEl[R];
@@ -575,11 +608,11 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
     rN[r] = qN[r] = pCv[r] = pWv[r] = pSN[r] = make_double2(0.0, 0.0);
     rW[r] = qW[r] = rE[r] = qE[r] = pWEl[r] = 0.0;
     if (it.active) {
-      rN[r] = ld2(rOld + id + PX);
-      qN[r] = (wb && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2(a.q + id + PX);
-      pCv[r] = ldg2(a.pC + id);
-      pWv[r] = ldg2(a.pW + id);
-      pSN[r] = ldg2(a.pS + id + PX);
+      rN[r] = ld2h(rOld + id + PX, pl.r);
+      qN[r] = (wb && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2h(a.q + id + PX, pl.qz);
+      pCv[r] = ldg2h(a.pC + id, pl.c);
+      pWv[r] = ldg2h(a.pW + id, pl.c);
+      pSN[r] = ldg2h(a.pS + id + PX, pl.c);
       if (it.edgeW) { rW[r] = rOld[id - 1]; qW[r] = a.q[id - 1]; }
       if (it.edgeE) { rE[r] = rOld[id + 2]; qE[r] = a.q[id + 2]; pWEl[r] = __ldg(a.pW + id + 2); }
     }
@@ -597,10 +630,10 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
     double z1 = pCv[r].y * rC.y + pWv[r].y * rC.x + pWE * rEn + pSj.y * rS.y + pSN[r].y * rNn.y;
     if (it.active) {
       double2 zv = make_double2(z0, z1);
-      st2(rNew + id, rC);
+      st2h(rNew + id, rC, pl.r);
       const bool inRes = wb && j + r - it.j0 < a.resRows;
       if (inRes) st2(wb + (size_t)(j + r - it.j0) * 64, zv);   // z replaces the dead q of this row
-      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2(a.z + id, zv);
+      if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2h(a.z + id, zv, pl.qz);
       push2v(a, it, j + r, rNew, rC, a.z, zv);
       accE += rC.x * rC.x;
       accE += rC.y * rC.y;
@@ -612,7 +645,7 @@ __device__ __forceinline__ void ca2_rows(const Cg2dArgs &a, const double *__rest
 }
 
 __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, double *__restrict__ rNew,
-                          const double *__restrict__ sCur, double alpha, double *sm, double *wb) {
+                          const double *__restrict__ sCur, double alpha, double *sm, double *wb, const L2Pol &pl) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -627,14 +660,14 @@ __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, do
     size_t idx = it.base;
     double2 rS = make_double2(0.0, 0.0), rC = rS, pSj = rS;
     if (it.active) {
-      double2 r0 = ld2(rOld + idx - PX), q0 = ld2(a.q + idx - PX), r1 = ld2(rOld + idx), q1 = wb ? ld2(wb) : ld2(a.q + idx);
+      double2 r0 = ld2h(rOld + idx - PX, pl.r), q0 = ld2h(a.q + idx - PX, pl.qz), r1 = ld2h(rOld + idx, pl.r), q1 = wb ? ld2(wb) : ld2h(a.q + idx, pl.qz);
       rS = make_double2(r0.x - alpha * q0.x, r0.y - alpha * q0.y);
       rC = make_double2(r1.x - alpha * q1.x, r1.y - alpha * q1.y);
-      pSj = ldg2(a.pS + idx);
+      pSj = ldg2h(a.pS + idx, pl.c);
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) ca2_rows<2>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb);
-    if (j <= it.j1) ca2_rows<1>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) ca2_rows<2>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb, pl);
+    if (j <= it.j1) ca2_rows<1>(a, rOld, rNew, sCur, alpha, it, idx, j, rS, rC, pSj, acc[0], acc[1], wb, pl);
   }
   block_partials<2, false>(a, acc, sm);
 }
@@ -651,6 +684,14 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   double *wb = a.resident ? cg_wbuf + (size_t)(threadIdx.x >> 5) * a.resRows * 64 + 2 * (threadIdx.x & 31) : nullptr;
   double t1[1], t2[2];
   unsigned long long rseq = a.seq0;
+  // a.l2mask: bit 0 keep q/z, bit 1 keep x, bit 2 keep s, bit 3 keep r, bit 4 everything else evict_first
+  const int other = (a.l2mask & 16) ? 2 : 0;
+  L2Pol pl;
+  pl.qz = l2_policy((a.l2mask & 1) ? 1 : other);
+  pl.x = l2_policy((a.l2mask & 2) ? 1 : other);
+  pl.s = l2_policy((a.l2mask & 4) ? 1 : other);
+  pl.r = l2_policy((a.l2mask & 8) ? 1 : other);
+  pl.c = l2_policy(other);
 
   phase_scale_b(a, sm);
   grid.sync();
@@ -693,7 +734,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm, wb, wb != nullptr && it2d > 1);
+      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm, wb, wb != nullptr && it2d > 1, pl);
       else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
       saveMin = false;
       scur ^= 1;
@@ -702,7 +743,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
       const double alpha = eta_qrN / t1[0];
       sLast = a.s[scur];
       alphaLast = alpha;
-      if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm, wb);
+      if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm, wb, pl);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
       grid.sync();
@@ -1135,7 +1176,8 @@ static bool ensure_ws(int maxIters) {
       MG_CUDA(cudaMemset(w->block, 0, w->blockBytes));
     }
     double *p = w->block;
-    for (double **q : {&w->r[0], &w->r[1], &w->s[0], &w->s[1], &w->q, &w->z, &w->v, &w->xmin, &w->xw}) { *q = p; p += n2; }
+    // q, z and the x copy are adjacent: one L2 access-policy window can cover the three (MITGCM_B200_CG2D_L2WIN)
+    for (double **q : {&w->r[0], &w->r[1], &w->s[0], &w->s[1], &w->v, &w->xmin, &w->q, &w->z, &w->xw}) { *q = p; p += n2; }
     w->mail = reinterpret_cast<Mail *>(p);
     w->gtot = reinterpret_cast<double *>(reinterpret_cast<char *>(p) + mailBytes);
     w->gflag = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p) + mailBytes + totBytes);
@@ -1213,7 +1255,8 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   double *xUser = to_device(cg2d_x, g.n2, 1, true);
   if (!a.b || !xUser || !a.aW || !a.pC) return false;
   a.x = xUser;
-  if (w->nRanks > 1) {   // x needs halo pushes from the peers: iterate on the copy inside the shared block
+  const int l2win = getenv("MITGCM_B200_CG2D_L2WIN") ? atoi(getenv("MITGCM_B200_CG2D_L2WIN")) : 0;
+  if (w->nRanks > 1 || l2win) {   // x needs halo pushes from the peers: iterate on the copy inside the shared block
     MG_CUDA(cudaMemcpyAsync(w->xw, xUser, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     a.x = w->xw;
   }
@@ -1231,6 +1274,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   a.cg2dNorm = c.p.D(MP_CG2DNORM); a.tolSq = c.p.D(MP_CG2DTOLERANCE_SQ);
   a.normaliseRHS = c.p.I(MI_CG2DNORMALISERHS);
   a.maxIters = *numIters; a.nIterMinIn = *nIterMin;
+  a.l2mask = getenv("MITGCM_B200_CG2D_L2") ? atoi(getenv("MITGCM_B200_CG2D_L2")) : 0;
   // Work decomposition.  Warp items are column strips (32 columns scalar / 64 columns vector)
   // of RY rows; RY is chosen so that every co-resident warp gets one item of equal size
   // (balanced: no tail), but never fewer than 2 rows.
@@ -1277,6 +1321,24 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->v}) MG_CUDA(cudaMemsetAsync(p, 0, bytes, c.stream));
   static const int zero = 0;
   MG_CUDA(cudaMemcpyToSymbolAsync(g_cg2d_spin_error, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, c.stream));
+  if (l2win) {   // experiment: persisting L2 window over q, z and x (l2win = percent of the window that persists)
+    cudaDeviceProp pr;
+    MG_CUDA(cudaGetDeviceProperties(&pr, c.device));
+    static bool told = false;
+    if (!told) {
+      fprintf(stderr, "cg2d: persistingL2CacheMaxSize %d accessPolicyMaxWindowSize %d l2CacheSize %d\n", pr.persistingL2CacheMaxSize,
+              pr.accessPolicyMaxWindowSize, pr.l2CacheSize);
+      told = true;
+    }
+    MG_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pr.persistingL2CacheMaxSize));
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = w->q;
+    av.accessPolicyWindow.num_bytes = std::min<size_t>(3 * g.n2 * sizeof(double), (size_t)pr.accessPolicyMaxWindowSize);
+    av.accessPolicyWindow.hitRatio = std::min(1.0f, l2win / 100.0f);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    MG_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &av));
+  }
   void *args[] = {&a};
   c.launches++;
   MG_CUDA(cudaLaunchCooperativeKernel(sr ? (void *)cg2d_sr_kernel : (void *)cg2d_kernel, dim3(blocks), dim3(CG_THREADS),
@@ -1284,7 +1346,12 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   Cg2dOut out;
   MG_CUDA(cudaMemcpyAsync(&out, w->out, sizeof(out), cudaMemcpyDeviceToHost, c.stream));
   if (!from_device(cg2d_b, a.b, g.n2)) return false;
-  if (w->nRanks > 1) MG_CUDA(cudaMemcpyAsync(xUser, w->xw, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  if (l2win) {
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
+  if (w->nRanks > 1 || l2win) MG_CUDA(cudaMemcpyAsync(xUser, w->xw, g.n2 * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
   if (!from_device(cg2d_x, xUser, g.n2)) return false;
   MG_CUDA(cudaStreamSynchronize(c.stream));
   *firstResidual = out.firstResidual;

@@ -35,3 +35,8 @@ if __name__ == "__main__":
         with open(os.path.join(HERE, exp + ".json"), "w") as f:
             json.dump(parse(exp), f, indent=1)
         print("wrote", exp)
+    # secondary outputs of an experiment (results/output.<name>.txt)
+    for exp, name in (("advect_xy", "ab3_c4"),):
+        with open(os.path.join(HERE, f"{exp}.{name}.json"), "w") as f:
+            json.dump(parse(exp, f"results/output.{name}.txt"), f, indent=1)
+        print("wrote", exp, name)

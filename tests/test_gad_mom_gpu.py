@@ -179,3 +179,33 @@ def test_mom_rejects_bad_range(rt):
     with pytest.raises(rt.B200Error):
         rt.mom_fluxform(1, 1, 1, 1 - d.OLx, d.sNx + d.OLx, 0, 9, k3, k3, z.copy(), z.copy(), z.copy(), z.copy(),
                         z.copy(), z.copy(), z3, z3, z3, z3.copy(), z3.copy())
+
+
+def test_advect_xy_ab3_c4_golden_with_the_cuda_kernel(rt):
+    """verification/advect_xy input.ab3_c4 (scheme 4 + AB3, 100 steps) with gad_calc_rhs_b200_ in the loop: every
+    printed digit of %MON dynstat_theta_* / dynstat_salt_* at steps 10, ..., 100."""
+    import json
+    import os
+    from oracle import advect_xy as ax
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "advect_xy.ab3_c4.json")))
+    d, g, _, _ = ax.setup_ab3()
+    rt.init(d)
+    rt.set_grid(g)
+    calls = [0]
+
+    def cuda_rhs(bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld, uTrans, vTrans,
+                 rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB, deltaTLev, advScheme, vertAdvScheme,
+                 calcAdvection, implicitAdvection, applyAB_onTracer, trUseDiffKr4, fZon, fMer, fVerT, gTracer):
+        calls[0] += 1
+        rt.gad_calc_rhs(bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld, uTrans, vTrans,
+                        rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB, deltaTLev, 1, advScheme,
+                        vertAdvScheme, calcAdvection, implicitAdvection, applyAB_onTracer, trUseDiffKr4, 0, 0, 0, fZon, fMer,
+                        fVerT, gTracer)
+    out = ax.run_ab3(100, calc_rhs=cuda_rhs)
+    assert calls[0] == 100 * 2 * 2
+    for i, (t, s) in enumerate(out):
+        if i == 0:
+            continue
+        for r, fld in ((t, "theta"), (s, "salt")):
+            for st in ("max", "min", "mean", "sd"):
+                assert f"{r[st]:.13E}" == gold[f"dynstat_{fld}_{st}"][i], (i, fld, st)

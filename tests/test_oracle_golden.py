@@ -255,6 +255,35 @@ def test_advect_xy_is_independent_of_the_tiling():
 
 
 # ---------------------------------------------------------------------------------------
+# verification/advect_xy, input.ab3_c4 (results/output.ab3_c4.txt): tempAdvScheme = saltAdvScheme = 4 through
+# GAD_CALC_RHS (gad_c4_adv_{x,y}.F) with the third-order Adams-Bashforth scheme on the tendencies
+# (adams_bashforth3.F), 100 steps.  Pins scheme 4 and AB3.
+# ---------------------------------------------------------------------------------------
+def test_advect_xy_ab3_c4_statistics_every_printed_digit():
+    from oracle import advect_xy as ax
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "advect_xy.ab3_c4.json")))
+    out = ax.run_ab3(100)
+    assert len(out) == len(gold["dynstat_theta_sd"]) == 11          # steps 0, 10, ..., 100
+    for i, (t, s) in enumerate(out):
+        for r, fld in ((t, "theta"), (s, "salt")):
+            for st in ("max", "min", "mean", "sd"):
+                if fld == "theta" and st == "min" and i == 0:
+                    assert r[st] == pytest.approx(float(gold[f"dynstat_{fld}_{st}"][i]), rel=1e-12)      # 6.5e-28: EXP round-off
+                    continue
+                assert fmt(r[st], 13) == gold[f"dynstat_{fld}_{st}"][i], (i, fld, st)
+
+
+def test_ab3_start_up_factors():
+    """adams_bashforth3.F:66-83: forward step, then the two-level form, then the full three-level form."""
+    from oracle.advect_xy import ab3_factors
+    a, b = 0.5, 0.281105
+    assert ab3_factors(0, 0, 0, a, b) == (0.0, 0.0, 0.0)
+    assert ab3_factors(1, 0, 0, a, b) == (a, -a, 0.0)
+    assert ab3_factors(0, 0, 1, a, b) == (a, -a, 0.0)
+    assert ab3_factors(2, 0, 0, a, b) == (a + b, -a - 2.0 * b, b)
+
+
+# ---------------------------------------------------------------------------------------
 # verification/solid-body.cs-32x32x1: solid-body rotation of a one-layer atmosphere on the cs32 cube,
 # vectorInvariantMomentum = T.  Pins MOM_VECINV (relative vorticity with the three-cell facet corners,
 # KE gradient, vorticity advection, Coriolis) and GAD_CALC_RHS on the cube (passive salt), 25 steps.
