@@ -35,7 +35,7 @@ constexpr int MAX_PART = 2048;   // max CTAs in the cooperative grid
 struct Cg2dOut {
   double firstResidual, minResidualSq, lastResidual, sumRHS, rhsMax;
   int numIters, nIterMin, error;
-  unsigned long long seq;
+  unsigned long long seq, bseq;
 };
 
 // Cross-GPU reduction mailbox, "LL" style (flag travels inside the data word, as in NCCL's low-latency protocol):
@@ -66,6 +66,8 @@ struct Cg2dArgs {
   unsigned long long *gflag;
   unsigned long long seq0;  // reduction sequence number at kernel start
   double *partials;      // [4][MAX_PART]
+  Mail *ll;              // [2][4][MAX_PART] LL slots of the flag barrier / reduction; nullptr: grid.sync() + partials
+  unsigned long long bseq0;   // barrier sequence number at kernel start
   double *resid;         // per-iteration residual (sqrt(err_sq)), maxIters entries
   Cg2dOut *out;
   double cg2dNorm, tolSq;
@@ -84,7 +86,8 @@ struct Cg2dWs {
   int nRanks = 1, myRank = 0;
   void *peerBase[8] = {};        // peer mappings of every rank's block (own block for myRank)
   int nbrRank[5] = {0, 0, 0, 0, 0};
-  unsigned long long seq = 0;
+  unsigned long long seq = 0, bseq = 0;
+  Mail *ll = nullptr;
   double *partials = nullptr, *resid = nullptr;
   Cg2dOut *out = nullptr;
   int residCap = 0;
@@ -102,6 +105,7 @@ void cg2d_free_workspace() {
   for (double *p : {in_arena(w->block) ? nullptr : w->block, w->partials, w->resid})
     if (p) cudaFree(p);
   if (w->out) cudaFree(w->out);
+  if (w->ll) cudaFree(w->ll);
   delete w;
   c.cg2d = nullptr;
 }
@@ -164,7 +168,73 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
-// CTA-level reduction of up to 3 sums, written to partials[k][blockIdx.x].
+// ---- grid-wide barrier and reduction without cooperative_groups::grid.sync() -------------------------------------
+// Measured on B200 (296 CTAs): grid.sync() + "every CTA re-sums the per-CTA partials" costs about 5 us, and CG2D
+// needs two per iteration (10 of the 98 us of an iteration at 2048^2).  Here the barrier IS the reduction: every
+// CTA posts its partial sums as "LL" words (value halves with the sequence number in the upper 32 bits, as the
+// cross-GPU mailbox above) into its slot; every CTA then polls all slots.  Seeing CTA b's word with the current
+// sequence number means b has finished the phase (its stores were fenced before the post), so having all slots is
+// the grid barrier, and the slots are the operands of the ordered sum -- one L2 round trip instead of an atomic
+// counter, a spin, and a second pass over the partials.  Slots are double-buffered by the parity of the sequence
+// number: a CTA can only overwrite a slot two reductions later, after every reader has posted the one in between.
+// The launch is still cooperative (co-residency is what makes spinning safe).
+__shared__ unsigned long long cg_rseq_sh;      // number of the last completed reduction (uniform over the grid)
+__device__ int g_cg2d_spin_error = 0;
+#ifndef CG2D_LL_TIMEOUT_CYCLES
+#define CG2D_LL_TIMEOUT_CYCLES 6000000000LL      // about 3 s: a CTA that never arrives means a bug, not a slow peer
+#endif
+
+__device__ __forceinline__ void ll_post(Mail *slot, double v, unsigned long long seq) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v), flag = (seq & 0xffffffffull) << 32;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((bits & 0xffffffffull) | flag),
+               "l"((bits >> 32) | flag)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_try(const Mail *slot, unsigned long long seq, double &v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  const unsigned long long f = seq & 0xffffffffull;
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return (w0 >> 32) == f && (w1 >> 32) == f;
+}
+// the slots i = lane, lane + 32, ... < n of one value, accumulated in that order (4 polls in flight)
+template <bool MAXOP>
+__device__ __forceinline__ double ll_gather(const Mail *slots, int n, unsigned long long seq, int lane) {
+  double t = 0.0;
+  long long t0 = 0;
+  for (int i0 = lane; i0 < n; i0 += 128) {
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    bool ok[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) ok[m] = i0 + 32 * m >= n;
+    for (;;) {
+#pragma unroll
+      for (int m = 0; m < 4; m++)
+        if (!ok[m]) ok[m] = ll_try(slots + i0 + 32 * m, seq, p[m]);
+      if (ok[0] && ok[1] && ok[2] && ok[3]) break;
+      if (!t0) t0 = clock64();
+      else if (clock64() - t0 > CG2D_LL_TIMEOUT_CYCLES) { g_cg2d_spin_error = 3; break; }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+      if (i0 + 32 * m < n) t = MAXOP ? fmax(t, p[m]) : t + p[m];
+  }
+  return t;
+}
+
+// Local barrier without a reduction (slot 3 of the parity of its own counter).
+template <class Grid>
+__device__ __forceinline__ void grid_barrier(const Cg2dArgs &a, Grid &grid, unsigned long long &bseq) {
+  if (!a.ll) { grid.sync(); return; }
+  bseq++;
+  Mail *slots = a.ll + ((bseq & 1) * 4 + 3) * MAX_PART;
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); ll_post(slots + blockIdx.x, 0.0, bseq); }
+  if (threadIdx.x < 32) { (void)ll_gather<false>(slots, (int)gridDim.x, bseq, threadIdx.x); __threadfence(); }
+  __syncthreads();
+}
+
+// CTA-level reduction of up to 3 sums, posted to this CTA's slots (a.ll) / written to partials[k][blockIdx.x].
 template <int N, bool MAXOP>
 __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N], double *sm) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -183,7 +253,12 @@ __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N]
   if (threadIdx.x < N) {
     double t = sm[threadIdx.x * CG_WARPS];
     for (int i = 1; i < CG_WARPS; i++) t = MAXOP ? fmax(t, sm[threadIdx.x * CG_WARPS + i]) : t + sm[threadIdx.x * CG_WARPS + i];
-    a.partials[threadIdx.x * MAX_PART + blockIdx.x] = t;
+    if (a.ll) {
+      const unsigned long long seq = cg_rseq_sh + 1;      // the reduction this partial belongs to
+      __threadfence();      // release: everything the CTA stored in this phase (ordered before me by the barrier above)
+      ll_post(a.ll + ((seq & 1) * 4 + threadIdx.x) * MAX_PART + blockIdx.x, t, seq);
+    } else
+      a.partials[threadIdx.x * MAX_PART + blockIdx.x] = t;
   }
   __syncthreads();
 }
@@ -192,8 +267,8 @@ __device__ __forceinline__ void block_partials(const Cg2dArgs &a, double (&v)[N]
 // several ranks, CTA 0 then exchanges the rank totals through the peer-mapped mailboxes
 // (replaces the MPI_Allreduce of global_sum_tile.F:182) and publishes the rank-ordered sum.
 // rseq counts reductions; it is uniform across all threads of all ranks.
-// (zeroed by the host before every launch; a rank that times out reports error 71 and the caller must re-connect)
-__device__ int g_cg2d_spin_error = 0;
+// (g_cg2d_spin_error is zeroed by the host before every launch; a rank that times out reports error 71 and the caller
+// must re-connect)
 #ifndef CG2D_SPIN_LIMIT
 #define CG2D_SPIN_LIMIT (1LL << 31)
 #endif
@@ -205,10 +280,14 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
   if (a.nRanks == 1 || blockIdx.x == 0) {
     if (w < N) {
       double t = 0.0;
-      for (int i = lane; i < (int)gridDim.x; i += 32) {
-        double p = __ldcg(&a.partials[w * MAX_PART + i]);
-        t = MAXOP ? fmax(t, p) : t + p;
-      }
+      if (a.ll) {      // the gather is the grid barrier (see above)
+        t = ll_gather<MAXOP>(a.ll + ((rseq & 1) * 4 + w) * MAX_PART, (int)gridDim.x, rseq, lane);
+        __threadfence();      // acquire
+      } else
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+          double p = __ldcg(&a.partials[w * MAX_PART + i]);
+          t = MAXOP ? fmax(t, p) : t + p;
+        }
       t = MAXOP ? warp_max(t) : warp_sum(t);
       if (lane == 0) sm[w] = t;
     }
@@ -270,6 +349,7 @@ __device__ __forceinline__ void grid_totals(const Cg2dArgs &a, double (&tot)[N],
   }
 #pragma unroll
   for (int k = 0; k < N; k++) tot[k] = sm[k];
+  if (threadIdx.x == 0) cg_rseq_sh = rseq;
   __syncthreads();
 }
 
@@ -683,7 +763,9 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   extern __shared__ __align__(16) double cg_wbuf[];
   double *wb = a.resident ? cg_wbuf + (size_t)(threadIdx.x >> 5) * a.resRows * 64 + 2 * (threadIdx.x & 31) : nullptr;
   double t1[1], t2[2];
-  unsigned long long rseq = a.seq0;
+  unsigned long long rseq = a.seq0, bseq = a.bseq0;
+  if (threadIdx.x == 0) cg_rseq_sh = rseq;
+  __syncthreads();
   // a.l2mask: bit 0 keep q/z, bit 1 keep x, bit 2 keep s, bit 3 keep r, bit 4 everything else evict_first
   const int other = (a.l2mask & 16) ? 2 : 0;
   L2Pol pl;
@@ -694,7 +776,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   pl.c = l2_policy(other);
 
   phase_scale_b(a, sm);
-  grid.sync();
+  if (!a.ll) grid.sync();
   grid_totals<1, true>(a, t1, sm, rseq);
   const double rhsMax = t1[0];
   double rhsNorm = 1.0;
@@ -703,12 +785,12 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
   if (a.nRanks > 1) {   // the peers' x-edge pushes must have landed before the residual reads the halo:
     double dummy[1] = {0.0};   // a cross-rank reduction doubles as the barrier
     block_partials<1, true>(a, dummy, sm);
-    grid.sync();
+    if (!a.ll) grid.sync();
     grid_totals<1, true>(a, t1, sm, rseq);
   }
-  grid.sync();
+  grid_barrier(a, grid, bseq);
   phase_residual(a, sm);
-  grid.sync();
+  if (!a.ll) grid.sync();
   grid_totals<2, false>(a, t2, sm, rseq);
   double err_sq = t2[0];
   const double sumRHS = t2[1];
@@ -728,7 +810,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     phase_ca(a, a.r[0], a.r[1], a.s[0], 0.0, true, sm);
     cur = 1;   // r[1] now holds r (with halos); s[0] is the (zero) current s
     int scur = 0;
-    grid.sync();
+    if (!a.ll) grid.sync();
     grid_totals<2, false>(a, t2, sm, rseq);
     double eta_qrN = t2[1];
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
@@ -738,7 +820,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
       else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
       saveMin = false;
       scur ^= 1;
-      grid.sync();
+      if (!a.ll) grid.sync();
       grid_totals<1, false>(a, t1, sm, rseq);
       const double alpha = eta_qrN / t1[0];
       sLast = a.s[scur];
@@ -746,7 +828,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
       if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm, wb, pl);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
-      grid.sync();
+      if (!a.ll) grid.sync();
       grid_totals<2, false>(a, t2, sm, rseq);
       err_sq = t2[0];
       eta_qrN = t2[1];
@@ -773,6 +855,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
     a.out->numIters = actualIts;
     a.out->nIterMin = nIterMin;
     a.out->seq = rseq;
+    a.out->bseq = bseq;
     a.out->error = *reinterpret_cast<volatile int *>(&g_cg2d_spin_error);
   }
 }
@@ -1062,11 +1145,13 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   double t1[1], t2[2], t3[3];
-  unsigned long long rseq = a.seq0;
+  unsigned long long rseq = a.seq0, bseq = a.bseq0;
+  if (threadIdx.x == 0) cg_rseq_sh = rseq;
+  __syncthreads();
   double *r = a.r[0], *y = a.z, *s = a.s[0];
 
   phase_scale_b(a, sm);
-  grid.sync();
+  if (!a.ll) grid.sync();
   grid_totals<1, true>(a, t1, sm, rseq);
   const double rhsMax = t1[0];
   double rhsNorm = 1.0;
@@ -1075,12 +1160,12 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
   if (a.nRanks > 1) {   // the peers' x-edge pushes must have landed before the residual reads the halo:
     double dummy[1] = {0.0};   // a cross-rank reduction doubles as the barrier
     block_partials<1, true>(a, dummy, sm);
-    grid.sync();
+    if (!a.ll) grid.sync();
     grid_totals<1, true>(a, t1, sm, rseq);
   }
-  grid.sync();
+  grid_barrier(a, grid, bseq);
   phase_residual(a, sm);
-  grid.sync();
+  if (!a.ll) grid.sync();
   grid_totals<2, false>(a, t2, sm, rseq);
   double err_sq = t2[0];
   const double sumRHS = t2[1];
@@ -1094,23 +1179,23 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
   if (!(err_sq < a.tolSq)) {
     // start-up iteration, cg2d_sr.F:220-291
     if (a.vec2) sr_phase_y2(a, r, y, s, sm, true); else sr_phase_y(a, r, y, s, sm, true);
-    grid.sync();
+    if (!a.ll) grid.sync();
     grid_totals<1, false>(a, t1, sm, rseq);
     double eta_qrN = t1[0];
     double eta_qrNM1 = eta_qrN;
     if (a.vec2) sr_phase_as2(a, s, sm); else sr_phase_as(a, s, sm);
-    grid.sync();
+    if (!a.ll) grid.sync();
     grid_totals<1, false>(a, t1, sm, rseq);
     double alpha = t1[0];
     double sigma = eta_qrN / alpha;
     if (a.vec2) sr_phase_update2(a, r, 0.0, sigma, true, false); else sr_phase_update(a, r, 0.0, sigma, true, false);
-    grid.sync();
+    grid_barrier(a, grid, bseq);
     bool converged = false;
     for (it2d = 1; it2d <= a.maxIters - 1; it2d++) {
       if (a.vec2) sr_phase_y2(a, r, y, nullptr, sm, false); else sr_phase_y(a, r, y, nullptr, sm, false);
-      grid.sync();
+      grid_barrier(a, grid, bseq);
       if (a.vec2) sr_phase_v2(a, y, r, sm); else sr_phase_v(a, y, r, sm);
-      grid.sync();
+      if (!a.ll) grid.sync();
       grid_totals<3, false>(a, t3, sm, rseq);
       eta_qrN = t3[0];
       const double delta = t3[1];
@@ -1124,11 +1209,11 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
       alpha = delta - (cgBeta * cgBeta) * alpha;
       sigma = eta_qrN / alpha;
       if (a.vec2) sr_phase_update2(a, r, cgBeta, sigma, false, saveMin); else sr_phase_update(a, r, cgBeta, sigma, false, saveMin);
-      grid.sync();
+      grid_barrier(a, grid, bseq);
     }
     if (!converged) {
       sr_phase_err(a, r, sm);
-      grid.sync();
+      if (!a.ll) grid.sync();
       grid_totals<1, false>(a, t1, sm, rseq);
       err_sq = t1[0];
     }
@@ -1144,6 +1229,7 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a
     a.out->numIters = it2d;
     a.out->nIterMin = nIterMin;
     a.out->seq = rseq;
+    a.out->bseq = bseq;
     a.out->error = *reinterpret_cast<volatile int *>(&g_cg2d_spin_error);
   }
 }
@@ -1161,6 +1247,7 @@ static bool ensure_ws(int maxIters) {
         for (double *p : {in_arena(w->block) ? nullptr : w->block, w->partials})
           if (p) cudaFree(p);
         if (w->out) cudaFree(w->out);
+        if (w->ll) cudaFree(w->ll);
         delete w;
       }
     } guard{new Cg2dWs()};
@@ -1183,6 +1270,8 @@ static bool ensure_ws(int maxIters) {
     w->gflag = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p) + mailBytes + totBytes);
     w->peerBase[0] = w->block;
     MG_CUDA(cudaMalloc(&w->partials, 4 * MAX_PART * sizeof(double)));
+    MG_CUDA(cudaMalloc(&w->ll, 2 * 4 * MAX_PART * sizeof(Mail)));
+    MG_CUDA(cudaMemset(w->ll, 0, 2 * 4 * MAX_PART * sizeof(Mail)));
     MG_CUDA(cudaMalloc(&w->out, sizeof(Cg2dOut)));
     int nb = 0;
     MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg2d_kernel, CG_THREADS, 0));
@@ -1234,6 +1323,8 @@ bool cg2d_comm_wire() {
   MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
   // a fresh connection starts the reduction sequence over on every rank (also the recovery path after error 71)
   w->seq = 0;
+  w->bseq = 0;
+  MG_CUDA(cudaMemset(w->ll, 0, 2 * 4 * MAX_PART * sizeof(Mail)));
   MG_CUDA(cudaMemset(w->mail, 0, sizeof(Mail) * MAIL_SLOTS));
   MG_CUDA(cudaMemset(w->gflag, 0, 64));
   return true;
@@ -1270,6 +1361,16 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
     a.peerDelta[sl] = reinterpret_cast<char *>(w->peerBase[w->nbrRank[sl]]) - reinterpret_cast<char *>(w->block);
   a.r[0] = w->r[0]; a.r[1] = w->r[1]; a.s[0] = w->s[0]; a.s[1] = w->s[1];
   a.q = w->q; a.z = w->z; a.xmin = w->xmin; a.v = w->v;
+  // flag barrier / reduction (see grid_barrier) where it was measured faster: large tiles, where CTAs arrive spread out
+  // and the gather overlaps the wait (2048^2: 95.3 vs 98.0 us/iteration, CG2D_SR 143.8 vs 158.6); on small tiles all
+  // CTAs arrive together and grid.sync()'s single counter is cheaper (1024^2: 28.8 vs 25.8, 256^2: 12.4 vs 9.8).
+  // MITGCM_B200_CG2D_COOPSYNC=1 / 0 forces grid.sync() / the flags.
+  {
+    const char *e = getenv("MITGCM_B200_CG2D_COOPSYNC");
+    const bool flags = e ? atoi(e) == 0 : (g.n2 >= (size_t)3 << 20);
+    a.ll = flags ? w->ll : nullptr;
+  }
+  a.bseq0 = w->bseq;
   a.pushTab = c.pushTab; a.partials = w->partials; a.resid = w->resid; a.out = w->out;
   a.cg2dNorm = c.p.D(MP_CG2DNORM); a.tolSq = c.p.D(MP_CG2DTOLERANCE_SQ);
   a.normaliseRHS = c.p.I(MI_CG2DNORMALISERHS);
@@ -1363,6 +1464,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   w->rhsMax = out.rhsMax;
   w->lastIters = out.numIters;
   w->seq = out.seq;
+  w->bseq = out.bseq;
   if (out.error) return fail(71, "cg2d: timed out waiting for a peer rank");
   return true;
 }

@@ -188,7 +188,7 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   if (!build_push_tables()) return;
   c.nRanks = g.nPx * g.nPy;
   c.myRank = g.myPx + g.nPx * g.myPy;
-  c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false;
+  c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false; c.attrDynTmaUV = 0;
   if (c.nRanks > 1) {
     // peer arena: header (flags) + 7 tile3d + 4 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)
     // + the two strip buffers of halo.cu: (2 OLx sNy + 4 OLx OLy) x (4 Nr + 4) doubles each

@@ -60,7 +60,7 @@ struct Ctx {
   int nRanks = 1, myRank = 0;
   struct HaloWs *halo = nullptr;
   // function attributes (dynamic shared memory opt-in) are per device: set once per init
-  bool attrDyn = false, attrThermo = false, attrVi = false, attrDynTma = false;
+  bool attrDyn = false, attrThermo = false, attrVi = false, attrDynTma = false; int attrDynTmaUV = 0;
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;

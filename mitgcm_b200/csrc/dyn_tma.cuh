@@ -33,12 +33,14 @@ struct DynTmaStage {
   double patch[DP_NPATCH][DT_PATCH_D];
   double own[DO_NOWN][DT_OWN_D];
 };
-struct DynTmaSmem {
-  DynTmaStage st[2];
+template <int NST>
+struct DynTmaSmemN {
+  DynTmaStage st[NST];
   double uT[FT_N], vT[FT_N], wA[FT_N], hZ[FT_N], mCk[FT_N], dyG[FT_N], dxG[FT_N], rA[FT_N];
   VertSmem vs;
-  uint64_t full[2];
+  uint64_t full[NST];
 };
+typedef DynTmaSmemN<2> DynTmaSmem;
 struct DynTmaMaps {
   CUtensorMap u, v, hW, hS, hC, w, mC, phi;      // box 34 x 10 x 1
   CUtensorMap kU, kV, rhW, rhS, guO, gvO, mW, mS;   // box 34 x 8 x 1
@@ -326,6 +328,280 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
     uKm1 = uK; uK = uKp1; vKm1 = vK; vK = vKp1; mWk = mWkp1; mSk = mSkp1;
     (void)uKm1; (void)vKm1;
   }
+}
+
+// ---- role-split variant: 512 threads, warps 0-7 compute the U tendency, warps 8-15 the V tendency ----------------
+// dyn_tma_kernel is issue-bound at 4 warps per scheduler (128 registers x 256 threads x 2 CTAs fill the register
+// file; ncu: 25 % warps active, 36 % issue-active, FP64 pipe 32 %).  Splitting the two momentum components over two
+// thread groups of the SAME CTA halves what a thread has to keep alive (k-invariant metrics, carried vertical
+// fluxes, own-column operands): twice the warps on the same staged shared memory, same TMA traffic, same
+// expressions (bit-identical output; tests/test_step_gpu.py).  The component is a template parameter of the level
+// loop (ROLE 0: U, 1: V), so array choices and neighbour offsets are immediates, not selects: the first version with
+// a run-time role spent 22 % of its instructions on IMAD / ISETP / FSEL (profiles/r02_dyn_tma_uv_kernel_*.txt).
+// NST = depth of the TMA ring (2: two CTAs per SM; 3-5: one CTA per SM with NST - 1 levels in flight).
+__device__ __forceinline__ void dyn_uv_bar() { asm volatile("bar.sync 1, %0;" ::"n"(2 * FT_X * FT_Y) : "memory"); }
+
+template <int NST, int ROLE>
+__device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTmaMaps &maps, const TileGrid &g, const MomState &st,
+                                              const MomPar &p, const double *__restrict__ sf, double *__restrict__ gOut,
+                                              double *__restrict__ gNm1, double deltaTMom, double abFac, int momForcing,
+                                              int dissInAB, int hasPhi, int t, int i, int j, bool active, bool hzok, int c,
+                                              int co, int x0, int y0) {
+  constexpr int dP = ROLE ? FT_W : 1;              // patch offset towards "my" neighbour: west for U, south for V
+  constexpr int P_F = ROLE ? DP_V : DP_U, O_M = ROLE ? DO_MS : DO_MW, O_K = ROLE ? DO_KV : DO_KU;
+  constexpr int O_RH = ROLE ? DO_RHS : DO_RHW, O_G = ROLE ? DO_GVO : DO_GUO;
+  const size_t s = active ? g.s(i, j) : g.s(0, 0);
+  const int PX = g.PX;
+  const int dn = ROLE ? PX : 1;
+  // U: dyF00, dyFm0, rdxF00, rdxFm0, dxV00, dxV01, rdyU00, rdyU01;  V: dxF00, dxF0m, rdyF00, rdyF0m, dyU00, dyU10, rdxV00, rdxV10
+  const double r_rA = ROLE ? g.recip_rAs[s] : g.recip_rAw[s], rAx = ROLE ? g.rAs[s] : g.rAw[s];
+  const double mA0 = ROLE ? g.dxF[s] : g.dyF[s], mA1 = ROLE ? g.dxF[s - PX] : g.dyF[s - 1];
+  const double mB0 = ROLE ? g.recip_dyF[s] : g.recip_dxF[s], mB1 = ROLE ? g.recip_dyF[s - PX] : g.recip_dxF[s - 1];
+  const double mC0 = ROLE ? g.dyU[s] : g.dxV[s], mC1 = ROLE ? g.dyU[s + 1] : g.dxV[s + PX];
+  const double mD0 = ROLE ? g.recip_dxV[s] : g.recip_dyU[s], mD1 = ROLE ? g.recip_dxV[s + 1] : g.recip_dyU[s + PX];
+  const int jc = j + g.OLy - 1 < g.PY ? j + g.OLy - 1 : 0;
+  const double cf = ROLE ? g.cosFacV[jc] : g.cosFacU[jc];
+  const double fC00 = g.fCori[s], fCn = g.fCori[s - dn];
+  const double uDudxFac = p.afFacMom, AhFac = p.vfFacMom, ArFac = p.implicitViscosity ? 0. : p.vfFacMom;
+  const double gp = ROLE ? ((hasPhi && j >= 1) ? g.recip_dyC[s] : 0.) : ((hasPhi && i >= 1) ? g.recip_dxC[s] : 0.);
+  const size_t slab = g.slab;
+  const double *__restrict__ fCol = (ROLE ? st.v : st.u) + s;      // own column of my component, advanced level by level
+  const bool forcRange = ROLE ? (j >= 1 && j <= g.sNy + 1) : (i >= 1 && i <= g.sNx + 1);
+  mbar_wait(&sm.full[0], 0);
+  mbar_wait(&sm.full[1], 0);
+  unsigned ph = 3;
+  double fK = sm.st[1].patch[P_F][c];
+  double mk = sm.st[0].own[O_M][co];
+  if (t < FT_N) sm.wA[t] = sm.st[0].patch[DP_W][t] * sm.rA[t];
+  dyn_uv_bar();
+  double fkm = 0.;
+  if (!p.rigidLid) fkm = (0.5 * (sm.wA[c - dP] + sm.wA[c])) * fK;
+  double fVrUp = 0.;
+  dyn_uv_bar();
+  int rb = 0;                       // ring slot of level k; rp = slot of level k-1 (freed after the derive phase)
+  for (int k = 1; k <= g.Nr; k++) {
+    const int rp = rb;
+    rb = rb + 1 == NST ? 0 : rb + 1;
+    const DynTmaStage &S = sm.st[rb];
+    const double *__restrict__ mCk1 = sm.st[rp].patch[DP_MC];
+    const double drFk = sm.vs.drF[k - 1], rdrF = sm.vs.rdrF[k - 1];
+    const bool below = k + 1 <= g.Nr;
+    double fKp1 = 0.;
+    if (below) fKp1 = fCol[slab];
+    fCol += slab;
+    if (k > 1) {
+      mbar_wait(&sm.full[rb], (ph >> rb) & 1);
+      ph ^= 1u << rb;
+      dyn_uv_bar();      // every thread is done with the derived arrays of level k-1
+    }
+    if (t < FT_N) {
+      const int e = t;
+      const double hW = S.patch[DP_HW][e], hS = S.patch[DP_HS][e];
+      sm.uT[e] = S.patch[DP_U][e] * (sm.dyG[e] * drFk * hW);
+      sm.vT[e] = S.patch[DP_V][e] * (sm.dxG[e] * drFk * hS);
+      if (below) sm.wA[e] = S.patch[DP_W][e] * sm.rA[e];
+      sm.mCk[e] = mCk1[e];
+      if (hzok) {
+        const double hWs = S.patch[DP_HW][e - FT_W], hSw = S.patch[DP_HS][e - 1];
+        double h = hW < hWs ? hW : hWs;
+        h = hS < h ? hS : h;
+        h = hSw < h ? hSw : h;
+        sm.hZ[e] = h;
+      }
+    }
+    dyn_uv_bar();      // derived arrays visible; slot rp (level k-1) is no longer read by anybody
+    if (t == 0 && k + NST - 1 <= g.Nr) dyn_tma_issue(maps, sm.st[rp], &sm.full[rp], x0, y0, k + NST - 1, g.Nr, hasPhi != 0);
+    const double mkp1 = below ? S.own[O_M][co] : 0.;
+    const double kapkp1 = S.own[O_K][co];
+    if (active) {
+#define PU(di, dj) S.patch[DP_U][c + (dj)*FT_W + (di)]
+#define PV(di, dj) S.patch[DP_V][c + (dj)*FT_W + (di)]
+#define PHC(di, dj) S.patch[DP_HC][c + (dj)*FT_W + (di)]
+#define PMC1(di, dj) S.patch[DP_MC][c + (dj)*FT_W + (di)]
+#define DUT(di, dj) sm.uT[c + (dj)*FT_W + (di)]
+#define DVT(di, dj) sm.vT[c + (dj)*FT_W + (di)]
+#define DHZ(di, dj) sm.hZ[c + (dj)*FT_W + (di)]
+#define DWA(di, dj) sm.wA[c + (dj)*FT_W + (di)]
+#define DMC(di, dj) sm.mCk[c + (dj)*FT_W + (di)]
+      const double rh = S.own[O_RH][co];
+      const double gOld = S.own[O_G][co];
+      double dp = 0.;
+      if (hasPhi) dp = gp * 1. * (S.patch[DP_PHI][c] - S.patch[DP_PHI][c - dP]) * 1.;
+      double fkp = 0.;
+      if (below) {      // vertical advective flux at interface k+1 (MOM_U_ADV_WU / MOM_V_ADV_WV)
+        const double wA00 = DWA(0, 0), wAn = sm.wA[c - dP];
+        const double rT = 0.5 * (wAn + wA00);
+        fkp = rT * 0.5 * (fKp1 + fK);
+        if (!p.rigidLid) {
+          const double d00 = PMC1(0, 0) - DMC(0, 0);
+          fkp = fkp + 0.25 * (wA00 * d00 + wAn * (S.patch[DP_MC][c - dP] - sm.mCk[c - dP])) * fKp1;
+        }
+      }
+      double gt, gD;
+      if (ROLE == 0) {
+        const double u00 = PU(0, 0), uE = PU(1, 0), uW = PU(-1, 0), uN = PU(0, 1), uS = PU(0, -1);
+        {
+          const double uT00 = DUT(0, 0);
+          const double fzU1 = 0.25 * (uT00 + DUT(1, 0)) * (u00 + uE);
+          const double fzU0 = 0.25 * (DUT(-1, 0) + uT00) * (uW + u00);
+          const double fmU1 = 0.25 * (DVT(0, 1) + DVT(-1, 1)) * (uN + u00);
+          const double fmU0 = 0.25 * (DVT(0, 0) + DVT(-1, 0)) * (u00 + uS);
+          gt = -rh * rdrF * r_rA * ((fzU1 - fzU0) * uDudxFac + (fmU1 - fmU0) * uDudxFac + (fkp - fkm) * p.rkSign * uDudxFac);
+        }
+        {
+          const double hZ00 = DHZ(0, 0), hZ01 = DHZ(0, 1);
+          const double xv1 = mA0 * drFk * PHC(0, 0) * (-p.viscAhD * (uE - u00) * cf) * mB0;
+          const double xv0 = mA1 * drFk * PHC(-1, 0) * (-p.viscAhD * (u00 - uW) * cf) * mB1;
+          const double yv1 = mC1 * drFk * hZ01 * (-p.viscAhZ * (uN - u00)) * mD1;
+          const double yv0 = mC0 * drFk * hZ00 * (-p.viscAhZ * (u00 - uS)) * mD0;
+          double fVrDw = 0.;
+          if (!p.implicitViscosity && below) fVrDw = -kapkp1 * rAx * (fKp1 - fK) * p.rkSign * sm.vs.rdrC[k] * mkp1 * mk;
+          gD = -rh * rdrF * r_rA * ((xv1 - xv0) * AhFac + (yv1 - yv0) * AhFac + (fVrDw - fVrUp) * p.rkSign * ArFac);
+          fVrUp = fVrDw;
+          if (p.no_slip_sides) {
+            const double hWc = S.patch[DP_HW][c];
+            const double tu = p.viscAhZ * u00;
+            gD = gD + (-rh * rdrF * r_rA * ((hWc - hZ00) * mC0 * mD0 * tu + (hWc - hZ01) * mC1 * mD1 * tu) * drFk * p.sideDragFactor);
+          }
+          if (p.bottomDragTerms) {
+            const double viscFac = p.no_slip_bottom ? 2. : 0.;
+            const double recDrC = (k == g.Nr) ? rdrF : sm.vs.rdrC[k];
+            double cu = p.bottomDragLinear * 1.;
+            if (p.no_slip_bottom && p.bottomVisc_pCell) cu = cu + kapkp1 * recDrC * viscFac * rh;
+            else if (p.no_slip_bottom) cu = cu + kapkp1 * recDrC * viscFac;
+            if (k == g.Nr) cu = cu * mk;
+            else cu = cu * mk * (1. - mkp1);
+            gD = gD - cu * u00 * rh * rdrF;
+          }
+        }
+        if (!p.useCDscheme) {
+          const double v00 = PV(0, 0), vN = PV(0, 1), vW = PV(-1, 0);
+          double uCf;
+          if (p.selectCoriScheme >= 2) uCf = 0.5 * (fC00 * 0.5 * (v00 + vN) + fCn * 0.5 * (vW + PV(-1, 1)));
+          else uCf = 0.5 * (fC00 + fCn) * 0.25 * (v00 + vN + vW + PV(-1, 1));
+          gt = gt + p.cfFacMom * uCf;
+        }
+      } else {
+        const double v00 = PV(0, 0), vE = PV(1, 0), vW = PV(-1, 0), vN = PV(0, 1), vS = PV(0, -1);
+        {
+          const double vT00 = DVT(0, 0);
+          const double fzV1 = 0.25 * (DUT(1, 0) + DUT(1, -1)) * (vE + v00);
+          const double fzV0 = 0.25 * (DUT(0, 0) + DUT(0, -1)) * (v00 + vW);
+          const double fmV1 = 0.25 * (vT00 + DVT(0, 1)) * (v00 + vN);
+          const double fmV0 = 0.25 * (DVT(0, -1) + vT00) * (vS + v00);
+          gt = -rh * rdrF * r_rA * ((fzV1 - fzV0) * uDudxFac + (fmV1 - fmV0) * uDudxFac + (fkp - fkm) * p.rkSign * uDudxFac);
+        }
+        {
+          const double hZ00 = DHZ(0, 0), hZ10 = DHZ(1, 0);
+          const double xw1 = mC1 * drFk * hZ10 * (-p.viscAhZ * (vE - v00) * cf) * mD1;
+          const double xw0 = mC0 * drFk * hZ00 * (-p.viscAhZ * (v00 - vW) * cf) * mD0;
+          const double yw1 = mA0 * drFk * PHC(0, 0) * (-p.viscAhD * (vN - v00)) * mB0;
+          const double yw0 = mA1 * drFk * PHC(0, -1) * (-p.viscAhD * (v00 - vS)) * mB1;
+          double gVrDw = 0.;
+          if (!p.implicitViscosity && below) gVrDw = -kapkp1 * rAx * (fKp1 - fK) * p.rkSign * sm.vs.rdrC[k] * mkp1 * mk;
+          gD = -rh * rdrF * r_rA * ((xw1 - xw0) * AhFac + (yw1 - yw0) * AhFac + (gVrDw - fVrUp) * p.rkSign * ArFac);
+          fVrUp = gVrDw;
+          if (p.no_slip_sides) {
+            const double hSc = S.patch[DP_HS][c];
+            const double tv = p.viscAhZ * v00 * cf;
+            gD = gD + (-rh * rdrF * r_rA * ((hSc - hZ00) * mC0 * mD0 * tv + (hSc - hZ10) * mC1 * mD1 * tv) * drFk * p.sideDragFactor);
+          }
+          if (p.bottomDragTerms) {
+            const double viscFac = p.no_slip_bottom ? 2. : 0.;
+            const double recDrC = (k == g.Nr) ? rdrF : sm.vs.rdrC[k];
+            double cv = p.bottomDragLinear * 1.;
+            if (p.no_slip_bottom && p.bottomVisc_pCell) cv = cv + kapkp1 * recDrC * viscFac * rh;
+            else if (p.no_slip_bottom) cv = cv + kapkp1 * recDrC * viscFac;
+            if (k == g.Nr) cv = cv * mk;
+            else cv = cv * mk * (1. - mkp1);
+            gD = gD - cv * v00 * rh * rdrF;
+          }
+        }
+        if (!p.useCDscheme) {
+          const double u00 = PU(0, 0), uE = PU(1, 0), uS = PU(0, -1);
+          double vCf;
+          if (p.selectCoriScheme >= 2) vCf = -0.5 * (fC00 * 0.5 * (u00 + uE) + fCn * 0.5 * (uS + PU(1, -1)));
+          else vCf = -0.5 * (fC00 + fCn) * 0.25 * (u00 + uE + uS + PU(1, -1));
+          gt = gt + p.cfFacMom * vCf;
+        }
+      }
+      gt = gt * mk; gD = gD * mk;      // mom_fluxform.F:1044-1051
+      gt = gt - 1. * dp;               // timestep.F:120-121, phFac = pfFacMom = 1
+      if (dissInAB) gt = gt + gD;
+      if (momForcing) {
+        double ge = 0.;
+        if (k == 1 && forcRange) ge = 0. + sf[s] * sm.vs.rdrF[0] * rh;
+        gt = gt + ge;
+      }
+      const size_t s3 = s + slab * (size_t)(k - 1);
+      const double ab = abFac * (gt - gOld);
+      gNm1[s3] = gt;
+      gt = gt + ab;
+      if (!dissInAB) gt = gt + gD;
+      gOut[s3] = fK + deltaTMom * (gt + 0.) * mk;
+      fkm = fkp;
+#undef PU
+#undef PV
+#undef PHC
+#undef PMC1
+#undef DUT
+#undef DVT
+#undef DHZ
+#undef DWA
+#undef DMC
+    }
+    fK = fKp1; mk = mkp1;
+  }
+}
+
+template <int NST, int MINB>
+__global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
+    dyn_tma_uv_kernel(const __grid_constant__ DynTmaMaps maps, TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU,
+                      const double *__restrict__ sfV, double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
+                      double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB, int hasPhi) {
+  extern __shared__ __align__(1024) unsigned char dyn_tma_smem_raw[];
+  DynTmaSmemN<NST> &sm = *reinterpret_cast<DynTmaSmemN<NST> *>(dyn_tma_smem_raw);
+  constexpr int NT = 2 * FT_X * FT_Y;
+  const int tx = threadIdx.x, ty = threadIdx.y, role = threadIdx.z;      // role 0: U, role 1: V (warp-uniform)
+  const int t = (role * FT_Y + ty) * FT_X + tx;
+  const int i0 = blockIdx.x * FT_X, j0 = blockIdx.y * FT_Y;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool active = i <= g.sNx + 1 && j <= g.sNy + 1;
+  const int c = (ty + 1) * FT_W + (tx + 1);
+  const int co = ty * DT_OWN_W + (tx + 1);
+  const int x0 = i0 - 1 + g.OLx - 1, y0 = j0 - 1 + g.OLy - 1;
+  if (t == 0) {
+#pragma unroll
+    for (int q = 0; q < NST; q++) mbar_init(&sm.full[q], 1);
+    mbar_fence_init();
+  }
+  stage_vert(sm.vs, g, t, NT);
+  bool hzok = false;
+  if (t < FT_N) {
+    const int li = t % FT_W, lj = t / FT_W;
+    hzok = li >= 1 && lj >= 1;
+    const int gi = min(i0 - 1 + li, g.sNx + g.OLx), gj = min(j0 - 1 + lj, g.sNy + g.OLy);
+    const size_t q = g.s(gi, gj);
+    sm.dyG[t] = g.dyG[q]; sm.dxG[t] = g.dxG[q]; sm.rA[t] = g.rA[q];
+  }
+  __syncthreads();
+  if (t == 0) {
+    mbar_expect_tx(&sm.full[0], 2 * DT_PATCH_BYTES + 2 * DT_OWN_BYTES);
+    tma_load3(sm.st[0].patch[DP_W], &maps.w, x0, y0, 0, &sm.full[0]);
+    tma_load3(sm.st[0].patch[DP_MC], &maps.mC, x0, y0, 0, &sm.full[0]);
+    tma_load3(sm.st[0].own[DO_MW], &maps.mW, x0, y0 + 1, 0, &sm.full[0]);
+    tma_load3(sm.st[0].own[DO_MS], &maps.mS, x0, y0 + 1, 0, &sm.full[0]);
+#pragma unroll
+    for (int q = 1; q < NST; q++)
+      if (q <= g.Nr) dyn_tma_issue(maps, sm.st[q], &sm.full[q], x0, y0, q, g.Nr, hasPhi != 0);
+  }
+  // the two components run the same level loop, compiled once per component; both sides meet at the named barrier
+  if (role == 0)
+    dyn_uv_levels<NST, 0>(sm, maps, g, st, p, sfU, gU, guNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
+                          c, co, x0, y0);
+  else
+    dyn_uv_levels<NST, 1>(sm, maps, g, st, p, sfV, gV, gvNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
+                          c, co, x0, y0);
 }
 
 // The TMA path additionally needs both horizontal terms on and a 16-byte row pitch.

@@ -633,6 +633,28 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
             MG_CUDA(cudaFuncSetAttribute(dyn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
             c.attrDynTma = true;
           }
+          if (!getenv("MITGCM_B200_DYN_TMA_NOSPLIT")) {      // U and V on two thread groups of one CTA (16 warps)
+            // ring depth: 3 = one 512-thread CTA per SM, 110 registers, no spills (measured at 2048^2 x 50: 8.86 ms; 2 stages x 2 CTAs
+            // at 64 registers: 9.06; 4: 8.87; the 256-thread dyn_tma_kernel: 9.75)
+            const int nst = getenv("MITGCM_B200_DYN_TMA_STAGES") ? atoi(getenv("MITGCM_B200_DYN_TMA_STAGES")) : 3;
+            const dim3 grdT((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), blkT(FT_X, FT_Y, 2);
+#define DYN_UV_LAUNCH(NST, MINB)                                                                                              \
+  {                                                                                                                           \
+    const int smB = (int)sizeof(DynTmaSmemN<NST>) + 128;                                                                      \
+    if (c.attrDynTmaUV != NST) {                                                                                              \
+      MG_CUDA(cudaFuncSetAttribute(dyn_tma_uv_kernel<NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smB));          \
+      c.attrDynTmaUV = NST;                                                                                                   \
+    }                                                                                                                         \
+    dyn_tma_uv_kernel<NST, MINB><<<grdT, blkT, smB, c.stream>>>(maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3,       \
+                                                                guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,                 \
+                                                                q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0);   \
+  }
+            if (nst == 3) DYN_UV_LAUNCH(3, 1)
+            else if (nst == 4) DYN_UV_LAUNCH(4, 1)
+            else if (nst == 5) DYN_UV_LAUNCH(5, 1)
+            else DYN_UV_LAUNCH(2, 2)
+#undef DYN_UV_LAUNCH
+          } else
           dyn_tma_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), smemBytes, c.stream>>>(
               maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,
               q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0);

@@ -157,8 +157,11 @@ def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeyp
     dyn_kernel<0>: the same fields after 3 steps on a partial-cell grid with land and 2 x 1 tiles (np.array_equal:
     the TMA kernel skips the identically-zero biharmonic terms, which can only flip the sign of a zero)."""
     outs = []
-    for env in ({}, {"MITGCM_B200_DYN_NOTMA": "1"}, {"MITGCM_B200_GENERIC_STEP": "1"}):
-        for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP"):
+    # default: the role-split TMA kernel (dyn_tma_uv_kernel: U and V on two thread groups); then the 256-thread one
+    for env in ({}, {"MITGCM_B200_DYN_TMA_STAGES": "2"}, {"MITGCM_B200_DYN_TMA_STAGES": "3"}, {"MITGCM_B200_DYN_TMA_STAGES": "4"},
+                {"MITGCM_B200_DYN_TMA_STAGES": "5"}, {"MITGCM_B200_DYN_TMA_NOSPLIT": "1"}, {"MITGCM_B200_DYN_NOTMA": "1"},
+                {"MITGCM_B200_GENERIC_STEP": "1"}):
+        for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP", "MITGCM_B200_DYN_TMA_NOSPLIT", "MITGCM_B200_DYN_TMA_STAGES"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
