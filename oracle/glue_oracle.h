@@ -48,6 +48,21 @@ void og_calc_phi_hyd(const og_grid *g, int bi, int bj, int iMin, int iMax, int j
 void og_integr_continuity_ec(const og_grid *g, const og_params *p, int bi, int bj, const double *uVel,
                              const double *vVel, const double *etaH, double *dEtaHdt, double *etaN,
                              int updateEtaN);
+
+/* ---- the non-hydrostatic step around CG3D (nh_oracle.c) ---- */
+int og_calc_gw(const og_grid *g, const og_params *p, int bi, int bj, const double *R_low, const double *Ro_surf,
+               const double *rLowW, const double *rSurfW, const double *rLowS, const double *rSurfS,
+               const double *rC, const double *kappaRU, const double *kappaRV, double viscAhW, double viscA4W,
+               int momDissip_In_AB, double abFac, const double *uVel, const double *vVel, const double *wVel,
+               double *gW, double *gwNm1);
+void og_timestep_wvel(const og_grid *g, const og_params *p, int bi, int bj, double *gW, double *wVel);
+void og_solve_rhs_nh(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf, const double *etaN,
+                     const double *phi_nh, const double *gU, const double *gV, double *cg2d_b, double *cg2d_x,
+                     double *cg3d_b);
+void og_pre_cg3d(const og_grid *g, const og_params *p, int bi, int bj, const double *cg2d_x, const double *etaN,
+                 const double *wVel, double *cg3d_b);
+void og_correction_step_nh(const og_grid *g, const og_params *p, int bi, int bj, const double *Bo_surf, const double *etaN,
+                           const double *phi_nh, const double *gU, const double *gV, double *uVel, double *vVel);
 #ifdef __cplusplus
 }
 #endif

@@ -241,6 +241,29 @@ class Oracle:
     def integrate_for_w(self, bi, bj, uVel, vVel, wVel):
         self.lib.og_integrate_for_w(C.byref(self.g), C.byref(self.p), bi, bj, ptr(uVel), ptr(vVel), ptr(wVel))
 
+    # ---- non-hydrostatic step around CG3D (nh_oracle.c) ----
+    def calc_gw(self, bi, bj, R_low, Ro_surf, rLowW, rSurfW, rLowS, rSurfS, rC, kappaRU, kappaRV, viscAhW, viscA4W,
+                momDissip_In_AB, abFac, uVel, vVel, wVel, gW, gwNm1):
+        """CALC_GW + ADAMS_BASHFORTH2 on gW (calc_gw.F:156-640); returns non-zero for options that are not restated."""
+        return self.lib.og_calc_gw(C.byref(self.g), C.byref(self.p), bi, bj, ptr(R_low), ptr(Ro_surf), ptr(rLowW), ptr(rSurfW),
+                                   ptr(rLowS), ptr(rSurfS), ptr(rC), ptr(kappaRU), ptr(kappaRV), C.c_double(viscAhW),
+                                   C.c_double(viscA4W), int(momDissip_In_AB), C.c_double(abFac), ptr(uVel), ptr(vVel),
+                                   ptr(wVel), ptr(gW), ptr(gwNm1))
+
+    def timestep_wvel(self, bi, bj, gW, wVel):
+        self.lib.og_timestep_wvel(C.byref(self.g), C.byref(self.p), bi, bj, ptr(gW), ptr(wVel))
+
+    def solve_rhs_nh(self, bi, bj, etaN, phi_nh, gU, gV, b, x, b3):
+        self.lib.og_solve_rhs_nh(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]), ptr(etaN),
+                                 ptr(phi_nh), ptr(gU), ptr(gV), ptr(b), ptr(x), ptr(b3))
+
+    def pre_cg3d(self, bi, bj, cg2d_x, etaN, wVel, b3):
+        self.lib.og_pre_cg3d(C.byref(self.g), C.byref(self.p), bi, bj, ptr(cg2d_x), ptr(etaN), ptr(wVel), ptr(b3))
+
+    def correction_step_nh(self, bi, bj, etaN, phi_nh, gU, gV, uVel, vVel):
+        self.lib.og_correction_step_nh(C.byref(self.g), C.byref(self.p), bi, bj, ptr(self.grid.a["Bo_surf"]), ptr(etaN),
+                                       ptr(phi_nh), ptr(gU), ptr(gV), ptr(uVel), ptr(vVel))
+
     # ---- physics glue of config 2 (phys_oracle.c) ----
     def density_ivdc(self, eos, bi, bj, theta, salt, tRef, sRef, rhoInSitu, IVDConvCount):
         self.lib.og_density_ivdc(C.byref(self.g), C.byref(self.p), C.byref(eos), bi, bj, ptr(theta), ptr(salt),

@@ -49,10 +49,25 @@ def solid_body_fixture():
     print("wrote solid_body_cs32.npz")
 
 
+def deep_convection_fixture():
+    """tutorial_deep_convection (the non-hydrostatic step around CG3D): start state T / U / V / Eta at 120 min and the
+    surface heat flux, real*4 big-endian as the model reads them (readBinaryPrec = 32), kept as float32."""
+    import numpy as np
+    dc = os.path.join(REF, "tutorial_deep_convection/input")
+    out = {}
+    for n, f in (("T", "T.120mn.bin"), ("U", "U.120mn.bin"), ("V", "V.120mn.bin")):
+        out[n] = np.fromfile(os.path.join(dc, f), ">f4").reshape(50, 100, 100).astype(np.float32)
+    for n, f in (("Eta", "Eta.120mn.bin"), ("Qnet", "Qnet_p32.bin")):
+        out[n] = np.fromfile(os.path.join(dc, f), ">f4").reshape(100, 100).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "deep_convection.npz"), **out)
+    print("wrote deep_convection.npz")
+
+
 if __name__ == "__main__":
     os.makedirs(HERE, exist_ok=True)
     cs32_fixture()
     solid_body_fixture()
+    deep_convection_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

@@ -43,11 +43,11 @@ class CudaEngine:
     CUDA library through mitgcm_b200.runtime, i.e. through the C ABI with host buffers and the reference
     argument lists.  Lets the end-to-end drivers under oracle/ run with the CUDA kernels in the loop."""
 
-    def __init__(self, rt, use_gad=True, use_mom=True, use_cg2d=True, fallback=None):
+    def __init__(self, rt, use_gad=True, use_mom=True, use_cg2d=True, fallback=None, use_cg3d=True):
         self.rt, self.fb = rt, fallback
-        self.use_gad, self.use_mom, self.use_cg2d = use_gad, use_mom, use_cg2d
+        self.use_gad, self.use_mom, self.use_cg2d, self.use_cg3d = use_gad, use_mom, use_cg2d, use_cg3d
 
-    def setup(self, g, params, op, topo=None):
+    def setup(self, g, params, op, topo=None, op3=None):
         from mitgcm_b200 import _lib
         rt = self.rt
         rt.init(g.d)
@@ -58,6 +58,8 @@ class CudaEngine:
         known = {k: v for k, v in params.items() if "MP_" + k.upper() in _lib.ENUMS or "MI_" + k.upper() in _lib.ENUMS}
         rt.set_params(**known)
         rt.set_cg2d_operator(op)
+        if op3 is not None:
+            rt.set_cg3d_operator(op3)
 
     def gad_calc_rhs(self, bi, bj, iMin, iMax, jMin, jMax, k, kM1, kUp, kDown, xA, yA, maskUp, uFld, vFld, wFld,
                      uTrans, vTrans, rTrans, rTransKp1, diffKh, diffK4, KappaR, diffKr4, TracerN, TracAB, deltaTLev,
@@ -81,6 +83,11 @@ class CudaEngine:
         if not self.use_cg2d:
             return self.fb.cg2d(op, b, x, numIters, nIterMin, sr=sr)
         return self.rt.cg2d(b, x, numIters, nIterMin, sr=sr)
+
+    def cg3d(self, op3, b, x, numIters):
+        if not self.use_cg3d:
+            return self.fb.cg3d(op3, b, x, numIters)
+        return self.rt.cg3d(b, x, numIters)
 
 
 def load_cs32():

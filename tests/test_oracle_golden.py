@@ -368,6 +368,52 @@ def test_ini_cg3d_normalisation_factor_of_tutorial_deep_convection():
 
 
 # ---------------------------------------------------------------------------------------
+# verification/tutorial_deep_convection, all 3 steps of the golden: the NON-HYDROSTATIC step (CALC_GW, TIMESTEP_WVEL,
+# the NH right-hand sides, PRE_CG3D, CG3D with 100 iterations per step, the correction with phi_nh) from the
+# experiment's own start files.  PINS CG3D (cg3d_oracle.c) and, through cg2dUseMinResSol = 1, the minimum-residual
+# solution of CG2D.  oracle/deep_convection.py; the restatement reproduced every printed digit on its first run.
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def deep_conv():
+    from oracle import deep_convection as dc
+    return dc.run(3)
+
+
+DC_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_deep_convection.json")))
+
+
+def test_deep_convection_solver_lines_every_printed_digit(deep_conv):
+    op, op3, out, rec0 = deep_conv
+    G = DC_GOLD
+    assert fmt(op["cg2dNorm"], 16) == G["cg2dNorm"] and fmt(op3["cg3dNorm"], 16) == G["cg3dNorm"]
+    assert [r["numIters"] for r in out] == G["cg2d_iters"] == [100, 123, 122]
+    assert [r["nIterMin"] for r in out] == G["cg2d_iters_min"]                   # cg2dUseMinResSol = 1
+    assert [r["cg3d"]["numIters"] for r in out] == G["cg3d_iters"] == [100, 100, 100]
+    for n, r in enumerate(out):
+        assert (fmt(r["sumRHS"], 14), fmt(r["rhsMax"], 14)) == tuple(G["sumRHS_rhsMax"][n])
+        assert fmt(r["firstResidual"], 14) == G["cg2d_init_res"][n]
+        assert fmt(r["lastResidual"], 14) == G["cg2d_last_res"][n]
+        assert fmt(np.sqrt(r["minResidualSq"]), 14) == G["cg2d_min_res"][n]
+        c = r["cg3d"]
+        # Sum(rhs) is the round-off of a 5e5-term sum of 4e-3 numbers (2e-13): reproduced digit for digit all the same
+        assert (fmt(c["sumRHS"], 14), fmt(c["rhsMax"], 14)) == tuple(G["cg3d_sumRHS_rhsMax"][n])
+        assert fmt(c["firstResidual"], 14) == G["cg3d_init_res"][n]
+        assert fmt(c["lastResidual"], 14) == G["cg3d_last_res"][n]               # after 100 CG3D iterations
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel", "theta"])
+def test_deep_convection_monitor_statistics_every_printed_digit(deep_conv, fld):
+    _, _, out, rec0 = deep_conv
+    for n, r in enumerate([rec0] + out):
+        for st in ("max", "min", "mean", "sd"):
+            gold = DC_GOLD[f"dynstat_{fld}_{st}"][n]
+            if abs(float(gold)) < 1e-12:          # means that cancel to round-off (w, eta)
+                assert abs(r[fld][st] - float(gold)) < 1e-15, (n, st)
+            else:
+                assert fmt(r[fld][st], 13) == gold, (n, fld, st)
+
+
+# ---------------------------------------------------------------------------------------
 # verification/adjustment.128x64x1: gravity-wave adjustment of a one-layer atmosphere (p coordinates) on the global
 # lat-lon grid, pole to pole (zero-width faces closed by ADD_WALLS2MASKS), 2 x 2 tiles, 24 steps.  The golden was
 # written by an older model version (older SOLVE_FOR_PRESSURE print-out): agreement is >= 11 digits, not every digit.
