@@ -234,6 +234,11 @@ void mitgcm_b200_set_cs_tiles_(const int *csCorners, const int *myFace, const in
  * the step are returned like SOLVE_FOR_PRESSURE prints them (solve_for_pressure.F:337-348). */
 void mitgcm_b200_forward_step_(const int *myIter, double *cg2d_init_res, int *cg2d_iters,
                                double *cg2d_last_res, int *ierr);
+/* Column geometry of the resident step (csrc/colgeom.cu): 1 = the nine mirrors hFacC/W/S, recip_hFacC/W/S, maskC/W/S
+ * have the z-level form (1 down to the deepest wet level, one partial value there, 0 below; mask = hFac != 0) and the
+ * step kernels rebuild them per column instead of reading the 3-D arrays; 0 = not checked since a mirror last changed
+ * (the check runs at the next forward step); -1 = they do not (general kernels).  MITGCM_B200_NO_COLGEOM=1 disables it. */
+int mitgcm_b200_col_geom_state_(void);
 /* EXCH_XYZ_RL / EXCH_XY_RL on a mirror (eesupp/src/exch_xyz_rx.template, exch_xy_rx.template):
  * full-width halo with corners. */
 void mitgcm_b200_exch_(const int *id, int *ierr);

@@ -225,6 +225,7 @@ void mitgcm_b200_finalize_(void) {
     c.e2UvCount[w] = 0;
   }
   cg2d_free_workspace();
+  col_geom_free();
   halo_free();               // unmaps the peers' arenas
   if (c.arena) cudaFree(c.arena);
   c.arena = nullptr;
@@ -263,6 +264,7 @@ void mitgcm_b200_set_field_(const int *id, const double *host, int *ierr) {
   cudaMemcpyKind kind = is_device_ptr(host) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (cudaMemcpyAsync(d, host, n * sizeof(double), kind, c.stream) != cudaSuccess) { fail(4, "set_field copy"); return; }
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(4, "set_field sync"); return; }
+  col_geom_touch(*id);
   *ierr = 0;
 }
 
@@ -292,10 +294,15 @@ void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr) {
   c.launches++;
   fill_kernel<<<c.numSMs * 8, 256, 0, c.stream>>>(d, field_elems(c.g, *id), *value);
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "fill_field"); return; }
+  col_geom_touch(*id);
   *ierr = 0;
 }
 
-double *mitgcm_b200_field_ptr(int id) { return ctx().ready ? field(id) : nullptr; }
+double *mitgcm_b200_field_ptr(int id) {
+  if (!ctx().ready) return nullptr;
+  col_geom_touch(id);      // the caller may write through the address
+  return field(id);
+}
 
 void mitgcm_b200_event_record_(const int *slot) {
   Ctx &c = ctx();

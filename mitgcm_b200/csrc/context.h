@@ -61,6 +61,13 @@ struct Ctx {
   struct HaloWs *halo = nullptr;
   // function attributes (dynamic shared memory opt-in) are per device: set once per init
   bool attrDyn = false, attrThermo = false, attrVi = false, attrDynTma = false; int attrDynTmaUV = 0;
+  // column geometry (colgeom.cu): the nine 3-D open-fraction / mask arrays compressed to (kLow, hLow, 1/hLow) per
+  // column and point type when they have the z-level form; state 0 = not checked since the arrays last changed,
+  // 1 = valid, -1 = the arrays do not have that form (general kernels)
+  int *cgK[3] = {nullptr, nullptr, nullptr};            // C, W, S: deepest wet level (0 = land)
+  double *cgH[3] = {nullptr, nullptr, nullptr}, *cgR[3] = {nullptr, nullptr, nullptr};   // hFac and recip_hFac at that level
+  int cgState = 0, cgFails = 0;
+  int *cgFlag = nullptr;
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;
@@ -71,6 +78,9 @@ struct Ctx {
 };
 
 Ctx &ctx();
+bool col_geom_ready();      // colgeom.cu: (re)builds the column geometry when needed; true = valid
+void col_geom_free();
+void col_geom_touch(int id);  // a geometry mirror may have changed
 bool fail(int code, const std::string &msg);          // records error, returns false
 #define MG_CUDA(call)                                                              \
   do {                                                                             \

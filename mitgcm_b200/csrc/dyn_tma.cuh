@@ -17,6 +17,7 @@
 #pragma once
 #include "step_fast.cuh"
 #include "tma.cuh"
+#include <type_traits>
 
 namespace mg {
 
@@ -35,6 +36,7 @@ struct DynTmaStage {
 };
 template <int NST>
 struct DynTmaSmemN {
+  static constexpr bool CG = false;
   DynTmaStage st[NST];
   double uT[FT_N], vT[FT_N], wA[FT_N], hZ[FT_N], mCk[FT_N], dyG[FT_N], dxG[FT_N], rA[FT_N];
   VertSmem vs;
@@ -330,6 +332,52 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
   }
 }
 
+// ---- column-geometry variant of the staging (colgeom.cu): the eight geometry boxes per level (hFacW/S/C, maskC and the
+// own-column recip_hFacW/S, maskW/S) are not fetched at all; the CTA keeps (kLow, hLow) of its patch for the three
+// point types in shared memory and rebuilds the level values by compare + select.  Half the TMA traffic and half the
+// ring: 20 KB per stage, so three stages fit twice per SM.
+enum { CP_U = 0, CP_V, CP_W, CP_PHI, CP_NPATCH };
+enum { CO_KU = 0, CO_KV, CO_GUO, CO_GVO, CO_NOWN };
+struct DynTmaStageCG {
+  double patch[CP_NPATCH][DT_PATCH_D];
+  double own[CO_NOWN][DT_OWN_D];
+};
+template <int NST>
+struct DynTmaSmemCG {
+  static constexpr bool CG = true;
+  DynTmaStageCG st[NST];
+  double uT[FT_N], vT[FT_N], wA[FT_N], hZ[FT_N], hC[FT_N], dyG[FT_N], dxG[FT_N], rA[FT_N];
+  double hLW[FT_N], hLS[FT_N], hLC[FT_N];
+  int kLW[FT_N], kLS[FT_N], kLC[FT_N];
+  VertSmem vs;
+  uint64_t full[NST];
+};
+__device__ __forceinline__ void dyn_tma_issue(const DynTmaMaps &m, DynTmaStageCG &s, uint64_t *bar, int x0, int y0, int k, int Nr,
+                                              bool hasPhi) {
+  const bool below = k + 1 <= Nr;
+  mbar_expect_tx(bar, 2 * DT_PATCH_BYTES + 4 * DT_OWN_BYTES + (below ? DT_PATCH_BYTES : 0) + (hasPhi ? DT_PATCH_BYTES : 0));
+  tma_load3(s.patch[CP_U], &m.u, x0, y0, k - 1, bar);
+  tma_load3(s.patch[CP_V], &m.v, x0, y0, k - 1, bar);
+  if (hasPhi) tma_load3(s.patch[CP_PHI], &m.phi, x0, y0, k - 1, bar);
+  tma_load3(s.own[CO_KU], &m.kU, x0, y0 + 1, k, bar);
+  tma_load3(s.own[CO_KV], &m.kV, x0, y0 + 1, k, bar);
+  tma_load3(s.own[CO_GUO], &m.guO, x0, y0 + 1, k - 1, bar);
+  tma_load3(s.own[CO_GVO], &m.gvO, x0, y0 + 1, k - 1, bar);
+  if (below) tma_load3(s.patch[CP_W], &m.w, x0, y0, k, bar);
+}
+// pseudo-level 0 in slot 0: what level 1 needs from "the level above" (w of level 1; the 3-D-array form also maskC, maskW/S)
+__device__ __forceinline__ void dyn_tma_issue0(const DynTmaMaps &m, DynTmaStageCG &s, uint64_t *bar, int x0, int y0) {
+  mbar_expect_tx(bar, DT_PATCH_BYTES);
+  tma_load3(s.patch[CP_W], &m.w, x0, y0, 0, bar);
+}
+__device__ __forceinline__ void dyn_tma_issue0(const DynTmaMaps &m, DynTmaStage &s, uint64_t *bar, int x0, int y0) {
+  mbar_expect_tx(bar, 2 * DT_PATCH_BYTES + 2 * DT_OWN_BYTES);
+  tma_load3(s.patch[DP_W], &m.w, x0, y0, 0, bar);
+  tma_load3(s.patch[DP_MC], &m.mC, x0, y0, 0, bar);
+  tma_load3(s.own[DO_MW], &m.mW, x0, y0 + 1, 0, bar);
+  tma_load3(s.own[DO_MS], &m.mS, x0, y0 + 1, 0, bar);
+}
+
 // ---- role-split variant: 512 threads, warps 0-7 compute the U tendency, warps 8-15 the V tendency ----------------
 // dyn_tma_kernel is issue-bound at 4 warps per scheduler (128 registers x 256 threads x 2 CTAs fill the register
 // file; ncu: 25 % warps active, 36 % issue-active, FP64 pipe 32 %).  Splitting the two momentum components over two
@@ -341,15 +389,31 @@ __global__ void __launch_bounds__(FT_X *FT_Y, DYNT_MINB)
 // NST = depth of the TMA ring (2: two CTAs per SM; 3-5: one CTA per SM with NST - 1 levels in flight).
 __device__ __forceinline__ void dyn_uv_bar() { asm volatile("bar.sync 1, %0;" ::"n"(2 * FT_X * FT_Y) : "memory"); }
 
-template <int NST, int ROLE>
-__device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTmaMaps &maps, const TileGrid &g, const MomState &st,
+// hFacC of a patch cell, and maskC(k+1) - maskC(k), from the staged arrays or from the column geometry
+template <bool CG, class SM, class ST>
+__device__ __forceinline__ double dyn_hc(const SM &sm, const ST &S, int e) {
+  if constexpr (CG) return sm.hC[e];
+  else return S.patch[DP_HC][e];
+}
+template <bool CG, class SM, class ST>
+__device__ __forceinline__ double dyn_dmask(const SM &sm, const ST &S, int e, int k) {
+  if constexpr (CG) return sm.kLC[e] == k ? -1. : 0.;      // 1 - 1, 0 - 1, 0 - 0
+  else return S.patch[DP_MC][e] - sm.mCk[e];
+}
+
+template <int NST, int ROLE, class SM>
+__device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, const TileGrid &g, const MomState &st,
                                               const MomPar &p, const double *__restrict__ sf, double *__restrict__ gOut,
                                               double *__restrict__ gNm1, double deltaTMom, double abFac, int momForcing,
                                               int dissInAB, int hasPhi, int t, int i, int j, bool active, bool hzok, int c,
                                               int co, int x0, int y0) {
+  constexpr bool CG = SM::CG;
   constexpr int dP = ROLE ? FT_W : 1;              // patch offset towards "my" neighbour: west for U, south for V
-  constexpr int P_F = ROLE ? DP_V : DP_U, O_M = ROLE ? DO_MS : DO_MW, O_K = ROLE ? DO_KV : DO_KU;
-  constexpr int O_RH = ROLE ? DO_RHS : DO_RHW, O_G = ROLE ? DO_GVO : DO_GUO;
+  constexpr int P_U = CG ? (int)CP_U : (int)DP_U, P_V = CG ? (int)CP_V : (int)DP_V, P_W = CG ? (int)CP_W : (int)DP_W;
+  constexpr int P_PHI = CG ? (int)CP_PHI : (int)DP_PHI;
+  constexpr int P_F = ROLE ? P_V : P_U, O_M = ROLE ? DO_MS : DO_MW;
+  constexpr int O_K = CG ? (ROLE ? (int)CO_KV : (int)CO_KU) : (ROLE ? (int)DO_KV : (int)DO_KU);
+  constexpr int O_RH = ROLE ? DO_RHS : DO_RHW, O_G = CG ? (ROLE ? (int)CO_GVO : (int)CO_GUO) : (ROLE ? (int)DO_GVO : (int)DO_GUO);
   const size_t s = active ? g.s(i, j) : g.s(0, 0);
   const int PX = g.PX;
   const int dn = ROLE ? PX : 1;
@@ -371,8 +435,18 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
   mbar_wait(&sm.full[1], 0);
   unsigned ph = 3;
   double fK = sm.st[1].patch[P_F][c];
-  double mk = sm.st[0].own[O_M][co];
-  if (t < FT_N) sm.wA[t] = sm.st[0].patch[DP_W][t] * sm.rA[t];
+  // column geometry of my own point (CG): deepest wet level, hFac and recip_hFac there
+  int kLo = 0;
+  double hLo = 0., rhLo = 0.;
+  double mk;
+  if constexpr (CG) {
+    kLo = ROLE ? g.kLowS[s] : g.kLowW[s];
+    hLo = ROLE ? g.hLowS[s] : g.hLowW[s];
+    rhLo = ROLE ? g.rhLowS[s] : g.rhLowW[s];
+    mk = cg_mask(1, kLo);
+  } else
+    mk = sm.st[0].own[O_M][co];
+  if (t < FT_N) sm.wA[t] = sm.st[0].patch[P_W][t] * sm.rA[t];
   dyn_uv_bar();
   double fkm = 0.;
   if (!p.rigidLid) fkm = (0.5 * (sm.wA[c - dP] + sm.wA[c])) * fK;
@@ -382,8 +456,7 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
   for (int k = 1; k <= g.Nr; k++) {
     const int rp = rb;
     rb = rb + 1 == NST ? 0 : rb + 1;
-    const DynTmaStage &S = sm.st[rb];
-    const double *__restrict__ mCk1 = sm.st[rp].patch[DP_MC];
+    const auto &S = sm.st[rb];
     const double drFk = sm.vs.drF[k - 1], rdrF = sm.vs.rdrF[k - 1];
     const bool below = k + 1 <= g.Nr;
     double fKp1 = 0.;
@@ -396,13 +469,21 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
     }
     if (t < FT_N) {
       const int e = t;
-      const double hW = S.patch[DP_HW][e], hS = S.patch[DP_HS][e];
-      sm.uT[e] = S.patch[DP_U][e] * (sm.dyG[e] * drFk * hW);
-      sm.vT[e] = S.patch[DP_V][e] * (sm.dxG[e] * drFk * hS);
-      if (below) sm.wA[e] = S.patch[DP_W][e] * sm.rA[e];
-      sm.mCk[e] = mCk1[e];
+      double hW, hS;
+      if constexpr (CG) {
+        hW = cg_hfac(k, sm.kLW[e], sm.hLW[e]); hS = cg_hfac(k, sm.kLS[e], sm.hLS[e]);
+        sm.hC[e] = cg_hfac(k, sm.kLC[e], sm.hLC[e]);
+      } else {
+        hW = S.patch[DP_HW][e]; hS = S.patch[DP_HS][e];
+        sm.mCk[e] = sm.st[rp].patch[DP_MC][e];      // maskC(k), fetched with level k-1
+      }
+      sm.uT[e] = S.patch[P_U][e] * (sm.dyG[e] * drFk * hW);
+      sm.vT[e] = S.patch[P_V][e] * (sm.dxG[e] * drFk * hS);
+      if (below) sm.wA[e] = S.patch[P_W][e] * sm.rA[e];
       if (hzok) {
-        const double hWs = S.patch[DP_HW][e - FT_W], hSw = S.patch[DP_HS][e - 1];
+        double hWs, hSw;
+        if constexpr (CG) { hWs = cg_hfac(k, sm.kLW[e - FT_W], sm.hLW[e - FT_W]); hSw = cg_hfac(k, sm.kLS[e - 1], sm.hLS[e - 1]); }
+        else { hWs = S.patch[DP_HW][e - FT_W]; hSw = S.patch[DP_HS][e - 1]; }
         double h = hW < hWs ? hW : hWs;
         h = hS < h ? hS : h;
         h = hSw < h ? hSw : h;
@@ -411,30 +492,32 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
     }
     dyn_uv_bar();      // derived arrays visible; slot rp (level k-1) is no longer read by anybody
     if (t == 0 && k + NST - 1 <= g.Nr) dyn_tma_issue(maps, sm.st[rp], &sm.full[rp], x0, y0, k + NST - 1, g.Nr, hasPhi != 0);
-    const double mkp1 = below ? S.own[O_M][co] : 0.;
+    double mkp1;
+    if constexpr (CG) mkp1 = below ? cg_mask(k + 1, kLo) : 0.;
+    else mkp1 = below ? S.own[O_M][co] : 0.;
     const double kapkp1 = S.own[O_K][co];
     if (active) {
-#define PU(di, dj) S.patch[DP_U][c + (dj)*FT_W + (di)]
-#define PV(di, dj) S.patch[DP_V][c + (dj)*FT_W + (di)]
-#define PHC(di, dj) S.patch[DP_HC][c + (dj)*FT_W + (di)]
-#define PMC1(di, dj) S.patch[DP_MC][c + (dj)*FT_W + (di)]
+#define PU(di, dj) S.patch[P_U][c + (dj)*FT_W + (di)]
+#define PV(di, dj) S.patch[P_V][c + (dj)*FT_W + (di)]
+#define PHC(di, dj) dyn_hc<CG>(sm, S, c + (dj)*FT_W + (di))
 #define DUT(di, dj) sm.uT[c + (dj)*FT_W + (di)]
 #define DVT(di, dj) sm.vT[c + (dj)*FT_W + (di)]
 #define DHZ(di, dj) sm.hZ[c + (dj)*FT_W + (di)]
 #define DWA(di, dj) sm.wA[c + (dj)*FT_W + (di)]
-#define DMC(di, dj) sm.mCk[c + (dj)*FT_W + (di)]
-      const double rh = S.own[O_RH][co];
+      double rh;
+      if constexpr (CG) rh = cg_hfac(k, kLo, rhLo);
+      else rh = S.own[O_RH][co];
       const double gOld = S.own[O_G][co];
       double dp = 0.;
-      if (hasPhi) dp = gp * 1. * (S.patch[DP_PHI][c] - S.patch[DP_PHI][c - dP]) * 1.;
+      if (hasPhi) dp = gp * 1. * (S.patch[P_PHI][c] - S.patch[P_PHI][c - dP]) * 1.;
       double fkp = 0.;
       if (below) {      // vertical advective flux at interface k+1 (MOM_U_ADV_WU / MOM_V_ADV_WV)
         const double wA00 = DWA(0, 0), wAn = sm.wA[c - dP];
         const double rT = 0.5 * (wAn + wA00);
         fkp = rT * 0.5 * (fKp1 + fK);
-        if (!p.rigidLid) {
-          const double d00 = PMC1(0, 0) - DMC(0, 0);
-          fkp = fkp + 0.25 * (wA00 * d00 + wAn * (S.patch[DP_MC][c - dP] - sm.mCk[c - dP])) * fKp1;
+        if (!p.rigidLid) {      // maskC(k+1) - maskC(k) at my cell and at my neighbour
+          const double d00 = dyn_dmask<CG>(sm, S, c, k), dn0 = dyn_dmask<CG>(sm, S, c - dP, k);
+          fkp = fkp + 0.25 * (wA00 * d00 + wAn * dn0) * fKp1;
         }
       }
       double gt, gD;
@@ -459,7 +542,9 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
           gD = -rh * rdrF * r_rA * ((xv1 - xv0) * AhFac + (yv1 - yv0) * AhFac + (fVrDw - fVrUp) * p.rkSign * ArFac);
           fVrUp = fVrDw;
           if (p.no_slip_sides) {
-            const double hWc = S.patch[DP_HW][c];
+            double hWc;
+            if constexpr (CG) hWc = cg_hfac(k, kLo, hLo);
+            else hWc = S.patch[DP_HW][c];
             const double tu = p.viscAhZ * u00;
             gD = gD + (-rh * rdrF * r_rA * ((hWc - hZ00) * mC0 * mD0 * tu + (hWc - hZ01) * mC1 * mD1 * tu) * drFk * p.sideDragFactor);
           }
@@ -502,7 +587,9 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
           gD = -rh * rdrF * r_rA * ((xw1 - xw0) * AhFac + (yw1 - yw0) * AhFac + (gVrDw - fVrUp) * p.rkSign * ArFac);
           fVrUp = gVrDw;
           if (p.no_slip_sides) {
-            const double hSc = S.patch[DP_HS][c];
+            double hSc;
+            if constexpr (CG) hSc = cg_hfac(k, kLo, hLo);
+            else hSc = S.patch[DP_HS][c];
             const double tv = p.viscAhZ * v00 * cf;
             gD = gD + (-rh * rdrF * r_rA * ((hSc - hZ00) * mC0 * mD0 * tv + (hSc - hZ10) * mC1 * mD1 * tv) * drFk * p.sideDragFactor);
           }
@@ -543,24 +630,23 @@ __device__ __forceinline__ void dyn_uv_levels(DynTmaSmemN<NST> &sm, const DynTma
 #undef PU
 #undef PV
 #undef PHC
-#undef PMC1
 #undef DUT
 #undef DVT
 #undef DHZ
 #undef DWA
-#undef DMC
     }
     fK = fKp1; mk = mkp1;
   }
 }
 
-template <int NST, int MINB>
+template <int NST, int MINB, bool CG = false>
 __global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
     dyn_tma_uv_kernel(const __grid_constant__ DynTmaMaps maps, TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU,
                       const double *__restrict__ sfV, double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
                       double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB, int hasPhi) {
   extern __shared__ __align__(1024) unsigned char dyn_tma_smem_raw[];
-  DynTmaSmemN<NST> &sm = *reinterpret_cast<DynTmaSmemN<NST> *>(dyn_tma_smem_raw);
+  typedef typename std::conditional<CG, DynTmaSmemCG<NST>, DynTmaSmemN<NST>>::type SM;
+  SM &sm = *reinterpret_cast<SM *>(dyn_tma_smem_raw);
   constexpr int NT = 2 * FT_X * FT_Y;
   const int tx = threadIdx.x, ty = threadIdx.y, role = threadIdx.z;      // role 0: U, role 1: V (warp-uniform)
   const int t = (role * FT_Y + ty) * FT_X + tx;
@@ -583,14 +669,14 @@ __global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
     const int gi = min(i0 - 1 + li, g.sNx + g.OLx), gj = min(j0 - 1 + lj, g.sNy + g.OLy);
     const size_t q = g.s(gi, gj);
     sm.dyG[t] = g.dyG[q]; sm.dxG[t] = g.dxG[q]; sm.rA[t] = g.rA[q];
+    if constexpr (CG) {
+      sm.kLW[t] = g.kLowW[q]; sm.hLW[t] = g.hLowW[q]; sm.kLS[t] = g.kLowS[q]; sm.hLS[t] = g.hLowS[q];
+      sm.kLC[t] = g.kLowC[q]; sm.hLC[t] = g.hLowC[q];
+    }
   }
   __syncthreads();
   if (t == 0) {
-    mbar_expect_tx(&sm.full[0], 2 * DT_PATCH_BYTES + 2 * DT_OWN_BYTES);
-    tma_load3(sm.st[0].patch[DP_W], &maps.w, x0, y0, 0, &sm.full[0]);
-    tma_load3(sm.st[0].patch[DP_MC], &maps.mC, x0, y0, 0, &sm.full[0]);
-    tma_load3(sm.st[0].own[DO_MW], &maps.mW, x0, y0 + 1, 0, &sm.full[0]);
-    tma_load3(sm.st[0].own[DO_MS], &maps.mS, x0, y0 + 1, 0, &sm.full[0]);
+    dyn_tma_issue0(maps, sm.st[0], &sm.full[0], x0, y0);
 #pragma unroll
     for (int q = 1; q < NST; q++)
       if (q <= g.Nr) dyn_tma_issue(maps, sm.st[q], &sm.full[q], x0, y0, q, g.Nr, hasPhi != 0);

@@ -73,6 +73,8 @@ bool make_tile_grid(int bi, int bj, TileGrid &t) {
   t.hFacC = f3(MG_HFACC); t.hFacW = f3(MG_HFACW); t.hFacS = f3(MG_HFACS);
   t.recip_hFacC = f3(MG_RECIP_HFACC); t.recip_hFacW = f3(MG_RECIP_HFACW); t.recip_hFacS = f3(MG_RECIP_HFACS);
   t.maskC = f3(MG_MASKC); t.maskW = f3(MG_MASKW); t.maskS = f3(MG_MASKS);
+  t.kLowC = t.kLowW = t.kLowS = nullptr;
+  t.hLowC = t.hLowW = t.hLowS = t.rhLowC = t.rhLowW = t.rhLowS = nullptr;
   return t.maskS != nullptr && t.recip_drC != nullptr;
 }
 

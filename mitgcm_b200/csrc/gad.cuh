@@ -28,13 +28,21 @@ struct TileGrid {
   const double *cosFacU, *cosFacV;                        // (PY) per tile
   const double *drF, *drC, *recip_drF, *recip_drC;        // vertical
   const double *hFacC, *hFacW, *hFacS, *recip_hFacC, *recip_hFacW, *recip_hFacS, *maskC, *maskW, *maskS;
+  // column geometry (colgeom.cu; nullptr unless the resident step attached it): tile2d arrays
+  const int *kLowC, *kLowW, *kLowS;
+  const double *hLowC, *hLowW, *hLowS, *rhLowC, *rhLowW, *rhLowS;
   __device__ __forceinline__ size_t s(int i, int j) const {
     return (size_t)(i + OLx - 1) + (size_t)PX * (size_t)(j + OLy - 1);
   }
   __device__ __forceinline__ size_t s3(int i, int j, int k) const { return s(i, j) + slab * (size_t)(k - 1); }
 };
 
+// hFac (or, with the reciprocal at kLow, recip_hFac) and mask of level k of a z-level column
+__device__ __forceinline__ double cg_hfac(int k, int kLow, double hLow) { return k < kLow ? 1. : (k == kLow ? hLow : 0.); }
+__device__ __forceinline__ double cg_mask(int k, int kLow) { return k <= kLow ? 1. : 0.; }
+
 bool make_tile_grid(int bi, int bj, TileGrid &tg);   // host: fills pointers from the mirrors
+bool attach_col_geom(int bi, int bj, TileGrid &tg);  // host: adds the column geometry when it is valid (colgeom.cu)
 // host: GAD_ADVECTION of one tile on device pointers (gad_advection.cu); dT = deltaTLev(Nr) on the device
 bool gad_advection_tile(TileGrid tg, size_t tile, int advScheme, int vertScheme, int implicitAdvection, const double *u,
                         const double *v, const double *w, const double *tr, double *gT, const double *dT);

@@ -248,7 +248,19 @@ __global__ void __launch_bounds__(VI == 2 ? 256 : 128, VI == 2 ? 2 : DYN_MINB) d
 #ifndef RHS_UNROLL
 #define RHS_UNROLL 10
 #endif
-__global__ void __launch_bounds__(128, RHS_MINB) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+// the column-geometry variants have fewer loads in flight per level: tuned separately (2048^2 x 50: rhs 1.33 -> 1.23 ms at
+// 12 CTAs/SM with 5 levels unrolled, corr 2.02 -> 1.88 ms at 4 CTAs/SM)
+#ifndef RHS_MINB_CG
+#define RHS_MINB_CG 12
+#endif
+#ifndef RHS_UNROLL_CG
+#define RHS_UNROLL_CG 5
+#endif
+#ifndef CORR_MINB_CG
+#define CORR_MINB_CG 4
+#endif
+template <bool CG>      // CG: open-water fractions from the column geometry (colgeom.cu) instead of the 3-D arrays
+__global__ void __launch_bounds__(128, CG ? RHS_MINB_CG : RHS_MINB) rhs_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
                                                   const double *__restrict__ etaN, const double *__restrict__ etaFS,
                                                   const double *__restrict__ Bo_surf,
                                                   double *__restrict__ cg2d_b, double *__restrict__ cg2d_x,
@@ -266,26 +278,34 @@ __global__ void __launch_bounds__(128, RHS_MINB) rhs_kernel(TileGrid g, const do
     const int PX = g.PX;
     const double dyG0 = g.dyG[s], dyG1 = g.dyG[s + 1], dxG0 = g.dxG[s], dxG1 = g.dxG[s + PX];
     const double *__restrict__ hW = g.hFacW, *__restrict__ hS = g.hFacS;
-UNROLL_N(RHS_UNROLL)
+    int kW0 = 0, kW1 = 0, kS0 = 0, kS1 = 0;
+    double lW0 = 0., lW1 = 0., lS0 = 0., lS1 = 0.;
+    if (CG) {
+      kW0 = g.kLowW[s]; kW1 = g.kLowW[s + 1]; kS0 = g.kLowS[s]; kS1 = g.kLowS[s + PX];
+      lW0 = g.hLowW[s]; lW1 = g.hLowW[s + 1]; lS0 = g.hLowS[s]; lS1 = g.hLowS[s + PX];
+    }
+UNROLL_N((CG ? RHS_UNROLL_CG : RHS_UNROLL))
     for (int k = g.Nr; k >= 1; k--) {
       const size_t q = s + slab * (size_t)(k - 1);
       const double drFk = g.drF[k - 1];
+      const double hW0 = CG ? cg_hfac(k, kW0, lW0) : hW[q], hW1 = CG ? cg_hfac(k, kW1, lW1) : hW[q + 1];
+      const double hS0 = CG ? cg_hfac(k, kS0, lS0) : hS[q], hS1 = CG ? cg_hfac(k, kS1, lS1) : hS[q + PX];
       // calc_div_ghat.F:64-167: pf = xA*gU/deltaTMom with xA = dyG*drF*hFacW
       double px1, px0, py1, py0;
       if (implicDiv2DFlow == 1.) {
-        px1 = dyG1 * drFk * hW[q + 1] * gU[q + 1] / deltaTMom; px0 = dyG0 * drFk * hW[q] * gU[q] / deltaTMom;
-        py1 = dxG1 * drFk * hS[q + PX] * gV[q + PX] / deltaTMom; py0 = dxG0 * drFk * hS[q] * gV[q] / deltaTMom;
+        px1 = dyG1 * drFk * hW1 * gU[q + 1] / deltaTMom; px0 = dyG0 * drFk * hW0 * gU[q] / deltaTMom;
+        py1 = dxG1 * drFk * hS1 * gV[q + PX] / deltaTMom; py0 = dxG0 * drFk * hS0 * gV[q] / deltaTMom;
       } else if (!uVel) {      // exactConserv (calc_div_ghat.F:81-87): the explicit part lives in etaH
-        px1 = implicDiv2DFlow * (dyG1 * drFk * hW[q + 1]) * gU[q + 1] / deltaTMom;
-        px0 = implicDiv2DFlow * (dyG0 * drFk * hW[q]) * gU[q] / deltaTMom;
-        py1 = implicDiv2DFlow * (dxG1 * drFk * hS[q + PX]) * gV[q + PX] / deltaTMom;
-        py0 = implicDiv2DFlow * (dxG0 * drFk * hS[q]) * gV[q] / deltaTMom;
+        px1 = implicDiv2DFlow * (dyG1 * drFk * hW1) * gU[q + 1] / deltaTMom;
+        px0 = implicDiv2DFlow * (dyG0 * drFk * hW0) * gU[q] / deltaTMom;
+        py1 = implicDiv2DFlow * (dxG1 * drFk * hS1) * gV[q + PX] / deltaTMom;
+        py0 = implicDiv2DFlow * (dxG0 * drFk * hS0) * gV[q] / deltaTMom;
       } else {                 // calc_div_ghat.F:88-95
         const double om = 1. - implicDiv2DFlow;
-        px1 = (implicDiv2DFlow * gU[q + 1] + om * uVel[q + 1]) * (dyG1 * drFk * hW[q + 1]) / deltaTMom;
-        px0 = (implicDiv2DFlow * gU[q] + om * uVel[q]) * (dyG0 * drFk * hW[q]) / deltaTMom;
-        py1 = (implicDiv2DFlow * gV[q + PX] + om * vVel[q + PX]) * (dxG1 * drFk * hS[q + PX]) / deltaTMom;
-        py0 = (implicDiv2DFlow * gV[q] + om * vVel[q]) * (dxG0 * drFk * hS[q]) / deltaTMom;
+        px1 = (implicDiv2DFlow * gU[q + 1] + om * uVel[q + 1]) * (dyG1 * drFk * hW1) / deltaTMom;
+        px0 = (implicDiv2DFlow * gU[q] + om * uVel[q]) * (dyG0 * drFk * hW0) / deltaTMom;
+        py1 = (implicDiv2DFlow * gV[q + PX] + om * vVel[q + PX]) * (dxG1 * drFk * hS1) / deltaTMom;
+        py0 = (implicDiv2DFlow * gV[q] + om * vVel[q]) * (dxG0 * drFk * hS0) / deltaTMom;
       }
       b = b + px1 - px0;
       b = b + py1 - py0;
@@ -334,7 +354,8 @@ __global__ void corr_edge_kernel(TileGrid g, const double *__restrict__ gU, cons
 #ifndef CORR_UNROLL
 #define CORR_UNROLL 5
 #endif
-__global__ void __launch_bounds__(128, CORR_MINB) corr_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
+template <bool CG>
+__global__ void __launch_bounds__(128, CG ? CORR_MINB_CG : CORR_MINB) corr_kernel(TileGrid g, const double *__restrict__ gU, const double *__restrict__ gV,
                                                    const double *__restrict__ etaN, const double *__restrict__ Bo_surf,
                                                    double *__restrict__ uVel, double *__restrict__ vVel, double *__restrict__ wVel,
                                                    double deltaTMom, double implicSurfPress, int rigidLid) {
@@ -346,36 +367,47 @@ __global__ void __launch_bounds__(128, CORR_MINB) corr_kernel(TileGrid g, const 
   auto phiY = [&](int jj) { return g.recip_dyC[g.s(i, jj)] * (Bo_surf[g.s(i, jj)] * etaN[g.s(i, jj)] - Bo_surf[g.s(i, jj - 1)] * etaN[g.s(i, jj - 1)]); };
   const double px0 = phiX(i), px1 = phiX(i + 1), py0 = phiY(j), py1 = phiY(j + 1);
   double wKp1 = 0.;
+  int kW0 = 0, kW1 = 0, kS0 = 0, kS1 = 0, kC = 0;
+  double lW0 = 0., lW1 = 0., lS0 = 0., lS1 = 0.;
+  if (CG) {
+    const size_t s = g.s(i, j);
+    kW0 = g.kLowW[s]; kW1 = g.kLowW[s + 1]; kS0 = g.kLowS[s]; kS1 = g.kLowS[s + g.PX]; kC = g.kLowC[s];
+    lW0 = g.hLowW[s]; lW1 = g.hLowW[s + 1]; lS0 = g.hLowS[s]; lS1 = g.hLowS[s + g.PX];
+  }
 UNROLL_N(CORR_UNROLL)
   for (int k = g.Nr; k >= 1; k--) {
-    auto uNew = [&](int ii, double px) {
+    auto uNew = [&](int ii, double px, int kW) {
       size_t q = g.s3(ii, j, k);
-      double dpx = -psFac * px * g.maskW[q];
-      return (gU[q] + deltaTMom * dpx) * g.maskW[q];
+      const double mW = CG ? cg_mask(k, kW) : g.maskW[q];
+      double dpx = -psFac * px * mW;
+      return (gU[q] + deltaTMom * dpx) * mW;
     };
-    auto vNew = [&](int jj, double py) {
+    auto vNew = [&](int jj, double py, int kS) {
       size_t q = g.s3(i, jj, k);
-      double dpy = -psFac * py * g.maskS[q];
-      return (gV[q] + deltaTMom * dpy) * g.maskS[q];
+      const double mS = CG ? cg_mask(k, kS) : g.maskS[q];
+      double dpy = -psFac * py * mS;
+      return (gV[q] + deltaTMom * dpy) * mS;
     };
-    const double u0 = uNew(i, px0), u1 = uNew(i + 1, px1), v0 = vNew(j, py0), v1 = vNew(j + 1, py1);
+    const double u0 = uNew(i, px0, kW0), u1 = uNew(i + 1, px1, kW1), v0 = vNew(j, py0, kS0), v1 = vNew(j + 1, py1, kS1);
     const size_t s3 = g.s3(i, j, k);
     uVel[s3] = u0;
     vVel[s3] = v0;
     // INTEGRATE_FOR_W
-    const double uT0 = u0 * g.dyG[g.s(i, j)] * g.drF[k - 1] * g.hFacW[s3];
-    const double uT1 = u1 * g.dyG[g.s(i + 1, j)] * g.drF[k - 1] * g.hFacW[g.s3(i + 1, j, k)];
-    const double vT0 = v0 * g.dxG[g.s(i, j)] * g.drF[k - 1] * g.hFacS[s3];
-    const double vT1 = v1 * g.dxG[g.s(i, j + 1)] * g.drF[k - 1] * g.hFacS[g.s3(i, j + 1, k)];
+    const double uT0 = u0 * g.dyG[g.s(i, j)] * g.drF[k - 1] * (CG ? cg_hfac(k, kW0, lW0) : g.hFacW[s3]);
+    const double uT1 = u1 * g.dyG[g.s(i + 1, j)] * g.drF[k - 1] * (CG ? cg_hfac(k, kW1, lW1) : g.hFacW[g.s3(i + 1, j, k)]);
+    const double vT0 = v0 * g.dxG[g.s(i, j)] * g.drF[k - 1] * (CG ? cg_hfac(k, kS0, lS0) : g.hFacS[s3]);
+    const double vT1 = v1 * g.dxG[g.s(i, j + 1)] * g.drF[k - 1] * (CG ? cg_hfac(k, kS1, lS1) : g.hFacS[g.s3(i, j + 1, k)]);
     const double conv2d = -(uT1 - uT0 + vT1 - vT0);
+    const double mCk = CG ? cg_mask(k, kC) : g.maskC[s3];
     double wv;
     if (rigidLid) {
+      const double mCkm1 = k == 1 ? 0. : (CG ? cg_mask(k - 1, kC) : g.maskC[g.s3(i, j, k - 1)]);
       if (k == 1) wv = 0.;
-      else if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * g.maskC[s3] * g.maskC[g.s3(i, j, k - 1)];
-      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * g.maskC[s3] * g.maskC[g.s3(i, j, k - 1)];
+      else if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * mCk * mCkm1;
+      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * mCk * mCkm1;
     } else {
-      if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * g.maskC[s3];
-      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * g.maskC[s3];
+      if (k == g.Nr) wv = conv2d * g.recip_rA[g.s(i, j)] * mCk;
+      else wv = (wKp1 + conv2d * g.recip_rA[g.s(i, j)]) * mCk;
     }
     wVel[s3] = wv;
     wKp1 = wv;
@@ -477,6 +509,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
     if (!c.pev[n]) cudaEventCreate(&c.pev[n]);
     cudaEventRecord(c.pev[n], c.stream);
   };
+  col_geom_ready();      // (re)checks the z-level form of the geometry mirrors when they changed; attach_col_geom uses the result
   if (part == 0) {
   mark(0);
   // DO_OCEANIC_PHYS: surface relaxation forcing, in-situ density, convective flag -> kappaRT
@@ -556,10 +589,14 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         c.launches++;
         if (thermo_fast_ok(g, p) && !(getenv("MITGCM_B200_THERMO_NOPIPE") && !multiDim)) {
           if (!c.attrThermo) {      // per device / context: reset by mitgcm_b200_init_
-            MG_CUDA(cudaFuncSetAttribute(thermo_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThermoPipeSmem)));
+            MG_CUDA(cudaFuncSetAttribute(thermo_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThermoPipeSmemT<false>)));
+            MG_CUDA(cudaFuncSetAttribute(thermo_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThermoPipeSmemT<true>)));
             c.attrThermo = true;
           }
-          thermo_pipe_kernel<<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ThermoPipeSmem), c.stream>>>(
+          const bool cgT = attach_col_geom(bi, bj, tg);
+          (cgT ? thermo_pipe_kernel<true> : thermo_pipe_kernel<false>)
+              <<<dim3((g.sNx + FT_X - 1) / FT_X, (g.sNy + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y),
+                 cgT ? sizeof(ThermoPipeSmemT<true>) : sizeof(ThermoPipeSmemT<false>), c.stream>>>(
               tg, u + o3, v + o3, w + o3, th + o3, kapT + o3, th2 + o3, gtN + o3, p, abFac, sfT ? sfT + o2 : nullptr,
               multiDim ? gTadv + o3 : nullptr, abScheme ? 1 : 0);
         } else if (!multiDim && thermo_fast_ok(g, p))
@@ -638,21 +675,31 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
             // at 64 registers: 9.06; 4: 8.87; the 256-thread dyn_tma_kernel: 9.75)
             const int nst = getenv("MITGCM_B200_DYN_TMA_STAGES") ? atoi(getenv("MITGCM_B200_DYN_TMA_STAGES")) : 3;
             const dim3 grdT((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), blkT(FT_X, FT_Y, 2);
-#define DYN_UV_LAUNCH(NST, MINB)                                                                                              \
+#define DYN_UV_LAUNCH(NST, MINB, CGF)                                                                                         \
   {                                                                                                                           \
-    const int smB = (int)sizeof(DynTmaSmemN<NST>) + 128;                                                                      \
-    if (c.attrDynTmaUV != NST) {                                                                                              \
-      MG_CUDA(cudaFuncSetAttribute(dyn_tma_uv_kernel<NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smB));          \
-      c.attrDynTmaUV = NST;                                                                                                   \
+    const int smB = (int)(CGF ? sizeof(DynTmaSmemCG<NST>) : sizeof(DynTmaSmemN<NST>)) + 128;                                  \
+    const int key = NST + 16 * MINB + (CGF ? 256 : 0);                                                                        \
+    if (c.attrDynTmaUV != key) {                                                                                              \
+      MG_CUDA(cudaFuncSetAttribute(dyn_tma_uv_kernel<NST, MINB, CGF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smB));     \
+      c.attrDynTmaUV = key;                                                                                                   \
     }                                                                                                                         \
-    dyn_tma_uv_kernel<NST, MINB><<<grdT, blkT, smB, c.stream>>>(maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3,       \
-                                                                guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,                 \
-                                                                q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0);   \
+    dyn_tma_uv_kernel<NST, MINB, CGF><<<grdT, blkT, smB, c.stream>>>(maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3,  \
+                                                                     guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,            \
+                                                                     q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0); \
   }
-            if (nst == 3) DYN_UV_LAUNCH(3, 1)
-            else if (nst == 4) DYN_UV_LAUNCH(4, 1)
-            else if (nst == 5) DYN_UV_LAUNCH(5, 1)
-            else DYN_UV_LAUNCH(2, 2)
+            if (attach_col_geom(bi, bj, tg)) {      // geometry from (kLow, hLow) per column: 8 instead of 16 boxes per level
+              // 20 KB stages: three of them fit twice per SM (measured at 2048^2 x 50: <3,2> 8.08 ms, <2,2> 8.12, <3,1> 8.39, <4,1> 8.44;
+              // the 3-D-array form <3,1>: 8.76)
+              const int minb = getenv("MITGCM_B200_DYN_TMA_MINB") ? atoi(getenv("MITGCM_B200_DYN_TMA_MINB")) : 2;
+              if (nst == 2) DYN_UV_LAUNCH(2, 2, true)
+              else if (nst == 4) DYN_UV_LAUNCH(4, 1, true)
+              else if (nst == 5) DYN_UV_LAUNCH(5, 1, true)
+              else if (minb == 2) DYN_UV_LAUNCH(3, 2, true)
+              else DYN_UV_LAUNCH(3, 1, true)
+            } else if (nst == 3) DYN_UV_LAUNCH(3, 1, false)
+            else if (nst == 4) DYN_UV_LAUNCH(4, 1, false)
+            else if (nst == 5) DYN_UV_LAUNCH(5, 1, false)
+            else DYN_UV_LAUNCH(2, 2, false)
 #undef DYN_UV_LAUNCH
           } else
           dyn_tma_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), smemBytes, c.stream>>>(
@@ -696,7 +743,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
-        rhs_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
+        (attach_col_geom(bi, bj, tg) ? rhs_kernel<true> : rhs_kernel<false>)<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, (exactConserv ? etaH : eta) + o2, Bo + o2, b + o2, x + o2, q.D(MP_DELTATMOM),
                                               q.D(MP_DELTATFREESURF), q.D(MP_FREESURFFAC), q.D(MP_IMPLICDIV2DFLOW),
                                               exactConserv ? nullptr : u + o3, exactConserv ? nullptr : v + o3);
       }
@@ -732,7 +779,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         size_t t = (size_t)(bi - 1) + (size_t)g.nSx * (bj - 1);
         size_t o3 = ns * g.Nr * t, o2 = ns * t;
         c.launches++;
-        corr_kernel<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
+        (attach_col_geom(bi, bj, tg) ? corr_kernel<true> : corr_kernel<false>)<<<grd, cb, 0, c.stream>>>(tg, gU + o3, gV + o3, eta + o2, Bo + o2, u + o3, v + o3, w + o3,
                                                q.D(MP_DELTATMOM), q.D(MP_IMPLICSURFPRESS), q.I(MI_RIGIDLID));
         if (q.I(MI_EXACTCONSERV)) {
           c.launches++;

@@ -621,21 +621,30 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THF_MINB)
 // ---- pipelined variant: level k-1 (theta, u, v, hFacW, hFacS of the patch) is fetched with cp.async into a two-slot
 // ring while level k is computed; same arithmetic as thermo_fast_kernel (bit-identical results).
 enum { TR_T = 0, TR_U, TR_V, TR_HW, TR_HS, TR_N };
-struct ThermoPipeSmem {
-  double raw[2][TR_N][FT_N];
+template <bool CG>
+struct ThermoPipeSmemT {
+  double raw[2][CG ? TR_HW : TR_N][FT_N];      // CG: no ring slots for hFacW / hFacS ...
   double T[FT_N], xA[FT_N], yA[FT_N], uT[FT_N], vT[FT_N], dyG[FT_N], dxG[FT_N];
+  // ... but the column geometry of the patch, from which they are rebuilt per level
+  double hLW[CG ? FT_N : 1], hLS[CG ? FT_N : 1];
+  int kLW[CG ? FT_N : 1], kLS[CG ? FT_N : 1];
 };
-__device__ __forceinline__ void thermo_pipe_prefetch(ThermoPipeSmem &sm, int slot, int e, size_t q, const TileGrid &g,
+typedef ThermoPipeSmemT<false> ThermoPipeSmem;
+template <bool CG>
+__device__ __forceinline__ void thermo_pipe_prefetch(ThermoPipeSmemT<CG> &sm, int slot, int e, size_t q, const TileGrid &g,
                                                      const double *u, const double *v, const double *theta) {
   __pipeline_memcpy_async(&sm.raw[slot][TR_T][e], theta + q, 8);
   __pipeline_memcpy_async(&sm.raw[slot][TR_U][e], u + q, 8);
   __pipeline_memcpy_async(&sm.raw[slot][TR_V][e], v + q, 8);
-  __pipeline_memcpy_async(&sm.raw[slot][TR_HW][e], g.hFacW + q, 8);
-  __pipeline_memcpy_async(&sm.raw[slot][TR_HS][e], g.hFacS + q, 8);
+  if (!CG) {
+    __pipeline_memcpy_async(&sm.raw[slot][CG ? 0 : TR_HW][e], g.hFacW + q, 8);
+    __pipeline_memcpy_async(&sm.raw[slot][CG ? 0 : TR_HS][e], g.hFacS + q, 8);
+  }
 }
 #ifndef THP_MINB
 #define THP_MINB 3
 #endif
+template <bool CG>      // CG: hFacW/S, maskC, recip_hFacC from the column geometry (colgeom.cu), not from the 3-D arrays
 __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
     thermo_pipe_kernel(TileGrid g, const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
                        const double *__restrict__ theta, const double *__restrict__ kapT, double *__restrict__ thetaNew,
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
                        const double *__restrict__ gT0, int doAB) {
   // gT0: tendency to start from (GAD_ADVECTION's, with calcAdvection = F); doAB: AdamsBashforthGt
   extern __shared__ __align__(16) unsigned char thermo_pipe_smem[];
-  ThermoPipeSmem &sm = *reinterpret_cast<ThermoPipeSmem *>(thermo_pipe_smem);
+  ThermoPipeSmemT<CG> &sm = *reinterpret_cast<ThermoPipeSmemT<CG> *>(thermo_pipe_smem);
   __shared__ VertSmem vs;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FT_X + tx;
   stage_vert(vs, g, t, FT_X * FT_Y);
@@ -680,16 +689,24 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
   for (int r = 0; r < 2; r++)
     if (sv_[r]) {
       sm.dyG[se[r]] = g.dyG[sg[r]]; sm.dxG[se[r]] = g.dxG[sg[r]];
-      thermo_pipe_prefetch(sm, 0, se[r], sg[r] + slab * (size_t)(g.Nr - 1), g, u, v, theta);
+      if (CG) {
+        sm.kLW[CG ? se[r] : 0] = g.kLowW[sg[r]]; sm.hLW[CG ? se[r] : 0] = g.hLowW[sg[r]];
+        sm.kLS[CG ? se[r] : 0] = g.kLowS[sg[r]]; sm.hLS[CG ? se[r] : 0] = g.hLowS[sg[r]];
+      }
+      thermo_pipe_prefetch<CG>(sm, 0, se[r], sg[r] + slab * (size_t)(g.Nr - 1), g, u, v, theta);
     }
   __pipeline_commit();
+  int kLC = 0;
+  double rhLC = 0.;
+  if (CG) { kLC = g.kLowC[s]; rhLC = g.rhLowC[s]; }
   for (int k = g.Nr; k >= 1; k--) {
     const size_t ko = slab * (size_t)(k - 1);
     const double drFk = vs.drF[k - 1];
     // own-column loads first: one exposed memory latency per level
     const size_t s3 = s + ko;
-    const double Tkm1 = k >= 2 ? theta[s3 - slab] : 0., mC = g.maskC[s3], mCm1 = k >= 2 ? g.maskC[s3 - slab] : 0.;
-    const double wK = w[s3], kapK = kapT[s3], rhC = g.recip_hFacC[s3], gtOld = doAB ? gtNm1[s3] : 0.;
+    const double Tkm1 = k >= 2 ? theta[s3 - slab] : 0.;
+    const double mC = CG ? cg_mask(k, kLC) : g.maskC[s3], mCm1 = k >= 2 ? (CG ? cg_mask(k - 1, kLC) : g.maskC[s3 - slab]) : 0.;
+    const double wK = w[s3], kapK = kapT[s3], rhC = CG ? cg_hfac(k, kLC, rhLC) : g.recip_hFacC[s3], gtOld = doAB ? gtNm1[s3] : 0.;
     const double gTin = gT0 ? gT0[s3] : 0.;
     __pipeline_wait_prior(0);
     __syncthreads();             // level k has landed in slot rb; everybody is done with the previous level's tiles
@@ -697,7 +714,9 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
     for (int r = 0; r < 2; r++)
       if (sv_[r]) {
         const int e = se[r];
-        const double xA = sm.dyG[e] * drFk * sm.raw[rb][TR_HW][e], yA = sm.dxG[e] * drFk * sm.raw[rb][TR_HS][e];
+        const double hW = CG ? cg_hfac(k, sm.kLW[CG ? e : 0], sm.hLW[CG ? e : 0]) : sm.raw[rb][CG ? 0 : TR_HW][e];
+        const double hS = CG ? cg_hfac(k, sm.kLS[CG ? e : 0], sm.hLS[CG ? e : 0]) : sm.raw[rb][CG ? 0 : TR_HS][e];
+        const double xA = sm.dyG[e] * drFk * hW, yA = sm.dxG[e] * drFk * hS;
         sm.T[e] = sm.raw[rb][TR_T][e]; sm.xA[e] = xA; sm.yA[e] = yA;
         sm.uT[e] = sm.raw[rb][TR_U][e] * xA; sm.vT[e] = sm.raw[rb][TR_V][e] * yA;
       }
@@ -705,7 +724,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, THP_MINB)
     if (k >= 2) {                // fetch level k-1 into the other slot while this level is computed
 #pragma unroll
       for (int r = 0; r < 2; r++)
-        if (sv_[r]) thermo_pipe_prefetch(sm, rb ^ 1, se[r], sg[r] + ko - slab, g, u, v, theta);
+        if (sv_[r]) thermo_pipe_prefetch<CG>(sm, rb ^ 1, se[r], sg[r] + ko - slab, g, u, v, theta);
     }
     __pipeline_commit();
     if (active) {

@@ -158,10 +158,13 @@ def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeyp
     the TMA kernel skips the identically-zero biharmonic terms, which can only flip the sign of a zero)."""
     outs = []
     # default: the role-split TMA kernel (dyn_tma_uv_kernel: U and V on two thread groups); then the 256-thread one
-    for env in ({}, {"MITGCM_B200_DYN_TMA_STAGES": "2"}, {"MITGCM_B200_DYN_TMA_STAGES": "3"}, {"MITGCM_B200_DYN_TMA_STAGES": "4"},
-                {"MITGCM_B200_DYN_TMA_STAGES": "5"}, {"MITGCM_B200_DYN_TMA_NOSPLIT": "1"}, {"MITGCM_B200_DYN_NOTMA": "1"},
-                {"MITGCM_B200_GENERIC_STEP": "1"}):
-        for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP", "MITGCM_B200_DYN_TMA_NOSPLIT", "MITGCM_B200_DYN_TMA_STAGES"):
+    NC = {"MITGCM_B200_NO_COLGEOM": "1"}      # the 3-D-array form of every kernel (default: geometry per column, colgeom.cu)
+    for env in ({}, {"MITGCM_B200_DYN_TMA_STAGES": "2"}, {"MITGCM_B200_DYN_TMA_MINB": "1"}, {"MITGCM_B200_DYN_TMA_STAGES": "4"},
+                {"MITGCM_B200_DYN_TMA_STAGES": "5"}, NC, dict(NC, MITGCM_B200_DYN_TMA_STAGES="2"),
+                dict(NC, MITGCM_B200_DYN_TMA_STAGES="4"), dict(NC, MITGCM_B200_DYN_TMA_STAGES="5"),
+                dict(NC, MITGCM_B200_DYN_TMA_NOSPLIT="1"), dict(NC, MITGCM_B200_DYN_NOTMA="1"), {"MITGCM_B200_GENERIC_STEP": "1"}):
+        for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP", "MITGCM_B200_DYN_TMA_NOSPLIT", "MITGCM_B200_DYN_TMA_STAGES",
+                  "MITGCM_B200_NO_COLGEOM", "MITGCM_B200_DYN_TMA_MINB"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -177,6 +180,54 @@ def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeyp
     for o in outs[1:]:
         for n in o:
             assert np.array_equal(o[n], outs[0][n]), n
+
+
+@pytest.mark.parametrize("opts", [dict(buoyancyLinear=1), dict(buoyancyLinear=0, rigidLid=1)], ids=["free-surface", "rigid-lid"])
+def test_column_geometry_kernels_are_bit_identical_to_the_3d_array_kernels(monkeypatch, opts):
+    """csrc/colgeom.cu: with z-level geometry (land, partial bottom cells) the step kernels rebuild hFac / mask /
+    recip_hFac per column from (kLow, hLow) instead of reading the nine 3-D arrays; the fields after 3 steps must be
+    bit-identical to the run that reads the arrays (MITGCM_B200_NO_COLGEOM=1)."""
+    from mitgcm_b200 import _lib
+    outs, states = [], []
+    for env in ({}, {"MITGCM_B200_NO_COLGEOM": "1"}):
+        monkeypatch.delenv("MITGCM_B200_NO_COLGEOM", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g, P, s = make_channel(sNx=70, sNy=44, Nr=7, nSx=2, nSy=1, land_frac=0.15, **opts)
+        co = ChannelOracle(g, P, s)
+        m = Model(g, P, s, co.op)
+        try:
+            for _ in range(3):
+                m.step()
+            states.append(_lib.lib().mitgcm_b200_col_geom_state_())
+            outs.append({n: m.get(n) for n in ("uVel", "vVel", "wVel", "etaN", "theta", "gU", "gV", "gtNm1", "cg2d_b")})
+        finally:
+            m.close()
+    assert states == [1, 0]          # compressed form in use / never checked
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n]), n
+
+
+def test_column_geometry_is_refused_for_surface_following_thickness():
+    """hFac scaled by a smooth column factor (what r* does): not the z-level form -> the general kernels run and the
+    step still matches the oracle."""
+    from mitgcm_b200 import _lib, runtime as rt
+    g, P, s = make_channel(sNx=40, sNy=24, Nr=5, land_frac=0.1)
+    f = 1.0 + 0.02 * np.sin(np.linspace(0, 6, g.d.PX))[None, None, None, None, :]
+    from mitgcm_b200.grid import set_hfac
+    set_hfac(g, g.a["hFacC"] * f, g.a["hFacW"] * f, g.a["hFacS"] * f)
+    co = ChannelOracle(g, P, s)
+    m = Model(g, P, s, co.op)
+    try:
+        jj, ii = g.d.interior()
+        for it in range(4):          # the check is retried three times, then given up (state -1)
+            ro, rg = co.step(), m.step()
+            assert abs(ro["numIters"] - rg["numIters"]) <= 1
+        assert _lib.lib().mitgcm_b200_col_geom_state_() == -1
+        for n in ("uVel", "vVel", "theta", "etaN"):
+            assert rel(m.get(n)[..., jj, ii], co.s[n][..., jj, ii]) < 1e-9, n
+    finally:
+        m.close()
 
 
 @pytest.mark.parametrize("scheme", [2, 33])
