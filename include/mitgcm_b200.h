@@ -98,6 +98,11 @@ void mitgcm_b200_set_field_(const int *id, const double *host, int *ierr);
 void mitgcm_b200_get_field_(const int *id, double *host, int *ierr);
 double *mitgcm_b200_field_ptr(int id);
 void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr);   /* mirror := value */
+/* Page-locks a HOST array the caller will keep passing to the per-call entry points (the COMMON-block arrays cg2d_b,
+ * cg2d_x, gU, gV, theta ... have fixed addresses for the whole run), so that their staging copies are direct DMA
+ * transfers instead of going through the driver's bounce buffer (cudaHostRegister; undone by mitgcm_b200_finalize_).
+ * nDoubles = length of the array.  Optional: unpinned arrays work, only slower. */
+void mitgcm_b200_pin_host_(double *host, const long long *nDoubles, int *ierr);
 void mitgcm_b200_sync_(void);
 /* Timing on the library's own stream (CUDA events), for bench.py: record event `slot`
  * (0..15) / elapsed milliseconds between two recorded slots (synchronises on the later one). */

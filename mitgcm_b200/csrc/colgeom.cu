@@ -110,7 +110,7 @@ bool col_geom_ready() {
 
 bool attach_col_geom(int bi, int bj, TileGrid &t) {
   Ctx &c = ctx();
-  if (c.cgState != 1) return false;
+  if (c.cgState != 1 || getenv("MITGCM_B200_NO_COLGEOM")) return false;
   const size_t o = c.g.slab * ((size_t)(bi - 1) + (size_t)c.g.nSx * (size_t)(bj - 1));
   t.kLowC = c.cgK[0] + o; t.kLowW = c.cgK[1] + o; t.kLowS = c.cgK[2] + o;
   t.hLowC = c.cgH[0] + o; t.hLowW = c.cgH[1] + o; t.hLowS = c.cgH[2] + o;

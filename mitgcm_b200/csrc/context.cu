@@ -224,6 +224,8 @@ void mitgcm_b200_finalize_(void) {
     c.e2UvList[w] = nullptr;
     c.e2UvCount[w] = 0;
   }
+  for (void *p : c.pinned) cudaHostUnregister(p);
+  c.pinned.clear();
   cg2d_free_workspace();
   col_geom_free();
   halo_free();               // unmaps the peers' arenas
@@ -295,6 +297,21 @@ void mitgcm_b200_fill_field_(const int *id, const double *value, int *ierr) {
   fill_kernel<<<c.numSMs * 8, 256, 0, c.stream>>>(d, field_elems(c.g, *id), *value);
   if (cudaStreamSynchronize(c.stream) != cudaSuccess) { fail(6, "fill_field"); return; }
   col_geom_touch(*id);
+  *ierr = 0;
+}
+
+void mitgcm_b200_pin_host_(double *host, const long long *nDoubles, int *ierr) {
+  Ctx &c = ctx();
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  for (void *p : c.pinned)
+    if (p == host) { *ierr = 0; return; }
+  if (cudaHostRegister(host, (size_t)*nDoubles * sizeof(double), cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fail(7, "pin_host: cudaHostRegister failed (the array stays pageable)");
+    return;
+  }
+  c.pinned.push_back(host);
   *ierr = 0;
 }
 

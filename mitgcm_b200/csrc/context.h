@@ -68,6 +68,7 @@ struct Ctx {
   double *cgH[3] = {nullptr, nullptr, nullptr}, *cgR[3] = {nullptr, nullptr, nullptr};   // hFac and recip_hFac at that level
   int cgState = 0, cgFails = 0;
   int *cgFlag = nullptr;
+  std::vector<void *> pinned;      // host arrays page-locked by mitgcm_b200_pin_host_
   // cg2d workspace
   struct Cg2dWs *cg2d = nullptr;
   int numSMs = 0;

@@ -118,6 +118,14 @@ def set_cg2d_operator(op: dict):
                cg2dNormaliseRHS=bool(op["cg2dNormaliseRHS"]))
 
 
+def pin_host(a: np.ndarray):
+    """mitgcm_b200_pin_host_: page-lock a host array that will be passed to the per-call entry points again and again
+    (what the shims do for the COMMON-block arrays); keep the array alive until finalize()."""
+    ierr = C.c_int(0)
+    _lib.lib().mitgcm_b200_pin_host_(_addr(a), C.byref(C.c_longlong(a.size)), C.byref(ierr))
+    _check(ierr)
+
+
 def update_cg2d(myIter: int, myTime: float = 0.0, myThid: int = 1):
     """CALL UPDATE_CG2D( myTime, myIter, myThid ) -- model/src/update_cg2d.F:7: operator (and preconditioner) from
     the current hFacW / hFacS mirrors."""
