@@ -42,9 +42,8 @@ sys.path.insert(0, ROOT)
 CG2D_BYTES_PER_POINT_ITER = 136.0     # 17 words, the minimum of the three-sync CG2D structure
 DYN_BYTES_PER_CELL = 136.0            # MOM_FLUXFORM behind the reference argument list: 17 words
 THERMO_BYTES_PER_CELL = 88.0          # GAD_CALC_RHS + AB2 on the tendency: 11 words per cell and tracer
-# what the fused kernels of this implementation have to move at least, reported beside it
-DYN_BYTES_FUSED = 160.0               # 20 words: MOM_FLUXFORM + TIMESTEP + AB2 fused (19) + phiHyd of CALC_GRAD_PHI_HYD
-THERMO_BYTES_FUSED = 112.0            # 12 words (GAD_CALC_RHS + AB2 + TIMESTEP_TRACER) + 2 (phihyd_kernel: R theta, W phiHyd)
+# (what the kernels actually move is reported beside it from the ncu capture in profiles/r02_traffic.json: with the column
+# geometry of csrc/colgeom.cu the 3-D kernels move LESS than the section-8(d) figures, which count the geometry arrays)
 from mitgcm_b200.model import BENCH_FSIN_AMP as FSIN_AMP      # f = 1e-4 + 6.5e-5 sin(2 pi y / block length)
 T_TOP, T_BOT, T_NOISE = 6.0, 4.0, 0.01
 
@@ -385,12 +384,18 @@ def run_cuda(args, rank, world):
     gbs = lambda nbytes, ms_: float(nbytes / (max(ms_, 1e-9) * 1e-3) / 1e9)
     dom = max(cand, key=lambda k: cand[k][1])
     ach = gbs(*cand[dom])
-    traffic, traffic_src = None, None
-    try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
+    traffic, traffic_src, moved = None, None, {}
+    try:        # DRAM bytes per launch from the committed ncu capture of this workload (not measured in this run)
         tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
-        if tj.get("workload") == f"{NX}x{NY}x{NR}" and dom in tj:
-            traffic = tj[dom]["dram_bytes_per_launch"]
-            traffic_src = f"profiles/{TRAFFIC_FILE} (ncu --set full capture of this workload, not measured in this run)"
+        if tj.get("workload") == f"{NX}x{NY}x{NR}" and not os.environ.get("MITGCM_B200_NO_COLGEOM"):
+            if dom in tj:
+                traffic = tj[dom]["dram_bytes_per_launch"]
+                traffic_src = f"profiles/{TRAFFIC_FILE} (ncu --set full capture of this workload, not measured in this run)"
+            # fraction of the peak on the bytes ncu saw move (CG2D: scaled to this run's iteration count)
+            for k_, ms_ in (("cg2d_kernel", phase[3] / K), ("dyn_kernel", phase[1] / K), ("thermo_kernel", phase[0] / K)):
+                if k_ in tj:
+                    nb = tj[k_]["dram_bytes_per_launch"] * ((tot_iters / K) / 150.0 if k_ == "cg2d_kernel" else 1.0)
+                    moved[k_] = gbs(nb, ms_) / peak
     except Exception:
         pass
     mult = 1 if strong else world
@@ -417,8 +422,7 @@ def run_cuda(args, rank, world):
         "phase_share": shares, "phase_ms_per_step": {n: float(phase[i] / K) for i, n in enumerate(names)},
         "kernel_hbm_gbs": {k: gbs(*v) for k, v in cand.items()},
         "kernel_frac_of_peak": {k: gbs(*v) / peak for k, v in cand.items()},
-        "kernel_frac_of_peak_fused_bytes": {"dyn_kernel": gbs(DYN_BYTES_FUSED * cells, phase[1] / K) / peak,
-                                            "thermo_kernel": gbs(THERMO_BYTES_FUSED * cells, phase[0] / K) / peak},
+        "kernel_frac_of_peak_moved_bytes": moved or None,
         "step_hbm_frac": gbs((DYN_BYTES_PER_CELL + THERMO_BYTES_PER_CELL) * cells
                              + CG2D_BYTES_PER_POINT_ITER * NX * NY * tot_iters / K, ms_per_step) / peak,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
