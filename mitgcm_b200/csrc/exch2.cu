@@ -243,6 +243,14 @@ static bool set_topology(const E2Tables &T) {
       lst.push_back(T.local[dt] * (int)g.slab + (int)(q % g.slab));
       lst.push_back(T.local[st] * (int)g.slab + prov[q] % (int)g.slab);
     }
+  // the gather runs in place and in parallel (f[dst] = f[src]): that equals the buffered two-pass exchange only if no
+  // source of the composed list is itself a destination (sources must be cells no entry writes: interior cells)
+  {
+    std::vector<char> isDst((size_t)g.slab * g.nTiles, 0);
+    for (size_t e = 0; e + 1 < lst.size(); e += 2) isDst[lst[e]] = 1;
+    for (size_t e = 0; e + 1 < lst.size(); e += 2)
+      if (isDst[lst[e + 1]]) return fail(72, "exch2: a halo cell is both source and destination of the composed exchange");
+  }
   if (c.e2List) cudaFree(c.e2List);
   MG_CUDA(cudaMalloc(&c.e2List, std::max<size_t>(lst.size(), 2) * sizeof(int)));
   MG_CUDA(cudaMemcpy(c.e2List, lst.data(), lst.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -285,6 +293,12 @@ static bool set_topology(const E2Tables &T) {
     if (!compile_uv(T, g.sNx, g.sNy, g.OLx, w == 1, pr)) return false;
     std::vector<int> ul;
     uv_list(pr, T.local, g.slab, ul);
+    {      // same in-place condition for the vector pair: (array, cell) written by one entry must not be read by another
+      std::vector<char> isDst[2] = {std::vector<char>((size_t)g.slab * g.nTiles, 0), std::vector<char>((size_t)g.slab * g.nTiles, 0)};
+      for (size_t e = 0; e + 3 < ul.size(); e += 4) isDst[ul[e]][ul[e + 1]] = 1;
+      for (size_t e = 0; e + 3 < ul.size(); e += 4)
+        if (isDst[ul[e + 2] >> 1][ul[e + 3]]) return fail(72, "exch2: a halo cell is both source and destination of the composed vector exchange");
+    }
     if (c.e2UvList[w]) cudaFree(c.e2UvList[w]);
     MG_CUDA(cudaMalloc(&c.e2UvList[w], std::max<size_t>(ul.size(), 4) * sizeof(int)));
     MG_CUDA(cudaMemcpy(c.e2UvList[w], ul.data(), ul.size() * sizeof(int), cudaMemcpyHostToDevice));
