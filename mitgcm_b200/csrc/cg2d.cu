@@ -28,8 +28,12 @@ namespace cgrp = cooperative_groups;
 
 namespace mg {
 
-constexpr int CG_THREADS = 256;
+#ifndef CG_THREADS_N
+#define CG_THREADS_N 256
+#endif
+constexpr int CG_THREADS = CG_THREADS_N;      // 256: two CTAs per SM; 512: one (half as many participants in the grid barrier)
 constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int CG_MINB = 512 / CG_THREADS;
 constexpr int MAX_PART = 2048;   // max CTAs in the cooperative grid
 
 struct Cg2dOut {
@@ -752,7 +756,7 @@ __device__ void phase_ca2(const Cg2dArgs &a, const double *__restrict__ rOld, do
   block_partials<2, false>(a, acc, sm);
 }
 
-__global__ void __launch_bounds__(CG_THREADS, 2) cg2d_kernel(Cg2dArgs a) {
+__global__ void __launch_bounds__(CG_THREADS, CG_MINB) cg2d_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   // Resident strips: with one equal strip per warp (balanced partition) the warp that produces q
@@ -1141,7 +1145,7 @@ __device__ void sr_phase_err(const Cg2dArgs &a, const double *r, double *sm) {
 #ifndef SR_MINB
 #define SR_MINB 4
 #endif
-__global__ void __launch_bounds__(CG_THREADS, SR_MINB) cg2d_sr_kernel(Cg2dArgs a) {
+__global__ void __launch_bounds__(CG_THREADS, SR_MINB * 256 / CG_THREADS) cg2d_sr_kernel(Cg2dArgs a) {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ double sm[4 * CG_WARPS];
   double t1[1], t2[2], t3[3];
@@ -1403,7 +1407,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
     // as many rows of each strip as fit next to a second CTA on the SM (a whole vector of a
     // 2048^2 tile is 227 KB per SM and does not fit: half of every strip stays resident there)
     // (larger carve-outs starve the L1: 100 KB per CTA was measured 25 % slower than none)
-    const int rowsFit = (int)((size_t)(56 * 1024) / ((size_t)CG_WARPS * 64 * sizeof(double)));
+    const int rowsFit = (int)((size_t)(56 * 1024) * (CG_THREADS / 256) / ((size_t)CG_WARPS * 64 * sizeof(double)));
     const int rows = std::min(a.RY2, rowsFit);
     const size_t need = (size_t)CG_WARPS * rows * 64 * sizeof(double);
     int nb = 0;
