@@ -77,6 +77,7 @@ struct Cg2dArgs {
   double cg2dNorm, tolSq;
   int normaliseRHS, maxIters, nIterMinIn;
   int l2mask;            // L2 eviction-priority classes of the vector phases (see L2Pol)
+  int deferX;            // apply the x updates two at a time (every second iteration)
 };
 
 struct Cg2dWs {
@@ -465,8 +466,12 @@ __device__ void phase_ca(const Cg2dArgs &a, const double *rOld, double *rNew, co
 
 // Phase B (cg2d.F:252-289): s = z + beta s on the stencil, q = A s, partial <s,q>.
 // saveMin: store the lowest-residual solution first (cg2d.F:338-351).
+// updX: pending x updates applied in this pass (cg2d.F:311, deferred to share the reads of s): 0 none, 1: x += alphaPrev *
+// sOld, 2: x = (x + alphaPrev2 * s2) + alphaPrev * sOld with s2 = the iterate before sOld, which still sits in the buffer
+// sNew is about to overwrite.  The order of the additions is the reference's (one update per iteration), so deferring one
+// update by an iteration changes no bit of x and saves a read and a write of x every second iteration.
 __device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, double beta, bool saveMin, double alphaPrev,
-                        bool updX, double *sm) {
+                        int updX, double alphaPrev2, double *sm) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -482,11 +487,14 @@ __device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, dou
       double tW = a.z[idx - 1] + beta * sOld[idx - 1];
       double tE = a.z[idx + 1] + beta * sOld[idx + 1];
       double qv = a.aW[idx] * tW + a.aW[idx + 1] * tE + a.aS[idx] * tS + a.aS[idx + PX] * tN + a.aC[idx] * tC;
+      const double s2 = updX == 2 ? sNew[idx] : 0.;
       sNew[idx] = tC;
       a.q[idx] = qv;
       push2(a, it, j, sNew, tC, a.q, qv);
-      if (updX) {   // x += alpha s of the previous iteration (cg2d.F:311), deferred to share the read of s
-        double xv = a.x[idx] + alphaPrev * sOld[idx];
+      if (updX) {   // pending x updates (cg2d.F:311)
+        double xv = a.x[idx];
+        if (updX == 2) xv = xv + alphaPrev2 * s2;
+        xv = xv + alphaPrev * sOld[idx];
         a.x[idx] = xv;
         if (saveMin) a.xmin[idx] = xv;
       } else if (saveMin) a.xmin[idx] = a.x[idx];
@@ -500,7 +508,8 @@ __device__ void phase_b(const Cg2dArgs &a, const double *sOld, double *sNew, dou
 
 // cg2d.F:358-384: restore the min-residual solution, un-normalise.
 __device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending, double rhsNorm,
-                             const double *sLast = nullptr, double alphaLast = 0.0) {
+                             const double *sLast = nullptr, double alphaLast = 0.0, const double *sLast2 = nullptr,
+                             double alphaLast2 = 0.0) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   (void)saveMinPending;
@@ -510,7 +519,8 @@ __device__ void phase_finish(const Cg2dArgs &a, bool useMin, bool saveMinPending
     size_t idx = it.base;
     for (int j = it.j0; j <= it.j1; j++, idx += a.PX) {
       double xv = useMin ? a.xmin[idx] : a.x[idx];
-      if (!useMin && sLast) xv = xv + alphaLast * sLast[idx];   // the x update of the last iteration (cg2d.F:311)
+      if (!useMin && sLast2) xv = xv + alphaLast2 * sLast2[idx];   // the x updates of the last iterations (cg2d.F:311)
+      if (!useMin && sLast) xv = xv + alphaLast * sLast[idx];
       if (a.normaliseRHS) xv = xv / rhsNorm;
       a.x[idx] = xv;
     }
@@ -600,18 +610,19 @@ __device__ __forceinline__ void push2v(const Cg2dArgs &a, const Item2 &it, int j
 }
 
 // R rows of phase B starting at row j (flat index idx of column it.i).
-template <int R>
+template <int R, int updX>      // updX is a template parameter: the second pending iterate costs registers only where it is read
 __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew,
-                                        double beta, bool saveMin, double alphaPrev, bool updX, const Item2 &it, size_t idx,
+                                        double beta, bool saveMin, double alphaPrev, double alphaPrev2, const Item2 &it, size_t idx,
                                         int j, double2 &tS, double2 &tC, double2 &aSj, double2 &sC, double &acc,
                                         double *wb, bool zRes, const L2Pol &pl) {
   const int PX = a.PX;
-  double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R];
+  double2 zN[R], sN[R], aSN[R], aWv[R], aCv[R], xv[R], s2[updX == 2 ? R : 1];
   double zW[R], sW[R], zE[R], sE[R], aWEl[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     size_t id = idx + (size_t)r * PX;
     zN[r] = sN[r] = aSN[r] = aWv[r] = aCv[r] = xv[r] = make_double2(0.0, 0.0);
+    if (updX == 2) s2[updX == 2 ? r : 0] = make_double2(0.0, 0.0);
     zW[r] = sW[r] = zE[r] = sE[r] = aWEl[r] = 0.0;
     if (it.active) {
       zN[r] = (zRes && j + r + 1 <= it.j1 && j + r + 1 - it.j0 < a.resRows) ? ld2(wb + (size_t)(j + r + 1 - it.j0) * 64) : ld2h(a.z + id + PX, pl.qz);
@@ -620,6 +631,7 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
       aWv[r] = ldg2h(a.aW + id, pl.c);
       aCv[r] = ldg2h(a.aC + id, pl.c);
       if (saveMin || updX) xv[r] = ld2h(a.x + id, pl.x);
+      if (updX == 2) s2[updX == 2 ? r : 0] = ld2h(sNew + id, pl.s);      // the iterate before sOld, about to be overwritten
       if (it.edgeW) { zW[r] = a.z[id - 1]; sW[r] = sOld[id - 1]; }
       if (it.edgeE) { zE[r] = a.z[id + 2]; sE[r] = sOld[id + 2]; aWEl[r] = __ldg(a.aW + id + 2); }
     }
@@ -642,7 +654,8 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
       if (inRes) st2(wb + (size_t)(j + r - it.j0) * 64, qv);   // q replaces the dead z of this row in the resident strip
       if (!inRes || j + r == it.j0 || j + r == it.j1 || it.edgeW || it.edgeE) st2h(a.q + id, qv, pl.qz);   // neighbours read the rim
       push2v(a, it, j + r, sNew, tC, a.q, qv);
-      if (updX) {   // deferred x += alpha s of the previous iteration (sC = old s of this row)
+      if (updX) {   // pending x updates (sC = sOld of this row)
+        if (updX == 2) xv[r] = make_double2(xv[r].x + alphaPrev2 * s2[updX == 2 ? r : 0].x, xv[r].y + alphaPrev2 * s2[updX == 2 ? r : 0].y);
         xv[r] = make_double2(xv[r].x + alphaPrev * sC.x, xv[r].y + alphaPrev * sC.y);
         st2h(a.x + id, xv[r], pl.x);
       }
@@ -654,8 +667,10 @@ __device__ __forceinline__ void b2_rows(const Cg2dArgs &a, const double *__restr
   }
 }
 
+template <int updX>
 __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, double *__restrict__ sNew, double beta,
-                         bool saveMin, double alphaPrev, bool updX, double *sm, double *wb, bool zRes, const L2Pol &pl) {
+                         bool saveMin, double alphaPrev, double alphaPrev2, double *sm, double *wb, bool zRes,
+                         const L2Pol &pl) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * CG_WARPS + (threadIdx.x >> 5), nw = gridDim.x * CG_WARPS;
   const int PX = a.PX;
@@ -672,8 +687,8 @@ __device__ void phase_b2(const Cg2dArgs &a, const double *__restrict__ sOld, dou
       sC = s1;
     }
     int j = it.j0;
-    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
-    if (j <= it.j1) b2_rows<1>(a, sOld, sNew, beta, saveMin, alphaPrev, updX, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
+    for (; j + 1 <= it.j1; j += 2, idx += 2 * (size_t)PX) b2_rows<2, updX>(a, sOld, sNew, beta, saveMin, alphaPrev, alphaPrev2, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
+    if (j <= it.j1) b2_rows<1, updX>(a, sOld, sNew, beta, saveMin, alphaPrev, alphaPrev2, it, idx, j, tS, tC, aSj, sC, acc[0], wb, zRes, pl);
   }
   block_partials<1, false>(a, acc, sm);
 }
@@ -806,29 +821,39 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MINB) cg2d_kernel(Cg2dArgs a) {
   double eta_qrNM1 = 1.0;
   int cur = 0;              // r[cur] / s[cur] hold the current iterate
   bool saveMin = false;     // x_min = x is pending (done inside the next phase B)
-  const double *sLast = nullptr;   // s and alpha of the last iteration: its x update is still pending
-  double alphaLast = 0.0;
+  // pending x updates (cg2d.F:311 deferred): nPend = 0, 1, 2; alphaLast goes with s[scur] (the latest iterate), alphaLast2
+  // with the iterate before it, which sits in s[scur ^ 1] until the next phase B overwrites it
+  int nPend = 0, scur = 0;          // s[scur] holds the current search direction (with halos)
+  double alphaLast = 0.0, alphaLast2 = 0.0;
 
   if (!(err_sq < a.tolSq)) {
     // z = M r for the first iteration
     phase_ca(a, a.r[0], a.r[1], a.s[0], 0.0, true, sm);
     cur = 1;   // r[1] now holds r (with halos); s[0] is the (zero) current s
-    int scur = 0;
     if (!a.ll) grid.sync();
     grid_totals<2, false>(a, t2, sm, rseq);
     double eta_qrN = t2[1];
     for (int it2d = 1; it2d <= a.maxIters; it2d++) {
       const double cgBeta = eta_qrN / eta_qrNM1;
       eta_qrNM1 = eta_qrN;
-      if (a.vec2) phase_b2(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm, wb, wb != nullptr && it2d > 1, pl);
-      else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, sLast != nullptr, sm);
+      // two pending updates must go now (the older iterate is overwritten in this pass); a single one waits for the next
+      // pass unless the solution is wanted (x_min) or deferral is off
+      const int updX = nPend == 2 ? 2 : (nPend == 1 && (saveMin || !a.deferX)) ? 1 : 0;
+      if (a.vec2) {
+        const bool zRes = wb != nullptr && it2d > 1;
+        if (updX == 2) phase_b2<2>(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, alphaLast2, sm, wb, zRes, pl);
+        else if (updX == 1) phase_b2<1>(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, alphaLast2, sm, wb, zRes, pl);
+        else phase_b2<0>(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, alphaLast2, sm, wb, zRes, pl);
+      } else phase_b(a, a.s[scur], a.s[scur ^ 1], cgBeta, saveMin, alphaLast, updX, alphaLast2, sm);
+      if (updX) nPend = 0;
       saveMin = false;
       scur ^= 1;
       if (!a.ll) grid.sync();
       grid_totals<1, false>(a, t1, sm, rseq);
       const double alpha = eta_qrN / t1[0];
-      sLast = a.s[scur];
+      alphaLast2 = alphaLast;      // (meaningful only while nPend == 1: it then goes with the previous iterate)
       alphaLast = alpha;
+      nPend++;
       if (a.vec2) phase_ca2(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, sm, wb, pl);
       else phase_ca(a, a.r[cur], a.r[cur ^ 1], a.s[scur], alpha, false, sm);
       cur ^= 1;
@@ -849,7 +874,7 @@ __global__ void __launch_bounds__(CG_THREADS, CG_MINB) cg2d_kernel(Cg2dArgs a) {
   // a pending x_min = x copy only matters if x_min is used, i.e. err_sq > minResidualSq, which
   // cannot hold for the iterate that set minResidualSq = err_sq; so it can be dropped.
   const bool useMin = (nIterMin >= 0 && err_sq > minResidualSq);
-  phase_finish(a, useMin, saveMin, rhsNorm, sLast, alphaLast);
+  phase_finish(a, useMin, saveMin, rhsNorm, nPend >= 1 ? a.s[scur] : nullptr, alphaLast, nPend == 2 ? a.s[scur ^ 1] : nullptr, alphaLast2);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.out->firstResidual = firstResidual;
     a.out->minResidualSq = minResidualSq;
@@ -1380,6 +1405,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   a.normaliseRHS = c.p.I(MI_CG2DNORMALISERHS);
   a.maxIters = *numIters; a.nIterMinIn = *nIterMin;
   a.l2mask = getenv("MITGCM_B200_CG2D_L2") ? atoi(getenv("MITGCM_B200_CG2D_L2")) : 0;
+  a.deferX = getenv("MITGCM_B200_CG2D_NODEFERX") ? 0 : 1;
   // Work decomposition.  Warp items are column strips (32 columns scalar / 64 columns vector)
   // of RY rows; RY is chosen so that every co-resident warp gets one item of equal size
   // (balanced: no tail), but never fewer than 2 rows.

@@ -100,6 +100,42 @@ def test_min_residual_solution(rt):
         assert relerr(xg[:, :, jj, ii], xo[:, :, jj, ii]) < 1e-9
 
 
+@pytest.mark.parametrize("case", [CASES[0], CASES[4], CASES[5]], ids=lambda c: "x".join(str(v) for v in c.values()))
+def test_deferred_x_update_changes_no_bit(rt, case, monkeypatch):
+    """cg2d.cu applies the x updates of cg2d.F:311 two at a time, x = (x + a1 s1) + a2 s2, every second iteration (one
+    read and one write of x saved per two iterations): the additions keep the reference's order, so x must be
+    bit-identical to the run that updates every iteration (MITGCM_B200_CG2D_NODEFERX=1) -- for odd and even iteration
+    counts (one or two updates pending at the end), with the minimum-residual copy, and for the converged solve."""
+    g = make_grid(**case, seed=13)
+    o, op, b, x = cg2d_problem(g, tol=1e-30)
+    o2, op2, b2, x2 = cg2d_problem(g, tol=1e-9)
+    setup(rt, g, op)
+    for nit, nmin in ((1, -1), (2, -1), (3, -1), (4, -1), (7, -1), (24, -1), (25, -1), (30, 0), (31, 0)):
+        outs = []
+        for env in (None, "1"):
+            if env:
+                monkeypatch.setenv("MITGCM_B200_CG2D_NODEFERX", env)
+            else:
+                monkeypatch.delenv("MITGCM_B200_CG2D_NODEFERX", raising=False)
+            bg, xg = b.copy(), x.copy()
+            r = rt.cg2d(bg, xg, nit, nmin)
+            outs.append((xg, r))
+        assert outs[0][1]["numIters"] == outs[1][1]["numIters"] == nit
+        assert outs[0][1]["nIterMin"] == outs[1][1]["nIterMin"]
+        assert np.array_equal(outs[0][0], outs[1][0]), (nit, nmin)
+    rt.set_cg2d_operator(op2)
+    outs = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("MITGCM_B200_CG2D_NODEFERX", env)
+        else:
+            monkeypatch.delenv("MITGCM_B200_CG2D_NODEFERX", raising=False)
+        bg, xg = b2.copy(), x2.copy()
+        outs.append((xg, rt.cg2d(bg, xg, 2000, -1)))
+    assert outs[0][1]["numIters"] == outs[1][1]["numIters"]
+    assert np.array_equal(outs[0][0], outs[1][0])
+
+
 def test_early_exit_when_first_guess_solves(rt):
     g = make_grid(40, 24, 2, seed=9)
     o, op, b, x = cg2d_problem(g, tol=1e-7)
