@@ -644,10 +644,13 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
           vp.myFace = c.csFace.empty() ? 0 : c.csFace[t];
           if (!semiImpl && vi_fast_ok(g, vp)) {
             if (!c.attrVi) {
-              MG_CUDA(cudaFuncSetAttribute(vi_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViPipeSmem)));
+              MG_CUDA(cudaFuncSetAttribute(vi_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViPipeSmem)));
+              MG_CUDA(cudaFuncSetAttribute(vi_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ViPipeSmem)));
               c.attrVi = true;
             }
-            vi_pipe_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ViPipeSmem),
+            // the column-geometry form of this kernel was measured SLOWER (21.5 vs 19.9 ms at 2048^2 x 50: it is issue-bound,
+            // and filling the geometry slots costs instructions): kept for experiments only (MITGCM_B200_VI_COLGEOM=1)
+            ((getenv("MITGCM_B200_VI_COLGEOM") && attach_col_geom(bi, bj, tg)) ? vi_pipe_kernel<true> : vi_pipe_kernel<false>)<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), sizeof(ViPipeSmem),
                              c.stream>>>(tg, st, vp, sfU + o2, sfV + o2, gU + o3, gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),
                                          abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? phiHyd + o3 : nullptr);
           } else if (!getenv("MITGCM_B200_VI_NOTILE") && !vp.highOrderVorticity && !vp.upwindVorticity)   // C4 reads j+2: past the patch

@@ -22,6 +22,10 @@ struct ViPipeSmem {
   double raw[2][VR_N][FT_N];      // ring: u, v, hFacW, hFacS, recip_hFacC of level k; w, maskC of level k+1
   double hZ[FT_N], z3[FT_N], om[FT_N], KE[FT_N], hD[FT_N], wA[FT_N], mCk[FT_N];
   double dxG[FT_N], dyG[FT_N], dxC[FT_N], dyC[FT_N], rAzI[FT_N], rA[FT_N], rrA[FT_N], fG[FT_N];
+  // column geometry of the patch (CG variant, colgeom.cu): the four geometry slots of the ring are then FILLED by
+  // compare + select from these instead of being fetched, so everything downstream reads the same shared memory
+  double hLW[FT_N], hLS[FT_N], rhLC[FT_N];
+  int kLW[FT_N], kLS[FT_N], kLC[FT_N];
 };
 
 struct ViRingSrc {
@@ -47,23 +51,32 @@ struct ViRingAcc {
   __device__ double hDiv(int i, int j) const { return sm.hD[e(i, j)]; }
 };
 
+template <bool CG>
 __device__ __forceinline__ void vi_pipe_prefetch(ViPipeSmem &sm, int slot, int e, size_t sg, const TileGrid &g,
                                                  const MomState &st, size_t slab, int k, bool below) {
   const size_t q = sg + slab * (size_t)(k - 1);
   __pipeline_memcpy_async(&sm.raw[slot][VR_U][e], st.u + q, 8);
   __pipeline_memcpy_async(&sm.raw[slot][VR_V][e], st.v + q, 8);
-  __pipeline_memcpy_async(&sm.raw[slot][VR_HW][e], g.hFacW + q, 8);
-  __pipeline_memcpy_async(&sm.raw[slot][VR_HS][e], g.hFacS + q, 8);
-  __pipeline_memcpy_async(&sm.raw[slot][VR_RHC][e], g.recip_hFacC + q, 8);
+  if (CG) {      // plain stores into the slot nobody reads before the next barrier
+    sm.raw[slot][VR_HW][e] = cg_hfac(k, sm.kLW[e], sm.hLW[e]);
+    sm.raw[slot][VR_HS][e] = cg_hfac(k, sm.kLS[e], sm.hLS[e]);
+    sm.raw[slot][VR_RHC][e] = cg_hfac(k, sm.kLC[e], sm.rhLC[e]);
+  } else {
+    __pipeline_memcpy_async(&sm.raw[slot][VR_HW][e], g.hFacW + q, 8);
+    __pipeline_memcpy_async(&sm.raw[slot][VR_HS][e], g.hFacS + q, 8);
+    __pipeline_memcpy_async(&sm.raw[slot][VR_RHC][e], g.recip_hFacC + q, 8);
+  }
   if (below) {
     __pipeline_memcpy_async(&sm.raw[slot][VR_W][e], st.w + q + slab, 8);
-    __pipeline_memcpy_async(&sm.raw[slot][VR_MC][e], g.maskC + q + slab, 8);
+    if (CG) sm.raw[slot][VR_MC][e] = cg_mask(k + 1, sm.kLC[e]);
+    else __pipeline_memcpy_async(&sm.raw[slot][VR_MC][e], g.maskC + q + slab, 8);
   }
 }
 
 #ifndef VIP_MINB
 #define VIP_MINB 2
 #endif
+template <bool CG>
 __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
     vi_pipe_kernel(TileGrid g, MomState st, ViPar vp, const double *__restrict__ sfU, const double *__restrict__ sfV,
                    double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
@@ -111,7 +124,10 @@ __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
   // own-column values carried between levels
   const size_t slab = g.slab;
   double uKm1 = 0., vKm1 = 0.;
-  double uK = st.u[s], vK = st.v[s], mWk = g.maskW[s], mSk = g.maskS[s];
+  int kLoW = 0, kLoS = 0;
+  double rhLoW = 0., rhLoS = 0.;
+  if (CG) { kLoW = g.kLowW[s]; kLoS = g.kLowS[s]; rhLoW = g.rhLowW[s]; rhLoS = g.rhLowS[s]; }
+  double uK = st.u[s], vK = st.v[s], mWk = CG ? cg_mask(1, kLoW) : g.maskW[s], mSk = CG ? cg_mask(1, kLoS) : g.maskS[s];
   // k-invariant patch metrics, the interface of level 1 (w*rA and maskC of level 1: MOM_VI_{U,V}_VERTSHEAR at
   // k = 1 reads them with mask_Km1 = 0), and the asynchronous prefetch of level 1 into ring slot 1
   int rb = 1;
@@ -122,8 +138,13 @@ __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
       sm.dxG[e] = g.dxG[sg[r]]; sm.dyG[e] = g.dyG[sg[r]]; sm.dxC[e] = g.dxC[sg[r]]; sm.dyC[e] = g.dyC[sg[r]];
       sm.rAzI[e] = g.recip_rAz[sg[r]]; sm.rA[e] = g.rA[sg[r]]; sm.rrA[e] = g.recip_rA[sg[r]]; sm.fG[e] = g.fCoriG[sg[r]];
       sm.wA[e] = st.w[sg[r]] * g.rA[sg[r]];
-      sm.raw[0][VR_MC][e] = g.maskC[sg[r]];
-      vi_pipe_prefetch(sm, 1, e, sg[r], g, st, slab, 1, 1 + 1 <= g.Nr);
+      if (CG) {
+        sm.kLW[e] = g.kLowW[sg[r]]; sm.hLW[e] = g.hLowW[sg[r]]; sm.kLS[e] = g.kLowS[sg[r]]; sm.hLS[e] = g.hLowS[sg[r]];
+        sm.kLC[e] = g.kLowC[sg[r]]; sm.rhLC[e] = g.rhLowC[sg[r]];
+        sm.raw[0][VR_MC][e] = cg_mask(1, sm.kLC[e]);
+      } else
+        sm.raw[0][VR_MC][e] = g.maskC[sg[r]];
+      vi_pipe_prefetch<CG>(sm, 1, e, sg[r], g, st, slab, 1, 1 + 1 <= g.Nr);
     }
   __pipeline_commit();
   __syncthreads();
@@ -140,8 +161,11 @@ __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
     const size_t s3 = s + ko;
     double uKp1 = 0., vKp1 = 0., mWkp1 = 0., mSkp1 = 0.;
     const double kapUkp1 = st.kapU[s3 + slab], kapVkp1 = st.kapV[s3 + slab];
-    if (below) { uKp1 = st.u[s3 + slab]; vKp1 = st.v[s3 + slab]; mWkp1 = g.maskW[s3 + slab]; mSkp1 = g.maskS[s3 + slab]; }
-    const double rhW = g.recip_hFacW[s3], rhS = g.recip_hFacS[s3];
+    if (below) {
+      uKp1 = st.u[s3 + slab]; vKp1 = st.v[s3 + slab];
+      mWkp1 = CG ? cg_mask(k + 1, kLoW) : g.maskW[s3 + slab]; mSkp1 = CG ? cg_mask(k + 1, kLoS) : g.maskS[s3 + slab];
+    }
+    const double rhW = CG ? cg_hfac(k, kLoW, rhLoW) : g.recip_hFacW[s3], rhS = CG ? cg_hfac(k, kLoS, rhLoS) : g.recip_hFacS[s3];
     const double guOld = guNm1[s3], gvOld = gvNm1[s3];
     double dpx = 0., dpy = 0.;
     if (phiHyd) {
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(FT_X *FT_Y, VIP_MINB)
     if (below) {      // prefetch level k+1 into the other slot while this level is computed
 #pragma unroll
       for (int r = 0; r < 2; r++)
-        if (sv_[r]) vi_pipe_prefetch(sm, rb ^ 1, se[r], sg[r], g, st, slab, k + 1, k + 2 <= g.Nr);
+        if (sv_[r]) vi_pipe_prefetch<CG>(sm, rb ^ 1, se[r], sg[r], g, st, slab, k + 1, k + 2 <= g.Nr);
     }
     __pipeline_commit();
     if (active) {

@@ -182,7 +182,8 @@ def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeyp
             assert np.array_equal(o[n], outs[0][n]), n
 
 
-@pytest.mark.parametrize("opts", [dict(buoyancyLinear=1), dict(buoyancyLinear=0, rigidLid=1)], ids=["free-surface", "rigid-lid"])
+@pytest.mark.parametrize("opts", [dict(buoyancyLinear=1), dict(buoyancyLinear=0, rigidLid=1),
+                                  dict(buoyancyLinear=1, vectorInvariantMomentum=1)], ids=["free-surface", "rigid-lid", "vecinv"])
 def test_column_geometry_kernels_are_bit_identical_to_the_3d_array_kernels(monkeypatch, opts):
     """csrc/colgeom.cu: with z-level geometry (land, partial bottom cells) the step kernels rebuild hFac / mask /
     recip_hFac per column from (kLow, hLow) instead of reading the nine 3-D arrays; the fields after 3 steps must be
@@ -193,6 +194,8 @@ def test_column_geometry_kernels_are_bit_identical_to_the_3d_array_kernels(monke
         monkeypatch.delenv("MITGCM_B200_NO_COLGEOM", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
+        if opts.get("vectorInvariantMomentum"):      # off by default for MOM_VECINV (measured slower): switch it on here
+            monkeypatch.setenv("MITGCM_B200_VI_COLGEOM", "1")
         g, P, s = make_channel(sNx=70, sNy=44, Nr=7, nSx=2, nSy=1, land_frac=0.15, **opts)
         co = ChannelOracle(g, P, s)
         m = Model(g, P, s, co.op)
