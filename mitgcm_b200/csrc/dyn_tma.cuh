@@ -349,8 +349,15 @@ struct DynTmaSmemCG {
   double uT[FT_N], vT[FT_N], wA[FT_N], hZ[FT_N], hC[FT_N], dyG[FT_N], dxG[FT_N], rA[FT_N];
   double hLW[FT_N], hLS[FT_N], hLC[FT_N];
   int kLW[FT_N], kLS[FT_N], kLC[FT_N];
+  // CALC_PHI_HYD fused (PHIF): the PHI slot of the ring carries theta, every patch cell integrates its own column
+  double phi[FT_N], dM[FT_NRMAX], dP[FT_NRMAX], tRf[FT_NRMAX];
   VertSmem vs;
   uint64_t full[NST];
+};
+// linear equation of state + the vertical grid CALC_PHI_HYD integrates over (phys.cuh: phihyd_kernel, same expressions)
+struct PhiFuse {
+  double rhoNil, dRho, tAlpha, gravity, recip_rhoConst;
+  const double *tRef, *rF, *rC;
 };
 __device__ __forceinline__ void dyn_tma_issue(const DynTmaMaps &m, DynTmaStageCG &s, uint64_t *bar, int x0, int y0, int k, int Nr,
                                               bool hasPhi) {
@@ -401,8 +408,8 @@ __device__ __forceinline__ double dyn_dmask(const SM &sm, const ST &S, int e, in
   else return S.patch[DP_MC][e] - sm.mCk[e];
 }
 
-template <int NST, int ROLE, class SM>
-__device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, const TileGrid &g, const MomState &st,
+template <int NST, int ROLE, bool PHIF, class SM>
+__device__ __forceinline__ void dyn_uv_levels(const PhiFuse &pf, SM &sm, const DynTmaMaps &maps, const TileGrid &g, const MomState &st,
                                               const MomPar &p, const double *__restrict__ sf, double *__restrict__ gOut,
                                               double *__restrict__ gNm1, double deltaTMom, double abFac, int momForcing,
                                               int dissInAB, int hasPhi, int t, int i, int j, bool active, bool hzok, int c,
@@ -451,6 +458,7 @@ __device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, co
   double fkm = 0.;
   if (!p.rigidLid) fkm = (0.5 * (sm.wA[c - dP] + sm.wA[c])) * fK;
   double fVrUp = 0.;
+  double phiF = 0.;                 // PHIF: potential at the upper face of level k of MY patch cell (thread t < FT_N)
   dyn_uv_bar();
   int rb = 0;                       // ring slot of level k; rp = slot of level k-1 (freed after the derive phase)
   for (int k = 1; k <= g.Nr; k++) {
@@ -480,6 +488,12 @@ __device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, co
       sm.uT[e] = S.patch[P_U][e] * (sm.dyG[e] * drFk * hW);
       sm.vT[e] = S.patch[P_V][e] * (sm.dxG[e] * drFk * hS);
       if (below) sm.wA[e] = S.patch[P_W][e] * sm.rA[e];
+      if constexpr (PHIF) {      // CALC_PHI_HYD (calc_phi_hyd.F:240-262), the expressions of phihyd_kernel
+        const double a_ = pf.rhoNil * (0. - pf.tAlpha * (S.patch[P_PHI][e] - sm.tRf[k - 1])) + pf.dRho;
+        const double phiC = phiF + sm.dM[k - 1] * pf.gravity * a_ * pf.recip_rhoConst;
+        phiF = phiC + sm.dP[k - 1] * pf.gravity * a_ * pf.recip_rhoConst;
+        sm.phi[e] = phiC;
+      }
       if (hzok) {
         double hWs, hSw;
         if constexpr (CG) { hWs = cg_hfac(k, sm.kLW[e - FT_W], sm.hLW[e - FT_W]); hSw = cg_hfac(k, sm.kLS[e - 1], sm.hLS[e - 1]); }
@@ -509,7 +523,8 @@ __device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, co
       else rh = S.own[O_RH][co];
       const double gOld = S.own[O_G][co];
       double dp = 0.;
-      if (hasPhi) dp = gp * 1. * (S.patch[P_PHI][c] - S.patch[P_PHI][c - dP]) * 1.;
+      if constexpr (PHIF) dp = gp * 1. * (sm.phi[c] - sm.phi[c - dP]) * 1.;
+      else if (hasPhi) dp = gp * 1. * (S.patch[P_PHI][c] - S.patch[P_PHI][c - dP]) * 1.;
       double fkp = 0.;
       if (below) {      // vertical advective flux at interface k+1 (MOM_U_ADV_WU / MOM_V_ADV_WV)
         const double wA00 = DWA(0, 0), wAn = sm.wA[c - dP];
@@ -639,11 +654,13 @@ __device__ __forceinline__ void dyn_uv_levels(SM &sm, const DynTmaMaps &maps, co
   }
 }
 
-template <int NST, int MINB, bool CG = false>
+template <int NST, int MINB, bool CG = false, bool PHIF = false>
 __global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
     dyn_tma_uv_kernel(const __grid_constant__ DynTmaMaps maps, TileGrid g, MomState st, MomPar p, const double *__restrict__ sfU,
                       const double *__restrict__ sfV, double *__restrict__ gU, double *__restrict__ gV, double *__restrict__ guNm1,
-                      double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB, int hasPhi) {
+                      double *__restrict__ gvNm1, double deltaTMom, double abFac, int momForcing, int dissInAB, int hasPhi,
+                      PhiFuse pf) {
+  static_assert(!PHIF || CG, "the fused CALC_PHI_HYD exists for the column-geometry form only");
   extern __shared__ __align__(1024) unsigned char dyn_tma_smem_raw[];
   typedef typename std::conditional<CG, DynTmaSmemCG<NST>, DynTmaSmemN<NST>>::type SM;
   SM &sm = *reinterpret_cast<SM *>(dyn_tma_smem_raw);
@@ -662,6 +679,15 @@ __global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
     mbar_fence_init();
   }
   stage_vert(sm.vs, g, t, NT);
+  if constexpr (PHIF)
+    for (int k = 1 + t; k <= g.Nr; k += NT) {      // dRlocM, dRlocP of phihyd_kernel (integr_GeoPot = 2)
+      double dRlocM = 0.5 * g.drC[k - 1] * 1.;
+      if (k == 1) dRlocM = (pf.rF[0] - pf.rC[0]) * 1.;
+      double dRlocP;
+      if (k == g.Nr) dRlocP = (pf.rC[k - 1] - pf.rF[k]) * 1.;
+      else dRlocP = 0.5 * g.drC[k] * 1.;
+      sm.dM[k - 1] = dRlocM; sm.dP[k - 1] = dRlocP; sm.tRf[k - 1] = pf.tRef[k - 1];
+    }
   bool hzok = false;
   if (t < FT_N) {
     const int li = t % FT_W, lj = t / FT_W;
@@ -683,10 +709,10 @@ __global__ void __launch_bounds__(2 * FT_X *FT_Y, MINB)
   }
   // the two components run the same level loop, compiled once per component; both sides meet at the named barrier
   if (role == 0)
-    dyn_uv_levels<NST, 0>(sm, maps, g, st, p, sfU, gU, guNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
+    dyn_uv_levels<NST, 0, PHIF>(pf, sm, maps, g, st, p, sfU, gU, guNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
                           c, co, x0, y0);
   else
-    dyn_uv_levels<NST, 1>(sm, maps, g, st, p, sfV, gV, gvNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
+    dyn_uv_levels<NST, 1, PHIF>(pf, sm, maps, g, st, p, sfV, gV, gvNm1, deltaTMom, abFac, momForcing, dissInAB, hasPhi, t, i, j, active, hzok,
                           c, co, x0, y0);
 }
 

@@ -537,7 +537,16 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   // CALC_PHI_HYD for all levels (dynamics.F:436-441 marches it level by level inside DYNAMICS; it only
   // depends on the density of DO_OCEANIC_PHYS, i.e. on theta BEFORE the thermodynamics step, so it runs here).
   // Without IVDC nobody else needs rhoInSitu and the EOS is evaluated on the fly.
-  if (buoy) {
+  // CALC_PHI_HYD rides inside the dynamics kernel when that is the column-geometry TMA kernel in its default shape and the
+  // density needs theta only (no IVDC density array, sBeta = 0): the kernel then integrates the potential of its patch
+  // cells from the theta of BEFORE the thermodynamics step, which CYCLE_TRACER leaves in the other buffer.  The mirror
+  // MG_PHIHYD is not written in that case (nothing else reads it).
+  const bool fusePhi = buoy && !ivdc && q.D(MP_SBETA) == 0. && !vecinv && !semiImpl && c.cgState == 1 && dyn_tma_ok(g, mp) &&
+                       !getenv("MITGCM_B200_NO_COLGEOM") && !getenv("MITGCM_B200_DYN_NOPIPE") && !getenv("MITGCM_B200_DYN_NOTMA") &&
+                       !getenv("MITGCM_B200_DYN_TMA_NOSPLIT") && !getenv("MITGCM_B200_DYN_TMA_STAGES") &&
+                       !getenv("MITGCM_B200_DYN_TMA_MINB") && !getenv("MITGCM_B200_NO_PHIFUSE");
+  const double *thetaBefore = nullptr;      // theta this step started from (set once the tracer step has run)
+  if (buoy && !fusePhi) {
     double *rF = field(MG_RF), *rC = field(MG_RC), *th = field(MG_THETA), *sa = field(MG_SALT);
     double *tRef = field(MG_TREF), *sRef = field(MG_SREF);
     if (!rF || !rC || !th || !sa || !tRef || !sRef) return false;
