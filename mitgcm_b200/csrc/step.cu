@@ -628,6 +628,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
                                            q.D(MP_DIFFKHT), q.D(MP_DIFFK4T), sfT)) return false;
   if (q.I(MI_SALTSTEPPING) && !step_tracer(MG_SALT, MG_SALT2, MG_GSNM1, MG_KAPPARS, q.I(MI_SALTADVSCHEME), q.I(MI_SALTVERTADVSCHEME),
                                            q.D(MP_DIFFKHS), q.D(MP_DIFFK4S), nullptr)) return false;
+  if (fusePhi) thetaBefore = field(q.I(MI_TEMPSTEPPING) ? MG_THETA2 : MG_THETA);      // CYCLE_TRACER swapped the buffers
   // multi-rank, peer pushes: the new theta / salt halos travel on the side stream while DYNAMICS and CG2D run
   // (the NCCL path of mitgcm_b200/distributed.py exchanges them at the end of the step instead)
   if (peerHalo) {
@@ -676,7 +677,15 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
         } else if (!semiImpl && dyn_tma_ok(g, mp) && !getenv("MITGCM_B200_DYN_NOPIPE") && !getenv("MITGCM_B200_DYN_NOTMA")) {
           // operands staged by TMA (dyn_tma.cuh); the cp.async kernel below stays as the A/B reference
           DynTmaMaps maps;
-          if (!dyn_tma_maps(tg, st, guN + o3, gvN + o3, buoy ? phiHyd + o3 : nullptr, maps)) return fail(63, "forward_step: cuTensorMapEncodeTiled failed");
+          const bool phiF = fusePhi && thetaBefore && c.cgState == 1;
+          if (!dyn_tma_maps(tg, st, guN + o3, gvN + o3, phiF ? thetaBefore + o3 : (buoy ? phiHyd + o3 : nullptr), maps)) return fail(63, "forward_step: cuTensorMapEncodeTiled failed");
+          PhiFuse pf{};
+          if (phiF) {
+            pf.rhoNil = q.D(MP_RHONIL); pf.dRho = q.D(MP_RHONIL) - q.D(MP_RHOCONST); pf.tAlpha = q.D(MP_TALPHA);
+            pf.gravity = q.D(MP_GRAVITY); pf.recip_rhoConst = 1.0 / q.D(MP_RHOCONST);
+            pf.tRef = field(MG_TREF); pf.rF = field(MG_RF); pf.rC = field(MG_RC);
+            if (!pf.tRef || !pf.rF || !pf.rC) return false;
+          } else if (fusePhi) return fail(64, "forward_step: fused CALC_PHI_HYD was planned but the dynamics kernel cannot take it");
           const int smemBytes = (int)sizeof(DynTmaSmem) + 128;
           if (!c.attrDynTma) {
             MG_CUDA(cudaFuncSetAttribute(dyn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
@@ -687,31 +696,34 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
             // at 64 registers: 9.06; 4: 8.87; the 256-thread dyn_tma_kernel: 9.75)
             const int nst = getenv("MITGCM_B200_DYN_TMA_STAGES") ? atoi(getenv("MITGCM_B200_DYN_TMA_STAGES")) : 3;
             const dim3 grdT((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), blkT(FT_X, FT_Y, 2);
-#define DYN_UV_LAUNCH(NST, MINB, CGF)                                                                                         \
+#define DYN_UV_LAUNCH(NST, MINB, CGF, PHF)                                                                                    \
   {                                                                                                                           \
     const int smB = (int)(CGF ? sizeof(DynTmaSmemCG<NST>) : sizeof(DynTmaSmemN<NST>)) + 128;                                  \
-    const int key = NST + 16 * MINB + (CGF ? 256 : 0);                                                                        \
+    const int key = NST + 16 * MINB + (CGF ? 256 : 0) + (PHF ? 512 : 0);                                                      \
     if (c.attrDynTmaUV != key) {                                                                                              \
-      MG_CUDA(cudaFuncSetAttribute(dyn_tma_uv_kernel<NST, MINB, CGF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smB));     \
+      MG_CUDA(cudaFuncSetAttribute(dyn_tma_uv_kernel<NST, MINB, CGF, PHF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smB)); \
       c.attrDynTmaUV = key;                                                                                                   \
     }                                                                                                                         \
-    dyn_tma_uv_kernel<NST, MINB, CGF><<<grdT, blkT, smB, c.stream>>>(maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3, gV + o3,  \
-                                                                     guN + o3, gvN + o3, q.D(MP_DELTATMOM), abFac,            \
-                                                                     q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), buoy ? 1 : 0); \
+    dyn_tma_uv_kernel<NST, MINB, CGF, PHF><<<grdT, blkT, smB, c.stream>>>(maps, tg, st, mp, sfU + o2, sfV + o2, gU + o3,      \
+                                                                          gV + o3, guN + o3, gvN + o3, q.D(MP_DELTATMOM),     \
+                                                                          abFac, q.I(MI_MOMFORCING), q.I(MI_MOMDISSIP_IN_AB), \
+                                                                          buoy ? 1 : 0, pf);                                  \
   }
             if (attach_col_geom(bi, bj, tg)) {      // geometry from (kLow, hLow) per column: 8 instead of 16 boxes per level
               // 20 KB stages: three of them fit twice per SM (measured at 2048^2 x 50: <3,2> 8.08 ms, <2,2> 8.12, <3,1> 8.39, <4,1> 8.44;
               // the 3-D-array form <3,1>: 8.76)
               const int minb = getenv("MITGCM_B200_DYN_TMA_MINB") ? atoi(getenv("MITGCM_B200_DYN_TMA_MINB")) : 2;
-              if (nst == 2) DYN_UV_LAUNCH(2, 2, true)
-              else if (nst == 4) DYN_UV_LAUNCH(4, 1, true)
-              else if (nst == 5) DYN_UV_LAUNCH(5, 1, true)
-              else if (minb == 2) DYN_UV_LAUNCH(3, 2, true)
-              else DYN_UV_LAUNCH(3, 1, true)
-            } else if (nst == 3) DYN_UV_LAUNCH(3, 1, false)
-            else if (nst == 4) DYN_UV_LAUNCH(4, 1, false)
-            else if (nst == 5) DYN_UV_LAUNCH(5, 1, false)
-            else DYN_UV_LAUNCH(2, 2, false)
+              if (phiF) DYN_UV_LAUNCH(3, 2, true, true)      // (fusePhi implies the default shape)
+              else if (nst == 2) DYN_UV_LAUNCH(2, 2, true, false)
+              else if (nst == 4) DYN_UV_LAUNCH(4, 1, true, false)
+              else if (nst == 5) DYN_UV_LAUNCH(5, 1, true, false)
+              else if (minb == 2) DYN_UV_LAUNCH(3, 2, true, false)
+              else DYN_UV_LAUNCH(3, 1, true, false)
+            } else if (phiF) return fail(64, "forward_step: fused CALC_PHI_HYD without the column geometry");
+            else if (nst == 3) DYN_UV_LAUNCH(3, 1, false, false)
+            else if (nst == 4) DYN_UV_LAUNCH(4, 1, false, false)
+            else if (nst == 5) DYN_UV_LAUNCH(5, 1, false, false)
+            else DYN_UV_LAUNCH(2, 2, false, false)
 #undef DYN_UV_LAUNCH
           } else
           dyn_tma_kernel<<<dim3((g.sNx + 2 + FT_X - 1) / FT_X, (g.sNy + 2 + FT_Y - 1) / FT_Y), dim3(FT_X, FT_Y), smemBytes, c.stream>>>(

@@ -159,12 +159,12 @@ def test_dyn_tma_kernel_is_identical_to_the_cp_async_and_generic_kernels(monkeyp
     outs = []
     # default: the role-split TMA kernel (dyn_tma_uv_kernel: U and V on two thread groups); then the 256-thread one
     NC = {"MITGCM_B200_NO_COLGEOM": "1"}      # the 3-D-array form of every kernel (default: geometry per column, colgeom.cu)
-    for env in ({}, {"MITGCM_B200_DYN_TMA_STAGES": "2"}, {"MITGCM_B200_DYN_TMA_MINB": "1"}, {"MITGCM_B200_DYN_TMA_STAGES": "4"},
+    for env in ({}, {"MITGCM_B200_NO_PHIFUSE": "1"}, {"MITGCM_B200_DYN_TMA_STAGES": "2"}, {"MITGCM_B200_DYN_TMA_MINB": "1"}, {"MITGCM_B200_DYN_TMA_STAGES": "4"},
                 {"MITGCM_B200_DYN_TMA_STAGES": "5"}, NC, dict(NC, MITGCM_B200_DYN_TMA_STAGES="2"),
                 dict(NC, MITGCM_B200_DYN_TMA_STAGES="4"), dict(NC, MITGCM_B200_DYN_TMA_STAGES="5"),
                 dict(NC, MITGCM_B200_DYN_TMA_NOSPLIT="1"), dict(NC, MITGCM_B200_DYN_NOTMA="1"), {"MITGCM_B200_GENERIC_STEP": "1"}):
         for k in ("MITGCM_B200_DYN_NOTMA", "MITGCM_B200_GENERIC_STEP", "MITGCM_B200_DYN_TMA_NOSPLIT", "MITGCM_B200_DYN_TMA_STAGES",
-                  "MITGCM_B200_NO_COLGEOM", "MITGCM_B200_DYN_TMA_MINB"):
+                  "MITGCM_B200_NO_COLGEOM", "MITGCM_B200_DYN_TMA_MINB", "MITGCM_B200_NO_PHIFUSE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
