@@ -179,6 +179,26 @@ def test_device_pointers(rt):
     assert np.abs(xd.cpu().numpy()[:, :, jj, ii] - xo[:, :, jj, ii]).max() < 1e-6 * np.abs(xo).max()
 
 
+def test_page_locked_host_arrays(rt):
+    """mitgcm_b200_pin_host_ (what the cg2d.F shim does once for the COMMON arrays cg2d_b, cg2d_x): the same bits as
+    with pageable arrays; pinning an array twice is accepted; finalize() unpins."""
+    g = make_grid(64, 48, 2, nSx=2, seed=13)
+    o, op, b, x = cg2d_problem(g, tol=1e-9)
+    setup(rt, g, op)
+    b1, x1 = b.copy(), x.copy()
+    r1 = rt.cg2d(b1, x1, 2000, -1)
+    b2, x2 = np.empty_like(b), np.empty_like(x)
+    rt.pin_host(b2)
+    rt.pin_host(x2)
+    rt.pin_host(x2)
+    for _ in range(2):          # the caller refills the same arrays every step
+        b2[...] = b
+        x2[...] = x
+        r2 = rt.cg2d(b2, x2, 2000, -1)
+        assert r2["numIters"] == r1["numIters"]
+        assert np.array_equal(x2, x1) and np.array_equal(b2, b1)
+
+
 def test_barotropic_gyre_golden_with_cuda_solver(rt):
     """Config 1 end to end with the CUDA solver in the loop: the reference's own acceptance
     quantity (cg2d_init_res of every step, verification/testreport:267-270) and the iteration
