@@ -1,5 +1,7 @@
 """CG3D timing on a synthetic doubly-periodic flat-bottom box (device-resident b, x).
-usage: python scripts/cg3d_perf.py [N=512] [Nr=50] [iters=50] [reps=3]"""
+usage: python scripts/cg3d_perf.py [N=512] [Nr=50] [iters=50] [reps=3] [sweep|smem]
+sweep: time the four-sweep kernel and every variant of the fused kernel (csrc/cg3d.cu) in one process.
+smem: the default variant with 0, 4, 8, ... levels of z' in shared memory."""
 import os
 import sys
 import time
@@ -43,7 +45,17 @@ rt.set_cg3d_operator(dict(aW3d=full(aH * norm), aS3d=full(aH * norm), aV3d=aVk, 
 rt.fill_field("maskC", 1.0)
 g = torch.Generator(device="cuda").manual_seed(1)
 jj, ii = d.interior()
-for rep in range(reps):
+sweep = len(sys.argv) > 5 and sys.argv[5] == "sweep"
+configs = [("default", {})]
+if sweep:
+    configs = [("four-sweep", {"MITGCM_B200_CG3D_UNFUSED": "1"})] + [
+        (f"fused variant {v}", {"MITGCM_B200_CG3D_VARIANT": str(v)}) for v in range(4)]
+if len(sys.argv) > 5 and sys.argv[5] == "smem":
+    configs = [(f"fused, <= {n} levels in shared memory", {"MITGCM_B200_CG3D_SMEM_LEVELS": str(n)}) for n in (0, 4, 8, 12, 16, 24, 32)]
+for label, env in [c for c in configs for _ in range(reps)]:
+    for k in ("MITGCM_B200_CG3D_UNFUSED", "MITGCM_B200_CG3D_VARIANT", "MITGCM_B200_CG3D_SMEM_LEVELS"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
     b = torch.zeros(d.shape3, dtype=torch.float64, device="cuda")
     b[..., jj, ii] = torch.randn((1, 1, Nr, N, N), dtype=torch.float64, device="cuda", generator=g)
     x = torch.zeros_like(b)
@@ -53,7 +65,7 @@ for rep in range(reps):
     torch.cuda.synchronize()
     t = time.perf_counter() - t0
     cells = N * N * Nr
-    print(f"N={N} Nr={Nr} iters={r['numIters']} time={t * 1e3:.2f} ms  {t / r['numIters'] * 1e6:.1f} us/it  "
+    print(f"{label}: N={N} Nr={Nr} iters={r['numIters']} time={t * 1e3:.2f} ms  {t / r['numIters'] * 1e6:.1f} us/it  "
           f"{168.0 * cells * r['numIters'] / t / 1e9:.1f} GB/s (168 B/cell/it) = {168.0 * cells * r['numIters'] / t / 1e9 / 6556.2 * 100:.1f}% of measured HBM peak; "
           f"res {r['firstResidual']:.3e}->{r['lastResidual']:.3e}")
 rt.finalize()
