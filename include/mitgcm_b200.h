@@ -254,18 +254,38 @@ void mitgcm_b200_exch_(const int *id, int *ierr);
  * Fortran order: (W2_maxNeighbours, nTiles), pij (4, W2_maxNeighbours, nTiles).  From then on the
  * width-1 exchange inside CG2D / CG2D_SR follows EXCH2_S3D_RX (exch2_s3d_rx.template) and
  * mitgcm_b200_exch_ follows EXCH2_3D_RX (exch2_3d_rx.template: IGNORE_CORNERS pass, then
- * UPDATE_CORNERS pass) instead of the periodic nSx x nSy tiling.  All tiles live on this GPU. */
+ * UPDATE_CORNERS pass) instead of the periodic nSx x nSy tiling.
+ * One process: all nTiles = nSx*nSy tiles live on this GPU.  Several processes (nPx*nPy > 1 in mitgcm_b200_init_,
+ * peers connected): nTiles is the size of the whole graph, every rank holds nTiles / nRanks of them (W2_myTileList in
+ * increasing tile id) and mitgcm_b200_set_exch2_tile_proc_ must have named the owners; halo cells whose source tile
+ * lives on another rank are then read from that rank's peer arena over NVLink -- the MPI messages of
+ * exch2_send_rx{1,2}.template / exch2_recv_rx{1,2}.template -- and CG2D pushes its edge values into the owner's halo. */
 void mitgcm_b200_set_exch2_topology_(
     const int *nTiles, const int *maxNeighbours, const int *nNeighbours, const int *neighbourId,
     const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
     const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex, const int *tBasey,
     const int *isNedge, const int *isSedge, const int *isEedge, const int *isWedge,
     const int *myTileList, int *ierr);
+/* W2_tileProc(nTiles) (pkg/exch2/W2_EXCH2_TOPOLOGY.h:153-165, set by w2_map_procs.F:91): 1-based number of the process
+ * that owns each tile; process p is rank p-1 of mitgcm_b200_comm_connect_.  Call before mitgcm_b200_set_exch2_topology_
+ * when the graph is spread over several ranks. */
+void mitgcm_b200_set_exch2_tile_proc_(const int *nTiles, const int *tileProc, int *ierr);
 /* EXCH_UV_XY_RL/RS, EXCH_UV_XYZ_RL/RS on a pair of mirrors (eesupp/src/exch_uv_xyz_rx.template): on an exch2
  * tile graph EXCH2_UV_3D_RX (pkg/exch2/exch2_uv_3d_rx.template: two EXCH2_RX2_CUBE passes with the C-grid index
  * offsets of exch2_get_uv_bounds.F, u/v swapped and, when withSigns, negated across rotated facet edges, then
  * the cube-corner fix-ups); on the plain periodic tiling two scalar exchanges. */
 void mitgcm_b200_exch_uv_(const int *idU, const int *idV, const int *withSigns, int *ierr);
+/* Host-only helper (no device needed): the lists rank `myRank` of `nRanks` is given when the tile graph is spread
+ * over ranks (what mitgcm_b200_set_exch2_topology_ uploads there): scalar gather list (2 ints per entry: dst,
+ * owner << 28 | src), the width-1 push table of its tiles (owner << 28 | halo index) and the vector-pair gather list
+ * (4 ints per entry), indices relative to the owning rank's (nTiles / nRanks, sNy+2*OL, sNx+2*OL) arrays.
+ * dims3 = (sNx, sNy, OL); sizes(3): capacities in ints on entry, ints written on return. */
+void mitgcm_b200_exch2_dist_lists_(
+    const int *dims3, const int *nRanks, const int *myRank, const int *tileProc, const int *withSigns, const int *nTiles,
+    const int *maxNeighbours, const int *nNeighbours, const int *neighbourId, const int *opposingSend,
+    const int *neighbourDir, const int *pij, const int *oi, const int *oj, const int *iLo, const int *iHi, const int *jLo,
+    const int *jHi, const int *tBasex, const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge,
+    const int *isWedge, int *sizes, int *scalarOut, int *pushOut, int *uvOut, int *ierr);
 /* Host-only helper (no device needed): the compiled vector-pair exchange of a tile graph as a list of 4-int
  * entries (dst array 0/1, dst flat cell, src array << 1 | negate, src flat cell) over (nTiles, sNy+2*OL,
  * sNx+2*OL) arrays; dims3 = {sNx, sNy, OL}.  Used by the host set-up code and the CPU tests. */

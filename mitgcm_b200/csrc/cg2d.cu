@@ -63,7 +63,7 @@ struct Cg2dArgs {
   double *b, *x;
   double *r[2], *s[2], *q, *z, *xmin, *v;   // v: extra vector of the SR variant
   const int *pushTab;    // bits 0..27 index, bits 28..30 peer slot (0 self, 1 W, 2 E, 3 S, 4 N)
-  long long peerDelta[5];   // byte offset from this rank's workspace block to the peer's mapping of its block
+  long long peerDelta[8];   // byte offset from this rank's workspace block to the peer's mapping of its block, per push-table slot
   int nRanks, myRank;
   struct Mail *mail[8];     // every rank's mailbox array (peer-mapped), indexed by rank
   double *gtot;             // [2][4] cross-rank totals published by CTA 0
@@ -90,7 +90,7 @@ struct Cg2dWs {
   unsigned long long *gflag = nullptr;
   int nRanks = 1, myRank = 0;
   void *peerBase[8] = {};        // peer mappings of every rank's block (own block for myRank)
-  int nbrRank[5] = {0, 0, 0, 0, 0};
+  int nbrRank[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // rank behind push-table slot s: grid mode 0 self, 1 W, 2 E, 3 S, 4 N; tile-graph mode: slot = rank
   unsigned long long seq = 0, bseq = 0;
   Mail *ll = nullptr;
   double *partials = nullptr, *resid = nullptr;
@@ -1331,31 +1331,42 @@ bool cg2d_comm_wire() {
   const Geom &g = c.g;
   const int nRanks = c.nRanks, myRank = c.myRank;
   if (nRanks > 8) return fail(70, "comm_connect: at most 8 ranks");
-  if (g.nTiles != 1) return fail(70, "comm_connect: multi-rank runs use one tile per rank (nSx = nSy = 1)");
   Cg2dWs *w = c.cg2d;
   if (!in_arena(w->block)) return fail(70, "comm_connect: the CG2D workspace is not in the peer arena");
   w->nRanks = nRanks; w->myRank = myRank;
   const size_t off = reinterpret_cast<char *>(w->block) - c.arena;
   for (int r = 0; r < nRanks; r++) w->peerBase[r] = c.peerArena[r] + off;
-  auto rk = [&](int px, int py) { return ((px % g.nPx) + g.nPx) % g.nPx + g.nPx * (((py % g.nPy) + g.nPy) % g.nPy); };
-  w->nbrRank[0] = myRank;
-  w->nbrRank[1] = rk(g.myPx - 1, g.myPy); w->nbrRank[2] = rk(g.myPx + 1, g.myPy);
-  w->nbrRank[3] = rk(g.myPx, g.myPy - 1); w->nbrRank[4] = rk(g.myPx, g.myPy + 1);
-  // re-encode the push table: edges whose neighbour lives on another rank get the peer slot
-  const int per = 2 * g.sNy + 2 * g.sNx;
-  std::vector<int> t(per);
-  MG_CUDA(cudaMemcpy(t.data(), c.pushTab, per * sizeof(int), cudaMemcpyDeviceToHost));
-  for (int n = 0; n < per; n++) {
-    int slot = n < g.sNy ? 1 : n < 2 * g.sNy ? 2 : n < 2 * g.sNy + g.sNx ? 3 : 4;
-    if (w->nbrRank[slot] != myRank) t[n] = (t[n] & 0x0FFFFFFF) | (slot << 28);
+  if (g.nTiles == 1) {
+    auto rk = [&](int px, int py) { return ((px % g.nPx) + g.nPx) % g.nPx + g.nPx * (((py % g.nPy) + g.nPy) % g.nPy); };
+    for (int sl = 0; sl < 8; sl++) w->nbrRank[sl] = myRank;
+    w->nbrRank[1] = rk(g.myPx - 1, g.myPy); w->nbrRank[2] = rk(g.myPx + 1, g.myPy);
+    w->nbrRank[3] = rk(g.myPx, g.myPy - 1); w->nbrRank[4] = rk(g.myPx, g.myPy + 1);
+    // re-encode the push table: edges whose neighbour lives on another rank get the peer slot
+    const int per = 2 * g.sNy + 2 * g.sNx;
+    std::vector<int> t(per);
+    MG_CUDA(cudaMemcpy(t.data(), c.pushTab, per * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int n = 0; n < per; n++) {
+      int slot = n < g.sNy ? 1 : n < 2 * g.sNy ? 2 : n < 2 * g.sNy + g.sNx ? 3 : 4;
+      if (w->nbrRank[slot] != myRank) t[n] = (t[n] & 0x0FFFFFFF) | (slot << 28);
+    }
+    MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
+  } else if (!cg2d_comm_rank_slots()) {      // several tiles per rank: the exch2 topology call writes the push table
+    return false;
   }
-  MG_CUDA(cudaMemcpy(c.pushTab, t.data(), per * sizeof(int), cudaMemcpyHostToDevice));
   // a fresh connection starts the reduction sequence over on every rank (also the recovery path after error 71)
   w->seq = 0;
   w->bseq = 0;
   MG_CUDA(cudaMemset(w->ll, 0, 2 * 4 * MAX_PART * sizeof(Mail)));
   MG_CUDA(cudaMemset(w->mail, 0, sizeof(Mail) * MAIL_SLOTS));
   MG_CUDA(cudaMemset(w->gflag, 0, 64));
+  return true;
+}
+
+// exch2 tile graph across ranks (exch2.cu writes push-table entries as rank << 28 | halo index)
+bool cg2d_comm_rank_slots() {
+  Ctx &c = ctx();
+  if (!c.cg2d) return fail(70, "cg2d_comm_rank_slots: CG2D workspace not wired (mitgcm_b200_comm_connect_)");
+  for (int sl = 0; sl < 8; sl++) c.cg2d->nbrRank[sl] = sl < c.nRanks ? sl : c.myRank;
   return true;
 }
 
@@ -1386,7 +1397,7 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
     a.mail[r] = r < w->nRanks ? reinterpret_cast<Mail *>(reinterpret_cast<char *>(w->peerBase[r]) +
                                                          (reinterpret_cast<char *>(w->mail) - reinterpret_cast<char *>(w->block)))
                               : nullptr;
-  for (int sl = 0; sl < 5; sl++)
+  for (int sl = 0; sl < 8; sl++)
     a.peerDelta[sl] = reinterpret_cast<char *>(w->peerBase[w->nbrRank[sl]]) - reinterpret_cast<char *>(w->block);
   a.r[0] = w->r[0]; a.r[1] = w->r[1]; a.s[0] = w->s[0]; a.s[1] = w->s[1];
   a.q = w->q; a.z = w->z; a.xmin = w->xmin; a.v = w->v;

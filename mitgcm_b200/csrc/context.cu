@@ -188,6 +188,9 @@ void mitgcm_b200_init_(const int *dims, const int *device, int *ierr) {
   if (!build_push_tables()) return;
   c.nRanks = g.nPx * g.nPy;
   c.myRank = g.myPx + g.nPx * g.myPy;
+  c.e2Owner.clear();
+  c.e2Seq = 0;
+  for (int r = 0; r < 8; r++) c.arenaDelta[r] = 0;
   c.attrDyn = c.attrThermo = c.attrVi = c.attrDynTma = false; c.attrDynTmaUV = 0;
   if (c.nRanks > 1) {
     // peer arena: header (flags) + 7 tile3d + 4 tile2d exchanged fields + the CG2D workspace block (9 tile2d + mailboxes)

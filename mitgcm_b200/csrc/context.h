@@ -51,12 +51,17 @@ struct Ctx {
   int e2UvCount[2] = {0, 0};
   // cubed sphere: facet corners each local tile owns (1 SW, 2 SE, 4 NE, 8 NW) and its facet number
   std::vector<int> csCorners, csFace, csEdges;    // csEdges: 1 N | 2 S | 4 E | 8 W facet edges the tile touches
+  // exch2 tile graph across ranks: W2_tileProc - 1 per tile id (empty: one process holds every tile); the gather
+  // lists then carry the owner's rank next to the source index and read it through the peer arenas
+  std::vector<int> e2Owner;
+  unsigned long long e2Seq = 0;     // rank barriers of the distributed exchange so far (same on every rank)
   // Peer arena (multi-rank runs only): ONE allocation per rank that holds everything the neighbouring GPUs
   // write into -- the exchanged state fields (halo pushes), the CG2D workspace block (edge pushes, mailboxes) and
   // the exchange flags -- so one CUDA IPC mapping per peer serves all of it (halo.cu).
   char *arena = nullptr;
   size_t arenaBytes = 0, arenaUsed = 0;
   char *peerArena[8] = {};          // every rank's arena as mapped here (own arena for my rank)
+  long long arenaDelta[8] = {};     // peerArena[r] - arena: a mirror in the arena sits at the same offset on every rank
   int nRanks = 1, myRank = 0;
   struct HaloWs *halo = nullptr;
   // function attributes (dynamic shared memory opt-in) are per device: set once per init
@@ -113,6 +118,8 @@ bool halo_exchange(const int *ids, int n, bool sideStream = false);   // EXCH_XY
 bool halo_join();                                      // main stream waits for a side-stream exchange
 void halo_free();
 bool halo_check_error();
+int *halo_error_word();                                // device view of the mapped word a timed-out spin writes (nullptr: not connected)
+bool cg2d_comm_rank_slots();                           // cg2d.cu: push-table peer slots name ranks (exch2 tile graph across ranks)
 void cg3d_free_workspace();                            // cg3d.cu                    // EXCH_XY(Z)_RL on a mirror (step.cu)
 
 }  // namespace mg

@@ -9,6 +9,16 @@
 // later neighbour entries overriding earlier ones exactly as the sequential GETs do).  An exchange
 // of any field is then one launch of a coalesced gather over (list entry, level), and the width-1
 // exchange inside CG2D (EXCH2_S3D_RX, exch2_s3d_rx.template:45-62) becomes the solver's push table.
+//
+// Across GPUs (the reference: exch2_send_rx{1,2}.template / exch2_recv_rx{1,2}.template, MPI messages between
+// W2_tileProc(source tile) and W2_tileProc(target tile)): every rank holds nSx*nSy tiles of the graph
+// (W2_myTileList) and compiles the SAME global provenance map; its gather list keeps the entries whose destination
+// is one of its tiles and tags every source with the rank that owns it (rank << 28 | index in that rank's arrays).
+// A source on another rank is read straight out of that rank's peer arena over NVLink (the exchanged mirrors sit
+// at the same arena offset on every rank, context.cu), between two rank barriers on the stream: "every rank's
+// interior is final" before the gather, "every rank has finished reading" after it.  Sources are interior cells
+// and destinations halo cells (checked), so the gathers of different ranks never conflict.  The CG2D push table
+// gets the same rank tags; the solver already stores edge values through them (cg2d.cu: pdst).
 #include <algorithm>
 #include <vector>
 #include "context.h"
@@ -17,7 +27,8 @@ namespace mg {
 
 struct E2Tables {
   int nT = 0, maxN = 0;
-  std::vector<int> nN, nid, opp, ndir, pij, oi, oj, iLo, iHi, jLo, jHi, bx, by, local;
+  std::vector<int> nN, nid, opp, ndir, pij, oi, oj, iLo, iHi, jLo, jHi, bx, by;
+  std::vector<int> local, owner;         // position of the tile in its owner's (bi,bj) order; owning rank (0-based)
   std::vector<int> isN, isS, isE, isW;   // exch2_isNedge .. exch2_isWedge
   int N(int t) const { return nN[t]; }
   int at(const std::vector<int> &a, int n, int t) const { return a[n + maxN * t]; }
@@ -65,15 +76,61 @@ static bool compile_gather(const E2Tables &T, int sNx, int sNy, int OL, int eW, 
   return true;
 }
 
-__global__ void gather_kernel(double *f, const int2 *lst, int n, int nz, size_t slab) {
+struct PeerDeltas { long long d[8]; };      // byte offset from my arena to rank r's, as mapped here (0 for my rank)
+
+// value of element `idx` of the mirror `f` as rank `r` holds it
+__device__ __forceinline__ double peer_load(const double *f, const PeerDeltas &pd, int r, size_t idx) {
+  const long long d = pd.d[r];
+  const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(f) + d) + idx;
+  return d ? __ldcv(p) : *p;      // peer memory: never from a stale cache line
+}
+
+__global__ void gather_kernel(double *f, const int2 *lst, int n, int nz, size_t slab, PeerDeltas pd) {
   const size_t total = (size_t)n * nz;
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
     const int e = (int)(q % n), k = (int)(q / n);
-    const int2 ds = lst[e];   // (dst, src) as tile*slab + cell of a 2-D array; the level offset is added here
+    const int2 ds = lst[e];   // (dst, rank << 28 | src) as tile*slab + cell of a 2-D array; the level offset is added here
     const size_t dt = (size_t)ds.x / slab, dc = (size_t)ds.x % slab;
-    const size_t st = (size_t)ds.y / slab, sc = (size_t)ds.y % slab;
-    f[dc + slab * (k + (size_t)nz * dt)] = f[sc + slab * (k + (size_t)nz * st)];
+    const size_t src = (size_t)(ds.y & 0x0FFFFFFF), st = src / slab, sc = src % slab;
+    f[dc + slab * (k + (size_t)nz * dt)] = peer_load(f, pd, (ds.y >> 28) & 7, sc + slab * (k + (size_t)nz * st));
   }
+}
+
+// Rank barrier on the stream: tell every rank "I am here" (sequence number into its flag word for me), wait until
+// every rank has said the same.  Flags: 8 words at arena + 2048 (zeroed by mitgcm_b200_comm_connect_).
+#ifndef E2_SPIN_LIMIT
+#define E2_SPIN_LIMIT (1LL << 31)
+#endif
+__global__ void e2_barrier_kernel(unsigned long long *flags, PeerDeltas pd, int nRanks, int myRank, unsigned long long seq, int *err) {
+  const int r = threadIdx.x;
+  __threadfence_system();
+  if (r < nRanks) {
+    unsigned long long *peer = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(flags) + pd.d[r]);
+    *reinterpret_cast<volatile unsigned long long *>(peer + myRank) = seq;
+    long long spins = 0;
+    while (*reinterpret_cast<volatile unsigned long long *>(flags + r) < seq)
+      if (++spins > E2_SPIN_LIMIT) { if (err) *err = 83; break; }
+  }
+  __threadfence_system();
+}
+
+static bool e2_distributed() { return ctx().nRanks > 1; }
+
+static PeerDeltas e2_deltas() {
+  PeerDeltas pd;
+  for (int r = 0; r < 8; r++) pd.d[r] = ctx().arenaDelta[r];
+  return pd;
+}
+
+static bool e2_barrier() {
+  Ctx &c = ctx();
+  if (!halo_connected()) return fail(70, "exch2 across ranks: peers not connected (mitgcm_b200_comm_connect_)");
+  if (!halo_check_error()) return false;
+  c.launches++;
+  e2_barrier_kernel<<<1, 32, 0, c.stream>>>(reinterpret_cast<unsigned long long *>(c.arena + 2048), e2_deltas(), c.nRanks, c.myRank,
+                                          ++c.e2Seq, halo_error_word());
+  MG_CUDA(cudaGetLastError());
+  return true;
 }
 
 // ---- vector pairs on the C grid: EXCH2_UV_3D_RX -------------------------------------------------------
@@ -179,28 +236,33 @@ static bool compile_uv(const E2Tables &T, int sNx, int sNy, int OL, bool withSig
   return true;
 }
 
-// list entries: 4 ints (dst array, dst tile*slab+cell, src array << 1 | (sign < 0), src tile*slab+cell)
-static void uv_list(const std::vector<Prov> pr[2], const std::vector<int> &local, size_t slab, std::vector<int> &lst) {
+// list entries: 4 ints (dst array, dst tile*slab+cell, src array << 1 | (sign < 0), owner rank << 28 | src tile*slab+cell);
+// only destinations in tiles of rank `me` (me < 0: all)
+static void uv_list(const std::vector<Prov> pr[2], const std::vector<int> &local, const std::vector<int> &owner, int me,
+                    size_t slab, std::vector<int> &lst) {
   lst.clear();
   for (int a = 0; a < 2; a++)
     for (size_t q = 0; q < pr[a].size(); q++) {
       const Prov &v = pr[a][q];
       if (v.arr == a && v.cell == (int)q && v.sign == 1) continue;
+      if (me >= 0 && owner[q / slab] != me) continue;
+      const int st = v.cell / (int)slab;
       lst.push_back(a);
       lst.push_back(local[q / slab] * (int)slab + (int)(q % slab));
       lst.push_back((v.arr << 1) | (v.sign < 0 ? 1 : 0));
-      lst.push_back(local[v.cell / (int)slab] * (int)slab + v.cell % (int)slab);
+      lst.push_back((local[st] * (int)slab + v.cell % (int)slab) | ((me >= 0 ? owner[st] : 0) << 28));
     }
 }
 
-__global__ void gather_uv_kernel(double *u, double *v, const int4 *lst, int n, int nz, size_t slab) {
+__global__ void gather_uv_kernel(double *u, double *v, const int4 *lst, int n, int nz, size_t slab, PeerDeltas pd) {
   const size_t total = (size_t)n * nz;
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
     const int e = (int)(q % n), k = (int)(q / n);
     const int4 d = lst[e];
-    const size_t dt = (size_t)d.y / slab, dc = (size_t)d.y % slab, st = (size_t)d.w / slab, sc = (size_t)d.w % slab;
+    const size_t s0 = (size_t)(d.w & 0x0FFFFFFF);
+    const size_t dt = (size_t)d.y / slab, dc = (size_t)d.y % slab, st = s0 / slab, sc = s0 % slab;
     const double *src = (d.z >> 1) ? v : u;
-    double val = src[sc + slab * (k + (size_t)nz * st)];
+    double val = peer_load(src, pd, (d.w >> 28) & 7, sc + slab * (k + (size_t)nz * st));
     if (d.z & 1) val = -val;
     (d.x ? v : u)[dc + slab * (k + (size_t)nz * dt)] = val;
   }
@@ -211,10 +273,16 @@ bool exch2_uv_field(double *u, double *v, int nz, bool withSigns) {
   const int w = withSigns ? 1 : 0;
   const size_t total = (size_t)c.e2UvCount[w] * nz;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  const bool dist = e2_distributed();
+  if (dist) {
+    if (!in_arena(u) || !in_arena(v)) return fail(70, "exch2 across ranks: the vector pair must be mirrors in the peer arena (uVel / vVel)");
+    if (!e2_barrier()) return false;
+  }
   c.launches++;
-  gather_uv_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(u, v, reinterpret_cast<const int4 *>(c.e2UvList[w]), c.e2UvCount[w], nz, c.g.slab);
+  gather_uv_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(u, v, reinterpret_cast<const int4 *>(c.e2UvList[w]), c.e2UvCount[w], nz, c.g.slab,
+                                                              e2_deltas());
   MG_CUDA(cudaGetLastError());
-  return true;
+  return !dist || e2_barrier();
 }
 
 bool exch2_active() { return ctx().e2Count > 0; }
@@ -223,43 +291,51 @@ bool exch2_field(double *f, int nz) {
   Ctx &c = ctx();
   const size_t total = (size_t)c.e2Count * nz;
   int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)c.numSMs * 16);
+  const bool dist = e2_distributed();
+  if (dist) {
+    if (!in_arena(f)) return fail(70, "exch2 across ranks: the field must be a mirror in the peer arena (uVel, vVel, wVel, theta, salt, etaN, etaH, cg2d_x, aC2d)");
+    if (!e2_barrier()) return false;
+  }
   c.launches++;
-  gather_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(f, reinterpret_cast<const int2 *>(c.e2List), c.e2Count, nz, c.g.slab);
+  gather_kernel<<<std::max(blocks, 1), 256, 0, c.stream>>>(f, reinterpret_cast<const int2 *>(c.e2List), c.e2Count, nz, c.g.slab, e2_deltas());
   MG_CUDA(cudaGetLastError());
-  return true;
+  return !dist || e2_barrier();
 }
 
-static bool set_topology(const E2Tables &T) {
-  Ctx &c = ctx();
-  const Geom &g = c.g;
+// What one rank needs of a tile graph, compiled on the host (no device involved): the scalar gather list, the
+// width-1 push table of its tiles and the two vector-pair gather lists.  g: sizes of one rank (nTiles = its tiles).
+struct E2Lists { std::vector<int> scalar, push, uv[2]; };
+static bool compile_lists(const E2Tables &T, const Geom &g, int me, bool dist, E2Lists &L) {
+  const int slab = (int)g.slab;
+  const size_t nGlobal = (size_t)g.slab * T.nT;
+  auto enc = [&](int tile, int cell) { return (T.local[tile] * slab + cell) | ((dist ? T.owner[tile] : 0) << 28); };
   // ---- full-width scalar exchange: gather list over halo cells -------------------------------
   std::vector<int> prov;
   if (!compile_gather(T, g.sNx, g.sNy, g.OLx, g.OLx, true, prov)) return false;
-  std::vector<int> lst;
+  // the gather runs in place and in parallel on every rank (f[dst] = f[src]): that equals the buffered two-pass exchange
+  // only if no source of the composed map is itself a destination (sources must be cells no entry writes: interior cells)
+  {
+    std::vector<char> isDst(nGlobal, 0);
+    for (size_t q = 0; q < prov.size(); q++) isDst[q] = prov[q] != (int)q;
+    for (size_t q = 0; q < prov.size(); q++)
+      if (isDst[q] && isDst[prov[q]]) return fail(72, "exch2: a halo cell is both source and destination of the composed exchange");
+  }
+  std::vector<int> &lst = L.scalar;
+  lst.clear();
   for (size_t q = 0; q < prov.size(); q++)
     if (prov[q] != (int)q) {
-      // tile ids -> positions of the tiles in this process's (bi,bj) order
-      const int dt = (int)(q / g.slab), st = prov[q] / (int)g.slab;
-      lst.push_back(T.local[dt] * (int)g.slab + (int)(q % g.slab));
-      lst.push_back(T.local[st] * (int)g.slab + prov[q] % (int)g.slab);
+      // tile ids -> positions of the tiles in their owner's (bi,bj) order; destinations: my tiles only
+      const int dt = (int)(q / g.slab), st = prov[q] / slab;
+      if (T.owner[dt] != me) continue;
+      lst.push_back(T.local[dt] * slab + (int)(q % g.slab));
+      lst.push_back(enc(st, prov[q] % slab));
     }
-  // the gather runs in place and in parallel (f[dst] = f[src]): that equals the buffered two-pass exchange only if no
-  // source of the composed list is itself a destination (sources must be cells no entry writes: interior cells)
-  {
-    std::vector<char> isDst((size_t)g.slab * g.nTiles, 0);
-    for (size_t e = 0; e + 1 < lst.size(); e += 2) isDst[lst[e]] = 1;
-    for (size_t e = 0; e + 1 < lst.size(); e += 2)
-      if (isDst[lst[e + 1]]) return fail(72, "exch2: a halo cell is both source and destination of the composed exchange");
-  }
-  if (c.e2List) cudaFree(c.e2List);
-  MG_CUDA(cudaMalloc(&c.e2List, std::max<size_t>(lst.size(), 2) * sizeof(int)));
-  MG_CUDA(cudaMemcpy(c.e2List, lst.data(), lst.size() * sizeof(int), cudaMemcpyHostToDevice));
-  c.e2Count = (int)(lst.size() / 2);
   // ---- width-1 exchange of CG2D: the push table ------------------------------------------------
   std::vector<int> p1;
   if (!compile_gather(T, g.sNx, g.sNy, 1, 1, false, p1)) return false;
   const int per = 2 * g.sNy + 2 * g.sNx, P1X = g.sNx + 2, P1Y = g.sNy + 2;
-  std::vector<int> tab((size_t)per * g.nTiles, -1);
+  std::vector<int> &tab = L.push;
+  tab.assign((size_t)per * g.nTiles, -1);
   auto idx = [&](int i, int j, int tile) {
     return (int)((size_t)(i + g.OLx - 1) + (size_t)g.PX * (size_t)(j + g.OLy - 1) + g.slab * (size_t)tile);
   };
@@ -273,6 +349,7 @@ static bool set_topology(const E2Tables &T) {
         for (int i = r[0]; i <= r[1]; i++) {
           const int src = p1[(t * P1Y + j) * P1X + i];
           if (src / (P1X * P1Y) != s) return fail(72, "exch2: width-1 map is not a single-source copy");
+          if (T.owner[s] != me) continue;      // the rank that owns the source edge pushes it
           const int si = src % P1X, sj = (src / P1X) % P1Y;   // 0-based in the (0:sNx+1) frame = Fortran index
           int slot;
           if (sdir == 4) slot = sj - 1;                         // west edge, by j
@@ -281,28 +358,51 @@ static bool set_topology(const E2Tables &T) {
           else slot = 2 * g.sNy + g.sNx + si - 1;               // north edge
           int &e = tab[(size_t)per * T.local[s] + slot];
           if (e != -1) return fail(72, "exch2: an edge point feeds two halo cells through one edge");
-          e = idx(i, j, T.local[t]);
+          e = idx(i, j, T.local[t]) | ((dist ? T.owner[t] : 0) << 28);      // into the halo of tile t, on its owner
         }
     }
   for (int v : tab)
     if (v < 0) return fail(72, "exch2: an edge point has no neighbour (open edges are not supported)");
-  MG_CUDA(cudaMemcpy(c.pushTab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
   // ---- vector-pair exchange (EXCH_UV_XY / EXCH_UV_XYZ), unsigned and signed ----------------------------
   for (int w = 0; w < 2; w++) {
     std::vector<Prov> pr[2];
     if (!compile_uv(T, g.sNx, g.sNy, g.OLx, w == 1, pr)) return false;
-    std::vector<int> ul;
-    uv_list(pr, T.local, g.slab, ul);
     {      // same in-place condition for the vector pair: (array, cell) written by one entry must not be read by another
-      std::vector<char> isDst[2] = {std::vector<char>((size_t)g.slab * g.nTiles, 0), std::vector<char>((size_t)g.slab * g.nTiles, 0)};
-      for (size_t e = 0; e + 3 < ul.size(); e += 4) isDst[ul[e]][ul[e + 1]] = 1;
-      for (size_t e = 0; e + 3 < ul.size(); e += 4)
-        if (isDst[ul[e + 2] >> 1][ul[e + 3]]) return fail(72, "exch2: a halo cell is both source and destination of the composed vector exchange");
+      std::vector<char> isDst[2] = {std::vector<char>(nGlobal, 0), std::vector<char>(nGlobal, 0)};
+      for (int a = 0; a < 2; a++)
+        for (size_t q = 0; q < pr[a].size(); q++) {
+          const Prov &v = pr[a][q];
+          isDst[a][q] = !(v.arr == a && v.cell == (int)q && v.sign == 1);
+        }
+      for (int a = 0; a < 2; a++)
+        for (size_t q = 0; q < pr[a].size(); q++)
+          if (isDst[a][q] && isDst[pr[a][q].arr][pr[a][q].cell])
+            return fail(72, "exch2: a halo cell is both source and destination of the composed vector exchange");
     }
-    if (c.e2UvList[w]) cudaFree(c.e2UvList[w]);
-    MG_CUDA(cudaMalloc(&c.e2UvList[w], std::max<size_t>(ul.size(), 4) * sizeof(int)));
-    MG_CUDA(cudaMemcpy(c.e2UvList[w], ul.data(), ul.size() * sizeof(int), cudaMemcpyHostToDevice));
-    c.e2UvCount[w] = (int)(ul.size() / 4);
+    uv_list(pr, T.local, T.owner, dist ? me : -1, g.slab, L.uv[w]);
+  }
+  return true;
+}
+
+static bool set_topology(const E2Tables &T) {
+  Ctx &c = ctx();
+  const bool dist = c.nRanks > 1;
+  E2Lists L;
+  if (!compile_lists(T, c.g, c.myRank, dist, L)) return false;
+  auto upload = [&](int **dev, const std::vector<int> &v, size_t minInts) {
+    if (*dev) cudaFree(*dev);
+    *dev = nullptr;
+    MG_CUDA(cudaMalloc(dev, std::max(v.size(), minInts) * sizeof(int)));
+    MG_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return true;
+  };
+  if (!upload(&c.e2List, L.scalar, 2)) return false;
+  c.e2Count = (int)(L.scalar.size() / 2);
+  MG_CUDA(cudaMemcpy(c.pushTab, L.push.data(), L.push.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (dist && !cg2d_comm_rank_slots()) return false;
+  for (int w = 0; w < 2; w++) {
+    if (!upload(&c.e2UvList[w], L.uv[w], 4)) return false;
+    c.e2UvCount[w] = (int)(L.uv[w].size() / 4);
   }
   return true;
 }
@@ -311,7 +411,8 @@ static bool load_tables(E2Tables &T, int nT, int maxN, int nLocal, const int *nN
                         const int *opposingSend, const int *neighbourDir, const int *pij, const int *oi, const int *oj,
                         const int *iLo, const int *iHi, const int *jLo, const int *jHi, const int *tBasex,
                         const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge,
-                        const int *isWedge, const int *myTileList) {
+                        const int *isWedge, const int *myTileList, int nRanks, int myRank,
+                        const std::vector<int> &tileOwner) {
   T.nT = nT; T.maxN = maxN;
   const size_t nn = (size_t)T.nT * T.maxN;
   T.nN.assign(nNeighbours, nNeighbours + T.nT);
@@ -323,10 +424,33 @@ static bool load_tables(E2Tables &T, int nT, int maxN, int nLocal, const int *nN
   T.isN.assign(isNedge, isNedge + T.nT); T.isS.assign(isSedge, isSedge + T.nT);
   T.isE.assign(isEedge, isEedge + T.nT); T.isW.assign(isWedge, isWedge + T.nT);
   T.local.assign(T.nT, -1);
-  for (int l = 0; l < nLocal; l++) {
-    const int id = myTileList[l];
-    if (id < 1 || id > T.nT || T.local[id - 1] != -1) return fail(70, "exch2 topology: bad W2_myTileList");
-    T.local[id - 1] = l;
+  T.owner.assign(T.nT, 0);
+  const bool dist = nRanks > 1;
+  if (dist) {
+    // W2_tileProc (mitgcm_b200_set_exch2_tile_proc_): tiles are numbered on their owner in increasing tile id, as
+    // W2_SET_MAP_TILES fills W2_myTileList; every rank holds the same number of tiles (same arena layout)
+    if ((int)tileOwner.size() != T.nT) return fail(70, "exch2 topology across ranks: call mitgcm_b200_set_exch2_tile_proc_ first (W2_tileProc for every tile)");
+    if (T.nT != nLocal * nRanks) return fail(70, "exch2 topology across ranks: every rank must hold nTiles / nRanks tiles");
+    std::vector<int> cnt(nRanks, 0);
+    for (int t = 0; t < T.nT; t++) {
+      const int r = tileOwner[t];
+      if (r < 0 || r >= nRanks) return fail(70, "exch2 topology: W2_tileProc out of range");
+      T.owner[t] = r;
+      T.local[t] = cnt[r]++;
+    }
+    for (int r = 0; r < nRanks; r++)
+      if (cnt[r] != nLocal) return fail(70, "exch2 topology across ranks: every rank must hold nTiles / nRanks tiles");
+    for (int l = 0; l < nLocal; l++) {
+      const int id = myTileList[l];
+      if (id < 1 || id > T.nT || T.owner[id - 1] != myRank || T.local[id - 1] != l)
+        return fail(70, "exch2 topology: W2_myTileList must list this rank's tiles (W2_tileProc) in increasing tile id");
+    }
+  } else {
+    for (int l = 0; l < nLocal; l++) {
+      const int id = myTileList[l];
+      if (id < 1 || id > T.nT || T.local[id - 1] != -1) return fail(70, "exch2 topology: bad W2_myTileList");
+      T.local[id - 1] = l;
+    }
   }
   for (int t = 0; t < T.nT; t++) {
     if (T.local[t] < 0) return fail(70, "exch2 topology: every tile must be in W2_myTileList (one process)");
@@ -353,14 +477,30 @@ extern "C" void mitgcm_b200_set_exch2_topology_(
   *ierr = 1;
   if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
   const Geom &g = c.g;
-  if (g.nPx != 1 || g.nPy != 1) { fail(70, "exch2 topology: one process (one GPU) holds all tiles"); return; }
-  if (*nTiles != g.nTiles) { fail(70, "exch2 topology: nTiles must equal nSx*nSy of this process"); return; }
+  if (c.nRanks > 1 && !halo_connected()) { fail(70, "exch2 topology across ranks: connect the peers first (mitgcm_b200_comm_connect_)"); return; }
+  if (*nTiles != g.nTiles * c.nRanks) { fail(70, "exch2 topology: nTiles must equal nSx*nSy of this process times the number of ranks"); return; }
   if (g.OLx != g.OLy) { fail(70, "exch2 topology: OLx must equal OLy"); return; }
   if ((size_t)g.n2 >= ((size_t)1 << 31)) { fail(70, "exch2 topology: tile2d array too large for the gather list"); return; }
   E2Tables T;
   if (!load_tables(T, *nTiles, *maxNeighbours, g.nTiles, nNeighbours, neighbourId, opposingSend, neighbourDir, pij, oi, oj,
-                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, myTileList)) return;
+                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, myTileList, c.nRanks, c.myRank,
+                   c.e2Owner)) return;
   if (!set_topology(T)) return;
+  *ierr = 0;
+}
+
+// W2_tileProc (W2_EXCH2_TOPOLOGY.h:153-165, filled by w2_map_procs.F:91): 1-based process number owning every tile.
+// Needed before mitgcm_b200_set_exch2_topology_ when the tile graph is spread over several ranks.
+extern "C" void mitgcm_b200_set_exch2_tile_proc_(const int *nTiles, const int *tileProc, int *ierr) {
+  Ctx &c = ctx();
+  *ierr = 1;
+  if (!c.ready) { fail(30, "mitgcm_b200_init_ not called"); return; }
+  if (*nTiles < 1) { fail(70, "set_exch2_tile_proc: nTiles < 1"); return; }
+  c.e2Owner.resize(*nTiles);
+  for (int t = 0; t < *nTiles; t++) {
+    if (tileProc[t] < 1 || tileProc[t] > c.nRanks) { c.e2Owner.clear(); fail(70, "set_exch2_tile_proc: W2_tileProc must be 1 .. number of ranks"); return; }
+    c.e2Owner[t] = tileProc[t] - 1;
+  }
   *ierr = 0;
 }
 
@@ -378,13 +518,51 @@ extern "C" void mitgcm_b200_exch2_uv_map_(
   std::vector<int> ids(*nTiles);
   for (int t = 0; t < *nTiles; t++) ids[t] = t + 1;
   if (!load_tables(T, *nTiles, *maxNeighbours, *nTiles, nNeighbours, neighbourId, opposingSend, neighbourDir, pij, oi, oj,
-                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, ids.data())) return;
+                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, ids.data(), 1, 0, {})) return;
   std::vector<Prov> pr[2];
   if (!compile_uv(T, dims3[0], dims3[1], dims3[2], *withSigns != 0, pr)) return;
   std::vector<int> lst;
-  uv_list(pr, T.local, (size_t)(dims3[0] + 2 * dims3[2]) * (dims3[1] + 2 * dims3[2]), lst);
+  uv_list(pr, T.local, T.owner, -1, (size_t)(dims3[0] + 2 * dims3[2]) * (dims3[1] + 2 * dims3[2]), lst);
   *nEntries = (int)(lst.size() / 4);
   if (*nEntries > *maxEntries) { fail(74, "exch2_uv_map: output buffer too small"); return; }
   std::copy(lst.begin(), lst.end(), out4);
+  *ierr = 0;
+}
+
+// Host-only (no device needed): what rank `myRank` of `nRanks` would be given for a tile graph spread over ranks --
+// the scalar gather list (2 ints per entry: dst, owner << 28 | src), the width-1 push table of its tiles (per tile
+// W | E | S | N edge points: owner << 28 | halo index) and the vector-pair gather list (4 ints per entry, source tagged
+// the same way), all indices relative to the owning rank's (nTiles / nRanks, sNy+2*OL, sNx+2*OL) arrays.  The CPU tests
+// drive a many-rank exchange through these lists in numpy against the literal exch2 algorithm.
+// dims3 = (sNx, sNy, OL); sizes(3) in: capacities in ints, out: ints written (scalar, push, uv).
+extern "C" void mitgcm_b200_exch2_dist_lists_(
+    const int *dims3, const int *nRanks, const int *myRank, const int *tileProc, const int *withSigns, const int *nTiles,
+    const int *maxNeighbours, const int *nNeighbours, const int *neighbourId, const int *opposingSend,
+    const int *neighbourDir, const int *pij, const int *oi, const int *oj, const int *iLo, const int *iHi, const int *jLo,
+    const int *jHi, const int *tBasex, const int *tBasey, const int *isNedge, const int *isSedge, const int *isEedge,
+    const int *isWedge, int *sizes, int *scalarOut, int *pushOut, int *uvOut, int *ierr) {
+  *ierr = 1;
+  if (*nRanks < 1 || *nRanks > 8 || *myRank < 0 || *myRank >= *nRanks || *nTiles % *nRanks) { fail(70, "exch2_dist_lists: bad rank layout"); return; }
+  Geom g{};
+  g.sNx = dims3[0]; g.sNy = dims3[1]; g.OLx = g.OLy = dims3[2];
+  g.PX = g.sNx + 2 * g.OLx; g.PY = g.sNy + 2 * g.OLy; g.nTiles = *nTiles / *nRanks;
+  g.slab = (size_t)g.PX * g.PY;
+  std::vector<int> owner(*nTiles), mine;
+  for (int t = 0; t < *nTiles; t++) {
+    owner[t] = tileProc[t] - 1;
+    if (owner[t] == *myRank) mine.push_back(t + 1);
+  }
+  if ((int)mine.size() != g.nTiles) { fail(70, "exch2_dist_lists: every rank must hold nTiles / nRanks tiles"); return; }
+  E2Tables T;
+  if (!load_tables(T, *nTiles, *maxNeighbours, g.nTiles, nNeighbours, neighbourId, opposingSend, neighbourDir, pij, oi, oj,
+                   iLo, iHi, jLo, jHi, tBasex, tBasey, isNedge, isSedge, isEedge, isWedge, mine.data(), *nRanks, *myRank, owner)) return;
+  E2Lists L;
+  if (!compile_lists(T, g, *myRank, *nRanks > 1, L)) return;
+  const std::vector<int> &uv = L.uv[*withSigns != 0 ? 1 : 0];
+  if ((int)L.scalar.size() > sizes[0] || (int)L.push.size() > sizes[1] || (int)uv.size() > sizes[2]) { fail(74, "exch2_dist_lists: output buffer too small"); return; }
+  std::copy(L.scalar.begin(), L.scalar.end(), scalarOut);
+  std::copy(L.push.begin(), L.push.end(), pushOut);
+  std::copy(uv.begin(), uv.end(), uvOut);
+  sizes[0] = (int)L.scalar.size(); sizes[1] = (int)L.push.size(); sizes[2] = (int)uv.size();
   *ierr = 0;
 }

@@ -40,6 +40,7 @@ struct HaloWs {
   bool sidePending = false;
   int *errHost = nullptr, *errDev = nullptr;   // mapped pinned word: a timed-out spin reports without a sync
   bool connected = false;
+  bool gridMode = true;       // one tile per rank on the periodic nPx x nPy grid; false: several tiles per rank (exch2 tile graph)
   void *ipcBase[8] = {};      // what cudaIpcOpenMemHandle returned per rank (the peer's whole allocation)
   double *strip[2] = {nullptr, nullptr};   // per channel: receive buffer of the packed W / E / corner pieces (in the arena)
   long stripLevels = 0;                    // levels a strip buffer holds
@@ -184,12 +185,14 @@ void halo_free() {
   c.halo = nullptr;
 }
 
+int *halo_error_word() { return ctx().halo ? ctx().halo->errDev : nullptr; }
+
 bool halo_check_error() {
   HaloWs *h = ctx().halo;
   if (h && h->errHost && *reinterpret_cast<volatile int *>(h->errHost)) {
     int e = *h->errHost;
     *h->errHost = 0;
-    return fail(e, "halo exchange: timed out waiting for a neighbouring rank (re-connect to recover)");
+    return fail(e, "halo / exch2 exchange: timed out waiting for another rank (re-connect to recover)");
   }
   return true;
 }
@@ -232,12 +235,14 @@ static bool comm_connect(int nRanks, int myRank, const unsigned char *handles) {
   if (!c.arena) return fail(70, "comm_connect: single-rank context has no peer arena");
   if (nRanks != c.nRanks || nRanks > 8) return fail(70, "comm_connect: nRanks must equal nPx*nPy (<= 8)");
   if (myRank != c.myRank) return fail(70, "comm_connect: rank must be myPx + nPx*myPy");
-  if (g.nTiles != 1) return fail(70, "comm_connect: multi-rank runs use one tile per rank (nSx = nSy = 1)");
   if (g.OLx > g.sNx || g.OLy > g.sNy) return fail(70, "comm_connect: overlap wider than the tile");
   MG_CUDA(cudaStreamSynchronize(c.stream));
   halo_free();
   HaloWs *h = new HaloWs();
   c.halo = h;
+  // several tiles per rank: the ranks are not a periodic grid of tiles; every exchange then follows the exch2 tile
+  // graph (exch2.cu reads the peers' arenas), which mitgcm_b200_set_exch2_topology_ must supply
+  h->gridMode = g.nTiles == 1;
   for (int r = 0; r < nRanks; r++) {
     if (r == myRank) { c.peerArena[r] = c.arena; continue; }
     cudaIpcMemHandle_t ih;
@@ -254,6 +259,8 @@ static bool comm_connect(int nRanks, int myRank, const unsigned char *handles) {
     h->nbrRank[d] = rk(g.myPx + dir_dx(d), g.myPy + dir_dy(d));
     h->peerDelta[d] = c.peerArena[h->nbrRank[d]] - c.arena;
   }
+  for (int r = 0; r < 8; r++) c.arenaDelta[r] = r < nRanks ? c.peerArena[r] - c.arena : 0;
+  c.e2Seq = 0;
   MG_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   MG_CUDA(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   MG_CUDA(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
@@ -263,7 +270,7 @@ static bool comm_connect(int nRanks, int myRank, const unsigned char *handles) {
   MG_CUDA(cudaMemset(c.arena, 0, 4096));      // flags start over (the caller barriers before the first exchange)
   h->stripLevels = 4L * g.Nr + 4;
   const size_t stripBytes = (size_t)(2L * g.OLx * g.sNy + 4L * g.OLx * g.OLy) * (size_t)h->stripLevels * sizeof(double);
-  for (int ch = 0; ch < 2; ch++) {
+  for (int ch = 0; ch < 2 && h->gridMode; ch++) {
     h->strip[ch] = static_cast<double *>(arena_alloc(stripBytes));
     if (!h->strip[ch]) return fail(3, "comm_connect: peer arena exhausted (strip buffers)");
   }
@@ -276,6 +283,7 @@ bool halo_exchange(const int *ids, int n, bool sideStream) {
   Ctx &c = ctx();
   HaloWs *h = c.halo;
   if (!h || !h->connected) return fail(70, "halo_exchange: peers not connected (mitgcm_b200_comm_connect_)");
+  if (!h->gridMode) return fail(70, "halo_exchange: several tiles per rank -- exchanges follow the exch2 tile graph (mitgcm_b200_set_exch2_topology_)");
   if (!halo_check_error()) return false;
   if (n < 1 || n > HALO_MAXF) return fail(70, "halo_exchange: 1..8 fields per exchange");
   const Geom &g = c.g;

@@ -467,7 +467,8 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   const Params &q = c.p;
   if (q.I(MI_USECDSCHEME)) return fail(61, "forward_step: the CD scheme is not supported");
   const bool semiImpl = q.D(MP_IMPLICSURFPRESS) != 1.0 || q.D(MP_IMPLICDIV2DFLOW) != 1.0;
-  if (semiImpl && g.nPx * g.nPy > 1) return fail(61, "forward_step: implicSurfPress/implicDiv2DFlow < 1 is single-rank for now");
+  // (an exch2 tile graph across ranks runs the single-process sequence: its exchanges reach the other ranks themselves)
+  if (semiImpl && g.nPx * g.nPy > 1 && !exch2_active()) return fail(61, "forward_step: implicSurfPress/implicDiv2DFlow < 1 is single-rank for now");
   MomPar mp;
   if (!make_mom_par(mp)) return false;
   const bool vecinv = q.I(MI_VECTORINVARIANTMOMENTUM) != 0;
@@ -494,7 +495,7 @@ static bool step_part(int part, int myIter, double *initRes, int *iters, double 
   const bool exactConserv = q.I(MI_EXACTCONSERV) != 0, implDiff = q.I(MI_IMPLICITDIFFUSION) != 0;
   // buoyancy and relaxation work on the halo'd slab of each rank (theta halos are exchanged every step);
   // the exactConserv update needs the u, v halo exchange in the middle of the continuity step
-  if (exactConserv && g.nPx * g.nPy > 1) return fail(61, "forward_step: exactConserv is single-rank for now");
+  if (exactConserv && g.nPx * g.nPy > 1 && !exch2_active()) return fail(61, "forward_step: exactConserv is single-rank for now");
   if (g.Nr > PHYS_NRMAX && implDiff) return fail(61, "forward_step: implicit diffusion supports Nr <= 64");
   if (g.Nr > PHYS_NRMAX && mp.momViscosity && mp.implicitViscosity) return fail(61, "forward_step: implicit viscosity supports Nr <= 64");
   double *rho = nullptr, *phiHyd = nullptr, *sfT = nullptr, *etaH = nullptr;
@@ -845,8 +846,10 @@ static bool forward_step(int myIter, double *initRes, int *iters, double *lastRe
   if (!c.ready) return fail(30, "mitgcm_b200_init_ not called");
   const Geom &g = c.g;
   const Params &q = c.p;
-  const bool multi = g.nPx * g.nPy > 1;
-  if (multi && !halo_connected())
+  // ranks on the periodic process grid: peer pushes (halo.cu).  An exch2 tile graph spread over ranks takes the
+  // single-process sequence below: exch2_field / exch2_uv_field gather across the peer arenas (exch2.cu)
+  const bool multi = g.nPx * g.nPy > 1 && !exch2_active();
+  if (g.nPx * g.nPy > 1 && !halo_connected())
     return fail(62, "forward_step: multi-rank runs need mitgcm_b200_comm_connect_ (or step through mitgcm_b200_step_part_ + NCCL exchanges)");
   const bool prof = q.I(MI_PROFILE) != 0;
   auto mark = [&](int n) {

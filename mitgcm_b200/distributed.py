@@ -34,7 +34,7 @@ def setup(d: Dims, transport: str | None = None):
     L = _lib.lib()
     world, rank = dist.get_world_size(), dist.get_rank()
     assert world == d.nPx * d.nPy and rank == d.myPx + d.nPx * d.myPy
-    assert d.nSx == 1 and d.nSy == 1, "multi-rank runs use one tile per rank"
+    # one tile per rank on the periodic process grid, or several tiles of an exch2 tile graph (exch2.set_topology with tileProc)
     transport = transport or os.environ.get("MITGCM_B200_TRANSPORT", "peer")
     assert transport in ("peer", "nccl")
     h = (C.c_ubyte * 72)()

@@ -191,16 +191,33 @@ def cubed_sphere_topology(nFace: int, sNx: int, sNy: int, maxNeighbours: int = 8
                          iLo, iHi, jLo, jHi, isEdge)
 
 
-def set_topology(topo: Exch2Topology, myTileList=None):
+def tile_proc(nTiles: int, nRanks: int) -> np.ndarray:
+    """W2_tileProc as W2_MAP_PROCS fills it (w2_map_procs.F:60-91): consecutive blocks of nTiles / nRanks tile ids
+    per process, 1-based process numbers."""
+    assert nTiles % nRanks == 0
+    return (np.arange(nTiles) // (nTiles // nRanks) + 1).astype(np.int32)
+
+
+def set_topology(topo: Exch2Topology, myTileList=None, tileProc=None):
     """Hands the tables to the CUDA library (mitgcm_b200_set_exch2_topology_): from then on the
     width-1 exchange inside CG2D and mitgcm_b200_exch_ follow the exch2 tile graph instead of the
-    periodic nSx x nSy tiling.  myTileList(nSx*nSy) = W2_myTileList, default 1..nTiles."""
+    periodic nSx x nSy tiling.  myTileList(nSx*nSy) = W2_myTileList, default 1..nTiles.
+    tileProc(nTiles) = W2_tileProc (1-based owner of every tile): the graph is spread over several ranks
+    (after distributed.setup) and myTileList defaults to this rank's tiles."""
     from . import _lib
     L = _lib.lib()
     tb = topo.tables()
-    tl = np.arange(1, topo.nTiles + 1, dtype=np.int32) if myTileList is None else np.ascontiguousarray(myTileList, np.int32)
     ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
     ierr = C.c_int(0)
+    if tileProc is not None:
+        import torch.distributed as dist
+        tp = np.ascontiguousarray(tileProc, np.int32)
+        L.mitgcm_b200_set_exch2_tile_proc_(C.byref(C.c_int(topo.nTiles)), ip(tp), C.byref(ierr))
+        if ierr.value:
+            raise RuntimeError(f"set_exch2_tile_proc failed: {L.mitgcm_b200_last_error_string().decode()}")
+        if myTileList is None:
+            myTileList = np.nonzero(tp == dist.get_rank() + 1)[0] + 1
+    tl = np.arange(1, topo.nTiles + 1, dtype=np.int32) if myTileList is None else np.ascontiguousarray(myTileList, np.int32)
     L.mitgcm_b200_set_exch2_topology_(
         C.byref(C.c_int(topo.nTiles)), C.byref(C.c_int(topo.maxNeighbours)), ip(tb["nNeighbours"]),
         ip(tb["neighbourId"]), ip(tb["opposingSend"]), ip(tb["neighbourDir"]), ip(tb["pij"]), ip(tb["oi"]),
@@ -310,6 +327,34 @@ def uv_gather_map(T: Exch2Topology, OL: int, withSigns: bool):
         raise RuntimeError(f"exch2_uv_map failed: {L.mitgcm_b200_last_error_string().decode()}")
     e = out[:4 * n.value].reshape(-1, 4)
     return e[:, 0].copy(), e[:, 1].astype(np.int64), e[:, 2] >> 1, (e[:, 2] & 1).astype(bool), e[:, 3].astype(np.int64)
+
+
+def dist_lists(T: Exch2Topology, OL: int, nRanks: int, myRank: int, withSigns: bool = True, tileProc=None):
+    """What rank myRank of nRanks is given when the tile graph is spread over ranks (mitgcm_b200_exch2_dist_lists_,
+    host code: works without a GPU): (scalar (n,2): dst, owner << 28 | src;  push (nLocalTiles, 2 sNy + 2 sNx):
+    owner << 28 | halo index;  uv (n,4): dst array, dst, src array << 1 | negate, owner << 28 | src), indices relative to
+    the owning rank's (nTiles / nRanks, PY, PX) arrays -- exactly the lists the GPU kernels read."""
+    from . import _lib
+    L = _lib.lib()
+    tb = T.tables()
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    tp = np.ascontiguousarray(tile_proc(T.nTiles, nRanks) if tileProc is None else tileProc, np.int32)
+    nL = T.nTiles // nRanks
+    cells = nL * (T.sNx + 2 * OL) * (T.sNy + 2 * OL)
+    sizes = (C.c_int * 3)(2 * cells, nL * (2 * T.sNx + 2 * T.sNy), 8 * cells)
+    sc, pu, uv = (np.zeros(n, dtype=np.int32) for n in sizes)
+    ierr = C.c_int(0)
+    dims3 = (C.c_int * 3)(T.sNx, T.sNy, OL)
+    L.mitgcm_b200_exch2_dist_lists_(
+        dims3, C.byref(C.c_int(nRanks)), C.byref(C.c_int(myRank)), ip(tp), C.byref(C.c_int(int(withSigns))),
+        C.byref(C.c_int(T.nTiles)), C.byref(C.c_int(T.maxNeighbours)),
+        ip(tb["nNeighbours"]), ip(tb["neighbourId"]), ip(tb["opposingSend"]), ip(tb["neighbourDir"]), ip(tb["pij"]),
+        ip(tb["oi"]), ip(tb["oj"]), ip(tb["iLo"]), ip(tb["iHi"]), ip(tb["jLo"]), ip(tb["jHi"]), ip(tb["tBasex"]),
+        ip(tb["tBasey"]), ip(tb["isNedge"]), ip(tb["isSedge"]), ip(tb["isEedge"]), ip(tb["isWedge"]),
+        sizes, ip(sc), ip(pu), ip(uv), C.byref(ierr))
+    if ierr.value:
+        raise RuntimeError(f"exch2_dist_lists failed: {L.mitgcm_b200_last_error_string().decode()}")
+    return sc[:sizes[0]].reshape(-1, 2), pu[:sizes[1]].reshape(nL, -1), uv[:sizes[2]].reshape(-1, 4)
 
 
 def exchange_uv(T: Exch2Topology, u: np.ndarray, v: np.ndarray, OL: int, withSigns: bool, gmap=None):

@@ -102,14 +102,41 @@ def make_channel(sNx, sNy, Nr, nSx=1, nSy=1, OL=2, dx=20e3, dz=100.0, land_frac=
     return g, P, channel_state(g, seed, period=block, **strat)
 
 
-class Model:
-    """Device-resident model: Model(grid, params, state).step() == one FORWARD_STEP."""
+def rank_tiles(g: Grid, arrays: list, rank: int, world: int):
+    """This rank's share of a tile graph held as (1, nTiles, ...) arrays: consecutive blocks of nTiles / world tile ids
+    per rank (W2_MAP_PROCS, w2_map_procs.F:60-91).  Returns (local Grid, the dicts of `arrays` cut the same way)."""
+    d = g.d
+    assert d.nSy == 1 and d.nSx % world == 0 and d.nPx == d.nPy == 1
+    n = d.nSx // world
+    lo, hi = rank * n, (rank + 1) * n
 
-    def __init__(self, g: Grid, P: dict, state: dict, op: dict, device=-1, topo=None):
+    def cut(v):
+        if isinstance(v, np.ndarray) and v.ndim >= 4 and v.shape[:2] == (1, d.nSx):
+            return np.ascontiguousarray(v[:, lo:hi])
+        return v
+    dl = Dims(sNx=d.sNx, sNy=d.sNy, OLx=d.OLx, OLy=d.OLy, nSx=n, nSy=1, Nr=d.Nr, nPx=world, nPy=1, myPx=rank, myPy=0)
+    return Grid(dl, {k: cut(v) for k, v in g.a.items()}), [{k: cut(v) for k, v in a.items()} for a in arrays]
+
+
+class Model:
+    """Device-resident model: Model(grid, params, state).step() == one FORWARD_STEP.
+    ranks = (rank, world) with an exch2 topology: the tile graph is spread over `world` GPUs (one process each, NCCL
+    process group initialised); g, state and op describe the WHOLE graph and every rank keeps its share."""
+
+    def __init__(self, g: Grid, P: dict, state: dict, op: dict, device=-1, topo=None, ranks=None):
+        self.dist = ranks is not None and ranks[1] > 1
+        if self.dist:
+            assert topo is not None, "several ranks with several tiles each need the exch2 tile graph"
+            g, (state, op) = rank_tiles(g, [state, op], *ranks)
         self.g, self.d, self.P = g, g.d, P
         rt.init(g.d, device)
         rt.set_grid(g)
-        if topo is not None:          # pkg/exch2 tile graph (cubed sphere): all exchanges follow it
+        if self.dist:
+            from . import distributed
+            from .exch2 import set_topology, tile_proc
+            distributed.setup(g.d)
+            set_topology(topo, tileProc=tile_proc(topo.nTiles, ranks[1]))
+        elif topo is not None:        # pkg/exch2 tile graph (cubed sphere): all exchanges follow it
             from .exch2 import set_topology
             set_topology(topo)
         rt.set_params(**{k: P[k] for k in LIB_PARAMS if k in P})
@@ -152,6 +179,9 @@ class Model:
         return rt.get_field(name, np.zeros(shape))
 
     def close(self):
+        if self.dist:
+            from . import distributed
+            distributed.teardown()
         rt.finalize()
 
 
