@@ -1167,6 +1167,23 @@ __device__ void sr_phase_err(const Cg2dArgs &a, const double *r, double *sm) {
   block_partials<1, false>(a, acc, sm);
 }
 
+// Barrier between two phases of CG2D_SR that exchange edge values but share no dot product.  One rank: the grid
+// barrier.  Several ranks: the pushes of the phase before went into the PEERS' halos and the phase after reads halos
+// the peers pushed, so every rank has to have finished -- a cross-rank reduction of nothing is that barrier (as after
+// the x pushes of the set-up).  CG2D never needs it: each of its phases ends in a dot product.
+template <class Grid>
+__device__ __forceinline__ void rank_barrier(const Cg2dArgs &a, Grid &grid, double *sm, unsigned long long &rseq,
+                                             unsigned long long &bseq) {
+  if (a.nRanks > 1) {
+    double dummy[1] = {0.0}, t[1];
+    block_partials<1, true>(a, dummy, sm);
+    if (!a.ll) grid.sync();
+    grid_totals<1, true>(a, t, sm, rseq);
+  } else {
+    grid_barrier(a, grid, bseq);
+  }
+}
+
 #ifndef SR_MINB
 #define SR_MINB 4
 #endif
@@ -1218,11 +1235,11 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB * 256 / CG_THREADS) cg2d_s
     double alpha = t1[0];
     double sigma = eta_qrN / alpha;
     if (a.vec2) sr_phase_update2(a, r, 0.0, sigma, true, false); else sr_phase_update(a, r, 0.0, sigma, true, false);
-    grid_barrier(a, grid, bseq);
+    rank_barrier(a, grid, sm, rseq, bseq);
     bool converged = false;
     for (it2d = 1; it2d <= a.maxIters - 1; it2d++) {
       if (a.vec2) sr_phase_y2(a, r, y, nullptr, sm, false); else sr_phase_y(a, r, y, nullptr, sm, false);
-      grid_barrier(a, grid, bseq);
+      rank_barrier(a, grid, sm, rseq, bseq);
       if (a.vec2) sr_phase_v2(a, y, r, sm); else sr_phase_v(a, y, r, sm);
       if (!a.ll) grid.sync();
       grid_totals<3, false>(a, t3, sm, rseq);
@@ -1238,7 +1255,7 @@ __global__ void __launch_bounds__(CG_THREADS, SR_MINB * 256 / CG_THREADS) cg2d_s
       alpha = delta - (cgBeta * cgBeta) * alpha;
       sigma = eta_qrN / alpha;
       if (a.vec2) sr_phase_update2(a, r, cgBeta, sigma, false, saveMin); else sr_phase_update(a, r, cgBeta, sigma, false, saveMin);
-      grid_barrier(a, grid, bseq);
+      rank_barrier(a, grid, sm, rseq, bseq);
     }
     if (!converged) {
       sr_phase_err(a, r, sm);

@@ -112,7 +112,7 @@ def rank_tiles(g: Grid, arrays: list, rank: int, world: int):
 
     def cut(v):
         if isinstance(v, np.ndarray) and v.ndim >= 4 and v.shape[:2] == (1, d.nSx):
-            return np.ascontiguousarray(v[:, lo:hi])
+            return v[:, lo:hi].copy()
         return v
     dl = Dims(sNx=d.sNx, sNy=d.sNy, OLx=d.OLx, OLy=d.OLy, nSx=n, nSy=1, Nr=d.Nr, nPx=world, nPy=1, myPx=rank, myPy=0)
     return Grid(dl, {k: cut(v) for k, v in g.a.items()}), [{k: cut(v) for k, v in a.items()} for a in arrays]
