@@ -1478,6 +1478,9 @@ bool cg2d_run(bool sr, double *cg2d_b, double *cg2d_x, double *firstResidual, do
   // zero-initialised work arrays incl. ring 0 / sN+1 (cg2d.F:142-147)
   size_t bytes = g.n2 * sizeof(double);
   for (double *p : {w->r[0], w->r[1], w->s[0], w->s[1], w->q, w->z, w->v}) MG_CUDA(cudaMemsetAsync(p, 0, bytes, c.stream));
+  // residual history: CG2D_SR records iterations 1 .. numIters-1 only; what it does not write reads as zero, not as the
+  // previous solve's value
+  MG_CUDA(cudaMemsetAsync(w->resid, 0, (size_t)w->residCap * sizeof(double), c.stream));
   static const int zero = 0;
   MG_CUDA(cudaMemcpyToSymbolAsync(g_cg2d_spin_error, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, c.stream));
   if (l2win) {   // experiment: persisting L2 window over q, z and x (l2win = percent of the window that persists)

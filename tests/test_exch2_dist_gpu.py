@@ -10,7 +10,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nproc", [2, 3, 4])
+NPROC = [int(n) for n in os.environ.get("MITGCM_B200_DIST_NPROC", "2").split(",")]      # "2,3,4" on a larger box
+
+
+@pytest.mark.parametrize("nproc", NPROC)
 def test_tile_graph_across_gpus(nproc):
     import torch
     if torch.cuda.device_count() < nproc:
