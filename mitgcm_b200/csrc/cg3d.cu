@@ -17,8 +17,10 @@
 //        x += alpha s is applied two iterations at a time, x = (x + a1 s1) + a2 s2 (the reference's order of
 //        additions; both s buffers are still in memory), so odd iterations touch neither x nor s.
 //        R{r, q, zMC, zML | z', zMU, r} W{r, z' | z}  + x: 4 words every second iteration      10 + 2 words
-//   = 20 words = 160 B per cell and iteration (the backward sweep's re-reads of z' and r included) against
-//   21 + 2 re-read for the four-sweep form, and 2 instead of 4 grid barriers.
+//        (z' of the first C3_SMEM_LEVELS levels waits in shared memory instead of HBM)
+//   = about 19.5 words = 156 B per cell and iteration (the back substitution's re-reads included; ncu) against
+//   21 + 2 re-read for the four-sweep form, and 2 instead of 4 grid barriers.  Measured at 1024^2 x 50 on B200:
+//   1525 us per iteration against 2131 (profiles/r02_cg3d_fused_sweeps.log).
 //
 // cg3d_kernel (MITGCM_B200_CG3D_UNFUSED=1): the four-sweep form, four grid barriers per iteration
 //   M : q = M r down and up every column of the ring, eta = <q,r>            R{r,zMC,zML,zMU} W{q}
@@ -312,9 +314,9 @@ __global__ void __launch_bounds__(C3_THREADS, C3_MINB) cg3d_kernel(Cg3dArgs a) {
 #endif
 constexpr int C3_TX = C3_PATCH_X, C3_TY = C3_THREADS / C3_TX;      // SA: columns of one CTA = a C3_TX x C3_TY patch of a tile
 
-// Streaming hints: what a phase touches once (operators, q, x, s, the finished z) is loaded / stored with .cs so
-// that the L2 keeps what the back substitution reads again (z' and r of the columns in flight: 76 k columns x 50
-// levels x 16 B = 60 MB at two CTAs per SM).  C3_CS_HINTS=0 compiles plain accesses (A/B).
+// Streaming hints (-DC3_CS_HINTS=1, off by default): what a phase touches once (operators, q, x, s, the finished z)
+// loaded / stored with .cs so that the L2 would keep what the back substitution reads again (z' and r of the columns
+// in flight).  Measured slower at 1024^2 x 50: UM 789 -> 881 us per iteration; kept for A/B.
 #ifndef C3_CS_HINTS
 #define C3_CS_HINTS 0
 #endif
