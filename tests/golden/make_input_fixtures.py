@@ -63,11 +63,26 @@ def deep_convection_fixture():
     print("wrote deep_convection.npz")
 
 
+def advection_in_gyre_fixture():
+    """tutorial_advection_in_gyre: the spun-up barotropic gyre it restarts from (pickup.0000259200.data, 11 records of
+    60 x 60 float64: Uvel Vvel Theta Salt GuNm1 GvNm1 GtNm1 GsNm1 EtaN dEtaHdt EtaH), the basin and the wind stress."""
+    import numpy as np
+    ag = os.path.join(REF, "tutorial_advection_in_gyre/input")
+    pk = np.fromfile(os.path.join(ag, "pickup.0000259200.data"), ">f8").reshape(11, 60, 60).astype(np.float64)
+    names = "Uvel Vvel Theta Salt GuNm1 GvNm1 GtNm1 GsNm1 EtaN dEtaHdt EtaH".split()
+    out = {n: pk[q] for q, n in enumerate(names) if n in ("Uvel", "Vvel", "Theta", "GuNm1", "GvNm1", "GtNm1", "EtaN")}
+    out["topog"] = np.fromfile(os.path.join(ag, "topog.box5000"), ">f8").reshape(60, 60).astype(np.float64)
+    out["windx"] = np.fromfile(os.path.join(ag, "windx.m01cos2y"), ">f8").reshape(60, 60).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "advection_in_gyre.npz"), **out)
+    print("wrote advection_in_gyre.npz")
+
+
 if __name__ == "__main__":
     os.makedirs(HERE, exist_ok=True)
     cs32_fixture()
     solid_body_fixture()
     deep_convection_fixture()
+    advection_in_gyre_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

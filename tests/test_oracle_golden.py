@@ -429,3 +429,52 @@ def test_adjustment_128x64_lat_lon_all_steps():
         for f in ("eta", "uvel", "vvel"):
             for st in ("max", "min", "mean", "sd"):
                 assert r[f][st] == pytest.approx(float(gold[f"dynstat_{f}_{st}"][n + 1]), rel=2e-11, abs=1e-12), (n, f, st)
+
+
+# verification/tutorial_advection_in_gyre: the barotropic gyre restarted from a 10-year spin-up (|u| up to 0.26 m/s):
+# MOM_FLUXFORM's advective terms on a developed flow, no-slip sides AND bottom (viscAz = 0.01), AB2 continued from the
+# pickup's GuNm1 / GvNm1, CG2D started from Bo_surf * etaN (oracle/advection_in_gyre.py).  The flow is almost steady,
+# so cg2d_init_res (7e-10) and the wvel statistics (1e-14) are differences of nearly equal numbers: reproducing their
+# printed digits means the tendencies are the reference's bit for bit.
+GOLD_AG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_advection_in_gyre.json")))
+
+
+@pytest.fixture(scope="module")
+def run_ag():
+    from oracle import advection_in_gyre as ag
+    return ag.run(4)
+
+
+def test_advection_in_gyre_inputs_match_reference_files():
+    ref = "/root/reference/verification/tutorial_advection_in_gyre/input"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle import advection_in_gyre as ag
+    z = np.load(ag.FIXTURE)
+    pk = np.fromfile(os.path.join(ref, "pickup.0000259200.data"), ">f8").reshape(11, 60, 60)
+    for q, n in ((0, "Uvel"), (1, "Vvel"), (4, "GuNm1"), (5, "GvNm1"), (8, "EtaN")):
+        assert np.array_equal(z[n], pk[q]), n
+    assert np.array_equal(z["topog"], np.fromfile(os.path.join(ref, "topog.box5000"), ">f8").reshape(60, 60))
+    assert np.array_equal(z["windx"], np.fromfile(os.path.join(ref, "windx.m01cos2y"), ">f8").reshape(60, 60))
+
+
+def test_advection_in_gyre_solver_lines_every_digit(run_ag):
+    norm, _, out = run_ag
+    assert fmt(norm, 16) == GOLD_AG["cg2dNorm"]
+    assert [r["numIters"] for r in out] == GOLD_AG["cg2d_iters"] == [11, 10, 10, 11]
+    for r, ir, lr, (sr, rm) in zip(out, GOLD_AG["cg2d_init_res"], GOLD_AG["cg2d_last_res"], GOLD_AG["sumRHS_rhsMax"]):
+        assert fmt(r["firstResidual"], 14) == ir
+        assert fmt(r["lastResidual"], 14) == lr
+        assert fmt(r["rhsMax"], 14) == rm
+        assert fmt(r["sumRHS"], 14) == sr
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel"])
+@pytest.mark.parametrize("st", ["max", "min", "mean", "sd"])
+def test_advection_in_gyre_monitor_every_digit(run_ag, fld, st):
+    _, first, out = run_ag
+    gold = GOLD_AG[f"dynstat_{fld}_{st}"]
+    assert len(gold) == 5
+    assert fmt(first[fld][st], 13) == gold[0], "statistics of the pickup state"
+    for i, r in enumerate(out):
+        assert fmt(r[fld][st], 13) == gold[i + 1], (fld, st, i)
