@@ -46,7 +46,7 @@ if __name__ == "__main__":
             json.dump(parse(exp), f, indent=1)
         print("wrote", exp)
     # secondary outputs of an experiment (results/output.<name>.txt)
-    for exp, name in (("advect_xy", "ab3_c4"),):
+    for exp, name in (("advect_xy", "ab3_c4"), ("flt_example", "with_flt")):
         with open(os.path.join(HERE, f"{exp}.{name}.json"), "w") as f:
             json.dump(parse(exp, f"results/output.{name}.txt"), f, indent=1)
         print("wrote", exp, name)

@@ -77,12 +77,23 @@ def advection_in_gyre_fixture():
     print("wrote advection_in_gyre.npz")
 
 
+def flt_example_fixture():
+    """flt_example: the bump topography (partial cells with hFacMin = 0.2) and the zonal wind stress, 42 x 80 float64."""
+    import numpy as np
+    fe = os.path.join(REF, "flt_example/input")
+    out = dict(topog=np.fromfile(os.path.join(fe, "topog.bump"), ">f8").reshape(42, 80).astype(np.float64),
+               windx=np.fromfile(os.path.join(fe, "windx.sin_y"), ">f8").reshape(42, 80).astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "flt_example.npz"), **out)
+    print("wrote flt_example.npz")
+
+
 if __name__ == "__main__":
     os.makedirs(HERE, exist_ok=True)
     cs32_fixture()
     solid_body_fixture()
     deep_convection_fixture()
     advection_in_gyre_fixture()
+    flt_example_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

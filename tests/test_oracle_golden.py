@@ -478,3 +478,49 @@ def test_advection_in_gyre_monitor_every_digit(run_ag, fld, st):
     assert fmt(first[fld][st], 13) == gold[0], "statistics of the pickup state"
     for i, r in enumerate(out):
         assert fmt(r[fld][st], 13) == gold[i + 1], (fld, st, i)
+
+
+# verification/flt_example (the ocean underneath the float package): wind-driven f-plane channel over a bump with
+# PARTIAL CELLS (hFacMin = 0.2), 80 x 42 x 8, stratified, explicit vertical diffusion: the time stepping on hFac < 1
+# (oracle/flt_example.py); golden: results/output.with_flt.txt
+GOLD_FE = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "flt_example.with_flt.json")))
+FE_STEPS = 18
+
+
+@pytest.fixture(scope="module")
+def run_fe():
+    from oracle import flt_example as fe
+    return fe.run(FE_STEPS)
+
+
+def test_flt_example_inputs_match_reference_files_and_have_partial_cells():
+    from oracle import flt_example as fe
+    z, d, g, P = fe.setup()
+    part = (g.hFacC > 0) & (g.hFacC < 1)
+    assert part.sum() > 1000 and g.hFacC[g.hFacC > 0].min() >= 0.2          # the point of this experiment
+    ref = "/root/reference/verification/flt_example/input"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    assert np.array_equal(z["topog"], np.fromfile(os.path.join(ref, "topog.bump"), ">f8").reshape(42, 80))
+    assert np.array_equal(z["windx"], np.fromfile(os.path.join(ref, "windx.sin_y"), ">f8").reshape(42, 80))
+
+
+def test_flt_example_solver_lines_every_digit(run_fe):
+    norm, _, out = run_fe
+    assert fmt(norm, 16) == GOLD_FE["cg2dNorm"]
+    assert [r["numIters"] for r in out] == GOLD_FE["cg2d_iters"][:FE_STEPS]
+    for r, ir, lr, (sr, rm) in zip(out, GOLD_FE["cg2d_init_res"], GOLD_FE["cg2d_last_res"], GOLD_FE["sumRHS_rhsMax"]):
+        assert fmt(r["firstResidual"], 14) == ir
+        assert fmt(r["lastResidual"], 14) == lr
+        assert fmt(r["rhsMax"], 14) == rm
+        assert abs(r["sumRHS"] - float(sr)) <= 1e-14 or fmt(r["sumRHS"], 14) == sr      # a sum of round-off (1e-12)
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel", "theta"])
+@pytest.mark.parametrize("st", ["max", "min", "mean", "sd"])
+def test_flt_example_monitor_every_digit(run_fe, fld, st):
+    _, first, out = run_fe
+    gold = GOLD_FE[f"dynstat_{fld}_{st}"]
+    assert float(fmt(first[fld][st], 13)) == float(gold[0]), "start state"
+    for i, r in enumerate(out):
+        assert fmt(r[fld][st], 13) == gold[i + 1], (fld, st, i)      # incl. the eta / wvel means, which are round-off (1e-17, 1e-22)

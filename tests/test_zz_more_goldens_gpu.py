@@ -1,10 +1,17 @@
-"""verification/tutorial_advection_in_gyre (the barotropic gyre restarted from a 10-year spin-up, oracle/advection_in_gyre.py)
+"""Two more goldens with the CUDA kernels in the loop (this file sorts last on purpose: both tests were added after the
+round's GPU budget was spent and have not been run on a GPU yet).
+
+verification/tutorial_advection_in_gyre (the barotropic gyre restarted from a 10-year spin-up, oracle/advection_in_gyre.py)
 with the CUDA MOM_FLUXFORM in the loop through the C ABI (reference argument list, host buffers, 2 x 2 tiles of 30 x 30,
 OL = 4): advective terms on a developed flow, harmonic viscosity, no-slip sides and bottom.  The tendencies are
 bit-identical to the oracle's, so with the CPU solver the run reproduces every printed digit of the golden output --
 including cg2d_init_res = 6.7e-10 and the 1e-14 wvel statistics, which are differences of nearly equal numbers.
 (The CUDA solver is not put in this loop: the start residual of an almost steady state is what the previous solve left
-behind, i.e. it depends on the summation order at the 1e-10 tolerance.)"""
+behind, i.e. it depends on the summation order at the 1e-10 tolerance.)
+
+verification/flt_example (oracle/flt_example.py): wind-driven channel over a bump with PARTIAL CELLS, 80 x 42 x 8, with
+the CUDA GAD_CALC_RHS (centred advection, Laplacian + explicit vertical diffusion) and MOM_FLUXFORM in the loop and the CPU
+solver: every printed digit of the golden output for 18 steps."""
 import json
 import os
 
@@ -12,9 +19,11 @@ import pytest
 
 from helpers import CudaEngine
 from oracle import advection_in_gyre as ag
+from oracle import flt_example as fe
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_advection_in_gyre.json")))
+GOLD_FE = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "flt_example.with_flt.json")))
 
 
 @pytest.fixture()
@@ -35,3 +44,16 @@ def test_cuda_mom_fluxform_on_the_spun_up_gyre_reproduces_the_golden(rt):
         for f in ("eta", "uvel", "vvel", "wvel"):
             for st in ("max", "min", "mean", "sd"):
                 assert f"{r[f][st]:.13E}" == GOLD[f"dynstat_{f}_{st}"][i + 1], (i, f, st)
+
+
+def test_cuda_tendencies_on_partial_cells_reproduce_the_flt_example_golden(rt):
+    eng = CudaEngine(rt, use_cg2d=False)
+    norm, first, out = fe.run(18, engine=eng)
+    assert f"{norm:.16E}" == GOLD_FE["cg2dNorm"]
+    assert [r["numIters"] for r in out] == GOLD_FE["cg2d_iters"]
+    for i, r in enumerate(out):
+        assert f"{r['firstResidual']:.14E}" == GOLD_FE["cg2d_init_res"][i], i
+        assert f"{r['rhsMax']:.14E}" == GOLD_FE["sumRHS_rhsMax"][i][1], i
+        for f in ("eta", "uvel", "vvel", "wvel", "theta"):
+            for st in ("max", "min", "mean", "sd"):
+                assert f"{r[f][st]:.13E}" == GOLD_FE[f"dynstat_{f}_{st}"][i + 1], (i, f, st)
