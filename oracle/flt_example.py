@@ -43,6 +43,18 @@ def setup():
 def run(nSteps=18, engine=None):
     """Returns (cg2dNorm, statistics of the start state, [per-step dict])."""
     z, d, g, P = setup()
+    rhoConst = 999.8
+    return step_loop(d, g, P, nSteps, engine, tRef=TREF, salt0=35.0, rhoConst=rhoConst, tAlpha=2e-4, gravity=9.81, abEps=0.1,
+                     viscAr=1e-3, diffKhT=1e3, diffKrT=1e-5, deltaT=600.0,
+                     sfU=tile_field(d, z["windx"]) * (1.0 / rhoConst),          # external_forcing_surf.F:214
+                     phi0surf=np.zeros(d.shape2))
+
+
+def step_loop(d, g, P, nSteps, engine, *, tRef, salt0, rhoConst, tAlpha, gravity, abEps, viscAr, diffKhT, diffKrT, deltaT,
+              sfU, phi0surf):
+    """The hydrostatic step of a linear-EOS box started from rest with theta = tRef(k) (no exactConserv, explicit
+    diffusion, AB2 on the tendencies); shared with oracle/inverted_barometer.py."""
+    NR = d.Nr
     o = Oracle(g, P)
     e = engine or o
     op = o.ini_cg2d()
@@ -50,22 +62,19 @@ def run(nSteps=18, engine=None):
         engine.setup(g, o.params, op)
     if engine is not None and getattr(engine, "fb", 0) is None:
         engine.fb = o
-    rhoConst = rhoNil = 999.8
-    gravity = 9.81
+    rhoNil = rhoConst
     recip_rhoConst = 1.0 / rhoConst
-    eos = Eos(rhoNil, rhoConst, 2e-4, 0.0)
-    tRef, sRef = np.array(TREF), np.full(NR, 35.0)
-    abEps, viscAr, diffKhT, diffKrT = 0.1, 1e-3, 1e3, 1e-5
-    dT = np.full(NR, 600.0)
+    eos = Eos(rhoNil, rhoConst, tAlpha, 0.0)
+    tRef, sRef = np.array(tRef), np.full(NR, salt0)
+    dT = np.full(NR, deltaT)
     zr = np.zeros(NR)
     ns = (d.PY, d.PX)
     tiles = [(bi, bj) for bj in range(1, d.nSy + 1) for bi in range(1, d.nSx + 1)]
-    sfU = tile_field(d, z["windx"]) * recip_rhoConst            # external_forcing_surf.F:214
-    sfV, sfT, phi0surf = (np.zeros(d.shape2) for _ in range(3))
+    sfV, sfT = (np.zeros(d.shape2) for _ in range(2))
     z3 = lambda: np.zeros(d.shape3)
     uVel, vVel, wVel, gU, gV, guNm1, gvNm1, gtNm1, rhoInSitu, ivdc = (z3() for _ in range(10))
     theta = np.where(g.maskC != 0.0, tRef[None, None, :, None, None], 0.0)      # ini_theta.F
-    salt = np.where(g.maskC != 0.0, 35.0, 0.0)
+    salt = np.where(g.maskC != 0.0, salt0, 0.0)
     etaN = np.zeros(d.shape2)
     kapU = np.full((NR + 1,) + ns, viscAr)
     kbl, dkr = np.zeros(NR), np.full(NR, diffKrT)

@@ -77,6 +77,16 @@ def advection_in_gyre_fixture():
     print("wrote advection_in_gyre.npz")
 
 
+def inverted_barometer_fixture():
+    """inverted_barometer: the closed basin and the atmospheric pressure load, 60 x 60 float64."""
+    import numpy as np
+    ib = os.path.join(REF, "inverted_barometer/input")
+    np.savez_compressed(os.path.join(HERE, "inverted_barometer.npz"),
+                        topog=np.fromfile(os.path.join(ib, "topog.box"), ">f8").reshape(60, 60).astype(np.float64),
+                        pLoad=np.fromfile(os.path.join(ib, "pLoad.bin"), ">f8").reshape(60, 60).astype(np.float64))
+    print("wrote inverted_barometer.npz")
+
+
 def flt_example_fixture():
     """flt_example: the bump topography (partial cells with hFacMin = 0.2) and the zonal wind stress, 42 x 80 float64."""
     import numpy as np
@@ -94,6 +104,7 @@ if __name__ == "__main__":
     deep_convection_fixture()
     advection_in_gyre_fixture()
     flt_example_fixture()
+    inverted_barometer_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

@@ -524,3 +524,51 @@ def test_flt_example_monitor_every_digit(run_fe, fld, st):
     assert float(fmt(first[fld][st], 13)) == float(gold[0]), "start state"
     for i, r in enumerate(out):
         assert fmt(r[fld][st], 13) == gold[i + 1], (fld, st, i)      # incl. the eta / wvel means, which are round-off (1e-17, 1e-22)
+
+
+# verification/inverted_barometer: a closed stratified f-plane box under an atmospheric pressure load (phi0surf = pLoad /
+# rhoConst added to the hydrostatic potential), no-slip bottom at Nr = 4, free-slip walls (oracle/inverted_barometer.py).
+# The golden output was written by checkpoint62c (2010), before the bottom-drag routines were re-arranged: as for
+# adjustment.128x64x1 the agreement is the reference's own pass rule (matching digits), not every printed digit.
+GOLD_IB = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "inverted_barometer.json")))
+
+
+@pytest.fixture(scope="module")
+def run_ib():
+    from oracle import inverted_barometer as ib
+    return ib.run(40)
+
+
+def _digits(a, b):
+    return 99.0 if a == b else -np.log10(abs(a - b) / (0.5 * (abs(a) + abs(b))))
+
+
+def test_inverted_barometer_solver_lines(run_ib):
+    norm, _, out = run_ib
+    assert fmt(norm, 16) == GOLD_IB["cg2dNorm"]
+    assert [r["numIters"] for r in out] == GOLD_IB["cg2d_iters"]              # 40 solves to 1e-13: 35 36 35 35 34 ...
+    assert fmt(out[0]["firstResidual"], 14) == GOLD_IB["cg2d_init_res"][0]   # the first step: every printed digit
+    assert fmt(out[0]["lastResidual"], 14) == GOLD_IB["cg2d_last_res"][0]
+    for r, ir, (_, rm) in zip(out, GOLD_IB["cg2d_init_res"], GOLD_IB["sumRHS_rhsMax"]):
+        assert _digits(r["firstResidual"], float(ir)) >= 13.5
+        assert _digits(r["rhsMax"], float(rm)) >= 13.5
+
+
+@pytest.mark.parametrize("fld", ["eta", "uvel", "vvel", "wvel", "theta"])
+@pytest.mark.parametrize("st", ["max", "min", "sd"])
+def test_inverted_barometer_monitor(run_ib, fld, st):
+    _, first, out = run_ib
+    gold = GOLD_IB[f"dynstat_{fld}_{st}"]
+    assert len(gold) == 41
+    assert fmt(out[0][fld][st], 13) == gold[1]                                # the first step: every printed digit
+    for i, r in enumerate(out):
+        assert _digits(r[fld][st], float(gold[i + 1])) >= 12.5, (fld, st, i)
+
+
+def test_inverted_barometer_adjusts_towards_the_load(run_ib):
+    """what the experiment is about: the sea surface moves towards -pLoad / (rhoConst g)"""
+    from oracle import inverted_barometer as ib
+    z, d, g, P = ib.setup()
+    target = np.abs(z["pLoad"]).max() / (999.8 * 9.81)
+    _, _, out = run_ib
+    assert out[0]["eta"]["max"] < out[10]["eta"]["max"] < 1.3 * target and out[-1]["eta"]["max"] > 0.5 * target
