@@ -114,3 +114,53 @@ def test_tile_proc_and_rank_tiles():
     assert gl.d.nSx == 2 and gl.d.nPx == 3 and gl.d.myPx == 1 and gl.a["rA"].shape == gl.d.shape2
     assert np.array_equal(gl.a["rA"], g.a["rA"][:, 2:4]) and np.array_equal(sl["theta"], st["theta"][:, 2:4])
     assert sl["cg2dNorm"] == 3.0 and np.array_equal(gl.a["drF"], g.a["drF"])
+
+
+def test_gloo_world2_tile_graph_exchange_and_cg2d_sums():
+    """Two real processes (gloo): each holds half of the cube's tiles, fetches the cells its gather list names from
+    the owner (all_gather stands in for the NVLink read of the peer arena), and must end with exactly what the literal
+    exch2 exchange gives its tiles; the CG2D dot product over the distributed tiles is added in rank order."""
+    import torch.multiprocessing as mp
+    mp.spawn(_gloo_tile_graph_worker, args=(2,), nprocs=2, join=True)
+
+
+def _gloo_tile_graph_worker(rank, world):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29519")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mitgcm_b200.parallel import ordered_global_sum
+    nf, sx, sy, OL, nz = 8, 4, 4, 2, 2
+    T = cubed_sphere_topology(nf, sx, sy)
+    n = T.nTiles // world
+    rng = np.random.default_rng(11)                      # the same global field in both processes
+    a = rng.standard_normal((T.nTiles, nz, sy + 2 * OL, sx + 2 * OL))
+    mine = a[rank * n:(rank + 1) * n].copy()
+    t = torch.from_numpy(mine.transpose(1, 0, 2, 3).reshape(nz, -1).copy())
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)                            # what the peers hold (pre-exchange values)
+    sc, _, _ = dist_lists(T, OL, world, rank)
+    new = t.clone()
+    dst, src, own = sc[:, 0].astype(np.int64), (sc[:, 1] & MASK).astype(np.int64), (sc[:, 1] >> 28) & 7
+    for o in range(world):
+        m = own == o
+        new[:, dst[m]] = parts[o][:, src[m]]
+    eo.exch2_3d(T, a, OL)
+    got = new.numpy().reshape(nz, n, sy + 2 * OL, sx + 2 * OL).transpose(1, 0, 2, 3)
+    assert np.array_equal(got, a[rank * n:(rank + 1) * n])
+    # GLOBAL_SUM_TILE_RL over the distributed tiles: tile sums in tile order inside a rank, ranks in rank order
+    tile_sums = [float(np.sum(got[l, :, OL:OL + sy, OL:OL + sx] ** 2)) for l in range(n)]
+    part = 0.0
+    for v in tile_sums:
+        part = part + v
+    tot = ordered_global_sum(torch.tensor([part], dtype=torch.float64))
+    ref = 0.0
+    for r in range(world):
+        p = 0.0
+        for l in range(n):
+            p = p + float(np.sum(a[r * n + l, :, OL:OL + sy, OL:OL + sx] ** 2))
+        ref = ref + p
+    assert tot.item() == ref
+    dist.destroy_process_group()
