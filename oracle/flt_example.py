@@ -40,18 +40,18 @@ def setup():
     return z, d, g, P
 
 
-def run(nSteps=18, engine=None):
-    """Returns (cg2dNorm, statistics of the start state, [per-step dict])."""
+def run(nSteps=18, engine=None, sr=False):
+    """Returns (cg2dNorm, statistics of the start state, [per-step dict]).  sr: CG2D_SR instead of CG2D (useSRCGSolver)."""
     z, d, g, P = setup()
     rhoConst = 999.8
     return step_loop(d, g, P, nSteps, engine, tRef=TREF, salt0=35.0, rhoConst=rhoConst, tAlpha=2e-4, gravity=9.81, abEps=0.1,
                      viscAr=1e-3, diffKhT=1e3, diffKrT=1e-5, deltaT=600.0,
                      sfU=tile_field(d, z["windx"]) * (1.0 / rhoConst),          # external_forcing_surf.F:214
-                     phi0surf=np.zeros(d.shape2))
+                     phi0surf=np.zeros(d.shape2), sr=sr)
 
 
 def step_loop(d, g, P, nSteps, engine, *, tRef, salt0, rhoConst, tAlpha, gravity, abEps, viscAr, diffKhT, diffKrT, deltaT,
-              sfU, phi0surf):
+              sfU, phi0surf, sr=False):
     """The hydrostatic step of a linear-EOS box started from rest with theta = tRef(k) (no exactConserv, explicit
     diffusion, AB2 on the tendencies); shared with oracle/inverted_barometer.py."""
     NR = d.Nr
@@ -134,7 +134,7 @@ def step_loop(d, g, P, nSteps, engine, *, tRef, salt0, rhoConst, tAlpha, gravity
         b, x = np.zeros(d.shape2), np.zeros(d.shape2)
         for bi, bj in tiles:
             o.solve_rhs(bi, bj, etaN, gU, gV, b, x)
-        res = e.cg2d(op, b, x, 1000, -1)
+        res = e.cg2d(op, b, x, 1000, -1, sr=sr)
         o.exch_xyz(x)
         etaN = g.recip_Bo * x
         for bi, bj in tiles:

@@ -572,3 +572,19 @@ def test_inverted_barometer_adjusts_towards_the_load(run_ib):
     target = np.abs(z["pLoad"]).max() / (999.8 * 9.81)
     _, _, out = run_ib
     assert out[0]["eta"]["max"] < out[10]["eta"]["max"] < 1.3 * target and out[-1]["eta"]["max"] > 0.5 * target
+
+
+def test_cg2d_sr_in_place_of_cg2d_meets_the_flt_example_golden():
+    """CG2D_SR has no golden of its own (the one experiment that sets useSRCGSolver needs sea ice and GM/Redi).  Held to a
+    reference output anyway: with the single-reduction solver in place of CG2D the flt_example run must pass the reference's
+    own rule against results/output.with_flt.txt -- here: the same iteration count in all 18 solves (about 130 each) and
+    >= 13 of the 14 printed digits of cg2d_init_res and of every max / min / sd."""
+    from oracle import flt_example as fe
+    _, _, out = fe.run(18, sr=True)
+    assert [r["numIters"] for r in out] == GOLD_FE["cg2d_iters"]
+    for i, r in enumerate(out):
+        if float(GOLD_FE["cg2d_init_res"][i]) != 0.0:
+            assert _digits(r["firstResidual"], float(GOLD_FE["cg2d_init_res"][i])) >= 13.0, i
+        for fld in ("eta", "uvel", "vvel", "wvel", "theta"):
+            for st in ("max", "min", "sd"):
+                assert _digits(r[fld][st], float(GOLD_FE[f"dynstat_{fld}_{st}"][i + 1])) >= 13.0, (i, fld, st)
