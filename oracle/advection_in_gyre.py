@@ -24,18 +24,23 @@ from mitgcm_b200.grid import Dims, cartesian_grid, masks_from_depth, global_area
 from .barotropic_gyre import mon_stats, tile_field
 from .pyoracle import Oracle
 
-FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "inputs",
-                       "advection_in_gyre.npz")
-NX = NY = 60
+INPUTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "inputs")
+FIXTURE = os.path.join(INPUTS, "advection_in_gyre.npz")
+# tutorial_advection_in_gyre; oracle/matrix_example.py runs the same sequence with its own numbers
+CONFIG = dict(fixture=FIXTURE, n=60, dx=20e3, tiles=(2, 2), OL=4, ygOrigin=0.0, deltaT=1200.0, viscAh=400.0, viscAr=1e-2,
+              abEps=0.1, rhoConst=999.8, tol=1e-10)
 
 
-def setup():
-    z = np.load(FIXTURE)
-    d = Dims(sNx=30, sNy=30, OLx=4, OLy=4, nSx=2, nSy=2, Nr=1)
-    g = cartesian_grid(d, [20e3] * NX, [20e3] * NY, [5000.0], f0=1e-4, beta=1e-11, gBaro=9.81)
+def setup(cfg=CONFIG):
+    z = np.load(cfg["fixture"])
+    n, (nSx, nSy) = cfg["n"], cfg["tiles"]
+    d = Dims(sNx=n // nSx, sNy=n // nSy, OLx=cfg["OL"], OLy=cfg["OL"], nSx=nSx, nSy=nSy, Nr=1)
+    g = cartesian_grid(d, [cfg["dx"]] * n, [cfg["dx"]] * n, [5000.0], ygOrigin=cfg["ygOrigin"], f0=1e-4, beta=1e-11,
+                       gBaro=9.81)
     masks_from_depth(g, z["topog"], hFacMin=1.0, hFacMinDr=0.0)
-    P = dict(deltaTMom=1200.0, deltaTFreeSurf=1200.0, viscAhD=400.0, viscAhZ=400.0, no_slip_sides=1, sideDragFactor=2.0,
-             no_slip_bottom=1, selectBotDragQuadr=-1, cg2dTargetResidual=1e-10, globalArea=global_area(g))
+    P = dict(deltaTMom=cfg["deltaT"], deltaTFreeSurf=cfg["deltaT"], viscAhD=cfg["viscAh"], viscAhZ=cfg["viscAh"],
+             no_slip_sides=1, sideDragFactor=2.0, no_slip_bottom=1, selectBotDragQuadr=-1,
+             cg2dTargetResidual=cfg["tol"], globalArea=global_area(g))
     return z, d, g, P
 
 
@@ -47,10 +52,10 @@ def stats(d, g, etaN, uVel, vVel, wVel):
                 wvel=mon_stats(d, wVel, g.maskC, maskInC, g.rA, g.drC[:1]))
 
 
-def run(nSteps=4, engine=None):
+def run(nSteps=4, engine=None, cfg=CONFIG):
     """Returns (cg2dNorm, statistics of the pickup state, [per-step dict]).  `engine` as in baroclinic_gyre.py
     (mom_fluxform / cg2d from the CUDA library; it must not be used to claim oracle parity)."""
-    z, d, g, P = setup()
+    z, d, g, P = setup(cfg)
     o = Oracle(g, P)
     e = engine or o
     op = o.ini_cg2d()
@@ -58,7 +63,7 @@ def run(nSteps=4, engine=None):
         engine.setup(g, o.params, op)
     if engine is not None and getattr(engine, "fb", 0) is None:
         engine.fb = o                                # routines the engine does not replace stay on this oracle
-    viscAr, abEps, rhoConst = 1e-2, 0.1, 999.8
+    viscAr, abEps, rhoConst = cfg["viscAr"], cfg["abEps"], cfg["rhoConst"]
     t3 = lambda a: tile_field(d, a)[:, :, None].copy()
     uVel, vVel = t3(z["Uvel"]), t3(z["Vvel"])
     guNm1, gvNm1 = t3(z["GuNm1"]), t3(z["GvNm1"])

@@ -41,7 +41,7 @@ def parse(exp, out="results/output.txt"):
 if __name__ == "__main__":
     for exp in ("tutorial_barotropic_gyre", "tutorial_baroclinic_gyre", "global_ocean.90x40x15",
                 "global_ocean.cs32x15", "adjustment.cs-32x32x1", "advect_xy", "solid-body.cs-32x32x1", "advect_cs", "adjustment.128x64x1",
-                "tutorial_deep_convection", "tutorial_advection_in_gyre", "inverted_barometer"):
+                "tutorial_deep_convection", "tutorial_advection_in_gyre", "inverted_barometer", "matrix_example"):
         with open(os.path.join(HERE, exp + ".json"), "w") as f:
             json.dump(parse(exp), f, indent=1)
         print("wrote", exp)

@@ -87,6 +87,20 @@ def inverted_barometer_fixture():
     print("wrote inverted_barometer.npz")
 
 
+def matrix_example_fixture():
+    """matrix_example: pickup.0000200000.data (no field list: the older record order Uvel GuNm1 Vvel GvNm1 Theta GtNm1
+    Salt GsNm1 EtaN dEtaHdt EtaH, 32 x 32 float64), basin and wind stress (float32 files: readBinaryPrec = 32)."""
+    import numpy as np
+    me = os.path.join(REF, "matrix_example/input")
+    pk = np.fromfile(os.path.join(me, "pickup.0000200000.data"), ">f8").reshape(11, 32, 32).astype(np.float64)
+    names = "Uvel GuNm1 Vvel GvNm1 Theta GtNm1 Salt GsNm1 EtaN dEtaHdt EtaH".split()
+    out = {n: pk[q] for q, n in enumerate(names) if n in ("Uvel", "Vvel", "Theta", "GuNm1", "GvNm1", "GtNm1", "EtaN")}
+    out["topog"] = np.fromfile(os.path.join(me, "topo_box.bin"), ">f4").reshape(32, 32).astype(np.float64)
+    out["windx"] = np.fromfile(os.path.join(me, "taux_cosY.bin"), ">f4").reshape(32, 32).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "matrix_example.npz"), **out)
+    print("wrote matrix_example.npz")
+
+
 def flt_example_fixture():
     """flt_example: the bump topography (partial cells with hFacMin = 0.2) and the zonal wind stress, 42 x 80 float64."""
     import numpy as np
@@ -105,6 +119,7 @@ if __name__ == "__main__":
     advection_in_gyre_fixture()
     flt_example_fixture()
     inverted_barometer_fixture()
+    matrix_example_fixture()
     for dst, src in FILES.items():
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

@@ -588,3 +588,25 @@ def test_cg2d_sr_in_place_of_cg2d_meets_the_flt_example_golden():
         for fld in ("eta", "uvel", "vvel", "wvel", "theta"):
             for st in ("max", "min", "sd"):
                 assert _digits(r[fld][st], float(GOLD_FE[f"dynstat_{fld}_{st}"][i + 1])) >= 13.0, (i, fld, st)
+
+
+# verification/matrix_example: another barotropic gyre restarted from a pickup (32 x 32 cells of 50 km, 2 x 4 tiles of
+# 16 x 8, OL = 3, deltaT = 20000 s, rhoConst = 1035): the sequence of oracle/advection_in_gyre.py with other numbers
+GOLD_MX = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "matrix_example.json")))
+
+
+def test_matrix_example_every_digit():
+    from oracle import matrix_example as mx
+    norm, first, out = mx.run(10)
+    assert fmt(norm, 16) == GOLD_MX["cg2dNorm"]
+    assert [r["numIters"] for r in out] == GOLD_MX["cg2d_iters"]
+    for i, r in enumerate(out):
+        assert fmt(r["firstResidual"], 14) == GOLD_MX["cg2d_init_res"][i]
+        assert fmt(r["lastResidual"], 14) == GOLD_MX["cg2d_last_res"][i]
+        assert (fmt(r["sumRHS"], 14), fmt(r["rhsMax"], 14)) == tuple(GOLD_MX["sumRHS_rhsMax"][i])
+    for fld in ("eta", "uvel", "vvel", "wvel"):
+        for st in ("max", "min", "mean", "sd"):
+            gold = GOLD_MX[f"dynstat_{fld}_{st}"]
+            assert fmt(first[fld][st], 13) == gold[0], (fld, st)
+            for i, r in enumerate(out):
+                assert fmt(r[fld][st], 13) == gold[i + 1], (fld, st, i)
