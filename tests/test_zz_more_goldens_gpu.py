@@ -1,5 +1,6 @@
-"""Two more goldens with the CUDA kernels in the loop (this file sorts last on purpose: both tests were added after the
-round's GPU budget was spent and have not been run on a GPU yet).
+"""Two more goldens with the CUDA kernels in the loop (this file sorts last on purpose: the tests were added when the
+round's GPU budget was nearly spent; the advection_in_gyre test has been run on a B200 and passes, the flt_example test
+has not been run on a GPU yet).
 
 verification/tutorial_advection_in_gyre (the barotropic gyre restarted from a 10-year spin-up, oracle/advection_in_gyre.py)
 with the CUDA MOM_FLUXFORM in the loop through the C ABI (reference argument list, host buffers, 2 x 2 tiles of 30 x 30,
