@@ -66,4 +66,7 @@ def test_cuda_tendencies_on_partial_cells_reproduce_the_flt_example_golden(rt):
         for f in ("eta", "uvel", "vvel", "wvel", "theta"):
             for st in ("max", "min", "sd"):
                 ref = float(GOLD_FE[f"dynstat_{f}_{st}"][i + 1])
-                assert digits(r[f][st], ref) >= 13.0 or abs(r[f][st] - ref) < 1e-300, (i, f, st)
+                if abs(ref) < 1e-15:      # round-off of a field that is still zero (w after the first step: 3e-19)
+                    assert abs(r[f][st]) < 1e-15, (i, f, st)
+                    continue
+                assert digits(r[f][st], ref) >= 13.0, (i, f, st)
