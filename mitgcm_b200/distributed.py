@@ -37,6 +37,7 @@ def setup(d: Dims, transport: str | None = None):
     # one tile per rank on the periodic process grid, or several tiles of an exch2 tile graph (exch2.set_topology with tileProc)
     transport = transport or os.environ.get("MITGCM_B200_TRANSPORT", "peer")
     assert transport in ("peer", "nccl")
+    assert transport == "peer" or (d.nSx == 1 and d.nSy == 1), "the NCCL strip exchange handles one tile per rank"
     h = (C.c_ubyte * 72)()
     ierr = C.c_int(0)
     L.mitgcm_b200_comm_handle_(h, C.byref(ierr))
